@@ -1,0 +1,71 @@
+/*
+ * sperr_b200 -- C ABI of the B200-native SPERR hot path (libsperr_b200.so).
+ *
+ * Section 1 are drop-in replacements of the reference's C API: same names, argument meaning,
+ * ownership rules and return codes as /root/reference/include/SPERR_C_API.h:53-156, so a program
+ * (or an FFI binding: H5Z-SPERR, the Fortran wrapper, ctypes) links against this library instead
+ * of libSPERR without source changes. Buffers are HOST memory unless a name ends in _dev.
+ *
+ * Section 2 are additive GPU-side entry points (device-resident data, chunk-range sharding for
+ * one-process-per-GPU jobs); section 3 are stage-level hooks used by the parity tests.
+ *
+ * All functions are synchronous and thread-compatible (one call at a time per process is the
+ * tested configuration). The library has no CPU execution path: without a CUDA device every
+ * compute entry point returns -1.
+ */
+#ifndef SPERR_B200_H
+#define SPERR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* 1. Reference-compatible API                                                                 */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Replaces C_API::sperr_comp_3d (SPERR_C_API.h:84-111, src/SPERR_C_API.cpp:156-216).
+ * mode: 1 = fixed bit-per-pixel, 2 = fixed PSNR, 3 = fixed point-wise error.
+ * `nthreads` is accepted for signature compatibility and ignored (the chunk loop runs on the GPU).
+ * Returns 0 ok; 1 *dst not NULL; 2 bad parameter; -1 other error. *dst is malloc'd. */
+int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_t dimz,
+                  size_t chunk_x, size_t chunk_y, size_t chunk_z, int mode, double quality,
+                  size_t nthreads, void** dst, size_t* dst_len);
+
+/* Replaces C_API::sperr_decomp_3d (SPERR_C_API.h:113-131, src/SPERR_C_API.cpp:218-258). */
+int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nthreads, size_t* dimx,
+                    size_t* dimy, size_t* dimz, void** dst);
+
+/* Replaces C_API::sperr_parse_header (SPERR_C_API.h:74-82, src/SPERR_C_API.cpp:136-154). */
+void sperr_parse_header(const void* src, size_t* dimx, size_t* dimy, size_t* dimz, int* is_float);
+
+/* ------------------------------------------------------------------------------------------ */
+/* 2. GPU-side extensions                                                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Same as sperr_comp_3d but `src` is a DEVICE pointer to the whole volume and the output container
+ * is written to a malloc'd HOST buffer. */
+int sperr_b200_comp_3d_dev(const void* d_src, int is_float, size_t dimx, size_t dimy, size_t dimz,
+                           size_t chunk_x, size_t chunk_y, size_t chunk_z, int mode, double quality,
+                           void** dst, size_t* dst_len);
+
+/* ------------------------------------------------------------------------------------------ */
+/* 3. Stage-level hooks (parity tests)                                                         */
+/* ------------------------------------------------------------------------------------------ */
+
+int sperr_b200_stage_condition(const void* src, int is_float, size_t nx, size_t ny, size_t nz,
+                               double* out_vals, double* out_mean, int* out_is_const);
+int sperr_b200_stage_dwt(double* buf, size_t nx, size_t ny, size_t nz, int inverse, int is_2d);
+int sperr_b200_stage_quantize(const double* vals, size_t nx, size_t ny, size_t nz, double q,
+                              uint64_t* mags, uint8_t* signs, int* wide);
+int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, size_t nx, size_t ny,
+                                    size_t nz, size_t budget_bits, uint8_t* out, size_t cap,
+                                    size_t* out_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

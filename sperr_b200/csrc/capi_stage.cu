@@ -1,0 +1,181 @@
+// Stage-level C entry points (host buffers in, host buffers out). They exist so that the parity
+// tests can pin each kernel family against the oracle separately; they run the same kernels as
+// the full pipeline. Declared in include/sperr_b200.h.
+#include "../../include/sperr_b200.h"
+
+#include "batch.h"
+#include "speck3d.h"
+
+using namespace sperr_b200;
+
+namespace {
+
+template <typename F>
+int guarded(F&& f)
+{
+  try {
+    return f();
+  }
+  catch (const std::exception& e) {
+    if (std::getenv("SPERR_B200_VERBOSE"))
+      std::fprintf(stderr, "sperr_b200: %s\n", e.what());
+    return -1;
+  }
+}
+
+Chunk whole(size_t nx, size_t ny, size_t nz)
+{
+  Chunk c;
+  c.x0 = c.y0 = c.z0 = 0;
+  c.lx = uint32_t(nx); c.ly = uint32_t(ny); c.lz = uint32_t(nz);
+  return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sperr_b200_stage_condition(const void* src, int is_float, size_t nx, size_t ny, size_t nz,
+                               double* out_vals, double* out_mean, int* out_is_const)
+{
+  return guarded([&] {
+    cudaStream_t st = 0;
+    BatchBuffers b;
+    b.setup({whole(nx, ny, nz)}, true, false, false, st);
+    const size_t n = nx * ny * nz;
+    rt::DBuf d_src(n * (is_float ? 4 : 8));
+    rt::h2d(d_src.p, src, d_src.bytes, st);
+    SrcVol sv{d_src.p, is_float, nx, ny};
+    const unsigned ns = unsigned(mean_num_strides(n));
+    rt::DBuf d_sm(ns * 8), d_ns(4), d_nc(4);
+    rt::h2d(d_ns.p, &ns, 4, st);
+    rt::dset(d_nc.p, 0, 4, st);
+    launch_stats(sv, b.dev(), 1, d_sm.as<double>(), int(ns), d_ns.as<unsigned>(), d_nc.as<unsigned>(),
+                 false, st);
+    launch_gather(sv, b.dev(), 1, n, st);
+    b.pull(st);
+    *out_mean = b.h[0].mean;
+    *out_is_const = b.h[0].is_const;
+    if (!b.h[0].is_const)
+      rt::d2h(out_vals, b.h[0].coef, n * 8, st);
+    rt::sync(st);
+    return 0;
+  });
+}
+
+int sperr_b200_stage_dwt(double* buf, size_t nx, size_t ny, size_t nz, int inverse, int is_2d)
+{
+  return guarded([&] {
+    cudaStream_t st = 0;
+    BatchBuffers b;
+    b.setup({whole(nx, ny, nz)}, true, false, false, st);
+    const size_t n = nx * ny * nz;
+    rt::h2d(b.h[0].coef, buf, n * 8, st);
+    rt::DBuf ids(4);
+    const int zero = 0;
+    rt::h2d(ids.p, &zero, 4, st);
+    launch_dwt(inverse != 0, b.dev(), ids.as<int>(), 1, uint32_t(nx), uint32_t(ny), uint32_t(nz),
+               is_2d != 0, st);
+    rt::d2h(buf, b.h[0].coef, n * 8, st);
+    rt::sync(st);
+    return 0;
+  });
+}
+
+int sperr_b200_stage_quantize(const double* vals, size_t nx, size_t ny, size_t nz, double q,
+                              uint64_t* mags, uint8_t* signs, int* wide)
+{
+  return guarded([&] {
+    cudaStream_t st = 0;
+    const size_t n = nx * ny * nz;
+    BatchBuffers b;
+    b.setup({whole(nx, ny, nz)}, true, true, false, st);
+    rt::h2d(b.h[0].coef, vals, n * 8, st);
+    b.h[0].q = q;
+    b.push(st);
+    launch_absmax(b.dev(), 1, n, st);
+    launch_qdecide(b.dev(), 1, st);
+    b.pull(st);
+    if (b.h[0].fe_invalid)
+      return -1;
+    if (b.h[0].wide) {
+      b.make_wide(st);
+      b.push(st);
+    }
+    launch_quantize(b.dev(), 1, n, st);
+    std::vector<uint32_t> sw((n + 31) / 32);
+    rt::d2h(sw.data(), b.h[0].signs, sw.size() * 4, st);
+    if (b.h[0].wide)
+      rt::d2h(mags, b.h[0].mag, n * 8, st);
+    else {
+      std::vector<uint32_t> m(n);
+      rt::d2h(m.data(), b.h[0].mag, n * 4, st);
+      rt::sync(st);
+      for (size_t i = 0; i < n; i++)
+        mags[i] = m[i];
+    }
+    rt::sync(st);
+    for (size_t i = 0; i < n; i++)
+      signs[i] = (sw[i >> 5] >> (i & 31)) & 1u;
+    *wide = b.h[0].wide;
+    return 0;
+  });
+}
+
+int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, size_t nx, size_t ny,
+                                    size_t nz, size_t budget_bits, uint8_t* out, size_t cap,
+                                    size_t* out_len)
+{
+  return guarded([&] {
+    cudaStream_t st = 0;
+    const size_t n = nx * ny * nz;
+    bool wide = false;
+    for (size_t i = 0; i < n; i++)
+      if (mags[i] > 0xFFFFFFFFull)
+        wide = true;
+    BatchBuffers b;
+    b.setup({whole(nx, ny, nz)}, false, true, wide, st);
+    std::vector<uint32_t> sw((n + 31) / 32, 0);
+    std::vector<int8_t> pl(n);
+    for (size_t i = 0; i < n; i++) {
+      if (signs[i])
+        sw[i >> 5] |= 1u << (i & 31);
+      int p = -1;
+      for (uint64_t v = mags[i]; v; v >>= 1)
+        p++;
+      pl[i] = int8_t(p);
+    }
+    if (wide)
+      rt::h2d(b.h[0].mag, mags, n * 8, st);
+    else {
+      std::vector<uint32_t> m(n);
+      for (size_t i = 0; i < n; i++)
+        m[i] = uint32_t(mags[i]);
+      rt::h2d(b.h[0].mag, m.data(), n * 4, st);
+      rt::sync(st);
+    }
+    rt::h2d(b.h[0].signs, sw.data(), sw.size() * 4, st);
+    rt::h2d(b.h[0].pleaf, pl.data(), n, st);
+    if (budget_bits) {
+      while (budget_bits % 8)
+        budget_bits++;
+      b.h[0].budget = budget_bits;
+    }
+    b.push(st);
+    Speck3DEncoder enc;
+    std::vector<EncResult> res;
+    enc.encode(b.dev(), b.h, b.dev_shapes(), b.shapes, res, st);
+    const size_t len = 9 + res[0].payload_bytes;
+    *out_len = len;
+    if (len > cap)
+      return -2;
+    out[0] = uint8_t(res[0].planes);
+    const uint64_t tb = res[0].total_bits;
+    std::memcpy(out + 1, &tb, 8);
+    rt::d2h(out + 9, res[0].payload, res[0].payload_bytes, st);
+    rt::sync(st);
+    return 0;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,332 @@
+#include "geom.h"
+
+#include <algorithm>
+#include <stdexcept>
+
+namespace sperr_b200 {
+
+size_t num_of_xforms(size_t len)
+{
+  size_t n = 0;
+  while (len >= 9) {
+    n++;
+    len -= len / 2;
+  }
+  return std::min<size_t>(n, 6);
+}
+
+size_t num_of_partitions(size_t len)
+{
+  size_t n = 0;
+  while (len > 1) {
+    n++;
+    len -= len / 2;
+  }
+  return n;
+}
+
+int can_use_dyadic(size_t nx, size_t ny, size_t nz)
+{
+  if (nz < 2 || ny < 2)
+    return -1;
+  const size_t xy = num_of_xforms(std::min(nx, ny));
+  const size_t z = num_of_xforms(nz);
+  if (xy == z || (xy >= 5 && z >= 5))
+    return int(std::min(xy, z));
+  return -1;
+}
+
+std::array<size_t, 2> calc_approx_detail_len(size_t len, size_t lev)
+{
+  size_t low = len, high = 0;
+  for (size_t i = 0; i < lev; i++) {
+    high = low / 2;
+    low -= high;
+  }
+  return {low, high};
+}
+
+std::vector<Chunk> chunk_volume(const size_t vol[3], const size_t chunk[3])
+{
+  size_t nseg[3];
+  for (int a = 0; a < 3; a++) {
+    nseg[a] = vol[a] / chunk[a];
+    if (vol[a] % chunk[a] > chunk[a] / 2)
+      nseg[a]++;
+    if (nseg[a] == 0)
+      nseg[a] = 1;
+  }
+  auto seg = [&](int a, size_t i, uint32_t& beg, uint32_t& len) {
+    const size_t b = i * chunk[a];
+    const size_t e = (i + 1 == nseg[a]) ? vol[a] : (i + 1) * chunk[a];
+    beg = uint32_t(b);
+    len = uint32_t(e - b);
+  };
+  std::vector<Chunk> out;
+  out.reserve(nseg[0] * nseg[1] * nseg[2]);
+  for (size_t z = 0; z < nseg[2]; z++)
+    for (size_t y = 0; y < nseg[1]; y++)
+      for (size_t x = 0; x < nseg[0]; x++) {
+        Chunk c;
+        seg(0, x, c.x0, c.lx);
+        seg(1, y, c.y0, c.ly);
+        seg(2, z, c.z0, c.lz);
+        out.push_back(c);
+      }
+  return out;
+}
+
+size_t mean_num_strides(size_t len)
+{
+  size_t ns = 2048;
+  if (len % ns == 0)
+    return ns;
+  size_t num;
+  for (num = ns; num <= 32768; num++)
+    if (len % num == 0)
+      break;
+  if (len % num == 0)
+    return num;
+  for (num = ns; num > 0; num--)
+    if (len % num == 0)
+      break;
+  return num;
+}
+
+namespace {
+
+struct AxisBuild {
+  std::vector<std::vector<uint32_t>> bnd, child0;
+  std::vector<std::vector<uint8_t>> lev;
+  int D = 0;
+};
+
+AxisBuild build_axis(uint32_t L)
+{
+  AxisBuild a;
+  a.bnd.push_back({0, L});
+  a.lev.push_back({0});
+  for (;;) {
+    const auto& b = a.bnd.back();
+    const auto& lv = a.lev.back();
+    const size_t cnt = b.size() - 1;
+    bool all1 = true;
+    for (size_t k = 0; k < cnt; k++)
+      if (b[k + 1] - b[k] > 1)
+        all1 = false;
+    if (all1)
+      break;
+    std::vector<uint32_t> nb, c0;
+    std::vector<uint8_t> nl;
+    for (size_t k = 0; k < cnt; k++) {
+      const uint32_t len = b[k + 1] - b[k];
+      c0.push_back(uint32_t(nb.size()));
+      nb.push_back(b[k]);
+      nl.push_back(uint8_t(lv[k] + (len > 1 ? 1 : 0)));
+      if (len > 1) {
+        nb.push_back(b[k] + (len - len / 2));
+        nl.push_back(uint8_t(lv[k] + 1));
+      }
+    }
+    c0.push_back(uint32_t(nb.size()));
+    nb.push_back(L);
+    a.child0.push_back(c0);
+    a.bnd.push_back(nb);
+    a.lev.push_back(nl);
+  }
+  a.D = int(a.bnd.size()) - 1;
+  // identity child table for the deepest depth (clamped lookups)
+  std::vector<uint32_t> idc(a.bnd.back().size());
+  for (size_t k = 0; k < idc.size(); k++)
+    idc[k] = uint32_t(k);
+  a.child0.push_back(idc);
+  return a;
+}
+
+}  // namespace
+
+ShapeTables build_shape(uint32_t nx, uint32_t ny, uint32_t nz)
+{
+  ShapeTables t;
+  ShapeHeader& h = t.h;
+  h = ShapeHeader();
+  h.nx = nx; h.ny = ny; h.nz = nz;
+  const uint32_t dims[3] = {nx, ny, nz};
+  AxisBuild ab[3];
+  for (int a = 0; a < 3; a++) {
+    ab[a] = build_axis(dims[a]);
+    if (ab[a].D > kMaxAxisDepth - 1)
+      throw std::runtime_error("chunk dimension too large");
+    h.ax[a].D = ab[a].D;
+    h.tab_off[a] = t.bnd.size();
+    for (int d = 0; d <= ab[a].D; d++) {
+      h.ax[a].cnt[d] = int(ab[a].bnd[d].size()) - 1;
+      h.ax[a].off[d] = int(t.bnd.size() - h.tab_off[a]);
+      for (size_t k = 0; k < ab[a].bnd[d].size(); k++) {
+        t.bnd.push_back(ab[a].bnd[d][k]);
+        t.child0.push_back(ab[a].child0[d][k]);
+        t.lev.push_back(k < ab[a].lev[d].size() ? ab[a].lev[d][k] : 0);
+      }
+    }
+  }
+  const int D[3] = {h.ax[0].D, h.ax[1].D, h.ax[2].D};
+
+  // ---- chains of levels ----
+  h.nlevels = 0;
+  auto add_level = [&](int dx, int dy, int dz, int chain, int j) {
+    if (h.nlevels >= kMaxLevels)
+      throw std::runtime_error("too many pyramid levels");
+    LevelDesc& l = h.lv[h.nlevels];
+    l.dx = dx; l.dy = dy; l.dz = dz;
+    l.cx = h.ax[0].cnt[dx]; l.cy = h.ax[1].cnt[dy]; l.cz = h.ax[2].cnt[dz];
+    l.chain = chain; l.j = j; l.child = -1; l.p_off = 0;
+    return h.nlevels++;
+  };
+  h.leaf_level = add_level(D[0], D[1], D[2], -1, 0);
+  std::vector<std::array<int, 3>> chain_start;   // start triple of each chain
+  std::vector<int> chain_first_level;            // LevelDesc index of j = 0
+  auto add_chain = [&](int sx, int sy, int sz) {
+    const int c = int(chain_start.size());
+    chain_start.push_back({sx, sy, sz});
+    int first = -1, prev = -1;
+    for (int j = 0;; j++) {
+      const int dx = std::min(sx + j, D[0]), dy = std::min(sy + j, D[1]), dz = std::min(sz + j, D[2]);
+      if (dx == D[0] && dy == D[1] && dz == D[2]) {
+        if (prev >= 0)
+          h.lv[prev].child = h.leaf_level;
+        if (first < 0)
+          first = h.leaf_level;
+        break;
+      }
+      const int li = add_level(dx, dy, dz, c, j);
+      if (prev >= 0)
+        h.lv[prev].child = li;
+      if (first < 0)
+        first = li;
+      prev = li;
+    }
+    chain_first_level.push_back(first);
+    return c;
+  };
+  auto level_of = [&](int chain, int j) {
+    // levels of a chain are contiguous, the last one may be the shared leaf grid
+    int li = chain_first_level[chain];
+    for (int k = 0; k < j; k++)
+      li = h.lv[li].child;
+    return li;
+  };
+  add_chain(0, 0, 0);
+
+  // ---- initial LIS (m_initialize_lists) ----
+  h.dyadic = can_use_dyadic(nx, ny, nz);
+  size_t nxy, nzz;
+  if (h.dyadic >= 0)
+    nxy = nzz = size_t(h.dyadic);
+  else {
+    nxy = num_of_xforms(std::min(nx, ny));
+    nzz = num_of_xforms(nz);
+  }
+  h.nlis = int(num_of_partitions(nx) + num_of_partitions(ny) + num_of_partitions(nz) + 1);
+  std::vector<std::vector<RootDesc>> lists(h.nlis);
+  h.ngroups = 0;
+  int bchain = 0, bj = 0;           // where `big` lives
+  uint32_t blen[3] = {nx, ny, nz};  // extent of `big` (always anchored at the origin)
+  auto lis_of = [&](int level, int ix, int iy, int iz) {
+    const LevelDesc& l = h.lv[level];
+    return int(ab[0].lev[l.dx][ix]) + int(ab[1].lev[l.dy][iy]) + int(ab[2].lev[l.dz][iz]);
+  };
+  auto add_group = [&](int chain, int j, const uint32_t outer[3], const uint32_t inner[3]) {
+    if (h.ngroups >= kMaxGroups)
+      throw std::runtime_error("too many root groups");
+    GroupDesc& g = h.grp[h.ngroups++];
+    g.chain = chain; g.j_root = j;
+    g.ox = int(outer[0]); g.oy = int(outer[1]); g.oz = int(outer[2]);
+    g.ix = int(inner[0]); g.iy = int(inner[1]); g.iz = int(inner[2]);
+  };
+  size_t xf = 0;
+  auto split = [&](bool sx, bool sy, bool sz) {
+    // children of big = interval 0 on every axis; which axes advance is given by the flags
+    const int pl = level_of(bchain, bj);
+    const LevelDesc P = h.lv[pl];
+    int cchain, cj;
+    if (sx && sy && sz) {
+      cchain = bchain;
+      cj = bj + 1;
+    }
+    else {
+      cchain = add_chain(std::min(P.dx + (sx ? 1 : 0), D[0]), std::min(P.dy + (sy ? 1 : 0), D[1]),
+                         std::min(P.dz + (sz ? 1 : 0), D[2]));
+      cj = 0;
+    }
+    const int cl = level_of(cchain, cj);
+    const LevelDesc C = h.lv[cl];
+    // number of children per axis: 2 if that axis advanced and the interval really split
+    const int n0 = (C.dx != P.dx && blen[0] > 1) ? 2 : 1;
+    const int n1 = (C.dy != P.dy && blen[1] > 1) ? 2 : 1;
+    const int n2 = (C.dz != P.dz && blen[2] > 1) ? 2 : 1;
+    for (int cz = 0; cz < n2; cz++)
+      for (int cy = 0; cy < n1; cy++)
+        for (int cx = 0; cx < n0; cx++) {
+          if (cx == 0 && cy == 0 && cz == 0)
+            continue;
+          RootDesc r;
+          r.level = cl; r.ix = cx; r.iy = cy; r.iz = cz;
+          r.lis = lis_of(cl, cx, cy, cz);
+          r.order = 0;
+          lists[r.lis].push_back(r);
+        }
+    uint32_t inner[3] = {blen[0], blen[1], blen[2]};
+    if (n0 == 2) inner[0] = blen[0] - blen[0] / 2;
+    if (n1 == 2) inner[1] = blen[1] - blen[1] / 2;
+    if (n2 == 2) inner[2] = blen[2] - blen[2] / 2;
+    add_group(cchain, cj, blen, inner);
+    blen[0] = inner[0]; blen[1] = inner[1]; blen[2] = inner[2];
+    bchain = cchain;
+    bj = cj;
+  };
+  while (xf < nxy && xf < nzz) {
+    split(true, true, true);
+    xf++;
+  }
+  while (xf < nxy) {
+    split(true, true, false);
+    xf++;
+  }
+  while (xf < nzz) {
+    split(false, false, true);
+    xf++;
+  }
+  {
+    RootDesc r;
+    r.level = level_of(bchain, bj);
+    r.ix = r.iy = r.iz = 0;
+    r.lis = lis_of(r.level, 0, 0, 0);
+    r.order = 0;
+    lists[r.lis].insert(lists[r.lis].begin(), r);
+    const uint32_t none[3] = {0, 0, 0};
+    add_group(bchain, bj, blen, none);
+  }
+  h.nroots = 0;
+  for (int l = h.nlis - 1; l >= 0; l--)
+    for (size_t k = 0; k < lists[l].size(); k++) {
+      if (h.nroots >= kMaxRoots)
+        throw std::runtime_error("too many initial sets");
+      RootDesc r = lists[l][k];
+      r.order = int(k);
+      h.roots[h.nroots++] = r;
+    }
+
+  // ---- pyramid layout ----
+  unsigned long long off = 0;
+  for (int i = 0; i < h.nlevels; i++) {
+    if (i == h.leaf_level)
+      continue;
+    h.lv[i].p_off = off;
+    off += (unsigned long long)h.lv[i].cx * h.lv[i].cy * h.lv[i].cz;
+  }
+  h.pyr_nodes = off;
+  h.set_nodes = off;
+  return t;
+}
+
+}  // namespace sperr_b200

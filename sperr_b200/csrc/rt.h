@@ -1,0 +1,156 @@
+// Thin runtime layer: CUDA under nvcc; under -DSPERR_EMUL (tests/emul, test infrastructure only)
+// the same kernels are executed by a CPU SIMT emulator so their logic can be debugged in a
+// container without a GPU. The product library is always the nvcc build.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#ifdef SPERR_EMUL
+#include "cuda_emul.h"
+typedef int cudaStream_t;
+#define LAUNCH(kern, grid, block, smem, stream, ...) \
+  emu::launch(grid, block, smem, [=]() { kern(__VA_ARGS__); })
+#define DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem())
+#define HD
+#else
+#include <cuda_runtime.h>
+#define LAUNCH(kern, grid, block, smem, stream, ...)        \
+  do {                                                      \
+    kern<<<grid, block, smem, stream>>>(__VA_ARGS__);       \
+    rt::check(cudaGetLastError(), #kern, __FILE__, __LINE__); \
+  } while (0)
+#define DYN_SMEM(type, name)                                        \
+  extern __shared__ __align__(16) unsigned char name##_raw_smem[];  \
+  type* name = reinterpret_cast<type*>(name##_raw_smem)
+#define HD __host__ __device__
+#endif
+
+namespace rt {
+
+#ifndef SPERR_EMUL
+inline void check(cudaError_t e, const char* what, const char* file, int line)
+{
+  if (e != cudaSuccess) {
+    std::string msg = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what + " (" +
+                      file + ":" + std::to_string(line) + ")";
+    throw std::runtime_error(msg);
+  }
+}
+#define RT_CHECK(x) rt::check((x), #x, __FILE__, __LINE__)
+
+inline void* dmalloc(size_t n)
+{
+  void* p = nullptr;
+  RT_CHECK(cudaMalloc(&p, n ? n : 1));
+  return p;
+}
+inline void dfree(void* p)
+{
+  if (p)
+    cudaFree(p);
+}
+inline void h2d(void* d, const void* s, size_t n, cudaStream_t st)
+{
+  if (n)
+    RT_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st));
+}
+inline void d2h(void* d, const void* s, size_t n, cudaStream_t st)
+{
+  if (n)
+    RT_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st));
+}
+inline void d2d(void* d, const void* s, size_t n, cudaStream_t st)
+{
+  if (n)
+    RT_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, st));
+}
+inline void dset(void* d, int v, size_t n, cudaStream_t st)
+{
+  if (n)
+    RT_CHECK(cudaMemsetAsync(d, v, n, st));
+}
+inline void sync(cudaStream_t st) { RT_CHECK(cudaStreamSynchronize(st)); }
+inline void* hmalloc_pinned(size_t n)
+{
+  void* p = nullptr;
+  RT_CHECK(cudaMallocHost(&p, n ? n : 1));
+  return p;
+}
+inline void hfree_pinned(void* p)
+{
+  if (p)
+    cudaFreeHost(p);
+}
+inline bool is_device_ptr(const void* p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+#else
+inline void* dmalloc(size_t n) { return std::malloc(n ? n : 1); }
+inline void dfree(void* p) { std::free(p); }
+inline void h2d(void* d, const void* s, size_t n, cudaStream_t) { std::memcpy(d, s, n); }
+inline void d2h(void* d, const void* s, size_t n, cudaStream_t) { std::memcpy(d, s, n); }
+inline void d2d(void* d, const void* s, size_t n, cudaStream_t) { std::memmove(d, s, n); }
+inline void dset(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); }
+inline void sync(cudaStream_t) {}
+inline void* hmalloc_pinned(size_t n) { return std::malloc(n ? n : 1); }
+inline void hfree_pinned(void* p) { std::free(p); }
+inline bool is_device_ptr(const void*) { return false; }
+#endif
+
+// RAII device buffer
+struct DBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DBuf() = default;
+  explicit DBuf(size_t n) { alloc(n); }
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DBuf& operator=(DBuf&& o) noexcept
+  {
+    if (this != &o) {
+      release();
+      p = o.p; bytes = o.bytes;
+      o.p = nullptr; o.bytes = 0;
+    }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  void alloc(size_t n)
+  {
+    release();
+    p = dmalloc(n);
+    bytes = n;
+  }
+  // grow-only
+  void reserve(size_t n)
+  {
+    if (n > bytes)
+      alloc(n);
+  }
+  void release()
+  {
+    dfree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const
+  {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+}  // namespace rt
