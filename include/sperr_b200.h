@@ -65,6 +65,10 @@ int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, 
                                     size_t nz, size_t budget_bits, uint8_t* out, size_t cap,
                                     size_t* out_len);
 
+int sperr_b200_stage_outlier_encode(const uint64_t* pos, const double* err, size_t n_out,
+                                    size_t total_len, double tol, uint8_t* out, size_t cap,
+                                    size_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

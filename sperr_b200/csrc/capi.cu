@@ -1,0 +1,158 @@
+// Reference-compatible C API (include/sperr_b200.h section 1) and its device-pointer variants.
+// Host side of the container format: header build / parse are byte-exact restatements of
+//   SPERR3D_OMP_C::m_generate_header          /root/reference/src/SPERR3D_OMP_C.cpp:163-234
+//   SPERR3D_Stream_Tools::get_stream_header   /root/reference/src/SPERR3D_Stream_Tools.cpp:46-105
+//   C_API::sperr_comp_3d / sperr_decomp_3d    /root/reference/src/SPERR_C_API.cpp:156-258
+#include "../../include/sperr_b200.h"
+
+#include <mutex>
+
+#include "pipeline.h"
+
+using namespace sperr_b200;
+
+namespace {
+
+std::mutex g_mutex;  // one job at a time per process: the work buffers are shared
+Compressor* g_comp = nullptr;
+
+bool device_ok()
+{
+#ifndef SPERR_EMUL
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return false;
+  }
+#endif
+  return true;
+}
+
+template <typename F>
+int guarded(F&& f)
+{
+  try {
+    if (!device_ok())
+      throw std::runtime_error("no CUDA device: this library has no CPU path");
+    return f();
+  }
+  catch (const std::exception& e) {
+    if (std::getenv("SPERR_B200_VERBOSE"))
+      std::fprintf(stderr, "sperr_b200: %s\n", e.what());
+    return -1;
+  }
+}
+
+// Shared tail of sperr_comp_3d: `d_src` is the device-resident volume.
+int comp_3d_device(const void* d_src, int is_float, size_t dimx, size_t dimy, size_t dimz,
+                   size_t chunk_x, size_t chunk_y, size_t chunk_z, int mode, double quality,
+                   void** dst, size_t* dst_len, cudaStream_t st)
+{
+  const size_t vol[3] = {dimx, dimy, dimz};
+  size_t cd[3] = {chunk_x, chunk_y, chunk_z};
+  for (int i = 0; i < 3; i++)  // SPERR3D_OMP_C::set_dims_and_chunks, :22-29
+    cd[i] = std::min(std::max<size_t>(1, cd[i]), vol[i]);
+  if (dimx == 0 || dimy == 0 || dimz == 0)
+    return -1;
+  if (dimx > 0xFFFFFFFFull || dimy > 0xFFFFFFFFull || dimz > 0xFFFFFFFFull)
+    return -1;
+  const auto chunks = chunk_volume(vol, cd);
+  for (auto& c : chunks)
+    if (c.lx > 65535 || c.ly > 65535 || c.lz > 65535 || c.nelem() >= (1ull << 31))
+      return -1;  // Set3D coordinates are 16-bit in the reference as well
+  if (!g_comp)
+    g_comp = new Compressor();
+  SrcVol sv{d_src, is_float, dimx, dimy};
+  rt::DBuf d_out(size_t(1) << 20);
+  std::vector<size_t> lens;
+  g_comp->compress(sv, chunks, mode, quality, false, d_out, lens, st);
+
+  const size_t nchunks = chunks.size();
+  const size_t hlen = (nchunks > 1 ? 20 : 14) + 4 * nchunks;
+  size_t total = hlen;
+  for (size_t l : lens) {
+    if (l > 0xFFFFFFFFull)
+      return -1;
+    total += l;
+  }
+  uint8_t* o = static_cast<uint8_t*>(std::malloc(total));
+  if (!o)
+    return -1;
+  o[0] = 0;  // SPERR_VERSION_MAJOR
+  o[1] = uint8_t(0x40 | (is_float ? 0x20 : 0) | (nchunks > 1 ? 0x10 : 0));
+  const uint32_t v3[3] = {uint32_t(dimx), uint32_t(dimy), uint32_t(dimz)};
+  std::memcpy(o + 2, v3, 12);
+  size_t pos = 14;
+  if (nchunks > 1) {
+    const uint16_t c3[3] = {uint16_t(cd[0]), uint16_t(cd[1]), uint16_t(cd[2])};
+    std::memcpy(o + pos, c3, 6);
+    pos += 6;
+  }
+  for (size_t l : lens) {
+    const uint32_t l32 = uint32_t(l);
+    std::memcpy(o + pos, &l32, 4);
+    pos += 4;
+  }
+  rt::d2h(o + pos, d_out.p, total - hlen, st);
+  rt::sync(st);
+  *dst = o;
+  *dst_len = total;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_t dimz,
+                  size_t chunk_x, size_t chunk_y, size_t chunk_z, int mode, double quality,
+                  size_t nthreads, void** dst, size_t* dst_len)
+{
+  (void)nthreads;
+  if (*dst != nullptr)
+    return 1;
+  if (quality <= 0.0)
+    return 2;
+  if (mode < 1 || mode > 3)
+    return 2;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return guarded([&] {
+    cudaStream_t st = 0;
+    const size_t bytes = dimx * dimy * dimz * (is_float ? 4 : 8);
+    rt::DBuf d_src(bytes);
+    rt::h2d(d_src.p, src, bytes, st);
+    return comp_3d_device(d_src.p, is_float, dimx, dimy, dimz, chunk_x, chunk_y, chunk_z, mode,
+                          quality, dst, dst_len, st);
+  });
+}
+
+int sperr_b200_comp_3d_dev(const void* d_src, int is_float, size_t dimx, size_t dimy, size_t dimz,
+                           size_t chunk_x, size_t chunk_y, size_t chunk_z, int mode, double quality,
+                           void** dst, size_t* dst_len)
+{
+  if (*dst != nullptr)
+    return 1;
+  if (quality <= 0.0)
+    return 2;
+  if (mode < 1 || mode > 3)
+    return 2;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return guarded([&] {
+    return comp_3d_device(d_src, is_float, dimx, dimy, dimz, chunk_x, chunk_y, chunk_z, mode, quality,
+                          dst, dst_len, 0);
+  });
+}
+
+void sperr_parse_header(const void* src, size_t* dimx, size_t* dimy, size_t* dimz, int* is_float)
+{
+  const uint8_t* p = static_cast<const uint8_t*>(src);
+  const bool is_3d = (p[1] & 0x40) != 0;
+  *is_float = (p[1] & 0x20) ? 1 : 0;
+  uint32_t d[3] = {1, 1, 1};
+  std::memcpy(d, p + 2, is_3d ? 12 : 8);
+  *dimx = d[0];
+  *dimy = d[1];
+  *dimz = d[2];
+}
+
+}  // extern "C"

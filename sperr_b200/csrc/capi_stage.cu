@@ -4,7 +4,8 @@
 #include "../../include/sperr_b200.h"
 
 #include "batch.h"
-#include "speck3d.h"
+#include "outlier.h"
+#include "speck.h"
 
 using namespace sperr_b200;
 
@@ -165,6 +166,34 @@ int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, 
     Speck3DEncoder enc;
     std::vector<EncResult> res;
     enc.encode(b.dev(), b.h, b.dev_shapes(), b.shapes, res, st);
+    const size_t len = 9 + res[0].payload_bytes;
+    *out_len = len;
+    if (len > cap)
+      return -2;
+    out[0] = uint8_t(res[0].planes);
+    const uint64_t tb = res[0].total_bits;
+    std::memcpy(out + 1, &tb, 8);
+    rt::d2h(out + 9, res[0].payload, res[0].payload_bytes, st);
+    rt::sync(st);
+    return 0;
+  });
+}
+
+int sperr_b200_stage_outlier_encode(const uint64_t* pos, const double* err, size_t n_out,
+                                    size_t total_len, double tol, uint8_t* out, size_t cap,
+                                    size_t* out_len)
+{
+  return guarded([&] {
+    cudaStream_t st = 0;
+    if (n_out == 0 || total_len == 0 || tol <= 0.0)
+      return -1;
+    std::vector<unsigned> p32(n_out);
+    for (size_t i = 0; i < n_out; i++)
+      p32[i] = unsigned(pos[i]);
+    OutlierCoder oc;
+    oc.set_outliers({0ull, (unsigned long long)n_out}, p32.data(), err, st);
+    std::vector<EncResult> res;
+    oc.encode({(unsigned long long)total_len}, tol, res, st);
     const size_t len = 9 + res[0].payload_bytes;
     *out_len = len;
     if (len > cap)

@@ -1,0 +1,357 @@
+#include "pipeline.h"
+
+#include <cmath>
+#include <limits>
+
+namespace sperr_b200 {
+
+namespace {
+
+// inverse of the order-preserving key used for atomic min / max of doubles
+double key_to_double(unsigned long long k)
+{
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  double v;
+  std::memcpy(&v, &b, 8);
+  return v;
+}
+
+struct Piece {
+  const unsigned char* src;
+  unsigned long long dst_off;
+  unsigned long long len;
+};
+
+}  // namespace
+
+// One block column per piece; bytes are copied with a grid-stride loop.
+__global__ void k_copy_pieces(const Piece* pieces, unsigned char* dst)
+{
+  const Piece p = pieces[blockIdx.y];
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.len;
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    dst[p.dst_off + i] = p.src[i];
+}
+
+size_t pick_batch_chunks(const std::vector<Chunk>& chunks, size_t first, bool pwe)
+{
+  // Rough HBM footprint per value: fp64 buffer 8, magnitudes 4 (8 when wide), msb / creation maps
+  // 2, pyramid ~0.8, payload staging ~2-4, list buffers ~9 => budget 40 bytes per value.
+  size_t free_b = size_t(64) << 30, total_b = 0;
+#ifndef SPERR_EMUL
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+    free_b = size_t(64) << 30;
+#endif
+  (void)total_b;
+  (void)pwe;
+  const double budget = double(free_b) * 0.7;
+  double used = 0;
+  size_t n = 0;
+  while (first + n < chunks.size() && n < 256) {
+    const double need = double(chunks[first + n].nelem()) * 40.0 + (64 << 20);
+    if (n > 0 && used + need > budget)
+      break;
+    used += need;
+    n++;
+  }
+  return std::max<size_t>(n, 1);
+}
+
+void Compressor::compress(const SrcVol& src, const std::vector<Chunk>& chunks, int mode,
+                          double quality, bool is_2d, rt::DBuf& d_out, std::vector<size_t>& lens,
+                          cudaStream_t st)
+{
+  lens.assign(chunks.size(), 0);
+  size_t used = 0;  // bytes of d_out in use
+  size_t first = 0;
+  while (first < chunks.size()) {
+    const size_t nb = pick_batch_chunks(chunks, first, mode == kModePWE);
+    std::vector<Chunk> sub(chunks.begin() + first, chunks.begin() + first + nb);
+    std::vector<std::vector<uint8_t>> hdrs;
+    run_batch(src, sub, mode, quality, is_2d, hdrs, st);
+
+    // ---- assemble: condi(17) | speck header(9) | payload | [outlier header(9) | payload] ----
+    auto has_outliers = [&](size_t c) {
+      return mode == kModePWE && !b_.h[c].is_const && out_.ooff[c + 1] > out_.ooff[c];
+    };
+    std::vector<Piece> pieces;
+    std::vector<unsigned char> hbytes;
+    struct Ref { size_t hoff, hlen; };
+    size_t batch_total = 0;
+    for (size_t c = 0; c < nb; c++) {
+      size_t len = hdrs[c].size();
+      if (!b_.h[c].is_const) {
+        len += spk_res_[c].payload_bytes;
+        if (has_outliers(c))
+          len += 9 + out_res_[c].payload_bytes;
+      }
+      lens[first + c] = len;
+      batch_total += len;
+    }
+    if (used + batch_total > d_out.bytes) {
+      rt::DBuf bigger(std::max(used + batch_total, d_out.bytes * 2));
+      rt::d2d(bigger.p, d_out.p, used, st);
+      rt::sync(st);
+      d_out = std::move(bigger);
+    }
+    size_t off = used;
+    std::vector<size_t> hdr_off(nb), ohdr_off(nb, 0);
+    for (size_t c = 0; c < nb; c++) {
+      hdr_off[c] = hbytes.size();
+      hbytes.insert(hbytes.end(), hdrs[c].begin(), hdrs[c].end());
+      if (!b_.h[c].is_const && has_outliers(c)) {
+        ohdr_off[c] = hbytes.size();
+        unsigned char oh[9];
+        oh[0] = (unsigned char)out_res_[c].planes;
+        const unsigned long long tb = out_res_[c].total_bits;
+        std::memcpy(oh + 1, &tb, 8);
+        hbytes.insert(hbytes.end(), oh, oh + 9);
+      }
+    }
+    rt::DBuf d_h(hbytes.size() + 16);
+    rt::h2d(d_h.p, hbytes.data(), hbytes.size(), st);
+    const unsigned char* dh = d_h.as<unsigned char>();
+    for (size_t c = 0; c < nb; c++) {
+      pieces.push_back({dh + hdr_off[c], off, hdrs[c].size()});
+      off += hdrs[c].size();
+      if (b_.h[c].is_const)
+        continue;
+      if (spk_res_[c].payload_bytes) {
+        pieces.push_back({reinterpret_cast<const unsigned char*>(spk_res_[c].payload), off,
+                          spk_res_[c].payload_bytes});
+        off += spk_res_[c].payload_bytes;
+      }
+      if (has_outliers(c)) {
+        pieces.push_back({dh + ohdr_off[c], off, 9});
+        off += 9;
+        if (out_res_[c].payload_bytes) {
+          pieces.push_back({reinterpret_cast<const unsigned char*>(out_res_[c].payload), off,
+                            out_res_[c].payload_bytes});
+          off += out_res_[c].payload_bytes;
+        }
+      }
+    }
+    rt::DBuf d_p(pieces.size() * sizeof(Piece));
+    rt::h2d(d_p.p, pieces.data(), pieces.size() * sizeof(Piece), st);
+    const Piece* dp = d_p.as<Piece>();
+    unsigned char* dst = d_out.as<unsigned char>();
+    LAUNCH(k_copy_pieces, dim3(64, unsigned(pieces.size())), dim3(256), 0, st, dp, dst);
+    rt::sync(st);
+    used = off;
+    first += nb;
+  }
+}
+
+void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, int mode,
+                           double quality, bool is_2d, std::vector<std::vector<uint8_t>>& hdrs,
+                           cudaStream_t st)
+{
+  if (is_2d)
+    throw std::runtime_error("2D path not built yet");
+  const int nc = int(chunks.size());
+  b_.setup(chunks, true, true, false, st);
+
+  // ---- conditioner ----
+  std::vector<unsigned> ns(nc);
+  int max_strides = 1;
+  for (int c = 0; c < nc; c++) {
+    ns[c] = unsigned(mean_num_strides(chunks[c].nelem()));
+    max_strides = std::max<int>(max_strides, int(ns[c]));
+  }
+  stride_mean_.reserve((size_t)nc * max_strides * 8);
+  nstrides_.reserve(nc * 4);
+  not_const_.reserve(nc * 4);
+  rt::h2d(nstrides_.p, ns.data(), nc * 4, st);
+  rt::dset(not_const_.p, 0, nc * 4, st);
+  launch_stats(src, b_.dev(), nc, stride_mean_.as<double>(), max_strides, nstrides_.as<unsigned>(),
+               not_const_.as<unsigned>(), mode == kModePSNR, st);
+  launch_gather(src, b_.dev(), nc, b_.max_n, st);
+
+  // ---- wavelet transform, one launch series per distinct chunk shape ----
+  std::vector<std::vector<int>> groups(b_.shapes.size());
+  for (int c = 0; c < nc; c++)
+    groups[b_.h[c].shape].push_back(c);
+  std::vector<int> flat;
+  std::vector<size_t> goff;
+  for (auto& g : groups) {
+    goff.push_back(flat.size());
+    flat.insert(flat.end(), g.begin(), g.end());
+  }
+  ids_.reserve(flat.size() * 4 + 4);
+  rt::h2d(ids_.p, flat.data(), flat.size() * 4, st);
+  rt::sync(st);
+  auto transform = [&](bool inverse) {
+    for (size_t s = 0; s < groups.size(); s++) {
+      if (groups[s].empty())
+        continue;
+      const ShapeHeader& h = b_.shapes[s].h;
+      launch_dwt(inverse, b_.dev(), ids_.as<int>() + goff[s], int(groups[s].size()), h.nx, h.ny, h.nz,
+                 is_2d, st);
+    }
+  };
+  transform(false);
+  launch_absmax(b_.dev(), nc, b_.max_n, st);
+  b_.pull(st);
+
+  // ---- quantisation step per chunk (SPECK_FLT::m_estimate_q, src/SPECK_FLT.cpp:268-309) ----
+  std::vector<double> maxabs(nc);
+  for (int c = 0; c < nc; c++) {
+    ChunkDev& d = b_.h[c];
+    std::memcpy(&maxabs[c], &d.max_bits, 8);
+    if (d.is_const)
+      continue;
+    if (mode == kModePWE)
+      d.q = quality * 1.5;
+    else if (mode == kModeRate) {
+      d.q = maxabs[c] / double(std::numeric_limits<uint32_t>::max());
+      size_t bud = size_t(quality * double(d.n));
+      while (bud % 8 != 0)
+        bud++;
+      d.budget = bud == 0 ? ~0ull : bud;
+    }
+  }
+  if (mode == kModePSNR) {
+    std::vector<double> t_mse(nc, 0.0), q(nc, 0.0);
+    std::vector<int> todo;
+    size_t max_s = 1;
+    for (int c = 0; c < nc; c++) {
+      ChunkDev& d = b_.h[c];
+      if (d.is_const)
+        continue;
+      const double mx = key_to_double(d.max_key) - d.mean;
+      const double mn = key_to_double(d.min_key) - d.mean;
+      const double range = mx - mn;
+      t_mse[c] = (range * range) * std::pow(10.0, -quality / 10.0);
+      q[c] = 2.0 * std::sqrt(t_mse[c] * 3.0);
+      todo.push_back(c);
+      max_s = std::max<size_t>(max_s, d.n / 4096 + 1);
+    }
+    mse_ids_.reserve(nc * 4);
+    mse_q_.reserve(nc * 8);
+    mse_out_.reserve(nc * 8);
+    mse_part_.reserve((size_t)nc * max_s * 8);
+    while (!todo.empty()) {
+      std::vector<double> qs;
+      for (int c : todo)
+        qs.push_back(q[c]);
+      rt::h2d(mse_ids_.p, todo.data(), todo.size() * 4, st);
+      rt::h2d(mse_q_.p, qs.data(), qs.size() * 8, st);
+      launch_mse(b_.dev(), mse_ids_.as<int>(), mse_q_.as<double>(), mse_part_.as<double>(), int(max_s),
+                 mse_out_.as<double>(), int(todo.size()), st);
+      std::vector<double> mse(todo.size());
+      rt::d2h(mse.data(), mse_out_.p, todo.size() * 8, st);
+      rt::sync(st);
+      std::vector<int> next;
+      for (size_t i = 0; i < todo.size(); i++) {
+        const int c = todo[i];
+        // NaN compares false, exactly as in the reference's while loop
+        if (mse[i] > t_mse[c]) {
+          q[c] /= std::exp2(0.25);
+          next.push_back(c);
+        }
+      }
+      todo.swap(next);
+    }
+    for (int c = 0; c < nc; c++)
+      if (!b_.h[c].is_const)
+        b_.h[c].q = q[c];
+  }
+  b_.push(st);
+
+  auto quantize_and_encode = [&](Speck3DEncoder& enc, std::vector<EncResult>& res) {
+    launch_qdecide(b_.dev(), nc, st);
+    b_.pull(st);
+    bool any_wide = false;
+    for (auto& d : b_.h) {
+      if (!d.is_const && d.fe_invalid)
+        throw std::runtime_error("FE_INVALID while quantising");
+      any_wide |= (!d.is_const && d.wide);
+    }
+    if (any_wide && !b_.wide) {
+      b_.make_wide(st);
+      b_.push(st);
+    }
+    launch_quantize(b_.dev(), nc, b_.max_n, st);
+    if (mode == kModePWE) {
+      launch_inv_quantize(b_.dev(), nc, b_.max_n, st);
+      transform(true);
+      out_.detect(src, b_.dev(), nc, b_.max_n, quality, st);
+      std::vector<unsigned long long> tl(nc);
+      for (int c = 0; c < nc; c++)
+        tl[c] = b_.h[c].n;
+      out_.encode(tl, quality, out_res_, st);
+    }
+    enc.encode(b_.dev(), b_.h, b_.dev_shapes(), b_.shapes, res, st);
+  };
+  quantize_and_encode(enc_, spk_res_);
+
+  // ---- fixed-rate: not enough bits produced => redo with the high-precision step (:530-538) ----
+  if (mode == kModeRate) {
+    std::vector<int> retry;
+    for (int c = 0; c < nc; c++) {
+      if (b_.h[c].is_const)
+        continue;
+      const unsigned long long actual = (9ull + spk_res_[c].payload_bytes) * 8ull;
+      const size_t budget = size_t(quality * double(b_.h[c].n));
+      if (actual < budget)
+        retry.push_back(c);
+    }
+    if (!retry.empty()) {
+      // keep the finished chunks out of the second pass by flagging them constant for a moment
+      std::vector<int> saved(nc);
+      std::vector<double> q_keep(nc);
+      for (int c = 0; c < nc; c++) {
+        saved[c] = b_.h[c].is_const;
+        q_keep[c] = b_.h[c].q;
+        b_.h[c].is_const = 1;
+      }
+      for (int c : retry) {
+        b_.h[c].is_const = 0;
+        b_.h[c].q = maxabs[c] / 0x1.fffffffffffffp52;
+        b_.h[c].wide = 0;
+        b_.h[c].fe_invalid = 0;
+      }
+      b_.push(st);
+      rt::dset(b_.cmap.p, 0xFF, b_.cmap.bytes, st);
+      std::vector<EncResult> res2;
+      // the second pass needs its own payload staging: the first-pass payloads are still needed
+      quantize_and_encode(enc_hp_, res2);
+      for (int c : retry)
+        spk_res_[c] = res2[c];
+      for (int c = 0; c < nc; c++) {
+        const bool was_retry = std::find(retry.begin(), retry.end(), c) != retry.end();
+        b_.h[c].is_const = saved[c];
+        if (!was_retry)
+          b_.h[c].q = q_keep[c];
+      }
+    }
+  }
+  else {
+    b_.pull(st);
+  }
+
+  // ---- per-chunk headers: conditioner (17 bytes) + SPECK stream header (9 bytes) ----
+  hdrs.assign(nc, {});
+  for (int c = 0; c < nc; c++) {
+    const ChunkDev& d = b_.h[c];
+    std::vector<uint8_t>& h = hdrs[c];
+    h.assign(17, 0);
+    if (d.is_const) {
+      // Conditioner::condition, src/Conditioner.cpp:28-44: {0x81, u64 nval, f64 value}
+      h[0] = 0x81;
+      const uint64_t nval = d.n;
+      std::memcpy(&h[1], &nval, 8);
+      std::memcpy(&h[9], &d.first_val, 8);
+      continue;
+    }
+    h[0] = 0x80;
+    std::memcpy(&h[1], &d.mean, 8);
+    std::memcpy(&h[9], &d.q, 8);  // Conditioner::save_q, :104-108
+    h.resize(26);
+    h[17] = uint8_t(spk_res_[c].planes);
+    const uint64_t tb = spk_res_[c].total_bits;
+    std::memcpy(&h[18], &tb, 8);
+  }
+}
+
+}  // namespace sperr_b200

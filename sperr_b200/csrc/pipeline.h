@@ -1,0 +1,39 @@
+// Chunk-batch pipelines: the GPU counterpart of SPERR3D_OMP_C / SPERR3D_OMP_D's per-chunk loop
+// (/root/reference/src/SPERR3D_OMP_C.cpp:62-141, src/SPERR3D_OMP_D.cpp:51-135) with
+// SPECK_FLT::compress / decompress (src/SPECK_FLT.cpp:401-606) inside.
+#pragma once
+
+#include "batch.h"
+#include "outlier.h"
+#include "speck.h"
+
+namespace sperr_b200 {
+
+enum Mode { kModeRate = 1, kModePSNR = 2, kModePWE = 3 };
+
+struct StageTimes {  // milliseconds, filled when profiling is requested
+  float stats = 0, transform = 0, quant = 0, outlier = 0, speck = 0, assemble = 0;
+};
+
+class Compressor {
+ public:
+  // Compresses `chunks` of the device-resident volume `src`. On return `d_out` holds the chunk
+  // streams back to back (device memory) and `lens` their lengths. Throws on error.
+  void compress(const SrcVol& src, const std::vector<Chunk>& chunks, int mode, double quality,
+                bool is_2d, rt::DBuf& d_out, std::vector<size_t>& lens, cudaStream_t st);
+
+ private:
+  void run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, int mode, double quality,
+                 bool is_2d, std::vector<std::vector<uint8_t>>& hdrs, cudaStream_t st);
+  BatchBuffers b_;
+  Speck3DEncoder enc_, enc_hp_;
+  OutlierCoder out_;
+  rt::DBuf stride_mean_, nstrides_, not_const_, ids_, mse_ids_, mse_q_, mse_part_, mse_out_;
+  // results of the last batch
+  std::vector<EncResult> spk_res_, out_res_;
+};
+
+// Largest number of chunks processed at once (bounded by the list-key layout and by memory).
+size_t pick_batch_chunks(const std::vector<Chunk>& chunks, size_t first, bool pwe);
+
+}  // namespace sperr_b200

@@ -1,4 +1,4 @@
-// SPECK3D integer coder: batch-level context and host drivers.
+// Integer SPECK coders: batch-level context and host drivers.
 #pragma once
 
 #include "kernels.h"
@@ -46,6 +46,12 @@ struct EncResult {
   size_t payload_bytes = 0;           // ceil(min(budget, total_bits) / 8)
 };
 
+// Work buffers of the bit-plane loop (grow-only, reused across calls).
+struct EncWork {
+  rt::DBuf keys[2], nodes[2], fnode[2], fpos[2], rseg, rpos, scan_tmp, sort_tmp, small, stage,
+      counts, sizes;
+};
+
 class Speck3DEncoder {
  public:
   // Expects for every chunk: mag, signs, pleaf filled; cmap set to -1; pyr_p / pyr_d allocated;
@@ -55,23 +61,8 @@ class Speck3DEncoder {
               std::vector<EncResult>& results, cudaStream_t st);
 
  private:
-  rt::DBuf ids_, keys_[2], nodes_[2], fnode_[2], fpos_[2], rseg_, rpos_, scan_tmp_, sort_tmp_,
-      small_, stage_, counts_, sizes_;
-};
-
-struct DecResult {
-  int ok = 1;
-};
-
-class Speck3DDecoder {
- public:
-  // Expects for every chunk: mag / signs allocated; stream pointers set in the DecChunk array.
-  void decode(ChunkDev* d_chunks, const std::vector<ChunkDev>& h_chunks, const ShapeDev* d_shapes,
-              const std::vector<ShapeTables>& shapes, const uint8_t* const* d_streams,
-              const std::vector<size_t>& stream_len, cudaStream_t st);
-
- private:
-  rt::DBuf work_;
+  rt::DBuf ids_;
+  EncWork work_;
 };
 
 }  // namespace sperr_b200

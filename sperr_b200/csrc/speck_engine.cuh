@@ -1,0 +1,617 @@
+// Tree-agnostic part of the integer SPECK encoder (shared by the 3D coefficient coder and the 1D
+// outlier coder). See speck3d_enc.cu for the idea. A "tree policy" T supplies:
+//   struct T::Data                                             device pointers describing the tree
+//   static __device__ void  T::pd(data, chunk, c, node, int& p, unsigned& d)
+//   static __device__ int   T::children(data, chunk, c, node, ChildRec out[8])
+// where p = msb position of the largest magnitude below the node (-1: all zero) and d = number of
+// bits the node's depth-first expansion emits in the plane it turns significant.
+#pragma once
+
+#include "speck.h"
+
+namespace sperr_b200 {
+
+struct ChildRec {
+  node_t id;
+  int p;
+  unsigned d;         // sets only
+  int kind;           // 0 pixel, 1 set whose children are all pixels, 2 any other set
+  unsigned lis_desc;  // sets only: (number of lists - 1 - list index)
+  unsigned sign;      // pixels only: sign bit (1 = non-negative)
+};
+
+__device__ __forceinline__ void put_bit(uint32_t* words, unsigned long long pos, unsigned bit)
+{
+  if (bit)
+    atomicOr(&words[pos >> 5], 1u << (pos & 31));
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. LIP / refinement parts: per-plane raster-order counts, scans and emission
+// ---------------------------------------------------------------------------------------------
+
+constexpr int kLrBlock = 1024;
+
+__device__ __forceinline__ unsigned long long load_mag(const ChunkDev& ch, unsigned long long i)
+{
+  return ch.wide ? reinterpret_cast<const unsigned long long*>(ch.mag)[i]
+                 : (unsigned long long)reinterpret_cast<const unsigned*>(ch.mag)[i];
+}
+
+// counts[((c*2 + part) * maxp + n) * nblk + blk], part 0 = LIP, 1 = refinement
+static __global__ void k_lipref_count(const ChunkDev* chunks, unsigned* counts, int maxp, unsigned nblk)
+{
+  __shared__ unsigned s_lip[64], s_ref[64];
+  __shared__ int s_cmax;
+  const unsigned c = blockIdx.y, blk = blockIdx.x;
+  const ChunkDev& ch = chunks[c];
+  if (ch.is_const || ch.planes == 0 || (unsigned long long)blk * kLrBlock >= ch.n)
+    return;
+  const unsigned long long i = (unsigned long long)blk * kLrBlock + threadIdx.x;
+  const bool valid = i < ch.n;
+  const int p = valid ? int(ch.pleaf[i]) : -1;
+  const int cm = valid ? int(ch.cmap[i]) : -1;
+  if (threadIdx.x < 64) {
+    s_lip[threadIdx.x] = 0;
+    s_ref[threadIdx.x] = 0;
+  }
+  if (threadIdx.x == 0)
+    s_cmax = -1;
+  __syncthreads();
+  const int wmax = __reduce_max_sync(0xffffffffu, cm);
+  if ((threadIdx.x & 31) == 0 && wmax >= 0)
+    atomicMax(&s_cmax, wmax);
+  __syncthreads();
+  const int cmax = s_cmax;  // bits exist only for planes n < cmax
+  for (int n = 0; n < cmax; n++) {
+    const bool inlip = cm > n && p <= n;
+    const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
+    const unsigned b1 = __ballot_sync(0xffffffffu, inlip && p == n);
+    const unsigned b2 = __ballot_sync(0xffffffffu, p > n);
+    if ((threadIdx.x & 31) == 0) {
+      const unsigned l = __popc(b0) + __popc(b1), r = __popc(b2);
+      if (l)
+        atomicAdd(&s_lip[n], l);
+      if (r)
+        atomicAdd(&s_ref[n], r);
+    }
+  }
+  __syncthreads();
+  if (int(threadIdx.x) < cmax) {
+    const int n = threadIdx.x;
+    counts[((size_t)(c * 2 + 0) * maxp + n) * nblk + blk] = s_lip[n];
+    counts[((size_t)(c * 2 + 1) * maxp + n) * nblk + blk] = s_ref[n];
+  }
+}
+
+// One block per (chunk, part, plane) row: exclusive scan over blocks in place, row total to sizes.
+static __global__ void k_lipref_scan(const ChunkDev* chunks, unsigned* counts, unsigned long long* sizes,
+                              int maxp, unsigned nblk)
+{
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned carry_s;
+  const unsigned c = blockIdx.y, part = blockIdx.x / maxp, n = blockIdx.x % maxp;
+  const ChunkDev& ch = chunks[c];
+  unsigned long long* out = &sizes[(size_t)(c * 2 + part) * maxp + n];
+  if (ch.is_const || int(n) >= ch.planes) {
+    if (threadIdx.x == 0)
+      *out = 0;
+    return;
+  }
+  unsigned* row = counts + ((size_t)(c * 2 + part) * maxp + n) * nblk;
+  const unsigned used = unsigned((ch.n + kLrBlock - 1) / kLrBlock);
+  if (threadIdx.x == 0)
+    carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned base = 0; base < used; base += blockDim.x) {
+    const unsigned i = base + threadIdx.x;
+    const unsigned v = i < used ? row[i] : 0;
+    unsigned inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o)
+        inc += t;
+    }
+    if (lane == 31)
+      wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = wsum[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o)
+          w += t;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const unsigned carry = carry_s;
+    const unsigned excl = carry + inc - v + (warp ? wsum[warp - 1] : 0);
+    if (i < used)
+      row[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      carry_s = carry + wsum[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *out = carry_s;
+}
+
+// bases[(c*2 + part) * maxp + n]: absolute bit position of that part (set by k_plane_begin)
+static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* counts,
+                              const unsigned long long* bases, int maxp, unsigned nblk)
+{
+  __shared__ unsigned s_w[2][32];
+  __shared__ int s_cmax;
+  const unsigned c = blockIdx.y, blk = blockIdx.x;
+  const ChunkDev& ch = chunks[c];
+  if (ch.is_const || ch.planes == 0 || (unsigned long long)blk * kLrBlock >= ch.n)
+    return;
+  const unsigned long long i = (unsigned long long)blk * kLrBlock + threadIdx.x;
+  const bool valid = i < ch.n;
+  const int p = valid ? int(ch.pleaf[i]) : -1;
+  const int cm = valid ? int(ch.cmap[i]) : -1;
+  const unsigned long long mag = (valid && p >= 0) ? load_mag(ch, i) : 0;
+  const unsigned sgn = valid ? (ch.signs[i >> 5] >> (i & 31)) & 1u : 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1;
+  if (threadIdx.x == 0)
+    s_cmax = -1;
+  __syncthreads();
+  const int wmax = __reduce_max_sync(0xffffffffu, cm);
+  if (lane == 0 && wmax >= 0)
+    atomicMax(&s_cmax, wmax);
+  __syncthreads();
+  const int cmax = s_cmax;
+  const int first = ch.last_plane;  // planes below this were never coded
+  for (int n = cmax - 1; n >= first; n--) {
+    const bool inlip = cm > n && p <= n;
+    const bool newsig = inlip && p == n;
+    const bool ref = p > n && !(n == ch.last_plane && ch.stop_after_sort);
+    const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
+    const unsigned b1 = __ballot_sync(0xffffffffu, newsig);
+    const unsigned b2 = __ballot_sync(0xffffffffu, ref);
+    if (lane == 0) {
+      s_w[0][warp] = __popc(b0) + __popc(b1);
+      s_w[1][warp] = __popc(b2);
+    }
+    __syncthreads();
+    if (warp < 2) {
+      unsigned v = s_w[warp][lane], inc = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+          inc += t;
+      }
+      s_w[warp][lane] = inc - v;
+    }
+    __syncthreads();
+    if (inlip) {
+      const unsigned long long pos = bases[(size_t)(c * 2 + 0) * maxp + n] +
+                                     counts[((size_t)(c * 2 + 0) * maxp + n) * nblk + blk] +
+                                     s_w[0][warp] + __popc(b0 & lt) + __popc(b1 & lt);
+      if (newsig) {
+        put_bit(ch.spk, pos, 1);
+        put_bit(ch.spk, pos + 1, sgn);
+      }
+    }
+    if (ref) {
+      const unsigned long long pos = bases[(size_t)(c * 2 + 1) * maxp + n] +
+                                     counts[((size_t)(c * 2 + 1) * maxp + n) * nblk + blk] +
+                                     s_w[1][warp] + __popc(b2 & lt);
+      put_bit(ch.spk, pos, unsigned(mag >> n) & 1u);
+    }
+    __syncthreads();
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// LIS part, one plane at a time
+// ---------------------------------------------------------------------------------------------
+
+// step s of the bit-plane loop: which plane does each chunk code?
+static __global__ void k_plane_pre(EncCtx ctx, int step)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ctx.nchunks)
+    return;
+  ChunkDev& ch = ctx.chunks[c];
+  ch.cur_n = ch.planes - 1 - step;
+  ch.plane_live = ch.active && ch.cur_n >= 0;
+  ch.ncand = 0;
+}
+
+template <class T>
+__global__ void k_root_seglen(EncCtx ctx, typename T::Data tree, unsigned long long nroots)
+{
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nroots;
+       i += stride) {
+    const unsigned c = key_chunk(ctx.rkey[i]);
+    const ChunkDev& ch = ctx.chunks[c];
+    int p;
+    unsigned d;
+    T::pd(tree, ch, c, ctx.rnode[i], p, d);
+    ctx.rseg[i] = 1 + (p == ch.cur_n ? d : 0u);
+  }
+}
+
+// Places the three parts of this plane and applies the fixed-rate budget rules
+// (src/SPECK_INT.cpp:145-158).
+static __global__ void k_plane_begin(EncCtx ctx)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ctx.nchunks)
+    return;
+  ChunkDev& ch = ctx.chunks[c];
+  ch.next_needed = 0;
+  if (!ch.plane_live)
+    return;
+  const int n = ch.cur_n;
+  const unsigned long long lis = ctx.rpos[ctx.rstart[c + 1]] - ctx.rpos[ctx.rstart[c]];
+  const unsigned long long lip = ctx.sizes[(size_t)(c * 2 + 0) * ctx.maxp + n];
+  const unsigned long long ref = ctx.sizes[(size_t)(c * 2 + 1) * ctx.maxp + n];
+  ctx.bases[(size_t)(c * 2 + 0) * ctx.maxp + n] = ch.cursor;
+  ch.lis_base = ch.cursor + lip;
+  const unsigned long long after_sort = ch.lis_base + lis;
+  ctx.bases[(size_t)(c * 2 + 1) * ctx.maxp + n] = after_sort;
+  ch.last_plane = n;
+  if (after_sort >= ch.budget) {
+    ch.stop_after_sort = 1;
+    ch.total_bits = after_sort;
+    ch.active = 0;
+    return;
+  }
+  const unsigned long long after_ref = after_sort + ref;
+  ch.total_bits = after_ref;
+  if (after_ref >= ch.budget || n == 0) {
+    ch.active = 0;
+    return;
+  }
+  ch.cursor = after_ref;
+  ch.next_needed = 1;
+}
+
+struct Appender {
+  EncCtx ctx;
+  __device__ __forceinline__ void cand(unsigned c, unsigned long long key, node_t nd) const
+  {
+    const unsigned long long slot = atomicAdd(ctx.cand_count, 1ull);
+    if (slot >= ctx.cand_cap) {
+      atomicOr(ctx.err, 1u);
+      return;
+    }
+    ctx.ckey[slot] = key;
+    ctx.cnode[slot] = nd;
+    atomicAdd(&ctx.chunks[c].ncand, 1u);
+  }
+  __device__ __forceinline__ void front(int dst, unsigned c, node_t nd, unsigned long long pos) const
+  {
+    const unsigned long long slot = atomicAdd(&ctx.fcount[dst], 1ull);
+    if (slot >= ctx.front_cap) {
+      atomicOr(ctx.err, 2u);
+      return;
+    }
+    ctx.fnode[dst][slot] = nd;
+    ctx.fpos[dst][slot] = (pos << 10) | c;
+  }
+};
+
+template <class T>
+__global__ void k_root_emit(EncCtx ctx, typename T::Data tree, unsigned long long nroots)
+{
+  const Appender app{ctx};
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nroots;
+       i += stride) {
+    const unsigned long long key = ctx.rkey[i];
+    const unsigned c = key_chunk(key);
+    const ChunkDev& ch = ctx.chunks[c];
+    if (!ch.plane_live)
+      continue;
+    const unsigned long long pos = ch.lis_base + (ctx.rpos[i] - ctx.rpos[ctx.rstart[c]]);
+    const node_t nd = ctx.rnode[i];
+    int p;
+    unsigned d;
+    T::pd(tree, ch, c, nd, p, d);
+    if (p == ch.cur_n) {
+      put_bit(ch.spk, pos, 1);
+      app.front(0, c, nd, pos + 1);
+    }
+    else if (ch.next_needed)  // insignificant: stays in its list, same position
+      app.cand(c, key, nd);
+  }
+}
+
+// One thread per significant set: m_code_S (src/SPECK3D_INT.cpp:140-212, src/SPECK1D_INT_ENC.cpp:
+// 121-160) with every child placed by its D instead of by recursion order.
+template <class T>
+__global__ void k_expand(EncCtx ctx, typename T::Data tree, int src)
+{
+  const Appender app{ctx};
+  const int dst = src ^ 1;
+  const unsigned long long count = ctx.fcount[src];
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += stride) {
+    const node_t nd = ctx.fnode[src][i];
+    const unsigned long long pc = ctx.fpos[src][i];
+    const unsigned c = unsigned(pc & 1023u);
+    unsigned long long cur = pc >> 10;
+    const ChunkDev& ch = ctx.chunks[c];
+    const int n = ch.cur_n;
+    ChildRec kid[8];
+    const int nch = T::children(tree, ch, c, nd, kid);
+    int sigc = 0;
+    for (int k = 0; k < nch; k++) {
+      const bool need = sigc != 0 || k != nch - 1;
+      const bool sig = !need || kid[k].p == n;
+      if (need) {
+        put_bit(ch.spk, cur, sig);
+        cur++;
+      }
+      if (kid[k].kind == 0) {
+        if (sig) {
+          put_bit(ch.spk, cur, kid[k].sign);
+          cur++;
+          sigc++;
+        }
+      }
+      else if (sig) {
+        sigc++;
+        if (kid[k].kind == 1) {  // all grandchildren are pixels: finish them here
+          ChildRec g[8];
+          const int ng = T::children(tree, ch, c, kid[k].id, g);
+          int gs = 0;
+          for (int j = 0; j < ng; j++) {
+            const bool gneed = gs != 0 || j != ng - 1;
+            const bool gsig = !gneed || g[j].p == n;
+            if (gneed) {
+              put_bit(ch.spk, cur, gsig);
+              cur++;
+            }
+            if (gsig) {
+              put_bit(ch.spk, cur, g[j].sign);
+              cur++;
+              gs++;
+            }
+          }
+        }
+        else {
+          app.front(dst, c, kid[k].id, cur);
+          cur += kid[k].d;
+        }
+      }
+      else if (ch.next_needed)
+        app.cand(c, make_key(c, kid[k].lis_desc, (cur - 1) + 64), kid[k].id);
+    }
+  }
+}
+
+static __global__ void k_front_reset(EncCtx ctx, int which)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    ctx.fcount[which] = 0;
+}
+
+// Single block: list segment of every chunk for the next plane.
+static __global__ void k_plane_end(EncCtx ctx)
+{
+  __shared__ unsigned long long s_start[kMaxBatchChunks + 1];
+  for (int c = threadIdx.x; c < ctx.nchunks; c += blockDim.x)
+    s_start[c] = ctx.chunks[c].ncand;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int c = 0; c < ctx.nchunks; c++) {
+      const unsigned long long v = s_start[c];
+      s_start[c] = acc;
+      acc += v;
+    }
+    s_start[ctx.nchunks] = acc;
+    *ctx.total_roots = acc;
+    *ctx.cand_count = 0;
+    ctx.fcount[0] = 0;
+    ctx.fcount[1] = 0;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c <= ctx.nchunks; c += blockDim.x)
+    ctx.rstart[c] = s_start[c];
+}
+
+// Seeds the per-chunk coder state once `planes` is known and lays the initial sets into the
+// sorted root arrays. `nroots[c]` initial sets per chunk are produced by T::root(data, c, r, ...).
+template <class T>
+__global__ void k_enc_seed(EncCtx ctx, typename T::Data tree)
+{
+  __shared__ unsigned long long s_start[kMaxBatchChunks + 1];
+  for (int c = threadIdx.x; c < ctx.nchunks; c += blockDim.x) {
+    ChunkDev& ch = ctx.chunks[c];
+    const int P = ch.is_const ? 0 : T::planes(tree, ch, c);
+    ch.planes = P;
+    ch.active = P > 0;
+    ch.cursor = 0;
+    ch.total_bits = 0;
+    ch.last_plane = 0;
+    ch.stop_after_sort = 0;
+    ch.ncand = 0;
+    s_start[c] = P > 0 ? T::num_roots(tree, ch, c) : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int c = 0; c < ctx.nchunks; c++) {
+      const unsigned long long v = s_start[c];
+      s_start[c] = acc;
+      acc += v;
+    }
+    s_start[ctx.nchunks] = acc;
+    *ctx.total_roots = acc;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c <= ctx.nchunks; c += blockDim.x)
+    ctx.rstart[c] = s_start[c];
+  for (int c = threadIdx.x; c < ctx.nchunks; c += blockDim.x) {
+    const ChunkDev& ch = ctx.chunks[c];
+    if (ch.planes == 0)
+      continue;
+    const int nr = T::num_roots(tree, ch, c);
+    for (int r = 0; r < nr; r++) {
+      unsigned lis_desc, order;
+      node_t nd;
+      T::root(tree, ch, c, r, nd, lis_desc, order);
+      ctx.rkey[s_start[c] + r] = make_key(c, lis_desc, order);
+      ctx.rnode[s_start[c] + r] = nd;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver of the bit-plane loop
+// ---------------------------------------------------------------------------------------------
+
+// `cap_nodes`: upper bound on the number of sets alive / expanded at once over the whole batch.
+// `bits_bound(c, planes)`: upper bound of the payload size of chunk c. `max_depth`: number of
+// expansion rounds that empties any frontier.
+template <class T, class BitsBound>
+void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
+                 const typename T::Data& tree, unsigned long long cap_nodes, int max_depth,
+                 BitsBound bits_bound, std::vector<EncResult>& results, cudaStream_t st)
+{
+  if (nchunks > kMaxBatchChunks)
+    throw std::runtime_error("too many chunks in one batch");
+  results.assign(nchunks, EncResult());
+  EncCtx ctx;
+  ctx.chunks = d_chunks;
+  ctx.nchunks = nchunks;
+  ctx.shapes = nullptr;
+  ctx.cand_cap = cap_nodes + 64ull * nchunks;
+  ctx.front_cap = ctx.cand_cap;
+  const size_t cap = size_t(ctx.cand_cap);
+  for (int i = 0; i < 2; i++) {
+    w.keys[i].reserve(cap * 8);
+    w.nodes[i].reserve(cap * 8);
+    w.fnode[i].reserve(cap * 8);
+    w.fpos[i].reserve(cap * 8);
+  }
+  w.rseg.reserve((cap + 1) * 4);
+  w.rpos.reserve((cap + 2) * 8);
+  w.scan_tmp.reserve(scan_tmp_bytes(cap + 1));
+  const size_t sort_bytes = sort_tmp_bytes(cap);
+  w.sort_tmp.reserve(sort_bytes);
+  w.small.reserve(4096 + (kMaxBatchChunks + 1) * 8);
+  rt::dset(w.small.p, 0, w.small.bytes, st);
+  unsigned long long* small = w.small.as<unsigned long long>();
+  ctx.total_roots = small + 0;
+  ctx.cand_count = small + 1;
+  ctx.fcount = small + 2;  // two counters
+  ctx.err = reinterpret_cast<unsigned*>(small + 4);
+  ctx.rstart = small + 8;
+  ctx.rkey = w.keys[0].as<unsigned long long>();
+  ctx.rnode = w.nodes[0].as<node_t>();
+  ctx.ckey = w.keys[1].as<unsigned long long>();
+  ctx.cnode = w.nodes[1].as<node_t>();
+  ctx.fnode[0] = w.fnode[0].as<node_t>(); ctx.fnode[1] = w.fnode[1].as<node_t>();
+  ctx.fpos[0] = w.fpos[0].as<unsigned long long>(); ctx.fpos[1] = w.fpos[1].as<unsigned long long>();
+  ctx.rseg = w.rseg.as<unsigned>();
+  ctx.rpos = w.rpos.as<unsigned long long>();
+  ctx.maxp = 1;
+  ctx.sizes = ctx.bases = nullptr;
+
+  LAUNCH(k_enc_seed<T>, dim3(1), dim3(1024), 0, st, ctx, tree);
+
+  // planes are only known on the device: fetch them to size the staging buffers and tables
+  std::vector<ChunkDev> hc(nchunks);
+  rt::d2h(hc.data(), d_chunks, sizeof(ChunkDev) * nchunks, st);
+  unsigned long long total_roots = 0;
+  rt::d2h(&total_roots, ctx.total_roots, 8, st);
+  rt::sync(st);
+  int maxp = 1;
+  for (auto& c : hc)
+    maxp = std::max(maxp, c.planes);
+  ctx.maxp = maxp;
+
+  // staging bit arrays
+  {
+    std::vector<unsigned long long> words_off(nchunks + 1, 0);
+    for (int c = 0; c < nchunks; c++) {
+      const unsigned long long bits = hc[c].planes > 0 ? bits_bound(c, hc[c]) : 0;
+      words_off[c + 1] = words_off[c] + (bits + 31) / 32 + 2;
+    }
+    w.stage.reserve(words_off[nchunks] * 4);
+    rt::dset(w.stage.p, 0, words_off[nchunks] * 4, st);
+    for (int c = 0; c < nchunks; c++) {
+      hc[c].spk = w.stage.as<uint32_t>() + words_off[c];
+      hc[c].spk_cap_bits = (words_off[c + 1] - words_off[c]) * 32;
+    }
+    rt::h2d(d_chunks, hc.data(), sizeof(ChunkDev) * nchunks, st);
+  }
+
+  // LIP / refinement counts for every plane
+  const unsigned nblk = unsigned((max_n + kLrBlock - 1) / kLrBlock);
+  const size_t ncounts = (size_t)nchunks * 2 * maxp * std::max(nblk, 1u);
+  w.counts.reserve(ncounts * 4);
+  rt::dset(w.counts.p, 0, ncounts * 4, st);
+  w.sizes.reserve((size_t)nchunks * 2 * maxp * 8 * 2);
+  rt::dset(w.sizes.p, 0, (size_t)nchunks * 2 * maxp * 8 * 2, st);
+  ctx.sizes = w.sizes.as<unsigned long long>();
+  ctx.bases = ctx.sizes + (size_t)nchunks * 2 * maxp;
+  unsigned* d_counts = w.counts.as<unsigned>();
+  if (nblk) {
+    LAUNCH(k_lipref_count, dim3(nblk, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, maxp, nblk);
+    LAUNCH(k_lipref_scan, dim3(2 * maxp, nchunks), dim3(1024), 0, st, d_chunks, d_counts, ctx.sizes,
+           maxp, nblk);
+  }
+
+  // bit-plane loop (LIS part)
+  void* d_scan_tmp = w.scan_tmp.p;
+  const unsigned cgrid = unsigned((nchunks + 127) / 128);
+  for (int step = 0; step < maxp; step++) {
+    LAUNCH(k_plane_pre, dim3(cgrid), dim3(128), 0, st, ctx, step);
+    const unsigned rgrid = unsigned(std::min<unsigned long long>((total_roots + 255) / 256, 148 * 16));
+    if (total_roots)
+      LAUNCH(k_root_seglen<T>, dim3(rgrid), dim3(256), 0, st, ctx, tree, total_roots);
+    exclusive_scan_u32(ctx.rseg, ctx.rpos, total_roots, d_scan_tmp, st);
+    LAUNCH(k_plane_begin, dim3(cgrid), dim3(128), 0, st, ctx);
+    if (total_roots) {
+      LAUNCH(k_root_emit<T>, dim3(rgrid), dim3(256), 0, st, ctx, tree, total_roots);
+      for (int d = 0; d < max_depth; d++) {
+        LAUNCH(k_expand<T>, dim3(148 * 8), dim3(256), 0, st, ctx, tree, d & 1);
+        LAUNCH(k_front_reset, dim3(1), dim3(32), 0, st, ctx, d & 1);
+      }
+    }
+    LAUNCH(k_plane_end, dim3(1), dim3(1024), 0, st, ctx);
+    rt::d2h(&total_roots, ctx.total_roots, 8, st);
+    rt::sync(st);
+    if (total_roots == 0)
+      continue;  // later planes have no LIS part; k_plane_begin still places LIP / refinement
+    if (total_roots > ctx.cand_cap)
+      throw std::runtime_error("SPECK list overflow");
+    sort_pairs_u64(ctx.ckey, ctx.rkey, ctx.cnode, ctx.rnode, total_roots, kKeyBits, w.sort_tmp.p,
+                   sort_bytes, st);
+  }
+
+  // LIP / refinement emission
+  if (nblk)
+    LAUNCH(k_lipref_emit, dim3(nblk, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, ctx.bases,
+           maxp, nblk);
+
+  rt::d2h(hc.data(), d_chunks, sizeof(ChunkDev) * nchunks, st);
+  unsigned err = 0;
+  rt::d2h(&err, ctx.err, 4, st);
+  rt::sync(st);
+  if (err)
+    throw std::runtime_error("SPECK encoder work-list overflow");
+  for (int c = 0; c < nchunks; c++) {
+    results[c].planes = hc[c].planes;
+    results[c].total_bits = hc[c].total_bits;
+    results[c].payload = hc[c].spk;
+    const unsigned long long pack = std::min(hc[c].total_bits, hc[c].budget);
+    results[c].payload_bytes = size_t((pack + 7) / 8);
+  }
+}
+
+}  // namespace sperr_b200

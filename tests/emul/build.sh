@@ -9,13 +9,17 @@ CXX=/usr/bin/g++
 FLAGS="-std=c++17 -O1 -g -fPIC -ffp-contract=off -DSPERR_EMUL -I$HERE -I$SRC -include $HERE/cuda_emul.h -Wall -Wno-unknown-pragmas -Wno-unused-function"
 OBJS=""
 mkdir -p "$HERE/obj"
+pids=()
 for f in $SRC/*.cu $SRC/*.cpp $HERE/cuda_emul.cpp; do
   o="$HERE/obj/$(basename $f).o"
-  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find $SRC $HERE -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer "$o" 2>/dev/null | head -1)" ]; then
-    $CXX $FLAGS -x c++ -c "$f" -o "$o" &
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find $SRC $HERE $HERE/../../include -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer "$o" 2>/dev/null | head -1)" ]; then
+    ( $CXX $FLAGS -x c++ -c "$f" -o "$o.tmp" 2> "$o.log" && mv "$o.tmp" "$o" || { rm -f "$o"; grep -m8 -E "error" "$o.log" >&2; exit 1; } ) &
+    pids+=($!)
   fi
   OBJS="$OBJS $o"
 done
-wait
+fail=0
+for p in "${pids[@]}"; do wait $p || fail=1; done
+[ $fail = 0 ] || { echo "emul build FAILED" >&2; exit 1; }
 $CXX -shared -o "$HERE/libsperr_emul.so" $OBJS -lpthread
 echo "built $HERE/libsperr_emul.so"
