@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- SPERR 3D hot-path throughput on B200 (BASELINE.json config #2).
+
+Workload: synthetic smooth turbulence-like 1024^3 fp32 field, PWE tolerance 1e-3,
+256^3 chunks (64 chunks). One "step" = compress the volume into a reference-layout SPERR container
+and decompress that container back to fp32. Metric = input GB/s = volume bytes / step time
+(compress-only and decompress-only rates are reported beside it).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 (torchrun, one rank per GPU): weak scaling -- the volume is 1024 x 1024 x (1024 N), each rank
+owns the 64 chunks of its own z-slab; chunk streams are gathered to rank 0 over NCCL.
+--impl reference: the UNMODIFIED reference (oracle/_ref/libsperr_ref.so, OpenMP, all host cores)
+on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GB = 1e9
+TOL = 1e-3
+CHUNK = 256
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic field (same construction as tests/refs.py: synthetic_field), evaluated on the device
+# ---------------------------------------------------------------------------------------------
+
+def mode_table(seed=1234, modes=48):
+    rng = np.random.default_rng(seed)
+    k = rng.uniform(1.0, 32.0, size=(modes, 3))
+    ph = rng.uniform(0.0, 2.0 * np.pi, size=(modes, 3))
+    amp = np.linalg.norm(k, axis=1) ** (-5.0 / 6.0) * rng.standard_normal(modes)
+    return k, ph, amp
+
+
+def field_numpy(dims, origin=(0, 0, 0)):
+    k, ph, amp = mode_table()
+    nx, ny, nz = dims
+    x = (np.arange(nx) + origin[0]) * (2.0 * np.pi / 512.0)
+    y = (np.arange(ny) + origin[1]) * (2.0 * np.pi / 512.0)
+    z = (np.arange(nz) + origin[2]) * (2.0 * np.pi / 512.0)
+    out = np.zeros((nz, ny, nx), dtype=np.float64)
+    for m in range(len(amp)):
+        sx = np.sin(k[m, 0] * x + ph[m, 0])
+        sy = np.sin(k[m, 1] * y + ph[m, 1])
+        s3 = np.sin(k[m, 2] * z + ph[m, 2])
+        out += amp[m] * s3[:, None, None] * sy[None, :, None] * sx[None, None, :]
+    return out.astype(np.float32).reshape(-1)
+
+
+def field_torch(dims, origin, device):
+    import torch
+    k, ph, amp = mode_table()
+    nx, ny, nz = dims
+    f64 = torch.float64
+    x = (torch.arange(nx, device=device, dtype=f64) + origin[0]) * (2.0 * np.pi / 512.0)
+    y = (torch.arange(ny, device=device, dtype=f64) + origin[1]) * (2.0 * np.pi / 512.0)
+    z = (torch.arange(nz, device=device, dtype=f64) + origin[2]) * (2.0 * np.pi / 512.0)
+    out = torch.zeros((nz, ny, nx), device=device, dtype=torch.float32)
+    zb = 64
+    for z0 in range(0, nz, zb):   # slab-wise in fp64, stored as fp32
+        acc = torch.zeros((min(zb, nz - z0), ny, nx), device=device, dtype=f64)
+        for m in range(len(amp)):
+            sx = torch.sin(k[m, 0] * x + ph[m, 0])
+            sy = torch.sin(k[m, 1] * y + ph[m, 1])
+            s3 = torch.sin(k[m, 2] * z[z0:z0 + zb] + ph[m, 2])
+            acc += amp[m] * s3[:, None, None] * sy[None, :, None] * sx[None, None, :]
+        out[z0:z0 + zb] = acc.to(torch.float32)
+    return out.reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------
+
+class Clocks:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.stop = False
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                   timeout=5).stdout.strip().split(",")
+                self.samples.append([s.strip() for s in o])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        sm = [int(s[0]) for s in self.samples if len(s) >= 6 and s[0].isdigit()]
+        mx = [int(s[1]) for s in self.samples if len(s) >= 6 and s[1].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            if len(s) >= 6:
+                for i, n in enumerate(names):
+                    if s[2 + i].lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference built by oracle/Makefile
+# ---------------------------------------------------------------------------------------------
+
+def load_cpu_lib():
+    ref = os.path.join(ROOT, "oracle", "_ref", "libsperr_ref.so")
+    if os.path.exists(ref):
+        return C.CDLL(ref), "reference", "sperr_"
+    port = os.path.join(ROOT, "oracle", "liboracle.so")
+    if not os.path.exists(port):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return C.CDLL(port), "port", "so_"
+
+
+def cpu_roundtrip(lib, prefix, vol, dims, do_decomp=True):
+    """One compress (+ decompress) through the reference C API with all host threads.
+    Returns (t_comp, t_decomp, stream_bytes)."""
+    sz, vp = C.c_size_t, C.c_void_p
+    comp = getattr(lib, prefix + "comp_3d")
+    comp.restype = C.c_int
+    comp.argtypes = [vp, C.c_int] + [sz] * 6 + [C.c_int, C.c_double, sz, C.POINTER(vp), C.POINTER(sz)]
+    dec = getattr(lib, prefix + "decomp_3d")
+    dec.restype = C.c_int
+    dec.argtypes = [vp, sz, C.c_int, sz, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(vp)]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [vp]
+    dst, n = vp(None), sz(0)
+    t0 = time.perf_counter()
+    rc = comp(vol.ctypes.data_as(vp), 1, *dims, CHUNK, CHUNK, CHUNK, 3, TOL, 0, C.byref(dst), C.byref(n))
+    t1 = time.perf_counter()
+    assert rc == 0, rc
+    td = 0.0
+    if do_decomp:
+        dx, dy, dz, out = sz(0), sz(0), sz(0), vp(None)
+        t2 = time.perf_counter()
+        rc = dec(dst, n.value, 1, 0, C.byref(dx), C.byref(dy), C.byref(dz), C.byref(out))
+        td = time.perf_counter() - t2
+        assert rc == 0, rc
+        libc.free(out)
+    libc.free(dst)
+    return t1 - t0, td, n.value
+
+
+def cpu_sample_dims():
+    # bounded sample of the workload: as many 256^3 chunks as host cores (max 32 = half the job),
+    # so that every OpenMP thread has exactly one chunk, like the full 64-chunk job on a big host
+    cores = os.cpu_count() or 1
+    nch = 1
+    while nch * 2 <= min(cores, 32):
+        nch *= 2
+    dims = [CHUNK, CHUNK, CHUNK]
+    a = 0
+    while nch > 1:
+        dims[a] *= 2
+        nch //= 2
+        a = (a + 1) % 3
+    return tuple(dims), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    lib, kind, prefix = load_cpu_lib()
+    dims, cores = cpu_sample_dims()
+    vol = field_numpy(dims)
+    nbytes = vol.size * 4
+    for _ in range(args.warmup_ref):
+        cpu_roundtrip(lib, prefix, vol, dims)
+    tc = td = 0.0
+    for _ in range(args.steps):
+        a, b, slen = cpu_roundtrip(lib, prefix, vol, dims)
+        tc += a
+        td += b
+    step = (tc + td) / args.steps
+    val = nbytes / step / GB
+    sample = "%dx%dx%d fp32 (%d chunks of 256^3) of the 1024^3 field, PWE %g" % (
+        dims + (vol.size // CHUNK ** 3, TOL))
+    print(json.dumps({
+        "impl": "reference", "metric": "compress+decompress input GB/s", "value": val, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup_ref,
+        "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "compress_gbs": nbytes / (tc / args.steps) / GB,
+        "decompress_gbs": nbytes / (td / args.steps) / GB,
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n):
+    return {"workload": "synthetic smooth 1024x1024x%d fp32, PWE tol 1e-3, 256^3 chunks (%d chunks), "
+                        "step = compress + decompress" % (1024 * n, 64 * n),
+            "l2": "inputs (4 GiB per GPU) larger than L2", "chunk": [CHUNK] * 3, "mode": "PWE",
+            "tolerance": TOL}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import sperr_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    L = sperr_b200.load()
+    n = args.size
+    dims = (n, n, n)
+    nbytes = n * n * n * 4
+    vol = field_torch(dims, (0, 0, rank * n), dev)
+    torch.cuda.synchronize()
+    has_decomp = hasattr(L.lib, "sperr_b200_decomp_3d_dev")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_dev():
+        rc, stream = L.compress_3d_dev(vol.data_ptr(), True, dims, (CHUNK,) * 3, 3, TOL)
+        assert rc == 0, rc
+        return stream
+
+    prof_on = L.fn("sperr_b200_prof_enable", None, [C.c_int])
+    prof_dump = L.fn("sperr_b200_prof_dump", C.c_size_t, [C.c_char_p, C.c_size_t])
+
+    for _ in range(args.warmup):
+        stream = step_dev()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with Clocks(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            stream = step_dev()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+
+    # stage profile (separate, untimed pass)
+    prof_on(1)
+    step_dev()
+    buf = C.create_string_buffer(1 << 16)
+    prof_dump(buf, len(buf))
+    prof_on(0)
+    stages = json.loads(buf.value.decode())
+
+    # e2e through the reference-facing C API with host buffers
+    hvol = vol.cpu().pin_memory().numpy() if args.e2e else None
+    e2e = None
+    if hvol is not None:
+        for _ in range(2):
+            rc, s2 = L.compress_3d(hvol, dims, (CHUNK,) * 3, 3, TOL)
+            assert rc == 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rc, s2 = L.compress_3d(hvol, dims, (CHUNK,) * 3, 3, TOL)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.steps
+        e2e = {"value": world * nbytes / dt / GB, "unit": "GB/s", "h2d_bytes_per_step": nbytes,
+               "d2h_bytes_per_step": int(s2.size)}
+
+    if rank == 0:
+        out = {
+            "metric": "compress input GB/s (decoder pending)", "value": world * nbytes / (ms * 1e-3) / GB,
+            "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "stream_bytes": int(stream.size), "bpp": stream.size * 8.0 / (n ** 3),
+            "clocks": clk.summary(), "stages_ms": {k: round(v["ms"], 3) for k, v in stages.items()},
+            "e2e": e2e, "has_decomp": has_decomp,
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--e2e", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

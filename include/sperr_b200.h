@@ -52,6 +52,12 @@ int sperr_b200_comp_3d_dev(const void* d_src, int is_float, size_t dimx, size_t 
                            size_t chunk_x, size_t chunk_y, size_t chunk_z, int mode, double quality,
                            void** dst, size_t* dst_len);
 
+/* Stage profiler: when enabled every stage of the pipelines is bracketed by CUDA events on the
+ * launching stream. prof_dump writes a JSON object {"stage": {"ms": total, "n": ranges}, ...} into
+ * buf (NUL-terminated, truncated to cap) and returns the full length. Enabling clears the totals. */
+void sperr_b200_prof_enable(int on);
+size_t sperr_b200_prof_dump(char* buf, size_t cap);
+
 /* ------------------------------------------------------------------------------------------ */
 /* 3. Stage-level hooks (parity tests)                                                         */
 /* ------------------------------------------------------------------------------------------ */

@@ -1,0 +1,119 @@
+"""ctypes binding of include/sperr_b200.h section 1 (the reference-compatible C API,
+/root/reference/include/SPERR_C_API.h:53-156) and section 2 (device-pointer extensions)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libsperr_b200.so")
+
+MODE_BPP, MODE_PSNR, MODE_PWE = 1, 2, 3
+
+sz = C.c_size_t
+vp = C.c_void_p
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [vp]
+_libc.free.restype = None
+
+
+class Library:
+    """One loaded libsperr_b200.so."""
+
+    def __init__(self, path=SO_PATH):
+        if not os.path.exists(path):
+            raise RuntimeError(
+                "%s is missing: build it with `python -m sperr_b200.build` "
+                "(there is no CPU fallback)" % path)
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.sperr_comp_3d.restype = C.c_int
+        L.sperr_comp_3d.argtypes = [vp, C.c_int] + [sz] * 6 + [C.c_int, C.c_double, sz,
+                                                                C.POINTER(vp), C.POINTER(sz)]
+        L.sperr_decomp_3d.restype = C.c_int
+        L.sperr_decomp_3d.argtypes = [vp, sz, C.c_int, sz, C.POINTER(sz), C.POINTER(sz),
+                                      C.POINTER(sz), C.POINTER(vp)]
+        L.sperr_b200_comp_3d_dev.restype = C.c_int
+        L.sperr_b200_comp_3d_dev.argtypes = [vp, C.c_int] + [sz] * 6 + [C.c_int, C.c_double,
+                                                                         C.POINTER(vp), C.POINTER(sz)]
+        L.sperr_parse_header.restype = None
+        L.sperr_parse_header.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz),
+                                         C.POINTER(C.c_int)]
+
+    # ---- host-buffer API (drop-in semantics) ----
+    def compress_3d(self, vol, dims, chunks, mode, quality, nthreads=0):
+        """vol: flat float32/float64 array, x fastest. Returns (rc, uint8 stream or None)."""
+        vol = np.ascontiguousarray(vol)
+        if vol.dtype not in (np.float32, np.float64):
+            raise TypeError("float32 or float64 input expected")
+        dst, n = vp(None), sz(0)
+        rc = self.lib.sperr_comp_3d(vol.ctypes.data_as(vp), int(vol.dtype == np.float32), *dims,
+                                    *chunks, mode, quality, nthreads, C.byref(dst), C.byref(n))
+        if rc != 0:
+            return rc, None
+        out = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
+        _libc.free(dst)
+        return 0, out
+
+    def decompress_3d(self, stream, output_float=True, nthreads=0):
+        """Returns (rc, flat array or None, (dimx, dimy, dimz) or None)."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        dx, dy, dz, dst = sz(0), sz(0), sz(0), vp(None)
+        rc = self.lib.sperr_decomp_3d(stream.ctypes.data_as(vp), stream.size, int(output_float),
+                                      nthreads, C.byref(dx), C.byref(dy), C.byref(dz), C.byref(dst))
+        if rc != 0:
+            return rc, None, None
+        n = dx.value * dy.value * dz.value
+        ct = C.c_float if output_float else C.c_double
+        out = np.ctypeslib.as_array(C.cast(dst, C.POINTER(ct)), shape=(n,)).copy()
+        _libc.free(dst)
+        return 0, out, (dx.value, dy.value, dz.value)
+
+    # ---- device-pointer extensions ----
+    def compress_3d_dev(self, d_ptr, is_float, dims, chunks, mode, quality):
+        """d_ptr: integer device address of the volume. Returns (rc, uint8 stream or None)."""
+        dst, n = vp(None), sz(0)
+        rc = self.lib.sperr_b200_comp_3d_dev(vp(d_ptr), int(is_float), *dims, *chunks, mode,
+                                             quality, C.byref(dst), C.byref(n))
+        if rc != 0:
+            return rc, None
+        out = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
+        _libc.free(dst)
+        return 0, out
+
+    def parse_header(self, stream):
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        dx, dy, dz, isf = sz(0), sz(0), sz(0), C.c_int(0)
+        self.lib.sperr_parse_header(stream.ctypes.data_as(vp), C.byref(dx), C.byref(dy),
+                                    C.byref(dz), C.byref(isf))
+        return (dx.value, dy.value, dz.value), bool(isf.value)
+
+    def fn(self, name, restype, argtypes):
+        f = getattr(self.lib, name)
+        f.restype = restype
+        f.argtypes = argtypes
+        return f
+
+
+_default = None
+
+
+def load(path=SO_PATH):
+    global _default
+    if _default is None or _default.path != path:
+        _default = Library(path)
+    return _default
+
+
+def compress_3d(vol, dims, chunks, mode, quality):
+    return load().compress_3d(vol, dims, chunks, mode, quality)
+
+
+def decompress_3d(stream, output_float=True):
+    return load().decompress_3d(stream, output_float)
+
+
+def parse_header(stream):
+    return load().parse_header(stream)

@@ -1,0 +1,80 @@
+"""Builds sperr_b200/libsperr_b200.so (the product library) in-tree with nvcc for sm_100a.
+
+    python -m sperr_b200.build [--force]
+
+Every .cu under csrc/ is compiled with ``-gencode arch=compute_100a,code=sm_100a -fmad=false``
+(-fmad=false is part of the parity contract: the fp64 lifting / quantiser arithmetic must round
+every multiply and add separately, like the reference built with -ffp-contract=off).
+"""
+import concurrent.futures as cf
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
+OUT = os.path.join(HERE, "libsperr_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr",
+    "-Xptxas", "-v" if os.environ.get("SPERR_B200_PTXAS_V") else "-O3",
+]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if c and os.path.exists(c):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def _sources():
+    srcs = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
+    return [os.path.join(CSRC, f) for f in srcs]
+
+
+def _headers_mtime():
+    m = 0.0
+    for d in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
+        for f in os.listdir(d):
+            if f.endswith((".h", ".cuh")):
+                m = max(m, os.path.getmtime(os.path.join(d, f)))
+    return max(m, os.path.getmtime(os.path.abspath(__file__)))
+
+
+def _compile(nvcc, src, obj):
+    cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu", "-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout[-4000:], r.stderr[-4000:]))
+    return r.stderr
+
+
+def build(force=False, verbose=False):
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    hm = _headers_mtime()
+    jobs, objs = [], []
+    for s in _sources():
+        o = os.path.join(OBJ, os.path.basename(s) + ".o")
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hm):
+            jobs.append((s, o))
+    if jobs:
+        with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            for log in ex.map(lambda j: _compile(nvcc, j[0], j[1]), jobs):
+                if verbose and log:
+                    sys.stderr.write(log)
+    if jobs or not os.path.exists(OUT):
+        cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stderr[-4000:])
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -143,6 +143,45 @@ int sperr_b200_comp_3d_dev(const void* d_src, int is_float, size_t dimx, size_t 
   });
 }
 
+int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nthreads, size_t* dimx,
+                    size_t* dimy, size_t* dimz, void** dst)
+{
+  (void)src; (void)src_len; (void)output_float; (void)nthreads; (void)dimx; (void)dimy; (void)dimz;
+  if (*dst != nullptr)
+    return 1;
+  return -1;  // decoder lands in the next commit
+}
+
+void sperr_b200_prof_enable(int on)
+{
+  rt::prof().on = on != 0;
+  if (on) {
+    rt::prof().acc.clear();
+    rt::prof().open.clear();
+  }
+}
+
+size_t sperr_b200_prof_dump(char* buf, size_t cap)
+{
+  rt::prof_collect();
+  std::string s = "{";
+  bool first = true;
+  for (auto& kv : rt::prof().acc) {
+    char tmp[256];
+    std::snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"n\": %ld}", first ? "" : ", ",
+                  kv.first.c_str(), kv.second.first, kv.second.second);
+    s += tmp;
+    first = false;
+  }
+  s += "}";
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, s.size());
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return s.size();
+}
+
 void sperr_parse_header(const void* src, size_t* dimx, size_t* dimy, size_t* dimz, int* is_float)
 {
   const uint8_t* p = static_cast<const uint8_t*>(src);

@@ -163,9 +163,15 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   not_const_.reserve(nc * 4);
   rt::h2d(nstrides_.p, ns.data(), nc * 4, st);
   rt::dset(not_const_.p, 0, nc * 4, st);
-  launch_stats(src, b_.dev(), nc, stride_mean_.as<double>(), max_strides, nstrides_.as<unsigned>(),
-               not_const_.as<unsigned>(), mode == kModePSNR, st);
-  launch_gather(src, b_.dev(), nc, b_.max_n, st);
+  {
+    rt::ProfScope ps("c.stats", st);
+    launch_stats(src, b_.dev(), nc, stride_mean_.as<double>(), max_strides, nstrides_.as<unsigned>(),
+                 not_const_.as<unsigned>(), mode == kModePSNR, st);
+  }
+  {
+    rt::ProfScope ps("c.gather", st);
+    launch_gather(src, b_.dev(), nc, b_.max_n, st);
+  }
 
   // ---- wavelet transform, one launch series per distinct chunk shape ----
   std::vector<std::vector<int>> groups(b_.shapes.size());
@@ -181,6 +187,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   rt::h2d(ids_.p, flat.data(), flat.size() * 4, st);
   rt::sync(st);
   auto transform = [&](bool inverse) {
+    rt::ProfScope ps(inverse ? "c.idwt" : "c.dwt", st);
     for (size_t s = 0; s < groups.size(); s++) {
       if (groups[s].empty())
         continue;
@@ -190,7 +197,10 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     }
   };
   transform(false);
-  launch_absmax(b_.dev(), nc, b_.max_n, st);
+  {
+    rt::ProfScope ps("c.absmax", st);
+    launch_absmax(b_.dev(), nc, b_.max_n, st);
+  }
   b_.pull(st);
 
   // ---- quantisation step per chunk (SPECK_FLT::m_estimate_q, src/SPECK_FLT.cpp:268-309) ----
@@ -271,16 +281,27 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
       b_.make_wide(st);
       b_.push(st);
     }
-    launch_quantize(b_.dev(), nc, b_.max_n, st);
+    {
+      rt::ProfScope ps("c.quantize", st);
+      launch_quantize(b_.dev(), nc, b_.max_n, st);
+    }
     if (mode == kModePWE) {
-      launch_inv_quantize(b_.dev(), nc, b_.max_n, st);
+      {
+        rt::ProfScope ps("c.inv_quantize", st);
+        launch_inv_quantize(b_.dev(), nc, b_.max_n, st);
+      }
       transform(true);
-      out_.detect(src, b_.dev(), nc, b_.max_n, quality, st);
+      {
+        rt::ProfScope ps("c.outlier_detect", st);
+        out_.detect(src, b_.dev(), nc, b_.max_n, quality, st);
+      }
       std::vector<unsigned long long> tl(nc);
       for (int c = 0; c < nc; c++)
         tl[c] = b_.h[c].n;
+      rt::ProfScope ps("c.outlier_encode", st);
       out_.encode(tl, quality, out_res_, st);
     }
+    rt::ProfScope ps("c.speck3d", st);
     enc.encode(b_.dev(), b_.h, b_.dev_shapes(), b_.shapes, res, st);
   };
   quantize_and_encode(enc_, spk_res_);

@@ -8,8 +8,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #ifdef SPERR_EMUL
 #include "cuda_emul.h"
@@ -108,6 +110,66 @@ inline void* hmalloc_pinned(size_t n) { return std::malloc(n ? n : 1); }
 inline void hfree_pinned(void* p) { std::free(p); }
 inline bool is_device_ptr(const void*) { return false; }
 #endif
+
+// ---- stage profiler: CUDA-event ranges on the launching stream, off unless enabled ----
+struct ProfEntry {
+  const char* name;
+#ifndef SPERR_EMUL
+  cudaEvent_t e0, e1;
+#endif
+};
+struct ProfState {
+  bool on = false;
+  std::vector<ProfEntry> open;                       // recorded, not yet resolved
+  std::map<std::string, std::pair<double, long>> acc;  // name -> (ms, ranges)
+};
+inline ProfState& prof()
+{
+  static ProfState s;
+  return s;
+}
+struct ProfScope {
+#ifndef SPERR_EMUL
+  cudaStream_t st;
+  ProfEntry e;
+  bool live;
+  ProfScope(const char* name, cudaStream_t s) : st(s), live(prof().on)
+  {
+    if (!live)
+      return;
+    e.name = name;
+    cudaEventCreate(&e.e0);
+    cudaEventCreate(&e.e1);
+    cudaEventRecord(e.e0, st);
+  }
+  ~ProfScope()
+  {
+    if (!live)
+      return;
+    cudaEventRecord(e.e1, st);
+    prof().open.push_back(e);
+  }
+#else
+  ProfScope(const char*, cudaStream_t) {}
+#endif
+};
+// Resolves all recorded ranges (synchronises) and adds them to the accumulators.
+inline void prof_collect()
+{
+#ifndef SPERR_EMUL
+  for (auto& e : prof().open) {
+    cudaEventSynchronize(e.e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e.e0, e.e1);
+    auto& a = prof().acc[e.name];
+    a.first += ms;
+    a.second += 1;
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+#endif
+  prof().open.clear();
+}
 
 // RAII device buffer
 struct DBuf {

@@ -294,6 +294,7 @@ void Speck3DEncoder::encode(ChunkDev* d_chunks, const std::vector<ChunkDev>& h_c
   }
   size_t id_off = 0;
   int max_depth = 1;
+  rt::ProfScope* ps_pyr = new rt::ProfScope("enc.pyramid", st);
   for (size_t si = 0; si < shapes.size(); si++) {
     const auto& g = groups[si];
     if (g.empty())
@@ -315,6 +316,7 @@ void Speck3DEncoder::encode(ChunkDev* d_chunks, const std::vector<ChunkDev>& h_c
              d_chunks, d_shapes, d_ids, l, check_real);
     }
   }
+  delete ps_pyr;
   Tree3D::Data tree{d_shapes};
   auto bound = [&](int c, const ChunkDev& hc) {
     const ShapeHeader& h = shapes[h_chunks[c].shape].h;

@@ -561,6 +561,7 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   ctx.bases = ctx.sizes + (size_t)nchunks * 2 * maxp;
   unsigned* d_counts = w.counts.as<unsigned>();
   if (nblk) {
+    rt::ProfScope ps("enc.lipref_count", st);
     LAUNCH(k_lipref_count, dim3(nblk, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, maxp, nblk);
     LAUNCH(k_lipref_scan, dim3(2 * maxp, nchunks), dim3(1024), 0, st, d_chunks, d_counts, ctx.sizes,
            maxp, nblk);
@@ -570,6 +571,7 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   void* d_scan_tmp = w.scan_tmp.p;
   const unsigned cgrid = unsigned((nchunks + 127) / 128);
   for (int step = 0; step < maxp; step++) {
+    rt::ProfScope ps("enc.plane_loop", st);
     LAUNCH(k_plane_pre, dim3(cgrid), dim3(128), 0, st, ctx, step);
     const unsigned rgrid = unsigned(std::min<unsigned long long>((total_roots + 255) / 256, 148 * 16));
     if (total_roots)
@@ -595,6 +597,7 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   }
 
   // LIP / refinement emission
+  rt::ProfScope ps_emit("enc.lipref_emit", st);
   if (nblk)
     LAUNCH(k_lipref_emit, dim3(nblk, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, ctx.bases,
            maxp, nblk);

@@ -1,0 +1,61 @@
+"""Shared parity cases: the same checks run against the CUDA library on a B200 (test_gpu_*.py,
+marked gpu) and -- small sizes only -- against the CPU SIMT emulation of the same kernels
+(test_emul_*.py), which is a container-side debugging aid and never a product path."""
+import numpy as np
+
+import refs
+
+# (fixture, dims, chunk dims, mode, quality)
+COMP3D_SMALL = [
+    ("wmag17.float", (17, 17, 17), (17, 17, 17), 3, 0.3),
+    ("wmag17.float", (17, 17, 17), (8, 8, 8), 2, 100.0),       # 8 ragged chunks
+    ("wmag17.float", (17, 17, 17), (17, 17, 17), 1, 2.0),
+    ("wmag17.float", (17, 17, 17), (17, 17, 17), 1, 40.0),     # fixed-rate high-precision retry
+    ("wmag16.float", (16, 16, 16), (16, 16, 16), 2, 60.0),
+    ("const32x20x16.float", (32, 20, 16), (16, 16, 16), 3, 1e-3),   # constant chunks: 17-byte streams
+    ("vorticity.128_128_41", (128, 128, 41), (64, 64, 41), 3, 1e-5),
+    ("vorticity.128_128_41", (128, 128, 41), (128, 128, 41), 3, 1e-5),   # wavelet-packet (non-dyadic)
+]
+
+COMP3D_GPU = COMP3D_SMALL + [
+    ("vorticity.128_128_41", (128, 128, 41), (64, 64, 41), 3, 2.9e-9),
+    ("vorticity.128_128_41", (128, 128, 41), (64, 64, 41), 3, 1.5e-7),
+    ("vorticity.128_128_41", (128, 128, 41), (64, 64, 64), 2, 88.0),
+    ("vorticity.128_128_41", (128, 128, 41), (64, 64, 64), 2, 125.0),
+    ("vorticity.128_128_41", (128, 128, 41), (64, 64, 41), 1, 4.0),
+    ("vorticity.128_128_41", (128, 128, 41), (64, 64, 41), 1, 20.0),
+    ("vorticity.128_128_41", (128, 128, 41), (64, 70, 20), 3, 6.7e-6),   # ragged
+]
+
+
+def fnv1a64(b):
+    h = 0xcbf29ce484222325
+    for x in bytes(b):
+        h = ((h ^ x) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+def check_comp3d(lib, oracle, case, f64=False):
+    name, dims, chunks, mode, q = case
+    v = refs.load_test_data(name)
+    assert v is not None and v.size == dims[0] * dims[1] * dims[2]
+    if f64:
+        v = v.astype(np.float64)
+    rc, got = lib.comp_3d(v, dims, chunks, mode, q)
+    rc2, exp = oracle.comp_3d(v, dims, chunks, mode, q)
+    assert rc == rc2 == 0
+    assert got.size == exp.size, (got.size, exp.size)
+    assert np.array_equal(got, exp), "first diff at byte %d" % int(np.argmax(got != exp))
+    return got
+
+
+def check_decomp3d(lib, oracle, stream, output_float=True):
+    rc, got, dims = lib.decomp_3d(stream, output_float)
+    rc2, exp, dims2 = oracle.decomp_3d(stream, output_float)
+    assert rc == rc2 == 0, (rc, rc2)
+    assert dims == dims2
+    # bit-identical decoded values
+    it = np.uint32 if output_float else np.uint64
+    assert np.array_equal(got.view(it), exp.view(it)), "%d values differ" % int(
+        np.count_nonzero(got.view(it) != exp.view(it)))
+    return got
