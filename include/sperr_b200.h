@@ -52,6 +52,13 @@ int sperr_b200_comp_3d_dev(const void* d_src, int is_float, size_t dimx, size_t 
                            size_t chunk_x, size_t chunk_y, size_t chunk_z, int mode, double quality,
                            void** dst, size_t* dst_len);
 
+/* Decompresses a reference-layout 3D container. `h_src` is the container in HOST memory (headers are
+ * parsed on the host); `d_src` is the same bytes in DEVICE memory, or NULL to have them uploaded.
+ * The decoded volume (float when output_float != 0, else double) is written to the DEVICE buffer
+ * d_dst, which must hold dimx*dimy*dimz values (see sperr_parse_header). */
+int sperr_b200_decomp_3d_dev(const void* h_src, const void* d_src, size_t src_len, int output_float,
+                             size_t* dimx, size_t* dimy, size_t* dimz, void* d_dst);
+
 /* Stage profiler: when enabled every stage of the pipelines is bracketed by CUDA events on the
  * launching stream. prof_dump writes a JSON object {"stage": {"ms": total, "n": ranges}, ...} into
  * buf (NUL-terminated, truncated to cap) and returns the full length. Enabling clears the totals. */

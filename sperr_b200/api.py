@@ -38,6 +38,9 @@ class Library:
         L.sperr_b200_comp_3d_dev.restype = C.c_int
         L.sperr_b200_comp_3d_dev.argtypes = [vp, C.c_int] + [sz] * 6 + [C.c_int, C.c_double,
                                                                          C.POINTER(vp), C.POINTER(sz)]
+        L.sperr_b200_decomp_3d_dev.restype = C.c_int
+        L.sperr_b200_decomp_3d_dev.argtypes = [vp, vp, sz, C.c_int, C.POINTER(sz), C.POINTER(sz),
+                                               C.POINTER(sz), vp]
         L.sperr_parse_header.restype = None
         L.sperr_parse_header.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz),
                                          C.POINTER(C.c_int)]
@@ -82,6 +85,15 @@ class Library:
         out = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
         _libc.free(dst)
         return 0, out
+
+    def decompress_3d_dev(self, stream, d_stream_ptr, d_out_ptr, output_float=True):
+        """stream: the container in host memory (uint8 array); d_stream_ptr: the same bytes in device
+        memory (0 = upload); d_out_ptr: device buffer for the decoded volume. Returns (rc, dims)."""
+        dx, dy, dz = sz(0), sz(0), sz(0)
+        rc = self.lib.sperr_b200_decomp_3d_dev(stream.ctypes.data_as(vp), vp(d_stream_ptr or None),
+                                               stream.size, int(output_float), C.byref(dx),
+                                               C.byref(dy), C.byref(dz), vp(d_out_ptr))
+        return rc, (dx.value, dy.value, dz.value)
 
     def parse_header(self, stream):
         stream = np.ascontiguousarray(stream, dtype=np.uint8)

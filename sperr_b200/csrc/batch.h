@@ -14,6 +14,7 @@ struct BatchBuffers {
   rt::DBuf d_chunks, d_shapes, shape_mem;
   rt::DBuf coef, mag, signs, pleaf, cmap, pyr_p, pyr_d;
   size_t max_n = 0;
+  size_t sign_words = 0, mag_elems = 0;   // totals over the batch (padded)
   bool wide = false;
 
   ChunkDev* dev() const { return d_chunks.as<ChunkDev>(); }
@@ -21,8 +22,9 @@ struct BatchBuffers {
   int size() const { return int(h.size()); }
 
   // Lays out every per-chunk array. `need_coef`: fp64 buffer; `need_speck`: integer-coder arrays.
+  // `need_enc`: also the encoder-only maps (msb positions, creation planes, significance pyramid).
   void setup(const std::vector<Chunk>& chunks, bool need_coef, bool need_speck, bool wide_mag,
-             cudaStream_t st)
+             cudaStream_t st, bool need_enc = true)
   {
     const int nc = int(chunks.size());
     h.assign(nc, ChunkDev());
@@ -59,11 +61,15 @@ struct BatchBuffers {
     if (need_speck) {
       mag.reserve(tot_n * (wide_mag ? 8 : 4));
       signs.reserve(tot_words * 4);
-      pleaf.reserve(tot_n);
-      cmap.reserve(tot_n);
-      pyr_p.reserve(tot_pyr);
-      pyr_d.reserve(tot_pyr * 4);
+      if (need_enc) {
+        pleaf.reserve(tot_n);
+        cmap.reserve(tot_n);
+        pyr_p.reserve(tot_pyr);
+        pyr_d.reserve(tot_pyr * 4);
+      }
     }
+    sign_words = tot_words;
+    mag_elems = tot_n;
     size_t on = 0, ow = 0, op = 0;
     for (int c = 0; c < nc; c++) {
       ChunkDev& d = h[c];
@@ -72,16 +78,18 @@ struct BatchBuffers {
       if (need_speck) {
         d.mag = mag.as<unsigned char>() + on * (wide_mag ? 8 : 4);
         d.signs = signs.as<uint32_t>() + ow;
-        d.pleaf = pleaf.as<int8_t>() + on;
-        d.cmap = cmap.as<int8_t>() + on;
-        d.pyr_p = pyr_p.as<int8_t>() + op;
-        d.pyr_d = pyr_d.as<uint32_t>() + op;
+        if (need_enc) {
+          d.pleaf = pleaf.as<int8_t>() + on;
+          d.cmap = cmap.as<int8_t>() + on;
+          d.pyr_p = pyr_p.as<int8_t>() + op;
+          d.pyr_d = pyr_d.as<uint32_t>() + op;
+        }
       }
       on += (d.n + 63) & ~size_t(63);
       ow += (d.n + 31) / 32 + 2;
       op += shapes[d.shape].h.pyr_nodes + 64;
     }
-    if (need_speck)
+    if (need_speck && need_enc)
       rt::dset(cmap.p, 0xFF, tot_n, st);
     upload_shapes(st);
     d_chunks.reserve(sizeof(ChunkDev) * nc);

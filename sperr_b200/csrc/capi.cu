@@ -100,6 +100,72 @@ int comp_3d_device(const void* d_src, int is_float, size_t dimx, size_t dimy, si
   return 0;
 }
 
+struct ContainerInfo {
+  size_t vol[3], cd[3];
+  std::vector<Chunk> chunks;
+  std::vector<ChunkStream> cs;
+};
+
+// SPERR3D_Stream_Tools::get_stream_header (src/SPERR3D_Stream_Tools.cpp:46-105) and the checks of
+// SPERR3D_OMP_D::use_bitstream (src/SPERR3D_OMP_D.cpp:23-49): version, 3D flag, total length.
+bool parse_container(const uint8_t* p, size_t len, ContainerInfo& ci)
+{
+  if (!p || len < 14)
+    return false;
+  if (p[0] != 0)  // SPERR_VERSION_MAJOR
+    return false;
+  if (!(p[1] & 0x40))
+    return false;
+  const bool multi = (p[1] & 0x10) != 0;
+  uint32_t v3[3];
+  std::memcpy(v3, p + 2, 12);
+  size_t pos = 14;
+  for (int i = 0; i < 3; i++)
+    ci.vol[i] = ci.cd[i] = v3[i];
+  if (multi) {
+    if (len < 20)
+      return false;
+    uint16_t c3[3];
+    std::memcpy(c3, p + 14, 6);
+    for (int i = 0; i < 3; i++)
+      ci.cd[i] = c3[i];
+    pos = 20;
+  }
+  for (int i = 0; i < 3; i++)
+    if (ci.vol[i] == 0 || ci.cd[i] == 0)
+      return false;
+  ci.chunks = chunk_volume(ci.vol, ci.cd);
+  const size_t nchunks = ci.chunks.size();
+  if (len < pos + 4 * nchunks)
+    return false;
+  ci.cs.resize(nchunks);
+  size_t off = pos + 4 * nchunks;
+  for (size_t i = 0; i < nchunks; i++) {
+    uint32_t l;
+    std::memcpy(&l, p + pos + 4 * i, 4);
+    ci.cs[i].off = off;
+    ci.cs[i].len = l;
+    off += l;
+  }
+  if (off != len)
+    return false;
+  for (auto& c : ci.chunks)
+    if (c.nelem() >= (1ull << 31))
+      return false;
+  return true;
+}
+
+Decompressor* g_decomp = nullptr;
+
+void decomp_3d_device(const uint8_t* h_stream, const uint8_t* d_stream, const ContainerInfo& ci,
+                      int output_float, void* d_dst, cudaStream_t st)
+{
+  if (!g_decomp)
+    g_decomp = new Decompressor();
+  SrcVol dv{d_dst, output_float, ci.vol[0], ci.vol[1]};
+  g_decomp->decompress(h_stream, d_stream, ci.chunks, ci.cs, dv, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -146,10 +212,58 @@ int sperr_b200_comp_3d_dev(const void* d_src, int is_float, size_t dimx, size_t 
 int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nthreads, size_t* dimx,
                     size_t* dimy, size_t* dimz, void** dst)
 {
-  (void)src; (void)src_len; (void)output_float; (void)nthreads; (void)dimx; (void)dimy; (void)dimz;
+  (void)nthreads;
   if (*dst != nullptr)
     return 1;
-  return -1;  // decoder lands in the next commit
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return guarded([&] {
+    cudaStream_t st = 0;
+    ContainerInfo ci;
+    if (!parse_container(static_cast<const uint8_t*>(src), src_len, ci))
+      return -1;
+    rt::DBuf d_stream(src_len);
+    rt::h2d(d_stream.p, src, src_len, st);
+    const size_t total = ci.vol[0] * ci.vol[1] * ci.vol[2];
+    const size_t esz = output_float ? 4 : 8;
+    rt::DBuf d_out(total * esz);
+    decomp_3d_device(static_cast<const uint8_t*>(src), d_stream.as<uint8_t>(), ci, output_float,
+                     d_out.p, st);
+    void* o = std::malloc(total * esz);
+    if (!o)
+      return -1;
+    rt::d2h(o, d_out.p, total * esz, st);
+    rt::sync(st);
+    *dimx = ci.vol[0];
+    *dimy = ci.vol[1];
+    *dimz = ci.vol[2];
+    *dst = o;
+    return 0;
+  });
+}
+
+int sperr_b200_decomp_3d_dev(const void* h_src, const void* d_src, size_t src_len, int output_float,
+                             size_t* dimx, size_t* dimy, size_t* dimz, void* d_dst)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return guarded([&] {
+    cudaStream_t st = 0;
+    ContainerInfo ci;
+    if (!parse_container(static_cast<const uint8_t*>(h_src), src_len, ci))
+      return -1;
+    rt::DBuf tmp;
+    const uint8_t* ds = static_cast<const uint8_t*>(d_src);
+    if (!ds) {
+      tmp.alloc(src_len);
+      rt::h2d(tmp.p, h_src, src_len, st);
+      ds = tmp.as<uint8_t>();
+    }
+    decomp_3d_device(static_cast<const uint8_t*>(h_src), ds, ci, output_float, d_dst, st);
+    rt::sync(st);
+    *dimx = ci.vol[0];
+    *dimy = ci.vol[1];
+    *dimz = ci.vol[2];
+    return 0;
+  });
 }
 
 void sperr_b200_prof_enable(int on)

@@ -326,6 +326,33 @@ ShapeTables build_shape(uint32_t nx, uint32_t ny, uint32_t nz)
   }
   h.pyr_nodes = off;
   h.set_nodes = off;
+
+  // ---- per-list capacity: histogram of the LIS index over all pyramid nodes ----
+  if (h.nlis > kMaxLis)
+    throw std::runtime_error("too many LIS lists");
+  std::vector<unsigned long long> cap(kMaxLis, 0);
+  for (int i = 0; i < h.nlevels; i++) {
+    if (i == h.leaf_level)
+      continue;
+    const LevelDesc& l = h.lv[i];
+    const int dd[3] = {l.dx, l.dy, l.dz};
+    std::vector<unsigned long long> hist[3];
+    for (int a = 0; a < 3; a++) {
+      hist[a].assign(kMaxAxisDepth + 2, 0);
+      for (uint8_t v : ab[a].lev[dd[a]])
+        hist[a][v]++;
+    }
+    for (int x = 0; x <= kMaxAxisDepth; x++)
+      for (int y = 0; y <= kMaxAxisDepth && hist[0][x]; y++)
+        for (int z = 0; z <= kMaxAxisDepth && hist[1][y]; z++)
+          if (hist[2][z] && x + y + z < kMaxLis)
+            cap[x + y + z] += hist[0][x] * hist[1][y] * hist[2][z];
+  }
+  for (int r = 0; r < h.nroots; r++)
+    cap[h.roots[r].lis] += 1;  // the initial sets (the root of chain 0 is not a pyramid child)
+  h.lis_off[0] = 0;
+  for (int l = 0; l < kMaxLis; l++)
+    h.lis_off[l + 1] = h.lis_off[l] + cap[l];
   return t;
 }
 

@@ -45,6 +45,7 @@ constexpr int kMaxAxisDepth = 17;  // dims <= 65535
 constexpr int kMaxLevels = 96;
 constexpr int kMaxRoots = 64;
 constexpr int kMaxGroups = 16;
+constexpr int kMaxLis = 64;
 
 struct AxisTab {
   int D;                        // deepest depth (all intervals have length 1)
@@ -89,6 +90,9 @@ struct ShapeHeader {
   int nlis;                       // number of LIS lists
   unsigned long long pyr_nodes;   // total nodes over all non-leaf levels (pyramid array length)
   unsigned long long set_nodes;   // upper bound on the number of sets (nodes with > 1 element)
+  // decoder list storage: list l may hold up to lis_off[l + 1] - lis_off[l] sets (every node of
+  // the pyramid whose LIS index is l)
+  unsigned long long lis_off[kMaxLis + 1];
 };
 
 struct ShapeTables {

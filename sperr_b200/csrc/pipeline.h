@@ -6,6 +6,7 @@
 #include "batch.h"
 #include "outlier.h"
 #include "speck.h"
+#include "speck_dec.h"
 
 namespace sperr_b200 {
 
@@ -31,6 +32,25 @@ class Compressor {
   rt::DBuf stride_mean_, nstrides_, not_const_, ids_, mse_ids_, mse_q_, mse_part_, mse_out_;
   // results of the last batch
   std::vector<EncResult> spk_res_, out_res_;
+};
+
+struct ChunkStream {   // where a chunk's stream sits inside the container
+  size_t off, len;
+};
+
+class Decompressor {
+ public:
+  // Decodes `chunks` (streams at h_stream + cs[i].off; d_stream is the same container in device
+  // memory) into the device-resident volume `dst`. Throws on malformed input.
+  void decompress(const uint8_t* h_stream, const uint8_t* d_stream, const std::vector<Chunk>& chunks,
+                  const std::vector<ChunkStream>& cs, const SrcVol& dst, cudaStream_t st);
+
+ private:
+  void run_batch(const uint8_t* h_stream, const uint8_t* d_stream, const std::vector<Chunk>& chunks,
+                 const ChunkStream* cs, const SrcVol& dst, cudaStream_t st);
+  BatchBuffers b_;
+  DecWork w3_, w1_;
+  rt::DBuf ids_, lis_off1_, omag_, osigns_, tols_;
 };
 
 // Largest number of chunks processed at once (bounded by the list-key layout and by memory).

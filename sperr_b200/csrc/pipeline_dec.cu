@@ -1,0 +1,265 @@
+// Chunk-batch decompression: the GPU counterpart of SPERR3D_OMP_D's per-chunk loop
+// (/root/reference/src/SPERR3D_OMP_D.cpp:51-135) with SPECK_FLT::use_bitstream / decompress
+// (src/SPECK_FLT.cpp:27-109, 543-606) inside.
+#include "pipeline.h"
+
+namespace sperr_b200 {
+
+namespace {
+
+// Device footprint per value while decoding: fp64 buffer 8, magnitudes 4 (+4 for outliers),
+// masks ~1, lists ~1.2.
+size_t pick_dec_batch(const std::vector<Chunk>& chunks, size_t first)
+{
+  size_t free_b = size_t(64) << 30, total_b = 0;
+#ifndef SPERR_EMUL
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+    free_b = size_t(64) << 30;
+#endif
+  (void)total_b;
+  const double budget = double(free_b) * 0.7;
+  double used = 0;
+  size_t n = 0;
+  while (first + n < chunks.size() && n < 1024) {
+    const double need = double(chunks[first + n].nelem()) * 24.0 + (16 << 20);
+    if (n > 0 && used + need > budget)
+      break;
+    used += need;
+    n++;
+  }
+  return std::max<size_t>(n, 1);
+}
+
+}  // namespace
+
+void Decompressor::decompress(const uint8_t* h_stream, const uint8_t* d_stream,
+                              const std::vector<Chunk>& chunks, const std::vector<ChunkStream>& cs,
+                              const SrcVol& dst, cudaStream_t st)
+{
+  size_t first = 0;
+  while (first < chunks.size()) {
+    const size_t nb = pick_dec_batch(chunks, first);
+    std::vector<Chunk> sub(chunks.begin() + first, chunks.begin() + first + nb);
+    run_batch(h_stream, d_stream, sub, cs.data() + first, dst, st);
+    first += nb;
+  }
+}
+
+void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
+                             const std::vector<Chunk>& chunks, const ChunkStream* cs,
+                             const SrcVol& dst, cudaStream_t st)
+{
+  const int nc = int(chunks.size());
+
+  // ---- parse the per-chunk headers (SPECK_FLT::use_bitstream) ----
+  struct Parsed {
+    bool is_const = false;
+    double mean = 0, q = 0, cval = 0;
+    int planes = 0;
+    unsigned long long total_bits = 0;
+    size_t spk_off = 0, spk_bytes = 0;     // payload (after the 9-byte header), container offsets
+    bool has_out = false;
+    int oplanes = 0;
+    unsigned long long ototal = 0;
+    size_t out_off = 0, out_bytes = 0;
+  };
+  std::vector<Parsed> ps(nc);
+  bool any_wide = false, any_out = false, any_owide = false;
+  for (int c = 0; c < nc; c++) {
+    const uint8_t* p = h_stream + cs[c].off;
+    const size_t len = cs[c].len;
+    Parsed& P = ps[c];
+    if (len < 17)
+      throw std::runtime_error("chunk stream shorter than the conditioner header");
+    if (p[0] & 0x01) {  // constant field: Conditioner::inverse_condition, src/Conditioner.cpp:66-80
+      if (len != 17)
+        throw std::runtime_error("constant chunk with trailing bytes");
+      P.is_const = true;
+      std::memcpy(&P.cval, p + 9, 8);
+      continue;
+    }
+    std::memcpy(&P.mean, p + 1, 8);
+    std::memcpy(&P.q, p + 9, 8);
+    size_t remaining = len - 17;
+    if (remaining < 9)
+      throw std::runtime_error("chunk stream without a SPECK header");
+    const uint8_t* sp = p + 17;
+    P.planes = sp[0];
+    std::memcpy(&P.total_bits, sp + 1, 8);
+    if (P.total_bits > (1ull << 48))
+      throw std::runtime_error("implausible SPECK stream length");
+    const size_t full = 9 + size_t((P.total_bits + 7) / 8);
+    const size_t speck_len = std::min(full, remaining);
+    P.spk_off = cs[c].off + 17 + 9;
+    P.spk_bytes = speck_len - 9;
+    any_wide |= P.planes > 32;
+    size_t pos = 17 + speck_len;
+    if (pos < len) {
+      remaining = len - pos;
+      if (remaining >= 9) {
+        const uint8_t* op = p + pos;
+        unsigned long long nb;
+        std::memcpy(&nb, op + 1, 8);
+        const size_t ofull = nb > (1ull << 48) ? 0 : 9 + size_t((nb + 7) / 8);
+        if (remaining == ofull) {
+          P.has_out = true;
+          P.oplanes = op[0];
+          P.ototal = nb;
+          P.out_off = cs[c].off + pos + 9;
+          P.out_bytes = ofull - 9;
+          any_out = true;
+          any_owide |= P.oplanes > 32;
+        }
+      }
+    }
+  }
+
+  b_.setup(chunks, true, true, any_wide, st, false);
+  for (int c = 0; c < nc; c++) {
+    ChunkDev& d = b_.h[c];
+    d.is_const = ps[c].is_const ? 1 : 0;
+    d.first_val = ps[c].cval;
+    d.mean = ps[c].mean;
+    d.q = ps[c].q;
+    d.wide = any_wide ? 1 : 0;
+  }
+  b_.push(st);
+
+  // ---- SPECK3D decode into (mag, signs) ----
+  {
+    rt::ProfScope pz("d.clear", st);
+    rt::dset(b_.mag.p, 0, b_.mag_elems * (any_wide ? 8 : 4), st);
+    rt::dset(b_.signs.p, 0xFF, b_.sign_words * 4, st);
+  }
+  std::vector<DecJob> jobs(nc);
+  for (int c = 0; c < nc; c++) {
+    DecJob& j = jobs[c];
+    const ShapeTables& sh = b_.shapes[b_.h[c].shape];
+    j.skip = ps[c].is_const || ps[c].planes == 0;
+    j.n = b_.h[c].n;
+    j.shape = b_.h[c].shape;
+    j.d_payload = d_stream + ps[c].spk_off;
+    j.payload_bytes = ps[c].spk_bytes;
+    j.planes = ps[c].planes;
+    j.total_bits = ps[c].total_bits;
+    j.mag = b_.h[c].mag;
+    j.signs = b_.h[c].signs;
+    j.wide = any_wide ? 1 : 0;
+    j.nlis = sh.h.nlis;
+    // lis_off lives inside the ShapeHeader copy on the device
+    j.d_lis_off = nullptr;
+    j.lis_total = sh.h.lis_off[kMaxLis];
+  }
+  {
+    // device addresses of ShapeHeader::lis_off: fetch the ShapeDev array once
+    std::vector<ShapeDev> sd(b_.shapes.size());
+    rt::d2h(sd.data(), b_.d_shapes.p, sizeof(ShapeDev) * sd.size(), st);
+    rt::sync(st);
+    for (int c = 0; c < nc; c++)
+      jobs[c].d_lis_off = reinterpret_cast<const unsigned long long*>(
+          reinterpret_cast<const unsigned char*>(sd[b_.h[c].shape].h) + offsetof(ShapeHeader, lis_off));
+  }
+  {
+    rt::ProfScope pd("d.speck3d", st);
+    speck3d_decode(w3_, jobs, b_.dev_shapes(), st);
+  }
+
+  // ---- inverse quantisation and inverse transform ----
+  {
+    rt::ProfScope pq("d.inv_quantize", st);
+    launch_inv_quantize(b_.dev(), nc, b_.max_n, st);
+  }
+  std::vector<std::vector<int>> groups(b_.shapes.size());
+  for (int c = 0; c < nc; c++)
+    if (!ps[c].is_const)
+      groups[b_.h[c].shape].push_back(c);
+  std::vector<int> flat;
+  std::vector<size_t> goff;
+  for (auto& g : groups) {
+    goff.push_back(flat.size());
+    flat.insert(flat.end(), g.begin(), g.end());
+  }
+  ids_.reserve(flat.size() * 4 + 4);
+  rt::h2d(ids_.p, flat.data(), flat.size() * 4, st);
+  rt::sync(st);
+  {
+    rt::ProfScope pt("d.idwt", st);
+    for (size_t s = 0; s < groups.size(); s++) {
+      if (groups[s].empty())
+        continue;
+      const ShapeHeader& h = b_.shapes[s].h;
+      launch_dwt(true, b_.dev(), ids_.as<int>() + goff[s], int(groups[s].size()), h.nx, h.ny, h.nz,
+                 false, st);
+    }
+  }
+
+  // ---- outliers: SPECK1D decode + correction (src/SPECK_FLT.cpp:576-585) ----
+  if (any_out) {
+    rt::ProfScope po("d.outliers", st);
+    size_t tot_n = 0, tot_w = 0, tot_lis = 0;
+    std::vector<size_t> on(nc), ow(nc);
+    std::vector<unsigned long long> h_lis_off;
+    std::vector<size_t> lo(nc, 0);
+    std::vector<int> nl(nc, 0);
+    for (int c = 0; c < nc; c++) {
+      on[c] = tot_n;
+      ow[c] = tot_w;
+      if (!ps[c].has_out || ps[c].oplanes == 0)
+        continue;
+      tot_n += (b_.h[c].n + 63) & ~size_t(63);
+      tot_w += (b_.h[c].n + 31) / 32 + 2;
+      // list capacities: level l holds at most min(2^l, bits in the stream) live sets
+      const int nlis = int(num_of_partitions(b_.h[c].n)) + 2;
+      nl[c] = nlis;
+      lo[c] = h_lis_off.size();
+      unsigned long long acc = 0;
+      for (int l = 0; l <= nlis; l++) {
+        h_lis_off.push_back(acc);
+        const unsigned long long cap2 = l >= 40 ? ~0ull : (1ull << l);
+        acc += std::min<unsigned long long>(cap2, ps[c].ototal + 2);
+      }
+      tot_lis = std::max<size_t>(tot_lis, acc);
+    }
+    const int ow_bytes = any_owide ? 8 : 4;
+    omag_.reserve(tot_n * ow_bytes + 16);
+    osigns_.reserve(tot_w * 4 + 16);
+    lis_off1_.reserve(h_lis_off.size() * 8 + 16);
+    rt::dset(omag_.p, 0, tot_n * ow_bytes, st);
+    rt::dset(osigns_.p, 0xFF, tot_w * 4, st);
+    rt::h2d(lis_off1_.p, h_lis_off.data(), h_lis_off.size() * 8, st);
+    std::vector<DecJob> oj(nc);
+    std::vector<double> tols(nc, 0.0);
+    for (int c = 0; c < nc; c++) {
+      DecJob& j = oj[c];
+      j.skip = !ps[c].has_out || ps[c].oplanes == 0;
+      if (j.skip)
+        continue;
+      j.n = b_.h[c].n;
+      j.d_payload = d_stream + ps[c].out_off;
+      j.payload_bytes = ps[c].out_bytes;
+      j.planes = ps[c].oplanes;
+      j.total_bits = ps[c].ototal;
+      j.mag = omag_.as<unsigned char>() + on[c] * ow_bytes;
+      j.signs = osigns_.as<uint32_t>() + ow[c];
+      j.wide = any_owide ? 1 : 0;
+      j.nlis = nl[c];
+      j.d_lis_off = lis_off1_.as<unsigned long long>() + lo[c];
+      j.lis_total = h_lis_off[lo[c] + nl[c]];
+      tols[c] = ps[c].q / 1.5;  // src/SPECK_FLT.cpp:578
+    }
+    speck1d_decode(w1_, oj, st);
+    tols_.reserve(nc * 8);
+    rt::h2d(tols_.p, tols.data(), nc * 8, st);
+    launch_outlier_apply(w1_.dchunks.as<DecChunk>(), b_.dev(), tols_.as<double>(), nc, b_.max_n, st);
+    rt::sync(st);  // `tols`, `h_lis_off` leave scope
+  }
+
+  // ---- add the mean back, convert and scatter into the output volume ----
+  {
+    rt::ProfScope psc("d.scatter", st);
+    launch_scatter_out(dst, b_.dev(), nc, b_.max_n, st);
+  }
+  rt::sync(st);
+}
+
+}  // namespace sperr_b200

@@ -1,0 +1,653 @@
+// Tree-agnostic integer SPECK decoder: one CTA per chunk walks the bit-planes of its stream.
+//
+// Reproduces SPECK_INT<T>::decode (/root/reference/src/SPECK_INT.cpp:165-228), the decoder's
+// refinement pass (:359-469) and the sorting passes of the 3D / 1D coders
+// (src/SPECK3D_INT.cpp:99-212 with src/SPECK3D_INT_DEC.cpp:8-49; src/SPECK1D_INT_DEC.cpp:12-125).
+//
+// How the work is split inside a CTA (not how the reference does it):
+//   * LIP part of a plane: the bit string is a 2-state grammar (significance bit, then a sign bit
+//     iff it was 1), so it is tokenised by a block-wide prefix scan over state-transition functions;
+//     results are matched to pixels by a popcount scan of the LIP mask in raster order.
+//   * LIS part: the only inherently serial piece -- every bit decides what the next bit means. One
+//     thread walks the lists depth-first. Lists hold only live (insignificant) sets and are
+//     compacted in place while they are iterated, which keeps SPECK's list order:
+//     survivors first, then the sets created in this plane in depth-first creation order.
+//   * refinement part: bit k belongs to the k-th pixel of the LSP mask in raster order (popcount
+//     scan); truncated streams stop exactly where the reference stops.
+// A "tree policy" T supplies the initial sets and the children of a set:
+//   static __device__ int  T::roots(data, dc, c, r, node_t& nd, int& lis)    r-th initial set
+//   static __device__ int  T::num_roots(data, dc, c)
+//   static __device__ int  T::children(data, dc, c, node, lis, DChild out[8])
+#pragma once
+
+#include "speck_dec.h"
+#include "speck.h"
+
+namespace sperr_b200 {
+
+constexpr int kDecThreads = 1024;
+constexpr int kDecWarps = kDecThreads / 32;
+
+struct DecShared {
+  unsigned long long pos;        // read position (bits)
+  unsigned long long klip, klsp; // population of the LIP / LSP masks
+  unsigned long long endpos;
+  unsigned long long wtot[kDecWarps];
+  unsigned long long wtot2[kDecWarps];
+  unsigned fA[kDecWarps], fB[kDecWarps];
+  unsigned tile_fA, tile_fB;
+};
+
+// ---- bit access -----------------------------------------------------------------------------
+
+// 64 bits starting at bit position p; bits at or beyond `avail` read as zero.
+__device__ __forceinline__ unsigned long long fetch64(const DecChunk& d, unsigned long long p)
+{
+  if (p >= d.avail)
+    return 0ull;
+  const unsigned long long w = p >> 5;
+  const unsigned sh = unsigned(p & 31);
+  const unsigned long long lo = d.bits[w], mid = d.bits[w + 1], hi = d.bits[w + 2];
+  unsigned long long v = (lo | (mid << 32)) >> sh;
+  if (sh)
+    v |= hi << (64 - sh);
+  const unsigned long long left = d.avail - p;
+  if (left < 64)
+    v &= (1ull << left) - 1ull;
+  return v;
+}
+
+struct BitReader {
+  const uint32_t* w;
+  unsigned long long avail, pos;
+  unsigned long long cur_idx;
+  uint32_t cur;
+  __device__ __forceinline__ void init(const DecChunk& d, unsigned long long p)
+  {
+    w = d.bits;
+    avail = d.avail;
+    pos = p;
+    cur_idx = ~0ull;
+    cur = 0;
+  }
+  __device__ __forceinline__ unsigned get()
+  {
+    unsigned b = 0;
+    if (pos < avail) {
+      const unsigned long long i = pos >> 5;
+      if (i != cur_idx) {
+        cur_idx = i;
+        cur = w[i];
+      }
+      b = (cur >> (pos & 31)) & 1u;
+    }
+    pos++;
+    return b;
+  }
+};
+
+// ---- transition functions of the LIP grammar ---------------------------------------------------
+// state 0: next bit is a significance bit; state 1: next bit is a sign bit.
+// A function is stored per entry state as (exit state | tokens << 1).
+
+__device__ __forceinline__ unsigned lip_sim(unsigned w, int s)
+{
+  unsigned c = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const unsigned b = (w >> i) & 1u;
+    if (s == 0) {
+      c++;
+      s = int(b);
+    }
+    else
+      s = 0;
+  }
+  return unsigned(s) | (c << 1);
+}
+
+// (g after f)
+__device__ __forceinline__ void lip_compose(unsigned fA, unsigned fB, unsigned gA, unsigned gB,
+                                            unsigned& oA, unsigned& oB)
+{
+  const unsigned ga = (fA & 1u) ? gB : gA;
+  const unsigned gb = (fB & 1u) ? gB : gA;
+  oA = (ga & 1u) | (((fA >> 1) + (ga >> 1)) << 1);
+  oB = (gb & 1u) | (((fB >> 1) + (gb >> 1)) << 1);
+}
+
+__device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long v, int lane)
+{
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o)
+      v += t;
+  }
+  return v;
+}
+
+// ---- magnitudes -------------------------------------------------------------------------------
+
+__device__ __forceinline__ void mag_set(const DecChunk& d, unsigned long long i, unsigned long long v)
+{
+  if (d.wide)
+    reinterpret_cast<unsigned long long*>(d.mag)[i] = v;
+  else
+    reinterpret_cast<unsigned*>(d.mag)[i] = unsigned(v);
+}
+__device__ __forceinline__ void mag_add(const DecChunk& d, unsigned long long i, long long dv)
+{
+  if (d.wide)
+    reinterpret_cast<unsigned long long*>(d.mag)[i] += (unsigned long long)dv;
+  else
+    reinterpret_cast<unsigned*>(d.mag)[i] += unsigned(dv);
+}
+
+// ---- LIP part ---------------------------------------------------------------------------------
+
+static __device__ void dec_lip_pass(DecChunk& d, DecShared& S)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long K = S.klip;
+  if (K == 0)
+    return;
+  for (unsigned long long i = tid; i < (K + 31) / 32 + 1; i += kDecThreads) {
+    d.sigarr[i] = 0;
+    d.signarr[i] = 0;
+  }
+  __syncthreads();
+
+  // stream side: tokenise until K pixels have been seen
+  unsigned long long base_pos = S.pos, ord_base = 0;
+  unsigned state_in = 0;
+  while (ord_base < K) {
+    const unsigned long long p = base_pos + 32ull * tid;
+    const unsigned long long w64 = fetch64(d, p);
+    const unsigned w = unsigned(w64);
+    unsigned fA = lip_sim(w, 0), fB = lip_sim(w, 1);
+    // inclusive scan of function composition inside the warp
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned pA = __shfl_up_sync(0xffffffffu, fA, o);
+      const unsigned pB = __shfl_up_sync(0xffffffffu, fB, o);
+      if (lane >= o) {
+        unsigned nA, nB;
+        lip_compose(pA, pB, fA, fB, nA, nB);
+        fA = nA;
+        fB = nB;
+      }
+    }
+    if (lane == 31) {
+      S.fA[warp] = fA;
+      S.fB[warp] = fB;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      unsigned gA = S.fA[lane], gB = S.fB[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned pA = __shfl_up_sync(0xffffffffu, gA, o);
+        const unsigned pB = __shfl_up_sync(0xffffffffu, gB, o);
+        if (lane >= o) {
+          unsigned nA, nB;
+          lip_compose(pA, pB, gA, gB, nA, nB);
+          gA = nA;
+          gB = nB;
+        }
+      }
+      S.fA[lane] = gA;   // inclusive over warps
+      S.fB[lane] = gB;
+      if (lane == 31) {
+        S.tile_fA = gA;
+        S.tile_fB = gB;
+      }
+    }
+    __syncthreads();
+    // exclusive prefix of this thread = (warps before) then (lanes before)
+    unsigned eA = __shfl_up_sync(0xffffffffu, fA, 1), eB = __shfl_up_sync(0xffffffffu, fB, 1);
+    if (lane == 0) {
+      eA = 0u;        // identity: state kept, no tokens
+      eB = 1u;
+    }
+    if (warp > 0) {
+      unsigned nA, nB;
+      lip_compose(S.fA[warp - 1], S.fB[warp - 1], eA, eB, nA, nB);
+      eA = nA;
+      eB = nB;
+    }
+    const unsigned mine = state_in ? eB : eA;
+    int s = int(mine & 1u);
+    unsigned long long ord = ord_base + (mine >> 1);
+#pragma unroll 4
+    for (int i = 0; i < 32; i++) {
+      const unsigned b = (w >> i) & 1u;
+      if (s == 0) {
+        if (ord < K) {
+          if (b) {
+            atomicOr(&d.sigarr[ord >> 5], 1u << (ord & 31));
+            if ((w64 >> (i + 1)) & 1ull)
+              atomicOr(&d.signarr[ord >> 5], 1u << (ord & 31));
+          }
+          if (ord == K - 1)
+            S.endpos = p + i + 1 + b;
+        }
+        ord++;
+        s = int(b);
+      }
+      else
+        s = 0;
+    }
+    const unsigned tile = state_in ? S.tile_fB : S.tile_fA;
+    ord_base += tile >> 1;
+    state_in = tile & 1u;
+    base_pos += 32ull * kDecThreads;
+    __syncthreads();
+  }
+
+  // mask side: the k-th LIP pixel in raster order owns token k
+  const unsigned long long words = (d.n + 31) / 32;
+  const unsigned long long per_warp = ((words + kDecWarps - 1) / kDecWarps + 31) / 32 * 32;
+  const unsigned long long w0 = per_warp * warp, w1 = min(words, w0 + per_warp);
+  unsigned long long cnt = 0;
+  for (unsigned long long j = w0 + lane; j < w1; j += 32)
+    cnt += __popc(d.lip[j]);
+  for (int o = 16; o; o >>= 1)
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0)
+    S.wtot[warp] = cnt;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long v = S.wtot[lane];
+    const unsigned long long inc = warp_incl_scan(v, lane);
+    S.wtot[lane] = inc - v;
+  }
+  __syncthreads();
+  unsigned long long run = S.wtot[warp];
+  unsigned long long nsig = 0;
+  for (unsigned long long j0 = w0; j0 < w1; j0 += 32) {
+    const unsigned long long j = j0 + lane;
+    unsigned m = j < w1 ? d.lip[j] : 0u;
+    const unsigned long long c = __popc(m);
+    const unsigned long long inc = warp_incl_scan(c, lane);
+    unsigned long long k = run + inc - c;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+    if (m) {
+      unsigned keep = m, nw = 0, neg = 0;
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        if ((d.sigarr[k >> 5] >> (k & 31)) & 1u) {
+          keep &= ~(1u << bit);
+          nw |= 1u << bit;
+          if (!((d.signarr[k >> 5] >> (k & 31)) & 1u))
+            neg |= 1u << bit;
+        }
+        k++;
+      }
+      if (nw) {
+        d.lip[j] = keep;
+        d.newm[j] |= nw;
+        if (neg)
+          d.signs[j] &= ~neg;
+        nsig += __popc(nw);
+      }
+    }
+  }
+  for (int o = 16; o; o >>= 1)
+    nsig += __shfl_xor_sync(0xffffffffu, nsig, o);
+  __syncthreads();
+  if (lane == 0)
+    S.wtot[warp] = nsig;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < kDecWarps; i++)
+      t += S.wtot[i];
+    S.klip -= t;
+    S.pos = S.endpos;
+  }
+  __syncthreads();
+}
+
+// ---- refinement part + promotion of the newly significant pixels -----------------------------
+// refine: read bits for the LSP pixels (src/SPECK_INT.cpp:359-469); always: newly significant
+// pixels get their initial value thr + thr - thr/2 - 1 and join the LSP.
+static __device__ void dec_refine_pass(DecChunk& d, DecShared& S, int n_plane, bool refine)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long thr = 1ull << n_plane;
+  const unsigned long long half = thr >> 1;
+  const unsigned long long init = thr + thr - half - 1ull;
+  const unsigned long long words = (d.n + 31) / 32;
+  const unsigned long long per_warp = ((words + kDecWarps - 1) / kDecWarps + 31) / 32 * 32;
+  const unsigned long long w0 = per_warp * warp, w1 = min(words, w0 + per_warp);
+  const unsigned long long R = S.pos;
+  unsigned long long nref = 0;
+  if (refine) {
+    nref = min(S.klsp, d.avail - R);
+    unsigned long long cnt = 0;
+    for (unsigned long long j = w0 + lane; j < w1; j += 32)
+      cnt += __popc(d.lsp[j]);
+    for (int o = 16; o; o >>= 1)
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0)
+      S.wtot[warp] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long v = S.wtot[lane];
+      const unsigned long long inc = warp_incl_scan(v, lane);
+      S.wtot[lane] = inc - v;
+    }
+    __syncthreads();
+  }
+  unsigned long long run = refine ? S.wtot[warp] : 0;
+  unsigned long long nnew = 0;
+  for (unsigned long long j0 = w0; j0 < w1; j0 += 32) {
+    const unsigned long long j = j0 + lane;
+    unsigned m = (refine && j < w1) ? d.lsp[j] : 0u;
+    const unsigned nw = j < w1 ? d.newm[j] : 0u;
+    if (refine) {
+      const unsigned long long c = __popc(m);
+      const unsigned long long inc = warp_incl_scan(c, lane);
+      unsigned long long k = run + inc - c;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+      while (m && k < nref) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const unsigned long long bp = R + k;
+        const unsigned b = (d.bits[bp >> 5] >> (bp & 31)) & 1u;
+        const unsigned long long i = j * 32 + bit;
+        if (thr >= 2)
+          mag_add(d, i, b ? (long long)half : -(long long)half);
+        else if (b)
+          mag_add(d, i, 1);
+        k++;
+      }
+    }
+    if (nw) {
+      unsigned t = nw;
+      while (t) {
+        const int bit = __ffs(t) - 1;
+        t &= t - 1;
+        mag_set(d, j * 32 + bit, init);
+      }
+      d.lsp[j] |= nw;
+      d.newm[j] = 0;
+      nnew += __popc(nw);
+    }
+  }
+  for (int o = 16; o; o >>= 1)
+    nnew += __shfl_xor_sync(0xffffffffu, nnew, o);
+  __syncthreads();
+  if (lane == 0)
+    S.wtot2[warp] = nnew;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < kDecWarps; i++)
+      t += S.wtot2[i];
+    S.klsp += t;
+    S.pos = R + nref;
+  }
+  __syncthreads();
+}
+
+// ---- LIS part: depth-first walk by one thread ---------------------------------------------------
+
+constexpr int kDecMaxDepth = 48;
+
+struct DecFrame {
+  DChild kid[8];
+  int nch, k, sigc;
+};
+
+template <class T>
+__device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c, BitReader& br,
+                           node_t root, int root_lis, DecFrame* stack, unsigned long long& klip)
+{
+  int depth = 0;
+  stack[0].nch = T::children(tree, d, c, root, root_lis, stack[0].kid);
+  stack[0].k = 0;
+  stack[0].sigc = 0;
+  while (depth >= 0) {
+    DecFrame& f = stack[depth];
+    if (f.k == f.nch) {
+      depth--;
+      continue;
+    }
+    const DChild ch = f.kid[f.k];
+
+    const bool need = f.sigc != 0 || f.k != f.nch - 1;
+    f.k++;
+    const unsigned sig = need ? br.get() : 1u;
+    if (ch.pixel) {
+      const unsigned long long i = ch.idx;
+      if (sig) {
+        const unsigned sgn = br.get();
+        d.newm[i >> 5] |= 1u << (i & 31);
+        if (!sgn)
+          d.signs[i >> 5] &= ~(1u << (i & 31));
+        f.sigc++;
+      }
+      else {
+        d.lip[i >> 5] |= 1u << (i & 31);
+        klip++;
+      }
+    }
+    else if (sig) {
+      f.sigc++;
+      if (depth + 1 >= kDecMaxDepth) {
+        d.err |= 2u;
+        return;
+      }
+      DecFrame& g = stack[depth + 1];
+      g.nch = T::children(tree, d, c, ch.id, ch.lis, g.kid);
+      g.k = 0;
+      g.sigc = 0;
+      depth++;
+    }
+    else {
+      const unsigned slot = d.lis_cnt[ch.lis];
+      if (d.lis_off[ch.lis] + slot >= d.lis_off[ch.lis + 1]) {
+        d.err |= 1u;
+        return;
+      }
+      d.lis[d.lis_off[ch.lis] + slot] = ch.id;
+      d.lis_cnt[ch.lis] = slot + 1;
+    }
+  }
+}
+
+template <class T>
+__device__ void dec_lis_walk(DecChunk& d, const typename T::Data& tree, unsigned c, DecShared& S,
+                             DecFrame* stack)
+{
+  BitReader br;
+  br.init(d, S.pos);
+  unsigned long long klip = S.klip;
+  for (int lev = d.nlis - 1; lev >= 0; lev--) {
+    const unsigned cnt = d.lis_cnt[lev];
+    if (cnt == 0)
+      continue;
+    node_t* list = d.lis + d.lis_off[lev];
+    unsigned w = 0;
+    for (unsigned i = 0; i < cnt; i++) {
+      const node_t nd = list[i];
+      if (br.get() == 0) {
+        list[w++] = nd;
+        continue;
+      }
+      dec_expand<T>(d, tree, c, br, nd, lev, stack, klip);
+      if (d.err)
+        return;
+    }
+    d.lis_cnt[lev] = w;
+  }
+  S.pos = br.pos;
+  S.klip = klip;
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+
+template <class T>
+__global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, typename T::Data tree)
+{
+  __shared__ DecShared S;
+  __shared__ DecFrame stack[kDecMaxDepth];
+  const unsigned c = blockIdx.x;
+  DecChunk& d = chunks[c];
+  if (d.skip || d.planes == 0)
+    return;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    S.pos = 0;
+    S.klip = 0;
+    S.klsp = 0;
+    S.endpos = 0;
+    for (int l = 0; l < d.nlis; l++)
+      d.lis_cnt[l] = 0;
+    const int nr = T::num_roots(tree, d, c);
+    for (int r = 0; r < nr; r++) {
+      node_t nd;
+      int lis;
+      T::root(tree, d, c, r, nd, lis);
+      d.lis[d.lis_off[lis] + d.lis_cnt[lis]] = nd;
+      d.lis_cnt[lis]++;
+    }
+  }
+  __syncthreads();
+  int n = d.planes - 1;
+  bool pending_new = false;
+  for (int bp = 0; bp < d.planes; bp++, n--) {
+    dec_lip_pass(d, S);
+    __syncthreads();   // every thread has read the LIP population before the walker changes it
+    if (tid == 0)
+      dec_lis_walk<T>(d, tree, c, S, stack);
+    __syncthreads();
+    if (d.err)
+      return;
+    if (S.pos >= d.avail) {
+      pending_new = true;
+      break;
+    }
+    dec_refine_pass(d, S, n, true);
+    if (S.pos >= d.avail)
+      break;
+  }
+  if (pending_new)
+    dec_refine_pass(d, S, n, false);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host driver
+// ---------------------------------------------------------------------------------------------
+
+// out[w] = little-endian word w of the byte string src[0, len), zero beyond it
+static __global__ void k_stage_bits(const DecChunk* chunks, const unsigned char* const* srcs,
+                                    const unsigned long long* lens, const unsigned long long* words)
+{
+  const unsigned c = blockIdx.y;
+  const unsigned char* src = srcs[c];
+  const unsigned long long len = lens[c], nw = words[c];
+  uint32_t* out = const_cast<uint32_t*>(chunks[c].bits);
+  for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nw;
+       w += (unsigned long long)gridDim.x * blockDim.x) {
+    uint32_t v = 0;
+    for (int b = 0; b < 4; b++) {
+      const unsigned long long i = w * 4 + b;
+      if (i < len)
+        v |= uint32_t(src[i]) << (8 * b);
+    }
+    out[w] = v;
+  }
+}
+
+// Decodes every job; on return w.h[c].lsp is the final significance mask of job c.
+template <class T>
+void run_decoder(DecWork& w, const std::vector<DecJob>& jobs, const typename T::Data& tree,
+                 cudaStream_t st)
+{
+  const int nj = int(jobs.size());
+  if (nj == 0)
+    return;
+  size_t mask_words = 0, lis_entries = 0, cnt_entries = 0, stage_words = 0;
+  std::vector<size_t> mw(nj), sw(nj);
+  for (int c = 0; c < nj; c++) {
+    const DecJob& j = jobs[c];
+    mw[c] = j.skip ? 0 : (size_t(j.n + 31) / 32 + 4);
+    sw[c] = j.skip ? 0 : (size_t(j.payload_bytes) / 4 + 4);
+    mask_words += 5 * mw[c];
+    lis_entries += j.skip ? 0 : j.lis_total;
+    cnt_entries += j.skip ? 0 : size_t(j.nlis + 1);
+    stage_words += sw[c];
+  }
+  w.masks.reserve(mask_words * 4 + 16);
+  w.lis.reserve(lis_entries * 8 + 16);
+  w.lis_cnt.reserve(cnt_entries * 4 + 16);
+  w.stage.reserve(stage_words * 4 + 16);
+  rt::dset(w.masks.p, 0, mask_words * 4, st);
+  w.h.assign(nj, DecChunk());
+  std::vector<const unsigned char*> srcs(nj);
+  std::vector<unsigned long long> lens(nj), words(nj);
+  size_t om = 0, ol = 0, oc = 0, os = 0, max_words = 1;
+  for (int c = 0; c < nj; c++) {
+    const DecJob& j = jobs[c];
+    DecChunk& d = w.h[c];
+    std::memset(&d, 0, sizeof(d));
+    d.skip = j.skip ? 1 : 0;
+    srcs[c] = j.d_payload;
+    lens[c] = j.skip ? 0 : j.payload_bytes;
+    words[c] = sw[c];
+    if (j.skip)
+      continue;
+    d.n = j.n;
+    d.shape = j.shape;
+    d.planes = j.planes;
+    d.avail = std::min<unsigned long long>(j.total_bits, j.payload_bytes * 8ull);
+    d.wide = j.wide;
+    d.mag = j.mag;
+    d.signs = j.signs;
+    uint32_t* m = w.masks.as<uint32_t>() + om;
+    d.lip = m;
+    d.lsp = m + mw[c];
+    d.newm = m + 2 * mw[c];
+    d.sigarr = m + 3 * mw[c];
+    d.signarr = m + 4 * mw[c];
+    om += 5 * mw[c];
+    d.lis = w.lis.as<node_t>() + ol;
+    ol += j.lis_total;
+    d.lis_off = j.d_lis_off;
+    d.lis_cnt = w.lis_cnt.as<unsigned>() + oc;
+    oc += size_t(j.nlis + 1);
+    d.nlis = j.nlis;
+    d.bits = w.stage.as<uint32_t>() + os;
+    os += sw[c];
+    max_words = std::max(max_words, sw[c]);
+  }
+  w.dchunks.reserve(sizeof(DecChunk) * nj);
+  rt::h2d(w.dchunks.p, w.h.data(), sizeof(DecChunk) * nj, st);
+  const size_t aux_bytes = size_t(nj) * 24;
+  w.aux.reserve(aux_bytes);
+  unsigned char* aux = w.aux.as<unsigned char>();
+  rt::h2d(aux, srcs.data(), nj * 8, st);
+  rt::h2d(aux + nj * 8, lens.data(), nj * 8, st);
+  rt::h2d(aux + nj * 16, words.data(), nj * 8, st);
+  DecChunk* dch = w.dchunks.as<DecChunk>();
+  {
+    rt::ProfScope ps("dec.stage_bits", st);
+    const unsigned gx = unsigned(std::min<size_t>((max_words + 255) / 256, 256));
+    LAUNCH(k_stage_bits, dim3(gx, nj), dim3(256), 0, st, dch,
+           reinterpret_cast<const unsigned char* const*>(aux),
+           reinterpret_cast<const unsigned long long*>(aux + nj * 8),
+           reinterpret_cast<const unsigned long long*>(aux + nj * 16));
+  }
+  {
+    rt::ProfScope ps("dec.speck_decode", st);
+    LAUNCH(k_speck_decode<T>, dim3(nj), dim3(kDecThreads), 0, st, dch, tree);
+  }
+  rt::d2h(w.h.data(), w.dchunks.p, sizeof(DecChunk) * nj, st);
+  rt::sync(st);
+  for (int c = 0; c < nj; c++)
+    if (w.h[c].err)
+      throw std::runtime_error("SPECK decoder: list capacity exceeded (corrupt stream?)");
+}
+
+}  // namespace sperr_b200

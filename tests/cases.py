@@ -28,6 +28,10 @@ COMP3D_GPU = COMP3D_SMALL + [
 ]
 
 
+def case_id(c):
+    return "%s-%s-m%d-%g" % (c[0][:8], "x".join(map(str, c[2])), c[3], c[4])
+
+
 def fnv1a64(b):
     h = 0xcbf29ce484222325
     for x in bytes(b):

@@ -12,6 +12,6 @@ def lib():
     return gpulib.load("emul")
 
 
-@pytest.mark.parametrize("case", cases.COMP3D_SMALL, ids=lambda c: "%s-%s-m%d-%g" % (c[0][:8], "x".join(map(str, c[2])), c[3], c[4]))
+@pytest.mark.parametrize("case", cases.COMP3D_SMALL, ids=cases.case_id)
 def test_comp3d_bytes_emulated(lib, oracle, case):
     cases.check_comp3d(lib, oracle, case)

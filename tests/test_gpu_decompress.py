@@ -1,0 +1,64 @@
+"""GPU parity: sperr_decomp_3d of libsperr_b200.so must return values bit-identical to the
+oracle's decoder for the same container, in every mode, for float and double output."""
+import numpy as np
+import pytest
+
+import cases
+import gpulib
+import refs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return gpulib.load("cuda")
+
+
+@pytest.mark.parametrize("case", cases.COMP3D_GPU, ids=cases.case_id)
+def test_decomp3d_bits(lib, oracle, case):
+    name, dims, chunks, mode, q = case
+    v = refs.load_test_data(name)
+    rc, stream = oracle.comp_3d(v, dims, chunks, mode, q)
+    assert rc == 0
+    cases.check_decomp3d(lib, oracle, stream, True)
+    cases.check_decomp3d(lib, oracle, stream, False)
+
+
+def test_roundtrip_own_stream_pwe_bound(lib, oracle):
+    # compress and decompress with the CUDA library only; the PWE bound must hold on every value
+    v = refs.load_test_data("vorticity.128_128_41")
+    for tol in (1e-5, 1.5e-7, 1e-2):
+        rc, stream = lib.comp_3d(v, (128, 128, 41), (64, 64, 41), 3, tol)
+        assert rc == 0
+        rc, out, dims = lib.decomp_3d(stream, False)
+        assert rc == 0 and dims == (128, 128, 41)
+        assert np.max(np.abs(out - v.astype(np.float64))) <= tol
+
+
+def test_decomp3d_synthetic_256(lib, oracle):
+    v = refs.synthetic_field((256, 256, 256))
+    for mode, q in ((3, 1e-3), (1, 1.0)):
+        rc, stream = lib.comp_3d(v, (256, 256, 256), (256, 256, 256), mode, q)
+        assert rc == 0
+        cases.check_decomp3d(lib, oracle, stream, True)
+
+
+def test_decomp3d_ragged_multichunk(lib, oracle):
+    v = refs.synthetic_field((200, 150, 130), seed=7)
+    for mode, q in ((3, 1e-3), (2, 70.0), (1, 1.5)):
+        rc, stream = oracle.comp_3d(v, (200, 150, 130), (64, 64, 64), mode, q)
+        assert rc == 0
+        cases.check_decomp3d(lib, oracle, stream, True)
+
+
+def test_decomp3d_rejects_bad_streams(lib, oracle):
+    v = refs.load_test_data("wmag17.float")
+    rc, stream = oracle.comp_3d(v, (17, 17, 17), (17, 17, 17), 3, 0.3)
+    bad = stream.copy()
+    bad[0] = 9                       # version byte (src/SPERR3D_OMP_D.cpp:33)
+    assert lib.decomp_3d(bad)[0] == -1
+    assert lib.decomp_3d(stream[:-3])[0] == -1   # length mismatch
+    bad = stream.copy()
+    bad[1] &= 0xBF                   # not a 3D stream
+    assert lib.decomp_3d(bad)[0] == -1
