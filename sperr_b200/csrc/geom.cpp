@@ -353,6 +353,11 @@ ShapeTables build_shape(uint32_t nx, uint32_t ny, uint32_t nz)
   h.lis_off[0] = 0;
   for (int l = 0; l < kMaxLis; l++)
     h.lis_off[l + 1] = h.lis_off[l] + cap[l];
+  auto is_pow2 = [](uint32_t v) { return v != 0 && (v & (v - 1)) == 0; };
+  h.pow2 = (h.dyadic >= 0 && chain_start.size() == 1 && is_pow2(nx) && is_pow2(ny) && is_pow2(nz) &&
+            h.leaf_level == 0)
+               ? 1
+               : 0;
   return t;
 }
 

@@ -93,6 +93,9 @@ struct ShapeHeader {
   // decoder list storage: list l may hold up to lis_off[l + 1] - lis_off[l] sets (every node of
   // the pyramid whose LIS index is l)
   unsigned long long lis_off[kMaxLis + 1];
+  // 1 when every extent is a power of two and the chunk is dyadic: all sets are then aligned
+  // boxes of a single chain and the coders can address them with shifts instead of the tables
+  int pow2;
 };
 
 struct ShapeTables {

@@ -149,6 +149,14 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     // lis_off lives inside the ShapeHeader copy on the device
     j.d_lis_off = nullptr;
     j.lis_total = sh.h.lis_off[kMaxLis];
+    if (sh.h.pow2 && !std::getenv("SPERR_B200_NO_FASTDEC")) {
+      j.pow2 = 1;
+      j.Dx = sh.h.ax[0].D; j.Dy = sh.h.ax[1].D; j.Dz = sh.h.ax[2].D;
+      j.nx = sh.h.nx; j.ny = sh.h.ny;
+      const int J = std::max(j.Dx, std::max(j.Dy, j.Dz));
+      const int nb = (j.Dx == J) + (j.Dy == J) + (j.Dz == J);   // axes that split at the last level
+      j.log_entries = (j.n >> nb) + 64;
+    }
   }
   {
     // device addresses of ShapeHeader::lis_off: fetch the ShapeDev array once

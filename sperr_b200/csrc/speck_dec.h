@@ -33,6 +33,13 @@ struct DecChunk {
   unsigned* lis_cnt;             // nlis counters
   int nlis;
   unsigned err;                  // 1: a list overflowed its capacity
+  // fast path for power-of-two dyadic chunks (ShapeHeader::pow2)
+  int pow2;
+  int Dx, Dy, Dz;                // bisection depth of every axis
+  unsigned nx, ny;
+  unsigned long long* log;       // bottom-level sets decoded in the current plane
+  unsigned long long log_cap;
+  unsigned long long stage_words;   // words in `bits`
 };
 
 // One integer stream to decode. `mag` (zeroed) and `signs` (all ones) are provided by the caller.
@@ -50,10 +57,13 @@ struct DecJob {
   int nlis = 0;
   const unsigned long long* d_lis_off = nullptr;   // device, nlis + 1 entries
   unsigned long long lis_total = 0;                // total list capacity (entries)
+  int pow2 = 0, Dx = 0, Dy = 0, Dz = 0;            // 3D fast path (see DecChunk)
+  unsigned nx = 0, ny = 0;
+  unsigned long long log_entries = 0;
 };
 
 struct DecWork {
-  rt::DBuf dchunks, masks, lis, lis_cnt, stage, aux;
+  rt::DBuf dchunks, masks, lis, lis_cnt, stage, aux, logs;
   std::vector<DecChunk> h;   // copy of the device state after the last run
 };
 

@@ -18,3 +18,8 @@ def test_decomp3d_bits_emulated(lib, oracle, case):
     rc, stream = oracle.comp_3d(v, dims, chunks, mode, q)
     assert rc == 0
     cases.check_decomp3d(lib, oracle, stream, True)
+
+
+@pytest.mark.parametrize("case", cases.SYN_SMALL, ids=cases.syn_id)
+def test_synthetic_roundtrip_emulated(lib, oracle, case):
+    cases.check_syn_roundtrip(lib, oracle, case)

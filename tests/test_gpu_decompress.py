@@ -62,3 +62,8 @@ def test_decomp3d_rejects_bad_streams(lib, oracle):
     bad = stream.copy()
     bad[1] &= 0xBF                   # not a 3D stream
     assert lib.decomp_3d(bad)[0] == -1
+
+
+@pytest.mark.parametrize("case", cases.SYN_GPU, ids=cases.syn_id)
+def test_synthetic_roundtrip(lib, oracle, case):
+    cases.check_syn_roundtrip(lib, oracle, case)
