@@ -279,13 +279,16 @@ def run_ours(args):
         stream = step_dev()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launch_count = L.fn("sperr_b200_launch_count", C.c_ulonglong, [])
     with Clocks(local) as clk:
         barrier()
+        l0 = launch_count()
         e0.record()
         for _ in range(args.steps):
             stream = step_dev()
         e1.record()
         barrier()
+        launches_per_step = (launch_count() - l0) // args.steps
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if dist is not None:
@@ -312,7 +315,7 @@ def run_ours(args):
     # decoded values are rounded to fp32 after the bound was enforced in fp64: allow one fp32 ulp
     assert maxerr <= TOL + 1.2e-7, "PWE bound violated: %g" % maxerr
 
-    # stage profile (separate, untimed pass)
+    # stage profile (separate, untimed pass): CUDA-event ranges on the launching stream
     prof_on(1)
     step_dev()
     buf = C.create_string_buffer(1 << 16)
@@ -320,14 +323,14 @@ def run_ours(args):
     prof_on(0)
     stages = json.loads(buf.value.decode())
 
-    # e2e through the reference-facing C API with host buffers
+    # e2e through the reference-facing C API with host buffers (pinned input, malloc'd outputs)
     hvol = vol.cpu().pin_memory().numpy() if args.e2e else None
     e2e = None
     if hvol is not None:
         def e2e_step():
-            rc, s2 = L.compress_3d(hvol, dims, (CHUNK,) * 3, 3, TOL)
+            rc, s2 = L.compress_3d(hvol, dims, (CHUNK,) * 3, 3, TOL, copy=False)
             assert rc == 0
-            rc, o2, d2 = L.decompress_3d(s2, True)
+            rc, o2, d2 = L.decompress_3d(s2, True, copy=False)
             assert rc == 0
             return s2
         e2e_step()
@@ -344,20 +347,84 @@ def run_ours(args):
                "h2d_bytes_per_step": nbytes + int(s2.size), "d2h_bytes_per_step": int(s2.size) + nbytes}
 
     if rank == 0:
+        nvals = n ** 3
         out = {
             "metric": "compress+decompress input GB/s", "value": world * nbytes / (ms * 1e-3) / GB,
             "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-            "stream_bytes": int(stream.size), "bpp": stream.size * 8.0 / (n ** 3),
+            "stream_bytes": int(stream.size), "bpp": stream.size * 8.0 / nvals,
             "clocks": clk.summary(), "stages_ms": {k: round(v["ms"], 3) for k, v in stages.items()},
             "compress_gbs": world * nbytes / (ms_c * 1e-3) / GB,
             "decompress_gbs": world * nbytes / (ms_d * 1e-3) / GB, "max_abs_err": maxerr,
-            "e2e": e2e,
+            "e2e": e2e, "gpu_launches": launches_per_step,
         }
+        out.update(rooflines(stages, nvals, int(stream.size)))
+        if world == 1 and args.cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def measured_peak():
+    """(GB/s, source): HBM copy bandwidth of this pool's B200s, as measured by the driver."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6550.0, "fallback (B200_PROFILING.md measured copy bandwidth)"
+
+
+# Algorithmic bytes per value of the kernels a stage consists of (SURVEY.md 8d, DESIGN.md "Kernels").
+# A stage is a CUDA-event range on the launching stream around that kernel (or kernel family).
+STAGE_MODELS = {
+    # one launch: reads the chunk streams, writes magnitudes (4 B) + sign bits (1/8 B) per value
+    "dec.speck_decode": ("k_speck_decode (SPECK3D+1D bit-plane decoder, one CTA per chunk)",
+                         lambda n, sb: 4.125 * n + sb),
+    # 5-level dyadic transform: 16 B per coefficient of every level box = 18.29 B per value
+    "c.dwt": ("forward CDF 9/7 transform, all levels (k_dwt_* family)", lambda n, sb: 18.29 * n),
+    "c.idwt": ("inverse CDF 9/7 transform, all levels (k_dwt_* family)", lambda n, sb: 18.29 * n),
+    "d.idwt": ("inverse CDF 9/7 transform, all levels (k_dwt_* family)", lambda n, sb: 18.29 * n),
+    "c.quantize": ("k_quantize", lambda n, sb: 12.1 * n),
+    "c.stats": ("k_stride_stats", lambda n, sb: 4.0 * n),
+    "c.outlier_detect": ("k_outlier_count + k_outlier_write", lambda n, sb: 12.0 * n),
+}
+
+
+def rooflines(stages, nvals, stream_bytes):
+    peak, src = measured_peak()
+    cands = [(v["ms"], k) for k, v in stages.items() if k in STAGE_MODELS and v["ms"] > 0]
+    if not cands:
+        return {}
+    res = {}
+
+    def entry(k):
+        ms = stages[k]["ms"]
+        name, fn = STAGE_MODELS[k]
+        by = fn(float(nvals), float(stream_bytes))
+        ach = by / (ms * 1e-3) / GB
+        return {"kernel": name, "stage": k, "bound": "hbm", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "ms": ms,
+                "algorithmic_bytes": by, "peak_source": src}
+    res["roofline"] = entry(max(cands)[1])
+    wl = [k for k in ("c.dwt", "d.idwt") if k in stages]
+    if wl:
+        res["roofline_wavelet"] = [entry(k) for k in wl]
+    return res
+
+
+def cpu_baseline_sample():
+    lib, kind, prefix = load_cpu_lib()
+    dims, cores = cpu_sample_dims()
+    vol = field_numpy(dims)
+    tc, td, slen = cpu_roundtrip(lib, prefix, vol, dims)
+    nbytes = vol.size * 4
+    return {"value": nbytes / (tc + td) / GB, "unit": "GB/s", "cores": cores, "kind": kind,
+            "compress_gbs": nbytes / tc / GB, "decompress_gbs": nbytes / td / GB,
+            "sample": "%dx%dx%d fp32 (%d chunks of 256^3) of the 1024^3 field, PWE %g, one "
+                      "compress+decompress through the reference C API, all host threads" % (
+                          dims + (vol.size // CHUNK ** 3, TOL))}
 
 
 def main():
@@ -369,6 +436,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--e2e", type=int, default=1)
+    ap.add_argument("--cpu-baseline", type=int, default=1)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -65,6 +65,10 @@ int sperr_b200_decomp_3d_dev(const void* h_src, const void* d_src, size_t src_le
 void sperr_b200_prof_enable(int on);
 size_t sperr_b200_prof_dump(char* buf, size_t cap);
 
+/* Number of kernels of this library launched by the calling process so far (library kernels such
+ * as cub's radix sort are not counted). */
+unsigned long long sperr_b200_launch_count(void);
+
 /* ------------------------------------------------------------------------------------------ */
 /* 3. Stage-level hooks (parity tests)                                                         */
 /* ------------------------------------------------------------------------------------------ */

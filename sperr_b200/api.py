@@ -2,6 +2,7 @@
 /root/reference/include/SPERR_C_API.h:53-156) and section 2 (device-pointer extensions)."""
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -16,6 +17,18 @@ vp = C.c_void_p
 _libc = C.CDLL(None)
 _libc.free.argtypes = [vp]
 _libc.free.restype = None
+
+
+def _adopt(ptr, ctype, n, copy):
+    """numpy view of a malloc'd result. copy=False hands the buffer itself to the caller (it is
+    free()d when the array is collected), which is what a C caller of the API gets."""
+    a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,))
+    if copy:
+        a = a.copy()
+        _libc.free(ptr)
+        return a
+    weakref.finalize(a, _libc.free, vp(ptr.value))
+    return a
 
 
 class Library:
@@ -46,7 +59,7 @@ class Library:
                                          C.POINTER(C.c_int)]
 
     # ---- host-buffer API (drop-in semantics) ----
-    def compress_3d(self, vol, dims, chunks, mode, quality, nthreads=0):
+    def compress_3d(self, vol, dims, chunks, mode, quality, nthreads=0, copy=True):
         """vol: flat float32/float64 array, x fastest. Returns (rc, uint8 stream or None)."""
         vol = np.ascontiguousarray(vol)
         if vol.dtype not in (np.float32, np.float64):
@@ -56,11 +69,9 @@ class Library:
                                     *chunks, mode, quality, nthreads, C.byref(dst), C.byref(n))
         if rc != 0:
             return rc, None
-        out = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_uint8)), shape=(n.value,)).copy()
-        _libc.free(dst)
-        return 0, out
+        return 0, _adopt(dst, C.c_uint8, n.value, copy)
 
-    def decompress_3d(self, stream, output_float=True, nthreads=0):
+    def decompress_3d(self, stream, output_float=True, nthreads=0, copy=True):
         """Returns (rc, flat array or None, (dimx, dimy, dimz) or None)."""
         stream = np.ascontiguousarray(stream, dtype=np.uint8)
         dx, dy, dz, dst = sz(0), sz(0), sz(0), vp(None)
@@ -70,9 +81,7 @@ class Library:
             return rc, None, None
         n = dx.value * dy.value * dz.value
         ct = C.c_float if output_float else C.c_double
-        out = np.ctypeslib.as_array(C.cast(dst, C.POINTER(ct)), shape=(n,)).copy()
-        _libc.free(dst)
-        return 0, out, (dx.value, dy.value, dz.value)
+        return 0, _adopt(dst, ct, n, copy), (dx.value, dy.value, dz.value)
 
     # ---- device-pointer extensions ----
     def compress_3d_dev(self, d_ptr, is_float, dims, chunks, mode, quality):

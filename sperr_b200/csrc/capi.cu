@@ -5,8 +5,11 @@
 //   C_API::sperr_comp_3d / sperr_decomp_3d    /root/reference/src/SPERR_C_API.cpp:156-258
 #include "../../include/sperr_b200.h"
 
+#include <sys/mman.h>
+
 #include <mutex>
 
+#include "hostpipe.h"
 #include "pipeline.h"
 
 using namespace sperr_b200;
@@ -15,6 +18,8 @@ namespace {
 
 std::mutex g_mutex;  // one job at a time per process: the work buffers are shared
 Compressor* g_comp = nullptr;
+// grow-only device staging of the host-pointer entry points (input volume, container, output volume)
+rt::DBuf g_in, g_stream, g_vol, g_cstream;
 
 bool device_ok()
 {
@@ -63,7 +68,8 @@ int comp_3d_device(const void* d_src, int is_float, size_t dimx, size_t dimy, si
   if (!g_comp)
     g_comp = new Compressor();
   SrcVol sv{d_src, is_float, dimx, dimy};
-  rt::DBuf d_out(size_t(1) << 20);
+  rt::DBuf& d_out = g_cstream;
+  d_out.reserve(size_t(1) << 20);
   std::vector<size_t> lens;
   g_comp->compress(sv, chunks, mode, quality, false, d_out, lens, st);
 
@@ -93,8 +99,7 @@ int comp_3d_device(const void* d_src, int is_float, size_t dimx, size_t dimy, si
     std::memcpy(o + pos, &l32, 4);
     pos += 4;
   }
-  rt::d2h(o + pos, d_out.p, total - hlen, st);
-  rt::sync(st);
+  HostPipe::get().d2h(o + pos, d_out.p, total - hlen, st);
   *dst = o;
   *dst_len = total;
   return 0;
@@ -185,9 +190,9 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
   return guarded([&] {
     cudaStream_t st = 0;
     const size_t bytes = dimx * dimy * dimz * (is_float ? 4 : 8);
-    rt::DBuf d_src(bytes);
-    rt::h2d(d_src.p, src, bytes, st);
-    return comp_3d_device(d_src.p, is_float, dimx, dimy, dimz, chunk_x, chunk_y, chunk_z, mode,
+    g_in.reserve(bytes);
+    HostPipe::get().h2d(g_in.p, src, bytes, st);
+    return comp_3d_device(g_in.p, is_float, dimx, dimy, dimz, chunk_x, chunk_y, chunk_z, mode,
                           quality, dst, dst_len, st);
   });
 }
@@ -221,18 +226,22 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
     ContainerInfo ci;
     if (!parse_container(static_cast<const uint8_t*>(src), src_len, ci))
       return -1;
-    rt::DBuf d_stream(src_len);
-    rt::h2d(d_stream.p, src, src_len, st);
+    g_stream.reserve(src_len);
+    HostPipe::get().h2d(g_stream.p, src, src_len, st);
     const size_t total = ci.vol[0] * ci.vol[1] * ci.vol[2];
     const size_t esz = output_float ? 4 : 8;
-    rt::DBuf d_out(total * esz);
-    decomp_3d_device(static_cast<const uint8_t*>(src), d_stream.as<uint8_t>(), ci, output_float,
-                     d_out.p, st);
+    g_vol.reserve(total * esz);
+    decomp_3d_device(static_cast<const uint8_t*>(src), g_stream.as<uint8_t>(), ci, output_float,
+                     g_vol.p, st);
     void* o = std::malloc(total * esz);
     if (!o)
       return -1;
-    rt::d2h(o, d_out.p, total * esz, st);
-    rt::sync(st);
+    if (total * esz >= (size_t(64) << 20)) {   // fewer first-touch faults while the result is filled
+      const uintptr_t a = (reinterpret_cast<uintptr_t>(o) + 4095) & ~uintptr_t(4095);
+      madvise(reinterpret_cast<void*>(a), total * esz - (a - reinterpret_cast<uintptr_t>(o)) & ~size_t(4095),
+              MADV_HUGEPAGE);
+    }
+    HostPipe::get().d2h(o, g_vol.p, total * esz, st);
     *dimx = ci.vol[0];
     *dimy = ci.vol[1];
     *dimz = ci.vol[2];
@@ -295,6 +304,8 @@ size_t sperr_b200_prof_dump(char* buf, size_t cap)
   }
   return s.size();
 }
+
+unsigned long long sperr_b200_launch_count(void) { return rt::launch_counter(); }
 
 void sperr_parse_header(const void* src, size_t* dimx, size_t* dimy, size_t* dimz, int* is_float)
 {

@@ -1,0 +1,53 @@
+// Host <-> device staging for the host-pointer C API.
+//
+// The reference API hands us pageable user memory and expects malloc'd results
+// (/root/reference/include/SPERR_C_API.h:21-31). cudaMemcpy on such memory is staged by the driver
+// at a few GB/s; here the copies go through a small ring of pinned slots instead, with a pool of
+// host threads doing the pageable side (memcpy, including the first-touch page faults of a fresh
+// malloc) while the DMA engine moves the neighbouring slot. Pinned user memory is copied directly.
+#pragma once
+
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+
+#include "rt.h"
+
+namespace sperr_b200 {
+
+class HostPipe {
+ public:
+  static HostPipe& get();
+  // dst_host may be pageable. Returns after the last byte is in dst_host.
+  void d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st);
+  // Returns after the last byte has been handed to the DMA engine AND the copy has completed.
+  void h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);
+  // Copies [0, bytes) with all workers; used for the pageable side.
+  void parallel_copy(void* dst, const void* src, size_t bytes);
+
+ private:
+  HostPipe();
+  ~HostPipe();
+  void worker();
+
+  static constexpr size_t kSlotBytes = size_t(32) << 20;
+  static constexpr int kSlots = 4;
+  void* slot_[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+#ifndef SPERR_EMUL
+  cudaEvent_t ev_[kSlots];
+#endif
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_work_, cv_done_;
+  struct Job {
+    char* dst;
+    const char* src;
+    size_t len;
+  };
+  std::vector<Job> jobs_;
+  size_t pending_ = 0;
+  bool stop_ = false;
+};
+
+}  // namespace sperr_b200

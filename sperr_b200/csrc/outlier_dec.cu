@@ -3,7 +3,7 @@
 //   SPECK1D_INT / _DEC          /root/reference/src/SPECK1D_INT.cpp:18-56, src/SPECK1D_INT_DEC.cpp:12-125
 //   Outlier_Coder::decode       /root/reference/src/Outlier_Coder.cpp:133-149, m_inverse_quantize :206-234
 //   application                 /root/reference/src/SPECK_FLT.cpp:576-585
-#include "speck_dec.cuh"
+#include "speck_dec_fast.cuh"
 
 namespace sperr_b200 {
 

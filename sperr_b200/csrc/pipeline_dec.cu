@@ -149,13 +149,20 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     // lis_off lives inside the ShapeHeader copy on the device
     j.d_lis_off = nullptr;
     j.lis_total = sh.h.lis_off[kMaxLis];
-    if (sh.h.pow2 && !std::getenv("SPERR_B200_NO_FASTDEC")) {
+    const int J3 = std::max(sh.h.ax[0].D, std::max(sh.h.ax[1].D, sh.h.ax[2].D));
+    if (sh.h.pow2 && J3 >= 4 && !std::getenv("SPERR_B200_NO_FASTDEC")) {
+      // power-of-two extents: every set is an aligned box, decoded by k_speck_decode_fast
       j.pow2 = 1;
       j.Dx = sh.h.ax[0].D; j.Dy = sh.h.ax[1].D; j.Dz = sh.h.ax[2].D;
       j.nx = sh.h.nx; j.ny = sh.h.ny;
-      const int J = std::max(j.Dx, std::max(j.Dy, j.Dz));
-      const int nb = (j.Dx == J) + (j.Dy == J) + (j.Dz == J);   // axes that split at the last level
-      j.log_entries = (j.n >> nb) + 64;
+      j.nroots = sh.h.nroots;
+      for (int r = 0; r < sh.h.nroots; r++) {
+        const RootDesc& rd = sh.h.roots[r];
+        const int dj = sh.h.lv[rd.level].j;   // single chain: depth of the set
+        const int bx = std::min(dj, j.Dx), by = std::min(dj, j.Dy);
+        j.roots[r] = ((unsigned long long)dj << 32) |
+                     (unsigned long long)(unsigned(rd.ix) | (unsigned(rd.iy) << bx) | (unsigned(rd.iz) << (bx + by)));
+      }
     }
   }
   {
@@ -253,6 +260,21 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
       j.nlis = nl[c];
       j.d_lis_off = lis_off1_.as<unsigned long long>() + lo[c];
       j.lis_total = h_lis_off[lo[c] + nl[c]];
+      const unsigned long long nn = b_.h[c].n;
+      if (nn >= 16 && (nn & (nn - 1)) == 0 && !std::getenv("SPERR_B200_NO_FASTDEC")) {
+        // power-of-two length: the binary tree of SPECK1D is the fast decoder's tree with one axis;
+        // the two initial halves sit at depth 1 (src/SPECK1D_INT.cpp:18-56)
+        j.pow2 = 1;
+        j.Dx = 0;
+        while ((1ull << j.Dx) < nn)
+          j.Dx++;
+        j.Dy = j.Dz = 0;
+        j.nx = unsigned(nn);
+        j.ny = 1;
+        j.nroots = 2;
+        j.roots[0] = (1ull << 32) | 0ull;
+        j.roots[1] = (1ull << 32) | 1ull;
+      }
       tols[c] = ps[c].q / 1.5;  // src/SPECK_FLT.cpp:578
     }
     speck1d_decode(w1_, oj, st);

@@ -26,6 +26,7 @@ typedef int cudaStream_t;
   do {                                                      \
     kern<<<grid, block, smem, stream>>>(__VA_ARGS__);       \
     rt::check(cudaGetLastError(), #kern, __FILE__, __LINE__); \
+    rt::launch_counter()++;                                 \
   } while (0)
 #define DYN_SMEM(type, name)                                        \
   extern __shared__ __align__(16) unsigned char name##_raw_smem[];  \
@@ -34,6 +35,13 @@ typedef int cudaStream_t;
 #endif
 
 namespace rt {
+
+// number of kernels of this library launched so far (bench.py reports the count per step)
+inline unsigned long long& launch_counter()
+{
+  static unsigned long long n = 0;
+  return n;
+}
 
 #ifndef SPERR_EMUL
 inline void check(cudaError_t e, const char* what, const char* file, int line)

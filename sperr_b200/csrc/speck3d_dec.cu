@@ -2,7 +2,7 @@
 //   set partitioning      /root/reference/src/SPECK3D_INT.cpp:214-326 (m_partition_S_XYZ and friends)
 //   initial sets          /root/reference/src/SPECK3D_INT.cpp:22-97
 //   decoder significance  /root/reference/src/SPECK3D_INT_DEC.cpp:8-49
-#include "speck_dec.cuh"
+#include "speck_dec_fast.cuh"
 #include "tree3d.cuh"
 
 namespace sperr_b200 {

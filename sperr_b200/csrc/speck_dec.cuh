@@ -485,198 +485,6 @@ __device__ void dec_lis_walk(DecChunk& d, const typename T::Data& tree, unsigned
   S.klip = klip;
 }
 
-// ---- LIS part, fast path: power-of-two dyadic 3D chunks ------------------------------------------
-// Every set is an aligned box: a node (j; ix, iy, iz) of chain 0 has extent 2^(D_a - min(j, D_a))
-// along axis a, its children are (2 i + c) on the axes that still split (j < D_a), its list index
-// is sum_a min(j, D_a), and the sets at j == J - 1 (J = max D_a) hold only single coefficients.
-// The walker keeps its frame in registers, reads bits through a 64-bit window, and instead of
-// touching the masks it logs one 64-bit entry per bottom-level set; the whole CTA applies the log
-// afterwards (dec_apply_log).
-
-struct FastBits {
-  const uint32_t* w;
-  unsigned long long nwords, widx;   // widx: next word to fetch
-  unsigned long long buf;
-  int cnt;
-  uint32_t nextw;
-  __device__ __forceinline__ void init(const DecChunk& d, unsigned long long pos)
-  {
-    w = d.bits;
-    nwords = d.stage_words;
-    widx = pos >> 5;
-    const uint32_t first = widx < nwords ? w[widx] : 0u;
-    const int sh = int(pos & 31);
-    buf = (unsigned long long)first >> sh;
-    cnt = 32 - sh;
-    widx++;
-    nextw = widx < nwords ? w[widx] : 0u;
-  }
-  __device__ __forceinline__ unsigned get()
-  {
-    if (cnt == 0) {
-      buf = nextw;
-      cnt = 32;
-      widx++;
-      nextw = widx < nwords ? w[widx] : 0u;
-    }
-    const unsigned b = unsigned(buf) & 1u;
-    buf >>= 1;
-    cnt--;
-    return b;
-  }
-  __device__ __forceinline__ unsigned long long pos() const { return widx * 32ull - (unsigned)cnt; }
-};
-
-constexpr int kFastMaxDepth = 20;
-
-struct FastShared {
-  unsigned long long off[kMaxLis + 1];
-  unsigned cnt[kMaxLis];
-  unsigned long long stack[kFastMaxDepth];
-  unsigned long long nlog;
-};
-
-// log entry: base raster index (32) | significance mask (8) | sign mask (8) | split flags (3)
-static __device__ void dec_lis_walk_pow2(DecChunk& d, DecShared& S, FastShared& F)
-{
-  const int Dx = d.Dx, Dy = d.Dy, Dz = d.Dz;
-  const int J = max(Dx, max(Dy, Dz));
-  const unsigned nx = d.nx, ny = d.ny;
-  FastBits br;
-  br.init(d, S.pos);
-  unsigned long long klip = S.klip;
-  unsigned long long nlog = 0;
-  const unsigned long long log_cap = d.log_cap;
-  unsigned long long* const log = d.log;
-  for (int lev = d.nlis - 1; lev >= 0; lev--) {
-    const unsigned cnt = F.cnt[lev];
-    if (cnt == 0)
-      continue;
-    node_t* const list = d.lis + F.off[lev];
-    unsigned w = 0;
-    node_t nxt = list[0];
-    for (unsigned i = 0; i < cnt; i++) {
-      const node_t nd = nxt;
-      if (i + 1 < cnt)
-        nxt = list[i + 1];
-      if (br.get() == 0) {
-        list[w++] = nd;
-        continue;
-      }
-      // depth-first expansion of a significant set; chain-0 level index = j + 1
-      unsigned ix = node_ix(nd), iy = node_iy(nd), iz = node_iz(nd);
-      int j = node_level(nd) - 1;
-      int k = 0, sigc = 0, depth = 0;
-      for (;;) {
-        const int sx = j < Dx, sy = j < Dy, sz = j < Dz;
-        const int nsplit = sx + sy + sz;
-        const int nch = 1 << nsplit;
-        bool pop = false;
-        if (j + 1 == J) {
-          unsigned sigm = 0, sgnm = 0;
-          int sc = 0;
-#pragma unroll
-          for (int kk = 0; kk < 8; kk++) {
-            if (kk < nch) {
-              const bool need = sc != 0 || kk != nch - 1;
-              const unsigned sig = need ? br.get() : 1u;
-              if (sig) {
-                const unsigned sgn = br.get();
-                sigm |= 1u << kk;
-                sgnm |= sgn << kk;
-                sc++;
-              }
-            }
-          }
-          klip += unsigned(nch - sc);
-          const unsigned x0 = sx ? ix * 2 : ix, y0 = sy ? iy * 2 : iy, z0 = sz ? iz * 2 : iz;
-          const unsigned long long base = ((unsigned long long)z0 * ny + y0) * nx + x0;
-          if (nlog < log_cap)
-            log[nlog] = base | ((unsigned long long)sigm << 32) | ((unsigned long long)sgnm << 40) |
-                        ((unsigned long long)(sx | (sy << 1) | (sz << 2)) << 48);
-          else
-            d.err |= 4u;
-          nlog++;
-          pop = true;
-        }
-        else if (k == nch)
-          pop = true;
-        if (pop) {
-          if (depth == 0)
-            break;
-          const unsigned long long fr = F.stack[--depth];
-          ix = unsigned(fr) & 0xffffu;
-          iy = unsigned(fr >> 16) & 0xffffu;
-          iz = unsigned(fr >> 32) & 0xffffu;
-          j = int(fr >> 48) & 0xff;
-          k = int(fr >> 56) & 0xf;
-          sigc = int(fr >> 60) & 1;
-          continue;
-        }
-        const bool need = sigc != 0 || k != nch - 1;
-        const unsigned sig = need ? br.get() : 1u;
-        const unsigned cx = sx ? (unsigned(k) & 1u) : 0u;
-        const unsigned cy = sy ? ((unsigned(k) >> sx) & 1u) : 0u;
-        const unsigned cz = sz ? ((unsigned(k) >> (sx + sy)) & 1u) : 0u;
-        const unsigned jx = sx ? ix * 2 + cx : ix, jy = sy ? iy * 2 + cy : iy, jz = sz ? iz * 2 + cz : iz;
-        k++;
-        if (sig) {
-          sigc = 1;
-          F.stack[depth++] = (unsigned long long)ix | ((unsigned long long)iy << 16) |
-                             ((unsigned long long)iz << 32) | ((unsigned long long)j << 48) |
-                             ((unsigned long long)k << 56) | (1ull << 60);
-          ix = jx; iy = jy; iz = jz;
-          j++;
-          k = 0;
-          sigc = 0;
-        }
-        else {
-          const int cl = min(j + 1, Dx) + min(j + 1, Dy) + min(j + 1, Dz);
-          const unsigned slot = F.cnt[cl];
-          if (F.off[cl] + slot >= F.off[cl + 1]) {
-            d.err |= 1u;
-            return;
-          }
-          d.lis[F.off[cl] + slot] = make_node(j + 2, jx, jy, jz);
-          F.cnt[cl] = slot + 1;
-        }
-      }
-    }
-    F.cnt[lev] = w;
-  }
-  S.pos = br.pos();
-  S.klip = klip;
-  F.nlog = nlog;
-}
-
-// All threads: turn the log of the plane into mask updates.
-static __device__ void dec_apply_log(DecChunk& d, FastShared& F)
-{
-  const unsigned long long nlog = F.nlog;
-  const unsigned long long nx = d.nx, nxy = (unsigned long long)d.nx * d.ny;
-  for (unsigned long long e = threadIdx.x; e < nlog; e += kDecThreads) {
-    const unsigned long long v = d.log[e];
-    const unsigned long long base = v & 0xffffffffull;
-    const unsigned sigm = unsigned(v >> 32) & 0xffu, sgnm = unsigned(v >> 40) & 0xffu;
-    const int sx = int(v >> 48) & 1, sy = int(v >> 49) & 1, sz = int(v >> 50) & 1;
-    const int nch = 1 << (sx + sy + sz);
-    for (int kk = 0; kk < nch; kk++) {
-      const unsigned cx = sx ? (unsigned(kk) & 1u) : 0u;
-      const unsigned cy = sy ? ((unsigned(kk) >> sx) & 1u) : 0u;
-      const unsigned cz = sz ? ((unsigned(kk) >> (sx + sy)) & 1u) : 0u;
-      const unsigned long long i = base + cx + cy * nx + cz * nxy;
-      const unsigned bit = 1u << (i & 31);
-      if ((sigm >> kk) & 1u) {
-        atomicOr(&d.newm[i >> 5], bit);
-        if (!((sgnm >> kk) & 1u))
-          atomicAnd(&d.signs[i >> 5], ~bit);
-      }
-      else
-        atomicOr(&d.lip[i >> 5], bit);
-    }
-  }
-}
-
 // ---- the kernel ---------------------------------------------------------------------------------
 
 template <class T>
@@ -684,13 +492,11 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
 {
   __shared__ DecShared S;
   __shared__ DecFrame stack[kDecMaxDepth];
-  __shared__ FastShared F;
   const unsigned c = blockIdx.x;
   DecChunk& d = chunks[c];
-  if (d.skip || d.planes == 0)
+  if (d.skip || d.planes == 0 || d.pow2)   // power-of-two trees: k_speck_decode_fast
     return;
   const int tid = threadIdx.x;
-  const bool fast = d.pow2 != 0;
   if (tid == 0) {
     S.pos = 0;
     S.klip = 0;
@@ -706,13 +512,6 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
       d.lis[d.lis_off[lis] + d.lis_cnt[lis]] = nd;
       d.lis_cnt[lis]++;
     }
-    if (fast) {
-      for (int l = 0; l <= d.nlis; l++)
-        F.off[l] = d.lis_off[l];
-      for (int l = 0; l < d.nlis; l++)
-        F.cnt[l] = d.lis_cnt[l];
-      F.nlog = 0;
-    }
   }
   __syncthreads();
   int n = d.planes - 1;
@@ -720,19 +519,11 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
   for (int bp = 0; bp < d.planes; bp++, n--) {
     dec_lip_pass(d, S);
     __syncthreads();   // every thread has read the LIP population before the walker changes it
-    if (tid == 0) {
-      if (fast)
-        dec_lis_walk_pow2(d, S, F);
-      else
-        dec_lis_walk<T>(d, tree, c, S, stack);
-    }
+    if (tid == 0)
+      dec_lis_walk<T>(d, tree, c, S, stack);
     __syncthreads();
     if (d.err)
       return;
-    if (fast) {
-      dec_apply_log(d, F);
-      __syncthreads();
-    }
     if (S.pos >= d.avail) {
       pending_new = true;
       break;
@@ -743,134 +534,6 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
   }
   if (pending_new)
     dec_refine_pass(d, S, n, false);
-}
-
-// ---------------------------------------------------------------------------------------------
-// host driver
-// ---------------------------------------------------------------------------------------------
-
-// out[w] = little-endian word w of the byte string src[0, len), zero beyond it
-static __global__ void k_stage_bits(const DecChunk* chunks, const unsigned char* const* srcs,
-                                    const unsigned long long* lens, const unsigned long long* words)
-{
-  const unsigned c = blockIdx.y;
-  const unsigned char* src = srcs[c];
-  const unsigned long long len = lens[c], nw = words[c];
-  uint32_t* out = const_cast<uint32_t*>(chunks[c].bits);
-  const unsigned long long avail = chunks[c].avail;
-  for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nw;
-       w += (unsigned long long)gridDim.x * blockDim.x) {
-    uint32_t v = 0;
-    for (int b = 0; b < 4; b++) {
-      const unsigned long long i = w * 4 + b;
-      if (i < len)
-        v |= uint32_t(src[i]) << (8 * b);
-    }
-    if (w * 32 >= avail)   // bits the stream does not really hold read as zero
-      v = 0;
-    else if (avail - w * 32 < 32)
-      v &= (1u << (avail - w * 32)) - 1u;
-    out[w] = v;
-  }
-}
-
-// Decodes every job; on return w.h[c].lsp is the final significance mask of job c.
-template <class T>
-void run_decoder(DecWork& w, const std::vector<DecJob>& jobs, const typename T::Data& tree,
-                 cudaStream_t st)
-{
-  const int nj = int(jobs.size());
-  if (nj == 0)
-    return;
-  size_t mask_words = 0, lis_entries = 0, cnt_entries = 0, stage_words = 0, log_entries = 0;
-  std::vector<size_t> mw(nj), sw(nj);
-  for (int c = 0; c < nj; c++) {
-    const DecJob& j = jobs[c];
-    mw[c] = j.skip ? 0 : (size_t(j.n + 31) / 32 + 4);
-    sw[c] = j.skip ? 0 : (size_t(j.payload_bytes) / 4 + 4);
-    mask_words += 5 * mw[c];
-    lis_entries += j.skip ? 0 : j.lis_total;
-    cnt_entries += j.skip ? 0 : size_t(j.nlis + 1);
-    stage_words += sw[c];
-    log_entries += j.skip ? 0 : size_t(j.log_entries);
-  }
-  w.logs.reserve(log_entries * 8 + 16);
-  w.masks.reserve(mask_words * 4 + 16);
-  w.lis.reserve(lis_entries * 8 + 16);
-  w.lis_cnt.reserve(cnt_entries * 4 + 16);
-  w.stage.reserve(stage_words * 4 + 16);
-  rt::dset(w.masks.p, 0, mask_words * 4, st);
-  w.h.assign(nj, DecChunk());
-  std::vector<const unsigned char*> srcs(nj);
-  std::vector<unsigned long long> lens(nj), words(nj);
-  size_t om = 0, ol = 0, oc = 0, os = 0, og = 0, max_words = 1;
-  for (int c = 0; c < nj; c++) {
-    const DecJob& j = jobs[c];
-    DecChunk& d = w.h[c];
-    std::memset(&d, 0, sizeof(d));
-    d.skip = j.skip ? 1 : 0;
-    srcs[c] = j.d_payload;
-    lens[c] = j.skip ? 0 : j.payload_bytes;
-    words[c] = sw[c];
-    if (j.skip)
-      continue;
-    d.n = j.n;
-    d.shape = j.shape;
-    d.planes = j.planes;
-    d.avail = std::min<unsigned long long>(j.total_bits, j.payload_bytes * 8ull);
-    d.wide = j.wide;
-    d.mag = j.mag;
-    d.signs = j.signs;
-    uint32_t* m = w.masks.as<uint32_t>() + om;
-    d.lip = m;
-    d.lsp = m + mw[c];
-    d.newm = m + 2 * mw[c];
-    d.sigarr = m + 3 * mw[c];
-    d.signarr = m + 4 * mw[c];
-    om += 5 * mw[c];
-    d.lis = w.lis.as<node_t>() + ol;
-    ol += j.lis_total;
-    d.lis_off = j.d_lis_off;
-    d.lis_cnt = w.lis_cnt.as<unsigned>() + oc;
-    oc += size_t(j.nlis + 1);
-    d.nlis = j.nlis;
-    d.bits = w.stage.as<uint32_t>() + os;
-    d.stage_words = sw[c];
-    os += sw[c];
-    d.pow2 = j.pow2;
-    d.Dx = j.Dx; d.Dy = j.Dy; d.Dz = j.Dz;
-    d.nx = j.nx; d.ny = j.ny;
-    d.log = w.logs.as<unsigned long long>() + og;
-    d.log_cap = j.log_entries;
-    og += size_t(j.log_entries);
-    max_words = std::max(max_words, sw[c]);
-  }
-  w.dchunks.reserve(sizeof(DecChunk) * nj);
-  rt::h2d(w.dchunks.p, w.h.data(), sizeof(DecChunk) * nj, st);
-  const size_t aux_bytes = size_t(nj) * 24;
-  w.aux.reserve(aux_bytes);
-  unsigned char* aux = w.aux.as<unsigned char>();
-  rt::h2d(aux, srcs.data(), nj * 8, st);
-  rt::h2d(aux + nj * 8, lens.data(), nj * 8, st);
-  rt::h2d(aux + nj * 16, words.data(), nj * 8, st);
-  DecChunk* dch = w.dchunks.as<DecChunk>();
-  {
-    rt::ProfScope ps("dec.stage_bits", st);
-    const unsigned gx = unsigned(std::min<size_t>((max_words + 255) / 256, 256));
-    LAUNCH(k_stage_bits, dim3(gx, nj), dim3(256), 0, st, dch,
-           reinterpret_cast<const unsigned char* const*>(aux),
-           reinterpret_cast<const unsigned long long*>(aux + nj * 8),
-           reinterpret_cast<const unsigned long long*>(aux + nj * 16));
-  }
-  {
-    rt::ProfScope ps("dec.speck_decode", st);
-    LAUNCH(k_speck_decode<T>, dim3(nj), dim3(kDecThreads), 0, st, dch, tree);
-  }
-  rt::d2h(w.h.data(), w.dchunks.p, sizeof(DecChunk) * nj, st);
-  rt::sync(st);
-  for (int c = 0; c < nj; c++)
-    if (w.h[c].err)
-      throw std::runtime_error("SPECK decoder: list capacity exceeded (corrupt stream?)");
 }
 
 }  // namespace sperr_b200

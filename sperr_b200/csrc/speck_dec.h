@@ -33,14 +33,20 @@ struct DecChunk {
   unsigned* lis_cnt;             // nlis counters
   int nlis;
   unsigned err;                  // 1: a list overflowed its capacity
-  // fast path for power-of-two dyadic chunks (ShapeHeader::pow2)
+  // fast path for power-of-two trees (speck_dec_fast.cuh): every set is an aligned box
   int pow2;
   int Dx, Dy, Dz;                // bisection depth of every axis
   unsigned nx, ny;
-  unsigned long long* log;       // bottom-level sets decoded in the current plane
-  unsigned long long log_cap;
+  int nroots;
+  unsigned long long roots[kMaxRoots];   // initial sets as (depth << 32 | linear index), list order
+  unsigned long long* scr;       // per-thread append staging of the token expanders
   unsigned long long stage_words;   // words in `bits`
+  // clock64() totals of the fast decoder's phases (thread 0): 0 LIP pass, 1 window staging + body
+  // tables, 2 token chains, 3 token expansion + commit, 4 tree walker, 5 refinement, 6 windows built
+  unsigned long long prof[8];
 };
+
+constexpr int kFastScrPerThread = 96;   // entries of DecChunk::scr per decoder thread
 
 // One integer stream to decode. `mag` (zeroed) and `signs` (all ones) are provided by the caller.
 struct DecJob {
@@ -57,13 +63,14 @@ struct DecJob {
   int nlis = 0;
   const unsigned long long* d_lis_off = nullptr;   // device, nlis + 1 entries
   unsigned long long lis_total = 0;                // total list capacity (entries)
-  int pow2 = 0, Dx = 0, Dy = 0, Dz = 0;            // 3D fast path (see DecChunk)
+  int pow2 = 0, Dx = 0, Dy = 0, Dz = 0;            // fast path (see DecChunk)
   unsigned nx = 0, ny = 0;
-  unsigned long long log_entries = 0;
+  int nroots = 0;
+  unsigned long long roots[kMaxRoots] = {0};
 };
 
 struct DecWork {
-  rt::DBuf dchunks, masks, lis, lis_cnt, stage, aux, logs;
+  rt::DBuf dchunks, masks, lis, lis_cnt, stage, aux, scr;
   std::vector<DecChunk> h;   // copy of the device state after the last run
 };
 
