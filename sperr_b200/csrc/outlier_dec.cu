@@ -43,40 +43,4 @@ void speck1d_decode(DecWork& w, const std::vector<DecJob>& jobs, cudaStream_t st
   run_decoder<DecTree1D>(w, jobs, tree, st);
 }
 
-// coef[i] += corrector for every decoded outlier (the significant pixels of the 1D decode)
-__global__ void k_outlier_apply(const DecChunk* jobs, const ChunkDev* chunks, const double* tols)
-{
-  const unsigned c = blockIdx.y;
-  const DecChunk& d = jobs[c];
-  if (d.skip || d.planes == 0)
-    return;
-  const ChunkDev& ch = chunks[c];
-  const double tol = tols[c];
-  const unsigned long long words = (d.n + 31) / 32;
-  for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < words;
-       j += (unsigned long long)gridDim.x * blockDim.x) {
-    unsigned m = d.lsp[j];
-    while (m) {
-      const int bit = __ffs(m) - 1;
-      m &= m - 1;
-      const unsigned long long i = j * 32 + bit;
-      const unsigned long long mg = d.wide ? reinterpret_cast<const unsigned long long*>(d.mag)[i]
-                                           : (unsigned long long)reinterpret_cast<const unsigned*>(d.mag)[i];
-      if (mg == 0)
-        continue;
-      const bool pos = (d.signs[i >> 5] >> (i & 31)) & 1u;
-      double e = mg == 1 ? 1.1 : __dsub_rn(__ull2double_rn(mg), 0.25);
-      e = __dmul_rn(e, __dmul_rn(tol, pos ? 1.0 : -1.0));
-      ch.coef[i] = __dadd_rn(ch.coef[i], e);
-    }
-  }
-}
-
-void launch_outlier_apply(const DecChunk* d_jobs, const ChunkDev* d_chunks, const double* d_tols,
-                          int nchunks, size_t max_n, cudaStream_t st)
-{
-  const unsigned gx = unsigned(std::min<size_t>((max_n / 32 + 255) / 256 + 1, 512));
-  LAUNCH(k_outlier_apply, dim3(gx, nchunks), dim3(256), 0, st, d_jobs, d_chunks, d_tols);
-}
-
 }  // namespace sperr_b200

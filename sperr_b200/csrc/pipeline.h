@@ -50,7 +50,7 @@ class Decompressor {
                  const ChunkStream* cs, const SrcVol& dst, cudaStream_t st);
   BatchBuffers b_;
   DecWork w3_, w1_;
-  rt::DBuf ids_, lis_off1_, omag_, osigns_, tols_;
+  rt::DBuf ids_, lis_off1_, tols_;
 };
 
 // Largest number of chunks processed at once (bounded by the list-key layout and by memory).

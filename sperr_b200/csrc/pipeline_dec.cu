@@ -114,23 +114,19 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     }
   }
 
-  b_.setup(chunks, true, true, any_wide, st, false);
+  (void)any_wide;
+  (void)any_owide;
+  b_.setup(chunks, true, false, false, st, false);
   for (int c = 0; c < nc; c++) {
     ChunkDev& d = b_.h[c];
     d.is_const = ps[c].is_const ? 1 : 0;
     d.first_val = ps[c].cval;
     d.mean = ps[c].mean;
     d.q = ps[c].q;
-    d.wide = any_wide ? 1 : 0;
   }
   b_.push(st);
 
-  // ---- SPECK3D decode into (mag, signs) ----
-  {
-    rt::ProfScope pz("d.clear", st);
-    rt::dset(b_.mag.p, 0, b_.mag_elems * (any_wide ? 8 : 4), st);
-    rt::dset(b_.signs.p, 0xFF, b_.sign_words * 4, st);
-  }
+  // ---- SPECK3D decode: sorting passes per chunk, then magnitudes + de-quantisation grid-wide ----
   std::vector<DecJob> jobs(nc);
   for (int c = 0; c < nc; c++) {
     DecJob& j = jobs[c];
@@ -142,9 +138,6 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     j.payload_bytes = ps[c].spk_bytes;
     j.planes = ps[c].planes;
     j.total_bits = ps[c].total_bits;
-    j.mag = b_.h[c].mag;
-    j.signs = b_.h[c].signs;
-    j.wide = any_wide ? 1 : 0;
     j.nlis = sh.h.nlis;
     // lis_off lives inside the ShapeHeader copy on the device
     j.d_lis_off = nullptr;
@@ -178,12 +171,13 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     rt::ProfScope pd("d.speck3d", st);
     speck3d_decode(w3_, jobs, b_.dev_shapes(), st);
   }
-
-  // ---- inverse quantisation and inverse transform ----
   {
-    rt::ProfScope pq("d.inv_quantize", st);
-    launch_inv_quantize(b_.dev(), nc, b_.max_n, st);
+    rt::ProfScope pq("d.reconstruct", st);
+    w3_.fill_n = b_.max_n;
+    speck_reconstruct(w3_, b_.dev(), 0, nullptr, st);
   }
+
+  // ---- inverse transform ----
   std::vector<std::vector<int>> groups(b_.shapes.size());
   for (int c = 0; c < nc; c++)
     if (!ps[c].is_const)
@@ -211,18 +205,13 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
   // ---- outliers: SPECK1D decode + correction (src/SPECK_FLT.cpp:576-585) ----
   if (any_out) {
     rt::ProfScope po("d.outliers", st);
-    size_t tot_n = 0, tot_w = 0, tot_lis = 0;
-    std::vector<size_t> on(nc), ow(nc);
+    size_t tot_lis = 0;
     std::vector<unsigned long long> h_lis_off;
     std::vector<size_t> lo(nc, 0);
     std::vector<int> nl(nc, 0);
     for (int c = 0; c < nc; c++) {
-      on[c] = tot_n;
-      ow[c] = tot_w;
       if (!ps[c].has_out || ps[c].oplanes == 0)
         continue;
-      tot_n += (b_.h[c].n + 63) & ~size_t(63);
-      tot_w += (b_.h[c].n + 31) / 32 + 2;
       // list capacities: level l holds at most min(2^l, bits in the stream) live sets
       const int nlis = int(num_of_partitions(b_.h[c].n)) + 2;
       nl[c] = nlis;
@@ -235,12 +224,7 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
       }
       tot_lis = std::max<size_t>(tot_lis, acc);
     }
-    const int ow_bytes = any_owide ? 8 : 4;
-    omag_.reserve(tot_n * ow_bytes + 16);
-    osigns_.reserve(tot_w * 4 + 16);
     lis_off1_.reserve(h_lis_off.size() * 8 + 16);
-    rt::dset(omag_.p, 0, tot_n * ow_bytes, st);
-    rt::dset(osigns_.p, 0xFF, tot_w * 4, st);
     rt::h2d(lis_off1_.p, h_lis_off.data(), h_lis_off.size() * 8, st);
     std::vector<DecJob> oj(nc);
     std::vector<double> tols(nc, 0.0);
@@ -254,9 +238,6 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
       j.payload_bytes = ps[c].out_bytes;
       j.planes = ps[c].oplanes;
       j.total_bits = ps[c].ototal;
-      j.mag = omag_.as<unsigned char>() + on[c] * ow_bytes;
-      j.signs = osigns_.as<uint32_t>() + ow[c];
-      j.wide = any_owide ? 1 : 0;
       j.nlis = nl[c];
       j.d_lis_off = lis_off1_.as<unsigned long long>() + lo[c];
       j.lis_total = h_lis_off[lo[c] + nl[c]];
@@ -280,7 +261,8 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     speck1d_decode(w1_, oj, st);
     tols_.reserve(nc * 8);
     rt::h2d(tols_.p, tols.data(), nc * 8, st);
-    launch_outlier_apply(w1_.dchunks.as<DecChunk>(), b_.dev(), tols_.as<double>(), nc, b_.max_n, st);
+    w1_.fill_n = 0;
+    speck_reconstruct(w1_, b_.dev(), 1, tols_.as<double>(), st);
     rt::sync(st);  // `tols`, `h_lis_off` leave scope
   }
 

@@ -30,7 +30,8 @@ constexpr int kDecWarps = kDecThreads / 32;
 
 struct DecShared {
   unsigned long long pos;        // read position (bits)
-  unsigned long long klip, klsp; // population of the LIP / LSP masks
+  unsigned long long klip, klsp; // population of the LIP / number of significant coefficients
+  unsigned long long knew;       // coefficients found significant in the current plane
   unsigned long long endpos;
   unsigned long long wtot[kDecWarps];
   unsigned long long wtot2[kDecWarps];
@@ -126,26 +127,9 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
   return v;
 }
 
-// ---- magnitudes -------------------------------------------------------------------------------
-
-__device__ __forceinline__ void mag_set(const DecChunk& d, unsigned long long i, unsigned long long v)
-{
-  if (d.wide)
-    reinterpret_cast<unsigned long long*>(d.mag)[i] = v;
-  else
-    reinterpret_cast<unsigned*>(d.mag)[i] = unsigned(v);
-}
-__device__ __forceinline__ void mag_add(const DecChunk& d, unsigned long long i, long long dv)
-{
-  if (d.wide)
-    reinterpret_cast<unsigned long long*>(d.mag)[i] += (unsigned long long)dv;
-  else
-    reinterpret_cast<unsigned*>(d.mag)[i] += unsigned(dv);
-}
-
 // ---- LIP part ---------------------------------------------------------------------------------
 
-static __device__ void dec_lip_pass(DecChunk& d, DecShared& S)
+static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long K = S.klip;
@@ -267,27 +251,30 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S)
     unsigned m = j < w1 ? d.lip[j] : 0u;
     const unsigned long long c = __popc(m);
     const unsigned long long inc = warp_incl_scan(c, lane);
-    unsigned long long k = run + inc - c;
+    const unsigned long long k = run + inc - c;
     run += __shfl_sync(0xffffffffu, inc, 31);
     if (m) {
-      unsigned keep = m, nw = 0, neg = 0;
-      while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        if ((d.sigarr[k >> 5] >> (k & 31)) & 1u) {
-          keep &= ~(1u << bit);
-          nw |= 1u << bit;
-          if (!((d.signarr[k >> 5] >> (k & 31)) & 1u))
-            neg |= 1u << bit;
+      // the c tokens of this word: bits [k, k + c) of the two result arrays
+      const unsigned long long wi = k >> 5;
+      const unsigned sh = unsigned(k & 31);
+      unsigned sg = __funnelshift_r(d.sigarr[wi], d.sigarr[wi + 1], sh);
+      if (c < 32)
+        sg &= (1u << c) - 1u;
+      if (sg) {
+        const unsigned sn = __funnelshift_r(d.signarr[wi], d.signarr[wi + 1], sh);
+        unsigned keep = m;
+        int t = 0;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          if ((sg >> t) & 1u) {
+            keep &= ~(1u << bit);
+            d.pl[j * 32 + bit] = uint8_t(n_plane | (((sn >> t) & 1u) ? 0 : 0x80));
+          }
+          t++;
         }
-        k++;
-      }
-      if (nw) {
         d.lip[j] = keep;
-        d.newm[j] |= nw;
-        if (neg)
-          d.signs[j] &= ~neg;
-        nsig += __popc(nw);
+        nsig += __popc(sg);
       }
     }
   }
@@ -302,92 +289,30 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S)
     for (int i = 0; i < kDecWarps; i++)
       t += S.wtot[i];
     S.klip -= t;
+    S.knew += t;
     S.pos = S.endpos;
   }
   __syncthreads();
 }
 
-// ---- refinement part + promotion of the newly significant pixels -----------------------------
-// refine: read bits for the LSP pixels (src/SPECK_INT.cpp:359-469); always: newly significant
-// pixels get their initial value thr + thr - thr/2 - 1 and join the LSP.
-static __device__ void dec_refine_pass(DecChunk& d, DecShared& S, int n_plane, bool refine)
+// ---- end of a plane: where its refinement bits are (src/SPECK_INT.cpp:165-228, 359-469) ---------
+// Called by thread 0 after the sorting pass of plane n. Returns false when decoding stops.
+static __device__ bool dec_plane_end(DecChunk& d, DecShared& S, int n_plane)
 {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned long long thr = 1ull << n_plane;
-  const unsigned long long half = thr >> 1;
-  const unsigned long long init = thr + thr - half - 1ull;
-  const unsigned long long words = (d.n + 31) / 32;
-  const unsigned long long per_warp = ((words + kDecWarps - 1) / kDecWarps + 31) / 32 * 32;
-  const unsigned long long w0 = per_warp * warp, w1 = min(words, w0 + per_warp);
-  const unsigned long long R = S.pos;
-  unsigned long long nref = 0;
-  if (refine) {
-    nref = min(S.klsp, d.avail - R);
-    unsigned long long cnt = 0;
-    for (unsigned long long j = w0 + lane; j < w1; j += 32)
-      cnt += __popc(d.lsp[j]);
-    for (int o = 16; o; o >>= 1)
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0)
-      S.wtot[warp] = cnt;
-    __syncthreads();
-    if (warp == 0) {
-      const unsigned long long v = S.wtot[lane];
-      const unsigned long long inc = warp_incl_scan(v, lane);
-      S.wtot[lane] = inc - v;
-    }
-    __syncthreads();
+  bool go = true;
+  if (S.pos >= d.avail)
+    go = false;   // the stream ended inside / right after the sorting pass: no refinement bits
+  else {
+    const unsigned long long nref = min(S.klsp, d.avail - S.pos);
+    d.ref_base[n_plane] = S.pos;
+    d.ref_cnt[n_plane] = nref;
+    S.pos += nref;
+    if (S.pos >= d.avail)
+      go = false;
   }
-  unsigned long long run = refine ? S.wtot[warp] : 0;
-  unsigned long long nnew = 0;
-  for (unsigned long long j0 = w0; j0 < w1; j0 += 32) {
-    const unsigned long long j = j0 + lane;
-    unsigned m = (refine && j < w1) ? d.lsp[j] : 0u;
-    const unsigned nw = j < w1 ? d.newm[j] : 0u;
-    if (refine) {
-      const unsigned long long c = __popc(m);
-      const unsigned long long inc = warp_incl_scan(c, lane);
-      unsigned long long k = run + inc - c;
-      run += __shfl_sync(0xffffffffu, inc, 31);
-      while (m && k < nref) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        const unsigned long long bp = R + k;
-        const unsigned b = (d.bits[bp >> 5] >> (bp & 31)) & 1u;
-        const unsigned long long i = j * 32 + bit;
-        if (thr >= 2)
-          mag_add(d, i, b ? (long long)half : -(long long)half);
-        else if (b)
-          mag_add(d, i, 1);
-        k++;
-      }
-    }
-    if (nw) {
-      unsigned t = nw;
-      while (t) {
-        const int bit = __ffs(t) - 1;
-        t &= t - 1;
-        mag_set(d, j * 32 + bit, init);
-      }
-      d.lsp[j] |= nw;
-      d.newm[j] = 0;
-      nnew += __popc(nw);
-    }
-  }
-  for (int o = 16; o; o >>= 1)
-    nnew += __shfl_xor_sync(0xffffffffu, nnew, o);
-  __syncthreads();
-  if (lane == 0)
-    S.wtot2[warp] = nnew;
-  __syncthreads();
-  if (tid == 0) {
-    unsigned long long t = 0;
-    for (int i = 0; i < kDecWarps; i++)
-      t += S.wtot2[i];
-    S.klsp += t;
-    S.pos = R + nref;
-  }
-  __syncthreads();
+  S.klsp += S.knew;
+  S.knew = 0;
+  return go;
 }
 
 // ---- LIS part: depth-first walk by one thread ---------------------------------------------------
@@ -401,7 +326,8 @@ struct DecFrame {
 
 template <class T>
 __device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c, BitReader& br,
-                           node_t root, int root_lis, DecFrame* stack, unsigned long long& klip)
+                           node_t root, int root_lis, DecFrame* stack, unsigned long long& klip,
+                           unsigned long long& knew, int n_plane)
 {
   int depth = 0;
   stack[0].nch = T::children(tree, d, c, root, root_lis, stack[0].kid);
@@ -422,9 +348,8 @@ __device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c
       const unsigned long long i = ch.idx;
       if (sig) {
         const unsigned sgn = br.get();
-        d.newm[i >> 5] |= 1u << (i & 31);
-        if (!sgn)
-          d.signs[i >> 5] &= ~(1u << (i & 31));
+        d.pl[i] = uint8_t(n_plane | (sgn ? 0 : 0x80));
+        knew++;
         f.sigc++;
       }
       else {
@@ -458,11 +383,11 @@ __device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c
 
 template <class T>
 __device__ void dec_lis_walk(DecChunk& d, const typename T::Data& tree, unsigned c, DecShared& S,
-                             DecFrame* stack)
+                             DecFrame* stack, int n_plane)
 {
   BitReader br;
   br.init(d, S.pos);
-  unsigned long long klip = S.klip;
+  unsigned long long klip = S.klip, knew = S.knew;
   for (int lev = d.nlis - 1; lev >= 0; lev--) {
     const unsigned cnt = d.lis_cnt[lev];
     if (cnt == 0)
@@ -475,7 +400,7 @@ __device__ void dec_lis_walk(DecChunk& d, const typename T::Data& tree, unsigned
         list[w++] = nd;
         continue;
       }
-      dec_expand<T>(d, tree, c, br, nd, lev, stack, klip);
+      dec_expand<T>(d, tree, c, br, nd, lev, stack, klip, knew, n_plane);
       if (d.err)
         return;
     }
@@ -483,6 +408,7 @@ __device__ void dec_lis_walk(DecChunk& d, const typename T::Data& tree, unsigned
   }
   S.pos = br.pos;
   S.klip = klip;
+  S.knew = knew;
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
@@ -492,6 +418,7 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
 {
   __shared__ DecShared S;
   __shared__ DecFrame stack[kDecMaxDepth];
+  __shared__ int s_go;
   const unsigned c = blockIdx.x;
   DecChunk& d = chunks[c];
   if (d.skip || d.planes == 0 || d.pow2)   // power-of-two trees: k_speck_decode_fast
@@ -501,6 +428,7 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
     S.pos = 0;
     S.klip = 0;
     S.klsp = 0;
+    S.knew = 0;
     S.endpos = 0;
     for (int l = 0; l < d.nlis; l++)
       d.lis_cnt[l] = 0;
@@ -515,25 +443,17 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
   }
   __syncthreads();
   int n = d.planes - 1;
-  bool pending_new = false;
   for (int bp = 0; bp < d.planes; bp++, n--) {
-    dec_lip_pass(d, S);
+    dec_lip_pass(d, S, n);
     __syncthreads();   // every thread has read the LIP population before the walker changes it
-    if (tid == 0)
-      dec_lis_walk<T>(d, tree, c, S, stack);
-    __syncthreads();
-    if (d.err)
-      return;
-    if (S.pos >= d.avail) {
-      pending_new = true;
-      break;
+    if (tid == 0) {
+      dec_lis_walk<T>(d, tree, c, S, stack, n);
+      s_go = (!d.err && dec_plane_end(d, S, n)) ? 1 : 0;
     }
-    dec_refine_pass(d, S, n, true);
-    if (S.pos >= d.avail)
-      break;
+    __syncthreads();
+    if (!s_go)
+      return;
   }
-  if (pending_new)
-    dec_refine_pass(d, S, n, false);
 }
 
 }  // namespace sperr_b200

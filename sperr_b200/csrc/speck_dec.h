@@ -1,4 +1,4 @@
-// Integer SPECK decoders: job description and host entry points (kernels in speck_dec.cuh).
+// Integer SPECK decoders: job description and host entry points (kernels in speck_dec*.cuh).
 #pragma once
 
 #include "kernels.h"
@@ -12,7 +12,15 @@ struct DChild {
   int pixel;
 };
 
+constexpr int kMaxPlanes = 64;
+
 // Decoder state of one chunk (device memory).
+//
+// The per-chunk kernels decode only the SORTING passes: they record for every coefficient the plane
+// at which it became significant (and its sign) in `pl`, and for every plane where its refinement
+// bits sit in the stream. Magnitudes are rebuilt afterwards by grid-wide kernels (k_rec_*), because
+// a coefficient's refinement bit in plane n is simply bit number rank_n(i) of that plane's section,
+// rank_n(i) = how many coefficients before i (raster order) were significant before plane n.
 struct DecChunk {
   const uint32_t* bits;          // payload, staged 4-byte aligned and zero padded
   unsigned long long avail;      // bits really present: min(total_bits, 8 * payload bytes)
@@ -20,12 +28,8 @@ struct DecChunk {
   int skip;                      // nothing to decode (constant chunk, or no stream)
   unsigned long long n;          // number of coefficients
   int shape;                     // 3D: index into the shape tables
-  int wide;                      // magnitudes are 64-bit
-  void* mag;                     // n magnitudes, zero on entry
-  uint32_t* signs;               // bit i = 1: non-negative; all ones on entry
-  uint32_t* lip;                 // masks, all zero on entry
-  uint32_t* lsp;
-  uint32_t* newm;
+  uint8_t* pl;                   // n bytes, 0xFF on entry: plane of significance | negative << 7
+  uint32_t* lip;                 // LIP mask, all zero on entry
   uint32_t* sigarr;              // scratch of the LIP pass (ceil(n / 32) + 2 words each)
   uint32_t* signarr;
   node_t* lis;                   // list storage
@@ -39,16 +43,17 @@ struct DecChunk {
   unsigned nx, ny;
   int nroots;
   unsigned long long roots[kMaxRoots];   // initial sets as (depth << 32 | linear index), list order
-  unsigned long long* scr;       // per-thread append staging of the token expanders
-  unsigned long long stage_words;   // words in `bits`
+  unsigned long long stage_words;        // words in `bits`
+  // refinement sections: plane n's bits start at ref_base[n]; the first ref_cnt[n] significant
+  // coefficients (raster order) own one bit each (fewer than all of them only where a truncated
+  // stream ends inside the section)
+  unsigned long long ref_base[kMaxPlanes], ref_cnt[kMaxPlanes];
   // clock64() totals of the fast decoder's phases (thread 0): 0 LIP pass, 1 window staging + body
-  // tables, 2 token chains, 3 token expansion + commit, 4 tree walker, 5 refinement, 6 windows built
+  // tables, 2 token chains, 3 token expansion, 4 tree walker, 6 windows built
   unsigned long long prof[8];
 };
 
-constexpr int kFastScrPerThread = 96;   // entries of DecChunk::scr per decoder thread
-
-// One integer stream to decode. `mag` (zeroed) and `signs` (all ones) are provided by the caller.
+// One integer stream to decode.
 struct DecJob {
   unsigned long long n = 0;
   int shape = 0;
@@ -57,9 +62,6 @@ struct DecJob {
   unsigned long long payload_bytes = 0;
   int planes = 0;
   unsigned long long total_bits = 0;
-  void* mag = nullptr;
-  uint32_t* signs = nullptr;
-  int wide = 0;
   int nlis = 0;
   const unsigned long long* d_lis_off = nullptr;   // device, nlis + 1 entries
   unsigned long long lis_total = 0;                // total list capacity (entries)
@@ -70,15 +72,25 @@ struct DecJob {
 };
 
 struct DecWork {
-  rt::DBuf dchunks, masks, lis, lis_cnt, stage, aux, scr;
+  rt::DBuf dchunks, masks, pl, lis, lis_cnt, stage, aux, counts;
   std::vector<DecChunk> h;   // copy of the device state after the last run
+  size_t max_n = 0;        // largest decoded job
+  size_t fill_n = 0;       // largest chunk of the batch (set by the caller; zero-fill of mode 0)
+  int max_planes = 0;
 };
 
-// Decodes every job; afterwards w.h[c].lsp is the final significance mask of job c.
+// Decodes the sorting passes of every job (see DecChunk).
 void speck3d_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d_shapes,
                     cudaStream_t st);
 void speck1d_decode(DecWork& w, const std::vector<DecJob>& jobs, cudaStream_t st);
-void launch_outlier_apply(const DecChunk* d_jobs, const ChunkDev* d_chunks, const double* d_tols,
-                          int nchunks, size_t max_n, cudaStream_t st);
+
+// Rebuilds the magnitudes from the decoded state of speck*_decode and
+//   mode 0: writes the de-quantised coefficients q * mag * sign to chunks[c].coef
+//           (SPECK_FLT::m_midtread_inv_quantize, /root/reference/src/SPECK_FLT.cpp:373-399);
+//   mode 1: treats them as outlier correctors and adds them to chunks[c].coef with tolerance
+//           tols[c] (Outlier_Coder::m_inverse_quantize, src/Outlier_Coder.cpp:206-234;
+//           src/SPECK_FLT.cpp:576-585).
+void speck_reconstruct(DecWork& w, const ChunkDev* d_chunks, int mode, const double* d_tols,
+                       cudaStream_t st);
 
 }  // namespace sperr_b200

@@ -35,8 +35,11 @@ constexpr int kFBits = kFW + kFLA;
 constexpr int kFBodyA = kFW + 1248;   // bodyA entries (bodyB needs up to +136 beyond its own range)
 constexpr int kFBodyB = kFW + 1104;   // bodyB entries (bodyC needs up to +1096)
 constexpr int kFNext = kFW + 1112;    // chain positions incl. the absorbing exits beyond the window
-constexpr int kFTok = 1024;           // tokens the walker may queue per round (one per thread)
+constexpr int kFTok = 1024;           // size-C tokens queued per round
+constexpr int kFQ = 2048;             // size-B / size-A tokens in flight (a slice of 256 parents)
+constexpr int kFSlice = kFQ / 8;
 constexpr int kFMaxDepth = 32;
+constexpr int kFRoots = 2048;         // roots of the walker's current list staged per round
 
 struct FastSmem {
   uint32_t bits[kFBits / 32 + 4];     // window of the stream, word aligned; bit q is at q + boff
@@ -46,8 +49,15 @@ struct FastSmem {
   uint16_t nxt[2][kFNext + 8];
   uint32_t mark[kFW / 32];
   uint16_t T1[256], T2[2][256];       // pixel-set tables: sig(4) | sign(4) << 4 | bits << 8
-  unsigned long long tok_node[kFTok];
-  uint32_t tok_pos[kFTok];
+  // token queues of one round: sets known to be significant, by size class (C: depth J-3, B: J-2,
+  // A: J-1), as (node, window position of the first bit of the body)
+  unsigned long long qc_node[kFTok];
+  uint16_t qc_pos[kFTok];
+  unsigned long long qb_node[kFQ];
+  uint16_t qb_pos[kFQ];
+  unsigned long long qa_node[kFQ];
+  uint16_t qa_pos[kFQ];
+  unsigned nqc, nqb, nqa;
   unsigned long long off[kMaxLis + 1];
   unsigned cnt[kMaxLis];
   unsigned long long wsum[kDecWarps];
@@ -64,7 +74,11 @@ struct FastSmem {
   unsigned long long wk_node[kFMaxDepth];
   unsigned char wk_k[kFMaxDepth], wk_sig[kFMaxDepth];
   int wk_done;
-  unsigned ntok;
+  unsigned wk_q;            // window position of the walker
+  unsigned long long win_base;   // absolute bit position of the window
+  unsigned long long rs_node[kFRoots];   // staged roots: entries [rs_first, rs_first + rs_cnt) of the list
+  unsigned rs_first, rs_cnt;
+  int go;
   unsigned err;
   unsigned long long prof[8];
 };
@@ -213,18 +227,21 @@ __device__ __forceinline__ unsigned f_pixels(const FastSmem& F, unsigned q, int 
 // Stages the stream window that starts at absolute bit position `base` and fills the body tables
 // up to `kinds` (0: bodyA only, 1: + bodyB, 2: + bodyC).
 static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsigned long long base,
-                                           int kinds);
-static __device__ void f_build_window(const DecChunk& d, FastSmem& F, unsigned long long base, int kinds)
+                                           int kinds, bool after_one);
+// after_one: the top table is only needed at positions that follow a set bit (roots of a list are
+// coded as [significance bit][body if 1])
+static __device__ void f_build_window(const DecChunk& d, FastSmem& F, unsigned long long base, int kinds,
+                                      bool after_one)
 {
   F_TIC();
-  f_build_window_impl(d, F, base, kinds);
+  f_build_window_impl(d, F, base, kinds, after_one);
   __syncthreads();
   F_TOC(F, 1);
   if (threadIdx.x == 0)
     F.prof[6]++;
 }
 static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsigned long long base,
-                                           int kinds)
+                                           int kinds, bool after_one)
 {
   const int tid = threadIdx.x;
   __syncthreads();   // every reader of the previous window is done
@@ -250,6 +267,8 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
   const int nchB = f_nch(F, J - 2);
   const int nB = kinds == 1 ? kFW + 8 : kFBodyB;
   for (int q = tid; q < nB; q += kDecThreads) {
+    if (kinds == 1 && after_one && q > 0 && !f_bit(F, q - 1))
+      continue;
     unsigned pos = q;
     int c = 0;
     for (int k = 0; k < nchB; k++) {
@@ -267,6 +286,8 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
   __syncthreads();
   const int nchC = f_nch(F, J - 3);
   for (int q = tid; q < kFW + 8; q += kDecThreads) {
+    if (after_one && q > 0 && !f_bit(F, q - 1))
+      continue;
     unsigned pos = q;
     int c = 0;
     for (int k = 0; k < nchC; k++) {
@@ -281,107 +302,182 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
   }
 }
 
-// ---- token expansion (one thread per token) -----------------------------------------------------
+// ---- token expansion ------------------------------------------------------------------------------
+// A round's tokens are expanded level by level: one thread per size-C token finds its children with
+// the bodyB table (significant ones become size-B tokens, the others join list B), the same one
+// level down with bodyA, and finally one thread per size-A token decodes its pixels. Queue slots and
+// list positions come from block scans, so both keep depth-first (= stream) order.
 
-struct FastExp {
-  unsigned q;              // cursor (window position)
-  unsigned nA, nB, nlip;   // sets left for the two deepest lists, pixels that entered the LIP
-  unsigned long long* scr; // this thread's staging: [0, 16) list B, [16, 96) list A
-};
-
-// pixels of a significant bottom-level set (depth J - 1)
-static __device__ void f_expand_pixels(const DecChunk& d, const FastSmem& F, FastExp& e, unsigned ix,
-                                       unsigned iy, unsigned iz)
+// pixels of a significant bottom-level set (depth J - 1) whose body starts at window position q
+static __device__ void f_expand_pixels(const DecChunk& d, const FastSmem& F, unsigned long long nd,
+                                       unsigned q, int n_plane, unsigned& nlip, unsigned& nsig)
 {
-  const int j = F.J - 1;
+  int j;
+  unsigned ix, iy, iz;
+  f_unpack(F, nd, j, ix, iy, iz);
   const int sx = j < F.Dx, sy = j < F.Dy, sz = j < F.Dz;
   const int nch = 1 << (sx + sy + sz);
   unsigned sigm, sgnm;
-  e.q += f_pixels(F, e.q, nch, sigm, sgnm);
-  e.nlip += unsigned(nch - __popc(sigm));
+  f_pixels(F, q, nch, sigm, sgnm);
+  nsig += unsigned(__popc(sigm));
+  nlip += unsigned(nch - __popc(sigm));
   const unsigned x0 = sx ? ix * 2 : ix, y0 = sy ? iy * 2 : iy, z0 = sz ? iz * 2 : iz;
   const unsigned long long nx = F.nx, nxy = (unsigned long long)F.nx * F.ny;
   const unsigned long long base = (unsigned long long)z0 * nxy + (unsigned long long)y0 * nx + x0;
-  // pixels that differ in x only are neighbours in the masks: one update per row
+  // pixels that differ in x only are neighbours in the LIP mask: one update per row
   const int per_row = sx ? 2 : 1;
   const int rows = nch / per_row;
+  const unsigned rm = sx ? 3u : 1u;
   for (int r = 0; r < rows; r++) {
     const unsigned cy = sy ? (unsigned(r) & 1u) : 0u;
     const unsigned cz = sz ? ((unsigned(r) >> sy) & 1u) : 0u;
     const unsigned long long i = base + cy * nx + cz * nxy;
-    const unsigned rm = sx ? 3u : 1u;
     const unsigned s = (sigm >> (r * per_row)) & rm, g = (sgnm >> (r * per_row)) & rm;
-    const unsigned sh = unsigned(i & 31);   // x0 is even when the row has two pixels: same word
-    const unsigned long long w = i >> 5;
-    if (s)
-      atomicOr(&d.newm[w], s << sh);
-    if (s & ~g)
-      atomicAnd(&d.signs[w], ~((s & ~g) << sh));
-    if (rm & ~s)
-      atomicOr(&d.lip[w], (rm & ~s) << sh);
+    if (s & 1u)
+      d.pl[i] = uint8_t(n_plane | ((g & 1u) ? 0 : 0x80));
+    if (s & 2u)
+      d.pl[i + 1] = uint8_t(n_plane | ((g & 2u) ? 0 : 0x80));
+    if (rm & ~s)   // x0 is even when a row has two pixels: both bits are in the same word
+      atomicOr(&d.lip[i >> 5], (rm & ~s) << (i & 31));
   }
 }
 
-// KIND 0: depth J-1 (children are pixels), 1: depth J-2, 2: depth J-3
-template <int KIND>
-static __device__ void f_expand(const DecChunk& d, const FastSmem& F, FastExp& e, unsigned ix,
-                                unsigned iy, unsigned iz)
+// One level of expansion: `np` parent tokens (pn, pp) at depth j; significant children go to the
+// child queue (cn, cp, *ncq), the others to the list of depth j + 1. CHILD_TAB: body table of the
+// children (bodyB for size-C parents, bodyA for size-B parents).
+template <class Tab>
+static __device__ void f_expand_level(DecChunk& d, FastSmem& F, int j, const unsigned long long* pn,
+                                      const uint16_t* pp, unsigned np, const Tab* child_body,
+                                      unsigned long long* cn, uint16_t* cp, unsigned* ncq)
 {
-  if (KIND == 0) {
-    f_expand_pixels(d, F, e, ix, iy, iz);
+  const int tid = threadIdx.x;
+  const int nch = f_nch(F, j);
+  const int cl = f_lis(F, j + 1);
+  // parents beyond the thread count are handled in further sweeps (np <= kFTok or kFSlice here)
+  for (unsigned p0 = 0; p0 < np; p0 += kDecThreads) {
+    const unsigned p = p0 + tid;
+    unsigned long long kid[8];
+    uint16_t kpos[8];
+    unsigned sigmask = 0;
+    int nk = 0;
+    if (p < np) {
+      int jj;
+      unsigned ix, iy, iz;
+      f_unpack(F, pn[p], jj, ix, iy, iz);
+      unsigned q = pp[p];
+      int c = 0;
+      for (int k = 0; k < nch; k++) {
+        const bool need = c != 0 || k != nch - 1;
+        const unsigned s = need ? f_bit(F, q++) : 1u;
+        unsigned jx, jy, jz;
+        f_child(F, j, ix, iy, iz, k, jx, jy, jz);
+        kid[k] = f_pack(F, j + 1, jx, jy, jz);
+        kpos[k] = uint16_t(q);
+        if (s) {
+          c = 1;
+          sigmask |= 1u << k;
+          q += child_body[q];
+        }
+      }
+      nk = nch;
+    }
+    const unsigned nsig = unsigned(__popc(sigmask)), nins = unsigned(nk) - nsig;
+    const unsigned long long ex = f_block_scan(F, (unsigned long long)nsig | ((unsigned long long)nins << 21));
+    const unsigned long long tot = F.scan_total;
+    const unsigned exs = unsigned(ex) & 0x1fffffu, exi = unsigned(ex >> 21) & 0x1fffffu;
+    const unsigned tots = unsigned(tot) & 0x1fffffu, toti = unsigned(tot >> 21) & 0x1fffffu;
+    const unsigned qbase = *ncq;
+    const unsigned long long lbase = F.off[cl] + F.cnt[cl];
+    const bool ok = lbase + toti <= F.off[cl + 1] && qbase + tots <= unsigned(kFQ);
+    if (ok) {
+      unsigned a = qbase + exs;
+      unsigned long long b = lbase + exi;
+      for (int k = 0; k < nk; k++) {
+        if ((sigmask >> k) & 1u) {
+          cn[a] = kid[k];
+          cp[a] = kpos[k];
+          a++;
+        }
+        else
+          d.lis[b++] = kid[k];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (!ok)
+        F.err |= 1u;
+      *ncq = qbase + tots;
+      F.cnt[cl] += toti;
+    }
+    __syncthreads();
+  }
+}
+
+// size-A tokens: decode the pixels
+static __device__ void f_expand_A(DecChunk& d, DecShared& S, FastSmem& F, const unsigned long long* an,
+                                  const uint16_t* ap, unsigned na, int n_plane)
+{
+  unsigned nlip = 0, nsig = 0;
+  for (unsigned p = threadIdx.x; p < na; p += kDecThreads)
+    f_expand_pixels(d, F, an[p], ap[p], n_plane, nlip, nsig);
+  f_block_scan(F, (unsigned long long)nlip | ((unsigned long long)nsig << 32));
+  if (threadIdx.x == 0) {
+    S.klip += F.scan_total & 0xffffffffull;
+    S.knew += F.scan_total >> 32;
+  }
+  __syncthreads();
+}
+
+// Expands the tokens of a round. kind: size class of the tokens in the entry queue
+// (2: qc, 1: qb, 0: qa).
+static __device__ void f_expand_round(DecChunk& d, DecShared& S, FastSmem& F, int kind, int n_plane)
+{
+  const int J = F.J;
+  if (kind == 0) {
+    f_expand_A(d, S, F, F.qa_node, F.qa_pos, F.nqa, n_plane);
     return;
   }
-  const int j = F.J - 1 - KIND;
-  const int nch = f_nch(F, j);
-  int c = 0;
-  for (int k = 0; k < nch; k++) {
-    const bool need = c != 0 || k != nch - 1;
-    const unsigned s = need ? f_bit(F, e.q++) : 1u;
-    unsigned jx, jy, jz;
-    f_child(F, j, ix, iy, iz, k, jx, jy, jz);
-    if (s) {
-      c = 1;
-      f_expand<(KIND > 0 ? KIND - 1 : 0)>(d, F, e, jx, jy, jz);
+  if (kind == 1) {
+    // the entry queue may hold up to kFQ size-B tokens: slices of kFSlice parents
+    const unsigned nb = F.nqb;
+    for (unsigned b0 = 0; b0 < nb; b0 += kFSlice) {
+      if (threadIdx.x == 0)
+        F.nqa = 0;
+      __syncthreads();
+      f_expand_level(d, F, J - 2, F.qb_node + b0, F.qb_pos + b0, min(unsigned(kFSlice), nb - b0),
+                     F.bodyA, F.qa_node, F.qa_pos, &F.nqa);
+      if (F.err)
+        return;
+      f_expand_A(d, S, F, F.qa_node, F.qa_pos, F.nqa, n_plane);
     }
-    else if (KIND == 1)
-      e.scr[16 + e.nA++] = f_pack(F, j + 1, jx, jy, jz);
-    else
-      e.scr[e.nB++] = f_pack(F, j + 1, jx, jy, jz);
+    return;
   }
-}
-
-// Appends what the expanders staged to the two deepest lists, in thread (= token) order.
-static __device__ void f_commit(DecChunk& d, DecShared& S, FastSmem& F, const FastExp& e)
-{
-  const unsigned long long packed =
-      (unsigned long long)e.nA | ((unsigned long long)e.nB << 21) | ((unsigned long long)e.nlip << 42);
-  const unsigned long long ex = f_block_scan(F, packed);
-  const unsigned long long tot = F.scan_total;
-  const unsigned exA = unsigned(ex) & 0x1fffffu, exB = unsigned(ex >> 21) & 0x1fffffu;
-  const unsigned totA = unsigned(tot) & 0x1fffffu, totB = unsigned(tot >> 21) & 0x1fffffu;
-  const int lisA = f_lis(F, F.J - 1), lisB = f_lis(F, F.J - 2);
-  const unsigned long long pa = F.off[lisA] + F.cnt[lisA], pb = F.off[lisB] + F.cnt[lisB];
-  const bool okA = pa + totA <= F.off[lisA + 1], okB = pb + totB <= F.off[lisB + 1];
-  if (okA)
-    for (unsigned i = 0; i < e.nA; i++)
-      d.lis[pa + exA + i] = e.scr[16 + i];
-  if (okB)
-    for (unsigned i = 0; i < e.nB; i++)
-      d.lis[pb + exB + i] = e.scr[i];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (!okA || !okB)
-      F.err |= 1u;
-    F.cnt[lisA] += totA;
-    F.cnt[lisB] += totB;
-    S.klip += tot >> 42;
+  const unsigned nc = F.nqc;
+  for (unsigned c0 = 0; c0 < nc; c0 += kFSlice) {
+    if (threadIdx.x == 0)
+      F.nqb = 0;
+    __syncthreads();
+    f_expand_level(d, F, J - 3, F.qc_node + c0, F.qc_pos + c0, min(unsigned(kFSlice), nc - c0),
+                   F.bodyB, F.qb_node, F.qb_pos, &F.nqb);
+    if (F.err)
+      return;
+    const unsigned nb = F.nqb;
+    for (unsigned b0 = 0; b0 < nb; b0 += kFSlice) {
+      if (threadIdx.x == 0)
+        F.nqa = 0;
+      __syncthreads();
+      f_expand_level(d, F, J - 2, F.qb_node + b0, F.qb_pos + b0, min(unsigned(kFSlice), nb - b0),
+                     F.bodyA, F.qa_node, F.qa_pos, &F.nqa);
+      if (F.err)
+        return;
+      f_expand_A(d, S, F, F.qa_node, F.qa_pos, F.nqa, n_plane);
+    }
   }
-  __syncthreads();
 }
 
 // ---- phase A: the lists of the three smallest set sizes, by token chains -------------------------
 
-static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, int kind)
+static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, int kind, int n_plane)
 {
   const int tid = threadIdx.x;
   const int j = F.J - 1 - kind;
@@ -390,9 +486,12 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
   if (m == 0)
     return;
   node_t* const list = d.lis + F.off[lis];
+  unsigned long long* const qn = kind == 0 ? F.qa_node : (kind == 1 ? F.qb_node : F.qc_node);
+  uint16_t* const qp = kind == 0 ? F.qa_pos : (kind == 1 ? F.qb_pos : F.qc_pos);
+  const unsigned qcap = kind == 2 ? unsigned(kFTok) : unsigned(kFQ);
   unsigned i0 = 0, wsurv = 0;
   while (i0 < m) {
-    f_build_window(d, F, S.pos, kind);
+    f_build_window(d, F, S.pos, kind, true);
     const long long f_tc = F_CLOCK();
     // token length of every window position; positions beyond the window absorb
     for (int q = tid; q < kFNext; q += kDecThreads) {
@@ -413,13 +512,12 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
     for (int r = 0; r < 14; r++) {
       const uint16_t* cn = F.nxt[cur];
       uint16_t* nn = F.nxt[cur ^ 1];
-      const unsigned mb = (F.mark[tid >> 2] >> ((tid & 3) * 8)) & 0xffu;   // my 8 positions
-      unsigned t = mb;
+      unsigned t = (F.mark[tid >> 2] >> ((tid & 3) * 8)) & 0xffu;   // my 8 positions
       while (t) {
         const int b = __ffs(t) - 1;
         t &= t - 1;
         const unsigned tgt = cn[tid * 8 + b];
-        if (tgt < kFW)
+        if (tgt < unsigned(kFW))
           atomicOr(&F.mark[tgt >> 5], 1u << (tgt & 31));
       }
       for (int q = tid; q < kFNext; q += kDecThreads)
@@ -435,9 +533,9 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
     unsigned long long ex = f_block_scan(F, (unsigned long long)__popc(mb));
     const unsigned total_marks = unsigned(F.scan_total);
     const unsigned T = min(total_marks, m - i0);
-    // collect my tokens: survivors keep their place in the list, significant ones are expanded
+    // my tokens: survivors keep their place in the list, significant ones are queued
     node_t surv[8], sigs[8];
-    unsigned sigq[8];
+    uint16_t sigq[8];
     int ns = 0, ng = 0;
     {
       unsigned t = mb, r = unsigned(ex);
@@ -449,7 +547,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
           const node_t nd = list[i0 + r];
           if (f_bit(F, q)) {
             sigs[ng] = nd;
-            sigq[ng++] = q + 1;
+            sigq[ng++] = uint16_t(q + 1);
           }
           else
             surv[ns++] = nd;
@@ -459,29 +557,37 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         r++;
       }
     }
-    ex = f_block_scan(F, (unsigned long long)ns);   // barrier inside: every root has been read
+    // barriers inside: every root of the window has been read before the survivors are written
+    ex = f_block_scan(F, (unsigned long long)ns | ((unsigned long long)ng << 32));
+    const unsigned tot_surv = unsigned(F.scan_total & 0xffffffffull);
+    const unsigned tot_sig = unsigned(F.scan_total >> 32);
+    for (int s = 0; s < ns; s++)
+      list[wsurv + unsigned(ex & 0xffffffffull) + s] = surv[s];
     const long long f_te = F_CLOCK();
     if (tid == 0)
       F.prof[2] += (unsigned long long)(f_te - f_tc);
-    const unsigned tot_surv = unsigned(F.scan_total);
-    for (int s = 0; s < ns; s++)
-      list[wsurv + unsigned(ex) + s] = surv[s];
-    FastExp e;
-    e.nA = e.nB = e.nlip = 0;
-    e.scr = d.scr + (size_t)tid * kFastScrPerThread;
-    for (int g = 0; g < ng; g++) {
-      int jj;
-      unsigned ix, iy, iz;
-      f_unpack(F, sigs[g], jj, ix, iy, iz);
-      e.q = sigq[g];
-      if (kind == 0)
-        f_expand<0>(d, F, e, ix, iy, iz);
-      else if (kind == 1)
-        f_expand<1>(d, F, e, ix, iy, iz);
-      else
-        f_expand<2>(d, F, e, ix, iy, iz);
+    // the significant roots enter the queue of their size class, qcap at a time
+    const unsigned myq = unsigned(ex >> 32);
+    for (unsigned g0 = 0; g0 < tot_sig; g0 += qcap) {
+      for (int g = 0; g < ng; g++) {
+        const unsigned slot = myq + g;
+        if (slot >= g0 && slot < g0 + qcap) {
+          qn[slot - g0] = sigs[g];
+          qp[slot - g0] = sigq[g];
+        }
+      }
+      if (tid == 0) {
+        const unsigned cntq = min(qcap, tot_sig - g0);
+        if (kind == 0) F.nqa = cntq;
+        else if (kind == 1) F.nqb = cntq;
+        else F.nqc = cntq;
+      }
+      __syncthreads();
+      f_expand_round(d, S, F, kind, n_plane);
+      __syncthreads();
+      if (F.err)
+        return;
     }
-    f_commit(d, S, F, e);
     if (tid == 0) {
       F.prof[3] += (unsigned long long)(F_CLOCK() - f_te);
       S.pos += T == total_marks ? exitpos : F.cutpos;
@@ -489,8 +595,6 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
     i0 += T;
     wsurv += tot_surv;
     __syncthreads();
-    if (F.err)
-      return;
   }
   if (tid == 0)
     F.cnt[lis] = wsurv;
@@ -499,75 +603,92 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
 
 // ---- phase B: larger sets, one thread walks the top of the tree ----------------------------------
 
-// Runs until the lists are exhausted (wk_done) or the window / token queue is used up.
+// Runs until the lists are exhausted (wk_done), the window or the token queue is used up, or the
+// staged roots of the current list have all been visited.
 static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
 {
-  const unsigned long long base = S.pos;
-  unsigned q = 0;            // window position
+  unsigned q = F.wk_q;       // window position
   unsigned ntok = 0;
   int depth = F.wk_depth;
   int lj = F.wk_j;
-  unsigned i = F.wk_i, w = F.wk_w, cnt = F.wk_cnt;
+  unsigned i = F.wk_i, w = F.wk_w;
+  const unsigned cnt = F.wk_cnt;
   const int jC = F.J - 3;
+  // the frame being expanded lives in registers; outer frames are parked in shared memory
+  int j = 0, k = 0, sg = 0, nch = 0;
+  unsigned ix = 0, iy = 0, iz = 0;
+  if (depth >= 0) {
+    f_unpack(F, F.wk_node[depth], j, ix, iy, iz);
+    k = F.wk_k[depth];
+    sg = F.wk_sig[depth];
+    nch = f_nch(F, j);
+  }
+  node_t* const list = d.lis + F.off[f_lis(F, lj)];
   for (;;) {
     if (depth < 0) {
-      if (i == cnt) {   // list finished: survivors are compacted, new sets of this plane follow them
-        if (lj >= 1)
-          F.cnt[f_lis(F, lj)] = w;
-        lj--;
-        if (lj < 1) {
-          F.wk_done = 1;
-          break;
-        }
-        i = 0;
-        w = 0;
-        cnt = F.cnt[f_lis(F, lj)];
-        continue;
-      }
-      if (q + 1 >= unsigned(kFW))
+      if (i == cnt)
+        break;   // list finished (the caller moves on to the next one)
+      if (q + 1 >= unsigned(kFW) || i >= F.rs_first + F.rs_cnt)
         break;
-      node_t* const list = d.lis + F.off[f_lis(F, lj)];
-      const node_t nd = list[i++];
-      if (f_bit(F, q++) == 0) {
-        list[w++] = nd;
+      // roots coded as 0 stay in the list: skip a whole run of them at once
+      const unsigned room = min(min(32u, F.rs_first + F.rs_cnt - i), unsigned(kFW) - 1u - q);
+      unsigned u = f_peek(F, q);
+      if (room < 32)
+        u &= (1u << room) - 1u;
+      const unsigned run = u ? unsigned(__ffs(u) - 1) : room;
+      if (w != i)
+        for (unsigned x = 0; x < run; x++)
+          list[w + x] = F.rs_node[i - F.rs_first + x];
+      i += run;
+      w += run;
+      q += run;
+      if (run == room)
         continue;
-      }
+      const node_t nd = F.rs_node[i - F.rs_first];
+      i++;
+      q++;
       depth = 0;
-      F.wk_node[0] = nd;
-      F.wk_k[0] = 0;
-      F.wk_sig[0] = 0;
+      f_unpack(F, nd, j, ix, iy, iz);
+      k = 0;
+      sg = 0;
+      nch = f_nch(F, j);
       continue;
     }
-    int j;
-    unsigned ix, iy, iz;
-    f_unpack(F, F.wk_node[depth], j, ix, iy, iz);
-    const int nch = f_nch(F, j);
-    const int k = F.wk_k[depth];
-    if (k == nch) {
+    if (k == nch) {   // pop
       depth--;
+      if (depth >= 0) {
+        f_unpack(F, F.wk_node[depth], j, ix, iy, iz);
+        k = F.wk_k[depth];
+        sg = F.wk_sig[depth];
+        nch = f_nch(F, j);
+      }
       continue;
     }
     if (q + 1 >= unsigned(kFW) || ntok >= unsigned(kFTok))
       break;
-    F.wk_k[depth] = (unsigned char)(k + 1);
-    const bool need = F.wk_sig[depth] != 0 || k != nch - 1;
+    const bool need = sg != 0 || k != nch - 1;
     const unsigned s = need ? f_bit(F, q++) : 1u;
     unsigned jx, jy, jz;
     f_child(F, j, ix, iy, iz, k, jx, jy, jz);
-    const node_t child = f_pack(F, j + 1, jx, jy, jz);
+    k++;
     if (s) {
-      F.wk_sig[depth] = 1;
-      if (j + 1 == jC) {   // a bodyC-sized set: queue it and skip its bits
-        F.tok_node[ntok] = child;
-        F.tok_pos[ntok] = q;
+      sg = 1;
+      if (j + 1 == jC) {   // a size-C set: queue it and skip its bits
+        F.qc_node[ntok] = f_pack(F, j + 1, jx, jy, jz);
+        F.qc_pos[ntok] = uint16_t(q);
         ntok++;
         q += F.bodyC[q];
       }
-      else {
+      else {   // push
+        F.wk_node[depth] = f_pack(F, j, ix, iy, iz);
+        F.wk_k[depth] = (unsigned char)k;
+        F.wk_sig[depth] = 1;
         depth++;
-        F.wk_node[depth] = child;
-        F.wk_k[depth] = 0;
-        F.wk_sig[depth] = 0;
+        j++;
+        ix = jx; iy = jy; iz = jz;
+        k = 0;
+        sg = 0;
+        nch = f_nch(F, j);
       }
     }
     else {
@@ -577,63 +698,85 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
         F.err |= 1u;
         break;
       }
-      d.lis[F.off[cl] + slot] = child;
+      d.lis[F.off[cl] + slot] = f_pack(F, j + 1, jx, jy, jz);
       F.cnt[cl] = slot + 1;
     }
   }
+  if (depth >= 0) {
+    F.wk_node[depth] = f_pack(F, j, ix, iy, iz);
+    F.wk_k[depth] = (unsigned char)k;
+    F.wk_sig[depth] = (unsigned char)sg;
+  }
   F.wk_depth = depth;
-  F.wk_j = lj;
   F.wk_i = i;
   F.wk_w = w;
-  F.wk_cnt = cnt;
-  F.ntok = ntok;
-  S.pos = base + q;
+  F.wk_q = q;
+  F.nqc = ntok;
+  S.pos = F.win_base + q;
 }
 
 // The LIS part of one bit-plane.
-static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F)
+static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int n_plane)
 {
   const int tid = threadIdx.x;
   for (int kind = 0; kind < 3; kind++) {
-    f_list_by_chain(d, S, F, kind);
+    f_list_by_chain(d, S, F, kind, n_plane);
     if (F.err)
       return;
   }
-  if (F.J - 4 < 1)
-    return;
-  if (tid == 0) {
-    F.wk_j = F.J - 4;
-    F.wk_i = 0;
-    F.wk_w = 0;
-    F.wk_cnt = F.cnt[f_lis(F, F.J - 4)];
-    F.wk_depth = -1;
-    F.wk_done = 0;
-  }
-  __syncthreads();
-  for (;;) {
-    f_build_window(d, F, S.pos, 2);
-    const long long f_tw = F_CLOCK();
-    if (tid == 0)
-      f_walk(d, S, F);
-    __syncthreads();
-    const long long f_te = F_CLOCK();
-    if (tid == 0)
-      F.prof[4] += (unsigned long long)(f_te - f_tw);
-    FastExp e;
-    e.nA = e.nB = e.nlip = 0;
-    e.scr = d.scr + (size_t)tid * kFastScrPerThread;
-    if (unsigned(tid) < F.ntok) {
-      int jj;
-      unsigned ix, iy, iz;
-      f_unpack(F, F.tok_node[tid], jj, ix, iy, iz);
-      e.q = F.tok_pos[tid];
-      f_expand<2>(d, F, e, ix, iy, iz);
+  bool have_window = false;
+  for (int lj = F.J - 4; lj >= 1; lj--) {
+    const int lis = f_lis(F, lj);
+    const unsigned cnt = F.cnt[lis];
+    if (cnt == 0)
+      continue;
+    if (tid == 0) {
+      F.wk_j = lj;
+      F.wk_i = 0;
+      F.wk_w = 0;
+      F.wk_cnt = cnt;
+      F.wk_depth = -1;
     }
-    f_commit(d, S, F, e);
+    __syncthreads();
+    for (;;) {
+      if (!have_window || F.wk_q + 1 >= unsigned(kFW)) {
+        f_build_window(d, F, S.pos, 2, false);
+        if (tid == 0) {
+          F.win_base = S.pos;
+          F.wk_q = 0;
+        }
+        have_window = true;
+      }
+      // stage the next roots of the list (the walker never reads the list itself)
+      const unsigned first = F.wk_i;
+      const unsigned nst = min(unsigned(kFRoots), cnt - first);
+      __syncthreads();
+      for (unsigned t = tid; t < nst; t += kDecThreads)
+        F.rs_node[t] = d.lis[F.off[lis] + first + t];
+      if (tid == 0) {
+        F.rs_first = first;
+        F.rs_cnt = nst;
+      }
+      __syncthreads();
+      const long long f_tw = F_CLOCK();
+      if (tid == 0)
+        f_walk(d, S, F);
+      __syncthreads();
+      const long long f_te = F_CLOCK();
+      if (tid == 0)
+        F.prof[4] += (unsigned long long)(f_te - f_tw);
+      f_expand_round(d, S, F, 2, n_plane);
+      __syncthreads();
+      if (tid == 0)
+        F.prof[3] += (unsigned long long)(F_CLOCK() - f_te);
+      if (F.err)
+        return;
+      if (F.wk_depth < 0 && F.wk_i == cnt)
+        break;
+    }
     if (tid == 0)
-      F.prof[3] += (unsigned long long)(F_CLOCK() - f_te);
-    if (F.err || F.wk_done)
-      break;
+      F.cnt[lis] = F.wk_w;   // survivors; the sets created in this plane went to deeper lists
+    __syncthreads();
   }
 }
 
@@ -653,11 +796,13 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     S.pos = 0;
     S.klip = 0;
     S.klsp = 0;
+    S.knew = 0;
     S.endpos = 0;
     F.Dx = d.Dx; F.Dy = d.Dy; F.Dz = d.Dz;
     F.J = max(d.Dx, max(d.Dy, d.Dz));
     F.nx = d.nx; F.ny = d.ny;
     F.err = 0;
+    F.nqa = F.nqb = F.nqc = 0;
     for (int k = 0; k < 8; k++)
       F.prof[k] = 0;
     for (int l = 0; l <= d.nlis; l++)
@@ -677,36 +822,26 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
   }
   __syncthreads();
   int n = d.planes - 1;
-  bool pending_new = false;
   for (int bp = 0; bp < d.planes; bp++, n--) {
     {
       F_TIC();
-      dec_lip_pass(d, S);
+      dec_lip_pass(d, S, n);
       __syncthreads();
       F_TOC(F, 0);
     }
-    dec_lis_fast(d, S, F);
+    dec_lis_fast(d, S, F, n);
     __syncthreads();
-    if (F.err) {
-      if (tid == 0)
-        d.err = F.err;
-      return;
-    }
-    if (S.pos >= d.avail) {
-      pending_new = true;
-      break;
-    }
-    F_TIC();
-    dec_refine_pass(d, S, n, true);
-    F_TOC(F, 5);
-    if (S.pos >= d.avail)
+    if (tid == 0)
+      F.go = (!F.err && dec_plane_end(d, S, n)) ? 1 : 0;
+    __syncthreads();
+    if (!F.go)
       break;
   }
-  if (pending_new)
-    dec_refine_pass(d, S, n, false);
-  if (tid == 0)
+  if (tid == 0) {
+    d.err = F.err;
     for (int k = 0; k < 8; k++)
       d.prof[k] = F.prof[k];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -738,7 +873,7 @@ static __global__ void k_stage_bits(const DecChunk* chunks, const unsigned char*
   }
 }
 
-// Decodes every job; on return w.h[c].lsp is the final significance mask of job c.
+// Decodes the sorting passes of every job; w.h / w.dchunks hold the decoder state afterwards.
 template <class T>
 void run_decoder(DecWork& w, const std::vector<DecJob>& jobs, const typename T::Data& tree,
                  cudaStream_t st)
@@ -746,31 +881,39 @@ void run_decoder(DecWork& w, const std::vector<DecJob>& jobs, const typename T::
   const int nj = int(jobs.size());
   if (nj == 0)
     return;
-  size_t mask_words = 0, lis_entries = 0, cnt_entries = 0, stage_words = 0;
+  size_t mask_words = 0, lis_entries = 0, cnt_entries = 0, stage_words = 0, pl_bytes = 0;
   bool any_fast = false, any_slow = false;
   std::vector<size_t> mw(nj), sw(nj);
+  w.max_n = 0;
+  w.max_planes = 0;
   for (int c = 0; c < nj; c++) {
     const DecJob& j = jobs[c];
     mw[c] = j.skip ? 0 : (size_t(j.n + 31) / 32 + 4);
     sw[c] = j.skip ? 0 : (size_t(j.payload_bytes) / 4 + 4);
-    mask_words += 5 * mw[c];
+    mask_words += 3 * mw[c];
+    pl_bytes += j.skip ? 0 : ((size_t(j.n) + 63) & ~size_t(63));
     lis_entries += j.skip ? 0 : j.lis_total;
     cnt_entries += j.skip ? 0 : size_t(j.nlis + 1);
     stage_words += sw[c];
-    if (!j.skip)
+    if (!j.skip) {
       (j.pow2 ? any_fast : any_slow) = true;
+      w.max_n = std::max<size_t>(w.max_n, j.n);
+      w.max_planes = std::max(w.max_planes, j.planes);
+      if (j.planes > kMaxPlanes)
+        throw std::runtime_error("SPECK stream with more than 64 bit-planes");
+    }
   }
-  if (any_fast)
-    w.scr.reserve(size_t(nj) * kDecThreads * kFastScrPerThread * 8);
   w.masks.reserve(mask_words * 4 + 16);
+  w.pl.reserve(pl_bytes + 16);
   w.lis.reserve(lis_entries * 8 + 16);
   w.lis_cnt.reserve(cnt_entries * 4 + 16);
   w.stage.reserve(stage_words * 4 + 16);
   rt::dset(w.masks.p, 0, mask_words * 4, st);
+  rt::dset(w.pl.p, 0xFF, pl_bytes, st);
   w.h.assign(nj, DecChunk());
   std::vector<const unsigned char*> srcs(nj);
   std::vector<unsigned long long> lens(nj), words(nj);
-  size_t om = 0, ol = 0, oc = 0, os = 0, max_words = 1;
+  size_t om = 0, ol = 0, oc = 0, os = 0, op = 0, max_words = 1;
   for (int c = 0; c < nj; c++) {
     const DecJob& j = jobs[c];
     DecChunk& d = w.h[c];
@@ -785,16 +928,13 @@ void run_decoder(DecWork& w, const std::vector<DecJob>& jobs, const typename T::
     d.shape = j.shape;
     d.planes = j.planes;
     d.avail = std::min<unsigned long long>(j.total_bits, j.payload_bytes * 8ull);
-    d.wide = j.wide;
-    d.mag = j.mag;
-    d.signs = j.signs;
     uint32_t* m = w.masks.as<uint32_t>() + om;
     d.lip = m;
-    d.lsp = m + mw[c];
-    d.newm = m + 2 * mw[c];
-    d.sigarr = m + 3 * mw[c];
-    d.signarr = m + 4 * mw[c];
-    om += 5 * mw[c];
+    d.sigarr = m + mw[c];
+    d.signarr = m + 2 * mw[c];
+    om += 3 * mw[c];
+    d.pl = w.pl.as<uint8_t>() + op;
+    op += (size_t(j.n) + 63) & ~size_t(63);
     d.lis = w.lis.as<node_t>() + ol;
     ol += j.lis_total;
     d.lis_off = j.d_lis_off;
@@ -810,8 +950,6 @@ void run_decoder(DecWork& w, const std::vector<DecJob>& jobs, const typename T::
     d.nroots = j.nroots;
     for (int r = 0; r < j.nroots; r++)
       d.roots[r] = j.roots[r];
-    d.scr = j.pow2 ? w.scr.as<unsigned long long>() + size_t(c) * kDecThreads * kFastScrPerThread
-                   : nullptr;
     max_words = std::max(max_words, sw[c]);
   }
   w.dchunks.reserve(sizeof(DecChunk) * nj);
@@ -854,10 +992,9 @@ void run_decoder(DecWork& w, const std::vector<DecJob>& jobs, const typename T::
       if (w.h[c].pow2 && !w.h[c].skip)
         std::fprintf(stderr,
                      "decprof job %d n=%llu: lip %.2f  windows %.2f (%llu)  chains %.2f  expand %.2f  walker "
-                     "%.2f  refine %.2f  Mcycles\n",
+                     "%.2f  Mcycles\n",
                      c, w.h[c].n, w.h[c].prof[0] * 1e-6, w.h[c].prof[1] * 1e-6, w.h[c].prof[6],
-                     w.h[c].prof[2] * 1e-6, w.h[c].prof[3] * 1e-6, w.h[c].prof[4] * 1e-6,
-                     w.h[c].prof[5] * 1e-6);
+                     w.h[c].prof[2] * 1e-6, w.h[c].prof[3] * 1e-6, w.h[c].prof[4] * 1e-6);
   for (int c = 0; c < nj; c++)
     if (w.h[c].err)
       throw std::runtime_error("SPECK decoder: list capacity exceeded (corrupt stream?)");

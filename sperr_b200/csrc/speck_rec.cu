@@ -1,0 +1,202 @@
+// Magnitude reconstruction after the SPECK sorting passes have been decoded (speck_dec*.cuh).
+//
+// Reference behaviour (bit-exact): SPECK_INT<T>::m_refinement_pass_decode and the initial value of a
+// newly significant coefficient (/root/reference/src/SPECK_INT.cpp:359-469), followed by
+//   mode 0: SPECK_FLT::m_midtread_inv_quantize (/root/reference/src/SPECK_FLT.cpp:373-399)
+//   mode 1: Outlier_Coder::m_inverse_quantize (src/Outlier_Coder.cpp:206-234) applied as in
+//           src/SPECK_FLT.cpp:576-585.
+// How: the reference refines plane by plane, walking the LSP mask each time. Here every coefficient
+// gathers its own bits: in plane n it owns bit number rank_n(i) of that plane's refinement section,
+// where rank_n(i) counts the coefficients before i (raster order) that were significant before
+// plane n. Ranks are per-block counts (k_rec_count), scanned over blocks (k_rec_scan), plus a
+// ballot prefix inside the block (k_rec_apply) -- one grid-wide pass over all chunks of the batch
+// instead of one pass per plane inside the per-chunk decoder.
+#include "speck_dec.h"
+
+namespace sperr_b200 {
+
+constexpr int kRecBlock = 1024;
+
+__device__ __forceinline__ int rec_plane(unsigned v) { return v == 0xFFu ? -1 : int(v & 63u); }
+
+// counts[(c * maxp + n) * nblk + blk] = coefficients of block blk significant before plane n
+__global__ void k_rec_count(const DecChunk* jobs, unsigned* counts, int maxp, unsigned nblk)
+{
+  __shared__ unsigned s_cnt[kMaxPlanes];
+  __shared__ int s_max;
+  const unsigned c = blockIdx.y, blk = blockIdx.x;
+  const DecChunk& d = jobs[c];
+  if (d.skip || (unsigned long long)blk * kRecBlock >= d.n)
+    return;
+  const unsigned long long i = (unsigned long long)blk * kRecBlock + threadIdx.x;
+  const int p = i < d.n ? rec_plane(d.pl[i]) : -1;
+  if (threadIdx.x < kMaxPlanes)
+    s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0)
+    s_max = -1;
+  __syncthreads();
+  const int wmax = __reduce_max_sync(0xffffffffu, p);
+  if ((threadIdx.x & 31) == 0 && wmax >= 0)
+    atomicMax(&s_max, wmax);
+  __syncthreads();
+  const int bmax = s_max;
+  for (int n = 0; n < bmax; n++) {
+    const unsigned b = __ballot_sync(0xffffffffu, p > n);
+    if ((threadIdx.x & 31) == 0 && b)
+      atomicAdd(&s_cnt[n], unsigned(__popc(b)));
+  }
+  __syncthreads();
+  if (int(threadIdx.x) < bmax)
+    counts[((size_t)c * maxp + threadIdx.x) * nblk + blk] = s_cnt[threadIdx.x];
+}
+
+// one block per (chunk, plane) row: exclusive scan over the blocks, in place
+__global__ void k_rec_scan(const DecChunk* jobs, unsigned* counts, int maxp, unsigned nblk)
+{
+  __shared__ unsigned wsum[32];
+  __shared__ unsigned carry_s;
+  const unsigned c = blockIdx.y, n = blockIdx.x;
+  const DecChunk& d = jobs[c];
+  if (d.skip || int(n) >= d.planes || d.ref_cnt[n] == 0)
+    return;
+  unsigned* row = counts + ((size_t)c * maxp + n) * nblk;
+  const unsigned used = unsigned((d.n + kRecBlock - 1) / kRecBlock);
+  if (threadIdx.x == 0)
+    carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned base = 0; base < used; base += blockDim.x) {
+    const unsigned i = base + threadIdx.x;
+    const unsigned v = i < used ? row[i] : 0;
+    unsigned inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o)
+        inc += t;
+    }
+    if (lane == 31)
+      wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned w = wsum[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o)
+          w += t;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const unsigned carry = carry_s;
+    const unsigned excl = carry + inc - v + (warp ? wsum[warp - 1] : 0);
+    if (i < used)
+      row[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 0)
+      carry_s = carry + wsum[31];
+    __syncthreads();
+  }
+}
+
+__global__ void k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const unsigned* counts,
+                            int maxp, unsigned nblk, int mode, const double* tols)
+{
+  __shared__ unsigned s_cnt[kMaxPlanes][32];   // per plane: significant-before-n count of every warp
+  __shared__ int s_max;
+  const unsigned c = blockIdx.y, blk = blockIdx.x;
+  const DecChunk& d = jobs[c];
+  const ChunkDev& ch = chunks[c];
+  const unsigned long long i = (unsigned long long)blk * kRecBlock + threadIdx.x;
+  if (d.skip) {
+    // no SPECK stream: every coefficient is zero (constant chunks never read their buffer)
+    if (mode == 0 && !ch.is_const && i < ch.n)
+      ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, 0.0), 1.0);
+    return;
+  }
+  if ((unsigned long long)blk * kRecBlock >= d.n)
+    return;
+  const unsigned v = i < d.n ? d.pl[i] : 0xFFu;
+  const int p = rec_plane(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0)
+    s_max = -1;
+  __syncthreads();
+  const int wmax = __reduce_max_sync(0xffffffffu, p);
+  if (lane == 0 && wmax >= 0)
+    atomicMax(&s_max, wmax);
+  __syncthreads();
+  const int bmax = s_max;
+  for (int n = 0; n < bmax; n++) {
+    const unsigned b = __ballot_sync(0xffffffffu, p > n);
+    if (lane == 0)
+      s_cnt[n][warp] = unsigned(__popc(b));
+  }
+  __syncthreads();
+  unsigned long long mag = 0;
+  if (p >= 0) {
+    const unsigned long long thr = 1ull << p;
+    mag = thr + thr - (thr >> 1) - 1ull;   // value given to a newly significant coefficient
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  for (int n = min(wmax, bmax) - 1; n >= 0; n--) {   // warp-uniform: planes below this warp's largest
+    const unsigned long long nref = d.ref_cnt[n];
+    if (nref == 0)
+      continue;   // plane never refined (not reached, or the stream ended before its section)
+    const bool mine = p > n;
+    const unsigned b = __ballot_sync(0xffffffffu, mine);
+    const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? s_cnt[n][lane] : 0u);
+    if (mine) {
+      const unsigned long long rank =
+          (unsigned long long)counts[((size_t)c * maxp + n) * nblk + blk] + before + __popc(b & lt);
+      if (rank < nref) {
+        const unsigned long long bp = d.ref_base[n] + rank;
+        const unsigned bit = (d.bits[bp >> 5] >> (bp & 31)) & 1u;
+        if (n >= 1) {
+          const unsigned long long half = 1ull << (n - 1);
+          mag = bit ? mag + half : mag - half;
+        }
+        else
+          mag += bit;
+      }
+    }
+  }
+  if (i >= d.n)
+    return;
+  const bool neg = p >= 0 && (v & 0x80u);
+  if (mode == 0) {
+    ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, __ull2double_rn(mag)), neg ? -1.0 : 1.0);
+  }
+  else if (p >= 0 && mag != 0) {
+    double e = mag == 1 ? 1.1 : __dsub_rn(__ull2double_rn(mag), 0.25);
+    e = __dmul_rn(e, __dmul_rn(tols[c], neg ? -1.0 : 1.0));
+    ch.coef[i] = __dadd_rn(ch.coef[i], e);
+  }
+}
+
+void speck_reconstruct(DecWork& w, const ChunkDev* d_chunks, int mode, const double* d_tols,
+                       cudaStream_t st)
+{
+  const int nj = int(w.h.size());
+  if (nj == 0)
+    return;
+  const DecChunk* dj = w.dchunks.as<DecChunk>();
+  // mode 0 must also zero-fill chunks without a stream, whose extent the jobs do not know
+  size_t max_n = w.max_n;
+  if (mode == 0)
+    max_n = std::max(max_n, w.fill_n);
+  if (max_n == 0)
+    return;
+  const unsigned nblk = unsigned((max_n + kRecBlock - 1) / kRecBlock);
+  const int maxp = std::max(1, w.max_planes);
+  const size_t ncounts = (size_t)nj * maxp * nblk;
+  w.counts.reserve(ncounts * 4);
+  rt::dset(w.counts.p, 0, ncounts * 4, st);
+  unsigned* cnt = w.counts.as<unsigned>();
+  if (w.max_n) {
+    LAUNCH(k_rec_count, dim3(nblk, nj), dim3(kRecBlock), 0, st, dj, cnt, maxp, nblk);
+    LAUNCH(k_rec_scan, dim3(maxp, nj), dim3(1024), 0, st, dj, cnt, maxp, nblk);
+  }
+  LAUNCH(k_rec_apply, dim3(nblk, nj), dim3(kRecBlock), 0, st, dj, d_chunks, cnt, maxp, nblk, mode, d_tols);
+}
+
+}  // namespace sperr_b200
