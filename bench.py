@@ -257,20 +257,43 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def comp_dev():
-        rc, stream = L.compress_3d_dev(vol.data_ptr(), True, dims, (CHUNK,) * 3, 3, TOL)
-        assert rc == 0, rc
-        return stream
+    if world == 1:
+        def comp_dev():
+            rc, stream = L.compress_3d_dev(vol.data_ptr(), True, dims, (CHUNK,) * 3, 3, TOL)
+            assert rc == 0, rc
+            return stream
 
-    def decomp_dev(stream, d_stream):
-        rc, d = L.decompress_3d_dev(stream, d_stream.data_ptr(), out_dev.data_ptr(), True)
-        assert rc == 0 and d == dims, (rc, d)
+        def decomp_dev(stream, d_stream):
+            rc, d = L.decompress_3d_dev(stream, d_stream.data_ptr(), out_dev.data_ptr(), True)
+            assert rc == 0 and d == dims, (rc, d)
 
-    def step_dev():
-        stream = comp_dev()
-        d_stream = torch.from_numpy(stream).to(dev)
-        decomp_dev(stream, d_stream)
-        return stream
+        def step_dev():
+            stream = comp_dev()
+            d_stream = torch.from_numpy(stream).to(dev)
+            decomp_dev(stream, d_stream)
+            return stream
+    else:
+        # N ranks: the volume is n x n x (n * N); rank r owns the chunks of its own z-slab. One
+        # exchange each way over NCCL: chunk lengths + chunk streams to rank 0 (which assembles the
+        # single reference-layout container), and the streams back out for decoding.
+        from sperr_b200 import sharded
+        gdims = (n, n, n * world)
+        box = vol.view(n, n, n)
+        state = {}
+
+        def comp_dev():
+            s = sharded.compress_3d_sharded(L.lib, box, gdims, (CHUNK,) * 3, 3, TOL)
+            state["stream"] = s
+            return s
+
+        def decomp_dev(stream, d_stream):
+            b, sh = sharded.decompress_3d_sharded(L.lib, stream, dev, True)
+            state["out"] = b
+
+        def step_dev():
+            stream = comp_dev()
+            decomp_dev(stream, None)
+            return stream
 
     prof_on = L.fn("sperr_b200_prof_enable", None, [C.c_int])
     prof_dump = L.fn("sperr_b200_prof_dump", C.c_size_t, [C.c_char_p, C.c_size_t])
@@ -308,10 +331,11 @@ def run_ours(args):
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
-    d_stream = torch.from_numpy(stream).to(dev)
+    d_stream = torch.from_numpy(stream).to(dev) if world == 1 else None
     ms_c = timed(comp_dev, args.steps)
     ms_d = timed(lambda: decomp_dev(stream, d_stream), args.steps)
-    maxerr = float((out_dev.double() - vol.double()).abs().max().item())
+    got = out_dev if world == 1 else state["out"].reshape(-1)
+    maxerr = float((got.double() - vol.double()).abs().max().item())
     # decoded values are rounded to fp32 after the bound was enforced in fp64: allow one fp32 ulp
     assert maxerr <= TOL + 1.2e-7, "PWE bound violated: %g" % maxerr
 
@@ -324,7 +348,7 @@ def run_ours(args):
     stages = json.loads(buf.value.decode())
 
     # e2e through the reference-facing C API with host buffers (pinned input, malloc'd outputs)
-    hvol = vol.cpu().pin_memory().numpy() if args.e2e else None
+    hvol = vol.cpu().pin_memory().numpy() if (args.e2e and world == 1) else None
     e2e = None
     if hvol is not None:
         def e2e_step():
@@ -346,6 +370,32 @@ def run_ours(args):
         e2e = {"value": world * nbytes / dt / GB, "unit": "GB/s",
                "h2d_bytes_per_step": nbytes + int(s2.size), "d2h_bytes_per_step": int(s2.size) + nbytes}
 
+    if args.e2e and world > 1:
+        # same metric through the sharded public API with HOST boxes: every rank uploads its box
+        # from pinned memory, the container is assembled on rank 0, scattered again, decoded, and
+        # every rank reads its decoded box back
+        hbox = vol.cpu().pin_memory()
+        hout = torch.empty_like(hbox).pin_memory()
+
+        def e2e_step():
+            dbox = hbox.to(dev).view(n, n, n)
+            s2 = sharded.compress_3d_sharded(L.lib, dbox, gdims, (CHUNK,) * 3, 3, TOL)
+            b, sh = sharded.decompress_3d_sharded(L.lib, s2, dev, True)
+            hout.copy_(b.reshape(-1))
+            return s2
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            s2 = e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        e2e = {"value": world * nbytes / dt / GB, "unit": "GB/s",
+               "h2d_bytes_per_step": world * nbytes + int(stream.size),
+               "d2h_bytes_per_step": int(stream.size) + world * nbytes}
+
     if rank == 0:
         nvals = n ** 3
         out = {
@@ -353,7 +403,7 @@ def run_ours(args):
             "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(world),
-            "stream_bytes": int(stream.size), "bpp": stream.size * 8.0 / nvals,
+            "stream_bytes": int(stream.size), "bpp": stream.size * 8.0 / (nvals * world),
             "clocks": clk.summary(), "stages_ms": {k: round(v["ms"], 3) for k, v in stages.items()},
             "compress_gbs": world * nbytes / (ms_c * 1e-3) / GB,
             "decompress_gbs": world * nbytes / (ms_d * 1e-3) / GB, "max_abs_err": maxerr,

@@ -59,6 +59,47 @@ int sperr_b200_comp_3d_dev(const void* d_src, int is_float, size_t dimx, size_t 
 int sperr_b200_decomp_3d_dev(const void* h_src, const void* d_src, size_t src_len, int output_float,
                              size_t* dimx, size_t* dimy, size_t* dimz, void* d_dst);
 
+/* ---- 2b. chunk-range sharding (one process per GPU) ----
+ * SPERR's chunks are coded independently (SPERR3D_OMP_C.cpp:94-130, SPERR3D_OMP_D.cpp:94-130): rank r
+ * codes chunks [chunk_begin, chunk_end) of chunk_volume's order (sperr_helper.cpp:542-592) out of
+ * the bounding box of those chunks, which it holds in device memory (x fastest, row length
+ * box_extent[0], box_extent[1] rows per plane). vol / chunk are the whole volume's extents and the
+ * preferred chunk extents, exactly as given to sperr_comp_3d. */
+
+/* Number of chunks of the volume. */
+size_t sperr_b200_num_chunks(const size_t vol[3], const size_t chunk[3]);
+
+/* Bounding box of chunks [begin, end). Returns 0, or -1 for a bad range. */
+int sperr_b200_chunk_box(const size_t vol[3], const size_t chunk[3], size_t begin, size_t end,
+                         size_t origin[3], size_t extent[3]);
+
+/* Compresses the chunks of the range. *dst (malloc'd, must be NULL on entry) receives their streams
+ * back to back, lens[i] the length of chunk chunk_begin + i. Return codes as sperr_comp_3d. */
+int sperr_b200_comp_3d_range_dev(const void* d_box, int is_float, const size_t vol[3],
+                                 const size_t chunk[3], const size_t box_origin[3],
+                                 const size_t box_extent[3], size_t chunk_begin, size_t chunk_end,
+                                 int mode, double quality, void** dst, size_t* dst_len, uint32_t* lens);
+
+/* Writes the reference container header (SPERR3D_OMP_C::m_generate_header, SPERR3D_OMP_C.cpp:
+ * 163-234) for `nchunks` chunk lengths into out[0, cap) and returns its length (call with out = NULL
+ * to size the buffer). The container is this header followed by all chunk streams in order. */
+size_t sperr_b200_container_header(const size_t vol[3], const size_t chunk[3], int is_float,
+                                   const uint32_t* lens, size_t nchunks, void* out, size_t cap);
+
+/* Parses a container header (SPERR3D_Stream_Tools::get_stream_header, SPERR3D_Stream_Tools.cpp:
+ * 46-105). lens may be NULL; otherwise it receives *nchunks lengths (cap entries available). */
+int sperr_b200_parse_container(const void* src, size_t len, size_t vol[3], size_t chunk[3],
+                               int* is_float, size_t* header_len, uint32_t* lens, size_t cap,
+                               size_t* nchunks);
+
+/* Decodes the chunks of the range from their streams (HOST memory, back to back, lens[i] each) into
+ * the caller's DEVICE box (float when output_float != 0, else double). */
+int sperr_b200_decomp_3d_range_dev(const void* h_streams, size_t streams_len, const uint32_t* lens,
+                                   const size_t vol[3], const size_t chunk[3],
+                                   const size_t box_origin[3], const size_t box_extent[3],
+                                   size_t chunk_begin, size_t chunk_end, int output_float,
+                                   void* d_box_out);
+
 /* Stage profiler: when enabled every stage of the pipelines is bracketed by CUDA events on the
  * launching stream. prof_dump writes a JSON object {"stage": {"ms": total, "n": ranges}, ...} into
  * buf (NUL-terminated, truncated to cap) and returns the full length. Enabling clears the totals. */

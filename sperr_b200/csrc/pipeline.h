@@ -49,7 +49,7 @@ class Decompressor {
   void run_batch(const uint8_t* h_stream, const uint8_t* d_stream, const std::vector<Chunk>& chunks,
                  const ChunkStream* cs, const SrcVol& dst, cudaStream_t st);
   BatchBuffers b_;
-  DecWork w3_, w1_;
+  DecWork w_;
   rt::DBuf ids_, lis_off1_, tols_;
 };
 

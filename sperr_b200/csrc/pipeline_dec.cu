@@ -127,7 +127,9 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
   b_.push(st);
 
   // ---- SPECK3D decode: sorting passes per chunk, then magnitudes + de-quantisation grid-wide ----
-  std::vector<DecJob> jobs(nc);
+  // jobs [0, nc): the chunks' SPECK3D streams; jobs [nc, 2 nc): their SPECK1D outlier streams. All
+  // of them are decoded side by side (one CTA each), so the outlier streams cost no extra time.
+  std::vector<DecJob> jobs(2 * nc);
   for (int c = 0; c < nc; c++) {
     DecJob& j = jobs[c];
     const ShapeTables& sh = b_.shapes[b_.h[c].shape];
@@ -167,46 +169,10 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
       jobs[c].d_lis_off = reinterpret_cast<const unsigned long long*>(
           reinterpret_cast<const unsigned char*>(sd[b_.h[c].shape].h) + offsetof(ShapeHeader, lis_off));
   }
-  {
-    rt::ProfScope pd("d.speck3d", st);
-    speck3d_decode(w3_, jobs, b_.dev_shapes(), st);
-  }
-  {
-    rt::ProfScope pq("d.reconstruct", st);
-    w3_.fill_n = b_.max_n;
-    speck_reconstruct(w3_, b_.dev(), 0, nullptr, st);
-  }
-
-  // ---- inverse transform ----
-  std::vector<std::vector<int>> groups(b_.shapes.size());
-  for (int c = 0; c < nc; c++)
-    if (!ps[c].is_const)
-      groups[b_.h[c].shape].push_back(c);
-  std::vector<int> flat;
-  std::vector<size_t> goff;
-  for (auto& g : groups) {
-    goff.push_back(flat.size());
-    flat.insert(flat.end(), g.begin(), g.end());
-  }
-  ids_.reserve(flat.size() * 4 + 4);
-  rt::h2d(ids_.p, flat.data(), flat.size() * 4, st);
-  rt::sync(st);
-  {
-    rt::ProfScope pt("d.idwt", st);
-    for (size_t s = 0; s < groups.size(); s++) {
-      if (groups[s].empty())
-        continue;
-      const ShapeHeader& h = b_.shapes[s].h;
-      launch_dwt(true, b_.dev(), ids_.as<int>() + goff[s], int(groups[s].size()), h.nx, h.ny, h.nz,
-                 false, st);
-    }
-  }
-
-  // ---- outliers: SPECK1D decode + correction (src/SPECK_FLT.cpp:576-585) ----
+  // ---- outlier streams (SPECK1D, src/SPECK_FLT.cpp:576-585) ----
+  std::vector<double> tols(nc, 0.0);
+  std::vector<unsigned long long> h_lis_off;
   if (any_out) {
-    rt::ProfScope po("d.outliers", st);
-    size_t tot_lis = 0;
-    std::vector<unsigned long long> h_lis_off;
     std::vector<size_t> lo(nc, 0);
     std::vector<int> nl(nc, 0);
     for (int c = 0; c < nc; c++) {
@@ -222,14 +188,12 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
         const unsigned long long cap2 = l >= 40 ? ~0ull : (1ull << l);
         acc += std::min<unsigned long long>(cap2, ps[c].ototal + 2);
       }
-      tot_lis = std::max<size_t>(tot_lis, acc);
     }
     lis_off1_.reserve(h_lis_off.size() * 8 + 16);
     rt::h2d(lis_off1_.p, h_lis_off.data(), h_lis_off.size() * 8, st);
-    std::vector<DecJob> oj(nc);
-    std::vector<double> tols(nc, 0.0);
     for (int c = 0; c < nc; c++) {
-      DecJob& j = oj[c];
+      DecJob& j = jobs[nc + c];
+      j.kind = 1;
       j.skip = !ps[c].has_out || ps[c].oplanes == 0;
       if (j.skip)
         continue;
@@ -258,12 +222,49 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
       }
       tols[c] = ps[c].q / 1.5;  // src/SPECK_FLT.cpp:578
     }
-    speck1d_decode(w1_, oj, st);
     tols_.reserve(nc * 8);
     rt::h2d(tols_.p, tols.data(), nc * 8, st);
-    w1_.fill_n = 0;
-    speck_reconstruct(w1_, b_.dev(), 1, tols_.as<double>(), st);
-    rt::sync(st);  // `tols`, `h_lis_off` leave scope
+  }
+  {
+    rt::ProfScope pd("d.speck", st);
+    speck_decode(w_, jobs, b_.dev_shapes(), st);
+  }
+  {
+    rt::ProfScope pq("d.reconstruct", st);
+    w_.fill_n = b_.max_n;
+    speck_reconstruct(w_, b_.dev(), 0, nullptr, 0, nc, st);
+  }
+
+  // ---- inverse transform ----
+  std::vector<std::vector<int>> groups(b_.shapes.size());
+  for (int c = 0; c < nc; c++)
+    if (!ps[c].is_const)
+      groups[b_.h[c].shape].push_back(c);
+  std::vector<int> flat;
+  std::vector<size_t> goff;
+  for (auto& g : groups) {
+    goff.push_back(flat.size());
+    flat.insert(flat.end(), g.begin(), g.end());
+  }
+  ids_.reserve(flat.size() * 4 + 4);
+  rt::h2d(ids_.p, flat.data(), flat.size() * 4, st);
+  rt::sync(st);
+  {
+    rt::ProfScope pt("d.idwt", st);
+    for (size_t s = 0; s < groups.size(); s++) {
+      if (groups[s].empty())
+        continue;
+      const ShapeHeader& h = b_.shapes[s].h;
+      launch_dwt(true, b_.dev(), ids_.as<int>() + goff[s], int(groups[s].size()), h.nx, h.ny, h.nz,
+                 false, st);
+    }
+  }
+
+  // ---- outlier correction ----
+  if (any_out) {
+    rt::ProfScope po("d.outliers", st);
+    w_.fill_n = 0;
+    speck_reconstruct(w_, b_.dev(), 1, tols_.as<double>(), nc, nc, st);
   }
 
   // ---- add the mean back, convert and scatter into the output volume ----

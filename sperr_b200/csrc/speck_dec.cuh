@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
   __shared__ int s_go;
   const unsigned c = blockIdx.x;
   DecChunk& d = chunks[c];
-  if (d.skip || d.planes == 0 || d.pow2)   // power-of-two trees: k_speck_decode_fast
+  if (d.skip || d.planes == 0 || d.pow2 || d.kind != T::kKind)   // power-of-two trees: k_speck_decode_fast
     return;
   const int tid = threadIdx.x;
   if (tid == 0) {

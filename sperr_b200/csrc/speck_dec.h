@@ -28,6 +28,7 @@ struct DecChunk {
   int skip;                      // nothing to decode (constant chunk, or no stream)
   unsigned long long n;          // number of coefficients
   int shape;                     // 3D: index into the shape tables
+  int kind;                      // 0: 3D coefficient stream, 1: 1D outlier stream
   uint8_t* pl;                   // n bytes, 0xFF on entry: plane of significance | negative << 7
   uint32_t* lip;                 // LIP mask, all zero on entry
   uint32_t* sigarr;              // scratch of the LIP pass (ceil(n / 32) + 2 words each)
@@ -57,6 +58,7 @@ struct DecChunk {
 struct DecJob {
   unsigned long long n = 0;
   int shape = 0;
+  int kind = 0;   // 0: 3D coefficient stream, 1: 1D outlier stream
   bool skip = true;
   const unsigned char* d_payload = nullptr;   // device pointer: bytes after the 9-byte header
   unsigned long long payload_bytes = 0;
@@ -79,10 +81,9 @@ struct DecWork {
   int max_planes = 0;
 };
 
-// Decodes the sorting passes of every job (see DecChunk).
-void speck3d_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d_shapes,
-                    cudaStream_t st);
-void speck1d_decode(DecWork& w, const std::vector<DecJob>& jobs, cudaStream_t st);
+// Decodes the sorting passes of every job (see DecChunk); 3D and 1D jobs may be mixed.
+void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d_shapes,
+                  cudaStream_t st);
 
 // Rebuilds the magnitudes from the decoded state of speck*_decode and
 //   mode 0: writes the de-quantised coefficients q * mag * sign to chunks[c].coef
@@ -90,7 +91,8 @@ void speck1d_decode(DecWork& w, const std::vector<DecJob>& jobs, cudaStream_t st
 //   mode 1: treats them as outlier correctors and adds them to chunks[c].coef with tolerance
 //           tols[c] (Outlier_Coder::m_inverse_quantize, src/Outlier_Coder.cpp:206-234;
 //           src/SPECK_FLT.cpp:576-585).
+// Works on jobs [first, first + count) of the last speck_decode; job first + c belongs to chunks[c].
 void speck_reconstruct(DecWork& w, const ChunkDev* d_chunks, int mode, const double* d_tols,
-                       cudaStream_t st);
+                       int first, int count, cudaStream_t st);
 
 }  // namespace sperr_b200

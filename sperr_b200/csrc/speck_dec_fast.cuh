@@ -844,160 +844,4 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// host driver
-// ---------------------------------------------------------------------------------------------
-
-// out[w] = little-endian word w of the byte string src[0, len), zero beyond it
-static __global__ void k_stage_bits(const DecChunk* chunks, const unsigned char* const* srcs,
-                                    const unsigned long long* lens, const unsigned long long* words)
-{
-  const unsigned c = blockIdx.y;
-  const unsigned char* src = srcs[c];
-  const unsigned long long len = lens[c], nw = words[c];
-  uint32_t* out = const_cast<uint32_t*>(chunks[c].bits);
-  const unsigned long long avail = chunks[c].avail;
-  for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < nw;
-       w += (unsigned long long)gridDim.x * blockDim.x) {
-    uint32_t v = 0;
-    for (int b = 0; b < 4; b++) {
-      const unsigned long long i = w * 4 + b;
-      if (i < len)
-        v |= uint32_t(src[i]) << (8 * b);
-    }
-    if (w * 32 >= avail)   // bits the stream does not really hold read as zero
-      v = 0;
-    else if (avail - w * 32 < 32)
-      v &= (1u << (avail - w * 32)) - 1u;
-    out[w] = v;
-  }
-}
-
-// Decodes the sorting passes of every job; w.h / w.dchunks hold the decoder state afterwards.
-template <class T>
-void run_decoder(DecWork& w, const std::vector<DecJob>& jobs, const typename T::Data& tree,
-                 cudaStream_t st)
-{
-  const int nj = int(jobs.size());
-  if (nj == 0)
-    return;
-  size_t mask_words = 0, lis_entries = 0, cnt_entries = 0, stage_words = 0, pl_bytes = 0;
-  bool any_fast = false, any_slow = false;
-  std::vector<size_t> mw(nj), sw(nj);
-  w.max_n = 0;
-  w.max_planes = 0;
-  for (int c = 0; c < nj; c++) {
-    const DecJob& j = jobs[c];
-    mw[c] = j.skip ? 0 : (size_t(j.n + 31) / 32 + 4);
-    sw[c] = j.skip ? 0 : (size_t(j.payload_bytes) / 4 + 4);
-    mask_words += 3 * mw[c];
-    pl_bytes += j.skip ? 0 : ((size_t(j.n) + 63) & ~size_t(63));
-    lis_entries += j.skip ? 0 : j.lis_total;
-    cnt_entries += j.skip ? 0 : size_t(j.nlis + 1);
-    stage_words += sw[c];
-    if (!j.skip) {
-      (j.pow2 ? any_fast : any_slow) = true;
-      w.max_n = std::max<size_t>(w.max_n, j.n);
-      w.max_planes = std::max(w.max_planes, j.planes);
-      if (j.planes > kMaxPlanes)
-        throw std::runtime_error("SPECK stream with more than 64 bit-planes");
-    }
-  }
-  w.masks.reserve(mask_words * 4 + 16);
-  w.pl.reserve(pl_bytes + 16);
-  w.lis.reserve(lis_entries * 8 + 16);
-  w.lis_cnt.reserve(cnt_entries * 4 + 16);
-  w.stage.reserve(stage_words * 4 + 16);
-  rt::dset(w.masks.p, 0, mask_words * 4, st);
-  rt::dset(w.pl.p, 0xFF, pl_bytes, st);
-  w.h.assign(nj, DecChunk());
-  std::vector<const unsigned char*> srcs(nj);
-  std::vector<unsigned long long> lens(nj), words(nj);
-  size_t om = 0, ol = 0, oc = 0, os = 0, op = 0, max_words = 1;
-  for (int c = 0; c < nj; c++) {
-    const DecJob& j = jobs[c];
-    DecChunk& d = w.h[c];
-    std::memset(&d, 0, sizeof(d));
-    d.skip = j.skip ? 1 : 0;
-    srcs[c] = j.d_payload;
-    lens[c] = j.skip ? 0 : j.payload_bytes;
-    words[c] = sw[c];
-    if (j.skip)
-      continue;
-    d.n = j.n;
-    d.shape = j.shape;
-    d.planes = j.planes;
-    d.avail = std::min<unsigned long long>(j.total_bits, j.payload_bytes * 8ull);
-    uint32_t* m = w.masks.as<uint32_t>() + om;
-    d.lip = m;
-    d.sigarr = m + mw[c];
-    d.signarr = m + 2 * mw[c];
-    om += 3 * mw[c];
-    d.pl = w.pl.as<uint8_t>() + op;
-    op += (size_t(j.n) + 63) & ~size_t(63);
-    d.lis = w.lis.as<node_t>() + ol;
-    ol += j.lis_total;
-    d.lis_off = j.d_lis_off;
-    d.lis_cnt = w.lis_cnt.as<unsigned>() + oc;
-    oc += size_t(j.nlis + 1);
-    d.nlis = j.nlis;
-    d.bits = w.stage.as<uint32_t>() + os;
-    d.stage_words = sw[c];
-    os += sw[c];
-    d.pow2 = j.pow2;
-    d.Dx = j.Dx; d.Dy = j.Dy; d.Dz = j.Dz;
-    d.nx = j.nx; d.ny = j.ny;
-    d.nroots = j.nroots;
-    for (int r = 0; r < j.nroots; r++)
-      d.roots[r] = j.roots[r];
-    max_words = std::max(max_words, sw[c]);
-  }
-  w.dchunks.reserve(sizeof(DecChunk) * nj);
-  rt::h2d(w.dchunks.p, w.h.data(), sizeof(DecChunk) * nj, st);
-  const size_t aux_bytes = size_t(nj) * 24;
-  w.aux.reserve(aux_bytes);
-  unsigned char* aux = w.aux.as<unsigned char>();
-  rt::h2d(aux, srcs.data(), nj * 8, st);
-  rt::h2d(aux + nj * 8, lens.data(), nj * 8, st);
-  rt::h2d(aux + nj * 16, words.data(), nj * 8, st);
-  DecChunk* dch = w.dchunks.as<DecChunk>();
-  {
-    rt::ProfScope ps("dec.stage_bits", st);
-    const unsigned gx = unsigned(std::min<size_t>((max_words + 255) / 256, 256));
-    LAUNCH(k_stage_bits, dim3(gx, nj), dim3(256), 0, st, dch,
-           reinterpret_cast<const unsigned char* const*>(aux),
-           reinterpret_cast<const unsigned long long*>(aux + nj * 8),
-           reinterpret_cast<const unsigned long long*>(aux + nj * 16));
-  }
-  {
-    rt::ProfScope ps("dec.speck_decode", st);
-    if (any_slow)
-      LAUNCH(k_speck_decode<T>, dim3(nj), dim3(kDecThreads), 0, st, dch, tree);
-    if (any_fast) {
-#ifndef SPERR_EMUL
-      static bool attr_done = false;
-      if (!attr_done) {
-        RT_CHECK(cudaFuncSetAttribute(k_speck_decode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(sizeof(FastSmem))));
-        attr_done = true;
-      }
-#endif
-      LAUNCH(k_speck_decode_fast, dim3(nj), dim3(kDecThreads), sizeof(FastSmem), st, dch);
-    }
-  }
-  rt::d2h(w.h.data(), w.dchunks.p, sizeof(DecChunk) * nj, st);
-  rt::sync(st);
-  if (std::getenv("SPERR_B200_DECPROF"))
-    for (int c = 0; c < nj && c < 2; c++)
-      if (w.h[c].pow2 && !w.h[c].skip)
-        std::fprintf(stderr,
-                     "decprof job %d n=%llu: lip %.2f  windows %.2f (%llu)  chains %.2f  expand %.2f  walker "
-                     "%.2f  Mcycles\n",
-                     c, w.h[c].n, w.h[c].prof[0] * 1e-6, w.h[c].prof[1] * 1e-6, w.h[c].prof[6],
-                     w.h[c].prof[2] * 1e-6, w.h[c].prof[3] * 1e-6, w.h[c].prof[4] * 1e-6);
-  for (int c = 0; c < nj; c++)
-    if (w.h[c].err)
-      throw std::runtime_error("SPECK decoder: list capacity exceeded (corrupt stream?)");
-}
-
 }  // namespace sperr_b200

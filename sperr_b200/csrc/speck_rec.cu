@@ -174,12 +174,12 @@ __global__ void k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const 
 }
 
 void speck_reconstruct(DecWork& w, const ChunkDev* d_chunks, int mode, const double* d_tols,
-                       cudaStream_t st)
+                       int first, int count, cudaStream_t st)
 {
-  const int nj = int(w.h.size());
+  const int nj = count;
   if (nj == 0)
     return;
-  const DecChunk* dj = w.dchunks.as<DecChunk>();
+  const DecChunk* dj = w.dchunks.as<DecChunk>() + first;
   // mode 0 must also zero-fill chunks without a stream, whose extent the jobs do not know
   size_t max_n = w.max_n;
   if (mode == 0)

@@ -1,0 +1,203 @@
+"""Chunk-sharded compression / decompression across the GPUs of one box (one process per GPU).
+
+SPERR's chunks are independent (/root/reference/src/SPERR3D_OMP_C.cpp:94-130), so the volume is
+partitioned into contiguous ranges of ``chunk_volume``'s order (sperr_helper.cpp:542-592) and every
+rank runs the CUDA hot path on its own chunks through the C ABI (include/sperr_b200.h, section 2b).
+``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests) is only plumbing for the one
+exchange each way: all-gather of the per-chunk byte counts, which the container header needs
+(SPERR3D_OMP_C.cpp:225-230), and gather / scatter of the compressed chunk streams. The result on
+rank 0 is the reference's single-stream container, byte-identical to what ``sperr_comp_3d`` writes
+for the whole volume.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sz = C.c_size_t
+vp = C.c_void_p
+sz3 = sz * 3
+
+_libc = C.CDLL(None)
+_libc.free.argtypes = [vp]
+_libc.free.restype = None
+
+
+def _bind(cdll):
+    if getattr(cdll, "_sperr_sharded_bound", False):
+        return cdll
+    cdll.sperr_b200_num_chunks.restype = sz
+    cdll.sperr_b200_num_chunks.argtypes = [sz3, sz3]
+    cdll.sperr_b200_chunk_box.restype = C.c_int
+    cdll.sperr_b200_chunk_box.argtypes = [sz3, sz3, sz, sz, sz3, sz3]
+    cdll.sperr_b200_comp_3d_range_dev.restype = C.c_int
+    cdll.sperr_b200_comp_3d_range_dev.argtypes = [vp, C.c_int, sz3, sz3, sz3, sz3, sz, sz, C.c_int,
+                                                  C.c_double, C.POINTER(vp), C.POINTER(sz), vp]
+    cdll.sperr_b200_container_header.restype = sz
+    cdll.sperr_b200_container_header.argtypes = [sz3, sz3, C.c_int, vp, sz, vp, sz]
+    cdll.sperr_b200_parse_container.restype = C.c_int
+    cdll.sperr_b200_parse_container.argtypes = [vp, sz, sz3, sz3, C.POINTER(C.c_int), C.POINTER(sz),
+                                                vp, sz, C.POINTER(sz)]
+    cdll.sperr_b200_decomp_3d_range_dev.restype = C.c_int
+    cdll.sperr_b200_decomp_3d_range_dev.argtypes = [vp, sz, vp, sz3, sz3, sz3, sz3, sz, sz, C.c_int, vp]
+    cdll._sperr_sharded_bound = True
+    return cdll
+
+
+def chunk_range(nchunks, rank, world):
+    """Contiguous range of chunk indices owned by `rank` (earlier ranks get the remainder)."""
+    base, rem = divmod(nchunks, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class Shard:
+    """What one rank owns: chunk range and the bounding box of those chunks inside the volume."""
+
+    def __init__(self, cdll, vol, chunk, rank, world):
+        self.cdll = _bind(cdll)
+        self.vol, self.chunk = sz3(*vol), sz3(*chunk)
+        self.nchunks = int(self.cdll.sperr_b200_num_chunks(self.vol, self.chunk))
+        if self.nchunks < world:
+            raise ValueError("fewer chunks (%d) than ranks (%d)" % (self.nchunks, world))
+        self.begin, self.end = chunk_range(self.nchunks, rank, world)
+        self.origin, self.extent = sz3(), sz3()
+        rc = self.cdll.sperr_b200_chunk_box(self.vol, self.chunk, self.begin, self.end, self.origin,
+                                            self.extent)
+        assert rc == 0
+        self.ranges = [chunk_range(self.nchunks, r, world) for r in range(world)]
+
+    @property
+    def box_origin(self):
+        return tuple(self.origin)
+
+    @property
+    def box_extent(self):
+        return tuple(self.extent)
+
+    def slices(self):
+        """numpy / torch index of the box inside a (z, y, x) view of the whole volume."""
+        o, e = self.box_origin, self.box_extent
+        return (slice(o[2], o[2] + e[2]), slice(o[1], o[1] + e[1]), slice(o[0], o[0] + e[0]))
+
+
+def _world(group):
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def compress_3d_sharded(cdll, box, vol, chunk, mode, quality, group=None):
+    """box: this rank's part of the volume as a contiguous float32 / float64 torch tensor (z, y, x)
+    that lives where the library computes (CUDA device for libsperr_b200.so). Returns the container
+    (uint8 numpy array) on rank 0 and None elsewhere."""
+    rank, world = _world(group)
+    sh = Shard(cdll, vol, chunk, rank, world)
+    assert box.is_contiguous() and tuple(box.shape) == sh.box_extent[::-1], (box.shape, sh.box_extent)
+    is_float = box.dtype == torch.float32
+    n_mine = sh.end - sh.begin
+    lens = np.zeros(n_mine, dtype=np.uint32)
+    dst, n = vp(None), sz(0)
+    rc = sh.cdll.sperr_b200_comp_3d_range_dev(vp(box.data_ptr()), int(is_float), sh.vol, sh.chunk,
+                                              sh.origin, sh.extent, sh.begin, sh.end, mode, quality,
+                                              C.byref(dst), C.byref(n), lens.ctypes.data_as(vp))
+    dev = box.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    ok = torch.tensor([abs(rc)], device=dev, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=group)
+    if int(ok.item()) != 0:
+        if rc == 0:
+            _libc.free(dst)
+        raise RuntimeError("sperr_b200_comp_3d_range_dev failed on some rank (rc=%d here)" % rc)
+    mine = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_uint8)), shape=(max(n.value, 1),))[:n.value]
+
+    # 1. all-gather the per-chunk byte counts (ranges may differ by one chunk: pad)
+    per = max(e - b for b, e in sh.ranges)
+    mylens = torch.zeros(per, dtype=torch.int64, device=dev)
+    mylens[:n_mine] = torch.from_numpy(lens.astype(np.int64)).to(dev)
+    all_lens = [torch.zeros(per, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_lens, mylens, group=group)
+    lens_by_rank = [t.cpu().numpy()[:e - b] for t, (b, e) in zip(all_lens, sh.ranges)]
+    bytes_by_rank = [int(l.sum()) for l in lens_by_rank]
+
+    # 2. gather the chunk streams on rank 0 (variable length: pad to the longest)
+    longest = max(bytes_by_rank)
+    payload = torch.zeros(longest, dtype=torch.uint8, device=dev)
+    payload[:n.value] = torch.from_numpy(mine.copy() if n.value else np.zeros(0, np.uint8)).to(dev)
+    _libc.free(dst)
+    parts = [torch.zeros(longest, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+    dist.gather(payload, parts, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    if rank != 0:
+        return None
+
+    # 3. reference-layout container: header with every chunk length, then the streams in chunk order
+    all32 = np.concatenate(lens_by_rank).astype(np.uint32)
+    hlen = int(sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), None, sh.nchunks, None, 0))
+    out = np.empty(hlen + sum(bytes_by_rank), dtype=np.uint8)
+    got = sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), all32.ctypes.data_as(vp),
+                                              sh.nchunks, out.ctypes.data_as(vp), out.size)
+    assert got == hlen
+    pos = hlen
+    for r in range(world):
+        out[pos:pos + bytes_by_rank[r]] = parts[r][:bytes_by_rank[r]].cpu().numpy()
+        pos += bytes_by_rank[r]
+    return out
+
+
+def parse_container(cdll, stream):
+    """(vol, chunk, is_float, header_len, lens) of a container held in host memory."""
+    cdll = _bind(cdll)
+    stream = np.ascontiguousarray(stream, dtype=np.uint8)
+    vol, chunk = sz3(), sz3()
+    isf, hlen, nch = C.c_int(0), sz(0), sz(0)
+    rc = cdll.sperr_b200_parse_container(stream.ctypes.data_as(vp), stream.size, vol, chunk, C.byref(isf),
+                                         C.byref(hlen), None, 0, C.byref(nch))
+    if rc != 0:
+        raise ValueError("not a SPERR 3D container")
+    lens = np.zeros(nch.value, dtype=np.uint32)
+    rc = cdll.sperr_b200_parse_container(stream.ctypes.data_as(vp), stream.size, vol, chunk, C.byref(isf),
+                                         C.byref(hlen), lens.ctypes.data_as(vp), lens.size, C.byref(nch))
+    if rc != 0 or hlen.value + int(lens.astype(np.int64).sum()) != stream.size:
+        raise ValueError("truncated SPERR 3D container")
+    return tuple(vol), tuple(chunk), bool(isf.value), hlen.value, lens
+
+
+def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
+    """stream: the container (uint8 numpy array) on rank 0, ignored elsewhere. Every rank returns
+    (box, shard): its part of the decoded volume as a (z, y, x) tensor on `device`, and the Shard that
+    says where the box sits."""
+    rank, world = _world(group)
+    cdll = _bind(cdll)
+    dev = device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    src0 = dist.get_global_rank(group, 0) if group is not None else 0
+    meta = [None]
+    if rank == 0:
+        vol, chunk, isf, hlen, lens = parse_container(cdll, stream)
+        meta = [(vol, chunk, lens)]
+    dist.broadcast_object_list(meta, src=src0, group=group)
+    vol, chunk, lens = meta[0]
+    sh = Shard(cdll, vol, chunk, rank, world)
+    bytes_by_rank = [int(lens[b:e].astype(np.int64).sum()) for b, e in sh.ranges]
+    longest = max(bytes_by_rank)
+    mine = torch.zeros(longest, dtype=torch.uint8, device=dev)
+    parts = None
+    if rank == 0:
+        parts, pos = [], hlen
+        for r in range(world):
+            t = torch.zeros(longest, dtype=torch.uint8)
+            t[:bytes_by_rank[r]] = torch.from_numpy(np.ascontiguousarray(stream[pos:pos + bytes_by_rank[r]]))
+            parts.append(t.to(dev))
+            pos += bytes_by_rank[r]
+    dist.scatter(mine, parts, src=src0, group=group)
+    h = mine[:bytes_by_rank[rank]].cpu().numpy()
+    h = np.ascontiguousarray(h)
+    mylens = np.ascontiguousarray(lens[sh.begin:sh.end], dtype=np.uint32)
+    e = sh.box_extent
+    box = torch.empty((e[2], e[1], e[0]), dtype=torch.float32 if output_float else torch.float64,
+                      device=device)
+    rc = cdll.sperr_b200_decomp_3d_range_dev(h.ctypes.data_as(vp), h.size, mylens.ctypes.data_as(vp), sh.vol,
+                                             sh.chunk, sh.origin, sh.extent, sh.begin, sh.end,
+                                             int(output_float), vp(box.data_ptr()))
+    ok = torch.tensor([abs(rc)], device=dev, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=group)
+    if int(ok.item()) != 0:
+        raise RuntimeError("sperr_b200_decomp_3d_range_dev failed (rc=%d here)" % rc)
+    return box, sh
