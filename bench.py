@@ -392,9 +392,9 @@ def run_ours(args):
         dt = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
+        ssz = int(stream.size) if stream is not None else 0
         e2e = {"value": world * nbytes / dt / GB, "unit": "GB/s",
-               "h2d_bytes_per_step": world * nbytes + int(stream.size),
-               "d2h_bytes_per_step": int(stream.size) + world * nbytes}
+               "h2d_bytes_per_step": world * nbytes + ssz, "d2h_bytes_per_step": ssz + world * nbytes}
 
     if rank == 0:
         nvals = n ** 3

@@ -73,12 +73,18 @@ size_t sperr_b200_num_chunks(const size_t vol[3], const size_t chunk[3]);
 int sperr_b200_chunk_box(const size_t vol[3], const size_t chunk[3], size_t begin, size_t end,
                          size_t origin[3], size_t extent[3]);
 
-/* Compresses the chunks of the range. *dst (malloc'd, must be NULL on entry) receives their streams
- * back to back, lens[i] the length of chunk chunk_begin + i. Return codes as sperr_comp_3d. */
+/* Compresses the chunks of the range. *d_streams receives a library-owned DEVICE buffer (valid
+ * until the next call into the library) holding their streams back to back, lens[i] the length of
+ * chunk chunk_begin + i. Returns 0 ok; 2 bad parameter; -1 other error. */
 int sperr_b200_comp_3d_range_dev(const void* d_box, int is_float, const size_t vol[3],
                                  const size_t chunk[3], const size_t box_origin[3],
                                  const size_t box_extent[3], size_t chunk_begin, size_t chunk_end,
-                                 int mode, double quality, void** dst, size_t* dst_len, uint32_t* lens);
+                                 int mode, double quality, const void** d_streams, size_t* streams_len,
+                                 uint32_t* lens);
+
+/* Synchronous copy helper for callers that hold raw pointers: kind 0 device -> device, 1 host ->
+ * device, 2 device -> host. */
+int sperr_b200_memcpy_dev(void* dst, const void* src, size_t n, int kind);
 
 /* Writes the reference container header (SPERR3D_OMP_C::m_generate_header, SPERR3D_OMP_C.cpp:
  * 163-234) for `nchunks` chunk lengths into out[0, cap) and returns its length (call with out = NULL
@@ -92,9 +98,12 @@ int sperr_b200_parse_container(const void* src, size_t len, size_t vol[3], size_
                                int* is_float, size_t* header_len, uint32_t* lens, size_t cap,
                                size_t* nchunks);
 
-/* Decodes the chunks of the range from their streams (HOST memory, back to back, lens[i] each) into
- * the caller's DEVICE box (float when output_float != 0, else double). */
-int sperr_b200_decomp_3d_range_dev(const void* h_streams, size_t streams_len, const uint32_t* lens,
+/* Decodes the chunks of the range from their streams (back to back, lens[i] each) into the caller's
+ * DEVICE box (float when output_float != 0, else double). h_streams: the streams in HOST memory
+ * (chunk headers are parsed on the host); d_streams: the same bytes in DEVICE memory, or NULL to
+ * have them uploaded. */
+int sperr_b200_decomp_3d_range_dev(const void* h_streams, const void* d_streams, size_t streams_len,
+                                   const uint32_t* lens,
                                    const size_t vol[3], const size_t chunk[3],
                                    const size_t box_origin[3], const size_t box_extent[3],
                                    size_t chunk_begin, size_t chunk_end, int output_float,

@@ -108,10 +108,9 @@ int sperr_b200_chunk_box(const size_t vol[3], const size_t chunk[3], size_t begi
 int sperr_b200_comp_3d_range_dev(const void* d_box, int is_float, const size_t vol[3],
                                  const size_t chunk[3], const size_t box_origin[3],
                                  const size_t box_extent[3], size_t chunk_begin, size_t chunk_end,
-                                 int mode, double quality, void** dst, size_t* dst_len, uint32_t* lens)
+                                 int mode, double quality, const void** d_streams, size_t* streams_len,
+                                 uint32_t* lens)
 {
-  if (*dst != nullptr)
-    return 1;
   if (quality <= 0.0 || mode < 1 || mode > 3)
     return 2;
   std::lock_guard<std::mutex> lock(g_rmutex);
@@ -133,13 +132,9 @@ int sperr_b200_comp_3d_range_dev(const void* d_box, int is_float, const size_t v
       lens[i] = uint32_t(l[i]);
       total += l[i];
     }
-    uint8_t* o = static_cast<uint8_t*>(std::malloc(total ? total : 1));
-    if (!o)
-      return -1;
-    rt::d2h(o, g_rout.p, total, st);
     rt::sync(st);
-    *dst = o;
-    *dst_len = total;
+    *d_streams = g_rout.p;   // library-owned device buffer, valid until the next call
+    *streams_len = total;
     return 0;
   });
 }
@@ -206,7 +201,23 @@ int sperr_b200_parse_container(const void* src, size_t len, size_t vol[3], size_
   return 0;
 }
 
-int sperr_b200_decomp_3d_range_dev(const void* h_streams, size_t streams_len, const uint32_t* lens,
+int sperr_b200_memcpy_dev(void* dst, const void* src, size_t n, int kind)
+{
+  return guarded([&] {
+    cudaStream_t st = 0;
+    if (kind == 0)
+      rt::d2d(dst, src, n, st);
+    else if (kind == 1)
+      rt::h2d(dst, src, n, st);
+    else
+      rt::d2h(dst, src, n, st);
+    rt::sync(st);
+    return 0;
+  });
+}
+
+int sperr_b200_decomp_3d_range_dev(const void* h_streams, const void* d_streams, size_t streams_len,
+                                   const uint32_t* lens,
                                    const size_t vol[3], const size_t chunk[3],
                                    const size_t box_origin[3], const size_t box_extent[3],
                                    size_t chunk_begin, size_t chunk_end, int output_float,
@@ -229,11 +240,14 @@ int sperr_b200_decomp_3d_range_dev(const void* h_streams, size_t streams_len, co
     if (!g_rdecomp)
       g_rdecomp = new Decompressor();
     cudaStream_t st = 0;
-    g_rstream.reserve(streams_len + 16);
-    rt::h2d(g_rstream.p, h_streams, streams_len, st);
+    const uint8_t* ds = static_cast<const uint8_t*>(d_streams);
+    if (!ds) {
+      g_rstream.reserve(streams_len + 16);
+      rt::h2d(g_rstream.p, h_streams, streams_len, st);
+      ds = g_rstream.as<uint8_t>();
+    }
     SrcVol dv{d_box_out, output_float, box_extent[0], box_extent[1]};
-    g_rdecomp->decompress(static_cast<const uint8_t*>(h_streams), g_rstream.as<uint8_t>(), chunks, cs,
-                          dv, st);
+    g_rdecomp->decompress(static_cast<const uint8_t*>(h_streams), ds, chunks, cs, dv, st);
     rt::sync(st);
     return 0;
   });

@@ -34,13 +34,15 @@ def _bind(cdll):
     cdll.sperr_b200_comp_3d_range_dev.restype = C.c_int
     cdll.sperr_b200_comp_3d_range_dev.argtypes = [vp, C.c_int, sz3, sz3, sz3, sz3, sz, sz, C.c_int,
                                                   C.c_double, C.POINTER(vp), C.POINTER(sz), vp]
+    cdll.sperr_b200_memcpy_dev.restype = C.c_int
+    cdll.sperr_b200_memcpy_dev.argtypes = [vp, vp, sz, C.c_int]
     cdll.sperr_b200_container_header.restype = sz
     cdll.sperr_b200_container_header.argtypes = [sz3, sz3, C.c_int, vp, sz, vp, sz]
     cdll.sperr_b200_parse_container.restype = C.c_int
     cdll.sperr_b200_parse_container.argtypes = [vp, sz, sz3, sz3, C.POINTER(C.c_int), C.POINTER(sz),
                                                 vp, sz, C.POINTER(sz)]
     cdll.sperr_b200_decomp_3d_range_dev.restype = C.c_int
-    cdll.sperr_b200_decomp_3d_range_dev.argtypes = [vp, sz, vp, sz3, sz3, sz3, sz3, sz, sz, C.c_int, vp]
+    cdll.sperr_b200_decomp_3d_range_dev.argtypes = [vp, vp, sz, vp, sz3, sz3, sz3, sz3, sz, sz, C.c_int, vp]
     cdll._sperr_sharded_bound = True
     return cdll
 
@@ -86,28 +88,39 @@ def _world(group):
     return dist.get_rank(group), dist.get_world_size(group)
 
 
+_pinned = {}
+
+
+def _pinned_u8(n, key):
+    """Grow-only pinned staging (one buffer per use per process)."""
+    t = _pinned.get(key)
+    if t is None or t.numel() < n:
+        t = torch.empty(max(n, 1 << 20), dtype=torch.uint8)
+        if torch.cuda.is_available():
+            t = t.pin_memory()
+        _pinned[key] = t
+    return t
+
+
 def compress_3d_sharded(cdll, box, vol, chunk, mode, quality, group=None):
     """box: this rank's part of the volume as a contiguous float32 / float64 torch tensor (z, y, x)
     that lives where the library computes (CUDA device for libsperr_b200.so). Returns the container
-    (uint8 numpy array) on rank 0 and None elsewhere."""
+    (uint8 numpy array, backed by a reused staging buffer) on rank 0 and None elsewhere."""
     rank, world = _world(group)
     sh = Shard(cdll, vol, chunk, rank, world)
     assert box.is_contiguous() and tuple(box.shape) == sh.box_extent[::-1], (box.shape, sh.box_extent)
     is_float = box.dtype == torch.float32
     n_mine = sh.end - sh.begin
     lens = np.zeros(n_mine, dtype=np.uint32)
-    dst, n = vp(None), sz(0)
+    d_streams, n = vp(None), sz(0)
     rc = sh.cdll.sperr_b200_comp_3d_range_dev(vp(box.data_ptr()), int(is_float), sh.vol, sh.chunk,
                                               sh.origin, sh.extent, sh.begin, sh.end, mode, quality,
-                                              C.byref(dst), C.byref(n), lens.ctypes.data_as(vp))
-    dev = box.device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+                                              C.byref(d_streams), C.byref(n), lens.ctypes.data_as(vp))
+    dev = box.device
     ok = torch.tensor([abs(rc)], device=dev, dtype=torch.int32)
     dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=group)
     if int(ok.item()) != 0:
-        if rc == 0:
-            _libc.free(dst)
         raise RuntimeError("sperr_b200_comp_3d_range_dev failed on some rank (rc=%d here)" % rc)
-    mine = np.ctypeslib.as_array(C.cast(dst, C.POINTER(C.c_uint8)), shape=(max(n.value, 1),))[:n.value]
 
     # 1. all-gather the per-chunk byte counts (ranges may differ by one chunk: pad)
     per = max(e - b for b, e in sh.ranges)
@@ -118,12 +131,13 @@ def compress_3d_sharded(cdll, box, vol, chunk, mode, quality, group=None):
     lens_by_rank = [t.cpu().numpy()[:e - b] for t, (b, e) in zip(all_lens, sh.ranges)]
     bytes_by_rank = [int(l.sum()) for l in lens_by_rank]
 
-    # 2. gather the chunk streams on rank 0 (variable length: pad to the longest)
-    longest = max(bytes_by_rank)
-    payload = torch.zeros(longest, dtype=torch.uint8, device=dev)
-    payload[:n.value] = torch.from_numpy(mine.copy() if n.value else np.zeros(0, np.uint8)).to(dev)
-    _libc.free(dst)
-    parts = [torch.zeros(longest, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+    # 2. gather the chunk streams on rank 0, device to device (variable length: pad to the longest)
+    longest = max(max(bytes_by_rank), 1)
+    payload = torch.empty(longest, dtype=torch.uint8, device=dev)
+    if n.value:
+        rc = sh.cdll.sperr_b200_memcpy_dev(vp(payload.data_ptr()), d_streams, n.value, 0)
+        assert rc == 0
+    parts = [torch.empty(longest, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
     dist.gather(payload, parts, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     if rank != 0:
         return None
@@ -131,14 +145,18 @@ def compress_3d_sharded(cdll, box, vol, chunk, mode, quality, group=None):
     # 3. reference-layout container: header with every chunk length, then the streams in chunk order
     all32 = np.concatenate(lens_by_rank).astype(np.uint32)
     hlen = int(sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), None, sh.nchunks, None, 0))
-    out = np.empty(hlen + sum(bytes_by_rank), dtype=np.uint8)
+    total = hlen + sum(bytes_by_rank)
+    stage = _pinned_u8(total, "container")
+    out = stage.numpy()[:total]
     got = sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), all32.ctypes.data_as(vp),
                                               sh.nchunks, out.ctypes.data_as(vp), out.size)
     assert got == hlen
     pos = hlen
     for r in range(world):
-        out[pos:pos + bytes_by_rank[r]] = parts[r][:bytes_by_rank[r]].cpu().numpy()
+        stage[pos:pos + bytes_by_rank[r]].copy_(parts[r][:bytes_by_rank[r]])
         pos += bytes_by_rank[r]
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
     return out
 
 
@@ -166,7 +184,7 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
     says where the box sits."""
     rank, world = _world(group)
     cdll = _bind(cdll)
-    dev = device if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    dev = torch.device(device)
     src0 = dist.get_global_rank(group, 0) if group is not None else 0
     meta = [None]
     if rank == 0:
@@ -176,26 +194,34 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
     vol, chunk, lens = meta[0]
     sh = Shard(cdll, vol, chunk, rank, world)
     bytes_by_rank = [int(lens[b:e].astype(np.int64).sum()) for b, e in sh.ranges]
-    longest = max(bytes_by_rank)
-    mine = torch.zeros(longest, dtype=torch.uint8, device=dev)
+    longest = max(max(bytes_by_rank), 1)
+    mine = torch.empty(longest, dtype=torch.uint8, device=dev)
     parts = None
     if rank == 0:
+        # one upload of the container, then equal-sized device slices for the scatter
+        d_all = torch.from_numpy(np.ascontiguousarray(stream)).to(dev)
         parts, pos = [], hlen
         for r in range(world):
-            t = torch.zeros(longest, dtype=torch.uint8)
-            t[:bytes_by_rank[r]] = torch.from_numpy(np.ascontiguousarray(stream[pos:pos + bytes_by_rank[r]]))
-            parts.append(t.to(dev))
+            t = torch.empty(longest, dtype=torch.uint8, device=dev)
+            t[:bytes_by_rank[r]].copy_(d_all[pos:pos + bytes_by_rank[r]])
+            parts.append(t)
             pos += bytes_by_rank[r]
     dist.scatter(mine, parts, src=src0, group=group)
-    h = mine[:bytes_by_rank[rank]].cpu().numpy()
-    h = np.ascontiguousarray(h)
+    nb = bytes_by_rank[rank]
+    # chunk headers are parsed on the host: bring this rank's streams over once (pinned staging)
+    stage = _pinned_u8(nb, "streams")
+    stage[:nb].copy_(mine[:nb])
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
+    h = stage.numpy()[:nb]
     mylens = np.ascontiguousarray(lens[sh.begin:sh.end], dtype=np.uint32)
     e = sh.box_extent
     box = torch.empty((e[2], e[1], e[0]), dtype=torch.float32 if output_float else torch.float64,
-                      device=device)
-    rc = cdll.sperr_b200_decomp_3d_range_dev(h.ctypes.data_as(vp), h.size, mylens.ctypes.data_as(vp), sh.vol,
-                                             sh.chunk, sh.origin, sh.extent, sh.begin, sh.end,
-                                             int(output_float), vp(box.data_ptr()))
+                      device=dev)
+    rc = cdll.sperr_b200_decomp_3d_range_dev(h.ctypes.data_as(vp), vp(mine.data_ptr()), nb,
+                                             mylens.ctypes.data_as(vp), sh.vol, sh.chunk, sh.origin,
+                                             sh.extent, sh.begin, sh.end, int(output_float),
+                                             vp(box.data_ptr()))
     ok = torch.tensor([abs(rc)], device=dev, dtype=torch.int32)
     dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=group)
     if int(ok.item()) != 0:
