@@ -239,10 +239,12 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    # one rank per GPU over NCCL; a single GPU is a world of one (same code path)
+    import torch.distributed as dist
+    if "MASTER_ADDR" not in os.environ:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(20000 + os.getpid() % 20000)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     L = sperr_b200.load()
     n = args.size
@@ -250,50 +252,32 @@ def run_ours(args):
     nbytes = n * n * n * 4
     vol = field_torch(dims, (0, 0, rank * n), dev)
     torch.cuda.synchronize()
-    out_dev = torch.empty(n * n * n, device=dev, dtype=torch.float32)
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        dist.barrier()
         torch.cuda.synchronize()
 
-    if world == 1:
-        def comp_dev():
-            rc, stream = L.compress_3d_dev(vol.data_ptr(), True, dims, (CHUNK,) * 3, 3, TOL)
-            assert rc == 0, rc
-            return stream
+    # The volume is n x n x (n * N); rank r owns the chunks of its own z-slab. One exchange each way
+    # over NCCL: chunk lengths + chunk streams to rank 0 (which assembles the single reference-layout
+    # container), and the streams back out for decoding.
+    from sperr_b200 import sharded
+    gdims = (n, n, n * world)
+    box = vol.view(n, n, n)
+    state = {}
 
-        def decomp_dev(stream, d_stream):
-            rc, d = L.decompress_3d_dev(stream, d_stream.data_ptr(), out_dev.data_ptr(), True)
-            assert rc == 0 and d == dims, (rc, d)
+    def comp_dev():
+        s = sharded.compress_3d_sharded(L.lib, box, gdims, (CHUNK,) * 3, 3, TOL)
+        state["stream"] = s
+        return s
 
-        def step_dev():
-            stream = comp_dev()
-            d_stream = torch.from_numpy(stream).to(dev)
-            decomp_dev(stream, d_stream)
-            return stream
-    else:
-        # N ranks: the volume is n x n x (n * N); rank r owns the chunks of its own z-slab. One
-        # exchange each way over NCCL: chunk lengths + chunk streams to rank 0 (which assembles the
-        # single reference-layout container), and the streams back out for decoding.
-        from sperr_b200 import sharded
-        gdims = (n, n, n * world)
-        box = vol.view(n, n, n)
-        state = {}
+    def decomp_dev(stream, d_stream=None):
+        b, sh = sharded.decompress_3d_sharded(L.lib, stream, dev, True)
+        state["out"] = b
 
-        def comp_dev():
-            s = sharded.compress_3d_sharded(L.lib, box, gdims, (CHUNK,) * 3, 3, TOL)
-            state["stream"] = s
-            return s
-
-        def decomp_dev(stream, d_stream):
-            b, sh = sharded.decompress_3d_sharded(L.lib, stream, dev, True)
-            state["out"] = b
-
-        def step_dev():
-            stream = comp_dev()
-            decomp_dev(stream, None)
-            return stream
+    def step_dev():
+        stream = comp_dev()
+        decomp_dev(stream)
+        return stream
 
     prof_on = L.fn("sperr_b200_prof_enable", None, [C.c_int])
     prof_dump = L.fn("sperr_b200_prof_dump", C.c_size_t, [C.c_char_p, C.c_size_t])
@@ -314,8 +298,7 @@ def run_ours(args):
         launches_per_step = (launch_count() - l0) // args.steps
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
 
     # compress-only and decompress-only rates (device-resident)
@@ -328,13 +311,11 @@ def run_ours(args):
         b.record()
         barrier()
         tt = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
-    d_stream = torch.from_numpy(stream).to(dev) if world == 1 else None
     ms_c = timed(comp_dev, args.steps)
-    ms_d = timed(lambda: decomp_dev(stream, d_stream), args.steps)
-    got = out_dev if world == 1 else state["out"].reshape(-1)
+    ms_d = timed(lambda: decomp_dev(stream), args.steps)
+    got = state["out"].reshape(-1)
     maxerr = float((got.double() - vol.double()).abs().max().item())
     # decoded values are rounded to fp32 after the bound was enforced in fp64: allow one fp32 ulp
     assert maxerr <= TOL + 1.2e-7, "PWE bound violated: %g" % maxerr
@@ -364,8 +345,7 @@ def run_ours(args):
             s2 = e2e_step()
         torch.cuda.synchronize()
         dt = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
-        if dist is not None:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
         e2e = {"value": world * nbytes / dt / GB, "unit": "GB/s",
                "h2d_bytes_per_step": nbytes + int(s2.size), "d2h_bytes_per_step": int(s2.size) + nbytes}
@@ -413,8 +393,7 @@ def run_ours(args):
         if world == 1 and args.cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(out))
-    if dist is not None:
-        dist.destroy_process_group()
+    dist.destroy_process_group()
 
 
 def measured_peak():
