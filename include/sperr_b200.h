@@ -126,6 +126,8 @@ unsigned long long sperr_b200_launch_count(void);
 int sperr_b200_stage_condition(const void* src, int is_float, size_t nx, size_t ny, size_t nz,
                                double* out_vals, double* out_mean, int* out_is_const);
 int sperr_b200_stage_dwt(double* buf, size_t nx, size_t ny, size_t nz, int inverse, int is_2d);
+/* Same transform through the fused one-round-trip-per-level kernels (dyadic shapes only; -2 else). */
+int sperr_b200_stage_dwt_fused(double* buf, size_t nx, size_t ny, size_t nz, int inverse);
 int sperr_b200_stage_quantize(const double* vals, size_t nx, size_t ny, size_t nz, double q,
                               uint64_t* mags, uint8_t* signs, int* wide);
 int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, size_t nx, size_t ny,

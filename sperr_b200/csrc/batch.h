@@ -12,11 +12,12 @@ struct BatchBuffers {
   std::vector<ChunkDev> h;           // host mirror of the device chunk array
   std::vector<ShapeTables> shapes;   // distinct chunk shapes of this batch
   rt::DBuf d_chunks, d_shapes, shape_mem;
-  rt::DBuf coef, mag, signs, pleaf, cmap, pyr_p, pyr_d;
+  rt::DBuf coef, mag, signs, pleaf, cmap, pyr_p, pyr_d, scratch;
   size_t max_n = 0;
   size_t sign_words = 0, mag_elems = 0;   // totals over the batch (padded)
   bool wide = false;
 
+  static bool no_fused() { return std::getenv("SPERR_B200_NO_FUSED_DWT") != nullptr; }
   ChunkDev* dev() const { return d_chunks.as<ChunkDev>(); }
   const ShapeDev* dev_shapes() const { return d_shapes.as<ShapeDev>(); }
   int size() const { return int(h.size()); }
@@ -30,7 +31,7 @@ struct BatchBuffers {
     h.assign(nc, ChunkDev());
     shapes.clear();
     std::map<std::array<uint32_t, 3>, int> seen;
-    size_t tot_n = 0, tot_words = 0, tot_pyr = 0;
+    size_t tot_n = 0, tot_words = 0, tot_pyr = 0, tot_scr = 0;
     max_n = 0;
     wide = wide_mag;
     for (int c = 0; c < nc; c++) {
@@ -51,13 +52,21 @@ struct BatchBuffers {
       d.min_key = ~0ull;
       d.max_key = 0;
       d.wide = wide_mag ? 1 : 0;
+      {
+        long long lo[8];
+        d.fused = (need_coef && shapes[d.shape].h.dyadic >= 1 && !no_fused()) ? 1 : 0;
+        if (d.fused)
+          tot_scr += (fused_scratch_elems(k.lx, k.ly, k.lz, lo) + 63) & ~size_t(63);
+      }
       tot_n += (d.n + 63) & ~size_t(63);
       tot_words += (d.n + 31) / 32 + 2;
       tot_pyr += shapes[d.shape].h.pyr_nodes + 64;
       max_n = std::max<size_t>(max_n, d.n);
     }
-    if (need_coef)
+    if (need_coef) {
       coef.reserve(tot_n * 8);
+      scratch.reserve(tot_scr * 8 + 64);
+    }
     if (need_speck) {
       mag.reserve(tot_n * (wide_mag ? 8 : 4));
       signs.reserve(tot_words * 4);
@@ -70,11 +79,16 @@ struct BatchBuffers {
     }
     sign_words = tot_words;
     mag_elems = tot_n;
-    size_t on = 0, ow = 0, op = 0;
+    size_t on = 0, ow = 0, op = 0, osc = 0;
     for (int c = 0; c < nc; c++) {
       ChunkDev& d = h[c];
       if (need_coef)
         d.coef = coef.as<double>() + on;
+      if (d.fused) {
+        long long lo[8];
+        d.scratch = scratch.as<double>() + osc;
+        osc += (fused_scratch_elems(d.nx, d.ny, d.nz, lo) + 63) & ~size_t(63);
+      }
       if (need_speck) {
         d.mag = mag.as<unsigned char>() + on * (wide_mag ? 8 : 4);
         d.signs = signs.as<uint32_t>() + ow;

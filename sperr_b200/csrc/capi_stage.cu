@@ -83,6 +83,37 @@ int sperr_b200_stage_dwt(double* buf, size_t nx, size_t ny, size_t nz, int inver
   });
 }
 
+int sperr_b200_stage_dwt_fused(double* buf, size_t nx, size_t ny, size_t nz, int inverse)
+{
+  return guarded([&] {
+    if (can_use_dyadic(nx, ny, nz) < 1)
+      return -2;   // not a shape the fused kernels handle
+    cudaStream_t st = 0;
+    BatchBuffers b;
+    b.setup({whole(nx, ny, nz)}, true, false, false, st);
+    if (!b.h[0].fused)
+      return -2;
+    const size_t n = nx * ny * nz;
+    rt::DBuf vol(n * 8), ids(4);
+    const int zero = 0;
+    rt::h2d(ids.p, &zero, 4, st);
+    SrcVol sv{vol.p, 0, nx, ny};
+    if (!inverse) {
+      rt::h2d(vol.p, buf, n * 8, st);   // mean is 0: v - 0.0 == v bit for bit
+      launch_dwt_fused_forward(sv, b.dev(), ids.as<int>(), 1, uint32_t(nx), uint32_t(ny), uint32_t(nz), st);
+      rt::d2h(buf, b.h[0].coef, n * 8, st);
+    }
+    else {
+      rt::h2d(b.h[0].coef, buf, n * 8, st);
+      launch_dwt_fused_inverse(sv, 0, b.dev(), ids.as<int>(), 1, uint32_t(nx), uint32_t(ny), uint32_t(nz), 0.0,
+                               OutlierSink{}, CorrectorList{}, st);
+      rt::d2h(buf, vol.p, n * 8, st);
+    }
+    rt::sync(st);
+    return 0;
+  });
+}
+
 int sperr_b200_stage_quantize(const double* vals, size_t nx, size_t ny, size_t nz, double q,
                               uint64_t* mags, uint8_t* signs, int* wide)
 {

@@ -23,6 +23,9 @@ struct ChunkDev {
   int shape;                // index into the batch's ShapeDev array
 
   double* coef;             // n fp64: conditioned values -> wavelet coefficients (in place)
+  double* scratch;          // fused transform: compact approx boxes of levels 1 .. L-1
+  int fused;                // dyadic shape: transformed by dwt_fused.cu (one round trip per level)
+  uint32_t* obits;          // decoder: bit i set when value i has an outlier corrector
   void* mag;                // n quantised magnitudes (uint32_t or uint64_t, see `wide`)
   uint32_t* signs;          // ceil(n/32) words, bit i = 1 when value i is non-negative
   int8_t* pleaf;            // n: msb position of each magnitude (-1 for zero)

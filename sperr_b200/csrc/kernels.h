@@ -15,6 +15,62 @@ struct SrcVol {
   unsigned long long vx, vy;   // row length and number of rows per plane
 };
 
+struct CdfC {
+  double ALPHA, BETA, GAMMA, DELTA, EPSILON, INV_EPSILON;
+};
+
+// Unordered append list of PWE outliers found by a batch: key = chunk << 32 | position in chunk.
+struct OutlierSink {
+  unsigned long long* total;   // entries appended so far (may exceed cap: the caller retries)
+  unsigned* per_chunk;         // entries per chunk
+  unsigned long long* key;
+  double* err;
+  unsigned long long cap;
+};
+__device__ __forceinline__ void outlier_append(const OutlierSink& s, unsigned chunk, unsigned long long pos,
+                                               double err)
+{
+  atomicAdd(&s.per_chunk[chunk], 1u);
+  const unsigned long long slot = atomicAdd(s.total, 1ull);
+  if (slot < s.cap) {
+    s.key[slot] = ((unsigned long long)chunk << 32) | pos;
+    s.err[slot] = err;
+  }
+}
+
+// Outlier correctors of a batch being decoded, sorted by key (chunk << 32 | position); chunk c's
+// entries are [off[c], off[c + 1]). key == nullptr: no chunk has correctors.
+struct CorrectorList {
+  const unsigned long long* key;
+  const double* val;
+  const unsigned long long* off;
+};
+__device__ __forceinline__ double corrector_lookup(const CorrectorList& l, unsigned chunk, unsigned long long pos)
+{
+  const unsigned long long want = ((unsigned long long)chunk << 32) | pos;
+  unsigned long long lo = l.off[chunk], hi = l.off[chunk + 1];
+  while (lo < hi) {
+    const unsigned long long mid = (lo + hi) >> 1;
+    const unsigned long long k = l.key[mid];
+    if (k == want)
+      return l.val[mid];
+    if (k < want)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return 0.0;
+}
+
+// ---- dwt_fused.cu: one HBM round trip per level, dyadic chunks only ----
+size_t fused_scratch_elems(uint32_t nx, uint32_t ny, uint32_t nz, long long off[8]);
+void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const int* d_ids, int nids,
+                              uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st);
+void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chunks, const int* d_ids,
+                              int nids, uint32_t nx, uint32_t ny, uint32_t nz, double tol,
+                              const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st);
+CdfC cdf_constants();
+
 // ---- transform.cu ----
 void launch_stats(const SrcVol& src, ChunkDev* d_chunks, int nchunks, double* d_stride_mean,
                   int max_strides, const unsigned* d_nstrides, unsigned* d_not_const,

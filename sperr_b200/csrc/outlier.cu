@@ -136,6 +136,91 @@ void OutlierCoder::detect(const SrcVol& src, const ChunkDev* d_chunks, int nchun
   }
 }
 
+// ---- detection through an unordered append list (fused inverse transform + k_outlier_append) ----
+
+// Outliers of the chunks that are NOT handled by the fused inverse transform (their reconstruction
+// sits in coef after the in-place inverse transform).
+__global__ void k_outlier_append(SrcVol src, const ChunkDev* chunks, double tol, OutlierSink sink)
+{
+  const unsigned c = blockIdx.y;
+  const ChunkDev& ch = chunks[c];
+  if (ch.is_const || ch.fused)
+    return;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < ch.n;
+       e += (unsigned long long)gridDim.x * blockDim.x) {
+    const double d = out_diff(src, ch, e);
+    if (fabs(d) > tol)
+      outlier_append(sink, c, e, d);
+  }
+}
+
+__global__ void k_outlier_split(const unsigned long long* key, unsigned* opos, unsigned long long n)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    opos[i] = unsigned(key[i] & 0xffffffffull);
+}
+
+OutlierSink OutlierCoder::begin_detect(int nchunks, size_t total_values, cudaStream_t st)
+{
+  if (sink_cap_ == 0)
+    sink_cap_ = std::max<size_t>(size_t(1) << 16, total_values / 64);
+  skey_[0].reserve(sink_cap_ * 8);
+  serr_[0].reserve(sink_cap_ * 8);
+  scount_.reserve(8 + size_t(nchunks) * 4);
+  rt::dset(scount_.p, 0, 8 + size_t(nchunks) * 4, st);
+  OutlierSink s;
+  s.total = scount_.as<unsigned long long>();
+  s.per_chunk = reinterpret_cast<unsigned*>(scount_.as<unsigned char>() + 8);
+  s.key = skey_[0].as<unsigned long long>();
+  s.err = serr_[0].as<double>();
+  s.cap = sink_cap_;
+  return s;
+}
+
+void OutlierCoder::append_unfused(const SrcVol& src, const ChunkDev* d_chunks, int nchunks, size_t max_n,
+                                  double tol, const OutlierSink& sink, cudaStream_t st)
+{
+  const unsigned gx = unsigned(std::min<size_t>((max_n + 255) / 256, 2048));
+  LAUNCH(k_outlier_append, dim3(gx, nchunks), dim3(256), 0, st, src, d_chunks, tol, sink);
+}
+
+bool OutlierCoder::end_detect(int nchunks, cudaStream_t st)
+{
+  std::vector<unsigned char> h(8 + size_t(nchunks) * 4);
+  rt::d2h(h.data(), scount_.p, h.size(), st);
+  rt::sync(st);
+  unsigned long long total;
+  std::memcpy(&total, h.data(), 8);
+  if (total > sink_cap_) {   // the list was too short: the caller repeats the detection
+    sink_cap_ = size_t(total) + size_t(total) / 8 + 1024;
+    return false;
+  }
+  ooff.assign(nchunks + 1, 0);
+  for (int c = 0; c < nchunks; c++) {
+    unsigned n;
+    std::memcpy(&n, h.data() + 8 + size_t(c) * 4, 4);
+    ooff[c + 1] = ooff[c] + n;
+  }
+  opos_.reserve((size_t(total) + 1) * 4);
+  oerr_.reserve((size_t(total) + 1) * 8);
+  if (total == 0)
+    return true;
+  // raster order inside every chunk, chunks in order: sort by (chunk << 32 | position)
+  skey_[1].reserve(sink_cap_ * 8);
+  const size_t tb = sort_tmp_bytes(size_t(total));
+  sort_tmp_.reserve(tb);
+  int bits = 33;
+  while ((1ll << (bits - 32)) < nchunks)
+    bits++;
+  sort_pairs_u64(skey_[0].as<unsigned long long>(), skey_[1].as<unsigned long long>(),
+                 serr_[0].as<unsigned long long>(), oerr_.as<unsigned long long>(), size_t(total), bits,
+                 sort_tmp_.p, tb, st);
+  LAUNCH(k_outlier_split, dim3(unsigned((total + 255) / 256)), dim3(256), 0, st,
+         skey_[1].as<unsigned long long>(), opos_.as<unsigned>(), total);
+  return true;
+}
+
 void OutlierCoder::set_outliers(const std::vector<unsigned long long>& offsets, const unsigned* h_pos,
                                 const double* h_err, cudaStream_t st)
 {

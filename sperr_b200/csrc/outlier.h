@@ -12,6 +12,14 @@ class OutlierCoder {
   // the concatenated device arrays).
   void detect(const SrcVol& src, const ChunkDev* d_chunks, int nchunks, size_t max_n, double tol,
               cudaStream_t st);
+  // The same through an unordered append list that several kernels may feed (the fused inverse
+  // transform records outliers while it rebuilds the values): begin_detect -> producers ->
+  // end_detect. end_detect returns false when the list overflowed; the caller then repeats from
+  // begin_detect (the list has been enlarged).
+  OutlierSink begin_detect(int nchunks, size_t total_values, cudaStream_t st);
+  void append_unfused(const SrcVol& src, const ChunkDev* d_chunks, int nchunks, size_t max_n, double tol,
+                      const OutlierSink& sink, cudaStream_t st);
+  bool end_detect(int nchunks, cudaStream_t st);
   // Alternative input for the stage-level test hook.
   void set_outliers(const std::vector<unsigned long long>& offsets, const unsigned* h_pos,
                     const double* h_err, cudaStream_t st);
@@ -24,7 +32,9 @@ class OutlierCoder {
 
  private:
   rt::DBuf cnt_, offs_, scan_tmp_, pick_, opos_, oerr_, meta_, omag_, osign_, nodes_, small_,
-      pkeys_[2], pvals_[2], sort_tmp_, ppleaf_, pcmap_, pmag_, psigns_, first_, ochunks_;
+      pkeys_[2], pvals_[2], sort_tmp_, ppleaf_, pcmap_, pmag_, psigns_, first_, ochunks_, skey_[2],
+      serr_[1], scount_;
+  size_t sink_cap_ = 0;
   EncWork work_;
 };
 

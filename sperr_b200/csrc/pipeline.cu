@@ -168,7 +168,13 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     launch_stats(src, b_.dev(), nc, stride_mean_.as<double>(), max_strides, nstrides_.as<unsigned>(),
                  not_const_.as<unsigned>(), mode == kModePSNR, st);
   }
-  {
+  bool any_unfused = false, any_fused = false;
+  size_t total_values = 0;
+  for (auto& d : b_.h) {
+    (d.fused ? any_fused : any_unfused) = true;
+    total_values += d.n;
+  }
+  if (any_unfused) {
     rt::ProfScope ps("c.gather", st);
     launch_gather(src, b_.dev(), nc, b_.max_n, st);
   }
@@ -186,18 +192,29 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   ids_.reserve(flat.size() * 4 + 4);
   rt::h2d(ids_.p, flat.data(), flat.size() * 4, st);
   rt::sync(st);
-  auto transform = [&](bool inverse) {
+  // dyadic shapes: fused kernels (dwt_fused.cu) that read the volume themselves and track the
+  // coefficient maximum; everything else: gather, per-axis passes in place, separate maximum
+  auto group_fused = [&](size_t s) { return b_.h[groups[s][0]].fused != 0; };
+  auto transform = [&](bool inverse, bool fused_groups, const OutlierSink& sink) {
     rt::ProfScope ps(inverse ? "c.idwt" : "c.dwt", st);
     for (size_t s = 0; s < groups.size(); s++) {
-      if (groups[s].empty())
+      if (groups[s].empty() || group_fused(s) != fused_groups)
         continue;
       const ShapeHeader& h = b_.shapes[s].h;
-      launch_dwt(inverse, b_.dev(), ids_.as<int>() + goff[s], int(groups[s].size()), h.nx, h.ny, h.nz,
-                 is_2d, st);
+      const int* ids = ids_.as<int>() + goff[s];
+      const int n = int(groups[s].size());
+      if (!fused_groups)
+        launch_dwt(inverse, b_.dev(), ids, n, h.nx, h.ny, h.nz, is_2d, st);
+      else if (!inverse)
+        launch_dwt_fused_forward(src, b_.dev(), ids, n, h.nx, h.ny, h.nz, st);
+      else   // PWE: rebuild the values, compare with the source, record the outliers
+        launch_dwt_fused_inverse(src, 2, b_.dev(), ids, n, h.nx, h.ny, h.nz, quality, sink,
+                                 CorrectorList{nullptr, nullptr, nullptr}, st);
     }
   };
-  transform(false);
-  {
+  transform(false, true, OutlierSink{});
+  if (any_unfused) {
+    transform(false, false, OutlierSink{});
     rt::ProfScope ps("c.absmax", st);
     launch_absmax(b_.dev(), nc, b_.max_n, st);
   }
@@ -290,10 +307,18 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
         rt::ProfScope ps("c.inv_quantize", st);
         launch_inv_quantize(b_.dev(), nc, b_.max_n, st);
       }
-      transform(true);
-      {
-        rt::ProfScope ps("c.outlier_detect", st);
-        out_.detect(src, b_.dev(), nc, b_.max_n, quality, st);
+      if (any_unfused)
+        transform(true, false, OutlierSink{});
+      for (;;) {
+        const OutlierSink sink = out_.begin_detect(nc, total_values, st);
+        if (any_fused)
+          transform(true, true, sink);
+        if (any_unfused) {
+          rt::ProfScope ps("c.outlier_detect", st);
+          out_.append_unfused(src, b_.dev(), nc, b_.max_n, quality, sink, st);
+        }
+        if (out_.end_detect(nc, st))
+          break;
       }
       std::vector<unsigned long long> tl(nc);
       for (int c = 0; c < nc; c++)

@@ -50,7 +50,7 @@ class Decompressor {
                  const ChunkStream* cs, const SrcVol& dst, cudaStream_t st);
   BatchBuffers b_;
   DecWork w_;
-  rt::DBuf ids_, lis_off1_, tols_;
+  rt::DBuf ids_, lis_off1_, tols_, obits_, ckey_[2], cval_[2], ccount_, coff_, csort_;
 };
 
 // Largest number of chunks processed at once (bounded by the list-key layout and by memory).

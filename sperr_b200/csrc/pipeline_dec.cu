@@ -232,14 +232,80 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
   {
     rt::ProfScope pq("d.reconstruct", st);
     w_.fill_n = b_.max_n;
-    speck_reconstruct(w_, b_.dev(), 0, nullptr, 0, nc, st);
+    speck_reconstruct(w_, b_.dev(), 0, nullptr, 0, nc, OutlierSink{}, st);
+  }
+
+  // ---- outlier correctors: sorted (chunk, position) list + one flag bit per value ----
+  CorrectorList cor{nullptr, nullptr, nullptr};
+  unsigned long long ncor = 0;
+  if (any_out) {
+    rt::ProfScope po("d.outliers", st);
+    size_t words = 0, cap = 16;
+    for (int c = 0; c < nc; c++) {
+      words += (b_.h[c].n + 31) / 32 + 1;
+      cap += size_t(ps[c].ototal / 2 + 1);   // a corrector costs at least a significance + a sign bit
+    }
+    obits_.reserve(words * 4);
+    rt::dset(obits_.p, 0, words * 4, st);
+    size_t wo = 0;
+    for (int c = 0; c < nc; c++) {
+      b_.h[c].obits = obits_.as<uint32_t>() + wo;
+      wo += (b_.h[c].n + 31) / 32 + 1;
+    }
+    b_.push(st);
+    ckey_[0].reserve(cap * 8);
+    ckey_[1].reserve(cap * 8);
+    cval_[0].reserve(cap * 8);
+    cval_[1].reserve(cap * 8);
+    ccount_.reserve(8 + size_t(nc + 1) * 8);
+    rt::dset(ccount_.p, 0, 8 + size_t(nc + 1) * 8, st);
+    OutlierSink sink;
+    sink.total = ccount_.as<unsigned long long>();
+    sink.per_chunk = reinterpret_cast<unsigned*>(ccount_.as<unsigned char>() + 8);
+    sink.key = ckey_[0].as<unsigned long long>();
+    sink.err = cval_[0].as<double>();
+    sink.cap = cap;
+    w_.fill_n = 0;
+    speck_reconstruct(w_, b_.dev(), 1, tols_.as<double>(), nc, nc, sink, st);
+    std::vector<unsigned char> hc(8 + size_t(nc) * 4);
+    rt::d2h(hc.data(), ccount_.p, hc.size(), st);
+    rt::sync(st);
+    std::memcpy(&ncor, hc.data(), 8);
+    if (ncor > cap)
+      throw std::runtime_error("outlier corrector list overflow");
+    if (ncor) {
+      std::vector<unsigned long long> off(nc + 1, 0);
+      for (int c = 0; c < nc; c++) {
+        unsigned n;
+        std::memcpy(&n, hc.data() + 8 + size_t(c) * 4, 4);
+        off[c + 1] = off[c] + n;
+      }
+      coff_.reserve((nc + 1) * 8);
+      rt::h2d(coff_.p, off.data(), (nc + 1) * 8, st);
+      const size_t tb = sort_tmp_bytes(size_t(ncor));
+      csort_.reserve(tb);
+      int bits = 33;
+      while ((1ll << (bits - 32)) < nc)
+        bits++;
+      sort_pairs_u64(ckey_[0].as<unsigned long long>(), ckey_[1].as<unsigned long long>(),
+                     cval_[0].as<unsigned long long>(), cval_[1].as<unsigned long long>(), size_t(ncor), bits,
+                     csort_.p, tb, st);
+      rt::sync(st);   // `off` leaves scope
+      cor.key = ckey_[1].as<unsigned long long>();
+      cor.val = cval_[1].as<double>();
+      cor.off = coff_.as<unsigned long long>();
+    }
   }
 
   // ---- inverse transform ----
   std::vector<std::vector<int>> groups(b_.shapes.size());
-  for (int c = 0; c < nc; c++)
+  bool any_unfused = false;
+  for (int c = 0; c < nc; c++) {
     if (!ps[c].is_const)
       groups[b_.h[c].shape].push_back(c);
+    if (ps[c].is_const || !b_.h[c].fused)
+      any_unfused = true;
+  }
   std::vector<int> flat;
   std::vector<size_t> goff;
   for (auto& g : groups) {
@@ -255,21 +321,20 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
       if (groups[s].empty())
         continue;
       const ShapeHeader& h = b_.shapes[s].h;
-      launch_dwt(true, b_.dev(), ids_.as<int>() + goff[s], int(groups[s].size()), h.nx, h.ny, h.nz,
-                 false, st);
+      const int* ids = ids_.as<int>() + goff[s];
+      if (b_.h[groups[s][0]].fused)   // corrector, mean, conversion and scatter fused into level 0
+        launch_dwt_fused_inverse(dst, 1, b_.dev(), ids, int(groups[s].size()), h.nx, h.ny, h.nz, 0.0,
+                                 OutlierSink{}, cor, st);
+      else
+        launch_dwt(true, b_.dev(), ids, int(groups[s].size()), h.nx, h.ny, h.nz, false, st);
     }
   }
 
-  // ---- outlier correction ----
-  if (any_out) {
-    rt::ProfScope po("d.outliers", st);
-    w_.fill_n = 0;
-    speck_reconstruct(w_, b_.dev(), 1, tols_.as<double>(), nc, nc, st);
-  }
-
-  // ---- add the mean back, convert and scatter into the output volume ----
-  {
+  // ---- the other chunks: correctors, mean, conversion, scatter; constant chunks: fill ----
+  if (any_unfused) {
     rt::ProfScope psc("d.scatter", st);
+    if (ncor)
+      launch_apply_correctors(b_.dev(), cor.key, cor.val, ncor, st);
     launch_scatter_out(dst, b_.dev(), nc, b_.max_n, st);
   }
   rt::sync(st);

@@ -88,11 +88,14 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
 // Rebuilds the magnitudes from the decoded state of speck*_decode and
 //   mode 0: writes the de-quantised coefficients q * mag * sign to chunks[c].coef
 //           (SPECK_FLT::m_midtread_inv_quantize, /root/reference/src/SPECK_FLT.cpp:373-399);
-//   mode 1: treats them as outlier correctors and adds them to chunks[c].coef with tolerance
-//           tols[c] (Outlier_Coder::m_inverse_quantize, src/Outlier_Coder.cpp:206-234;
-//           src/SPECK_FLT.cpp:576-585).
+//   mode 1: treats them as outlier correctors with tolerance tols[c] (Outlier_Coder::
+//           m_inverse_quantize, src/Outlier_Coder.cpp:206-234): appends (chunk << 32 | position,
+//           corrector) to `sink` and sets the value's bit in chunks[c].obits. The consumers add the
+//           corrector before the mean (src/SPECK_FLT.cpp:576-585).
 // Works on jobs [first, first + count) of the last speck_decode; job first + c belongs to chunks[c].
 void speck_reconstruct(DecWork& w, const ChunkDev* d_chunks, int mode, const double* d_tols,
-                       int first, int count, cudaStream_t st);
+                       int first, int count, const OutlierSink& sink, cudaStream_t st);
+void launch_apply_correctors(const ChunkDev* d_chunks, const unsigned long long* d_key,
+                             const double* d_val, unsigned long long n, cudaStream_t st);
 
 }  // namespace sperr_b200

@@ -99,7 +99,7 @@ __global__ void k_rec_scan(const DecChunk* jobs, unsigned* counts, int maxp, uns
 }
 
 __global__ void k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const unsigned* counts,
-                            int maxp, unsigned nblk, int mode, const double* tols)
+                            int maxp, unsigned nblk, int mode, const double* tols, OutlierSink sink)
 {
   __shared__ unsigned s_cnt[kMaxPlanes][32];   // per plane: significant-before-n count of every warp
   __shared__ int s_max;
@@ -160,21 +160,50 @@ __global__ void k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const 
       }
     }
   }
-  if (i >= d.n)
-    return;
+  const bool in = i < d.n;
   const bool neg = p >= 0 && (v & 0x80u);
   if (mode == 0) {
-    ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, __ull2double_rn(mag)), neg ? -1.0 : 1.0);
+    if (in)
+      ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, __ull2double_rn(mag)), neg ? -1.0 : 1.0);
   }
-  else if (p >= 0 && mag != 0) {
-    double e = mag == 1 ? 1.1 : __dsub_rn(__ull2double_rn(mag), 0.25);
-    e = __dmul_rn(e, __dmul_rn(tols[c], neg ? -1.0 : 1.0));
-    ch.coef[i] = __dadd_rn(ch.coef[i], e);
+  else {
+    // outlier correctors: a sorted list for the consumers plus one flag bit per value
+    const bool has = in && p >= 0 && mag != 0;
+    const unsigned b = __ballot_sync(0xffffffffu, has);
+    if (lane == 0 && in)
+      ch.obits[i >> 5] = b;
+    if (has) {
+      double e = mag == 1 ? 1.1 : __dsub_rn(__ull2double_rn(mag), 0.25);
+      e = __dmul_rn(e, __dmul_rn(tols[c], neg ? -1.0 : 1.0));
+      outlier_append(sink, c, i, e);
+    }
   }
 }
 
+// coef[pos] += corrector for the chunks that are not handled by the fused inverse transform
+__global__ void k_apply_correctors(const ChunkDev* chunks, const unsigned long long* key,
+                                   const double* val, unsigned long long n)
+{
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const unsigned long long k = key[i];
+  const ChunkDev& ch = chunks[unsigned(k >> 32)];
+  if (ch.fused)
+    return;
+  const unsigned long long pos = k & 0xffffffffull;
+  ch.coef[pos] = __dadd_rn(ch.coef[pos], val[i]);
+}
+
+void launch_apply_correctors(const ChunkDev* d_chunks, const unsigned long long* d_key,
+                             const double* d_val, unsigned long long n, cudaStream_t st)
+{
+  if (n)
+    LAUNCH(k_apply_correctors, dim3(unsigned((n + 255) / 256)), dim3(256), 0, st, d_chunks, d_key, d_val, n);
+}
+
 void speck_reconstruct(DecWork& w, const ChunkDev* d_chunks, int mode, const double* d_tols,
-                       int first, int count, cudaStream_t st)
+                       int first, int count, const OutlierSink& sink, cudaStream_t st)
 {
   const int nj = count;
   if (nj == 0)
@@ -196,7 +225,8 @@ void speck_reconstruct(DecWork& w, const ChunkDev* d_chunks, int mode, const dou
     LAUNCH(k_rec_count, dim3(nblk, nj), dim3(kRecBlock), 0, st, dj, cnt, maxp, nblk);
     LAUNCH(k_rec_scan, dim3(maxp, nj), dim3(1024), 0, st, dj, cnt, maxp, nblk);
   }
-  LAUNCH(k_rec_apply, dim3(nblk, nj), dim3(kRecBlock), 0, st, dj, d_chunks, cnt, maxp, nblk, mode, d_tols);
+  LAUNCH(k_rec_apply, dim3(nblk, nj), dim3(kRecBlock), 0, st, dj, d_chunks, cnt, maxp, nblk, mode, d_tols,
+         sink);
 }
 
 }  // namespace sperr_b200

@@ -107,7 +107,7 @@ __global__ void k_mean_finish(ChunkDev* chunks, const double* stride_mean, int m
 __global__ void k_gather_sub(SrcVol src, const ChunkDev* chunks)
 {
   const ChunkDev& ch = chunks[blockIdx.y];
-  if (ch.is_const)
+  if (ch.is_const || ch.fused)   // fused chunks are read straight from the volume by k_fwd3d
     return;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   const double mean = ch.mean;
@@ -124,10 +124,6 @@ __global__ void k_gather_sub(SrcVol src, const ChunkDev* chunks)
 // lifting steps on a line held in shared memory as evens (el) followed by odds (ol).
 // `get/put` index the line; `tid/nthr` enumerate the cooperating threads; `sync` separates steps.
 // ---------------------------------------------------------------------------------------------
-
-struct CdfC {
-  double ALPHA, BETA, GAMMA, DELTA, EPSILON, INV_EPSILON;
-};
 
 template <typename Line, typename Sync>
 __device__ __forceinline__ void lift_forward(const CdfC& k, Line L, int len, int tid, int nthr,
@@ -297,7 +293,7 @@ __global__ void k_dwt_col(const ChunkDev* chunks, const int* ids, CdfC k, int ax
 __global__ void k_absmax(ChunkDev* chunks)
 {
   ChunkDev& ch = chunks[blockIdx.y];
-  if (ch.is_const)
+  if (ch.is_const || ch.fused)   // k_fwd3d tracks the maximum itself
     return;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   unsigned long long m = 0;
@@ -421,6 +417,8 @@ __global__ void k_mse_finish(const ChunkDev* chunks, const int* ids, const doubl
 __global__ void k_scatter_out(SrcVol dst, const ChunkDev* chunks)
 {
   const ChunkDev& ch = chunks[blockIdx.y];
+  if (ch.fused && !ch.is_const)   // written by the fused inverse transform
+    return;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < ch.n;
        e += stride) {
@@ -440,7 +438,7 @@ __global__ void k_scatter_out(SrcVol dst, const ChunkDev* chunks)
 // host launchers
 // ---------------------------------------------------------------------------------------------
 
-static CdfC cdf_constants()
+CdfC cdf_constants()
 {
   // Same expressions as include/CDF97.h:136-147, evaluated in plain IEEE double arithmetic
   // (volatile blocks compile-time contraction or reassociation).

@@ -55,6 +55,14 @@ class Lib:
         assert rc == 0
         return buf
 
+    def stage_dwt_fused(self, vals, dims, inverse=False):
+        buf = np.ascontiguousarray(vals, dtype=np.float64).copy()
+        f = self.lib.sperr_b200_stage_dwt_fused
+        f.restype = C.c_int
+        f.argtypes = [vp, sz, sz, sz, C.c_int]
+        rc = f(_ptr(buf), *dims, int(inverse))
+        return rc, buf
+
     def stage_quantize(self, vals, dims, q):
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         mags = np.zeros(vals.size, dtype=np.uint64)
