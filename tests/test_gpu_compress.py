@@ -58,3 +58,17 @@ def test_stage_dwt_bits(lib, oracle):
         a2 = lib.stage_dwt(a, dims, inverse=True)
         b2 = oracle.dwt3d(b, dims, inverse=True)
         assert np.array_equal(a2.view(np.uint64), b2.view(np.uint64)), dims
+
+
+def test_stage_dwt_fused_bits(lib, oracle):
+    # the one-round-trip-per-level kernels (dyadic shapes): bit-identical coefficients both ways
+    rng = np.random.default_rng(4)
+    for dims in ((91, 91, 91), (256, 256, 256), (40, 24, 17), (128, 128, 128), (300, 280, 290)):
+        v = rng.standard_normal(dims[0] * dims[1] * dims[2])
+        rc, a = lib.stage_dwt_fused(v, dims)
+        assert rc == 0, (dims, rc)
+        b = oracle.dwt3d(v, dims)
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), dims
+        rc, a2 = lib.stage_dwt_fused(b, dims, inverse=True)
+        b2 = oracle.dwt3d(b, dims, inverse=True)
+        assert rc == 0 and np.array_equal(a2.view(np.uint64), b2.view(np.uint64)), dims
