@@ -77,31 +77,55 @@ __device__ __forceinline__ void inv_step(const CdfC& k, InvState& s, double e, d
 // In-place lifting of one line of kFNP pairs in shared memory (element i at p[i * stride]); on
 // return pairs 2 .. kFNP-3 hold the transformed values (forward: e, o interleaved as they came;
 // inverse: reconstructed samples), the outer ones are scratch.
+// The four lifting stages are skewed by one iteration each (stage s of iteration j works on what
+// stage s-1 produced in iteration j-1), so the stages of one iteration are independent instruction
+// chains: same operations on the same operands as fwd_step / inv_step, more ILP per thread.
 template <bool INVERSE>
 __device__ __forceinline__ void lift_line(const CdfC& k, double* p, int stride)
 {
   if (!INVERSE) {
-    FwdState s = {0.0, 0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-    for (int j = 0; j < kFNP; j++) {
-      double a, b;
-      fwd_step(k, s, p[(2 * j) * stride], p[(2 * j + 1) * stride], a, b);
-      if (j >= 4) {
-        p[(2 * j - 4) * stride] = a;
-        p[(2 * j - 3) * stride] = b;
+    double eA = 0.0, oA = 0.0, eB = 0.0;            // e[j-1], o[j-1], e[j-2]
+    double p1 = 0.0, p2 = 0.0, p3 = 0.0;            // o1[j-2], o1[j-3], o1[j-4]
+    double q1 = 0.0, q2 = 0.0, q3 = 0.0;            // e1[j-3], e1[j-4], e1[j-5]
+    double r1 = 0.0, r2 = 0.0;                      // o2[j-5], o2[j-6]
+#pragma unroll
+    for (int j = 0; j < kFNP + 3; j++) {
+      const double e = j < kFNP ? p[(2 * j) * stride] : 0.0;
+      const double o = j < kFNP ? p[(2 * j + 1) * stride] : 0.0;
+      const double n_o1 = __dadd_rn(oA, __dmul_rn(k.ALPHA, __dadd_rn(eA, e)));
+      const double n_e1 = __dadd_rn(eB, __dmul_rn(k.BETA, __dadd_rn(p2, p1)));
+      const double n_o2 = __dadd_rn(p3, __dmul_rn(k.GAMMA, __dadd_rn(q2, q1)));
+      if (j >= 7) {   // pair j - 5
+        p[(2 * j - 10) * stride] = __dmul_rn(k.EPSILON, __dadd_rn(q3, __dmul_rn(k.DELTA, __dadd_rn(r2, r1))));
+        p[(2 * j - 9) * stride] = __dmul_rn(r1, -k.INV_EPSILON);
       }
+      eB = eA; eA = e; oA = o;
+      p3 = p2; p2 = p1; p1 = n_o1;
+      q3 = q2; q2 = q1; q1 = n_e1;
+      r2 = r1; r1 = n_o2;
     }
   }
   else {
-    InvState s = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-    for (int j = 0; j < kFNP; j++) {
-      double a, b;
-      inv_step(k, s, p[(2 * j) * stride], p[(2 * j + 1) * stride], a, b);
-      if (j >= 4) {
-        p[(2 * j - 4) * stride] = a;
-        p[(2 * j - 3) * stride] = b;
+    double OP1 = 0.0, OP2 = 0.0;                    // O'[k-1], O'[k-2]
+    double E1a = 0.0, E1b = 0.0, E1c = 0.0;         // E1[k-1], E1[k-2], E1[k-3]
+    double O1a = 0.0, O1b = 0.0, O1c = 0.0;         // O1[k-3], O1[k-4], O1[k-5]
+    double E2a = 0.0, E2b = 0.0;                    // E2[k-4], E2[k-5]
+#pragma unroll
+    for (int j = 0; j < kFNP + 3; j++) {
+      const double e = j < kFNP ? p[(2 * j) * stride] : 0.0;
+      const double o = j < kFNP ? p[(2 * j + 1) * stride] : 0.0;
+      const double opn = __dmul_rn(o, -k.EPSILON);
+      const double e1n = __dsub_rn(__dmul_rn(e, k.INV_EPSILON), __dmul_rn(k.DELTA, __dadd_rn(OP1, opn)));
+      const double o1n = __dsub_rn(OP2, __dmul_rn(k.GAMMA, __dadd_rn(E1b, E1a)));
+      const double e2n = __dsub_rn(E1c, __dmul_rn(k.BETA, __dadd_rn(O1b, O1a)));
+      if (j >= 7) {   // pair j - 5
+        p[(2 * j - 10) * stride] = E2b;
+        p[(2 * j - 9) * stride] = __dsub_rn(O1c, __dmul_rn(k.ALPHA, __dadd_rn(E2b, E2a)));
       }
+      OP2 = OP1; OP1 = opn;
+      E1c = E1b; E1b = E1a; E1a = e1n;
+      O1c = O1b; O1b = O1a; O1a = o1n;
+      E2b = E2a; E2a = e2n;
     }
   }
 }
@@ -122,11 +146,20 @@ struct FusedArgs {
   CdfC k;
 };
 
+constexpr int kNPB = 3;                 // sample pairs (2 planes each) a CTA transforms per step
+constexpr int kPlanes = 2 * kNPB;
+constexpr size_t kFusedSmem = (size_t)kPlanes * kFI * kFP * sizeof(double);
+
+__device__ __forceinline__ unsigned long long abs_bits(double v)
+{
+  return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
+}
+
 // SRC 0: float volume, 1: double volume (both minus the chunk mean), 2: compact fp64 box in scratch
 template <int SRC>
-__global__ void __launch_bounds__(kFThreads, 3) k_fwd3d(FusedArgs a)
+__global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
 {
-  __shared__ double tile[2][kFI][kFP];
+  DYN_SMEM(double, tile);   // [kPlanes][kFI][kFP]
   __shared__ unsigned long long s_max;
   const ChunkDev& ch = a.chunks[a.ids[blockIdx.y]];
   if (ch.is_const)
@@ -164,75 +197,100 @@ __global__ void __launch_bounds__(kFThreads, 3) k_fwd3d(FusedArgs a)
   }
   const unsigned long long plane = SRC == 2 ? (unsigned long long)lx * ly : a.vol.vx * a.vol.vy;
   const double* sbox = SRC == 2 ? ch.scratch + a.src_off : nullptr;
+  const float* vf = reinterpret_cast<const float*>(a.vol.ptr);
+  const double* vd = reinterpret_cast<const double*>(a.vol.ptr);
 
-  FwdState st[4];
-  for (int c = 0; c < 4; c++)
-    st[c] = FwdState{0.0, 0.0, 0.0, 0.0, 0.0};
-  unsigned long long vmax = 0;
+  // the 4 (x, y) columns whose z lifting this thread runs, and where their outputs go
   const size_t cnx = ch.nx, cnxy = (size_t)ch.nx * ch.ny;
+  const int x = X0 + lane;
+  const int xo = (x >> 1) + ((x & 1) ? ax : 0);
+  FwdState st[4];
+  size_t dpos[4];      // offset of the column inside a z plane of coef (de-interleaved position)
+  long long apos[4];   // approx columns (x, y even): offset inside a z plane of the approx box; else -1
+  bool live[4];
+  for (int c = 0; c < 4; c++) {
+    st[c] = FwdState{0.0, 0.0, 0.0, 0.0, 0.0};
+    const int y = Y0 + warp + 8 * c;
+    live[c] = x < lx && y < ly;
+    dpos[c] = (size_t)((y >> 1) + ((y & 1) ? ay : 0)) * cnx + xo;
+    apos[c] = ((x | y) & 1) ? -1ll
+                            : (a.apx_off >= 0 ? (long long)(y >> 1) * ax + (x >> 1) : (long long)dpos[c]);
+  }
+  double* const abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : ch.coef;
+  const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
+  unsigned long long vmax = 0;
 
-  for (int j = k0 - 2; j <= k1 + 1; j++) {
-    // ---- load planes 2j and 2j + 1 (mirrored) ----
-    for (int p = 0; p < 2; p++) {
-      const int gz = mirror(2 * j + p, lz);
+  for (int j0 = k0 - 2; j0 <= k1 + 1; j0 += kNPB) {
+    // ---- load planes 2 j0 .. 2 j0 + kPlanes - 1 (mirrored) ----
+    for (int p = 0; p < kPlanes; p++) {
+      const int gz = mirror(2 * j0 + p, lz);
       const unsigned long long zoff = (SRC == 2 ? (unsigned long long)gz : (unsigned long long)(ch.z0 + gz)) * plane;
+      double* const tp = tile + (size_t)p * kFI * kFP;
+#ifndef SPERR_EMUL
+      if (SRC != 2 && j0 + kNPB <= k1 + 1) {
+        // the planes of the next step: pull them into L2 now, their loads then see L2 latency
+        const int gz2 = mirror(2 * (j0 + kNPB) + p, lz);
+        const unsigned long long zoff2 = (unsigned long long)(ch.z0 + gz2) * plane;
+#pragma unroll
+        for (int s = 0; s < kPer - 1; s++) {
+          const void* ptr = SRC == 0 ? (const void*)(vf + zoff2 + goff[s]) : (const void*)(vd + zoff2 + goff[s]);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        }
+      }
+#endif
+#pragma unroll
       for (int s = 0; s < kPer; s++) {
-        const int idx = tid + s * kFThreads;
-        if (idx < kFI * kFI) {
+        if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
           double v;
           if (SRC == 0)
-            v = __dsub_rn(double(reinterpret_cast<const float*>(a.vol.ptr)[zoff + goff[s]]), mean);
+            v = __dsub_rn(double(__ldg(vf + zoff + goff[s])), mean);
           else if (SRC == 1)
-            v = __dsub_rn(reinterpret_cast<const double*>(a.vol.ptr)[zoff + goff[s]], mean);
+            v = __dsub_rn(__ldg(vd + zoff + goff[s]), mean);
           else
             v = sbox[zoff + goff[s]];
-          (&tile[p][0][0])[sidx[s]] = v;
+          tp[sidx[s]] = v;
         }
       }
     }
     __syncthreads();
-    // ---- rows (x) ----
-    if (tid < 2 * kFI)
-      lift_line<false>(k, &tile[tid / kFI][tid % kFI][0], 1);
+    // ---- rows (x): kPlanes * 40 lines ----
+    if (tid < kPlanes * kFI)
+      lift_line<false>(k, tile + (size_t)(tid / kFI) * kFI * kFP + (tid % kFI) * kFP, 1);
     __syncthreads();
     // ---- columns (y), only the x positions that are valid after the row pass ----
-    if (tid < 2 * kFT)
-      lift_line<false>(k, &tile[tid / kFT][0][kFH + tid % kFT], kFP);
+    if (tid < kPlanes * kFT)
+      lift_line<false>(k, tile + (size_t)(tid / kFT) * kFI * kFP + kFH + tid % kFT, kFP);
     __syncthreads();
-    // ---- z: streaming state in registers, 4 (x, y) columns per thread ----
-    const int kk = j - 2;   // output pair index
-    const bool emit = kk >= k0 && kk < k1;
-    const int x = X0 + lane;
-    const int px = x & 1;
-    const int xo = (x >> 1) + (px ? ax : 0);
-    for (int c = 0; c < 4; c++) {
-      const int ry = warp + 8 * c;
-      double e2, o3;
-      fwd_step(k, st[c], tile[0][kFH + ry][kFH + lane], tile[1][kFH + ry][kFH + lane], e2, o3);
-      const int y = Y0 + ry;
-      if (emit && x < lx && y < ly) {
-        const int py = y & 1;
-        const int yo = (y >> 1) + (py ? ay : 0);
-        // even z output (plane kk of the low band)
-        if (px == 0 && py == 0) {   // approx band of this level
-          if (a.apx_off >= 0)
-            ch.scratch[a.apx_off + ((size_t)kk * ay + (y >> 1)) * ax + (x >> 1)] = e2;
-          else
-            ch.coef[(size_t)kk * cnxy + (size_t)(y >> 1) * cnx + (x >> 1)] = e2;
-          if (a.last) {
-            const unsigned long long b = (unsigned long long)__double_as_longlong(e2) & 0x7fffffffffffffffull;
+    // ---- z: streaming state in registers, 4 (x, y) columns per thread, kNPB pairs in order ----
+#pragma unroll
+    for (int q = 0; q < kNPB; q++) {
+      const int kk = j0 + q - 2;   // output pair index
+      const bool emit = kk >= k0 && kk < k1;
+      const double* const te = tile + (size_t)(2 * q) * kFI * kFP + kFH * kFP + kFH + lane;
+      const double* const to = te + kFI * kFP;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int ry = warp + 8 * c;
+        double e2, o3;
+        fwd_step(k, st[c], te[ry * kFP], to[ry * kFP], e2, o3);
+        if (emit && live[c]) {
+          if (apos[c] >= 0) {   // approx band of this level (plane kk of the low band)
+            abox[(size_t)kk * aplane + apos[c]] = e2;
+            if (a.last) {
+              const unsigned long long b = abs_bits(e2);
+              vmax = b > vmax ? b : vmax;
+            }
+          }
+          else {
+            ch.coef[(size_t)kk * cnxy + dpos[c]] = e2;
+            const unsigned long long b = abs_bits(e2);
             vmax = b > vmax ? b : vmax;
           }
-        }
-        else {
-          ch.coef[(size_t)kk * cnxy + (size_t)yo * cnx + xo] = e2;
-          const unsigned long long b = (unsigned long long)__double_as_longlong(e2) & 0x7fffffffffffffffull;
-          vmax = b > vmax ? b : vmax;
-        }
-        if (kk < lz / 2) {   // odd z output (plane az + kk)
-          ch.coef[(size_t)(az + kk) * cnxy + (size_t)yo * cnx + xo] = o3;
-          const unsigned long long b = (unsigned long long)__double_as_longlong(o3) & 0x7fffffffffffffffull;
-          vmax = b > vmax ? b : vmax;
+          if (kk < lz / 2) {   // odd z output (plane az + kk)
+            ch.coef[(size_t)(az + kk) * cnxy + dpos[c]] = o3;
+            const unsigned long long b = abs_bits(o3);
+            vmax = b > vmax ? b : vmax;
+          }
         }
       }
     }
@@ -255,7 +313,7 @@ __global__ void __launch_bounds__(kFThreads, 3) k_fwd3d(FusedArgs a)
 template <int OUT>
 __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
 {
-  __shared__ double tile[2][kFI][kFP];
+  DYN_SMEM(double, tile);   // [kPlanes][kFI][kFP]
   const ChunkDev& ch = a.chunks[a.ids[blockIdx.y]];
   if (ch.is_const)
     return;
@@ -276,8 +334,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
 
   // the (x, y) columns this thread runs the z lifting for: tile elements tid, tid + 256, ...
   constexpr int kPer = (kFI * kFI + kFThreads - 1) / kFThreads;   // 7
-  unsigned long long coff[kPer];   // offset inside a z plane of coef
-  long long aoff[kPer];            // offset inside a z plane of the approx box, or -1: not approx in (x, y)
+  unsigned coff[kPer];     // offset inside a z plane of coef (chunks hold < 2^31 values)
+  int aoff[kPer];          // offset inside a z plane of the approx box, or -1: not approx in (x, y)
   InvState st[kPer];
   unsigned short sidx[kPer];
   for (int s = 0; s < kPer; s++) {
@@ -287,75 +345,86 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     sidx[s] = (unsigned short)(ty * kFP + tx);
     const int gx = mirror(X0 - kFH + tx, lx), gy = mirror(Y0 - kFH + ty, ly);
     const int xo = (gx >> 1) + ((gx & 1) ? ax : 0), yo = (gy >> 1) + ((gy & 1) ? ay : 0);
-    coff[s] = (unsigned long long)yo * cnx + xo;
-    aoff[s] = ((gx | gy) & 1) ? -1ll
-                              : (a.apx_off >= 0 ? (long long)(gy >> 1) * ax + (gx >> 1)
-                                                : (long long)((size_t)(gy >> 1) * cnx + (gx >> 1)));
+    coff[s] = unsigned((size_t)yo * cnx + xo);
+    aoff[s] = ((gx | gy) & 1) ? -1
+                              : (a.apx_off >= 0 ? (gy >> 1) * ax + (gx >> 1) : int((size_t)(gy >> 1) * cnx + (gx >> 1)));
   }
   const double* abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : ch.coef;
   const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
 
-  for (int j = k0 - 2; j <= k1 + 1; j++) {
+  for (int j0 = k0 - 2; j0 <= k1 + 1; j0 += kNPB) {
     // ---- z: pair j = (low-band plane mirror(2j) / 2, high-band plane az + mirror(2j + 1) / 2) ----
-    const int ze = mirror(2 * j, lz) >> 1, zo = az + (mirror(2 * j + 1, lz) >> 1);
-    for (int s = 0; s < kPer; s++) {
-      const int idx = tid + s * kFThreads;
-      if (idx < kFI * kFI) {
-        const double e = aoff[s] >= 0 ? abox[(size_t)ze * aplane + aoff[s]] : ch.coef[(size_t)ze * cnxy + coff[s]];
-        const double o = ch.coef[(size_t)zo * cnxy + coff[s]];
-        double x0, x1;
-        inv_step(k, st[s], e, o, x0, x1);
-        (&tile[0][0][0])[sidx[s]] = x0;
-        (&tile[1][0][0])[sidx[s]] = x1;
+#pragma unroll
+    for (int q = 0; q < kNPB; q++) {
+      const int j = j0 + q;
+      const int ze = mirror(2 * j, lz) >> 1, zo = az + (mirror(2 * j + 1, lz) >> 1);
+      const double* const pe = ch.coef + (size_t)ze * cnxy;
+      const double* const po = ch.coef + (size_t)zo * cnxy;
+      const double* const pa = abox + (size_t)ze * aplane;
+      double* const t0 = tile + (size_t)(2 * q) * kFI * kFP;
+      double ev[kPer], ov[kPer];
+#pragma unroll
+      for (int s = 0; s < kPer; s++) {
+        if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
+          ev[s] = aoff[s] >= 0 ? pa[aoff[s]] : pe[coff[s]];
+          ov[s] = po[coff[s]];
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < kPer; s++) {
+        if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
+          double x0, x1;
+          inv_step(k, st[s], ev[s], ov[s], x0, x1);
+          t0[sidx[s]] = x0;
+          t0[kFI * kFP + sidx[s]] = x1;
+        }
       }
     }
     __syncthreads();
-    const int kk = j - 2;   // planes 2 kk and 2 kk + 1 of the rebuilt box
-    if (kk >= k0 && kk < k1) {   // block-uniform
-      // ---- columns (y) over all x of the tile, then rows (x) over the valid y ----
-      if (tid < 2 * kFI)
-        lift_line<true>(k, &tile[tid / kFI][0][tid % kFI], kFP);
-      __syncthreads();
-      if (tid < 2 * kFT)
-        lift_line<true>(k, &tile[tid / kFT][kFH + tid % kFT][0], 1);
-      __syncthreads();
-      // ---- epilogue: 2 planes x 32 x 32 values, 8 per thread ----
-      for (int s = 0; s < 8; s++) {
-        const int idx = tid + s * kFThreads;
-        const int p = idx >> 10, ry = (idx >> 5) & 31, rx = idx & 31;
-        const int x = X0 + rx, y = Y0 + ry, z = 2 * kk + p;
-        if (x < lx && y < ly && z < lz) {
-          const double v = tile[p][kFH + ry][kFH + rx];
-          if (OUT == 0 && a.out_off >= 0) {
-            ch.scratch[a.out_off + ((size_t)z * ly + y) * lx + x] = v;
+    // planes 2 (j0 - 2) .. of the rebuilt box sit in the tile; pair q is wanted iff k0 <= j0+q-2 < k1
+    // ---- columns (y) over all x of the tile, then rows (x) over the valid y ----
+    if (tid < kPlanes * kFI)
+      lift_line<true>(k, tile + (size_t)(tid / kFI) * kFI * kFP + tid % kFI, kFP);
+    __syncthreads();
+    if (tid < kPlanes * kFT)
+      lift_line<true>(k, tile + (size_t)(tid / kFT) * kFI * kFP + (kFH + tid % kFT) * kFP, 1);
+    __syncthreads();
+    // ---- epilogue: kPlanes x 32 x 32 values ----
+    for (int idx = tid; idx < kPlanes * kFT * kFT; idx += kFThreads) {
+      const int p = idx >> 10, ry = (idx >> 5) & 31, rx = idx & 31;
+      const int kk = j0 + (p >> 1) - 2;
+      const int x = X0 + rx, y = Y0 + ry, z = 2 * kk + (p & 1);
+      if (kk >= k0 && kk < k1 && x < lx && y < ly && z < lz) {
+        const double v = tile[(size_t)p * kFI * kFP + (kFH + ry) * kFP + kFH + rx];
+        if (OUT == 0 && a.out_off >= 0) {
+          ch.scratch[a.out_off + ((size_t)z * ly + y) * lx + x] = v;
+        }
+        else {
+          const unsigned long long g = (unsigned long long)(ch.z0 + z) * a.vol.vx * a.vol.vy +
+                                       (unsigned long long)(ch.y0 + y) * a.vol.vx + (ch.x0 + x);
+          if (OUT == 0) {
+            reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr))[g] = v;
+          }
+          else if (OUT == 1) {
+            double w = v;
+            if (a.cor.key) {   // src/SPECK_FLT.cpp:576-585: correctors are added before the mean
+              const unsigned long long i = (unsigned long long)z * cnxy + (size_t)y * cnx + x;
+              if ((ch.obits[i >> 5] >> (i & 31)) & 1u)
+                w = __dadd_rn(w, corrector_lookup(a.cor, a.ids[blockIdx.y], i));
+            }
+            w = __dadd_rn(w, ch.mean);
+            if (a.vol.is_float)
+              reinterpret_cast<float*>(const_cast<void*>(a.vol.ptr))[g] = __double2float_rn(w);
+            else
+              reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr))[g] = w;
           }
           else {
-            const unsigned long long g = (unsigned long long)(ch.z0 + z) * a.vol.vx * a.vol.vy +
-                                         (unsigned long long)(ch.y0 + y) * a.vol.vx + (ch.x0 + x);
-            if (OUT == 0) {
-              reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr))[g] = v;
-            }
-            else if (OUT == 1) {
-              double w = v;
-              if (a.cor.key) {   // src/SPECK_FLT.cpp:576-585: correctors are added before the mean
-                const unsigned long long i = (unsigned long long)z * cnxy + (size_t)y * cnx + x;
-                if ((ch.obits[i >> 5] >> (i & 31)) & 1u)
-                  w = __dadd_rn(w, corrector_lookup(a.cor, a.ids[blockIdx.y], i));
-              }
-              w = __dadd_rn(w, ch.mean);
-              if (a.vol.is_float)
-                reinterpret_cast<float*>(const_cast<void*>(a.vol.ptr))[g] = __double2float_rn(w);
-              else
-                reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr))[g] = w;
-            }
-            else {
-              const double orig = a.vol.is_float ? double(reinterpret_cast<const float*>(a.vol.ptr)[g])
-                                                 : reinterpret_cast<const double*>(a.vol.ptr)[g];
-              const double diff = __dsub_rn(__dsub_rn(orig, ch.mean), v);
-              if (fabs(diff) > a.tol)
-                outlier_append(a.sink, a.ids[blockIdx.y], (unsigned long long)z * cnxy + (size_t)y * cnx + x,
-                               diff);
-            }
+            const double orig = a.vol.is_float ? double(reinterpret_cast<const float*>(a.vol.ptr)[g])
+                                               : reinterpret_cast<const double*>(a.vol.ptr)[g];
+            const double diff = __dsub_rn(__dsub_rn(orig, ch.mean), v);
+            if (fabs(diff) > a.tol)
+              outlier_append(a.sink, a.ids[blockIdx.y], (unsigned long long)z * cnxy + (size_t)y * cnx + x,
+                             diff);
           }
         }
       }
@@ -399,11 +468,29 @@ static void fused_grid(FusedArgs& a, int nids, dim3& grid)
 
 CdfC cdf_constants();
 
+static void fused_attrs()
+{
+#ifndef SPERR_EMUL
+  static bool done = false;
+  if (done)
+    return;
+  const int sm = int(kFusedSmem);
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  done = true;
+#endif
+}
+
 // Forward transform of dyadic chunks straight from the source volume: coef receives the final
 // coefficients, ChunkDev::max_bits the largest magnitude.
 void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const int* d_ids, int nids,
                               uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st)
 {
+  fused_attrs();
   const int L = can_use_dyadic(nx, ny, nz);
   long long off[8];
   fused_scratch_elems(nx, ny, nz, off);
@@ -423,11 +510,11 @@ void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const
     dim3 grid;
     fused_grid(a, nids, grid);
     if (l > 0)
-      LAUNCH(k_fwd3d<2>, grid, dim3(kFThreads), 0, st, a);
+      LAUNCH(k_fwd3d<2>, grid, dim3(kFThreads), kFusedSmem, st, a);
     else if (src.is_float)
-      LAUNCH(k_fwd3d<0>, grid, dim3(kFThreads), 0, st, a);
+      LAUNCH(k_fwd3d<0>, grid, dim3(kFThreads), kFusedSmem, st, a);
     else
-      LAUNCH(k_fwd3d<1>, grid, dim3(kFThreads), 0, st, a);
+      LAUNCH(k_fwd3d<1>, grid, dim3(kFThreads), kFusedSmem, st, a);
   }
 }
 
@@ -439,6 +526,7 @@ void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chu
                               int nids, uint32_t nx, uint32_t ny, uint32_t nz, double tol,
                               const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st)
 {
+  fused_attrs();
   const int L = can_use_dyadic(nx, ny, nz);
   long long off[8];
   fused_scratch_elems(nx, ny, nz, off);
@@ -460,11 +548,11 @@ void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chu
     dim3 grid;
     fused_grid(a, nids, grid);
     if (l > 0 || mode == 0)
-      LAUNCH(k_inv3d<0>, grid, dim3(kFThreads), 0, st, a);
+      LAUNCH(k_inv3d<0>, grid, dim3(kFThreads), kFusedSmem, st, a);
     else if (mode == 1)
-      LAUNCH(k_inv3d<1>, grid, dim3(kFThreads), 0, st, a);
+      LAUNCH(k_inv3d<1>, grid, dim3(kFThreads), kFusedSmem, st, a);
     else
-      LAUNCH(k_inv3d<2>, grid, dim3(kFThreads), 0, st, a);
+      LAUNCH(k_inv3d<2>, grid, dim3(kFThreads), kFusedSmem, st, a);
   }
 }
 
