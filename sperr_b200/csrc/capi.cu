@@ -226,22 +226,32 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
     ContainerInfo ci;
     if (!parse_container(static_cast<const uint8_t*>(src), src_len, ci))
       return -1;
-    g_stream.reserve(src_len);
-    HostPipe::get().h2d(g_stream.p, src, src_len, st);
     const size_t total = ci.vol[0] * ci.vol[1] * ci.vol[2];
     const size_t esz = output_float ? 4 : 8;
-    g_vol.reserve(total * esz);
-    decomp_3d_device(static_cast<const uint8_t*>(src), g_stream.as<uint8_t>(), ci, output_float,
-                     g_vol.p, st);
+    // the result buffer first: its pages are faulted in by the copy threads while the GPU decodes
     void* o = std::malloc(total * esz);
     if (!o)
       return -1;
-    if (total * esz >= (size_t(64) << 20)) {   // fewer first-touch faults while the result is filled
+    if (total * esz >= (size_t(64) << 20)) {
       const uintptr_t a = (reinterpret_cast<uintptr_t>(o) + 4095) & ~uintptr_t(4095);
-      madvise(reinterpret_cast<void*>(a), total * esz - (a - reinterpret_cast<uintptr_t>(o)) & ~size_t(4095),
+      madvise(reinterpret_cast<void*>(a), (total * esz - (a - reinterpret_cast<uintptr_t>(o))) & ~size_t(4095),
               MADV_HUGEPAGE);
     }
-    HostPipe::get().d2h(o, g_vol.p, total * esz, st);
+    HostPipe::get().prefault_begin(o, total * esz);
+    try {
+      g_stream.reserve(src_len);
+      HostPipe::get().h2d(g_stream.p, src, src_len, st);
+      g_vol.reserve(total * esz);
+      decomp_3d_device(static_cast<const uint8_t*>(src), g_stream.as<uint8_t>(), ci, output_float,
+                       g_vol.p, st);
+      HostPipe::get().wait_idle();
+      HostPipe::get().d2h(o, g_vol.p, total * esz, st);
+    }
+    catch (...) {
+      HostPipe::get().wait_idle();
+      std::free(o);
+      throw;
+    }
     *dimx = ci.vol[0];
     *dimy = ci.vol[1];
     *dimz = ci.vol[2];
@@ -305,7 +315,7 @@ size_t sperr_b200_prof_dump(char* buf, size_t cap)
   return s.size();
 }
 
-unsigned long long sperr_b200_launch_count(void) { return rt::launch_counter(); }
+unsigned long long sperr_b200_launch_count(void) { return rt::launch_counter().load(); }
 
 void sperr_parse_header(const void* src, size_t* dimx, size_t* dimy, size_t* dimz, int* is_float)
 {

@@ -47,11 +47,36 @@ void HostPipe::worker()
     const Job j = jobs_.back();
     jobs_.pop_back();
     l.unlock();
-    std::memcpy(j.dst, j.src, j.len);
+    if (j.src)
+      std::memcpy(j.dst, j.src, j.len);
+    else   // first-touch: fault the pages in
+      for (size_t off = 0; off < j.len; off += 4096)
+        reinterpret_cast<volatile char*>(j.dst)[off] = 0;
     l.lock();
-    if (--pending_ == 0)
+    if (--(j.src ? pending_ : pending_pf_) == 0)
       cv_done_.notify_all();
   }
+}
+
+void HostPipe::prefault_begin(void* dst, size_t bytes)
+{
+  if (threads_.empty() || bytes < (size_t(16) << 20))
+    return;
+  const size_t piece = size_t(8) << 20;
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    for (size_t off = 0; off < bytes; off += piece) {
+      jobs_.insert(jobs_.begin(), {static_cast<char*>(dst) + off, nullptr, std::min(piece, bytes - off)});
+      pending_pf_++;
+    }
+  }
+  cv_work_.notify_all();
+}
+
+void HostPipe::wait_idle()
+{
+  std::unique_lock<std::mutex> l(mu_);
+  cv_done_.wait(l, [this] { return pending_ == 0 && pending_pf_ == 0; });
 }
 
 void HostPipe::parallel_copy(void* dst, const void* src, size_t bytes)

@@ -23,6 +23,10 @@ class HostPipe {
   void d2h(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st);
   // Returns after the last byte has been handed to the DMA engine AND the copy has completed.
   void h2d(void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st);
+  // Starts touching every page of a freshly malloc'd buffer on the worker threads (returns at once),
+  // so that the page faults overlap GPU work; wait_idle() before the buffer is filled.
+  void prefault_begin(void* dst, size_t bytes);
+  void wait_idle();
   // Copies [0, bytes) with all workers; used for the pageable side.
   void parallel_copy(void* dst, const void* src, size_t bytes);
 
@@ -46,7 +50,7 @@ class HostPipe {
     size_t len;
   };
   std::vector<Job> jobs_;
-  size_t pending_ = 0;
+  size_t pending_ = 0, pending_pf_ = 0;   // copy jobs / page-touch jobs in flight
   bool stop_ = false;
 };
 

@@ -1,7 +1,9 @@
 #include "pipeline.h"
 
 #include <cmath>
+#include <exception>
 #include <limits>
+#include <thread>
 
 namespace sperr_b200 {
 
@@ -195,7 +197,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   // dyadic shapes: fused kernels (dwt_fused.cu) that read the volume themselves and track the
   // coefficient maximum; everything else: gather, per-axis passes in place, separate maximum
   auto group_fused = [&](size_t s) { return b_.h[groups[s][0]].fused != 0; };
-  auto transform = [&](bool inverse, bool fused_groups, const OutlierSink& sink) {
+  auto transform = [&](bool inverse, bool fused_groups, const OutlierSink& sink, cudaStream_t st) {
     rt::ProfScope ps(inverse ? "c.idwt" : "c.dwt", st);
     for (size_t s = 0; s < groups.size(); s++) {
       if (groups[s].empty() || group_fused(s) != fused_groups)
@@ -212,9 +214,9 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
                                  CorrectorList{nullptr, nullptr, nullptr}, st);
     }
   };
-  transform(false, true, OutlierSink{});
+  transform(false, true, OutlierSink{}, st);
   if (any_unfused) {
-    transform(false, false, OutlierSink{});
+    transform(false, false, OutlierSink{}, st);
     rt::ProfScope ps("c.absmax", st);
     launch_absmax(b_.dev(), nc, b_.max_n, st);
   }
@@ -302,32 +304,75 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
       rt::ProfScope ps("c.quantize", st);
       launch_quantize(b_.dev(), nc, b_.max_n, st);
     }
-    if (mode == kModePWE) {
+    // PWE: the outlier path (de-quantise, inverse transform, compare with the source, SPECK1D-code
+    // the differences) only needs the quantised integers, like the SPECK3D encoder, and both are
+    // chains of small launches with host round trips: run them side by side on two streams.
+    auto outlier_chain = [&](cudaStream_t s) {
       {
-        rt::ProfScope ps("c.inv_quantize", st);
-        launch_inv_quantize(b_.dev(), nc, b_.max_n, st);
+        rt::ProfScope ps("c.inv_quantize", s);
+        launch_inv_quantize(b_.dev(), nc, b_.max_n, s);
       }
       if (any_unfused)
-        transform(true, false, OutlierSink{});
+        transform(true, false, OutlierSink{}, s);
       for (;;) {
-        const OutlierSink sink = out_.begin_detect(nc, total_values, st);
+        const OutlierSink sink = out_.begin_detect(nc, total_values, s);
         if (any_fused)
-          transform(true, true, sink);
+          transform(true, true, sink, s);
         if (any_unfused) {
-          rt::ProfScope ps("c.outlier_detect", st);
-          out_.append_unfused(src, b_.dev(), nc, b_.max_n, quality, sink, st);
+          rt::ProfScope ps("c.outlier_detect", s);
+          out_.append_unfused(src, b_.dev(), nc, b_.max_n, quality, sink, s);
         }
-        if (out_.end_detect(nc, st))
+        if (out_.end_detect(nc, s))
           break;
       }
       std::vector<unsigned long long> tl(nc);
       for (int c = 0; c < nc; c++)
         tl[c] = b_.h[c].n;
-      rt::ProfScope ps("c.outlier_encode", st);
-      out_.encode(tl, quality, out_res_, st);
+      rt::ProfScope ps("c.outlier_encode", s);
+      out_.encode(tl, quality, out_res_, s);
+    };
+    auto speck_chain = [&] {
+      rt::ProfScope ps("c.speck3d", st);
+      enc.encode(b_.dev(), b_.h, b_.dev_shapes(), b_.shapes, res, st);
+    };
+    if (mode != kModePWE) {
+      speck_chain();
+      return;
     }
-    rt::ProfScope ps("c.speck3d", st);
-    enc.encode(b_.dev(), b_.h, b_.dev_shapes(), b_.shapes, res, st);
+#ifdef SPERR_EMUL
+    outlier_chain(st);
+    speck_chain();
+#else
+    if (!side_) {
+      RT_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+      RT_CHECK(cudaEventCreateWithFlags(&side_ev_, cudaEventDisableTiming));
+    }
+    RT_CHECK(cudaEventRecord(side_ev_, st));
+    RT_CHECK(cudaStreamWaitEvent(side_, side_ev_, 0));
+    int dev = 0;
+    RT_CHECK(cudaGetDevice(&dev));
+    std::exception_ptr side_err;
+    std::thread helper([&] {
+      try {
+        RT_CHECK(cudaSetDevice(dev));
+        outlier_chain(side_);
+        rt::sync(side_);
+      }
+      catch (...) {
+        side_err = std::current_exception();
+      }
+    });
+    try {
+      speck_chain();
+    }
+    catch (...) {
+      helper.join();
+      throw;
+    }
+    helper.join();
+    if (side_err)
+      std::rethrow_exception(side_err);
+#endif
   };
   quantize_and_encode(enc_, spk_res_);
 

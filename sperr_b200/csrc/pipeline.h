@@ -32,6 +32,10 @@ class Compressor {
   rt::DBuf stride_mean_, nstrides_, not_const_, ids_, mse_ids_, mse_q_, mse_part_, mse_out_;
   // results of the last batch
   std::vector<EncResult> spk_res_, out_res_;
+#ifndef SPERR_EMUL
+  cudaStream_t side_ = nullptr;   // PWE: the outlier path runs beside the SPECK3D encoder
+  cudaEvent_t side_ev_ = nullptr;
+#endif
 };
 
 struct ChunkStream {   // where a chunk's stream sits inside the container

@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -37,9 +39,9 @@ typedef int cudaStream_t;
 namespace rt {
 
 // number of kernels of this library launched so far (bench.py reports the count per step)
-inline unsigned long long& launch_counter()
+inline std::atomic<unsigned long long>& launch_counter()
 {
-  static unsigned long long n = 0;
+  static std::atomic<unsigned long long> n{0};
   return n;
 }
 
@@ -128,6 +130,7 @@ struct ProfEntry {
 };
 struct ProfState {
   bool on = false;
+  std::mutex mu;   // ranges may be recorded by the pipelines' helper threads
   std::vector<ProfEntry> open;                       // recorded, not yet resolved
   std::map<std::string, std::pair<double, long>> acc;  // name -> (ms, ranges)
 };
@@ -155,6 +158,7 @@ struct ProfScope {
     if (!live)
       return;
     cudaEventRecord(e.e1, st);
+    std::lock_guard<std::mutex> l(prof().mu);
     prof().open.push_back(e);
   }
 #else
