@@ -7,7 +7,11 @@
 
 #include <sys/mman.h>
 
+#include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
+#include <thread>
 
 #include "hostpipe.h"
 #include "pipeline.h"
@@ -20,6 +24,9 @@ std::mutex g_mutex;  // one job at a time per process: the work buffers are shar
 Compressor* g_comp = nullptr;
 // grow-only device staging of the host-pointer entry points (input volume, container, output volume)
 rt::DBuf g_in, g_stream, g_vol, g_cstream;
+#ifndef SPERR_EMUL
+cudaStream_t g_copy_stream = nullptr;
+#endif
 
 bool device_ok()
 {
@@ -32,6 +39,100 @@ bool device_ok()
 #endif
   return true;
 }
+
+// One helper thread that runs posted jobs in order (device -> host copies of finished batches while
+// the next batch is being decoded).
+class SerialWorker {
+ public:
+  ~SerialWorker()
+  {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    if (th_.joinable())
+      th_.join();
+  }
+  void post(std::function<void()> fn)
+  {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      if (!th_.joinable())
+        th_ = std::thread([this] { run(); });
+      q_.push_back(std::move(fn));
+      busy_++;
+    }
+    cv_.notify_all();
+  }
+  // waits for everything posted so far; rethrows the first failure
+  void drain()
+  {
+    std::unique_lock<std::mutex> l(mu_);
+    done_.wait(l, [this] { return busy_ == 0; });
+    if (err_) {
+      auto e = err_;
+      err_ = nullptr;
+      std::rethrow_exception(e);
+    }
+  }
+
+ private:
+  void run()
+  {
+    std::unique_lock<std::mutex> l(mu_);
+    for (;;) {
+      cv_.wait(l, [this] { return stop_ || !q_.empty(); });
+      if (q_.empty())
+        return;
+      auto fn = std::move(q_.front());
+      q_.pop_front();
+      l.unlock();
+      try {
+        fn();
+      }
+      catch (...) {
+        l.lock();
+        if (!err_)
+          err_ = std::current_exception();
+        l.unlock();
+      }
+      l.lock();
+      if (--busy_ == 0)
+        done_.notify_all();
+    }
+  }
+  std::thread th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  std::deque<std::function<void()>> q_;
+  size_t busy_ = 0;
+  bool stop_ = false;
+  std::exception_ptr err_;
+};
+SerialWorker* g_d2h_worker = nullptr;
+
+// wall-clock phases of the host-pointer entry points, printed when SPERR_B200_TIMING is set
+struct PhaseTimer {
+  const bool on = std::getenv("SPERR_B200_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  std::string line;
+  void mark(const char* what)
+  {
+    if (!on)
+      return;
+    const auto t1 = std::chrono::steady_clock::now();
+    char buf[64];
+    std::snprintf(buf, sizeof(buf), " %s %.1f ms", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    line += buf;
+    t0 = t1;
+  }
+  void done(const char* fn)
+  {
+    if (on)
+      std::fprintf(stderr, "sperr_b200 timing %s:%s\n", fn, line.c_str());
+  }
+};
 
 template <typename F>
 int guarded(F&& f)
@@ -190,10 +291,73 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
   return guarded([&] {
     cudaStream_t st = 0;
     const size_t bytes = dimx * dimy * dimz * (is_float ? 4 : 8);
+    PhaseTimer pt;
     g_in.reserve(bytes);
-    HostPipe::get().h2d(g_in.p, src, bytes, st);
-    return comp_3d_device(g_in.p, is_float, dimx, dimy, dimz, chunk_x, chunk_y, chunk_z, mode,
+    if (!g_comp)
+      g_comp = new Compressor();
+    g_comp->max_batch = 0;
+    g_comp->before_batch = nullptr;
+#ifndef SPERR_EMUL
+    // Pinned source and several z-slabs of chunks: upload slab groups on a copy stream and let the
+    // coder start on the first group while the rest is still in flight.
+    std::vector<cudaEvent_t> evs;
+    const size_t esz = is_float ? 4 : 8;
+    if (rt::is_pinned_host(src) && dimx && dimy && dimz) {
+      const size_t vol[3] = {dimx, dimy, dimz};
+      size_t cd[3] = {chunk_x, chunk_y, chunk_z};
+      for (int i = 0; i < 3; i++)
+        cd[i] = std::min(std::max<size_t>(1, cd[i]), vol[i]);
+      const auto chunks = chunk_volume(vol, cd);
+      size_t per_slab = 0;
+      while (per_slab < chunks.size() && chunks[per_slab].z0 == chunks[0].z0)
+        per_slab++;
+      const size_t nslabs = chunks.size() / std::max<size_t>(per_slab, 1);
+      if (nslabs >= 2 && per_slab * nslabs == chunks.size() && bytes >= (size_t(256) << 20)) {
+        const size_t groups = nslabs >= 4 ? 4 : 2;
+        const size_t slabs_per = (nslabs + groups - 1) / groups;
+        g_comp->max_batch = slabs_per * per_slab;
+        if (!g_copy_stream)
+          RT_CHECK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        const size_t plane = dimx * dimy * esz;
+        for (size_t s0 = 0; s0 < nslabs; s0 += slabs_per) {
+          const size_t s1 = std::min(nslabs, s0 + slabs_per);
+          const size_t z0 = chunks[s0 * per_slab].z0;
+          const size_t z1 = s1 == nslabs ? dimz : chunks[s1 * per_slab].z0;
+          rt::h2d(static_cast<char*>(g_in.p) + z0 * plane, static_cast<const char*>(src) + z0 * plane,
+                  (z1 - z0) * plane, g_copy_stream);
+          cudaEvent_t e;
+          RT_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          RT_CHECK(cudaEventRecord(e, g_copy_stream));
+          evs.push_back(e);
+        }
+        const size_t mb = g_comp->max_batch;
+        g_comp->before_batch = [&evs, mb, st](size_t first, size_t count) {
+          for (size_t g = first / mb; g <= (first + count - 1) / mb && g < evs.size(); g++)
+            RT_CHECK(cudaStreamWaitEvent(st, evs[g], 0));
+        };
+      }
+    }
+    struct EvGuard {
+      std::vector<cudaEvent_t>& v;
+      ~EvGuard()
+      {
+        for (auto e : v)
+          cudaEventDestroy(e);
+        if (g_comp) {
+          g_comp->max_batch = 0;
+          g_comp->before_batch = nullptr;
+        }
+      }
+    } ev_guard{evs};
+    if (evs.empty())
+#endif
+      HostPipe::get().h2d(g_in.p, src, bytes, st);
+    pt.mark("h2d");
+    const int rc = comp_3d_device(g_in.p, is_float, dimx, dimy, dimz, chunk_x, chunk_y, chunk_z, mode,
                           quality, dst, dst_len, st);
+    pt.mark("compress+d2h");
+    pt.done("sperr_comp_3d");
+    return rc;
   });
 }
 
@@ -237,18 +401,86 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
       madvise(reinterpret_cast<void*>(a), (total * esz - (a - reinterpret_cast<uintptr_t>(o))) & ~size_t(4095),
               MADV_HUGEPAGE);
     }
+    PhaseTimer pt;
     HostPipe::get().prefault_begin(o, total * esz);
+    if (!g_decomp)
+      g_decomp = new Decompressor();
+    g_decomp->max_batch = 0;
+    g_decomp->after_batch = nullptr;
+    bool batched = false;
     try {
       g_stream.reserve(src_len);
       HostPipe::get().h2d(g_stream.p, src, src_len, st);
+      pt.mark("h2d");
       g_vol.reserve(total * esz);
+#ifndef SPERR_EMUL
+      // Several z-slabs of chunks: decode them group by group and copy every finished group to the
+      // host (helper thread + copy stream) while the next one is being decoded.
+      size_t per_slab = 0;
+      while (per_slab < ci.chunks.size() && ci.chunks[per_slab].z0 == ci.chunks[0].z0)
+        per_slab++;
+      const size_t nslabs = ci.chunks.size() / std::max<size_t>(per_slab, 1);
+      if (nslabs >= 2 && per_slab * nslabs == ci.chunks.size() && total * esz >= (size_t(256) << 20)) {
+        batched = true;
+        const size_t groups = nslabs >= 4 ? 4 : 2;
+        const size_t slabs_per = (nslabs + groups - 1) / groups;
+        g_decomp->max_batch = slabs_per * per_slab;
+        if (!g_copy_stream)
+          RT_CHECK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        if (!g_d2h_worker)
+          g_d2h_worker = new SerialWorker();
+        int dev = 0;
+        RT_CHECK(cudaGetDevice(&dev));
+        const size_t plane = ci.vol[0] * ci.vol[1] * esz;
+        const auto& chunks = ci.chunks;
+        const size_t dimz = ci.vol[2];
+        g_decomp->after_batch = [=, &chunks](size_t first, size_t count) {
+          // the batch is complete in g_vol (run_batch synchronises): its z range is final when the
+          // batch ends on a slab boundary
+          const size_t z0 = chunks[first].z0;
+          const size_t end = first + count;
+          const size_t z1 = end == chunks.size() ? dimz : chunks[end].z0;
+          char* hdst = static_cast<char*>(o) + z0 * plane;
+          const char* dsrc = static_cast<const char*>(g_vol.p) + z0 * plane;
+          const size_t nbytes = (z1 - z0) * plane;
+          g_d2h_worker->post([=] {
+            RT_CHECK(cudaSetDevice(dev));
+            HostPipe::get().d2h(hdst, dsrc, nbytes, g_copy_stream);
+          });
+        };
+      }
+#endif
       decomp_3d_device(static_cast<const uint8_t*>(src), g_stream.as<uint8_t>(), ci, output_float,
                        g_vol.p, st);
+      pt.mark("decode");
+      if (batched) {
+#ifndef SPERR_EMUL
+        g_d2h_worker->drain();
+#endif
+        pt.mark("d2h tail");
+      }
+      else {
+        HostPipe::get().d2h(o, g_vol.p, total * esz, st);
+        pt.mark("d2h");
+      }
       HostPipe::get().wait_idle();
-      HostPipe::get().d2h(o, g_vol.p, total * esz, st);
+      g_decomp->max_batch = 0;
+      g_decomp->after_batch = nullptr;
+      pt.done("sperr_decomp_3d");
     }
     catch (...) {
+#ifndef SPERR_EMUL
+      if (batched && g_d2h_worker) {
+        try {
+          g_d2h_worker->drain();
+        }
+        catch (...) {
+        }
+      }
+#endif
       HostPipe::get().wait_idle();
+      g_decomp->max_batch = 0;
+      g_decomp->after_batch = nullptr;
       std::free(o);
       throw;
     }

@@ -50,8 +50,8 @@ void HostPipe::worker()
     if (j.src)
       std::memcpy(j.dst, j.src, j.len);
     else   // first-touch: fault the pages in
-      for (size_t off = 0; off < j.len; off += 4096)
-        reinterpret_cast<volatile char*>(j.dst)[off] = 0;
+      for (size_t off = 0; off < j.len; off += 4096)   // a write access that changes nothing, so
+        __atomic_fetch_or(j.dst + off, 0, __ATOMIC_RELAXED);   // it may race with the real copy
     l.lock();
     if (--(j.src ? pending_ : pending_pf_) == 0)
       cv_done_.notify_all();

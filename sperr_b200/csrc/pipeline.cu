@@ -67,7 +67,11 @@ void Compressor::compress(const SrcVol& src, const std::vector<Chunk>& chunks, i
   size_t used = 0;  // bytes of d_out in use
   size_t first = 0;
   while (first < chunks.size()) {
-    const size_t nb = pick_batch_chunks(chunks, first, mode == kModePWE);
+    size_t nb = pick_batch_chunks(chunks, first, mode == kModePWE);
+    if (max_batch)
+      nb = std::min(nb, max_batch);
+    if (before_batch)
+      before_batch(first, nb);
     std::vector<Chunk> sub(chunks.begin() + first, chunks.begin() + first + nb);
     std::vector<std::vector<uint8_t>> hdrs;
     run_batch(src, sub, mode, quality, is_2d, hdrs, st);

@@ -3,6 +3,8 @@
 // SPECK_FLT::compress / decompress (src/SPECK_FLT.cpp:401-606) inside.
 #pragma once
 
+#include <functional>
+
 #include "batch.h"
 #include "outlier.h"
 #include "speck.h"
@@ -22,6 +24,10 @@ class Compressor {
   // streams back to back (device memory) and `lens` their lengths. Throws on error.
   void compress(const SrcVol& src, const std::vector<Chunk>& chunks, int mode, double quality,
                 bool is_2d, rt::DBuf& d_out, std::vector<size_t>& lens, cudaStream_t st);
+  // Batching hooks for callers that overlap transfers with the coder: at most `max_batch` chunks
+  // per batch (0: as many as fit), `before_batch(first, count)` runs before a batch is touched.
+  size_t max_batch = 0;
+  std::function<void(size_t, size_t)> before_batch;
 
  private:
   void run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, int mode, double quality,
@@ -48,6 +54,10 @@ class Decompressor {
   // memory) into the device-resident volume `dst`. Throws on malformed input.
   void decompress(const uint8_t* h_stream, const uint8_t* d_stream, const std::vector<Chunk>& chunks,
                   const std::vector<ChunkStream>& cs, const SrcVol& dst, cudaStream_t st);
+  // at most `max_batch` chunks per batch (0: as many as fit); `after_batch(first, count)` runs when
+  // the values of a batch are complete in `dst`
+  size_t max_batch = 0;
+  std::function<void(size_t, size_t)> after_batch;
 
  private:
   void run_batch(const uint8_t* h_stream, const uint8_t* d_stream, const std::vector<Chunk>& chunks,

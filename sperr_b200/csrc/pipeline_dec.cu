@@ -38,9 +38,13 @@ void Decompressor::decompress(const uint8_t* h_stream, const uint8_t* d_stream,
 {
   size_t first = 0;
   while (first < chunks.size()) {
-    const size_t nb = pick_dec_batch(chunks, first);
+    size_t nb = pick_dec_batch(chunks, first);
+    if (max_batch)
+      nb = std::min(nb, max_batch);
     std::vector<Chunk> sub(chunks.begin() + first, chunks.begin() + first + nb);
     run_batch(h_stream, d_stream, sub, cs.data() + first, dst, st);
+    if (after_batch)
+      after_batch(first, nb);
     first += nb;
   }
 }

@@ -99,6 +99,15 @@ inline void hfree_pinned(void* p)
   if (p)
     cudaFreeHost(p);
 }
+inline bool is_pinned_host(const void* p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
 inline bool is_device_ptr(const void* p)
 {
   cudaPointerAttributes a;

@@ -67,3 +67,27 @@ def test_decomp3d_rejects_bad_streams(lib, oracle):
 @pytest.mark.parametrize("case", cases.SYN_GPU, ids=cases.syn_id)
 def test_synthetic_roundtrip(lib, oracle, case):
     cases.check_syn_roundtrip(lib, oracle, case)
+
+
+def test_host_api_batched_overlap_path_512(lib):
+    # >= 256 MB and two z-slabs of chunks: sperr_comp_3d uploads slab groups on a copy stream while
+    # the coder runs (pinned source), sperr_decomp_3d copies finished groups out while it decodes.
+    # Both must give what the single-batch device-pointer path gives.
+    import torch
+    import sperr_b200
+    L = sperr_b200.load()
+    dims = (512, 512, 512)
+    v = refs.synthetic_field(dims, seed=9)
+    pinned = torch.from_numpy(v).pin_memory()
+    rc, s_host = L.compress_3d(pinned.numpy(), dims, (256, 256, 256), 3, 1e-3, copy=False)
+    assert rc == 0
+    d_vol = pinned.cuda()
+    rc, s_dev = L.compress_3d_dev(d_vol.data_ptr(), True, dims, (256, 256, 256), 3, 1e-3)
+    assert rc == 0 and np.array_equal(s_host, s_dev)
+    rc, out_host, d = L.decompress_3d(s_host, True, copy=False)
+    assert rc == 0 and d == dims
+    d_out = torch.empty(v.size, dtype=torch.float32, device="cuda")
+    rc, d2 = L.decompress_3d_dev(s_dev, 0, d_out.data_ptr(), True)
+    assert rc == 0 and d2 == dims
+    assert np.array_equal(out_host.view(np.uint32), d_out.cpu().numpy().view(np.uint32))
+    assert np.max(np.abs(out_host.astype(np.float64) - v.astype(np.float64))) <= 1e-3 + 1.2e-7
