@@ -312,8 +312,14 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
       while (per_slab < chunks.size() && chunks[per_slab].z0 == chunks[0].z0)
         per_slab++;
       const size_t nslabs = chunks.size() / std::max<size_t>(per_slab, 1);
-      if (nslabs >= 2 && per_slab * nslabs == chunks.size() && bytes >= (size_t(256) << 20)) {
-        const size_t groups = nslabs >= 4 ? 4 : 2;
+      // worth it only when every group still fills the GPU: the coder's plane loop and the
+      // per-chunk kernels are latency-bound, so small groups cost more than the overlap saves
+      const size_t min_group = std::getenv("SPERR_B200_OVERLAP_MIN_CHUNKS")
+                                   ? size_t(std::atoi(std::getenv("SPERR_B200_OVERLAP_MIN_CHUNKS")))
+                                   : 256;
+      if (nslabs >= 2 && per_slab * nslabs == chunks.size() && bytes >= (size_t(256) << 20) &&
+          chunks.size() >= 2 * min_group) {
+        const size_t groups = std::min<size_t>(nslabs, std::min<size_t>(4, chunks.size() / min_group));
         const size_t slabs_per = (nslabs + groups - 1) / groups;
         g_comp->max_batch = slabs_per * per_slab;
         if (!g_copy_stream)
@@ -420,9 +426,13 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
       while (per_slab < ci.chunks.size() && ci.chunks[per_slab].z0 == ci.chunks[0].z0)
         per_slab++;
       const size_t nslabs = ci.chunks.size() / std::max<size_t>(per_slab, 1);
-      if (nslabs >= 2 && per_slab * nslabs == ci.chunks.size() && total * esz >= (size_t(256) << 20)) {
+      const size_t min_group = std::getenv("SPERR_B200_OVERLAP_MIN_CHUNKS")
+                                   ? size_t(std::atoi(std::getenv("SPERR_B200_OVERLAP_MIN_CHUNKS")))
+                                   : 256;   // one CTA per chunk stream: smaller groups leave SMs idle
+      if (nslabs >= 2 && per_slab * nslabs == ci.chunks.size() && total * esz >= (size_t(256) << 20) &&
+          ci.chunks.size() >= 2 * min_group) {
         batched = true;
-        const size_t groups = nslabs >= 4 ? 4 : 2;
+        const size_t groups = std::min<size_t>(nslabs, std::min<size_t>(4, ci.chunks.size() / min_group));
         const size_t slabs_per = (nslabs + groups - 1) / groups;
         g_decomp->max_batch = slabs_per * per_slab;
         if (!g_copy_stream)

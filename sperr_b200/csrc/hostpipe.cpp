@@ -17,10 +17,10 @@ HostPipe::HostPipe()
     slot_[i] = rt::hmalloc_pinned(kSlotBytes);
     RT_CHECK(cudaEventCreateWithFlags(&ev_[i], cudaEventDisableTiming));
   }
-  unsigned hw = std::thread::hardware_concurrency();
+  const unsigned hw = std::thread::hardware_concurrency();
+  unsigned n = std::min(16u, std::max(2u, hw > 3 ? hw - 2 : 2u));   // memcpy + first-touch faults scale
   if (const char* e = std::getenv("SPERR_B200_COPY_THREADS"))
-    hw = unsigned(std::atoi(e)) * 2;
-  const unsigned n = std::min(12u, std::max(2u, hw / 2));
+    n = std::max(1, std::atoi(e));
   for (unsigned i = 0; i < n; i++)
     threads_.emplace_back([this] { worker(); });
 #endif

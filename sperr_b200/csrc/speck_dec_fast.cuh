@@ -46,6 +46,10 @@ struct FastSmem {
   uint16_t bodyC[kFW + 8];
   uint8_t bodyB[kFBodyB + 8];
   uint8_t bodyA[kFBodyA + 8];
+  // bits consumed by a set of the size class that is coded at this position with its significance
+  // bit ([bit][body if 1]): length in the low bits, the significance bit on top
+  uint8_t stepA[kFBodyA + 8];     // len | sig << 7
+  uint16_t stepB[kFBodyB + 8];    // len | sig << 15
   uint16_t nxt[2][kFNext + 8];
   uint32_t mark[kFW / 32];
   uint16_t T1[256], T2[2][256];       // pixel-set tables: sig(4) | sign(4) << 4 | bits << 8
@@ -261,6 +265,9 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
     unsigned sm, gm;
     F.bodyA[q] = uint8_t(f_pixels(F, q, nchA, sm, gm));
   }
+  __syncthreads();
+  for (int q = tid; q < nA - 1; q += kDecThreads)
+    F.stepA[q] = f_bit(F, q) ? uint8_t((1u + F.bodyA[q + 1]) | 0x80u) : uint8_t(1);
   if (kinds == 0)
     return;
   __syncthreads();
@@ -269,35 +276,38 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
   for (int q = tid; q < nB; q += kDecThreads) {
     if (kinds == 1 && after_one && q > 0 && !f_bit(F, q - 1))
       continue;
-    unsigned pos = q;
-    int c = 0;
-    for (int k = 0; k < nchB; k++) {
-      const bool need = c != 0 || k != nchB - 1;
-      const unsigned s = need ? f_bit(F, pos++) : 1u;
-      if (s) {
-        c = 1;
-        pos += F.bodyA[pos];
-      }
+    unsigned pos = q, c = 0;
+    for (int k = 0; k < nchB - 1; k++) {   // all but the last child carry a significance bit
+      const unsigned s = F.stepA[pos];
+      c |= s;
+      pos += s & 127u;
     }
+    pos += (c & 0x80u) ? (F.stepA[pos] & 127u) : F.bodyA[pos];   // the last one may be inferred
     F.bodyB[q] = uint8_t(pos - q);
+  }
+  if (kinds == 1 && after_one) {
+    __syncthreads();
+    for (int q = tid; q < nB - 1; q += kDecThreads)
+      F.stepB[q] = f_bit(F, q) ? uint16_t((1u + F.bodyB[q + 1]) | 0x8000u) : uint16_t(1);
+    return;
   }
   if (kinds == 1)
     return;
+  __syncthreads();
+  for (int q = tid; q < nB - 1; q += kDecThreads)
+    F.stepB[q] = f_bit(F, q) ? uint16_t((1u + F.bodyB[q + 1]) | 0x8000u) : uint16_t(1);
   __syncthreads();
   const int nchC = f_nch(F, J - 3);
   for (int q = tid; q < kFW + 8; q += kDecThreads) {
     if (after_one && q > 0 && !f_bit(F, q - 1))
       continue;
-    unsigned pos = q;
-    int c = 0;
-    for (int k = 0; k < nchC; k++) {
-      const bool need = c != 0 || k != nchC - 1;
-      const unsigned s = need ? f_bit(F, pos++) : 1u;
-      if (s) {
-        c = 1;
-        pos += F.bodyB[pos];
-      }
+    unsigned pos = q, c = 0;
+    for (int k = 0; k < nchC - 1; k++) {
+      const unsigned s = F.stepB[pos];
+      c |= s;
+      pos += s & 0x7fffu;
     }
+    pos += (c & 0x8000u) ? (F.stepB[pos] & 0x7fffu) : F.bodyB[pos];
     F.bodyC[q] = uint16_t(pos - q);
   }
 }
@@ -497,9 +507,13 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
     for (int q = tid; q < kFNext; q += kDecThreads) {
       unsigned nx = q;
       if (q < kFW) {
-        unsigned len = 1;
-        if (f_bit(F, q))
-          len += kind == 0 ? F.bodyA[q + 1] : (kind == 1 ? F.bodyB[q + 1] : F.bodyC[q + 1]);
+        unsigned len;
+        if (kind == 0)
+          len = F.stepA[q] & 127u;
+        else if (kind == 1)
+          len = F.stepB[q] & 0x7fffu;
+        else
+          len = f_bit(F, q) ? 1u + F.bodyC[q + 1] : 1u;
         nx = q + len;
       }
       F.nxt[0][q] = uint16_t(nx);

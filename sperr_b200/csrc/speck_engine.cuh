@@ -63,7 +63,7 @@ static __global__ void k_lipref_count(const ChunkDev* chunks, unsigned* counts, 
     atomicMax(&s_cmax, wmax);
   __syncthreads();
   const int cmax = s_cmax;  // bits exist only for planes n < cmax
-  for (int n = 0; n < cmax; n++) {
+  for (int n = 0; n < wmax; n++) {   // warp-uniform: this warp has no bits in planes >= its largest cm
     const bool inlip = cm > n && p <= n;
     const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
     const unsigned b1 = __ballot_sync(0xffffffffu, inlip && p == n);
@@ -143,7 +143,8 @@ static __global__ void k_lipref_scan(const ChunkDev* chunks, unsigned* counts, u
 static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* counts,
                               const unsigned long long* bases, int maxp, unsigned nblk)
 {
-  __shared__ unsigned s_w[2][32];
+  // per plane: bits every warp of the block contributes to the LIP part / the refinement part
+  __shared__ unsigned short s_lip[64][32], s_ref[64][32];
   __shared__ int s_cmax;
   const unsigned c = blockIdx.y, blk = blockIdx.x;
   const ChunkDev& ch = chunks[c];
@@ -153,57 +154,66 @@ static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* cou
   const bool valid = i < ch.n;
   const int p = valid ? int(ch.pleaf[i]) : -1;
   const int cm = valid ? int(ch.cmap[i]) : -1;
-  const unsigned long long mag = (valid && p >= 0) ? load_mag(ch, i) : 0;
-  const unsigned sgn = valid ? (ch.signs[i >> 5] >> (i & 31)) & 1u : 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
   if (threadIdx.x == 0)
     s_cmax = -1;
   __syncthreads();
-  const int wmax = __reduce_max_sync(0xffffffffu, cm);
+  const int wmax = __reduce_max_sync(0xffffffffu, cm);   // a coefficient has bits in planes < its cm
   if (lane == 0 && wmax >= 0)
     atomicMax(&s_cmax, wmax);
   __syncthreads();
   const int cmax = s_cmax;
   const int first = ch.last_plane;  // planes below this were never coded
-  for (int n = cmax - 1; n >= first; n--) {
+  const bool no_ref_last = ch.stop_after_sort != 0;
+  for (int n = first; n < cmax; n++) {
+    unsigned l = 0, r = 0;
+    if (n < wmax) {
+      const bool inlip = cm > n && p <= n;
+      const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
+      const unsigned b1 = __ballot_sync(0xffffffffu, inlip && p == n);
+      const unsigned b2 = __ballot_sync(0xffffffffu, p > n && !(n == first && no_ref_last));
+      l = unsigned(__popc(b0) + __popc(b1));
+      r = unsigned(__popc(b2));
+    }
+    if (lane == 0) {
+      s_lip[n][warp] = (unsigned short)l;
+      s_ref[n][warp] = (unsigned short)r;
+    }
+  }
+  __syncthreads();
+  if (wmax < 0)
+    return;
+  const unsigned long long mag = (valid && p >= 0) ? load_mag(ch, i) : 0;
+  const unsigned sgn = valid ? (ch.signs[i >> 5] >> (i & 31)) & 1u : 0;
+  for (int n = wmax - 1; n >= first; n--) {   // warp-uniform bounds
     const bool inlip = cm > n && p <= n;
     const bool newsig = inlip && p == n;
-    const bool ref = p > n && !(n == ch.last_plane && ch.stop_after_sort);
+    const bool ref = p > n && !(n == first && no_ref_last);
     const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
     const unsigned b1 = __ballot_sync(0xffffffffu, newsig);
     const unsigned b2 = __ballot_sync(0xffffffffu, ref);
-    if (lane == 0) {
-      s_w[0][warp] = __popc(b0) + __popc(b1);
-      s_w[1][warp] = __popc(b2);
-    }
-    __syncthreads();
-    if (warp < 2) {
-      unsigned v = s_w[warp][lane], inc = v;
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o)
-          inc += t;
-      }
-      s_w[warp][lane] = inc - v;
-    }
-    __syncthreads();
-    if (inlip) {
-      const unsigned long long pos = bases[(size_t)(c * 2 + 0) * maxp + n] +
-                                     counts[((size_t)(c * 2 + 0) * maxp + n) * nblk + blk] +
-                                     s_w[0][warp] + __popc(b0 & lt) + __popc(b1 & lt);
-      if (newsig) {
-        put_bit(ch.spk, pos, 1);
-        put_bit(ch.spk, pos + 1, sgn);
+    if (b0) {
+      const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? unsigned(s_lip[n][lane]) : 0u);
+      if (inlip) {
+        const unsigned long long pos = bases[(size_t)(c * 2 + 0) * maxp + n] +
+                                       counts[((size_t)(c * 2 + 0) * maxp + n) * nblk + blk] + before +
+                                       __popc(b0 & lt) + __popc(b1 & lt);
+        if (newsig) {
+          put_bit(ch.spk, pos, 1);
+          put_bit(ch.spk, pos + 1, sgn);
+        }
       }
     }
-    if (ref) {
-      const unsigned long long pos = bases[(size_t)(c * 2 + 1) * maxp + n] +
-                                     counts[((size_t)(c * 2 + 1) * maxp + n) * nblk + blk] +
-                                     s_w[1][warp] + __popc(b2 & lt);
-      put_bit(ch.spk, pos, unsigned(mag >> n) & 1u);
+    if (b2) {
+      const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? unsigned(s_ref[n][lane]) : 0u);
+      if (ref) {
+        const unsigned long long pos = bases[(size_t)(c * 2 + 1) * maxp + n] +
+                                       counts[((size_t)(c * 2 + 1) * maxp + n) * nblk + blk] + before +
+                                       __popc(b2 & lt);
+        put_bit(ch.spk, pos, unsigned(mag >> n) & 1u);
+      }
     }
-    __syncthreads();
   }
 }
 

@@ -40,7 +40,7 @@ __global__ void k_rec_count(const DecChunk* jobs, unsigned* counts, int maxp, un
     atomicMax(&s_max, wmax);
   __syncthreads();
   const int bmax = s_max;
-  for (int n = 0; n < bmax; n++) {
+  for (int n = 0; n < wmax; n++) {   // warp-uniform: nothing of this warp is significant before plane >= wmax
     const unsigned b = __ballot_sync(0xffffffffu, p > n);
     if ((threadIdx.x & 31) == 0 && b)
       atomicAdd(&s_cnt[n], unsigned(__popc(b)));

@@ -73,8 +73,10 @@ def test_host_api_batched_overlap_path_512(lib):
     # >= 256 MB and two z-slabs of chunks: sperr_comp_3d uploads slab groups on a copy stream while
     # the coder runs (pinned source), sperr_decomp_3d copies finished groups out while it decodes.
     # Both must give what the single-batch device-pointer path gives.
+    import os
     import torch
     import sperr_b200
+    os.environ["SPERR_B200_OVERLAP_MIN_CHUNKS"] = "4"   # default 256: 8 chunks would not be split
     L = sperr_b200.load()
     dims = (512, 512, 512)
     v = refs.synthetic_field(dims, seed=9)
@@ -91,3 +93,4 @@ def test_host_api_batched_overlap_path_512(lib):
     assert rc == 0 and d2 == dims
     assert np.array_equal(out_host.view(np.uint32), d_out.cpu().numpy().view(np.uint32))
     assert np.max(np.abs(out_host.astype(np.float64) - v.astype(np.float64))) <= 1e-3 + 1.2e-7
+    del os.environ["SPERR_B200_OVERLAP_MIN_CHUNKS"]
