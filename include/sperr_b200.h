@@ -42,6 +42,17 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
 /* Replaces C_API::sperr_parse_header (SPERR_C_API.h:74-82, src/SPERR_C_API.cpp:136-154). */
 void sperr_parse_header(const void* src, size_t* dimx, size_t* dimy, size_t* dimz, int* is_float);
 
+/* Replaces C_API::sperr_comp_2d (SPERR_C_API.h:33-60, src/SPERR_C_API.cpp:11-95): one 2D slice,
+ * x fastest. out_inc_header != 0 prepends the 10-byte 2D header {version, flags, u32 dimx, u32 dimy}.
+ * Returns 0 ok; 1 *dst not NULL; 2 bad parameter; -1 other error. *dst is malloc'd. */
+int sperr_comp_2d(const void* src, int is_float, size_t dimx, size_t dimy, int mode, double quality,
+                  int out_inc_header, void** dst, size_t* dst_len);
+
+/* Replaces C_API::sperr_decomp_2d (SPERR_C_API.h:62-72, src/SPERR_C_API.cpp:97-134): `src` is the
+ * stream WITHOUT the 10-byte header. */
+int sperr_decomp_2d(const void* src, size_t src_len, int output_float, size_t dimx, size_t dimy,
+                    void** dst);
+
 /* ------------------------------------------------------------------------------------------ */
 /* 2. GPU-side extensions                                                                      */
 /* ------------------------------------------------------------------------------------------ */
@@ -58,6 +69,25 @@ int sperr_b200_comp_3d_dev(const void* d_src, int is_float, size_t dimx, size_t 
  * d_dst, which must hold dimx*dimy*dimz values (see sperr_parse_header). */
 int sperr_b200_decomp_3d_dev(const void* h_src, const void* d_src, size_t src_len, int output_float,
                              size_t* dimx, size_t* dimy, size_t* dimz, void* d_dst);
+
+/* ---- 2a. batched 2D slices ----
+ * sperr_comp_2d codes one slice per call; a GPU wants many slices in flight. These entry points
+ * code `nslices` independent slices of dimx x dimy (contiguous, slice s at src + s*dimx*dimy) in one
+ * call: stream s is byte-identical to what sperr_comp_2d returns for slice s. The streams are
+ * written back to back into one malloc'd buffer *dst; lens[s] receives the length of stream s.
+ * `_dev`: src is a DEVICE pointer. */
+int sperr_b200_comp_2d_batch(const void* src, int is_float, size_t dimx, size_t dimy, size_t nslices,
+                             int mode, double quality, int out_inc_header, void** dst,
+                             size_t* lens);
+int sperr_b200_comp_2d_batch_dev(const void* d_src, int is_float, size_t dimx, size_t dimy,
+                                 size_t nslices, int mode, double quality, int out_inc_header,
+                                 void** dst, size_t* lens);
+/* Decodes `nslices` headerless slice streams (back to back in src, lens[s] each) into one malloc'd
+ * buffer *dst of nslices*dimx*dimy values (`_dev`: into the caller's DEVICE buffer d_dst). */
+int sperr_b200_decomp_2d_batch(const void* src, const size_t* lens, size_t nslices, int output_float,
+                               size_t dimx, size_t dimy, void** dst);
+int sperr_b200_decomp_2d_batch_dev(const void* src, const size_t* lens, size_t nslices,
+                                   int output_float, size_t dimx, size_t dimy, void* d_dst);
 
 /* ---- 2b. chunk-range sharding (one process per GPU) ----
  * SPERR's chunks are coded independently (SPERR3D_OMP_C.cpp:94-130, SPERR3D_OMP_D.cpp:94-130): rank r
@@ -133,6 +163,10 @@ int sperr_b200_stage_quantize(const double* vals, size_t nx, size_t ny, size_t n
 int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, size_t nx, size_t ny,
                                     size_t nz, size_t budget_bits, uint8_t* out, size_t cap,
                                     size_t* out_len);
+
+/* SPECK2D_INT_ENC on one slice (src/SPECK2D_INT*.cpp). */
+int sperr_b200_stage_speck2d_encode(const uint64_t* mags, const uint8_t* signs, size_t nx, size_t ny,
+                                    size_t budget_bits, uint8_t* out, size_t cap, size_t* out_len);
 
 int sperr_b200_stage_outlier_encode(const uint64_t* pos, const double* err, size_t n_out,
                                     size_t total_len, double tol, uint8_t* out, size_t cap,

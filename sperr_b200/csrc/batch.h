@@ -25,7 +25,7 @@ struct BatchBuffers {
   // Lays out every per-chunk array. `need_coef`: fp64 buffer; `need_speck`: integer-coder arrays.
   // `need_enc`: also the encoder-only maps (msb positions, creation planes, significance pyramid).
   void setup(const std::vector<Chunk>& chunks, bool need_coef, bool need_speck, bool wide_mag,
-             cudaStream_t st, bool need_enc = true)
+             cudaStream_t st, bool need_enc = true, bool is_2d = false)
   {
     const int nc = int(chunks.size());
     h.assign(nc, ChunkDev());
@@ -45,7 +45,7 @@ struct BatchBuffers {
       auto it = seen.find(key);
       if (it == seen.end()) {
         it = seen.emplace(key, int(shapes.size())).first;
-        shapes.push_back(build_shape(k.lx, k.ly, k.lz));
+        shapes.push_back(build_shape(k.lx, k.ly, k.lz, is_2d));
       }
       d.shape = it->second;
       d.budget = ~0ull;

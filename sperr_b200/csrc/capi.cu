@@ -272,6 +272,91 @@ void decomp_3d_device(const uint8_t* h_stream, const uint8_t* d_stream, const Co
   g_decomp->decompress(h_stream, d_stream, ci.chunks, ci.cs, dv, st);
 }
 
+// Shared tail of the 2D entry points: every slice is one chunk of extent dimx x dimy x 1 of a
+// "volume" of nslices planes, coded by SPECK2D_FLT's pipeline (dwt2d + SPECK2D_INT).
+std::vector<Chunk> slice_chunks(size_t dimx, size_t dimy, size_t nslices)
+{
+  if (dimx == 0 || dimy == 0 || nslices == 0 || dimx > 65535 || dimy > 65535 ||
+      dimx * dimy >= (1ull << 31) || nslices > 0xFFFFFFFFull)
+    throw std::runtime_error("unsupported slice extents");
+  std::vector<Chunk> chunks(nslices);
+  for (size_t s = 0; s < nslices; s++)
+    chunks[s] = Chunk{0, uint32_t(dimx), 0, uint32_t(dimy), uint32_t(s), 1};
+  return chunks;
+}
+
+int comp_2d_device(const void* d_src, int is_float, size_t dimx, size_t dimy, size_t nslices, int mode,
+                   double quality, int inc_header, void** dst, size_t* lens_out, cudaStream_t st)
+{
+  const auto chunks = slice_chunks(dimx, dimy, nslices);
+  if (!g_comp)
+    g_comp = new Compressor();
+  g_comp->max_batch = 0;
+  g_comp->before_batch = nullptr;
+  SrcVol sv{d_src, is_float, dimx, dimy};
+  rt::DBuf& d_out = g_cstream;
+  d_out.reserve(size_t(1) << 20);
+  std::vector<size_t> lens;
+  g_comp->compress(sv, chunks, mode, quality, true, d_out, lens, st);
+  const size_t hl = inc_header ? 10 : 0;
+  size_t payload = 0;
+  for (size_t l : lens)
+    payload += l;
+  const size_t total = payload + hl * nslices;
+  uint8_t* o = static_cast<uint8_t*>(std::malloc(std::max<size_t>(total, 1)));
+  if (!o)
+    return -1;
+  // one device -> host copy into the tail, then every stream moves forward behind its header
+  uint8_t* tail = o + hl * nslices;
+  try {
+    HostPipe::get().d2h(tail, d_out.p, payload, st);
+    HostPipe::get().wait_idle();
+  }
+  catch (...) {
+    std::free(o);
+    throw;
+  }
+  size_t src_off = 0, dst_off = 0;
+  for (size_t s = 0; s < nslices; s++) {
+    if (inc_header) {
+      uint8_t* h = o + dst_off;
+      h[0] = 0;                              // SPERR_VERSION_MAJOR
+      h[1] = uint8_t(is_float ? 0x20 : 0);   // not a portion, 2D, float flag
+      const uint32_t d2[2] = {uint32_t(dimx), uint32_t(dimy)};
+      std::memmove(o + dst_off + 10, tail + src_off, lens[s]);
+      std::memcpy(h + 2, d2, 8);
+    }
+    lens_out[s] = lens[s] + hl;
+    src_off += lens[s];
+    dst_off += lens[s] + hl;
+  }
+  *dst = o;
+  return 0;
+}
+
+void decomp_2d_device(const uint8_t* h_streams, const size_t* lens, size_t nslices, int output_float,
+                      size_t dimx, size_t dimy, void* d_dst, cudaStream_t st)
+{
+  if (!h_streams || !lens)
+    throw std::runtime_error("no stream");
+  const auto chunks = slice_chunks(dimx, dimy, nslices);
+  std::vector<ChunkStream> cs(nslices);
+  size_t off = 0;
+  for (size_t s = 0; s < nslices; s++) {
+    cs[s].off = off;
+    cs[s].len = lens[s];
+    off += lens[s];
+  }
+  g_stream.reserve(off + 16);
+  HostPipe::get().h2d(g_stream.p, h_streams, off, st);
+  if (!g_decomp)
+    g_decomp = new Decompressor();
+  g_decomp->max_batch = 0;
+  g_decomp->after_batch = nullptr;
+  SrcVol dv{d_dst, output_float, dimx, dimy};
+  g_decomp->decompress(h_streams, g_stream.as<uint8_t>(), chunks, cs, dv, st, true);
+}
+
 }  // namespace
 
 extern "C" {
@@ -525,6 +610,101 @@ int sperr_b200_decomp_3d_dev(const void* h_src, const void* d_src, size_t src_le
     *dimz = ci.vol[2];
     return 0;
   });
+}
+
+// ---- 2D slices (C_API::sperr_comp_2d / sperr_decomp_2d, /root/reference/src/SPERR_C_API.cpp:11-134) ----
+
+int sperr_b200_comp_2d_batch_dev(const void* d_src, int is_float, size_t dimx, size_t dimy,
+                                 size_t nslices, int mode, double quality, int out_inc_header,
+                                 void** dst, size_t* lens)
+{
+  if (*dst != nullptr)
+    return 1;
+  if (quality <= 0.0)
+    return 2;
+  if (mode < 1 || mode > 3)
+    return 2;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return guarded([&] { return comp_2d_device(d_src, is_float, dimx, dimy, nslices, mode, quality,
+                                             out_inc_header, dst, lens, 0); });
+}
+
+int sperr_b200_comp_2d_batch(const void* src, int is_float, size_t dimx, size_t dimy, size_t nslices,
+                             int mode, double quality, int out_inc_header, void** dst, size_t* lens)
+{
+  if (*dst != nullptr)
+    return 1;
+  if (quality <= 0.0)
+    return 2;
+  if (mode < 1 || mode > 3)
+    return 2;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return guarded([&] {
+    cudaStream_t st = 0;
+    const size_t bytes = dimx * dimy * nslices * (is_float ? 4 : 8);
+    g_in.reserve(bytes);
+    HostPipe::get().h2d(g_in.p, src, bytes, st);
+    return comp_2d_device(g_in.p, is_float, dimx, dimy, nslices, mode, quality, out_inc_header, dst,
+                          lens, st);
+  });
+}
+
+int sperr_comp_2d(const void* src, int is_float, size_t dimx, size_t dimy, int mode, double quality,
+                  int out_inc_header, void** dst, size_t* dst_len)
+{
+  size_t len = 0;
+  const int rc = sperr_b200_comp_2d_batch(src, is_float, dimx, dimy, 1, mode, quality, out_inc_header,
+                                          dst, &len);
+  if (rc == 0)
+    *dst_len = len;
+  return rc;
+}
+
+int sperr_b200_decomp_2d_batch_dev(const void* src, const size_t* lens, size_t nslices,
+                                   int output_float, size_t dimx, size_t dimy, void* d_dst)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return guarded([&] {
+    cudaStream_t st = 0;
+    decomp_2d_device(static_cast<const uint8_t*>(src), lens, nslices, output_float, dimx, dimy, d_dst, st);
+    rt::sync(st);
+    return 0;
+  });
+}
+
+int sperr_b200_decomp_2d_batch(const void* src, const size_t* lens, size_t nslices, int output_float,
+                               size_t dimx, size_t dimy, void** dst)
+{
+  if (*dst != nullptr)
+    return 1;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return guarded([&] {
+    cudaStream_t st = 0;
+    const size_t total = dimx * dimy * nslices, esz = output_float ? 4 : 8;
+    if (total == 0)
+      return -1;
+    g_vol.reserve(total * esz);
+    decomp_2d_device(static_cast<const uint8_t*>(src), lens, nslices, output_float, dimx, dimy, g_vol.p, st);
+    void* o = std::malloc(total * esz);
+    if (!o)
+      return -1;
+    try {
+      HostPipe::get().d2h(o, g_vol.p, total * esz, st);
+      HostPipe::get().wait_idle();
+    }
+    catch (...) {
+      std::free(o);
+      throw;
+    }
+    *dst = o;
+    return 0;
+  });
+}
+
+int sperr_decomp_2d(const void* src, size_t src_len, int output_float, size_t dimx, size_t dimy,
+                    void** dst)
+{
+  return sperr_b200_decomp_2d_batch(src, &src_len, 1, output_float, dimx, dimy, dst);
 }
 
 void sperr_b200_prof_enable(int on)

@@ -154,9 +154,9 @@ int sperr_b200_stage_quantize(const double* vals, size_t nx, size_t ny, size_t n
   });
 }
 
-int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, size_t nx, size_t ny,
-                                    size_t nz, size_t budget_bits, uint8_t* out, size_t cap,
-                                    size_t* out_len)
+static int stage_speck_encode(const uint64_t* mags, const uint8_t* signs, size_t nx, size_t ny,
+                              size_t nz, bool is_2d, size_t budget_bits, uint8_t* out, size_t cap,
+                              size_t* out_len)
 {
   return guarded([&] {
     cudaStream_t st = 0;
@@ -166,7 +166,7 @@ int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, 
       if (mags[i] > 0xFFFFFFFFull)
         wide = true;
     BatchBuffers b;
-    b.setup({whole(nx, ny, nz)}, false, true, wide, st);
+    b.setup({whole(nx, ny, nz)}, false, true, wide, st, true, is_2d);
     std::vector<uint32_t> sw((n + 31) / 32, 0);
     std::vector<int8_t> pl(n);
     for (size_t i = 0; i < n; i++) {
@@ -208,6 +208,19 @@ int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, 
     rt::sync(st);
     return 0;
   });
+}
+
+int sperr_b200_stage_speck3d_encode(const uint64_t* mags, const uint8_t* signs, size_t nx, size_t ny,
+                                    size_t nz, size_t budget_bits, uint8_t* out, size_t cap,
+                                    size_t* out_len)
+{
+  return stage_speck_encode(mags, signs, nx, ny, nz, false, budget_bits, out, cap, out_len);
+}
+
+int sperr_b200_stage_speck2d_encode(const uint64_t* mags, const uint8_t* signs, size_t nx, size_t ny,
+                                    size_t budget_bits, uint8_t* out, size_t cap, size_t* out_len)
+{
+  return stage_speck_encode(mags, signs, nx, ny, 1, true, budget_bits, out, cap, out_len);
 }
 
 int sperr_b200_stage_outlier_encode(const uint64_t* pos, const double* err, size_t n_out,

@@ -145,7 +145,7 @@ AxisBuild build_axis(uint32_t L)
 
 }  // namespace
 
-ShapeTables build_shape(uint32_t nx, uint32_t ny, uint32_t nz)
+ShapeTables build_shape(uint32_t nx, uint32_t ny, uint32_t nz, bool is_2d)
 {
   ShapeTables t;
   ShapeHeader& h = t.h;
@@ -216,6 +216,56 @@ ShapeTables build_shape(uint32_t nx, uint32_t ny, uint32_t nz)
     return li;
   };
   add_chain(0, 0, 0);
+
+  if (is_2d) {
+    // ---- SPECK2D_INT::m_initialize_lists (src/SPECK2D_INT.cpp:187-213) ----
+    if (nz != 1)
+      throw std::runtime_error("2D shape with more than one plane");
+    h.is2d = 1;
+    h.dyadic = -1;
+    h.nxf2d = int(num_of_xforms(std::min(nx, ny)));
+    h.nlis = int(num_of_partitions(std::max(nx, ny)) + 1);
+    if (h.nlis > kMaxLis - 1)
+      throw std::runtime_error("too many LIS lists");
+    for (int j = 0; j < kMaxAxisDepth + 2; j++)
+      h.lv2d[j] = -1;
+    {
+      int li = chain_first_level[0];
+      for (int j = 0; li >= 0 && j < kMaxAxisDepth + 2; j++) {
+        h.lv2d[j] = li;
+        if (li == h.leaf_level)
+          break;
+        li = h.lv[li].child;
+      }
+    }
+    h.ngroups = 0;
+    h.nroots = 1;
+    RootDesc r;
+    r.level = h.lv2d[h.nxf2d];
+    r.ix = r.iy = r.iz = 0;
+    r.lis = h.nxf2d;
+    r.order = 0;
+    h.roots[0] = r;
+    unsigned long long off = 0;
+    for (int i = 0; i < h.nlevels; i++) {
+      if (i == h.leaf_level)
+        continue;
+      h.lv[i].p_off = off;
+      off += (unsigned long long)h.lv[i].cx * h.lv[i].cy * h.lv[i].cz;
+    }
+    h.pyr_nodes = off;
+    h.set_nodes = off + 8;   // + the I sets
+    // list l holds sets of part_level l = nodes of chain position l
+    h.lis_off[0] = 0;
+    for (int l = 0; l < kMaxLis; l++) {
+      unsigned long long cap = 0;
+      if (l < kMaxAxisDepth + 2 && h.lv2d[l] >= 0 && h.lv2d[l] != h.leaf_level)
+        cap = (unsigned long long)h.lv[h.lv2d[l]].cx * h.lv[h.lv2d[l]].cy;
+      h.lis_off[l + 1] = h.lis_off[l] + cap;
+    }
+    h.pow2 = 0;
+    return t;
+  }
 
   // ---- initial LIS (m_initialize_lists) ----
   h.dyadic = can_use_dyadic(nx, ny, nz);

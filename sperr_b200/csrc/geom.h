@@ -96,6 +96,13 @@ struct ShapeHeader {
   // 1 when every extent is a power of two and the chunk is dyadic: all sets are then aligned
   // boxes of a single chain and the coders can address them with shifts instead of the tables
   int pow2;
+  // 2D slices (SPECK2D_INT, /root/reference/src/SPECK2D_INT.cpp:10-218): quadtree sets of one chain
+  // plus the set I = everything outside the transform's approximation band. nxf2d = number of
+  // transform levels = initial part_level of I; lv2d[j] = LevelDesc index of chain position j
+  // (= part_level j; the S sets cut out of I at part_level l are nodes (1,1), (1,0), (0,1) of it).
+  int is2d;
+  int nxf2d;
+  int lv2d[kMaxAxisDepth + 2];
 };
 
 struct ShapeTables {
@@ -105,6 +112,6 @@ struct ShapeTables {
   std::vector<uint8_t> lev;      // number of real splits from the root interval
 };
 
-ShapeTables build_shape(uint32_t nx, uint32_t ny, uint32_t nz);
+ShapeTables build_shape(uint32_t nx, uint32_t ny, uint32_t nz, bool is_2d = false);
 
 }  // namespace sperr_b200

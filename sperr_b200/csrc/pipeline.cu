@@ -152,10 +152,8 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
                            double quality, bool is_2d, std::vector<std::vector<uint8_t>>& hdrs,
                            cudaStream_t st)
 {
-  if (is_2d)
-    throw std::runtime_error("2D path not built yet");
   const int nc = int(chunks.size());
-  b_.setup(chunks, true, true, false, st);
+  b_.setup(chunks, true, true, false, st, true, is_2d);
 
   // ---- conditioner ----
   std::vector<unsigned> ns(nc);

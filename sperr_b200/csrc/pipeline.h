@@ -53,7 +53,8 @@ class Decompressor {
   // Decodes `chunks` (streams at h_stream + cs[i].off; d_stream is the same container in device
   // memory) into the device-resident volume `dst`. Throws on malformed input.
   void decompress(const uint8_t* h_stream, const uint8_t* d_stream, const std::vector<Chunk>& chunks,
-                  const std::vector<ChunkStream>& cs, const SrcVol& dst, cudaStream_t st);
+                  const std::vector<ChunkStream>& cs, const SrcVol& dst, cudaStream_t st,
+                  bool is_2d = false);
   // at most `max_batch` chunks per batch (0: as many as fit); `after_batch(first, count)` runs when
   // the values of a batch are complete in `dst`
   size_t max_batch = 0;
@@ -61,7 +62,7 @@ class Decompressor {
 
  private:
   void run_batch(const uint8_t* h_stream, const uint8_t* d_stream, const std::vector<Chunk>& chunks,
-                 const ChunkStream* cs, const SrcVol& dst, cudaStream_t st);
+                 const ChunkStream* cs, const SrcVol& dst, cudaStream_t st, bool is_2d);
   BatchBuffers b_;
   DecWork w_;
   rt::DBuf ids_, lis_off1_, tols_, obits_, ckey_[2], cval_[2], ccount_, coff_, csort_;

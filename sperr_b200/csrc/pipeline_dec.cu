@@ -34,7 +34,7 @@ size_t pick_dec_batch(const std::vector<Chunk>& chunks, size_t first)
 
 void Decompressor::decompress(const uint8_t* h_stream, const uint8_t* d_stream,
                               const std::vector<Chunk>& chunks, const std::vector<ChunkStream>& cs,
-                              const SrcVol& dst, cudaStream_t st)
+                              const SrcVol& dst, cudaStream_t st, bool is_2d)
 {
   size_t first = 0;
   while (first < chunks.size()) {
@@ -42,7 +42,7 @@ void Decompressor::decompress(const uint8_t* h_stream, const uint8_t* d_stream,
     if (max_batch)
       nb = std::min(nb, max_batch);
     std::vector<Chunk> sub(chunks.begin() + first, chunks.begin() + first + nb);
-    run_batch(h_stream, d_stream, sub, cs.data() + first, dst, st);
+    run_batch(h_stream, d_stream, sub, cs.data() + first, dst, st, is_2d);
     if (after_batch)
       after_batch(first, nb);
     first += nb;
@@ -51,7 +51,7 @@ void Decompressor::decompress(const uint8_t* h_stream, const uint8_t* d_stream,
 
 void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
                              const std::vector<Chunk>& chunks, const ChunkStream* cs,
-                             const SrcVol& dst, cudaStream_t st)
+                             const SrcVol& dst, cudaStream_t st, bool is_2d)
 {
   const int nc = int(chunks.size());
 
@@ -120,7 +120,7 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
 
   (void)any_wide;
   (void)any_owide;
-  b_.setup(chunks, true, false, false, st, false);
+  b_.setup(chunks, true, false, false, st, false, is_2d);
   for (int c = 0; c < nc; c++) {
     ChunkDev& d = b_.h[c];
     d.is_const = ps[c].is_const ? 1 : 0;
@@ -140,6 +140,7 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     j.skip = ps[c].is_const || ps[c].planes == 0;
     j.n = b_.h[c].n;
     j.shape = b_.h[c].shape;
+    j.kind = is_2d ? 2 : 0;
     j.d_payload = d_stream + ps[c].spk_off;
     j.payload_bytes = ps[c].spk_bytes;
     j.planes = ps[c].planes;
@@ -330,7 +331,7 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
         launch_dwt_fused_inverse(dst, 1, b_.dev(), ids, int(groups[s].size()), h.nx, h.ny, h.nz, 0.0,
                                  OutlierSink{}, cor, st);
       else
-        launch_dwt(true, b_.dev(), ids, int(groups[s].size()), h.nx, h.ny, h.nz, false, st);
+        launch_dwt(true, b_.dev(), ids, int(groups[s].size()), h.nx, h.ny, h.nz, is_2d, st);
     }
   }
 

@@ -59,8 +59,10 @@ __device__ __forceinline__ bool node_is_real(const ShapeDev& s, int L, unsigned 
 // 1. significance pyramid: p (msb of the max), D (expansion size), cmap (creation plane of pixels)
 // ---------------------------------------------------------------------------------------------
 
+// rev: the children are coded in reverse raster order (2D slices: BR, BL, TR, TL,
+// /root/reference/src/SPECK2D_INT.cpp:109-148)
 __global__ void k_pyr_level(const ChunkDev* chunks, const ShapeDev* shapes, const int* ids, int L,
-                            int check_real)
+                            int check_real, int rev)
 {
   const ChunkDev& ch = chunks[ids[blockIdx.y]];
   if (ch.is_const)
@@ -99,10 +101,11 @@ __global__ void k_pyr_level(const ChunkDev* chunks, const ShapeDev* shapes, cons
   if (pmax >= 0) {
     int sigc = 0;
     for (int k = 0; k < nch; k++) {
+      const int kk = rev ? nch - 1 - k : k;
       const bool need = sigc != 0 || k != nch - 1;
       D += need ? 1u : 0u;
-      if (pc[k] == pmax) {
-        D += dc[k];
+      if (pc[kk] == pmax) {
+        D += dc[kk];
         sigc++;
       }
     }
@@ -201,6 +204,165 @@ struct Tree3D {
 };
 
 // ---------------------------------------------------------------------------------------------
+// 3. tree policy of the 2D coder (SPECK2D_INT, /root/reference/src/SPECK2D_INT.cpp:10-218,
+//    src/SPECK2D_INT_ENC.cpp:7-121): quadtree S sets coded in reverse raster order, plus the set
+//    I_l = everything outside the approximation band of transform level l. I_l splits into
+//    BR, TR, BL of level l (always tested) and I_(l-1) (implied significant when none of the three
+//    was), and it is tested after all lists: it sorts behind every S set.
+//    I_l's p / D live behind the pyramid: pyr_p[pyr_nodes + l], pyr_d[pyr_nodes + l].
+// ---------------------------------------------------------------------------------------------
+
+constexpr int kINodeLevel = 0xFF;
+__device__ __forceinline__ bool is_inode(node_t nd) { return node_level(nd) == kINodeLevel; }
+
+// one thread per chunk: I_1 .. I_nxf bottom-up
+__global__ void k_pyr_iset(const ChunkDev* chunks, const ShapeDev* shapes, const int* ids, int nids)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nids)
+    return;
+  const ChunkDev& ch = chunks[ids[t]];
+  if (ch.is_const)
+    return;
+  const ShapeDev s = shapes[ch.shape];
+  const ShapeHeader* h = s.h;
+  int pi = -1;        // p of I_(l-1); I_0 is empty
+  unsigned di = 0;
+  for (int l = 1; l <= h->nxf2d; l++) {
+    const int L = h->lv2d[l];
+    const int cx[3] = {1, 1, 0}, cy[3] = {1, 0, 1};   // BR, TR, BL (src/SPECK2D_INT.cpp:150-185)
+    int pc[3], pmax = pi;
+    unsigned dc[3];
+    for (int k = 0; k < 3; k++) {
+      pc[k] = node_p(s, ch, L, cx[k], cy[k], 0);
+      dc[k] = node_d(s, ch, L, cx[k], cy[k], 0);
+      pmax = pc[k] > pmax ? pc[k] : pmax;
+    }
+    unsigned D = 0;
+    if (pmax >= 0) {
+      int sigc = 0;
+      for (int k = 0; k < 3; k++) {
+        D += 1;
+        if (pc[k] == pmax) {
+          D += dc[k];
+          sigc++;
+        }
+      }
+      if (l > 1) {
+        D += sigc != 0 ? 1u : 0u;
+        if (pi == pmax)
+          D += di;
+      }
+    }
+    ch.pyr_p[h->pyr_nodes + l] = int8_t(pmax);
+    ch.pyr_d[h->pyr_nodes + l] = D;
+    pi = pmax;
+    di = D;
+  }
+}
+
+struct Tree2D {
+  typedef Tree3D::Data Data;
+
+  static __device__ __forceinline__ void pd(const Data& t, const ChunkDev& ch, unsigned c, node_t nd,
+                                            int& p, unsigned& d)
+  {
+    if (is_inode(nd)) {
+      const ShapeHeader* h = t.shapes[ch.shape].h;
+      p = ch.pyr_p[h->pyr_nodes + node_ix(nd)];
+      d = ch.pyr_d[h->pyr_nodes + node_ix(nd)];
+      return;
+    }
+    Tree3D::pd(t, ch, c, nd, p, d);
+  }
+
+  static __device__ __forceinline__ void fill_set(const ShapeDev& s, const ChunkDev& ch, int L,
+                                                  unsigned jx, unsigned jy, ChildRec& r)
+  {
+    r.id = make_node(L, jx, jy, 0);
+    r.p = node_p(s, ch, L, jx, jy, 0);
+    unsigned lx, ly, lz;
+    node_len(s, L, jx, jy, 0, lx, ly, lz);
+    r.kind = (lx <= 2 && ly <= 2) ? 1 : 2;
+    r.d = node_d(s, ch, L, jx, jy, 0);
+    r.lis_desc = unsigned(s.h->nlis - 1 - s.h->lv[L].j);   // part_level = chain position
+    r.sign = 0;
+  }
+
+  // bit 8 of the result: every child is tested explicitly (no implied last child)
+  static __device__ __forceinline__ int children(const Data& t, const ChunkDev& ch, unsigned c,
+                                                 node_t nd, ChildRec* out)
+  {
+    const ShapeDev s = t.shapes[ch.shape];
+    const ShapeHeader* h = s.h;
+    if (is_inode(nd)) {
+      const int l = int(node_ix(nd));
+      const int L = h->lv2d[l];
+      fill_set(s, ch, L, 1, 1, out[0]);
+      fill_set(s, ch, L, 1, 0, out[1]);
+      fill_set(s, ch, L, 0, 1, out[2]);
+      if (l == 1)
+        return 3 | 0x100;
+      ChildRec& r = out[3];
+      r.id = make_node(kINodeLevel, unsigned(l - 1), 0, 0);
+      r.p = ch.pyr_p[h->pyr_nodes + l - 1];
+      r.d = ch.pyr_d[h->pyr_nodes + l - 1];
+      r.kind = 2;
+      r.lis_desc = unsigned(h->nlis);   // behind list 0
+      r.sign = 0;
+      return 4;
+    }
+    NodeGeom g;
+    node_geom(s, nd, g);
+    int k = 0;
+    for (int cy = int(g.nyc) - 1; cy >= 0; cy--)
+      for (int cx = int(g.nxc) - 1; cx >= 0; cx--, k++) {
+        const unsigned jx = g.x0 + cx, jy = g.y0 + cy;
+        ChildRec& r = out[k];
+        unsigned lx, ly, lz;
+        node_len(s, g.Lc, jx, jy, 0, lx, ly, lz);
+        if (lx * ly == 1) {
+          r.id = make_node(g.Lc, jx, jy, 0);
+          r.p = node_p(s, ch, g.Lc, jx, jy, 0);
+          r.kind = 0;
+          r.d = 0;
+          r.lis_desc = 0;
+          const unsigned long long ri = node_raster(s, g.Lc, jx, jy, 0);
+          r.sign = (ch.signs[ri >> 5] >> (ri & 31)) & 1u;
+        }
+        else
+          fill_set(s, ch, g.Lc, jx, jy, r);
+      }
+    return k;
+  }
+
+  static __device__ __forceinline__ int planes(const Data& t, const ChunkDev& ch, unsigned c)
+  {
+    return Tree3D::planes(t, ch, c);
+  }
+
+  static __device__ __forceinline__ int num_roots(const Data& t, const ChunkDev& ch, unsigned)
+  {
+    return t.shapes[ch.shape].h->nxf2d > 0 ? 2 : 1;
+  }
+
+  static __device__ __forceinline__ void root(const Data& t, const ChunkDev& ch, unsigned, int r,
+                                              node_t& nd, unsigned& lis_desc, unsigned& order)
+  {
+    const ShapeHeader* h = t.shapes[ch.shape].h;
+    order = 0;
+    if (r == 0) {
+      nd = make_node(h->lv2d[h->nxf2d], 0, 0, 0);
+      lis_desc = unsigned(h->nlis - 1 - h->nxf2d);
+    }
+    else {
+      nd = make_node(kINodeLevel, unsigned(h->nxf2d), 0, 0);
+      lis_desc = unsigned(h->nlis);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // host driver
 // ---------------------------------------------------------------------------------------------
 
@@ -229,6 +391,7 @@ void Speck3DEncoder::encode(ChunkDev* d_chunks, const std::vector<ChunkDev>& h_c
   }
   size_t id_off = 0;
   int max_depth = 1;
+  bool any_2d = false, any_3d = false;
   rt::ProfScope* ps_pyr = new rt::ProfScope("enc.pyramid", st);
   for (size_t si = 0; si < shapes.size(); si++) {
     const auto& g = groups[si];
@@ -244,14 +407,24 @@ void Speck3DEncoder::encode(ChunkDev* d_chunks, const std::vector<ChunkDev>& h_c
         max_depth = std::max(max_depth, h.lv[l].j + 2);
       }
     std::sort(order.begin(), order.end(), [&](int a, int b) { return h.lv[a].j > h.lv[b].j; });
-    const int check_real = h.dyadic < 0 ? 1 : 0;
+    const int check_real = (h.dyadic < 0 && !h.is2d) ? 1 : 0;
     for (int l : order) {
       const size_t nodes = (size_t)h.lv[l].cx * h.lv[l].cy * h.lv[l].cz;
       LAUNCH(k_pyr_level, dim3(unsigned((nodes + 255) / 256), unsigned(g.size())), dim3(256), 0, st,
-             d_chunks, d_shapes, d_ids, l, check_real);
+             d_chunks, d_shapes, d_ids, l, check_real, h.is2d);
     }
+    if (h.is2d) {
+      LAUNCH(k_pyr_iset, dim3(unsigned((g.size() + 63) / 64)), dim3(64), 0, st, d_chunks, d_shapes, d_ids,
+             int(g.size()));
+      max_depth += h.nxf2d + 1;
+      any_2d = true;
+    }
+    else
+      any_3d = true;
   }
   delete ps_pyr;
+  if (any_2d && any_3d)
+    throw std::runtime_error("2D and 3D chunks in one batch");
   Tree3D::Data tree{d_shapes};
   auto bound = [&](int c, const ChunkDev& hc) {
     const ShapeHeader& h = shapes[h_chunks[c].shape].h;
@@ -261,7 +434,10 @@ void Speck3DEncoder::encode(ChunkDev* d_chunks, const std::vector<ChunkDev>& h_c
       bits = std::min(bits, hc.budget + 3 * hc.n + h.set_nodes + 64);
     return bits;
   };
-  run_encoder<Tree3D>(work_, d_chunks, nchunks, max_n, tree, cap_nodes, max_depth, bound, results, st);
+  if (any_2d)
+    run_encoder<Tree2D>(work_, d_chunks, nchunks, max_n, tree, cap_nodes, max_depth, bound, results, st);
+  else
+    run_encoder<Tree3D>(work_, d_chunks, nchunks, max_n, tree, cap_nodes, max_depth, bound, results, st);
 }
 
 }  // namespace sperr_b200

@@ -12,6 +12,9 @@ namespace sperr_b200 {
 
 struct DecTree3D {
   static constexpr int kKind = 0;
+  static constexpr bool kHasI = false;
+  template <class D>
+  static __device__ __forceinline__ node_t iset(const D&, const DecChunk&, unsigned) { return 0; }
   struct Data {
     const ShapeDev* shapes;
   };
@@ -75,12 +78,83 @@ struct DecTree3D {
 };
 
 
+// 2D slices: quadtree in reverse raster order plus the set I (SPECK2D_INT,
+// /root/reference/src/SPECK2D_INT.cpp:60-213, src/SPECK2D_INT_DEC.cpp:5-52). I at part_level l is
+// node (level 0xFF, ix = l); its list index is -1 (it lives outside the lists).
+struct DecTree2D {
+  static constexpr int kKind = 2;
+  static constexpr bool kHasI = true;
+  typedef DecTree3D::Data Data;
+  static constexpr int kINode = 0xFF;
+
+  static __device__ __forceinline__ node_t iset(const Data& t, const DecChunk& d, unsigned)
+  {
+    const int l = t.shapes[d.shape].h->nxf2d;
+    return l > 0 ? make_node(kINode, unsigned(l), 0, 0) : 0;
+  }
+  static __device__ __forceinline__ int num_roots(const Data&, const DecChunk&, unsigned) { return 1; }
+  static __device__ __forceinline__ void root(const Data& t, const DecChunk& d, unsigned, int,
+                                              node_t& nd, int& lis)
+  {
+    const ShapeHeader* h = t.shapes[d.shape].h;
+    nd = make_node(h->lv2d[h->nxf2d], 0, 0, 0);
+    lis = h->nxf2d;
+  }
+  static __device__ __forceinline__ void fill(const ShapeDev& s, int L, unsigned jx, unsigned jy,
+                                              DChild& r)
+  {
+    unsigned lx, ly, lz;
+    node_len(s, L, jx, jy, 0, lx, ly, lz);
+    if (lx * ly == 1) {
+      r.pixel = 1;
+      r.id = 0;
+      r.lis = 0;
+      r.idx = node_raster(s, L, jx, jy, 0);
+    }
+    else {
+      r.pixel = 0;
+      r.id = make_node(L, jx, jy, 0);
+      r.idx = 0;
+      r.lis = s.h->lv[L].j;   // part_level = chain position
+    }
+  }
+  static __device__ __forceinline__ int children(const Data& t, const DecChunk& d, unsigned,
+                                                 node_t nd, int, DChild* out)
+  {
+    const ShapeDev s = t.shapes[d.shape];
+    const ShapeHeader* h = s.h;
+    if (node_level(nd) == kINode) {
+      const int l = int(node_ix(nd));
+      const int L = h->lv2d[l];
+      fill(s, L, 1, 1, out[0]);   // BR, TR, BL (src/SPECK2D_INT.cpp:150-185)
+      fill(s, L, 1, 0, out[1]);
+      fill(s, L, 0, 1, out[2]);
+      if (l == 1)
+        return 3 | 0x100;
+      out[3].pixel = 0;
+      out[3].id = make_node(kINode, unsigned(l - 1), 0, 0);
+      out[3].idx = 0;
+      out[3].lis = -1;
+      return 4;
+    }
+    NodeGeom g;
+    node_geom(s, nd, g);
+    int k = 0;
+    for (int cy = int(g.nyc) - 1; cy >= 0; cy--)
+      for (int cx = int(g.nxc) - 1; cx >= 0; cx--, k++)
+        fill(s, g.Lc, g.x0 + cx, g.y0 + cy, out[k]);
+    return k;
+  }
+};
+
 // node = start | len << 32 ; list index = depth of the set (the two initial halves are depth 1)
 struct DecTree1D {
   static constexpr int kKind = 1;
+  static constexpr bool kHasI = false;
   struct Data {
     int unused;
   };
+  static __device__ __forceinline__ node_t iset(const Data&, const DecChunk&, unsigned) { return 0; }
   static __device__ __forceinline__ int num_roots(const Data&, const DecChunk&, unsigned) { return 2; }
   static __device__ __forceinline__ void root(const Data&, const DecChunk& d, unsigned, int r,
                                               node_t& nd, int& lis)
@@ -145,7 +219,7 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
   if (nj == 0)
     return;
   size_t mask_words = 0, lis_entries = 0, cnt_entries = 0, stage_words = 0, pl_bytes = 0;
-  bool any_fast = false, any_slow3 = false, any_slow1 = false;
+  bool any_fast = false, any_slow3 = false, any_slow1 = false, any_slow2 = false;
   std::vector<size_t> mw(nj), sw(nj);
   w.max_n = 0;
   w.max_planes = 0;
@@ -159,7 +233,7 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
     cnt_entries += j.skip ? 0 : size_t(j.nlis + 1);
     stage_words += sw[c];
     if (!j.skip) {
-      (j.pow2 ? any_fast : (j.kind == 0 ? any_slow3 : any_slow1)) = true;
+      (j.pow2 ? any_fast : (j.kind == 0 ? any_slow3 : (j.kind == 2 ? any_slow2 : any_slow1))) = true;
       w.max_n = std::max<size_t>(w.max_n, j.n);
       w.max_planes = std::max(w.max_planes, j.planes);
       if (j.planes > kMaxPlanes)
@@ -237,6 +311,8 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
     rt::ProfScope ps("dec.speck_decode", st);
     if (any_slow3)
       LAUNCH(k_speck_decode<DecTree3D>, dim3(nj), dim3(kDecThreads), 0, st, dch, DecTree3D::Data{d_shapes});
+    if (any_slow2)
+      LAUNCH(k_speck_decode<DecTree2D>, dim3(nj), dim3(kDecThreads), 0, st, dch, DecTree2D::Data{d_shapes});
     if (any_slow1)
       LAUNCH(k_speck_decode<DecTree1D>, dim3(nj), dim3(kDecThreads), 0, st, dch, DecTree1D::Data{0});
     if (any_fast) {

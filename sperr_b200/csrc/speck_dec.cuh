@@ -18,6 +18,8 @@
 //   static __device__ int  T::roots(data, dc, c, r, node_t& nd, int& lis)    r-th initial set
 //   static __device__ int  T::num_roots(data, dc, c)
 //   static __device__ int  T::children(data, dc, c, node, lis, DChild out[8])
+//     (number of children; | 0x100 when even the last child is tested explicitly)
+//   T::kHasI / T::iset(data, dc, c): 2D only, the initial set I (0: none); a child with lis < 0 is I
 #pragma once
 
 #include "speck_dec.h"
@@ -322,6 +324,7 @@ constexpr int kDecMaxDepth = 48;
 struct DecFrame {
   DChild kid[8];
   int nch, k, sigc;
+  int all_tested;   // even the last child has its own significance bit (2D: last split of set I)
 };
 
 template <class T>
@@ -330,7 +333,11 @@ __device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c
                            unsigned long long& knew, int n_plane)
 {
   int depth = 0;
-  stack[0].nch = T::children(tree, d, c, root, root_lis, stack[0].kid);
+  {
+    const int nf = T::children(tree, d, c, root, root_lis, stack[0].kid);
+    stack[0].nch = nf & 0xff;
+    stack[0].all_tested = nf >> 8;
+  }
   stack[0].k = 0;
   stack[0].sigc = 0;
   while (depth >= 0) {
@@ -341,7 +348,7 @@ __device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c
     }
     const DChild ch = f.kid[f.k];
 
-    const bool need = f.sigc != 0 || f.k != f.nch - 1;
+    const bool need = f.sigc != 0 || f.k != f.nch - 1 || f.all_tested;
     f.k++;
     const unsigned sig = need ? br.get() : 1u;
     if (ch.pixel) {
@@ -364,11 +371,15 @@ __device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c
         return;
       }
       DecFrame& g = stack[depth + 1];
-      g.nch = T::children(tree, d, c, ch.id, ch.lis, g.kid);
+      const int nf = T::children(tree, d, c, ch.id, ch.lis, g.kid);
+      g.nch = nf & 0xff;
+      g.all_tested = nf >> 8;
       g.k = 0;
       g.sigc = 0;
       depth++;
     }
+    else if (T::kHasI && ch.lis < 0)
+      d.iset = ch.id;   // the set I stays outside the lists: it is tested after all of them
     else {
       const unsigned slot = d.lis_cnt[ch.lis];
       if (d.lis_off[ch.lis] + slot >= d.lis_off[ch.lis + 1]) {
@@ -406,6 +417,15 @@ __device__ void dec_lis_walk(DecChunk& d, const typename T::Data& tree, unsigned
     }
     d.lis_cnt[lev] = w;
   }
+  if (T::kHasI && d.iset) {   // SPECK2D_INT::m_sorting_pass, third step (src/SPECK2D_INT.cpp:54-57)
+    if (br.get()) {
+      const node_t nd = d.iset;
+      d.iset = 0;
+      dec_expand<T>(d, tree, c, br, nd, -1, stack, klip, knew, n_plane);
+      if (d.err)
+        return;
+    }
+  }
   S.pos = br.pos;
   S.klip = klip;
   S.knew = knew;
@@ -432,6 +452,7 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
     S.endpos = 0;
     for (int l = 0; l < d.nlis; l++)
       d.lis_cnt[l] = 0;
+    d.iset = T::kHasI ? T::iset(tree, d, c) : 0;
     const int nr = T::num_roots(tree, d, c);
     for (int r = 0; r < nr; r++) {
       node_t nd;

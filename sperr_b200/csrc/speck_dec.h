@@ -28,7 +28,8 @@ struct DecChunk {
   int skip;                      // nothing to decode (constant chunk, or no stream)
   unsigned long long n;          // number of coefficients
   int shape;                     // 3D: index into the shape tables
-  int kind;                      // 0: 3D coefficient stream, 1: 1D outlier stream
+  int kind;                      // 0: 3D coefficient stream, 1: 1D outlier stream, 2: 2D slice
+  node_t iset;                   // 2D: the live set I (0: none)
   uint8_t* pl;                   // n bytes, 0xFF on entry: plane of significance | negative << 7
   uint32_t* lip;                 // LIP mask, all zero on entry
   uint32_t* sigarr;              // scratch of the LIP pass (ceil(n / 32) + 2 words each)
@@ -58,7 +59,7 @@ struct DecChunk {
 struct DecJob {
   unsigned long long n = 0;
   int shape = 0;
-  int kind = 0;   // 0: 3D coefficient stream, 1: 1D outlier stream
+  int kind = 0;   // 0: 3D coefficient stream, 1: 1D outlier stream, 2: 2D slice (SPECK2D)
   bool skip = true;
   const unsigned char* d_payload = nullptr;   // device pointer: bytes after the 9-byte header
   unsigned long long payload_bytes = 0;

@@ -3,6 +3,7 @@
 //   struct T::Data                                             device pointers describing the tree
 //   static __device__ void  T::pd(data, chunk, c, node, int& p, unsigned& d)
 //   static __device__ int   T::children(data, chunk, c, node, ChildRec out[8])
+//     (number of children; | 0x100 when even the last child is tested explicitly)
 // where p = msb position of the largest magnitude below the node (-1: all zero) and d = number of
 // bits the node's depth-first expansion emits in the plane it turns significant.
 #pragma once
@@ -354,10 +355,12 @@ __global__ void k_expand(EncCtx ctx, typename T::Data tree, int src)
     const ChunkDev& ch = ctx.chunks[c];
     const int n = ch.cur_n;
     ChildRec kid[8];
-    const int nch = T::children(tree, ch, c, nd, kid);
+    const int nchf = T::children(tree, ch, c, nd, kid);
+    const int nch = nchf & 0xff;
+    const bool all_tested = (nchf & 0x100) != 0;   // 2D: last split of the set I
     int sigc = 0;
     for (int k = 0; k < nch; k++) {
-      const bool need = sigc != 0 || k != nch - 1;
+      const bool need = sigc != 0 || k != nch - 1 || all_tested;
       const bool sig = !need || kid[k].p == n;
       if (need) {
         put_bit(ch.spk, cur, sig);
@@ -374,7 +377,7 @@ __global__ void k_expand(EncCtx ctx, typename T::Data tree, int src)
         sigc++;
         if (kid[k].kind == 1) {  // all grandchildren are pixels: finish them here
           ChildRec g[8];
-          const int ng = T::children(tree, ch, c, kid[k].id, g);
+          const int ng = T::children(tree, ch, c, kid[k].id, g) & 0xff;
           int gs = 0;
           for (int j = 0; j < ng; j++) {
             const bool gneed = gs != 0 || j != ng - 1;

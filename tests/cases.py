@@ -96,3 +96,52 @@ def check_decomp3d(lib, oracle, stream, output_float=True):
     assert np.array_equal(got.view(it), exp.view(it)), "%d values differ" % int(
         np.count_nonzero(got.view(it) != exp.view(it)))
     return got
+
+
+# ---- 2D slices (sperr_comp_2d / sperr_decomp_2d): (dims, mode, quality, dtype) ----
+# fields: a z-plane of refs.synthetic_field (seed 7) cropped to dims, or a golden fixture by name
+SLICE_SMALL = [
+    ((64, 64), 3, 1e-3, np.float32),
+    ((90, 90), 3, 1e-4, np.float32),      # non power of two, 4 transform levels
+    ((15, 15), 2, 70.0, np.float32),      # 1 level
+    ((8, 8), 3, 1e-2, np.float32),        # no transform: the set I is empty
+    ((128, 40), 1, 3.0, np.float32),      # x and y run out of splits at different depths
+    ((40, 128), 2, 60.0, np.float64),
+    ((33, 70), 1, 20.0, np.float32),      # fixed rate, high-precision retry likely
+    ((1, 50), 3, 1e-3, np.float32),       # a single column
+]
+SLICE_GPU = SLICE_SMALL + [
+    ((512, 512), 3, 1e-3, np.float32),
+    ((1000, 300), 2, 90.0, np.float32),
+    ((2048, 2048), 3, 1e-3, np.float32),
+    ((256, 256), 1, 1.0, np.float64),
+]
+
+
+def slice_id(c):
+    return "slice%dx%d-m%d-%g-%s" % (c[0][0], c[0][1], c[1], c[2], np.dtype(c[3]).name)
+
+
+def slice_field(dims, dtype, seed=7, nslices=1):
+    v = refs.synthetic_field((dims[0], dims[1], nslices), seed=seed, dtype=np.float32)
+    return np.ascontiguousarray(v.reshape(nslices, dims[1], dims[0]).astype(dtype))
+
+
+def check_slice(lib, oracle, case):
+    """sperr_comp_2d bytes (with and without header) and sperr_decomp_2d bits equal the oracle's"""
+    dims, mode, q, dt = case
+    img = slice_field(dims, dt)[0]
+    for header in (False, True):
+        rc, got = lib.comp_2d(img, dims, mode, q, header)
+        rc2, exp = oracle.comp_2d(img, dims, mode, q, header)
+        assert rc == rc2 == 0, (rc, rc2)
+        assert got.size == exp.size, (got.size, exp.size)
+        assert np.array_equal(got, exp), "first diff at byte %d" % int(np.argmax(got != exp))
+    rc, exp = oracle.comp_2d(img, dims, mode, q, False)
+    for of in (True, False):
+        rc, dec = lib.decomp_2d(exp, dims, of)
+        rc2, dexp = oracle.decomp_2d(exp, dims, of)
+        assert rc == rc2 == 0, (rc, rc2)
+        it = np.uint32 if of else np.uint64
+        assert np.array_equal(dec.view(it), dexp.view(it)), "%d values differ" % int(
+            np.count_nonzero(dec.view(it) != dexp.view(it)))

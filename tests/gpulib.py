@@ -160,6 +160,89 @@ class Lib:
         return 0, out, (dx.value, dy.value, dz.value)
 
 
+    # ---- 2D slices ----
+    def stage_speck2d_encode(self, mags, signs, dims, budget_bits=0):
+        mags = np.ascontiguousarray(mags, dtype=np.uint64)
+        signs = np.ascontiguousarray(signs, dtype=np.uint8)
+        cap = mags.size * 10 + 64
+        out = np.zeros(cap, dtype=np.uint8)
+        n = sz(0)
+        f = self.lib.sperr_b200_stage_speck2d_encode
+        f.restype = C.c_int
+        f.argtypes = [vp, vp, sz, sz, sz, vp, sz, C.POINTER(sz)]
+        rc = f(_ptr(mags), _ptr(signs), dims[0], dims[1], budget_bits, _ptr(out), cap, C.byref(n))
+        assert rc == 0, rc
+        return out[:n.value].copy()
+
+    def comp_2d(self, img, dims, mode, quality, header=False):
+        img = np.ascontiguousarray(img)
+        f = self.lib.sperr_comp_2d
+        f.restype = C.c_int
+        f.argtypes = [vp, C.c_int, sz, sz, C.c_int, C.c_double, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+        dst = vp(None)
+        n = sz(0)
+        rc = f(_ptr(img), int(img.dtype == np.float32), dims[0], dims[1], mode, quality, int(header),
+               C.byref(dst), C.byref(n))
+        if rc != 0:
+            return rc, None
+        out = np.frombuffer(C.string_at(dst.value, n.value), dtype=np.uint8).copy()
+        _libc.free(dst)
+        return 0, out
+
+    def decomp_2d(self, stream, dims, output_float=True):
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        f = self.lib.sperr_decomp_2d
+        f.restype = C.c_int
+        f.argtypes = [vp, sz, C.c_int, sz, sz, C.POINTER(vp)]
+        dst = vp(None)
+        rc = f(_ptr(stream), stream.size, int(output_float), dims[0], dims[1], C.byref(dst))
+        if rc != 0:
+            return rc, None
+        dt = np.float32 if output_float else np.float64
+        n = dims[0] * dims[1]
+        out = np.frombuffer(C.string_at(dst.value, n * np.dtype(dt).itemsize), dtype=dt).copy()
+        _libc.free(dst)
+        return 0, out
+
+    def comp_2d_batch(self, imgs, dims, mode, quality, header=False):
+        """imgs: (nslices, dimy, dimx) array -> list of per-slice streams"""
+        imgs = np.ascontiguousarray(imgs)
+        ns = imgs.size // (dims[0] * dims[1])
+        f = self.lib.sperr_b200_comp_2d_batch
+        f.restype = C.c_int
+        f.argtypes = [vp, C.c_int, sz, sz, sz, C.c_int, C.c_double, C.c_int, C.POINTER(vp), vp]
+        dst = vp(None)
+        lens = np.zeros(ns, dtype=np.uint64)
+        rc = f(_ptr(imgs), int(imgs.dtype == np.float32), dims[0], dims[1], ns, mode, quality,
+               int(header), C.byref(dst), _ptr(lens))
+        if rc != 0:
+            return rc, None
+        total = int(lens.sum())
+        buf = np.frombuffer(C.string_at(dst.value, total), dtype=np.uint8).copy()
+        _libc.free(dst)
+        out, off = [], 0
+        for l in lens:
+            out.append(buf[off:off + int(l)])
+            off += int(l)
+        return 0, out
+
+    def decomp_2d_batch(self, streams, dims, output_float=True):
+        lens = np.array([s.size for s in streams], dtype=np.uint64)
+        buf = np.ascontiguousarray(np.concatenate(streams), dtype=np.uint8)
+        f = self.lib.sperr_b200_decomp_2d_batch
+        f.restype = C.c_int
+        f.argtypes = [vp, vp, sz, C.c_int, sz, sz, C.POINTER(vp)]
+        dst = vp(None)
+        rc = f(_ptr(buf), _ptr(lens), len(streams), int(output_float), dims[0], dims[1], C.byref(dst))
+        if rc != 0:
+            return rc, None
+        dt = np.float32 if output_float else np.float64
+        n = dims[0] * dims[1] * len(streams)
+        out = np.frombuffer(C.string_at(dst.value, n * np.dtype(dt).itemsize), dtype=dt).copy()
+        _libc.free(dst)
+        return 0, out.reshape(len(streams), dims[1], dims[0])
+
+
 def build_emul():
     subprocess.run([os.path.join(ROOT, "tests", "emul", "build.sh")], check=True,
                    stdout=subprocess.DEVNULL)
