@@ -42,6 +42,12 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
 /* Replaces C_API::sperr_parse_header (SPERR_C_API.h:74-82, src/SPERR_C_API.cpp:136-154). */
 void sperr_parse_header(const void* src, size_t* dimx, size_t* dimy, size_t* dimz, int* is_float);
 
+/* Replaces C_API::sperr_trunc_3d (SPERR_C_API.h:133-156, src/SPERR_C_API.cpp:260-281): keeps the
+ * first pct % of every chunk's stream (progressive access, SPERR3D_Stream_Tools.cpp:131-226) and
+ * marks the container as a portion. pct == 0 or >= 100 copies the stream. Host bytes only: needs no
+ * GPU. Returns 0 ok; 1 *dst not NULL; -1 malformed / short input. *dst is malloc'd. */
+int sperr_trunc_3d(const void* src, size_t src_len, unsigned pct, void** dst, size_t* dst_len);
+
 /* Replaces C_API::sperr_comp_2d (SPERR_C_API.h:33-60, src/SPERR_C_API.cpp:11-95): one 2D slice,
  * x fastest. out_inc_header != 0 prepends the 10-byte 2D header {version, flags, u32 dimx, u32 dimy}.
  * Returns 0 ok; 1 *dst not NULL; 2 bad parameter; -1 other error. *dst is malloc'd. */

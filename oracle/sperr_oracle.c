@@ -1984,3 +1984,75 @@ int so_decomp_2d(const void* src, size_t src_len, int output_float, size_t dimx,
     *dst = buf;
   return 0;
 }
+
+/* src/SPERR_C_API.cpp:260-281 over SPERR3D_Stream_Tools::progressive_truncate and
+ * m_progressive_helper (src/SPERR3D_Stream_Tools.cpp:131-226), extract_sections
+ * (src/sperr_helper.cpp:401-427) */
+int so_trunc_3d(const void* src, size_t src_len, unsigned pct, void** dst, size_t* dst_len)
+{
+  if (*dst != NULL)
+    return 1;
+  const uint8_t* p = (const uint8_t*)src;
+  if (src_len < 20)
+    return -1;
+  const int multi = (p[1] & 0x10) != 0;
+  uint32_t v3[3];
+  memcpy(v3, p + 2, 12);
+  size_t cd[3] = {v3[0], v3[1], v3[2]};
+  size_t pos = 14;
+  if (multi) {
+    uint16_t c3[3];
+    memcpy(c3, p + 14, 6);
+    cd[0] = c3[0]; cd[1] = c3[1]; cd[2] = c3[2];
+    pos = 20;
+  }
+  const size_t nchunks = so_chunk_volume(v3[0], v3[1], v3[2], cd[0], cd[1], cd[2], NULL, 0);
+  const size_t hlen = pos + 4 * nchunks;
+  if (src_len < hlen)
+    return -1;
+  size_t* off = (size_t*)malloc(nchunks * sizeof(size_t));
+  size_t* len = (size_t*)malloc(nchunks * sizeof(size_t));
+  size_t at = hlen, far = 0, total = hlen;
+  const int cut = pct != 0 && pct < 100;
+  for (size_t i = 0; i < nchunks; i++) {
+    uint32_t l;
+    memcpy(&l, p + pos + 4 * i, 4);
+    off[i] = at;
+    at += l;
+    size_t keep = l;
+    if (cut && keep > 64) {   /* m_progressive_min_chunk_bytes */
+      keep = (size_t)((double)pct / 100.0 * (double)keep);
+      if (keep < 64)
+        keep = 64;
+    }
+    len[i] = keep;
+    if (off[i] + keep > far)
+      far = off[i] + keep;
+    total += keep;
+  }
+  if (src_len < far) {
+    free(off);
+    free(len);
+    return -1;
+  }
+  uint8_t* o = (uint8_t*)malloc(total);
+  memcpy(o, p, hlen);
+  if (cut) {
+    o[0] = 0;
+    o[1] |= 0x80;
+    for (size_t i = 0; i < nchunks; i++) {
+      const uint32_t l = (uint32_t)len[i];
+      memcpy(o + pos + 4 * i, &l, 4);
+    }
+  }
+  size_t w = hlen;
+  for (size_t i = 0; i < nchunks; i++) {
+    memcpy(o + w, p + off[i], len[i]);
+    w += len[i];
+  }
+  free(off);
+  free(len);
+  *dst = o;
+  *dst_len = total;
+  return 0;
+}

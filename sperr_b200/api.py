@@ -54,6 +54,19 @@ class Library:
         L.sperr_b200_decomp_3d_dev.restype = C.c_int
         L.sperr_b200_decomp_3d_dev.argtypes = [vp, vp, sz, C.c_int, C.POINTER(sz), C.POINTER(sz),
                                                C.POINTER(sz), vp]
+        L.sperr_comp_2d.restype = C.c_int
+        L.sperr_comp_2d.argtypes = [vp, C.c_int, sz, sz, C.c_int, C.c_double, C.c_int, C.POINTER(vp),
+                                    C.POINTER(sz)]
+        L.sperr_decomp_2d.restype = C.c_int
+        L.sperr_decomp_2d.argtypes = [vp, sz, C.c_int, sz, sz, C.POINTER(vp)]
+        for name in ("sperr_b200_comp_2d_batch", "sperr_b200_comp_2d_batch_dev"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [vp, C.c_int, sz, sz, sz, C.c_int, C.c_double, C.c_int, C.POINTER(vp), vp]
+        L.sperr_b200_decomp_2d_batch.restype = C.c_int
+        L.sperr_b200_decomp_2d_batch.argtypes = [vp, vp, sz, C.c_int, sz, sz, C.POINTER(vp)]
+        L.sperr_b200_decomp_2d_batch_dev.restype = C.c_int
+        L.sperr_b200_decomp_2d_batch_dev.argtypes = [vp, vp, sz, C.c_int, sz, sz, vp]
         L.sperr_parse_header.restype = None
         L.sperr_parse_header.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz),
                                          C.POINTER(C.c_int)]
@@ -103,6 +116,66 @@ class Library:
                                                stream.size, int(output_float), C.byref(dx),
                                                C.byref(dy), C.byref(dz), vp(d_out_ptr))
         return rc, (dx.value, dy.value, dz.value)
+
+    # ---- 2D slices (sperr_comp_2d / sperr_decomp_2d, SPERR_C_API.h:33-72) ----
+    def compress_2d(self, img, dims, mode, quality, header=False):
+        """img: flat float32/float64 slice, x fastest. Returns (rc, uint8 stream or None)."""
+        img = np.ascontiguousarray(img)
+        if img.dtype not in (np.float32, np.float64):
+            raise TypeError("float32 or float64 input expected")
+        dst, n = vp(None), sz(0)
+        rc = self.lib.sperr_comp_2d(img.ctypes.data_as(vp), int(img.dtype == np.float32), dims[0],
+                                    dims[1], mode, quality, int(header), C.byref(dst), C.byref(n))
+        if rc != 0:
+            return rc, None
+        return 0, _adopt(dst, C.c_uint8, n.value, True)
+
+    def decompress_2d(self, stream, dims, output_float=True):
+        """stream: a slice stream WITHOUT the 10-byte header. Returns (rc, flat array or None)."""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        dst = vp(None)
+        rc = self.lib.sperr_decomp_2d(stream.ctypes.data_as(vp), stream.size, int(output_float),
+                                      dims[0], dims[1], C.byref(dst))
+        if rc != 0:
+            return rc, None
+        return 0, _adopt(dst, C.c_float if output_float else C.c_double, dims[0] * dims[1], True)
+
+    def compress_2d_batch(self, src, is_float, dims, nslices, mode, quality, header=False,
+                          device=False):
+        """src: host array of nslices contiguous slices, or (device=True) an integer device address.
+        Returns (rc, uint8 buffer of all streams back to back, uint64 lengths)."""
+        dst = vp(None)
+        lens = np.zeros(nslices, dtype=np.uint64)
+        if device:
+            f, ptr = self.lib.sperr_b200_comp_2d_batch_dev, vp(src)
+        else:
+            src = np.ascontiguousarray(src)
+            f, ptr = self.lib.sperr_b200_comp_2d_batch, src.ctypes.data_as(vp)
+        rc = f(ptr, int(is_float), dims[0], dims[1], nslices, mode, quality, int(header),
+               C.byref(dst), lens.ctypes.data_as(vp))
+        if rc != 0:
+            return rc, None, None
+        return 0, _adopt(dst, C.c_uint8, int(lens.sum()), False), lens
+
+    def decompress_2d_batch(self, streams, lens, dims, output_float=True, d_out_ptr=None):
+        """streams: uint8 buffer of headerless slice streams back to back; lens: their lengths.
+        Returns (rc, flat array) or, with d_out_ptr (device buffer), (rc, None)."""
+        streams = np.ascontiguousarray(streams, dtype=np.uint8)
+        lens = np.ascontiguousarray(lens, dtype=np.uint64)
+        if d_out_ptr is not None:
+            rc = self.lib.sperr_b200_decomp_2d_batch_dev(streams.ctypes.data_as(vp),
+                                                         lens.ctypes.data_as(vp), lens.size,
+                                                         int(output_float), dims[0], dims[1],
+                                                         vp(d_out_ptr))
+            return rc, None
+        dst = vp(None)
+        rc = self.lib.sperr_b200_decomp_2d_batch(streams.ctypes.data_as(vp), lens.ctypes.data_as(vp),
+                                                 lens.size, int(output_float), dims[0], dims[1],
+                                                 C.byref(dst))
+        if rc != 0:
+            return rc, None
+        ct = C.c_float if output_float else C.c_double
+        return 0, _adopt(dst, ct, dims[0] * dims[1] * lens.size, False)
 
     def parse_header(self, stream):
         stream = np.ascontiguousarray(stream, dtype=np.uint8)

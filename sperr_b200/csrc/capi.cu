@@ -707,6 +707,75 @@ int sperr_decomp_2d(const void* src, size_t src_len, int output_float, size_t di
   return sperr_b200_decomp_2d_batch(src, &src_len, 1, output_float, dimx, dimy, dst);
 }
 
+// C_API::sperr_trunc_3d (/root/reference/src/SPERR_C_API.cpp:260-281) over
+// SPERR3D_Stream_Tools::progressive_truncate / m_progressive_helper
+// (src/SPERR3D_Stream_Tools.cpp:131-226): keep the first pct % of every chunk's stream (at least 64
+// bytes, or the whole chunk when it is shorter), flag the container as a portion. Host bytes only.
+int sperr_trunc_3d(const void* src, size_t src_len, unsigned pct, void** dst, size_t* dst_len)
+{
+  if (*dst != nullptr)
+    return 1;
+  const uint8_t* p = static_cast<const uint8_t*>(src);
+  if (!p || src_len < 20)   // the reference reads 20 header bytes unconditionally
+    return -1;
+  const bool multi = (p[1] & 0x10) != 0;
+  uint32_t v3[3];
+  std::memcpy(v3, p + 2, 12);
+  size_t vol[3] = {v3[0], v3[1], v3[2]}, cd[3] = {v3[0], v3[1], v3[2]};
+  size_t pos = 14;
+  if (multi) {
+    uint16_t c3[3];
+    std::memcpy(c3, p + 14, 6);
+    for (int i = 0; i < 3; i++)
+      cd[i] = c3[i];
+    pos = 20;
+  }
+  for (int i = 0; i < 3; i++)
+    if (vol[i] == 0 || cd[i] == 0)
+      return -1;
+  const size_t nchunks = chunk_volume(vol, cd).size();
+  const size_t hlen = pos + 4 * nchunks;
+  if (src_len < hlen)
+    return -1;
+  std::vector<size_t> off(nchunks), len(nchunks);
+  size_t at = hlen, far = 0, total = hlen;
+  const size_t min_bytes = 64;   // m_progressive_min_chunk_bytes
+  for (size_t i = 0; i < nchunks; i++) {
+    uint32_t l;
+    std::memcpy(&l, p + pos + 4 * i, 4);
+    off[i] = at;
+    at += l;
+    size_t keep = l;
+    if (pct != 0 && pct < 100 && keep > min_bytes)
+      keep = std::max(min_bytes, size_t(double(pct) / 100.0 * double(keep)));
+    len[i] = keep;
+    far = std::max(far, off[i] + keep);
+    total += keep;
+  }
+  if (src_len < far)
+    return -1;
+  uint8_t* o = static_cast<uint8_t*>(std::malloc(total));
+  if (!o)
+    return -1;
+  std::memcpy(o, p, hlen);
+  if (pct != 0 && pct < 100) {
+    o[0] = 0;       // SPERR_VERSION_MAJOR
+    o[1] |= 0x80;   // is_portion
+    for (size_t i = 0; i < nchunks; i++) {
+      const uint32_t l = uint32_t(len[i]);
+      std::memcpy(o + pos + 4 * i, &l, 4);
+    }
+  }
+  size_t w = hlen;
+  for (size_t i = 0; i < nchunks; i++) {
+    std::memcpy(o + w, p + off[i], len[i]);
+    w += len[i];
+  }
+  *dst = o;
+  *dst_len = total;
+  return 0;
+}
+
 void sperr_b200_prof_enable(int on)
 {
   rt::prof().on = on != 0;

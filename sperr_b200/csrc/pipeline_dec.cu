@@ -150,7 +150,18 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     j.d_lis_off = nullptr;
     j.lis_total = sh.h.lis_off[kMaxLis];
     const int J3 = std::max(sh.h.ax[0].D, std::max(sh.h.ax[1].D, sh.h.ax[2].D));
-    if (sh.h.pow2 && J3 >= 4 && !std::getenv("SPERR_B200_NO_FASTDEC")) {
+    auto is_pow2 = [](uint32_t v) { return v != 0 && (v & (v - 1)) == 0; };
+    if (is_2d && is_pow2(sh.h.nx) && is_pow2(sh.h.ny) && J3 >= 4 && sh.h.nxf2d >= 1 &&
+        !std::getenv("SPERR_B200_NO_FASTDEC")) {
+      // power-of-two slice: quadtree of aligned boxes + the set I, decoded by k_speck_decode_fast
+      j.pow2 = 1;
+      j.Dx = sh.h.ax[0].D; j.Dy = sh.h.ax[1].D; j.Dz = 0;
+      j.nx = sh.h.nx; j.ny = sh.h.ny;
+      j.nroots = 1;
+      j.roots[0] = (unsigned long long)sh.h.nxf2d << 32;   // the approximation band, index 0
+      j.nxf2d = sh.h.nxf2d;
+    }
+    else if (sh.h.pow2 && J3 >= 4 && !std::getenv("SPERR_B200_NO_FASTDEC")) {
       // power-of-two extents: every set is an aligned box, decoded by k_speck_decode_fast
       j.pow2 = 1;
       j.Dx = sh.h.ax[0].D; j.Dy = sh.h.ax[1].D; j.Dz = sh.h.ax[2].D;

@@ -286,6 +286,7 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
     d.Dx = j.Dx; d.Dy = j.Dy; d.Dz = j.Dz;
     d.nx = j.nx; d.ny = j.ny;
     d.nroots = j.nroots;
+    d.iset = node_t(j.nxf2d);   // fast 2D path: I's part_level (the generic kernel sets its own)
     for (int r = 0; r < j.nroots; r++)
       d.roots[r] = j.roots[r];
     max_words = std::max(max_words, sw[c]);

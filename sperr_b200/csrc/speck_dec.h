@@ -72,6 +72,7 @@ struct DecJob {
   unsigned nx = 0, ny = 0;
   int nroots = 0;
   unsigned long long roots[kMaxRoots] = {0};
+  int nxf2d = 0;   // 2D fast path: transform levels = initial part_level of the set I
 };
 
 struct DecWork {

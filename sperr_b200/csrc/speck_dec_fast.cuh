@@ -71,6 +71,10 @@ struct FastSmem {
   // geometry
   int Dx, Dy, Dz, J;
   unsigned nx, ny;
+  // 2D slices (SPECK2D_INT): children are coded in reverse raster order, a set's list index is its
+  // depth, and the set I (everything outside the approximation band of transform level iset) is
+  // tested after all lists; iset == 0: I is used up
+  int is2d, iset;
   // walker (thread 0) state, kept here so that it can be suspended between windows
   int wk_j;                 // depth of the list being visited
   unsigned wk_i, wk_w, wk_cnt;
@@ -106,7 +110,7 @@ struct FastSmem {
 
 __device__ __forceinline__ int f_lis(const FastSmem& F, int j)
 {
-  return min(j, F.Dx) + min(j, F.Dy) + min(j, F.Dz);
+  return F.is2d ? j : min(j, F.Dx) + min(j, F.Dy) + min(j, F.Dz);
 }
 __device__ __forceinline__ unsigned long long f_pack(const FastSmem& F, int j, unsigned ix, unsigned iy,
                                                      unsigned iz)
@@ -133,6 +137,8 @@ __device__ __forceinline__ void f_child(const FastSmem& F, int j, unsigned ix, u
                                         int k, unsigned& jx, unsigned& jy, unsigned& jz)
 {
   const int sx = j < F.Dx, sy = j < F.Dy, sz = j < F.Dz;
+  if (F.is2d)   // BR, BL, TR, TL (/root/reference/src/SPECK2D_INT.cpp:109-148)
+    k = (1 << (sx + sy + sz)) - 1 - k;
   jx = sx ? ix * 2 + (unsigned(k) & 1u) : ix;
   jy = sy ? iy * 2 + ((unsigned(k) >> sx) & 1u) : iy;
   jz = sz ? iz * 2 + ((unsigned(k) >> (sx + sy)) & 1u) : iz;
@@ -329,6 +335,10 @@ static __device__ void f_expand_pixels(const DecChunk& d, const FastSmem& F, uns
   const int nch = 1 << (sx + sy + sz);
   unsigned sigm, sgnm;
   f_pixels(F, q, nch, sigm, sgnm);
+  if (F.is2d) {   // masks are in coding order = reverse raster order
+    sigm = __brev(sigm) >> (32 - nch);
+    sgnm = __brev(sgnm) >> (32 - nch);
+  }
   nsig += unsigned(__popc(sigm));
   nlip += unsigned(nch - __popc(sigm));
   const unsigned x0 = sx ? ix * 2 : ix, y0 = sy ? iy * 2 : iy, z0 = sz ? iz * 2 : iz;
@@ -631,11 +641,16 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
   // the frame being expanded lives in registers; outer frames are parked in shared memory
   int j = 0, k = 0, sg = 0, nch = 0;
   unsigned ix = 0, iy = 0, iz = 0;
+  // frames of the set I (2D) carry depth kIFrame | part_level: three S children + I one level up
+  constexpr int kIFrame = 0x100;
+  auto frame_nch = [&F](int jj) {
+    return (jj & kIFrame) ? (((jj & 0xff) > 1) ? 4 : 3) : f_nch(F, jj);
+  };
   if (depth >= 0) {
     f_unpack(F, F.wk_node[depth], j, ix, iy, iz);
     k = F.wk_k[depth];
     sg = F.wk_sig[depth];
-    nch = f_nch(F, j);
+    nch = frame_nch(j);
   }
   node_t* const list = d.lis + F.off[f_lis(F, lj)];
   for (;;) {
@@ -665,7 +680,9 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
       f_unpack(F, nd, j, ix, iy, iz);
       k = 0;
       sg = 0;
-      nch = f_nch(F, j);
+      nch = frame_nch(j);
+      if (j & kIFrame)
+        F.iset = 0;   // I is being split; what is left of it is recorded below
       continue;
     }
     if (k == nch) {   // pop
@@ -674,21 +691,41 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
         f_unpack(F, F.wk_node[depth], j, ix, iy, iz);
         k = F.wk_k[depth];
         sg = F.wk_sig[depth];
-        nch = f_nch(F, j);
+        nch = frame_nch(j);
       }
       continue;
     }
     if (q + 1 >= unsigned(kFW) || ntok >= unsigned(kFTok))
       break;
-    const bool need = sg != 0 || k != nch - 1;
+    const bool is_i = (j & kIFrame) != 0;
+    const int il = j & 0xff;
+    // SPECK2D_INT::m_code_I (src/SPECK2D_INT.cpp:82-95): the three S sets are always tested; when
+    // I's last level is split nothing follows them
+    const bool need = sg != 0 || k != nch - 1 || (is_i && il == 1);
     const unsigned s = need ? f_bit(F, q++) : 1u;
     unsigned jx, jy, jz;
-    f_child(F, j, ix, iy, iz, k, jx, jy, jz);
+    int cj;
+    bool child_i = false;
+    if (!is_i) {
+      f_child(F, j, ix, iy, iz, k, jx, jy, jz);
+      cj = j + 1;
+    }
+    else if (k < 3) {   // BR, TR, BL of transform level il (src/SPECK2D_INT.cpp:150-185)
+      jx = k == 2 ? 0u : 1u;
+      jy = k == 1 ? 0u : 1u;
+      jz = 0;
+      cj = il;
+    }
+    else {
+      jx = jy = jz = 0;
+      cj = kIFrame | (il - 1);
+      child_i = true;
+    }
     k++;
     if (s) {
       sg = 1;
-      if (j + 1 == jC) {   // a size-C set: queue it and skip its bits
-        F.qc_node[ntok] = f_pack(F, j + 1, jx, jy, jz);
+      if (!child_i && cj == jC) {   // a size-C set: queue it and skip its bits
+        F.qc_node[ntok] = f_pack(F, cj, jx, jy, jz);
         F.qc_pos[ntok] = uint16_t(q);
         ntok++;
         q += F.bodyC[q];
@@ -698,21 +735,23 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
         F.wk_k[depth] = (unsigned char)k;
         F.wk_sig[depth] = 1;
         depth++;
-        j++;
+        j = cj;
         ix = jx; iy = jy; iz = jz;
         k = 0;
         sg = 0;
-        nch = f_nch(F, j);
+        nch = frame_nch(j);
       }
     }
+    else if (child_i)
+      F.iset = il - 1;   // stays outside the lists, tested again in the next plane
     else {
-      const int cl = f_lis(F, j + 1);
+      const int cl = f_lis(F, cj);
       const unsigned slot = F.cnt[cl];
       if (F.off[cl] + slot >= F.off[cl + 1]) {
         F.err |= 1u;
         break;
       }
-      d.lis[F.off[cl] + slot] = f_pack(F, j + 1, jx, jy, jz);
+      d.lis[F.off[cl] + slot] = f_pack(F, cj, jx, jy, jz);
       F.cnt[cl] = slot + 1;
     }
   }
@@ -739,13 +778,16 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
       return;
   }
   bool have_window = false;
-  for (int lj = F.J - 4; lj >= 1; lj--) {
-    const int lis = f_lis(F, lj);
-    const unsigned cnt = F.cnt[lis];
+  // lj == 0 (2D only): the set I, tested after all lists (src/SPECK2D_INT.cpp:54-57), as a
+  // one-entry pseudo list
+  for (int lj = max(F.J - 4, 0); lj >= (F.is2d ? 0 : 1); lj--) {
+    const bool iphase = lj == 0;
+    const int lis = f_lis(F, iphase ? 1 : lj);
+    const unsigned cnt = iphase ? (F.iset > 0 ? 1u : 0u) : F.cnt[lis];
     if (cnt == 0)
       continue;
     if (tid == 0) {
-      F.wk_j = lj;
+      F.wk_j = iphase ? 1 : lj;
       F.wk_i = 0;
       F.wk_w = 0;
       F.wk_cnt = cnt;
@@ -766,7 +808,7 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
       const unsigned nst = min(unsigned(kFRoots), cnt - first);
       __syncthreads();
       for (unsigned t = tid; t < nst; t += kDecThreads)
-        F.rs_node[t] = d.lis[F.off[lis] + first + t];
+        F.rs_node[t] = iphase ? ((unsigned long long)(0x100 | F.iset) << 32) : d.lis[F.off[lis] + first + t];
       if (tid == 0) {
         F.rs_first = first;
         F.rs_cnt = nst;
@@ -788,7 +830,7 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
       if (F.wk_depth < 0 && F.wk_i == cnt)
         break;
     }
-    if (tid == 0)
+    if (tid == 0 && !iphase)
       F.cnt[lis] = F.wk_w;   // survivors; the sets created in this plane went to deeper lists
     __syncthreads();
   }
@@ -815,6 +857,8 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     F.Dx = d.Dx; F.Dy = d.Dy; F.Dz = d.Dz;
     F.J = max(d.Dx, max(d.Dy, d.Dz));
     F.nx = d.nx; F.ny = d.ny;
+    F.is2d = d.kind == 2;
+    F.iset = d.kind == 2 ? int(d.iset) : 0;
     F.err = 0;
     F.nqa = F.nqb = F.nqc = 0;
     for (int k = 0; k < 8; k++)

@@ -109,6 +109,11 @@ SLICE_SMALL = [
     ((40, 128), 2, 60.0, np.float64),
     ((33, 70), 1, 20.0, np.float32),      # fixed rate, high-precision retry likely
     ((1, 50), 3, 1e-3, np.float32),       # a single column
+    # power-of-two slices take the decoder's fast path (quadtree of aligned boxes + set I)
+    ((16, 16), 3, 1e-3, np.float32),
+    ((128, 32), 2, 70.0, np.float32),
+    ((32, 256), 1, 4.0, np.float32),
+    ((256, 256), 3, 1e-4, np.float64),
 ]
 SLICE_GPU = SLICE_SMALL + [
     ((512, 512), 3, 1e-3, np.float32),

@@ -160,6 +160,20 @@ class Lib:
         return 0, out, (dx.value, dy.value, dz.value)
 
 
+    def trunc_3d(self, stream, pct):
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        f = self.lib.sperr_trunc_3d
+        f.restype = C.c_int
+        f.argtypes = [vp, sz, C.c_uint, C.POINTER(vp), C.POINTER(sz)]
+        dst = vp(None)
+        n = sz(0)
+        rc = f(_ptr(stream), stream.size, pct, C.byref(dst), C.byref(n))
+        if rc != 0:
+            return rc, None
+        out = np.frombuffer(C.string_at(dst.value, n.value), dtype=np.uint8).copy()
+        _libc.free(dst)
+        return 0, out
+
     # ---- 2D slices ----
     def stage_speck2d_encode(self, mags, signs, dims, budget_bits=0):
         mags = np.ascontiguousarray(mags, dtype=np.uint64)

@@ -221,6 +221,18 @@ class Coder:
         libc_free(dst)
         return 0, out, (dx.value, dy.value, dz.value)
 
+    def trunc_3d(self, stream, pct):
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        f = self._capi("trunc_3d"); f.restype = C.c_int
+        f.argtypes = [vp, sz, C.c_uint, C.POINTER(vp), C.POINTER(sz)]
+        dst = vp(None); n = sz(0)
+        rc = f(_ptr(stream), stream.size, pct, C.byref(dst), C.byref(n))
+        if rc != 0:
+            return rc, None
+        out = np.frombuffer(C.string_at(dst.value, n.value), dtype=np.uint8).copy()
+        libc_free(dst)
+        return 0, out
+
     def comp_2d(self, img, dims, mode, quality, header=False):
         img = np.ascontiguousarray(img)
         f = self._capi("comp_2d"); f.restype = C.c_int

@@ -94,3 +94,17 @@ def test_host_api_batched_overlap_path_512(lib):
     assert np.array_equal(out_host.view(np.uint32), d_out.cpu().numpy().view(np.uint32))
     assert np.max(np.abs(out_host.astype(np.float64) - v.astype(np.float64))) <= 1e-3 + 1.2e-7
     del os.environ["SPERR_B200_OVERLAP_MIN_CHUNKS"]
+
+
+@pytest.mark.parametrize("pct", [5, 30, 70])
+def test_decode_truncated_container(lib, oracle, pct):
+    """sperr_trunc_3d output (progressive access) decodes to the oracle's bits: truncated SPECK
+    streams, outlier streams dropped when incomplete (src/SPECK_FLT.cpp:92-106)"""
+    import refs
+    v = refs.load_test_data("vorticity.128_128_41")
+    rc, s = oracle.comp_3d(v, (128, 128, 41), (64, 64, 41), 3, 1e-5)
+    assert rc == 0
+    rc, t = lib.trunc_3d(s, pct)
+    rc2, t2 = oracle.trunc_3d(s, pct)
+    assert rc == rc2 == 0 and np.array_equal(t, t2)
+    cases.check_decomp3d(lib, oracle, t, True)
