@@ -337,18 +337,20 @@ def run_ours(args):
             assert rc == 0
             rc, o2, d2 = L.decompress_3d(s2, True, copy=False)
             assert rc == 0
-            return s2
+            nb = int(s2.size)
+            del o2, s2   # free() both results inside the step, as a C caller does before its next call
+            return nb
         e2e_step()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            s2 = e2e_step()
+            s2_bytes = e2e_step()
         torch.cuda.synchronize()
         dt = torch.tensor([(time.perf_counter() - t0) / args.steps], device=dev, dtype=torch.float64)
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         dt = float(dt.item())
         e2e = {"value": world * nbytes / dt / GB, "unit": "GB/s",
-               "h2d_bytes_per_step": nbytes + int(s2.size), "d2h_bytes_per_step": int(s2.size) + nbytes}
+               "h2d_bytes_per_step": nbytes + s2_bytes, "d2h_bytes_per_step": s2_bytes + nbytes}
 
     if args.e2e and world > 1:
         # same metric through the sharded public API with HOST boxes: every rank uploads its box
