@@ -204,6 +204,154 @@ struct Tree3D {
 };
 
 // ---------------------------------------------------------------------------------------------
+// 2b. the same tree for power-of-two dyadic chunks (the bench shape: 256^3): every set at depth j
+//     is an aligned box, so children, pyramid slots and list indices are shifts instead of table
+//     look-ups. Node ids carry the depth j (not the LevelDesc index): make_node(j, ix, iy, iz).
+// ---------------------------------------------------------------------------------------------
+
+struct Pow2Info {
+  int Dx, Dy, Dz, J, nlis;
+  unsigned nx, ny;
+  unsigned long long p_off[kMaxAxisDepth + 1];   // pyramid offset of depth j < J
+};
+
+__device__ __forceinline__ size_t pow2_lin(const Pow2Info& g, int j, unsigned ix, unsigned iy, unsigned iz)
+{
+  const int bx = min(j, g.Dx), by = min(j, g.Dy);
+  return ((size_t)iz << (bx + by)) | ((size_t)iy << bx) | ix;
+}
+
+__global__ void k_pyr_pow2(const ChunkDev* chunks, Pow2Info g, int j)
+{
+  const ChunkDev& ch = chunks[blockIdx.y];
+  if (ch.is_const)
+    return;
+  const int bx = min(j, g.Dx), by = min(j, g.Dy), bz = min(j, g.Dz);
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >> (bx + by + bz))
+    return;
+  const unsigned ix = unsigned(idx) & ((1u << bx) - 1u), iy = unsigned(idx >> bx) & ((1u << by) - 1u),
+                 iz = unsigned(idx >> (bx + by));
+  const int sx = j < g.Dx, sy = j < g.Dy, sz = j < g.Dz;
+  const int nch = 1 << (sx + sy + sz), cj = j + 1;
+  const bool leaf = cj == g.J;
+  int pc[8];
+  unsigned dc[8];
+  size_t cpos[8];
+  int pmax = -1;
+  for (int k = 0; k < nch; k++) {
+    const unsigned jx = sx ? ix * 2 + (unsigned(k) & 1u) : ix;
+    const unsigned jy = sy ? iy * 2 + ((unsigned(k) >> sx) & 1u) : iy;
+    const unsigned jz = sz ? iz * 2 + ((unsigned(k) >> (sx + sy)) & 1u) : iz;
+    if (leaf) {
+      cpos[k] = ((size_t)jz * g.ny + jy) * g.nx + jx;
+      pc[k] = ch.pleaf[cpos[k]];
+      dc[k] = 1u;
+    }
+    else {
+      cpos[k] = g.p_off[cj] + pow2_lin(g, cj, jx, jy, jz);
+      pc[k] = ch.pyr_p[cpos[k]];
+      dc[k] = ch.pyr_d[cpos[k]];
+    }
+    pmax = pc[k] > pmax ? pc[k] : pmax;
+  }
+  unsigned D = 0;
+  if (pmax >= 0) {
+    int sigc = 0;
+    for (int k = 0; k < nch; k++) {
+      const bool need = sigc != 0 || k != nch - 1;
+      D += need ? 1u : 0u;
+      if (pc[k] == pmax) {
+        D += dc[k];
+        sigc++;
+      }
+    }
+  }
+  ch.pyr_p[g.p_off[j] + idx] = int8_t(pmax);
+  ch.pyr_d[g.p_off[j] + idx] = D;
+  if (leaf && pmax >= 0)   // pixels born when this set splits enter the LIP at plane pmax
+    for (int k = 0; k < nch; k++)
+      ch.cmap[cpos[k]] = int8_t(pmax);
+}
+
+struct Tree3DPow2 {
+  struct Data {
+    const ShapeDev* shapes;
+    Pow2Info g;
+  };
+
+  static __device__ __forceinline__ void pd(const Data& t, const ChunkDev& ch, unsigned, node_t nd,
+                                            int& p, unsigned& d)
+  {
+    const Pow2Info& g = t.g;
+    const int j = node_level(nd);
+    if (j == g.J) {
+      p = ch.pleaf[((size_t)node_iz(nd) * g.ny + node_iy(nd)) * g.nx + node_ix(nd)];
+      d = 0;
+      return;
+    }
+    const size_t at = g.p_off[j] + pow2_lin(g, j, node_ix(nd), node_iy(nd), node_iz(nd));
+    p = ch.pyr_p[at];
+    d = ch.pyr_d[at];
+  }
+
+  static __device__ __forceinline__ int children(const Data& t, const ChunkDev& ch, unsigned,
+                                                 node_t nd, ChildRec* out)
+  {
+    const Pow2Info& g = t.g;
+    const int j = node_level(nd), cj = j + 1;
+    const unsigned ix = node_ix(nd), iy = node_iy(nd), iz = node_iz(nd);
+    const int sx = j < g.Dx, sy = j < g.Dy, sz = j < g.Dz;
+    const int nch = 1 << (sx + sy + sz);
+    const int kind = cj == g.J ? 0 : (cj == g.J - 1 ? 1 : 2);
+    const unsigned lis_desc = unsigned(g.nlis - 1 - (min(cj, g.Dx) + min(cj, g.Dy) + min(cj, g.Dz)));
+    for (int k = 0; k < nch; k++) {
+      const unsigned jx = sx ? ix * 2 + (unsigned(k) & 1u) : ix;
+      const unsigned jy = sy ? iy * 2 + ((unsigned(k) >> sx) & 1u) : iy;
+      const unsigned jz = sz ? iz * 2 + ((unsigned(k) >> (sx + sy)) & 1u) : iz;
+      ChildRec& r = out[k];
+      r.id = make_node(cj, jx, jy, jz);
+      r.kind = kind;
+      if (kind == 0) {
+        const size_t ri = ((size_t)jz * g.ny + jy) * g.nx + jx;
+        r.p = ch.pleaf[ri];
+        r.d = 0;
+        r.lis_desc = 0;
+        r.sign = (ch.signs[ri >> 5] >> (ri & 31)) & 1u;
+      }
+      else {
+        const size_t at = g.p_off[cj] + pow2_lin(g, cj, jx, jy, jz);
+        r.p = ch.pyr_p[at];
+        r.d = ch.pyr_d[at];
+        r.lis_desc = lis_desc;
+        r.sign = 0;
+      }
+    }
+    return nch;
+  }
+
+  static __device__ __forceinline__ int planes(const Data& t, const ChunkDev& ch, unsigned)
+  {
+    return int(ch.pyr_p[t.g.p_off[0]]) + 1;
+  }
+
+  static __device__ __forceinline__ int num_roots(const Data& t, const ChunkDev& ch, unsigned)
+  {
+    return t.shapes[ch.shape].h->nroots;
+  }
+
+  static __device__ __forceinline__ void root(const Data& t, const ChunkDev& ch, unsigned, int r,
+                                              node_t& nd, unsigned& lis_desc, unsigned& order)
+  {
+    const ShapeHeader* h = t.shapes[ch.shape].h;
+    const RootDesc& rd = h->roots[r];
+    nd = make_node(h->lv[rd.level].j, rd.ix, rd.iy, rd.iz);
+    lis_desc = unsigned(h->nlis - 1 - rd.lis);
+    order = unsigned(rd.order);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // 3. tree policy of the 2D coder (SPECK2D_INT, /root/reference/src/SPECK2D_INT.cpp:10-218,
 //    src/SPECK2D_INT_ENC.cpp:7-121): quadtree S sets coded in reverse raster order, plus the set
 //    I_l = everything outside the approximation band of transform level l. I_l splits into
@@ -392,6 +540,38 @@ void Speck3DEncoder::encode(ChunkDev* d_chunks, const std::vector<ChunkDev>& h_c
   size_t id_off = 0;
   int max_depth = 1;
   bool any_2d = false, any_3d = false;
+  auto bound = [&](int c, const ChunkDev& hc) {
+    const ShapeHeader& h = shapes[h_chunks[c].shape].h;
+    unsigned long long bits = hc.n * (unsigned long long)(hc.planes + 1) +
+                              h.set_nodes * (unsigned long long)hc.planes + 64;
+    if (hc.budget != ~0ull)
+      bits = std::min(bits, hc.budget + 3 * hc.n + h.set_nodes + 64);
+    return bits;
+  };
+  // one power-of-two dyadic shape for the whole batch: shift-addressed tree (Tree3DPow2)
+  if (shapes.size() == 1 && shapes[0].h.pow2 && !shapes[0].h.is2d && !std::getenv("SPERR_B200_NO_POW2ENC")) {
+    const ShapeHeader& h = shapes[0].h;
+    Tree3DPow2::Data tree;
+    tree.shapes = d_shapes;
+    Pow2Info& g = tree.g;
+    g.Dx = h.ax[0].D; g.Dy = h.ax[1].D; g.Dz = h.ax[2].D;
+    g.J = std::max(g.Dx, std::max(g.Dy, g.Dz));
+    g.nlis = h.nlis;
+    g.nx = h.nx; g.ny = h.ny;
+    for (int l = 0; l < h.nlevels; l++)
+      if (l != h.leaf_level && h.lv[l].chain == 0)
+        g.p_off[h.lv[l].j] = h.lv[l].p_off;
+    {
+      rt::ProfScope ps("enc.pyramid", st);
+      for (int j = g.J - 1; j >= 0; j--) {
+        const size_t nodes = size_t(1) << (std::min(j, g.Dx) + std::min(j, g.Dy) + std::min(j, g.Dz));
+        LAUNCH(k_pyr_pow2, dim3(unsigned((nodes + 255) / 256), unsigned(nchunks)), dim3(256), 0, st, d_chunks,
+               g, j);
+      }
+    }
+    run_encoder<Tree3DPow2>(work_, d_chunks, nchunks, max_n, tree, cap_nodes, g.J + 2, bound, results, st);
+    return;
+  }
   rt::ProfScope* ps_pyr = new rt::ProfScope("enc.pyramid", st);
   for (size_t si = 0; si < shapes.size(); si++) {
     const auto& g = groups[si];
@@ -426,14 +606,6 @@ void Speck3DEncoder::encode(ChunkDev* d_chunks, const std::vector<ChunkDev>& h_c
   if (any_2d && any_3d)
     throw std::runtime_error("2D and 3D chunks in one batch");
   Tree3D::Data tree{d_shapes};
-  auto bound = [&](int c, const ChunkDev& hc) {
-    const ShapeHeader& h = shapes[h_chunks[c].shape].h;
-    unsigned long long bits = hc.n * (unsigned long long)(hc.planes + 1) +
-                              h.set_nodes * (unsigned long long)hc.planes + 64;
-    if (hc.budget != ~0ull)
-      bits = std::min(bits, hc.budget + 3 * hc.n + h.set_nodes + 64);
-    return bits;
-  };
   if (any_2d)
     run_encoder<Tree2D>(work_, d_chunks, nchunks, max_n, tree, cap_nodes, max_depth, bound, results, st);
   else

@@ -85,6 +85,7 @@ struct FastSmem {
   unsigned wk_q;            // window position of the walker
   unsigned long long win_base;   // absolute bit position of the window
   unsigned long long rs_node[kFRoots];   // staged roots: entries [rs_first, rs_first + rs_cnt) of the list
+  uint32_t rs_gone[kFRoots / 32];        // staged roots that turned significant in this round
   unsigned rs_first, rs_cnt;
   int go;
   unsigned err;
@@ -627,87 +628,126 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
 
 // ---- phase B: larger sets, one thread walks the top of the tree ----------------------------------
 
-// Runs until the lists are exhausted (wk_done), the window or the token queue is used up, or the
-// staged roots of the current list have all been visited.
+// Runs until the list is exhausted, the window or the token queue is used up, or the staged roots of
+// the current list have all been visited. Roots that turn significant are only MARKED (rs_gone); the
+// survivors are compacted into the list by the whole CTA afterwards (f_compact_roots), so a run of
+// insignificant roots costs the walker one look at 32 bits, not one store per root.
+// MODE 0: 3D chunk, 1: 1D outlier array (binary tree), 2: 2D slice (reverse child order, set I).
+template <int MODE>
 static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
 {
+  // geometry in registers: the helpers below are the f_* functions without the shared-memory reads
+  const int Dx = F.Dx, Dy = MODE == 1 ? 0 : F.Dy, Dz = MODE == 0 ? F.Dz : 0;
+  const unsigned boff = F.boff;
+  constexpr int kIFrame = 0x100;   // frames of the set I (2D) carry depth kIFrame | part_level
+  auto bit_at = [&](unsigned qq) {
+    qq += boff;
+    return (F.bits[qq >> 5] >> (qq & 31)) & 1u;
+  };
+  auto peek_at = [&](unsigned qq) {
+    qq += boff;
+    return __funnelshift_r(F.bits[qq >> 5], F.bits[(qq >> 5) + 1], qq & 31);
+  };
+  auto nch_of = [&](int jj) {
+    if (MODE == 2 && (jj & kIFrame))
+      return ((jj & 0xff) > 1) ? 4 : 3;
+    if (MODE == 1)
+      return 2;
+    return 1 << (int(jj < Dx) + int(jj < Dy) + int(jj < Dz));
+  };
+  auto lis_of = [&](int jj) { return MODE == 0 ? min(jj, Dx) + min(jj, Dy) + min(jj, Dz) : jj; };
+  auto pack = [&](int jj, unsigned x, unsigned y, unsigned z) {
+    if (MODE == 1)
+      return ((unsigned long long)jj << 32) | x;
+    const int bx = min(jj, Dx), by = min(jj, Dy);
+    return ((unsigned long long)jj << 32) | (unsigned long long)(x | (y << bx) | (z << (bx + by)));
+  };
+  auto unpack = [&](unsigned long long nd, int& jj, unsigned& x, unsigned& y, unsigned& z) {
+    jj = int(nd >> 32);
+    const unsigned lin = unsigned(nd);
+    if (MODE == 1) {
+      x = lin; y = 0; z = 0;
+      return;
+    }
+    const int bx = min(jj, Dx), by = min(jj, Dy);
+    x = lin & ((1u << bx) - 1u);
+    y = (lin >> bx) & ((1u << by) - 1u);
+    z = MODE == 0 ? lin >> (bx + by) : 0u;
+  };
+
   unsigned q = F.wk_q;       // window position
   unsigned ntok = 0;
   int depth = F.wk_depth;
-  int lj = F.wk_j;
-  unsigned i = F.wk_i, w = F.wk_w;
+  unsigned i = F.wk_i;
   const unsigned cnt = F.wk_cnt;
+  const unsigned i_end = F.rs_first + F.rs_cnt;
   const int jC = F.J - 3;
   // the frame being expanded lives in registers; outer frames are parked in shared memory
   int j = 0, k = 0, sg = 0, nch = 0;
   unsigned ix = 0, iy = 0, iz = 0;
-  // frames of the set I (2D) carry depth kIFrame | part_level: three S children + I one level up
-  constexpr int kIFrame = 0x100;
-  auto frame_nch = [&F](int jj) {
-    return (jj & kIFrame) ? (((jj & 0xff) > 1) ? 4 : 3) : f_nch(F, jj);
-  };
   if (depth >= 0) {
-    f_unpack(F, F.wk_node[depth], j, ix, iy, iz);
+    unpack(F.wk_node[depth], j, ix, iy, iz);
     k = F.wk_k[depth];
     sg = F.wk_sig[depth];
-    nch = frame_nch(j);
+    nch = nch_of(j);
   }
-  node_t* const list = d.lis + F.off[f_lis(F, lj)];
   for (;;) {
     if (depth < 0) {
       if (i == cnt)
         break;   // list finished (the caller moves on to the next one)
-      if (q + 1 >= unsigned(kFW) || i >= F.rs_first + F.rs_cnt)
+      if (q + 1 >= unsigned(kFW) || i >= i_end)
         break;
       // roots coded as 0 stay in the list: skip a whole run of them at once
-      const unsigned room = min(min(32u, F.rs_first + F.rs_cnt - i), unsigned(kFW) - 1u - q);
-      unsigned u = f_peek(F, q);
+      const unsigned room = min(min(32u, i_end - i), unsigned(kFW) - 1u - q);
+      unsigned u = peek_at(q);
       if (room < 32)
         u &= (1u << room) - 1u;
       const unsigned run = u ? unsigned(__ffs(u) - 1) : room;
-      if (w != i)
-        for (unsigned x = 0; x < run; x++)
-          list[w + x] = F.rs_node[i - F.rs_first + x];
       i += run;
-      w += run;
       q += run;
       if (run == room)
         continue;
-      const node_t nd = F.rs_node[i - F.rs_first];
+      const unsigned r = i - F.rs_first;
+      F.rs_gone[r >> 5] |= 1u << (r & 31);
+      const node_t nd = F.rs_node[r];
       i++;
       q++;
       depth = 0;
-      f_unpack(F, nd, j, ix, iy, iz);
+      unpack(nd, j, ix, iy, iz);
       k = 0;
       sg = 0;
-      nch = frame_nch(j);
-      if (j & kIFrame)
+      nch = nch_of(j);
+      if (MODE == 2 && (j & kIFrame))
         F.iset = 0;   // I is being split; what is left of it is recorded below
       continue;
     }
     if (k == nch) {   // pop
       depth--;
       if (depth >= 0) {
-        f_unpack(F, F.wk_node[depth], j, ix, iy, iz);
+        unpack(F.wk_node[depth], j, ix, iy, iz);
         k = F.wk_k[depth];
         sg = F.wk_sig[depth];
-        nch = frame_nch(j);
+        nch = nch_of(j);
       }
       continue;
     }
     if (q + 1 >= unsigned(kFW) || ntok >= unsigned(kFTok))
       break;
-    const bool is_i = (j & kIFrame) != 0;
+    const bool is_i = MODE == 2 && (j & kIFrame) != 0;
     const int il = j & 0xff;
     // SPECK2D_INT::m_code_I (src/SPECK2D_INT.cpp:82-95): the three S sets are always tested; when
     // I's last level is split nothing follows them
     const bool need = sg != 0 || k != nch - 1 || (is_i && il == 1);
-    const unsigned s = need ? f_bit(F, q++) : 1u;
+    const unsigned s = need ? bit_at(q++) : 1u;
     unsigned jx, jy, jz;
     int cj;
     bool child_i = false;
     if (!is_i) {
-      f_child(F, j, ix, iy, iz, k, jx, jy, jz);
+      const int sx = j < Dx, sy = j < Dy, sz = j < Dz;
+      const int kk = MODE == 2 ? nch - 1 - k : k;   // 2D: BR, BL, TR, TL (src/SPECK2D_INT.cpp:109-148)
+      jx = sx ? ix * 2 + (unsigned(kk) & 1u) : ix;
+      jy = sy ? iy * 2 + ((unsigned(kk) >> sx) & 1u) : iy;
+      jz = sz ? iz * 2 + ((unsigned(kk) >> (sx + sy)) & 1u) : iz;
       cj = j + 1;
     }
     else if (k < 3) {   // BR, TR, BL of transform level il (src/SPECK2D_INT.cpp:150-185)
@@ -725,47 +765,68 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
     if (s) {
       sg = 1;
       if (!child_i && cj == jC) {   // a size-C set: queue it and skip its bits
-        F.qc_node[ntok] = f_pack(F, cj, jx, jy, jz);
+        F.qc_node[ntok] = pack(cj, jx, jy, jz);
         F.qc_pos[ntok] = uint16_t(q);
         ntok++;
         q += F.bodyC[q];
       }
-      else {   // push
-        F.wk_node[depth] = f_pack(F, j, ix, iy, iz);
-        F.wk_k[depth] = (unsigned char)k;
-        F.wk_sig[depth] = 1;
-        depth++;
+      else {   // push (nothing to come back to when this was the last child)
+        if (k < nch) {
+          F.wk_node[depth] = pack(j, ix, iy, iz);
+          F.wk_k[depth] = (unsigned char)k;
+          F.wk_sig[depth] = 1;
+          depth++;
+        }
         j = cj;
         ix = jx; iy = jy; iz = jz;
         k = 0;
         sg = 0;
-        nch = frame_nch(j);
+        nch = nch_of(j);
       }
     }
     else if (child_i)
       F.iset = il - 1;   // stays outside the lists, tested again in the next plane
     else {
-      const int cl = f_lis(F, cj);
+      const int cl = lis_of(cj);
       const unsigned slot = F.cnt[cl];
       if (F.off[cl] + slot >= F.off[cl + 1]) {
         F.err |= 1u;
         break;
       }
-      d.lis[F.off[cl] + slot] = f_pack(F, cj, jx, jy, jz);
+      d.lis[F.off[cl] + slot] = pack(cj, jx, jy, jz);
       F.cnt[cl] = slot + 1;
     }
   }
   if (depth >= 0) {
-    F.wk_node[depth] = f_pack(F, j, ix, iy, iz);
+    F.wk_node[depth] = pack(j, ix, iy, iz);
     F.wk_k[depth] = (unsigned char)k;
     F.wk_sig[depth] = (unsigned char)sg;
   }
   F.wk_depth = depth;
   F.wk_i = i;
-  F.wk_w = w;
   F.wk_q = q;
   F.nqc = ntok;
   S.pos = F.win_base + q;
+}
+
+// Survivors of the staged roots [rs_first, wk_i) keep their order: list[wk_w ...] (whole CTA).
+static __device__ void f_compact_roots(FastSmem& F, node_t* list)
+{
+  const int tid = threadIdx.x;
+  const unsigned n = F.wk_i - F.rs_first;   // roots visited in this round
+  const unsigned w0 = F.wk_w;
+  unsigned total = 0;
+  for (unsigned b0 = 0; b0 < n; b0 += kDecThreads) {
+    const unsigned t = b0 + tid;
+    const bool keep = t < n && !((F.rs_gone[t >> 5] >> (t & 31)) & 1u);
+    const unsigned long long ex = f_block_scan(F, keep ? 1ull : 0ull);
+    if (keep && (w0 + total + unsigned(ex) != F.rs_first + t))
+      list[w0 + total + unsigned(ex)] = F.rs_node[t];
+    total += unsigned(F.scan_total);
+  }
+  __syncthreads();
+  if (tid == 0)
+    F.wk_w = w0 + total;
 }
 
 // The LIS part of one bit-plane.
@@ -809,14 +870,25 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
       __syncthreads();
       for (unsigned t = tid; t < nst; t += kDecThreads)
         F.rs_node[t] = iphase ? ((unsigned long long)(0x100 | F.iset) << 32) : d.lis[F.off[lis] + first + t];
+      for (unsigned t = tid; t < unsigned(kFRoots / 32); t += kDecThreads)
+        F.rs_gone[t] = 0;
       if (tid == 0) {
         F.rs_first = first;
         F.rs_cnt = nst;
       }
       __syncthreads();
       const long long f_tw = F_CLOCK();
-      if (tid == 0)
-        f_walk(d, S, F);
+      if (tid == 0) {
+        if (d.kind == 1)
+          f_walk<1>(d, S, F);
+        else if (d.kind == 2)
+          f_walk<2>(d, S, F);
+        else
+          f_walk<0>(d, S, F);
+      }
+      __syncthreads();
+      if (!iphase)
+        f_compact_roots(F, d.lis + F.off[lis]);
       __syncthreads();
       const long long f_te = F_CLOCK();
       if (tid == 0)

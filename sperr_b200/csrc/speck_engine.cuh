@@ -146,6 +146,8 @@ static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* cou
 {
   // per plane: bits every warp of the block contributes to the LIP part / the refinement part
   __shared__ unsigned short s_lip[64][32], s_ref[64][32];
+  // absolute position of this block's first LIP / refinement bit of every plane
+  __shared__ unsigned long long s_blip[64], s_bref[64];
   __shared__ int s_cmax;
   const unsigned c = blockIdx.y, blk = blockIdx.x;
   const ChunkDev& ch = chunks[c];
@@ -167,6 +169,17 @@ static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* cou
   const int cmax = s_cmax;
   const int first = ch.last_plane;  // planes below this were never coded
   const bool no_ref_last = ch.stop_after_sort != 0;
+  if (int(threadIdx.x) < 2 * 64) {   // one global round trip here instead of two per plane and warp
+    const int part = threadIdx.x >> 6, n = threadIdx.x & 63;
+    if (n >= first && n < cmax) {
+      const unsigned long long b = bases[(size_t)(c * 2 + part) * maxp + n] +
+                                   counts[((size_t)(c * 2 + part) * maxp + n) * nblk + blk];
+      if (part == 0)
+        s_blip[n] = b;
+      else
+        s_bref[n] = b;
+    }
+  }
   for (int n = first; n < cmax; n++) {
     unsigned l = 0, r = 0;
     if (n < wmax) {
@@ -197,9 +210,7 @@ static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* cou
     if (b0) {
       const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? unsigned(s_lip[n][lane]) : 0u);
       if (inlip) {
-        const unsigned long long pos = bases[(size_t)(c * 2 + 0) * maxp + n] +
-                                       counts[((size_t)(c * 2 + 0) * maxp + n) * nblk + blk] + before +
-                                       __popc(b0 & lt) + __popc(b1 & lt);
+        const unsigned long long pos = s_blip[n] + before + __popc(b0 & lt) + __popc(b1 & lt);
         if (newsig) {
           put_bit(ch.spk, pos, 1);
           put_bit(ch.spk, pos + 1, sgn);
@@ -209,9 +220,7 @@ static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* cou
     if (b2) {
       const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? unsigned(s_ref[n][lane]) : 0u);
       if (ref) {
-        const unsigned long long pos = bases[(size_t)(c * 2 + 1) * maxp + n] +
-                                       counts[((size_t)(c * 2 + 1) * maxp + n) * nblk + blk] + before +
-                                       __popc(b2 & lt);
+        const unsigned long long pos = s_bref[n] + before + __popc(b2 & lt);
         put_bit(ch.spk, pos, unsigned(mag >> n) & 1u);
       }
     }
