@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
   // the (x, y) columns this thread runs the z lifting for: tile elements tid, tid + 256, ...
   constexpr int kPer = (kFI * kFI + kFThreads - 1) / kFThreads;   // 7
   unsigned coff[kPer];     // offset inside a z plane of coef (chunks hold < 2^31 values)
-  int aoff[kPer];          // offset inside a z plane of the approx box, or -1: not approx in (x, y)
+  unsigned eoff[kPer];     // where the even-z sample comes from: offset inside a plane of the approx
+  unsigned apx = 0;        // box (bit s of apx set) or of coef
   InvState st[kPer];
   unsigned short sidx[kPer];
   for (int s = 0; s < kPer; s++) {
@@ -346,11 +347,27 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     const int gx = mirror(X0 - kFH + tx, lx), gy = mirror(Y0 - kFH + ty, ly);
     const int xo = (gx >> 1) + ((gx & 1) ? ax : 0), yo = (gy >> 1) + ((gy & 1) ? ay : 0);
     coff[s] = unsigned((size_t)yo * cnx + xo);
-    aoff[s] = ((gx | gy) & 1) ? -1
-                              : (a.apx_off >= 0 ? (gy >> 1) * ax + (gx >> 1) : int((size_t)(gy >> 1) * cnx + (gx >> 1)));
+    eoff[s] = coff[s];
+    if (!((gx | gy) & 1)) {
+      apx |= 1u << s;
+      eoff[s] = a.apx_off >= 0 ? unsigned((gy >> 1) * ax + (gx >> 1)) : unsigned((size_t)(gy >> 1) * cnx + (gx >> 1));
+    }
   }
   const double* abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : ch.coef;
   const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
+
+  // epilogue ownership: (x, y) = (X0 + lane, Y0 + warp + 8 c), c = 0 .. 3, of every plane
+  const int ep_lane = tid & 31, ep_warp = tid >> 5;
+  const unsigned long long ep_vplane = a.vol.vx * a.vol.vy;
+  const double ep_mean = ch.mean;
+  // offsets inside a z plane of the volume / of the chunk: c-th owned value at ep_g0 + c * ep_gs
+  const unsigned long long ep_g0 = (unsigned long long)(ch.y0 + Y0 + ep_warp) * a.vol.vx + (ch.x0 + X0 + ep_lane);
+  const unsigned long long ep_gs = 8ull * a.vol.vx;
+  const unsigned ep_c0 = unsigned((size_t)(Y0 + ep_warp) * cnx + X0 + ep_lane), ep_cs = unsigned(8 * cnx);
+  unsigned ep_live = 0;
+  for (int c = 0; c < 4; c++)
+    if (X0 + ep_lane < lx && Y0 + ep_warp + 8 * c < ly)
+      ep_live |= 1u << c;
 
   for (int j0 = k0 - 2; j0 <= k1 + 1; j0 += kNPB) {
     // ---- z: pair j = (low-band plane mirror(2j) / 2, high-band plane az + mirror(2j + 1) / 2) ----
@@ -366,7 +383,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
 #pragma unroll
       for (int s = 0; s < kPer; s++) {
         if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
-          ev[s] = aoff[s] >= 0 ? pa[aoff[s]] : pe[coff[s]];
+          ev[s] = (((apx >> s) & 1u) ? pa : pe)[eoff[s]];
           ov[s] = po[coff[s]];
         }
       }
@@ -389,43 +406,66 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     if (tid < kPlanes * kFT)
       lift_line<true>(k, tile + (size_t)(tid / kFT) * kFI * kFP + (kFH + tid % kFT) * kFP, 1);
     __syncthreads();
-    // ---- epilogue: kPlanes x 32 x 32 values ----
-    for (int idx = tid; idx < kPlanes * kFT * kFT; idx += kFThreads) {
-      const int p = idx >> 10, ry = (idx >> 5) & 31, rx = idx & 31;
+    // ---- epilogue: kPlanes x 32 x 32 values; a thread owns (lane, warp + 8 c) of every plane ----
+#pragma unroll
+    for (int p = 0; p < kPlanes; p++) {
       const int kk = j0 + (p >> 1) - 2;
-      const int x = X0 + rx, y = Y0 + ry, z = 2 * kk + (p & 1);
-      if (kk >= k0 && kk < k1 && x < lx && y < ly && z < lz) {
-        const double v = tile[(size_t)p * kFI * kFP + (kFH + ry) * kFP + kFH + rx];
-        if (OUT == 0 && a.out_off >= 0) {
-          ch.scratch[a.out_off + ((size_t)z * ly + y) * lx + x] = v;
+      const int z = 2 * kk + (p & 1);
+      if (kk < k0 || kk >= k1 || z >= lz)   // uniform over the CTA
+        continue;
+      const double* const tp = tile + (size_t)p * kFI * kFP + (kFH + ep_warp) * kFP + kFH + ep_lane;
+      if (OUT == 0 && a.out_off >= 0) {
+        double* const ob = ch.scratch + a.out_off + (size_t)z * ly * lx;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          if ((ep_live >> c) & 1u)
+            ob[(size_t)(Y0 + ep_warp + 8 * c) * lx + X0 + ep_lane] = tp[8 * c * kFP];
+        continue;
+      }
+      const unsigned long long gz = (unsigned long long)(ch.z0 + z) * ep_vplane;
+      if (OUT == 0) {
+        double* const vd = reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr)) + gz;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          if ((ep_live >> c) & 1u)
+            vd[ep_g0 + c * ep_gs] = tp[8 * c * kFP];
+      }
+      else if (OUT == 1) {
+        const unsigned long long iz = (unsigned long long)z * cnxy;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (!((ep_live >> c) & 1u))
+            continue;
+          double w = tp[8 * c * kFP];
+          if (a.cor.key) {   // src/SPECK_FLT.cpp:576-585: correctors are added before the mean
+            const unsigned long long i = iz + ep_c0 + c * ep_cs;
+            if ((ch.obits[i >> 5] >> (i & 31)) & 1u)
+              w = __dadd_rn(w, corrector_lookup(a.cor, a.ids[blockIdx.y], i));
+          }
+          w = __dadd_rn(w, ep_mean);
+          if (a.vol.is_float)
+            reinterpret_cast<float*>(const_cast<void*>(a.vol.ptr))[gz + ep_g0 + c * ep_gs] = __double2float_rn(w);
+          else
+            reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr))[gz + ep_g0 + c * ep_gs] = w;
         }
-        else {
-          const unsigned long long g = (unsigned long long)(ch.z0 + z) * a.vol.vx * a.vol.vy +
-                                       (unsigned long long)(ch.y0 + y) * a.vol.vx + (ch.x0 + x);
-          if (OUT == 0) {
-            reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr))[g] = v;
-          }
-          else if (OUT == 1) {
-            double w = v;
-            if (a.cor.key) {   // src/SPECK_FLT.cpp:576-585: correctors are added before the mean
-              const unsigned long long i = (unsigned long long)z * cnxy + (size_t)y * cnx + x;
-              if ((ch.obits[i >> 5] >> (i & 31)) & 1u)
-                w = __dadd_rn(w, corrector_lookup(a.cor, a.ids[blockIdx.y], i));
-            }
-            w = __dadd_rn(w, ch.mean);
-            if (a.vol.is_float)
-              reinterpret_cast<float*>(const_cast<void*>(a.vol.ptr))[g] = __double2float_rn(w);
-            else
-              reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr))[g] = w;
-          }
-          else {
-            const double orig = a.vol.is_float ? double(reinterpret_cast<const float*>(a.vol.ptr)[g])
-                                               : reinterpret_cast<const double*>(a.vol.ptr)[g];
-            const double diff = __dsub_rn(__dsub_rn(orig, ch.mean), v);
-            if (fabs(diff) > a.tol)
-              outlier_append(a.sink, a.ids[blockIdx.y], (unsigned long long)z * cnxy + (size_t)y * cnx + x,
-                             diff);
-          }
+      }
+      else {
+        // the four source values first (independent loads in flight), then the comparisons
+        double orig[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          orig[c] = 0.0;
+          if ((ep_live >> c) & 1u)
+            orig[c] = a.vol.is_float ? double(__ldg(reinterpret_cast<const float*>(a.vol.ptr) + gz + ep_g0 + c * ep_gs))
+                                     : __ldg(reinterpret_cast<const double*>(a.vol.ptr) + gz + ep_g0 + c * ep_gs);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          if (!((ep_live >> c) & 1u))
+            continue;
+          const double diff = __dsub_rn(__dsub_rn(orig[c], ep_mean), tp[8 * c * kFP]);
+          if (fabs(diff) > a.tol)
+            outlier_append(a.sink, a.ids[blockIdx.y], (unsigned long long)z * cnxy + ep_c0 + c * ep_cs, diff);
         }
       }
     }

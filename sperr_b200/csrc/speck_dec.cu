@@ -225,7 +225,7 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
   w.max_planes = 0;
   for (int c = 0; c < nj; c++) {
     const DecJob& j = jobs[c];
-    mw[c] = j.skip ? 0 : (size_t(j.n + 31) / 32 + 4);
+    mw[c] = j.skip ? 0 : ((size_t(j.n + 31) / 32 + 8) & ~size_t(3));   // 16-byte aligned pieces, zero padded
     sw[c] = j.skip ? 0 : (size_t(j.payload_bytes) / 4 + 4);
     mask_words += 3 * mw[c];
     pl_bytes += j.skip ? 0 : ((size_t(j.n) + 63) & ~size_t(63));

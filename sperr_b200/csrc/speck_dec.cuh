@@ -228,13 +228,16 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
     __syncthreads();
   }
 
-  // mask side: the k-th LIP pixel in raster order owns token k
+  // mask side: the k-th LIP pixel in raster order owns token k. A lane takes four mask words at a
+  // time (one 128-bit load; the mask arrays are 16-byte aligned and zero padded).
   const unsigned long long words = (d.n + 31) / 32;
-  const unsigned long long per_warp = ((words + kDecWarps - 1) / kDecWarps + 31) / 32 * 32;
-  const unsigned long long w0 = per_warp * warp, w1 = min(words, w0 + per_warp);
+  const unsigned long long per_warp = ((words + kDecWarps - 1) / kDecWarps + 127) / 128 * 128;
+  const unsigned long long w0 = per_warp * warp, w1 = min((words + 3) & ~3ull, w0 + per_warp);
   unsigned long long cnt = 0;
-  for (unsigned long long j = w0 + lane; j < w1; j += 32)
-    cnt += __popc(d.lip[j]);
+  for (unsigned long long j = w0 + 4ull * lane; j < w1; j += 128) {
+    const uint4 m4 = *reinterpret_cast<const uint4*>(d.lip + j);
+    cnt += __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w);
+  }
   for (int o = 16; o; o >>= 1)
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0)
@@ -248,37 +251,57 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
   __syncthreads();
   unsigned long long run = S.wtot[warp];
   unsigned long long nsig = 0;
-  for (unsigned long long j0 = w0; j0 < w1; j0 += 32) {
-    const unsigned long long j = j0 + lane;
-    unsigned m = j < w1 ? d.lip[j] : 0u;
-    const unsigned long long c = __popc(m);
-    const unsigned long long inc = warp_incl_scan(c, lane);
-    const unsigned long long k = run + inc - c;
+  for (unsigned long long j0 = w0; j0 < w1; j0 += 128) {
+    const unsigned long long j = j0 + 4ull * lane;
+    uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
+    if (j < w1)
+      m4 = *reinterpret_cast<const uint4*>(d.lip + j);
+    unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
+    const unsigned c4 = unsigned(__popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w));
+    unsigned inc = c4;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o)
+        inc += t;
+    }
+    unsigned long long k = run + inc - c4;
     run += __shfl_sync(0xffffffffu, inc, 31);
-    if (m) {
+    if (c4 == 0)
+      continue;
+    bool changed = false;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      unsigned m = mw[q];
+      const unsigned c = unsigned(__popc(m));
+      if (c == 0)
+        continue;
       // the c tokens of this word: bits [k, k + c) of the two result arrays
       const unsigned long long wi = k >> 5;
       const unsigned sh = unsigned(k & 31);
+      k += c;
       unsigned sg = __funnelshift_r(d.sigarr[wi], d.sigarr[wi + 1], sh);
       if (c < 32)
         sg &= (1u << c) - 1u;
-      if (sg) {
-        const unsigned sn = __funnelshift_r(d.signarr[wi], d.signarr[wi + 1], sh);
-        unsigned keep = m;
-        int t = 0;
-        while (m) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          if ((sg >> t) & 1u) {
-            keep &= ~(1u << bit);
-            d.pl[j * 32 + bit] = uint8_t(n_plane | (((sn >> t) & 1u) ? 0 : 0x80));
-          }
-          t++;
+      if (sg == 0)
+        continue;
+      const unsigned sn = __funnelshift_r(d.signarr[wi], d.signarr[wi + 1], sh);
+      unsigned keep = m;
+      int t = 0;
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        if ((sg >> t) & 1u) {
+          keep &= ~(1u << bit);
+          d.pl[(j + q) * 32 + bit] = uint8_t(n_plane | (((sn >> t) & 1u) ? 0 : 0x80));
         }
-        d.lip[j] = keep;
-        nsig += __popc(sg);
+        t++;
       }
+      mw[q] = keep;
+      changed = true;
+      nsig += __popc(sg);
     }
+    if (changed)
+      *reinterpret_cast<uint4*>(d.lip + j) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
   }
   for (int o = 16; o; o >>= 1)
     nsig += __shfl_xor_sync(0xffffffffu, nsig, o);

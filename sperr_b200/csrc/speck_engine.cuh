@@ -40,7 +40,7 @@ __device__ __forceinline__ unsigned long long load_mag(const ChunkDev& ch, unsig
 }
 
 // counts[((c*2 + part) * maxp + n) * nblk + blk], part 0 = LIP, 1 = refinement
-static __global__ void k_lipref_count(const ChunkDev* chunks, unsigned* counts, int maxp, unsigned nblk)
+static __global__ void __launch_bounds__(kLrBlock, 2) k_lipref_count(const ChunkDev* chunks, unsigned* counts, int maxp, unsigned nblk)
 {
   __shared__ unsigned s_lip[64], s_ref[64];
   __shared__ int s_cmax;
@@ -141,7 +141,7 @@ static __global__ void k_lipref_scan(const ChunkDev* chunks, unsigned* counts, u
 }
 
 // bases[(c*2 + part) * maxp + n]: absolute bit position of that part (set by k_plane_begin)
-static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* counts,
+static __global__ void __launch_bounds__(kLrBlock, 2) k_lipref_emit(const ChunkDev* chunks, const unsigned* counts,
                               const unsigned long long* bases, int maxp, unsigned nblk)
 {
   // per plane: bits every warp of the block contributes to the LIP part / the refinement part
@@ -159,6 +159,17 @@ static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* cou
   const int cm = valid ? int(ch.cmap[i]) : -1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1;
+  if (int(threadIdx.x) < 2 * 64) {   // one global round trip per block, in flight with the loads above
+    const int part = threadIdx.x >> 6, n = threadIdx.x & 63;
+    if (n < ch.planes && n < maxp) {
+      const unsigned long long b = bases[(size_t)(c * 2 + part) * maxp + n] +
+                                   counts[((size_t)(c * 2 + part) * maxp + n) * nblk + blk];
+      if (part == 0)
+        s_blip[n] = b;
+      else
+        s_bref[n] = b;
+    }
+  }
   if (threadIdx.x == 0)
     s_cmax = -1;
   __syncthreads();
@@ -169,17 +180,6 @@ static __global__ void k_lipref_emit(const ChunkDev* chunks, const unsigned* cou
   const int cmax = s_cmax;
   const int first = ch.last_plane;  // planes below this were never coded
   const bool no_ref_last = ch.stop_after_sort != 0;
-  if (int(threadIdx.x) < 2 * 64) {   // one global round trip here instead of two per plane and warp
-    const int part = threadIdx.x >> 6, n = threadIdx.x & 63;
-    if (n >= first && n < cmax) {
-      const unsigned long long b = bases[(size_t)(c * 2 + part) * maxp + n] +
-                                   counts[((size_t)(c * 2 + part) * maxp + n) * nblk + blk];
-      if (part == 0)
-        s_blip[n] = b;
-      else
-        s_bref[n] = b;
-    }
-  }
   for (int n = first; n < cmax; n++) {
     unsigned l = 0, r = 0;
     if (n < wmax) {

@@ -20,7 +20,7 @@ constexpr int kRecBlock = 1024;
 __device__ __forceinline__ int rec_plane(unsigned v) { return v == 0xFFu ? -1 : int(v & 63u); }
 
 // counts[(c * maxp + n) * nblk + blk] = coefficients of block blk significant before plane n
-__global__ void k_rec_count(const DecChunk* jobs, unsigned* counts, int maxp, unsigned nblk)
+__global__ void __launch_bounds__(kRecBlock, 2) k_rec_count(const DecChunk* jobs, unsigned* counts, int maxp, unsigned nblk)
 {
   __shared__ unsigned s_cnt[kMaxPlanes];
   __shared__ int s_max;
@@ -98,10 +98,14 @@ __global__ void k_rec_scan(const DecChunk* jobs, unsigned* counts, int maxp, uns
   }
 }
 
-__global__ void k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const unsigned* counts,
+__global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const unsigned* counts,
                             int maxp, unsigned nblk, int mode, const double* tols, OutlierSink sink)
 {
   __shared__ unsigned s_cnt[kMaxPlanes][32];   // per plane: significant-before-n count of every warp
+  // per plane: refinement bits available, where the section starts, and the rank of this block's
+  // first significant coefficient (one global round trip per block, not one per warp and plane)
+  __shared__ unsigned long long s_nref[kMaxPlanes], s_base[kMaxPlanes];
+  __shared__ unsigned s_rank0[kMaxPlanes];
   __shared__ int s_max;
   const unsigned c = blockIdx.y, blk = blockIdx.x;
   const DecChunk& d = jobs[c];
@@ -116,6 +120,14 @@ __global__ void k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const 
   if ((unsigned long long)blk * kRecBlock >= d.n)
     return;
   const unsigned v = i < d.n ? d.pl[i] : 0xFFu;
+  // per-plane section data, issued together with the load above (only planes below the block's
+  // largest significance plane are read back later)
+  if (int(threadIdx.x) < d.planes && threadIdx.x < kMaxPlanes) {
+    const int n = threadIdx.x;
+    s_nref[n] = d.ref_cnt[n];
+    s_base[n] = d.ref_base[n];
+    s_rank0[n] = counts[((size_t)c * maxp + n) * nblk + blk];
+  }
   const int p = rec_plane(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0)
@@ -126,6 +138,17 @@ __global__ void k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const 
     atomicMax(&s_max, wmax);
   __syncthreads();
   const int bmax = s_max;
+  if (bmax <= 0) {   // nothing in this block has refinement bits: all zero, or significant at plane 0
+    if (mode == 0) {
+      if (i < d.n) {
+        const bool ng = p >= 0 && (v & 0x80u);
+        ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, p >= 0 ? 1.0 : 0.0), ng ? -1.0 : 1.0);
+      }
+      return;
+    }
+    if (bmax < 0)
+      return;   // mode 1: the flag bits were cleared by the caller
+  }
   for (int n = 0; n < bmax; n++) {
     const unsigned b = __ballot_sync(0xffffffffu, p > n);
     if (lane == 0)
@@ -139,17 +162,18 @@ __global__ void k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const 
   }
   const unsigned lt = (1u << lane) - 1u;
   for (int n = min(wmax, bmax) - 1; n >= 0; n--) {   // warp-uniform: planes below this warp's largest
-    const unsigned long long nref = d.ref_cnt[n];
+    const unsigned long long nref = s_nref[n];
     if (nref == 0)
       continue;   // plane never refined (not reached, or the stream ended before its section)
     const bool mine = p > n;
     const unsigned b = __ballot_sync(0xffffffffu, mine);
+    if (b == 0)
+      continue;
     const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? s_cnt[n][lane] : 0u);
     if (mine) {
-      const unsigned long long rank =
-          (unsigned long long)counts[((size_t)c * maxp + n) * nblk + blk] + before + __popc(b & lt);
+      const unsigned long long rank = (unsigned long long)s_rank0[n] + before + __popc(b & lt);
       if (rank < nref) {
-        const unsigned long long bp = d.ref_base[n] + rank;
+        const unsigned long long bp = s_base[n] + rank;
         const unsigned bit = (d.bits[bp >> 5] >> (bp & 31)) & 1u;
         if (n >= 1) {
           const unsigned long long half = 1ull << (n - 1);

@@ -52,6 +52,7 @@ struct uint2 {
 struct uint4 {
   unsigned x, y, z, w;
 };
+inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 namespace emu {
 struct Fiber;
