@@ -39,49 +39,84 @@ __device__ __forceinline__ unsigned long long load_mag(const ChunkDev& ch, unsig
                  : (unsigned long long)reinterpret_cast<const unsigned*>(ch.mag)[i];
 }
 
-// counts[((c*2 + part) * maxp + n) * nblk + blk], part 0 = LIP, 1 = refinement
+// A CUDA block takes kLrUnits consecutive 1024-coefficient units: their loads are in flight together
+// and units in which no coefficient was ever created as a pixel before plane 0 (the fine sub-bands
+// of a smooth field) have no LIP or refinement bits and cost no barrier.
+constexpr int kLrUnits = 8;
+
+// per coefficient: msb position | creation plane << 8 (both -1 when absent)
+__device__ __forceinline__ int lr_load(const ChunkDev& ch, unsigned long long i)
+{
+  if (i >= ch.n)
+    return -1;
+  return (int(ch.pleaf[i]) & 0xff) | (int(ch.cmap[i]) << 8);
+}
+__device__ __forceinline__ int lr_p(int v) { return int(int8_t(v & 0xff)); }
+__device__ __forceinline__ int lr_cm(int v) { return v >> 8; }
+
+// counts[((c*2 + part) * maxp + n) * nblk + blk], part 0 = LIP, 1 = refinement (zeroed by the caller)
 static __global__ void __launch_bounds__(kLrBlock, 2) k_lipref_count(const ChunkDev* chunks, unsigned* counts, int maxp, unsigned nblk)
 {
   __shared__ unsigned s_lip[64], s_ref[64];
   __shared__ int s_cmax;
-  const unsigned c = blockIdx.y, blk = blockIdx.x;
+  __shared__ unsigned s_mask;
+  const unsigned c = blockIdx.y, blk0 = blockIdx.x * kLrUnits;
   const ChunkDev& ch = chunks[c];
-  if (ch.is_const || ch.planes == 0 || (unsigned long long)blk * kLrBlock >= ch.n)
+  if (ch.is_const || ch.planes == 0 || (unsigned long long)blk0 * kLrBlock >= ch.n)
     return;
-  const unsigned long long i = (unsigned long long)blk * kLrBlock + threadIdx.x;
-  const bool valid = i < ch.n;
-  const int p = valid ? int(ch.pleaf[i]) : -1;
-  const int cm = valid ? int(ch.cmap[i]) : -1;
-  if (threadIdx.x < 64) {
-    s_lip[threadIdx.x] = 0;
-    s_ref[threadIdx.x] = 0;
-  }
+  int vu[kLrUnits];
+#pragma unroll
+  for (int u = 0; u < kLrUnits; u++)
+    vu[u] = lr_load(ch, (unsigned long long)(blk0 + u) * kLrBlock + threadIdx.x);
+  unsigned live = 0;
+#pragma unroll
+  for (int u = 0; u < kLrUnits; u++)
+    live |= lr_cm(vu[u]) > 0 ? 1u << u : 0u;   // bits exist only in planes below the creation plane
   if (threadIdx.x == 0)
-    s_cmax = -1;
+    s_mask = 0;
   __syncthreads();
-  const int wmax = __reduce_max_sync(0xffffffffu, cm);
-  if ((threadIdx.x & 31) == 0 && wmax >= 0)
-    atomicMax(&s_cmax, wmax);
+  live = __reduce_or_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && live)
+    atomicOr(&s_mask, live);
   __syncthreads();
-  const int cmax = s_cmax;  // bits exist only for planes n < cmax
-  for (int n = 0; n < wmax; n++) {   // warp-uniform: this warp has no bits in planes >= its largest cm
-    const bool inlip = cm > n && p <= n;
-    const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
-    const unsigned b1 = __ballot_sync(0xffffffffu, inlip && p == n);
-    const unsigned b2 = __ballot_sync(0xffffffffu, p > n);
-    if ((threadIdx.x & 31) == 0) {
-      const unsigned l = __popc(b0) + __popc(b1), r = __popc(b2);
-      if (l)
-        atomicAdd(&s_lip[n], l);
-      if (r)
-        atomicAdd(&s_ref[n], r);
+  const unsigned mask = s_mask;
+#pragma unroll
+  for (int u = 0; u < kLrUnits; u++) {
+    if (!((mask >> u) & 1u))
+      continue;   // uniform over the block
+    const unsigned blk = blk0 + u;
+    const int p = lr_p(vu[u]), cm = lr_cm(vu[u]);
+    if (threadIdx.x < 64) {
+      s_lip[threadIdx.x] = 0;
+      s_ref[threadIdx.x] = 0;
     }
-  }
-  __syncthreads();
-  if (int(threadIdx.x) < cmax) {
-    const int n = threadIdx.x;
-    counts[((size_t)(c * 2 + 0) * maxp + n) * nblk + blk] = s_lip[n];
-    counts[((size_t)(c * 2 + 1) * maxp + n) * nblk + blk] = s_ref[n];
+    if (threadIdx.x == 0)
+      s_cmax = -1;
+    __syncthreads();
+    const int wmax = __reduce_max_sync(0xffffffffu, cm);
+    if ((threadIdx.x & 31) == 0 && wmax >= 0)
+      atomicMax(&s_cmax, wmax);
+    __syncthreads();
+    const int cmax = s_cmax;  // bits exist only for planes n < cmax
+    for (int n = 0; n < wmax; n++) {   // warp-uniform: this warp has no bits in planes >= its largest cm
+      const bool inlip = cm > n && p <= n;
+      const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
+      const unsigned b1 = __ballot_sync(0xffffffffu, inlip && p == n);
+      const unsigned b2 = __ballot_sync(0xffffffffu, p > n);
+      if ((threadIdx.x & 31) == 0) {
+        const unsigned l = __popc(b0) + __popc(b1), r = __popc(b2);
+        if (l)
+          atomicAdd(&s_lip[n], l);
+        if (r)
+          atomicAdd(&s_ref[n], r);
+      }
+    }
+    __syncthreads();
+    if (int(threadIdx.x) < cmax) {
+      const int n = threadIdx.x;
+      counts[((size_t)(c * 2 + 0) * maxp + n) * nblk + blk] = s_lip[n];
+      counts[((size_t)(c * 2 + 1) * maxp + n) * nblk + blk] = s_ref[n];
+    }
   }
 }
 
@@ -144,86 +179,109 @@ static __global__ void k_lipref_scan(const ChunkDev* chunks, unsigned* counts, u
 static __global__ void __launch_bounds__(kLrBlock, 2) k_lipref_emit(const ChunkDev* chunks, const unsigned* counts,
                               const unsigned long long* bases, int maxp, unsigned nblk)
 {
-  // per plane: bits every warp of the block contributes to the LIP part / the refinement part
+  // per plane: bits every warp of the unit contributes to the LIP part / the refinement part
   __shared__ unsigned short s_lip[64][32], s_ref[64][32];
-  // absolute position of this block's first LIP / refinement bit of every plane
+  // absolute position of the unit's first LIP / refinement bit of every plane
   __shared__ unsigned long long s_blip[64], s_bref[64];
   __shared__ int s_cmax;
-  const unsigned c = blockIdx.y, blk = blockIdx.x;
+  __shared__ unsigned s_mask;
+  const unsigned c = blockIdx.y, blk0 = blockIdx.x * kLrUnits;
   const ChunkDev& ch = chunks[c];
-  if (ch.is_const || ch.planes == 0 || (unsigned long long)blk * kLrBlock >= ch.n)
+  if (ch.is_const || ch.planes == 0 || (unsigned long long)blk0 * kLrBlock >= ch.n)
     return;
-  const unsigned long long i = (unsigned long long)blk * kLrBlock + threadIdx.x;
-  const bool valid = i < ch.n;
-  const int p = valid ? int(ch.pleaf[i]) : -1;
-  const int cm = valid ? int(ch.cmap[i]) : -1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt = (1u << lane) - 1;
-  if (int(threadIdx.x) < 2 * 64) {   // one global round trip per block, in flight with the loads above
-    const int part = threadIdx.x >> 6, n = threadIdx.x & 63;
-    if (n < ch.planes && n < maxp) {
-      const unsigned long long b = bases[(size_t)(c * 2 + part) * maxp + n] +
-                                   counts[((size_t)(c * 2 + part) * maxp + n) * nblk + blk];
-      if (part == 0)
-        s_blip[n] = b;
-      else
-        s_bref[n] = b;
-    }
-  }
-  if (threadIdx.x == 0)
-    s_cmax = -1;
-  __syncthreads();
-  const int wmax = __reduce_max_sync(0xffffffffu, cm);   // a coefficient has bits in planes < its cm
-  if (lane == 0 && wmax >= 0)
-    atomicMax(&s_cmax, wmax);
-  __syncthreads();
-  const int cmax = s_cmax;
+  int vu[kLrUnits];
+#pragma unroll
+  for (int u = 0; u < kLrUnits; u++)
+    vu[u] = lr_load(ch, (unsigned long long)(blk0 + u) * kLrBlock + threadIdx.x);
   const int first = ch.last_plane;  // planes below this were never coded
   const bool no_ref_last = ch.stop_after_sort != 0;
-  for (int n = first; n < cmax; n++) {
-    unsigned l = 0, r = 0;
-    if (n < wmax) {
-      const bool inlip = cm > n && p <= n;
-      const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
-      const unsigned b1 = __ballot_sync(0xffffffffu, inlip && p == n);
-      const unsigned b2 = __ballot_sync(0xffffffffu, p > n && !(n == first && no_ref_last));
-      l = unsigned(__popc(b0) + __popc(b1));
-      r = unsigned(__popc(b2));
-    }
-    if (lane == 0) {
-      s_lip[n][warp] = (unsigned short)l;
-      s_ref[n][warp] = (unsigned short)r;
-    }
-  }
+  unsigned live = 0;
+#pragma unroll
+  for (int u = 0; u < kLrUnits; u++)
+    live |= lr_cm(vu[u]) > first ? 1u << u : 0u;   // bits exist only in coded planes below the creation plane
+  if (threadIdx.x == 0)
+    s_mask = 0;
   __syncthreads();
-  if (wmax < 0)
-    return;
-  const unsigned long long mag = (valid && p >= 0) ? load_mag(ch, i) : 0;
-  const unsigned sgn = valid ? (ch.signs[i >> 5] >> (i & 31)) & 1u : 0;
-  for (int n = wmax - 1; n >= first; n--) {   // warp-uniform bounds
-    const bool inlip = cm > n && p <= n;
-    const bool newsig = inlip && p == n;
-    const bool ref = p > n && !(n == first && no_ref_last);
-    const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
-    const unsigned b1 = __ballot_sync(0xffffffffu, newsig);
-    const unsigned b2 = __ballot_sync(0xffffffffu, ref);
-    if (b0) {
-      const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? unsigned(s_lip[n][lane]) : 0u);
-      if (inlip) {
-        const unsigned long long pos = s_blip[n] + before + __popc(b0 & lt) + __popc(b1 & lt);
-        if (newsig) {
-          put_bit(ch.spk, pos, 1);
-          put_bit(ch.spk, pos + 1, sgn);
+  live = __reduce_or_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && live)
+    atomicOr(&s_mask, live);
+  __syncthreads();
+  const unsigned mask = s_mask;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1;
+#pragma unroll
+  for (int u = 0; u < kLrUnits; u++) {
+    if (!((mask >> u) & 1u))
+      continue;   // uniform over the block
+    const unsigned blk = blk0 + u;
+    const unsigned long long i = (unsigned long long)blk * kLrBlock + threadIdx.x;
+    const bool valid = i < ch.n;
+    const int p = lr_p(vu[u]), cm = lr_cm(vu[u]);
+    if (int(threadIdx.x) < 2 * 64) {   // one global round trip per unit instead of two per plane and warp
+      const int part = threadIdx.x >> 6, n = threadIdx.x & 63;
+      if (n < ch.planes && n < maxp) {
+        const unsigned long long b = bases[(size_t)(c * 2 + part) * maxp + n] +
+                                     counts[((size_t)(c * 2 + part) * maxp + n) * nblk + blk];
+        if (part == 0)
+          s_blip[n] = b;
+        else
+          s_bref[n] = b;
+      }
+    }
+    if (threadIdx.x == 0)
+      s_cmax = -1;
+    __syncthreads();
+    const int wmax = __reduce_max_sync(0xffffffffu, cm);   // a coefficient has bits in planes < its cm
+    if (lane == 0 && wmax >= 0)
+      atomicMax(&s_cmax, wmax);
+    __syncthreads();
+    const int cmax = s_cmax;
+    for (int n = first; n < cmax; n++) {
+      unsigned l = 0, r = 0;
+      if (n < wmax) {
+        const bool inlip = cm > n && p <= n;
+        const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
+        const unsigned b1 = __ballot_sync(0xffffffffu, inlip && p == n);
+        const unsigned b2 = __ballot_sync(0xffffffffu, p > n && !(n == first && no_ref_last));
+        l = unsigned(__popc(b0) + __popc(b1));
+        r = unsigned(__popc(b2));
+      }
+      if (lane == 0) {
+        s_lip[n][warp] = (unsigned short)l;
+        s_ref[n][warp] = (unsigned short)r;
+      }
+    }
+    __syncthreads();
+    const unsigned long long mag = (valid && p >= 0 && wmax >= 0) ? load_mag(ch, i) : 0;
+    const unsigned sgn = (valid && wmax >= 0) ? (ch.signs[i >> 5] >> (i & 31)) & 1u : 0;
+    for (int n = wmax - 1; n >= first; n--) {   // warp-uniform bounds (no iteration when wmax < 0)
+      const bool inlip = cm > n && p <= n;
+      const bool newsig = inlip && p == n;
+      const bool ref = p > n && !(n == first && no_ref_last);
+      const unsigned b0 = __ballot_sync(0xffffffffu, inlip);
+      const unsigned b1 = __ballot_sync(0xffffffffu, newsig);
+      const unsigned b2 = __ballot_sync(0xffffffffu, ref);
+      if (b0) {
+        const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? unsigned(s_lip[n][lane]) : 0u);
+        if (inlip) {
+          const unsigned long long pos = s_blip[n] + before + __popc(b0 & lt) + __popc(b1 & lt);
+          if (newsig) {
+            put_bit(ch.spk, pos, 1);
+            put_bit(ch.spk, pos + 1, sgn);
+          }
+        }
+      }
+      if (b2) {
+        const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? unsigned(s_ref[n][lane]) : 0u);
+        if (ref) {
+          const unsigned long long pos = s_bref[n] + before + __popc(b2 & lt);
+          put_bit(ch.spk, pos, unsigned(mag >> n) & 1u);
         }
       }
     }
-    if (b2) {
-      const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? unsigned(s_ref[n][lane]) : 0u);
-      if (ref) {
-        const unsigned long long pos = s_bref[n] + before + __popc(b2 & lt);
-        put_bit(ch.spk, pos, unsigned(mag >> n) & 1u);
-      }
-    }
+    // the shared arrays are rewritten by the next unit only after its first barrier ... except
+    // s_blip / s_bref, which the slowest warp may still be reading:
+    __syncthreads();
   }
 }
 
@@ -584,7 +642,7 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   unsigned* d_counts = w.counts.as<unsigned>();
   if (nblk) {
     rt::ProfScope ps("enc.lipref_count", st);
-    LAUNCH(k_lipref_count, dim3(nblk, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, maxp, nblk);
+    LAUNCH(k_lipref_count, dim3((nblk + kLrUnits - 1) / kLrUnits, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, maxp, nblk);
     LAUNCH(k_lipref_scan, dim3(2 * maxp, nchunks), dim3(1024), 0, st, d_chunks, d_counts, ctx.sizes,
            maxp, nblk);
   }
@@ -621,7 +679,7 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   // LIP / refinement emission
   rt::ProfScope ps_emit("enc.lipref_emit", st);
   if (nblk)
-    LAUNCH(k_lipref_emit, dim3(nblk, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, ctx.bases,
+    LAUNCH(k_lipref_emit, dim3((nblk + kLrUnits - 1) / kLrUnits, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, ctx.bases,
            maxp, nblk);
 
   rt::d2h(hc.data(), d_chunks, sizeof(ChunkDev) * nchunks, st);

@@ -19,35 +19,65 @@ constexpr int kRecBlock = 1024;
 
 __device__ __forceinline__ int rec_plane(unsigned v) { return v == 0xFFu ? -1 : int(v & 63u); }
 
-// counts[(c * maxp + n) * nblk + blk] = coefficients of block blk significant before plane n
-__global__ void __launch_bounds__(kRecBlock, 2) k_rec_count(const DecChunk* jobs, unsigned* counts, int maxp, unsigned nblk)
+// A CUDA block takes kRecUnits consecutive 1024-coefficient units: their loads are in flight
+// together and units without any significant coefficient (most of a sparse outlier array, the fine
+// sub-bands of a smooth field) cost no barrier at all.
+constexpr int kRecUnits = 8;
+
+// counts[(c * maxp + n) * nblk + blk] = coefficients of unit blk significant before plane n
+// (the caller zeroes the array: empty units write nothing)
+__global__ void __launch_bounds__(kRecBlock, 2) k_rec_count(const DecChunk* jobs, unsigned* counts, int maxp,
+                                                            unsigned nblk)
 {
   __shared__ unsigned s_cnt[kMaxPlanes];
   __shared__ int s_max;
-  const unsigned c = blockIdx.y, blk = blockIdx.x;
+  __shared__ unsigned s_mask;
+  const unsigned c = blockIdx.y, blk0 = blockIdx.x * kRecUnits;
   const DecChunk& d = jobs[c];
-  if (d.skip || (unsigned long long)blk * kRecBlock >= d.n)
+  if (d.skip || (unsigned long long)blk0 * kRecBlock >= d.n)
     return;
-  const unsigned long long i = (unsigned long long)blk * kRecBlock + threadIdx.x;
-  const int p = i < d.n ? rec_plane(d.pl[i]) : -1;
-  if (threadIdx.x < kMaxPlanes)
-    s_cnt[threadIdx.x] = 0;
-  if (threadIdx.x == 0)
-    s_max = -1;
-  __syncthreads();
-  const int wmax = __reduce_max_sync(0xffffffffu, p);
-  if ((threadIdx.x & 31) == 0 && wmax >= 0)
-    atomicMax(&s_max, wmax);
-  __syncthreads();
-  const int bmax = s_max;
-  for (int n = 0; n < wmax; n++) {   // warp-uniform: nothing of this warp is significant before plane >= wmax
-    const unsigned b = __ballot_sync(0xffffffffu, p > n);
-    if ((threadIdx.x & 31) == 0 && b)
-      atomicAdd(&s_cnt[n], unsigned(__popc(b)));
+  int pu[kRecUnits];
+  unsigned mine = 0;
+#pragma unroll
+  for (int u = 0; u < kRecUnits; u++) {
+    const unsigned long long i = (unsigned long long)(blk0 + u) * kRecBlock + threadIdx.x;
+    pu[u] = i < d.n ? rec_plane(d.pl[i]) : -1;
   }
+#pragma unroll
+  for (int u = 0; u < kRecUnits; u++)
+    mine |= pu[u] > 0 ? 1u << u : 0u;   // p == 0: significant, but never "before" any plane
+  if (threadIdx.x == 0)
+    s_mask = 0;
   __syncthreads();
-  if (int(threadIdx.x) < bmax)
-    counts[((size_t)c * maxp + threadIdx.x) * nblk + blk] = s_cnt[threadIdx.x];
+  mine = __reduce_or_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine)
+    atomicOr(&s_mask, mine);
+  __syncthreads();
+  const unsigned mask = s_mask;
+#pragma unroll
+  for (int u = 0; u < kRecUnits; u++) {
+    if (!((mask >> u) & 1u))
+      continue;   // uniform over the block
+    const int p = pu[u];
+    if (threadIdx.x < kMaxPlanes)
+      s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0)
+      s_max = -1;
+    __syncthreads();
+    const int wmax = __reduce_max_sync(0xffffffffu, p);
+    if ((threadIdx.x & 31) == 0 && wmax >= 0)
+      atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int bmax = s_max;
+    for (int n = 0; n < wmax; n++) {   // warp-uniform: nothing of this warp is significant before plane >= wmax
+      const unsigned b = __ballot_sync(0xffffffffu, p > n);
+      if ((threadIdx.x & 31) == 0 && b)
+        atomicAdd(&s_cnt[n], unsigned(__popc(b)));
+    }
+    __syncthreads();
+    if (int(threadIdx.x) < bmax)
+      counts[((size_t)c * maxp + threadIdx.x) * nblk + blk0 + u] = s_cnt[threadIdx.x];
+  }
 }
 
 // one block per (chunk, plane) row: exclusive scan over the blocks, in place
@@ -98,109 +128,129 @@ __global__ void k_rec_scan(const DecChunk* jobs, unsigned* counts, int maxp, uns
   }
 }
 
-__global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks, const unsigned* counts,
-                            int maxp, unsigned nblk, int mode, const double* tols, OutlierSink sink)
+__global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs, const ChunkDev* chunks,
+                                                            const unsigned* counts, int maxp, unsigned nblk,
+                                                            int mode, const double* tols, OutlierSink sink)
 {
   __shared__ unsigned s_cnt[kMaxPlanes][32];   // per plane: significant-before-n count of every warp
-  // per plane: refinement bits available, where the section starts, and the rank of this block's
-  // first significant coefficient (one global round trip per block, not one per warp and plane)
+  // per plane: refinement bits available and where the section starts (one global round trip per
+  // block, in flight with the loads of the coefficients' states)
   __shared__ unsigned long long s_nref[kMaxPlanes], s_base[kMaxPlanes];
-  __shared__ unsigned s_rank0[kMaxPlanes];
   __shared__ int s_max;
-  const unsigned c = blockIdx.y, blk = blockIdx.x;
+  __shared__ unsigned s_mask;
+  const unsigned c = blockIdx.y, blk0 = blockIdx.x * kRecUnits;
   const DecChunk& d = jobs[c];
   const ChunkDev& ch = chunks[c];
-  const unsigned long long i = (unsigned long long)blk * kRecBlock + threadIdx.x;
   if (d.skip) {
     // no SPECK stream: every coefficient is zero (constant chunks never read their buffer)
-    if (mode == 0 && !ch.is_const && i < ch.n)
-      ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, 0.0), 1.0);
+    if (mode == 0 && !ch.is_const)
+      for (int u = 0; u < kRecUnits; u++) {
+        const unsigned long long i = (unsigned long long)(blk0 + u) * kRecBlock + threadIdx.x;
+        if (i < ch.n)
+          ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, 0.0), 1.0);
+      }
     return;
   }
-  if ((unsigned long long)blk * kRecBlock >= d.n)
+  if ((unsigned long long)blk0 * kRecBlock >= d.n)
     return;
-  const unsigned v = i < d.n ? d.pl[i] : 0xFFu;
-  // per-plane section data, issued together with the load above (only planes below the block's
-  // largest significance plane are read back later)
+  unsigned vu[kRecUnits];
+#pragma unroll
+  for (int u = 0; u < kRecUnits; u++) {
+    const unsigned long long i = (unsigned long long)(blk0 + u) * kRecBlock + threadIdx.x;
+    vu[u] = i < d.n ? d.pl[i] : 0xFFu;
+  }
   if (int(threadIdx.x) < d.planes && threadIdx.x < kMaxPlanes) {
-    const int n = threadIdx.x;
-    s_nref[n] = d.ref_cnt[n];
-    s_base[n] = d.ref_base[n];
-    s_rank0[n] = counts[((size_t)c * maxp + n) * nblk + blk];
+    s_nref[threadIdx.x] = d.ref_cnt[threadIdx.x];
+    s_base[threadIdx.x] = d.ref_base[threadIdx.x];
   }
-  const int p = rec_plane(v);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // units that need the full path: something has refinement bits (mode 0) / is an outlier (mode 1)
+  unsigned full = 0;
+#pragma unroll
+  for (int u = 0; u < kRecUnits; u++)
+    full |= rec_plane(vu[u]) >= (mode == 0 ? 1 : 0) ? 1u << u : 0u;
   if (threadIdx.x == 0)
-    s_max = -1;
+    s_mask = 0;
   __syncthreads();
-  const int wmax = __reduce_max_sync(0xffffffffu, p);
-  if (lane == 0 && wmax >= 0)
-    atomicMax(&s_max, wmax);
+  full = __reduce_or_sync(0xffffffffu, full);
+  if ((threadIdx.x & 31) == 0 && full)
+    atomicOr(&s_mask, full);
   __syncthreads();
-  const int bmax = s_max;
-  if (bmax <= 0) {   // nothing in this block has refinement bits: all zero, or significant at plane 0
-    if (mode == 0) {
-      if (i < d.n) {
-        const bool ng = p >= 0 && (v & 0x80u);
-        ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, p >= 0 ? 1.0 : 0.0), ng ? -1.0 : 1.0);
-      }
-      return;
-    }
-    if (bmax < 0)
-      return;   // mode 1: the flag bits were cleared by the caller
-  }
-  for (int n = 0; n < bmax; n++) {
-    const unsigned b = __ballot_sync(0xffffffffu, p > n);
-    if (lane == 0)
-      s_cnt[n][warp] = unsigned(__popc(b));
-  }
-  __syncthreads();
-  unsigned long long mag = 0;
-  if (p >= 0) {
-    const unsigned long long thr = 1ull << p;
-    mag = thr + thr - (thr >> 1) - 1ull;   // value given to a newly significant coefficient
-  }
+  const unsigned mask = s_mask;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
-  for (int n = min(wmax, bmax) - 1; n >= 0; n--) {   // warp-uniform: planes below this warp's largest
-    const unsigned long long nref = s_nref[n];
-    if (nref == 0)
-      continue;   // plane never refined (not reached, or the stream ended before its section)
-    const bool mine = p > n;
-    const unsigned b = __ballot_sync(0xffffffffu, mine);
-    if (b == 0)
+#pragma unroll
+  for (int u = 0; u < kRecUnits; u++) {
+    const unsigned blk = blk0 + u;
+    const unsigned long long i = (unsigned long long)blk * kRecBlock + threadIdx.x;
+    const unsigned v = vu[u];
+    const int p = rec_plane(v);
+    const bool in = i < d.n;
+    const bool neg = p >= 0 && (v & 0x80u);
+    if (!((mask >> u) & 1u)) {   // uniform over the block: all zero, or significant at plane 0 only
+      if (mode == 0 && in)
+        ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, p >= 0 ? 1.0 : 0.0), neg ? -1.0 : 1.0);
       continue;
-    const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? s_cnt[n][lane] : 0u);
-    if (mine) {
-      const unsigned long long rank = (unsigned long long)s_rank0[n] + before + __popc(b & lt);
-      if (rank < nref) {
-        const unsigned long long bp = s_base[n] + rank;
-        const unsigned bit = (d.bits[bp >> 5] >> (bp & 31)) & 1u;
-        if (n >= 1) {
-          const unsigned long long half = 1ull << (n - 1);
-          mag = bit ? mag + half : mag - half;
+    }
+    if (threadIdx.x == 0)
+      s_max = -1;
+    __syncthreads();
+    const int wmax = __reduce_max_sync(0xffffffffu, p);
+    if (lane == 0 && wmax >= 0)
+      atomicMax(&s_max, wmax);
+    __syncthreads();
+    const int bmax = s_max;
+    for (int n = 0; n < bmax; n++) {
+      const unsigned b = __ballot_sync(0xffffffffu, p > n);
+      if (lane == 0)
+        s_cnt[n][warp] = unsigned(__popc(b));
+    }
+    __syncthreads();
+    unsigned long long mag = 0;
+    if (p >= 0) {
+      const unsigned long long thr = 1ull << p;
+      mag = thr + thr - (thr >> 1) - 1ull;   // value given to a newly significant coefficient
+    }
+    for (int n = min(wmax, bmax) - 1; n >= 0; n--) {   // warp-uniform: planes below this warp's largest
+      const unsigned long long nref = s_nref[n];
+      if (nref == 0)
+        continue;   // plane never refined (not reached, or the stream ended before its section)
+      const bool mine = p > n;
+      const unsigned b = __ballot_sync(0xffffffffu, mine);
+      if (b == 0)
+        continue;
+      const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? s_cnt[n][lane] : 0u);
+      if (mine) {
+        const unsigned long long rank =
+            (unsigned long long)counts[((size_t)c * maxp + n) * nblk + blk] + before + __popc(b & lt);
+        if (rank < nref) {
+          const unsigned long long bp = s_base[n] + rank;
+          const unsigned bit = (d.bits[bp >> 5] >> (bp & 31)) & 1u;
+          if (n >= 1) {
+            const unsigned long long half = 1ull << (n - 1);
+            mag = bit ? mag + half : mag - half;
+          }
+          else
+            mag += bit;
         }
-        else
-          mag += bit;
       }
     }
-  }
-  const bool in = i < d.n;
-  const bool neg = p >= 0 && (v & 0x80u);
-  if (mode == 0) {
-    if (in)
-      ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, __ull2double_rn(mag)), neg ? -1.0 : 1.0);
-  }
-  else {
-    // outlier correctors: a sorted list for the consumers plus one flag bit per value
-    const bool has = in && p >= 0 && mag != 0;
-    const unsigned b = __ballot_sync(0xffffffffu, has);
-    if (lane == 0 && in)
-      ch.obits[i >> 5] = b;
-    if (has) {
-      double e = mag == 1 ? 1.1 : __dsub_rn(__ull2double_rn(mag), 0.25);
-      e = __dmul_rn(e, __dmul_rn(tols[c], neg ? -1.0 : 1.0));
-      outlier_append(sink, c, i, e);
+    if (mode == 0) {
+      if (in)
+        ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, __ull2double_rn(mag)), neg ? -1.0 : 1.0);
     }
+    else {
+      // outlier correctors: a sorted list for the consumers plus one flag bit per value
+      const bool has = in && p >= 0 && mag != 0;
+      const unsigned b = __ballot_sync(0xffffffffu, has);
+      if (lane == 0 && in)
+        ch.obits[i >> 5] = b;
+      if (has) {
+        double e = mag == 1 ? 1.1 : __dsub_rn(__ull2double_rn(mag), 0.25);
+        e = __dmul_rn(e, __dmul_rn(tols[c], neg ? -1.0 : 1.0));
+        outlier_append(sink, c, i, e);
+      }
+    }
+    // s_cnt / s_max are rewritten by the next unit only after its first barrier
   }
 }
 
@@ -246,11 +296,11 @@ void speck_reconstruct(DecWork& w, const ChunkDev* d_chunks, int mode, const dou
   rt::dset(w.counts.p, 0, ncounts * 4, st);
   unsigned* cnt = w.counts.as<unsigned>();
   if (w.max_n) {
-    LAUNCH(k_rec_count, dim3(nblk, nj), dim3(kRecBlock), 0, st, dj, cnt, maxp, nblk);
+    LAUNCH(k_rec_count, dim3((nblk + kRecUnits - 1) / kRecUnits, nj), dim3(kRecBlock), 0, st, dj, cnt, maxp, nblk);
     LAUNCH(k_rec_scan, dim3(maxp, nj), dim3(1024), 0, st, dj, cnt, maxp, nblk);
   }
-  LAUNCH(k_rec_apply, dim3(nblk, nj), dim3(kRecBlock), 0, st, dj, d_chunks, cnt, maxp, nblk, mode, d_tols,
-         sink);
+  LAUNCH(k_rec_apply, dim3((nblk + kRecUnits - 1) / kRecUnits, nj), dim3(kRecBlock), 0, st, dj, d_chunks, cnt,
+         maxp, nblk, mode, d_tols, sink);
 }
 
 }  // namespace sperr_b200
