@@ -501,6 +501,7 @@ __global__ void k_pix_first(const unsigned long long* keys, unsigned npix_total,
 // ---------------------------------------------------------------------------------------------
 
 struct Tree1D {
+  static constexpr bool kHasLeaf8 = false;
   struct Data {
     const ONode* nodes;
     const OutMeta* meta;

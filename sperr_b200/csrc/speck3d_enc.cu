@@ -129,6 +129,7 @@ __global__ void k_pyr_level(const ChunkDev* chunks, const ShapeDev* shapes, cons
 // ---------------------------------------------------------------------------------------------
 
 struct Tree3D {
+  static constexpr bool kHasLeaf8 = false;
   struct Data {
     const ShapeDev* shapes;
   };
@@ -275,10 +276,43 @@ __global__ void k_pyr_pow2(const ChunkDev* chunks, Pow2Info g, int j)
 }
 
 struct Tree3DPow2 {
+  static constexpr bool kHasLeaf8 = true;
   struct Data {
     const ShapeDev* shapes;
     Pow2Info g;
   };
+
+  // the single coefficients below a set of depth J - 1, in coding order (x fastest): pairs along x
+  // share a 16-bit load of the msb map and a word of the sign map
+  static __device__ __forceinline__ int leaf8(const Data& t, const ChunkDev& ch, node_t nd, int* p,
+                                              unsigned& sg)
+  {
+    const Pow2Info& g = t.g;
+    const int j = node_level(nd);
+    const unsigned ix = node_ix(nd), iy = node_iy(nd), iz = node_iz(nd);
+    const int sx = j < g.Dx, sy = j < g.Dy, sz = j < g.Dz;
+    const int rows = 1 << (sy + sz);
+    sg = 0;
+    int k = 0;
+    for (int r = 0; r < rows; r++) {
+      const unsigned jy = sy ? iy * 2 + (unsigned(r) & 1u) : iy;
+      const unsigned jz = sz ? iz * 2 + ((unsigned(r) >> sy) & 1u) : iz;
+      const size_t ri = ((size_t)jz * g.ny + jy) * g.nx + (sx ? ix * 2 : ix);
+      if (sx) {   // ri is even: both values in one aligned 16-bit word, both sign bits in one word
+        const unsigned v = *reinterpret_cast<const unsigned short*>(ch.pleaf + ri);
+        p[k] = int(int8_t(v & 0xff));
+        p[k + 1] = int(int8_t(v >> 8));
+        sg |= ((ch.signs[ri >> 5] >> (ri & 31)) & 3u) << k;
+        k += 2;
+      }
+      else {
+        p[k] = ch.pleaf[ri];
+        sg |= ((ch.signs[ri >> 5] >> (ri & 31)) & 1u) << k;
+        k += 1;
+      }
+    }
+    return k;
+  }
 
   static __device__ __forceinline__ void pd(const Data& t, const ChunkDev& ch, unsigned, node_t nd,
                                             int& p, unsigned& d)
@@ -410,6 +444,7 @@ __global__ void k_pyr_iset(const ChunkDev* chunks, const ShapeDev* shapes, const
 }
 
 struct Tree2D {
+  static constexpr bool kHasLeaf8 = false;
   typedef Tree3D::Data Data;
 
   static __device__ __forceinline__ void pd(const Data& t, const ChunkDev& ch, unsigned c, node_t nd,

@@ -4,6 +4,8 @@
 //   static __device__ void  T::pd(data, chunk, c, node, int& p, unsigned& d)
 //   static __device__ int   T::children(data, chunk, c, node, ChildRec out[8])
 //     (number of children; | 0x100 when even the last child is tested explicitly)
+//   T::kHasLeaf8 / T::leaf8(data, chunk, node, int p[8], unsigned& signs): optional shortcut for a set
+//     whose children are all single coefficients (their msb positions and sign bits, coding order)
 // where p = msb position of the largest magnitude below the node (-1: all zero) and d = number of
 // bits the node's depth-first expansion emits in the plane it turns significant.
 #pragma once
@@ -26,6 +28,43 @@ __device__ __forceinline__ void put_bit(uint32_t* words, unsigned long long pos,
   if (bit)
     atomicOr(&words[pos >> 5], 1u << (pos & 31));
 }
+
+// Bits a thread emits at consecutive positions: gathered in a register, OR-ed into the stream one
+// word at a time (a set's test / sign bits are contiguous between the bodies of its larger children).
+struct BitRun {
+  uint32_t* w;
+  unsigned long long pos;   // position of bit 0 of acc
+  unsigned acc;
+  int n;
+  __device__ __forceinline__ void start(uint32_t* words, unsigned long long p)
+  {
+    w = words; pos = p; acc = 0; n = 0;
+  }
+  __device__ __forceinline__ unsigned long long cur() const { return pos + n; }
+  __device__ __forceinline__ void flush()
+  {
+    if (acc) {
+      const unsigned sh = unsigned(pos & 31);
+      atomicOr(&w[pos >> 5], acc << sh);
+      if (sh && (acc >> (32 - sh)))
+        atomicOr(&w[(pos >> 5) + 1], acc >> (32 - sh));
+    }
+    pos += n;
+    acc = 0;
+    n = 0;
+  }
+  __device__ __forceinline__ void push(unsigned bit)
+  {
+    acc |= bit << n;
+    if (++n == 32)
+      flush();
+  }
+  __device__ __forceinline__ void skip(unsigned long long d)   // bits written by someone else
+  {
+    flush();
+    pos += d;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
 // 2. LIP / refinement parts: per-plane raster-order counts, scans and emission
@@ -425,49 +464,57 @@ __global__ void k_expand(EncCtx ctx, typename T::Data tree, int src)
     const int nchf = T::children(tree, ch, c, nd, kid);
     const int nch = nchf & 0xff;
     const bool all_tested = (nchf & 0x100) != 0;   // 2D: last split of the set I
+    BitRun run;
+    run.start(ch.spk, cur);
     int sigc = 0;
     for (int k = 0; k < nch; k++) {
       const bool need = sigc != 0 || k != nch - 1 || all_tested;
       const bool sig = !need || kid[k].p == n;
-      if (need) {
-        put_bit(ch.spk, cur, sig);
-        cur++;
-      }
+      if (need)
+        run.push(sig);
       if (kid[k].kind == 0) {
         if (sig) {
-          put_bit(ch.spk, cur, kid[k].sign);
-          cur++;
+          run.push(kid[k].sign);
           sigc++;
         }
       }
       else if (sig) {
         sigc++;
         if (kid[k].kind == 1) {  // all grandchildren are pixels: finish them here
-          ChildRec g[8];
-          const int ng = T::children(tree, ch, c, kid[k].id, g) & 0xff;
+          int gp[8];
+          unsigned gsign = 0;
+          int ng;
+          if constexpr (T::kHasLeaf8)
+            ng = T::leaf8(tree, ch, kid[k].id, gp, gsign);
+          else {
+            ChildRec g[8];
+            ng = T::children(tree, ch, c, kid[k].id, g) & 0xff;
+            for (int j = 0; j < ng; j++) {
+              gp[j] = g[j].p;
+              gsign |= g[j].sign << j;
+            }
+          }
           int gs = 0;
           for (int j = 0; j < ng; j++) {
             const bool gneed = gs != 0 || j != ng - 1;
-            const bool gsig = !gneed || g[j].p == n;
-            if (gneed) {
-              put_bit(ch.spk, cur, gsig);
-              cur++;
-            }
+            const bool gsig = !gneed || gp[j] == n;
+            if (gneed)
+              run.push(gsig);
             if (gsig) {
-              put_bit(ch.spk, cur, g[j].sign);
-              cur++;
+              run.push((gsign >> j) & 1u);
               gs++;
             }
           }
         }
         else {
-          app.front(dst, c, kid[k].id, cur);
-          cur += kid[k].d;
+          app.front(dst, c, kid[k].id, run.cur());
+          run.skip(kid[k].d);
         }
       }
       else if (ch.next_needed)
-        app.cand(c, make_key(c, kid[k].lis_desc, (cur - 1) + 64), kid[k].id);
+        app.cand(c, make_key(c, kid[k].lis_desc, (run.cur() - 1) + 64), kid[k].id);
     }
+    run.flush();
   }
 }
 

@@ -40,6 +40,82 @@ __device__ __forceinline__ unsigned long long dkey(double v)
 // conditioner: strided mean in the reference's association order, constant test, min / max
 // ---------------------------------------------------------------------------------------------
 
+// Strides made of whole rows of a float volume can be staged through shared memory with coalesced
+// 128-bit loads (k_stride_stats_rows); everything else is walked by k_stride_stats.
+constexpr int kStatStrides = 128;   // strides (= threads) of a block
+constexpr int kStatSeg = 64;        // floats of a row staged per step and stride
+__device__ __forceinline__ bool stats_by_rows(const SrcVol& src, const ChunkDev& ch, unsigned ns)
+{
+  return src.is_float && ns != 0 && ch.nx % kStatSeg == 0 && (ch.n / ns) % ch.nx == 0 && ch.n % ns == 0 &&
+         ch.x0 % 4 == 0 && src.vx % 4 == 0 && (reinterpret_cast<unsigned long long>(src.ptr) & 15ull) == 0;
+}
+
+// One thread per stride, as below (the additions of a stride happen left to right in one thread,
+// src/Conditioner.cpp:119-135), but the values arrive through a [stride][segment] tile that the
+// block fills with coalesced loads: 128 strides x 64 floats per step.
+__global__ void __launch_bounds__(kStatStrides) k_stride_stats_rows(SrcVol src, ChunkDev* chunks, double* stride_mean,
+                                                                 int max_strides, const unsigned* nstrides,
+                                                                 unsigned* not_const, int want_minmax)
+{
+  __shared__ float tile[kStatStrides][kStatSeg + 1];
+  const unsigned c = blockIdx.y;
+  ChunkDev& ch = chunks[c];
+  const unsigned ns = nstrides[c];
+  const unsigned s0 = blockIdx.x * kStatStrides;
+  if (s0 >= ns || !stats_by_rows(src, ch, ns))
+    return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long len = ch.n / ns;
+  const unsigned rows = unsigned(len / ch.nx), segs = ch.nx / kStatSeg;
+  const unsigned s = s0 + tid;
+  const bool active = s < ns;
+  const float* const vf = reinterpret_cast<const float*>(src.ptr);
+  const double v0 = double(vf[src_index(src, ch, 0, 0, 0)]);
+  double acc = 0.0, mn = v0, mx = v0;
+  bool diff = false;
+  for (unsigned r = 0; r < rows; r++) {
+    for (unsigned g = 0; g < segs; g++) {
+      // a warp fetches the segments of two strides at a time: 16 lanes x 16 bytes each
+      for (unsigned k = 2 * warp + (lane >> 4); k < unsigned(kStatStrides); k += 2 * (kStatStrides / 32)) {
+        const unsigned ss = s0 + k;
+        if (ss < ns) {
+          const unsigned long long rho = (unsigned long long)ss * rows + r;   // row of the chunk
+          const unsigned y = unsigned(rho % ch.ny), z = unsigned(rho / ch.ny);
+          const float4 v =
+              reinterpret_cast<const float4*>(vf + src_index(src, ch, g * kStatSeg, y, z))[lane & 15];
+          float* const t = &tile[k][4 * (lane & 15)];
+          t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+        }
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll 8
+        for (int i = 0; i < kStatSeg; i++) {
+          const double v = double(tile[tid][i]);
+          acc = __dadd_rn(acc, v);
+          diff |= !(v == v0);
+          if (want_minmax) {
+            mn = v < mn ? v : mn;
+            mx = v > mx ? v : mx;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!active)
+    return;
+  stride_mean[(size_t)c * max_strides + s] = __ddiv_rn(acc, double(len));
+  if (diff)
+    atomicOr(&not_const[c], 1u);
+  if (want_minmax) {
+    atomicMin(&ch.min_key, dkey(mn));
+    atomicMax(&ch.max_key, dkey(mx));
+  }
+  if (s == 0)
+    ch.first_val = v0;
+}
+
 // One thread per stride; a stride is n / nstrides consecutive values of the chunk (x fastest).
 __global__ void k_stride_stats(SrcVol src, ChunkDev* chunks, double* stride_mean, int max_strides,
                                const unsigned* nstrides, unsigned* not_const, int want_minmax)
@@ -48,7 +124,7 @@ __global__ void k_stride_stats(SrcVol src, ChunkDev* chunks, double* stride_mean
   ChunkDev& ch = chunks[c];
   const unsigned ns = nstrides[c];
   const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= ns)
+  if (s >= ns || stats_by_rows(src, ch, ns))
     return;
   const unsigned long long len = ch.n / ns;
   unsigned long long e = (unsigned long long)s * len;
@@ -476,6 +552,9 @@ void launch_stats(const SrcVol& src, ChunkDev* d_chunks, int nchunks, double* d_
                   bool want_minmax, cudaStream_t st)
 {
   dim3 grid((max_strides + 127) / 128, nchunks);
+  if (src.is_float)   // chunks whose strides are whole rows (every kernel checks per chunk)
+    LAUNCH(k_stride_stats_rows, grid, dim3(kStatStrides), 0, st, src, d_chunks, d_stride_mean, max_strides,
+           d_nstrides, d_not_const, want_minmax ? 1 : 0);
   LAUNCH(k_stride_stats, grid, dim3(128), 0, st, src, d_chunks, d_stride_mean, max_strides,
          d_nstrides, d_not_const, want_minmax ? 1 : 0);
   LAUNCH(k_mean_finish, dim3((nchunks + 63) / 64), dim3(64), 0, st, d_chunks, d_stride_mean,
