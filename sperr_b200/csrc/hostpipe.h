@@ -7,6 +7,7 @@
 // malloc) while the DMA engine moves the neighbouring slot. Pinned user memory is copied directly.
 #pragma once
 
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -44,10 +45,23 @@ class HostPipe {
   std::vector<std::thread> threads_;
   std::mutex mu_;
   std::condition_variable cv_work_, cv_done_;
+  // Device -> pageable host as one pipeline: the caller keeps the DMA engine busy on the ring of
+  // pinned slots, the workers drain the slots piece by piece as they arrive (no fork / join per slot).
+  static constexpr int kPieces = 16;   // pieces of a slot handed to the workers
+  struct StreamCtl {
+    char* dst = nullptr;
+    size_t bytes = 0, nslots = 0;
+    std::atomic<long> dma_done{0};       // slots [0, dma_done) have landed in the ring
+    std::atomic<long> next{0};           // next (slot, piece) item to take
+    std::atomic<long> slot_done[4];      // pieces copied out of ring slot s, over all its occupants
+    std::atomic<long> total_done{0};
+  };
+  void drain_worker(StreamCtl* c);
   struct Job {
     char* dst;
     const char* src;
     size_t len;
+    StreamCtl* ctl = nullptr;
   };
   std::vector<Job> jobs_;
   size_t pending_ = 0, pending_pf_ = 0;   // copy jobs / page-touch jobs in flight

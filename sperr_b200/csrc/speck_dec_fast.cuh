@@ -268,9 +268,15 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
   const int J = F.J;
   const int nchA = f_nch(F, J - 1);
   const int nA = kinds == 0 ? kFW + 8 : (kinds == 1 ? kFW + 144 : kFBodyA);
-  for (int q = tid; q < nA; q += kDecThreads) {
-    unsigned sm, gm;
-    F.bodyA[q] = uint8_t(f_pixels(F, q, nchA, sm, gm));
+  // constant trip counts, fully unrolled: the table look-ups of a thread's positions are independent
+  // chains of shared-memory loads and overlap instead of queueing behind one another
+#pragma unroll
+  for (int it = 0; it < (kFBodyA + kDecThreads - 1) / kDecThreads; it++) {
+    const int q = tid + it * kDecThreads;
+    if (q < nA) {
+      unsigned sm, gm;
+      F.bodyA[q] = uint8_t(f_pixels(F, q, nchA, sm, gm));
+    }
   }
   __syncthreads();
   for (int q = tid; q < nA - 1; q += kDecThreads)
@@ -280,8 +286,10 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
   __syncthreads();
   const int nchB = f_nch(F, J - 2);
   const int nB = kinds == 1 ? kFW + 8 : kFBodyB;
-  for (int q = tid; q < nB; q += kDecThreads) {
-    if (kinds == 1 && after_one && q > 0 && !f_bit(F, q - 1))
+#pragma unroll
+  for (int it = 0; it < (kFBodyB + kDecThreads - 1) / kDecThreads; it++) {
+    const int q = tid + it * kDecThreads;
+    if (q >= nB || (kinds == 1 && after_one && q > 0 && !f_bit(F, q - 1)))
       continue;
     unsigned pos = q, c = 0;
     for (int k = 0; k < nchB - 1; k++) {   // all but the last child carry a significance bit
@@ -305,8 +313,10 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
     F.stepB[q] = f_bit(F, q) ? uint16_t((1u + F.bodyB[q + 1]) | 0x8000u) : uint16_t(1);
   __syncthreads();
   const int nchC = f_nch(F, J - 3);
-  for (int q = tid; q < kFW + 8; q += kDecThreads) {
-    if (after_one && q > 0 && !f_bit(F, q - 1))
+#pragma unroll
+  for (int it = 0; it < (kFW + 8 + kDecThreads - 1) / kDecThreads; it++) {
+    const int q = tid + it * kDecThreads;
+    if (q >= kFW + 8 || (after_one && q > 0 && !f_bit(F, q - 1)))
       continue;
     unsigned pos = q, c = 0;
     for (int k = 0; k < nchC - 1; k++) {
@@ -545,8 +555,12 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         if (tgt < unsigned(kFW))
           atomicOr(&F.mark[tgt >> 5], 1u << (tgt & 31));
       }
-      for (int q = tid; q < kFNext; q += kDecThreads)
-        nn[q] = q < kFW ? cn[cn[q]] : uint16_t(q);
+#pragma unroll
+      for (int it = 0; it < (kFNext + kDecThreads - 1) / kDecThreads; it++) {
+        const int q = tid + it * kDecThreads;
+        if (q < kFNext)
+          nn[q] = q < kFW ? cn[cn[q]] : uint16_t(q);
+      }
       __syncthreads();
       cur ^= 1;
       if (F.nxt[cur][0] >= kFW)   // 2^(r+1) steps leave the window: every token start is marked

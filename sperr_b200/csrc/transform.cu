@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kStatStrides) k_stride_stats_rows(SrcVol src, 
     return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long len = ch.n / ns;
-  const unsigned rows = unsigned(len / ch.nx), segs = ch.nx / kStatSeg;
+  const unsigned rows = unsigned(len / ch.nx), segs = ch.nx / kStatSeg, ny = ch.ny;
   const unsigned s = s0 + tid;
   const bool active = s < ns;
   const float* const vf = reinterpret_cast<const float*>(src.ptr);
@@ -75,16 +75,28 @@ __global__ void __launch_bounds__(kStatStrides) k_stride_stats_rows(SrcVol src, 
   bool diff = false;
   for (unsigned r = 0; r < rows; r++) {
     for (unsigned g = 0; g < segs; g++) {
-      // a warp fetches the segments of two strides at a time: 16 lanes x 16 bytes each
-      for (unsigned k = 2 * warp + (lane >> 4); k < unsigned(kStatStrides); k += 2 * (kStatStrides / 32)) {
-        const unsigned ss = s0 + k;
-        if (ss < ns) {
-          const unsigned long long rho = (unsigned long long)ss * rows + r;   // row of the chunk
-          const unsigned y = unsigned(rho % ch.ny), z = unsigned(rho / ch.ny);
-          const float4 v =
-              reinterpret_cast<const float4*>(vf + src_index(src, ch, g * kStatSeg, y, z))[lane & 15];
+      // a warp fetches the segments of two strides at a time (16 lanes x 16 bytes each); the loads
+      // of eight such pieces are in flight before the first one is stored
+      constexpr int kPieces = kStatStrides / 8;   // per lane and step
+#pragma unroll
+      for (int h = 0; h < kPieces; h += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const unsigned k = 2 * warp + (lane >> 4) + 8 * (h + j);
+          const unsigned ss = s0 + k;
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ss < ns) {
+            const unsigned rho = ss * rows + r;   // row of the chunk (< ny * nz: 32-bit arithmetic)
+            const unsigned z = rho / ny, y = rho - z * ny;
+            v[j] = __ldg(reinterpret_cast<const float4*>(vf + src_index(src, ch, g * kStatSeg, y, z)) + (lane & 15));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const unsigned k = 2 * warp + (lane >> 4) + 8 * (h + j);
           float* const t = &tile[k][4 * (lane & 15)];
-          t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+          t[0] = v[j].x; t[1] = v[j].y; t[2] = v[j].z; t[3] = v[j].w;
         }
       }
       __syncthreads();

@@ -43,6 +43,7 @@ struct double2 {
 struct float4 {
   float x, y, z, w;
 };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 struct float2 {
   float x, y;
 };
