@@ -545,9 +545,48 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
         };
       }
 #endif
+#ifndef SPERR_EMUL
+      // One batch, several z-slabs of chunks: the last stage of the batch runs slab group by slab
+      // group and every finished group starts its way to the host while the next is transformed.
+      if (!batched && nslabs >= 2 && per_slab * nslabs == ci.chunks.size() &&
+          total * esz >= (size_t(256) << 20) && !std::getenv("SPERR_B200_NO_GROUP_D2H")) {
+        const size_t groups = std::min<size_t>(nslabs, 4);
+        const size_t slabs_per = (nslabs + groups - 1) / groups;
+        g_decomp->group_chunks = slabs_per * per_slab;
+        if (!g_copy_stream)
+          RT_CHECK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        if (!g_d2h_worker)
+          g_d2h_worker = new SerialWorker();
+        int dev = 0;
+        RT_CHECK(cudaGetDevice(&dev));
+        const size_t plane = ci.vol[0] * ci.vol[1] * esz;
+        const auto& chunks = ci.chunks;
+        const size_t dimz = ci.vol[2];
+        g_decomp->after_group = [=, &chunks](size_t first, size_t count, cudaEvent_t ev) {
+          const size_t z0 = chunks[first].z0;
+          const size_t end = first + count;
+          const size_t z1 = end == chunks.size() ? dimz : chunks[end].z0;
+          char* hdst = static_cast<char*>(o) + z0 * plane;
+          const char* dsrc = static_cast<const char*>(g_vol.p) + z0 * plane;
+          const size_t nbytes = (z1 - z0) * plane;
+          g_d2h_worker->post([=] {
+            RT_CHECK(cudaSetDevice(dev));
+            RT_CHECK(cudaStreamWaitEvent(g_copy_stream, ev, 0));
+            HostPipe::get().d2h(hdst, dsrc, nbytes, g_copy_stream);
+            cudaEventDestroy(ev);
+          });
+        };
+      }
+#endif
       decomp_3d_device(static_cast<const uint8_t*>(src), g_stream.as<uint8_t>(), ci, output_float,
                        g_vol.p, st);
       pt.mark("decode");
+#ifndef SPERR_EMUL
+      if (!batched && g_decomp->groups_posted)
+        batched = true;   // the result is already on its way: wait for the copies below
+      g_decomp->group_chunks = 0;
+      g_decomp->after_group = nullptr;
+#endif
       if (batched) {
 #ifndef SPERR_EMUL
         g_d2h_worker->drain();
@@ -576,6 +615,8 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
       HostPipe::get().wait_idle();
       g_decomp->max_batch = 0;
       g_decomp->after_batch = nullptr;
+      g_decomp->group_chunks = 0;
+      g_decomp->after_group = nullptr;
       std::free(o);
       throw;
     }

@@ -59,12 +59,25 @@ class Decompressor {
   // the values of a batch are complete in `dst`
   size_t max_batch = 0;
   std::function<void(size_t, size_t)> after_batch;
+  // Inside a batch: when set, the final stage (inverse transform into `dst`) runs `group_chunks`
+  // chunks at a time and `after_group(first, count, event)` is called after each group has been
+  // launched; the values of those chunks are in `dst` once the event (owned by the callee) has
+  // completed. `groups_posted` tells whether the last batch was reported that way.
+  size_t group_chunks = 0;
+#ifndef SPERR_EMUL
+  std::function<void(size_t, size_t, cudaEvent_t)> after_group;
+#else
+  std::function<void(size_t, size_t, void*)> after_group;
+#endif
+  bool groups_posted = false;
 
  private:
   void run_batch(const uint8_t* h_stream, const uint8_t* d_stream, const std::vector<Chunk>& chunks,
                  const ChunkStream* cs, const SrcVol& dst, cudaStream_t st, bool is_2d);
   BatchBuffers b_;
   DecWork w_;
+  size_t batch_first_ = 0;   // index of the current batch's first chunk in the caller's list
+  bool whole_call_ = false;  // the current batch holds every chunk of the call
   rt::DBuf ids_, lis_off1_, tols_, obits_, ckey_[2], cval_[2], ccount_, coff_, csort_;
 };
 

@@ -42,6 +42,8 @@ void Decompressor::decompress(const uint8_t* h_stream, const uint8_t* d_stream,
     if (max_batch)
       nb = std::min(nb, max_batch);
     std::vector<Chunk> sub(chunks.begin() + first, chunks.begin() + first + nb);
+    batch_first_ = first;
+    whole_call_ = nb == chunks.size();   // group reporting needs slab-aligned groups: one batch only
     run_batch(h_stream, d_stream, sub, cs.data() + first, dst, st, is_2d);
     if (after_batch)
       after_batch(first, nb);
@@ -331,18 +333,42 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
   ids_.reserve(flat.size() * 4 + 4);
   rt::h2d(ids_.p, flat.data(), flat.size() * 4, st);
   rt::sync(st);
+  // The inverse transform writes final values. When every chunk goes through the fused kernels
+  // (which scatter into `dst` themselves) it is run slab group by slab group, and the caller is told
+  // after each group (with an event) so that it can start moving that part of the result while the
+  // next group is transformed.
+  groups_posted = false;
+  const bool by_groups =
+      after_group && group_chunks > 0 && !any_unfused && size_t(nc) > group_chunks && whole_call_;
   {
     rt::ProfScope pt("d.idwt", st);
-    for (size_t s = 0; s < groups.size(); s++) {
-      if (groups[s].empty())
-        continue;
-      const ShapeHeader& h = b_.shapes[s].h;
-      const int* ids = ids_.as<int>() + goff[s];
-      if (b_.h[groups[s][0]].fused)   // corrector, mean, conversion and scatter fused into level 0
-        launch_dwt_fused_inverse(dst, 1, b_.dev(), ids, int(groups[s].size()), h.nx, h.ny, h.nz, 0.0,
-                                 OutlierSink{}, cor, st);
-      else
-        launch_dwt(true, b_.dev(), ids, int(groups[s].size()), h.nx, h.ny, h.nz, is_2d, st);
+    for (size_t g0 = 0; g0 < size_t(nc); g0 += by_groups ? group_chunks : size_t(nc)) {
+      const size_t g1 = by_groups ? std::min(size_t(nc), g0 + group_chunks) : size_t(nc);
+      for (size_t s = 0; s < groups.size(); s++) {
+        if (groups[s].empty())
+          continue;
+        // chunk ids of a shape group ascend: the members inside [g0, g1) are one sub-range
+        const auto lo = std::lower_bound(groups[s].begin(), groups[s].end(), int(g0));
+        const auto hi = std::lower_bound(groups[s].begin(), groups[s].end(), int(g1));
+        if (lo == hi)
+          continue;
+        const ShapeHeader& h = b_.shapes[s].h;
+        const int* ids = ids_.as<int>() + goff[s] + (lo - groups[s].begin());
+        const int cnt = int(hi - lo);
+        if (b_.h[groups[s][0]].fused)   // corrector, mean, conversion and scatter fused into level 0
+          launch_dwt_fused_inverse(dst, 1, b_.dev(), ids, cnt, h.nx, h.ny, h.nz, 0.0, OutlierSink{}, cor, st);
+        else
+          launch_dwt(true, b_.dev(), ids, cnt, h.nx, h.ny, h.nz, is_2d, st);
+      }
+#ifndef SPERR_EMUL
+      if (by_groups) {
+        cudaEvent_t ev;
+        RT_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        RT_CHECK(cudaEventRecord(ev, st));
+        after_group(batch_first_ + g0, g1 - g0, ev);   // takes ownership of the event
+        groups_posted = true;
+      }
+#endif
     }
   }
 
