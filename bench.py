@@ -94,16 +94,43 @@ class Clocks:
         self.stop = False
         self.t = threading.Thread(target=self.run, daemon=True)
 
+    def _nvml(self):
+        """NVML handle of the GPU (same counters nvidia-smi prints, without spawning a process and
+        enumerating every device five times a second while the timed region runs)."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    idx = int(ids[self.index])
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+        except Exception:
+            return None, None
+
     def run(self):
+        nv, h = self._nvml()
         while not self.stop:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                   timeout=5).stdout.strip().split(",")
-                self.samples.append([s.strip() for s in o])
+                if nv is not None:
+                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    act = lambda bit: "Active" if (r & bit) else "Not Active"
+                    self.samples.append([str(sm), str(mx), act(nv.nvmlClocksThrottleReasonHwSlowdown),
+                                         act(nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                                         act(nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                                         act(nv.nvmlClocksThrottleReasonSwPowerCap)])
+                else:
+                    o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                        "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                       timeout=5).stdout.strip().split(",")
+                    self.samples.append([s.strip() for s in o])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.1 if nv is not None else 0.2)
 
     def __enter__(self):
         self.t.start()

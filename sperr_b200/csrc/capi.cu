@@ -427,6 +427,34 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
             RT_CHECK(cudaStreamWaitEvent(st, evs[g], 0));
         };
       }
+      else if (nslabs >= 2 && per_slab * nslabs == chunks.size() && bytes >= (size_t(256) << 20) &&
+               !std::getenv("SPERR_B200_NO_GROUP_H2D")) {
+        // One batch: upload slab groups on the copy stream; statistics and forward transform of a
+        // group start when its slabs have arrived (Compressor::before_group), the coder runs once
+        // over all chunks afterwards.
+        const size_t groups = std::min<size_t>(nslabs, 4);
+        const size_t slabs_per = (nslabs + groups - 1) / groups;
+        const size_t gc = slabs_per * per_slab;
+        if (!g_copy_stream)
+          RT_CHECK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        const size_t plane = dimx * dimy * esz;
+        for (size_t s0 = 0; s0 < nslabs; s0 += slabs_per) {
+          const size_t s1 = std::min(nslabs, s0 + slabs_per);
+          const size_t z0 = chunks[s0 * per_slab].z0;
+          const size_t z1 = s1 == nslabs ? dimz : chunks[s1 * per_slab].z0;
+          rt::h2d(static_cast<char*>(g_in.p) + z0 * plane, static_cast<const char*>(src) + z0 * plane,
+                  (z1 - z0) * plane, g_copy_stream);
+          cudaEvent_t e;
+          RT_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          RT_CHECK(cudaEventRecord(e, g_copy_stream));
+          evs.push_back(e);
+        }
+        g_comp->group_chunks = gc;
+        g_comp->before_group = [&evs, gc, st](size_t first, size_t count) {
+          for (size_t g = first / gc; g <= (first + count - 1) / gc && g < evs.size(); g++)
+            RT_CHECK(cudaStreamWaitEvent(st, evs[g], 0));
+        };
+      }
     }
     struct EvGuard {
       std::vector<cudaEvent_t>& v;
@@ -437,6 +465,8 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
         if (g_comp) {
           g_comp->max_batch = 0;
           g_comp->before_batch = nullptr;
+          g_comp->group_chunks = 0;
+          g_comp->before_group = nullptr;
         }
       }
     } ev_guard{evs};

@@ -72,6 +72,8 @@ void Compressor::compress(const SrcVol& src, const std::vector<Chunk>& chunks, i
       nb = std::min(nb, max_batch);
     if (before_batch)
       before_batch(first, nb);
+    batch_first_ = first;
+    whole_call_ = nb == chunks.size();
     std::vector<Chunk> sub(chunks.begin() + first, chunks.begin() + first + nb);
     std::vector<std::vector<uint8_t>> hdrs;
     run_batch(src, sub, mode, quality, is_2d, hdrs, st);
@@ -114,9 +116,9 @@ void Compressor::compress(const SrcVol& src, const std::vector<Chunk>& chunks, i
         hbytes.insert(hbytes.end(), oh, oh + 9);
       }
     }
-    rt::DBuf d_h(hbytes.size() + 16);
-    rt::h2d(d_h.p, hbytes.data(), hbytes.size(), st);
-    const unsigned char* dh = d_h.as<unsigned char>();
+    asm_hdr_.reserve(hbytes.size() + 16);   // grow-only members: no cudaMalloc / cudaFree per call
+    rt::h2d(asm_hdr_.p, hbytes.data(), hbytes.size(), st);
+    const unsigned char* dh = asm_hdr_.as<unsigned char>();
     for (size_t c = 0; c < nb; c++) {
       pieces.push_back({dh + hdr_off[c], off, hdrs[c].size()});
       off += hdrs[c].size();
@@ -137,9 +139,9 @@ void Compressor::compress(const SrcVol& src, const std::vector<Chunk>& chunks, i
         }
       }
     }
-    rt::DBuf d_p(pieces.size() * sizeof(Piece));
-    rt::h2d(d_p.p, pieces.data(), pieces.size() * sizeof(Piece), st);
-    const Piece* dp = d_p.as<Piece>();
+    asm_pieces_.reserve(pieces.size() * sizeof(Piece));
+    rt::h2d(asm_pieces_.p, pieces.data(), pieces.size() * sizeof(Piece), st);
+    const Piece* dp = asm_pieces_.as<Piece>();
     unsigned char* dst = d_out.as<unsigned char>();
     LAUNCH(k_copy_pieces, dim3(64, unsigned(pieces.size())), dim3(256), 0, st, dp, dst);
     rt::sync(st);
@@ -167,16 +169,23 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   not_const_.reserve(nc * 4);
   rt::h2d(nstrides_.p, ns.data(), nc * 4, st);
   rt::dset(not_const_.p, 0, nc * 4, st);
-  {
-    rt::ProfScope ps("c.stats", st);
-    launch_stats(src, b_.dev(), nc, stride_mean_.as<double>(), max_strides, nstrides_.as<unsigned>(),
-                 not_const_.as<unsigned>(), mode == kModePSNR, st);
-  }
   bool any_unfused = false, any_fused = false;
   size_t total_values = 0;
   for (auto& d : b_.h) {
     (d.fused ? any_fused : any_unfused) = true;
     total_values += d.n;
+  }
+  // Front end by slab groups (host-pointer API with a pinned source): the statistics and the forward
+  // transform of a group start as soon as `before_group` says its part of the volume has arrived,
+  // while the rest is still on its way over PCIe. Needs every chunk on the fused transform path.
+  const bool by_groups = before_group && group_chunks > 0 && !any_unfused && size_t(nc) > group_chunks &&
+                         whole_call_;
+  if (!by_groups) {
+    if (before_group)
+      before_group(batch_first_, size_t(nc));
+    rt::ProfScope ps("c.stats", st);
+    launch_stats(src, b_.dev(), nc, stride_mean_.as<double>(), max_strides, nstrides_.as<unsigned>(),
+                 not_const_.as<unsigned>(), mode == kModePSNR, st);
   }
   if (any_unfused) {
     rt::ProfScope ps("c.gather", st);
@@ -216,7 +225,33 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
                                  CorrectorList{nullptr, nullptr, nullptr}, st);
     }
   };
-  transform(false, true, OutlierSink{}, st);
+  if (by_groups) {
+    for (size_t g0 = 0; g0 < size_t(nc); g0 += group_chunks) {
+      const size_t g1 = std::min(size_t(nc), g0 + group_chunks);
+      before_group(batch_first_ + g0, g1 - g0);
+      {
+        rt::ProfScope ps("c.stats", st);
+        launch_stats(src, b_.dev() + g0, int(g1 - g0), stride_mean_.as<double>() + g0 * size_t(max_strides),
+                     max_strides, nstrides_.as<unsigned>() + g0, not_const_.as<unsigned>() + g0,
+                     mode == kModePSNR, st);
+      }
+      rt::ProfScope ps("c.dwt", st);
+      for (size_t si = 0; si < groups.size(); si++) {
+        if (groups[si].empty())
+          continue;
+        // chunk ids of a shape group ascend: the members inside [g0, g1) are one sub-range
+        const auto lo = std::lower_bound(groups[si].begin(), groups[si].end(), int(g0));
+        const auto hi = std::lower_bound(groups[si].begin(), groups[si].end(), int(g1));
+        if (lo == hi)
+          continue;
+        const ShapeHeader& h = b_.shapes[si].h;
+        launch_dwt_fused_forward(src, b_.dev(), ids_.as<int>() + goff[si] + (lo - groups[si].begin()),
+                                 int(hi - lo), h.nx, h.ny, h.nz, st);
+      }
+    }
+  }
+  else
+    transform(false, true, OutlierSink{}, st);
   if (any_unfused) {
     transform(false, false, OutlierSink{}, st);
     rt::ProfScope ps("c.absmax", st);

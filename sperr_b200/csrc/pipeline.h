@@ -28,14 +28,22 @@ class Compressor {
   // per batch (0: as many as fit), `before_batch(first, count)` runs before a batch is touched.
   size_t max_batch = 0;
   std::function<void(size_t, size_t)> before_batch;
+  // Inside a batch: when set, statistics + forward transform run `group_chunks` chunks at a time and
+  // `before_group(first, count)` is called before a group's part of the source is read (it makes
+  // the stream wait for that part); without grouping it is called once for the whole batch.
+  size_t group_chunks = 0;
+  std::function<void(size_t, size_t)> before_group;
 
  private:
+  size_t batch_first_ = 0;
+  bool whole_call_ = false;
   void run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, int mode, double quality,
                  bool is_2d, std::vector<std::vector<uint8_t>>& hdrs, cudaStream_t st);
   BatchBuffers b_;
   Speck3DEncoder enc_, enc_hp_;
   OutlierCoder out_;
   rt::DBuf stride_mean_, nstrides_, not_const_, ids_, mse_ids_, mse_q_, mse_part_, mse_out_;
+  rt::DBuf asm_hdr_, asm_pieces_;   // stream assembly: headers and the piece list
   // results of the last batch
   std::vector<EncResult> spk_res_, out_res_;
 #ifndef SPERR_EMUL
