@@ -222,7 +222,7 @@ def run_reference(args):
     dims, cores = cpu_sample_dims()
     vol = field_numpy(dims)
     nbytes = vol.size * 4
-    for _ in range(args.warmup_ref):
+    for _ in range(args.warmup):
         cpu_roundtrip(lib, prefix, vol, dims)
     tc = td = 0.0
     for _ in range(args.steps):
@@ -235,7 +235,7 @@ def run_reference(args):
         dims + (vol.size // CHUNK ** 3, TOL))
     print(json.dumps({
         "impl": "reference", "metric": "compress+decompress input GB/s", "value": val, "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup_ref,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
@@ -438,14 +438,17 @@ def measured_peak():
 # A stage is a CUDA-event range on the launching stream around that kernel (or kernel family).
 STAGE_MODELS = {
     # one launch: reads the chunk streams, writes magnitudes (4 B) + sign bits (1/8 B) per value
-    "dec.speck_decode": ("k_speck_decode (SPECK3D+1D bit-plane decoder, one CTA per chunk)",
-                         lambda n, sb: 4.125 * n + sb),
+    # one launch: reads the chunk streams, writes one state byte (plane of significance | sign) per value
+    "dec.speck_decode": ("k_speck_decode_fast (SPECK3D + SPECK1D sorting-pass decoder, one CTA per stream)",
+                         lambda n, sb: 1.0 * n + sb),
     # 5-level dyadic transform: 16 B per coefficient of every level box = 18.29 B per value
-    "c.dwt": ("forward CDF 9/7 transform, all levels (k_dwt_* family)", lambda n, sb: 18.29 * n),
-    "c.idwt": ("inverse CDF 9/7 transform, all levels (k_dwt_* family)", lambda n, sb: 18.29 * n),
-    "d.idwt": ("inverse CDF 9/7 transform, all levels (k_dwt_* family)", lambda n, sb: 18.29 * n),
+    "c.dwt": ("forward CDF 9/7 transform, all levels (k_fwd3d<*>, one launch per level)",
+              lambda n, sb: 18.29 * n),
+    "c.idwt": ("inverse CDF 9/7 transform + outlier scan, all levels (k_inv3d<*>)", lambda n, sb: 18.29 * n),
+    "d.idwt": ("inverse CDF 9/7 transform, all levels (k_inv3d<*>, one launch per level)",
+               lambda n, sb: 18.29 * n),
     "c.quantize": ("k_quantize", lambda n, sb: 12.1 * n),
-    "c.stats": ("k_stride_stats", lambda n, sb: 4.0 * n),
+    "c.stats": ("k_stride_stats_rows", lambda n, sb: 4.0 * n),
     "c.outlier_detect": ("k_outlier_count + k_outlier_write", lambda n, sb: 12.0 * n),
 }
 
@@ -457,13 +460,22 @@ def rooflines(stages, nvals, stream_bytes):
         return {}
     res = {}
 
+    # dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels from the committed ncu
+    # capture of this workload (profiles/ncu_traffic.json; bytes per launch series at 1024^3)
+    traffic = {}
+    try:
+        if nvals == 1024 ** 3:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["stages"]
+    except Exception:
+        traffic = {}
+
     def entry(k):
         ms = stages[k]["ms"]
         name, fn = STAGE_MODELS[k]
         by = fn(float(nvals), float(stream_bytes))
         ach = by / (ms * 1e-3) / GB
         return {"kernel": name, "stage": k, "bound": "hbm", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "ms": ms,
+                "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(k), "ms": ms,
                 "algorithmic_bytes": by, "peak_source": src}
     res["roofline"] = entry(max(cands)[1])
     wl = [k for k in ("c.dwt", "d.idwt") if k in stages]
@@ -490,7 +502,6 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--warmup-ref", type=int, default=1)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--e2e", type=int, default=1)
