@@ -76,6 +76,17 @@ int sperr_b200_comp_3d_dev(const void* d_src, int is_float, size_t dimx, size_t 
 int sperr_b200_decomp_3d_dev(const void* h_src, const void* d_src, size_t src_len, int output_float,
                              size_t* dimx, size_t* dimy, size_t* dimz, void* d_dst);
 
+/* Multi-resolution decoding (what sperr::SPERR3D_OMP_D::decompress(p, true) offers,
+ * include/SPERR3D_OMP_D.h:24-29, src/SPERR3D_OMP_D.cpp:70-126): besides the full volume (*dst, as
+ * sperr_decomp_3d) the coarsened volumes the inverse wavelet transform passes through, coarsest
+ * first. They exist when the volume is a whole number of chunks and the chunk shape has a dyadic
+ * transform (sperr::coarsened_resolutions, src/sperr_helper.cpp:70-123); otherwise *nlevels = 0.
+ * level_dims receives 3 extents per level (room for 8 levels), level_data one malloc'd buffer per
+ * level (room for 8 pointers; float or double like *dst; the caller frees them). */
+int sperr_b200_decomp_3d_multires(const void* src, size_t src_len, int output_float, size_t* dimx,
+                                  size_t* dimy, size_t* dimz, void** dst, size_t* nlevels,
+                                  size_t* level_dims, void** level_data);
+
 /* ---- 2a. batched 2D slices ----
  * sperr_comp_2d codes one slice per call; a GPU wants many slices in flight. These entry points
  * code `nslices` independent slices of dimx x dimy (contiguous, slice s at src + s*dimx*dimy) in one

@@ -5,8 +5,7 @@
 // utilities/sperr3d.cpp:277-329 -- compiles against this header by switching the namespace.
 // Header-only: everything goes through the C ABI of libsperr_b200.so (include/sperr_b200.h); the
 // chunk loop the reference runs on OpenMP threads runs on the GPU, set_num_threads() is accepted and
-// ignored. Multi-resolution decoding (decompress(p, true)) is not part of the hot path and returns
-// RTNType::Error.
+// ignored.
 #ifndef SPERR_B200_HPP
 #define SPERR_B200_HPP
 
@@ -121,15 +120,30 @@ class SPERR3D_OMP_D {
     return RTNType::Good;
   }
 
-  // The pointer MUST be the one given to use_bitstream() (src/SPERR3D_OMP_D.cpp:51-56).
+  // The pointer MUST be the one given to use_bitstream() (src/SPERR3D_OMP_D.cpp:51-56). With
+  // multi_res the coarsened volumes are kept as well (view_hierarchy, coarsest first).
   RTNType decompress(const void* bitstream, bool multi_res = false)
   {
-    if (bitstream == nullptr || m_ptr == nullptr || bitstream != m_ptr || multi_res)
+    if (bitstream == nullptr || m_ptr == nullptr || bitstream != m_ptr)
       return RTNType::Error;
     void* out = nullptr;
     size_t dx = 0, dy = 0, dz = 0;
-    if (sperr_decomp_3d(bitstream, m_len, 0, 0, &dx, &dy, &dz, &out) != 0)
-      return RTNType::Error;
+    m_hierarchy.clear();
+    if (!multi_res) {
+      if (sperr_decomp_3d(bitstream, m_len, 0, 0, &dx, &dy, &dz, &out) != 0)
+        return RTNType::Error;
+    }
+    else {
+      size_t nlev = 0, ld[24];
+      void* lv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+      if (sperr_b200_decomp_3d_multires(bitstream, m_len, 0, &dx, &dy, &dz, &out, &nlev, ld, lv) != 0)
+        return RTNType::Error;
+      for (size_t h = 0; h < nlev; h++) {
+        const double* p = static_cast<const double*>(lv[h]);
+        m_hierarchy.emplace_back(p, p + ld[3 * h] * ld[3 * h + 1] * ld[3 * h + 2]);
+        std::free(lv[h]);
+      }
+    }
     const double* d = static_cast<const double*>(out);
     m_vol.assign(d, d + dx * dy * dz);
     std::free(out);
@@ -138,6 +152,8 @@ class SPERR3D_OMP_D {
 
   const vecd_type& view_decoded_data() const { return m_vol; }
   vecd_type&& release_decoded_data() { return std::move(m_vol); }
+  const std::vector<vecd_type>& view_hierarchy() const { return m_hierarchy; }
+  std::vector<vecd_type>&& release_hierarchy() { return std::move(m_hierarchy); }
   dims_type get_dims() const { return m_dims; }
   dims_type get_chunk_dims() const { return m_chunk_dims; }
 
@@ -146,6 +162,7 @@ class SPERR3D_OMP_D {
   const uint8_t* m_ptr = nullptr;
   size_t m_len = 0;
   vecd_type m_vol;
+  std::vector<vecd_type> m_hierarchy;
 };
 
 }  // namespace sperr_b200

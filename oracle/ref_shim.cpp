@@ -17,6 +17,7 @@
 //   Outlier_Coder::encode / decode               src/Outlier_Coder.cpp:71-149
 //   chunk_volume, num_of_xforms, ...             src/sperr_helper.cpp
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -252,3 +253,33 @@ size_t ref_chunk_volume(size_t vx, size_t vy, size_t vz, size_t cx, size_t cy, s
 }
 
 }  // extern "C"
+
+// ---- multi-resolution decoding through the reference's own class (SPERR3D_OMP_D.cpp:51-135) ----
+#include "SPERR3D_OMP_D.h"
+
+extern "C" int ref_decomp_3d_multires(const void* src, size_t len, size_t* nlevels, size_t* level_dims,
+                                      double** levels, double** full, size_t* dims3)
+{
+  sperr::SPERR3D_OMP_D dec;
+  dec.set_num_threads(1);   // one decompressor object: a constant chunk then shows the reference's stale-data quirk deterministically
+  if (dec.use_bitstream(src, len) != sperr::RTNType::Good)
+    return -1;
+  if (dec.decompress(src, true) != sperr::RTNType::Good)
+    return -1;
+  const auto d = dec.get_dims();
+  for (int i = 0; i < 3; i++)
+    dims3[i] = d[i];
+  const auto& vol = dec.view_decoded_data();
+  *full = static_cast<double*>(std::malloc(vol.size() * sizeof(double)));
+  std::memcpy(*full, vol.data(), vol.size() * sizeof(double));
+  const auto& h = dec.view_hierarchy();
+  const auto res = sperr::coarsened_resolutions(d, dec.get_chunk_dims());
+  *nlevels = h.size();
+  for (size_t i = 0; i < h.size() && i < 8; i++) {
+    for (int k = 0; k < 3; k++)
+      level_dims[3 * i + k] = res[i][k];
+    levels[i] = static_cast<double*>(std::malloc(h[i].size() * sizeof(double)));
+    std::memcpy(levels[i], h[i].data(), h[i].size() * sizeof(double));
+  }
+  return 0;
+}

@@ -778,6 +778,90 @@ int sperr_decomp_2d(const void* src, size_t src_len, int output_float, size_t di
   return sperr_b200_decomp_2d_batch(src, &src_len, 1, output_float, dimx, dimy, dst);
 }
 
+// Multi-resolution decoding (SPERR3D_OMP_D::decompress(p, true), /root/reference/src/SPERR3D_OMP_D.cpp:
+// 51-135; sperr::coarsened_resolutions, src/sperr_helper.cpp:70-123). The reference's C API has no
+// entry for it; this is what the class mirror and tools/sperr3d use.
+int sperr_b200_decomp_3d_multires(const void* src, size_t src_len, int output_float, size_t* dimx,
+                                  size_t* dimy, size_t* dimz, void** dst, size_t* nlevels,
+                                  size_t* level_dims, void** level_data)
+{
+  if (*dst != nullptr)
+    return 1;
+  std::lock_guard<std::mutex> lock(g_mutex);
+  return guarded([&] {
+    cudaStream_t st = 0;
+    ContainerInfo ci;
+    if (!parse_container(static_cast<const uint8_t*>(src), src_len, ci))
+      return -1;
+    const size_t esz = output_float ? 4 : 8;
+    // levels exist when the volume is a whole number of dyadic chunks
+    MultiRes mr;
+    mr.is_float = output_float;
+    bool divisible = true;
+    for (int i = 0; i < 3; i++)
+      divisible &= ci.vol[i] % ci.cd[i] == 0;
+    const int L = (divisible && ci.cd[2] > 1) ? can_use_dyadic(ci.cd[0], ci.cd[1], ci.cd[2]) : -1;
+    std::vector<rt::DBuf> bufs;
+    if (L >= 1 && L <= 8 && !BatchBuffers::no_fused()) {
+      bufs.resize(size_t(L));
+      for (int lev = L; lev >= 1; lev--) {
+        std::array<size_t, 3> d;
+        for (int i = 0; i < 3; i++)
+          d[i] = calc_approx_detail_len(ci.cd[i], size_t(lev))[0] * (ci.vol[i] / ci.cd[i]);
+        mr.dims.push_back(d);
+        bufs[size_t(L - lev)].alloc(d[0] * d[1] * d[2] * esz);
+        mr.d_level.push_back(bufs[size_t(L - lev)].p);
+      }
+    }
+    const size_t total = ci.vol[0] * ci.vol[1] * ci.vol[2];
+    g_stream.reserve(src_len);
+    HostPipe::get().h2d(g_stream.p, src, src_len, st);
+    g_vol.reserve(total * esz);
+    if (!g_decomp)
+      g_decomp = new Decompressor();
+    g_decomp->max_batch = 0;
+    g_decomp->after_batch = nullptr;
+    g_decomp->multires = mr.d_level.empty() ? nullptr : &mr;
+    try {
+      decomp_3d_device(static_cast<const uint8_t*>(src), g_stream.as<uint8_t>(), ci, output_float, g_vol.p, st);
+    }
+    catch (...) {
+      g_decomp->multires = nullptr;
+      throw;
+    }
+    g_decomp->multires = nullptr;
+    std::vector<void*> outs;
+    auto fail = [&] {
+      for (void* p : outs)
+        std::free(p);
+      return -1;
+    };
+    void* o = std::malloc(std::max<size_t>(total * esz, 1));
+    if (!o)
+      return fail();
+    outs.push_back(o);
+    HostPipe::get().d2h(o, g_vol.p, total * esz, st);
+    for (size_t h = 0; h < mr.d_level.size(); h++) {
+      const size_t nb = mr.dims[h][0] * mr.dims[h][1] * mr.dims[h][2] * esz;
+      void* p = std::malloc(std::max<size_t>(nb, 1));
+      if (!p)
+        return fail();
+      outs.push_back(p);
+      HostPipe::get().d2h(p, mr.d_level[h], nb, st);
+    }
+    HostPipe::get().wait_idle();
+    *dst = o;
+    *dimx = ci.vol[0]; *dimy = ci.vol[1]; *dimz = ci.vol[2];
+    *nlevels = mr.d_level.size();
+    for (size_t h = 0; h < mr.d_level.size(); h++) {
+      for (int i = 0; i < 3; i++)
+        level_dims[3 * h + i] = mr.dims[h][i];
+      level_data[h] = outs[h + 1];
+    }
+    return 0;
+  });
+}
+
 // C_API::sperr_trunc_3d (/root/reference/src/SPERR_C_API.cpp:260-281) over
 // SPERR3D_Stream_Tools::progressive_truncate / m_progressive_helper
 // (src/SPERR3D_Stream_Tools.cpp:131-226): keep the first pct % of every chunk's stream (at least 64

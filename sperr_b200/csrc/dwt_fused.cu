@@ -473,9 +473,58 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
   }
 }
 
+// Multi-resolution output (CDF97::idwt3d_multi_res, /root/reference/src/CDF97.cpp:150-168;
+// SPECK_FLT::decompress :592-603; SPERR3D_OMP_D.cpp:70-126): the approximation box a chunk holds
+// before transform level `lev` is undone, plus the chunk mean, placed at the chunk's position in
+// the coarsened volume. After the fused inverse transform those boxes are still there: level L in
+// the corner of `coef`, levels 1 .. L-1 compact in `scratch`.
+__global__ void k_level_gather(const ChunkDev* chunks, int ax, int ay, int az, long long src_off,
+                               void* dst, int is_float, unsigned long long vx, unsigned long long vy)
+{
+  const ChunkDev& ch = chunks[blockIdx.y];
+  const unsigned long long n = (unsigned long long)ax * ay * az;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  // position of the chunk in the chunk grid (the volume is divisible by the chunk extents)
+  const unsigned long long ox = (unsigned long long)(ch.x0 / ch.nx) * ax, oy = (unsigned long long)(ch.y0 / ch.ny) * ay,
+                           oz = (unsigned long long)(ch.z0 / ch.nz) * az;
+  for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+    const unsigned x = unsigned(e % ax), y = unsigned((e / ax) % ay), z = unsigned(e / ((unsigned long long)ax * ay));
+    double v;
+    if (ch.is_const)
+      v = ch.first_val;   // the reference leaves such a chunk's coarse boxes unwritten
+    else {
+      const double c = src_off >= 0 ? ch.scratch[src_off + e]
+                                    : ch.coef[((size_t)z * ch.ny + y) * ch.nx + x];
+      v = __dadd_rn(c, ch.mean);
+    }
+    const unsigned long long g = ((oz + z) * vy + (oy + y)) * vx + (ox + x);
+    if (is_float)
+      reinterpret_cast<float*>(dst)[g] = __double2float_rn(v);
+    else
+      reinterpret_cast<double*>(dst)[g] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+
+// Coarse level `h` (0 = coarsest) of chunks of shape nx x ny x nz: see k_level_gather. `dst` is the
+// coarsened volume, vx x vy values per plane.
+void launch_level_gather(const ChunkDev* d_chunks, int nchunks, uint32_t nx, uint32_t ny, uint32_t nz,
+                         int h, void* dst, int is_float, size_t vx, size_t vy, cudaStream_t st)
+{
+  const int L = can_use_dyadic(nx, ny, nz);
+  const int lev = L - h;
+  long long off[8];
+  fused_scratch_elems(nx, ny, nz, off);
+  const int ax = int(calc_approx_detail_len(nx, lev)[0]), ay = int(calc_approx_detail_len(ny, lev)[0]),
+            az = int(calc_approx_detail_len(nz, lev)[0]);
+  const size_t n = size_t(ax) * ay * az;
+  const unsigned gx = unsigned(std::min<size_t>((n + 255) / 256, 1024));
+  LAUNCH(k_level_gather, dim3(gx, unsigned(nchunks)), dim3(256), 0, st, d_chunks, ax, ay, az,
+         lev == L ? -1ll : off[lev], dst, is_float, (unsigned long long)vx, (unsigned long long)vy);
+}
 
 // Doubles of ChunkDev::scratch a chunk of this shape needs (compact boxes of levels 1 .. L-1), and
 // the offset of every level's box.

@@ -56,6 +56,14 @@ struct ChunkStream {   // where a chunk's stream sits inside the container
   size_t off, len;
 };
 
+// Multi-resolution decoding: device buffers of the coarsened volumes, coarsest first
+// (sperr::coarsened_resolutions, /root/reference/src/sperr_helper.cpp:70-123).
+struct MultiRes {
+  int is_float = 0;
+  std::vector<void*> d_level;                 // one coarsened volume per level
+  std::vector<std::array<size_t, 3>> dims;    // its extents
+};
+
 class Decompressor {
  public:
   // Decodes `chunks` (streams at h_stream + cs[i].off; d_stream is the same container in device
@@ -78,6 +86,9 @@ class Decompressor {
   std::function<void(size_t, size_t, void*)> after_group;
 #endif
   bool groups_posted = false;
+  // when set, every batch also writes the coarse levels of its chunks (all chunks must have the
+  // same dyadic shape and the volume must be divisible by it: the caller checks)
+  const MultiRes* multires = nullptr;
 
  private:
   void run_batch(const uint8_t* h_stream, const uint8_t* d_stream, const std::vector<Chunk>& chunks,

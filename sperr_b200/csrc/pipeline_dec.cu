@@ -372,6 +372,16 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     }
   }
 
+  // ---- multi-resolution output: the coarse boxes the fused inverse transform left behind ----
+  if (multires) {
+    if (any_unfused && nc > 0 && !b_.h[0].fused)
+      throw std::runtime_error("multi-resolution decoding needs the fused transform path");
+    const ShapeHeader& h0 = b_.shapes[b_.h[0].shape].h;
+    for (size_t h = 0; h < multires->d_level.size(); h++)
+      launch_level_gather(b_.dev(), nc, h0.nx, h0.ny, h0.nz, int(h), multires->d_level[h], multires->is_float,
+                          multires->dims[h][0], multires->dims[h][1], st);
+  }
+
   // ---- the other chunks: correctors, mean, conversion, scatter; constant chunks: fill ----
   if (any_unfused) {
     rt::ProfScope psc("d.scatter", st);

@@ -150,3 +150,35 @@ def check_slice(lib, oracle, case):
         it = np.uint32 if of else np.uint64
         assert np.array_equal(dec.view(it), dexp.view(it)), "%d values differ" % int(
             np.count_nonzero(dec.view(it) != dexp.view(it)))
+
+
+# ---- multi-resolution decoding: (fixture or synthetic dims, volume dims, chunk dims, mode, quality) ----
+MULTIRES_SMALL = [
+    ("vorticity.128_128_41", (128, 128, 41), (64, 64, 41), 3, 1e-5),   # 3 levels, 2 x 2 x 1 chunks
+    ("wmag16.float", (16, 16, 16), (16, 16, 16), 2, 60.0),             # 1 level, one chunk
+    ((64, 64, 64), (64, 64, 64), (32, 32, 32), 3, 1e-3),               # synthetic, 2 levels, 8 chunks
+    ("wmag17.float", (17, 17, 17), (8, 8, 8), 3, 0.3),                 # not divisible: no hierarchy
+]
+
+
+def check_multires(lib, ref, oracle, case):
+    """full volume and every coarse level bit-identical to the reference class (fp64)"""
+    name, dims, chunks, mode, q = case
+    v = refs.load_test_data(name) if isinstance(name, str) else refs.synthetic_field(name, seed=5)
+    rc, stream = oracle.comp_3d(v, dims, chunks, mode, q)
+    assert rc == 0
+    rc, full, d, levels, ldims = lib.decomp_3d_multires(stream, False)
+    if any(a % b for a, b in zip(dims, chunks)):
+        # not a whole number of chunks: no hierarchy (the reference's class reads out of bounds here;
+        # its CLI refuses the combination, utilities/sperr3d.cpp:236-250), plain decode otherwise
+        rc2, exp, d2 = oracle.decomp_3d(stream, False)
+        assert rc == rc2 == 0 and d == d2 and levels == []
+        assert np.array_equal(full.view(np.uint64), exp.view(np.uint64))
+        return 0
+    rc2, rfull, rd, rlevels, rldims = ref.decomp_3d_multires(stream)
+    assert rc == rc2 == 0 and d == rd
+    assert np.array_equal(full.view(np.uint64), rfull.view(np.uint64))
+    assert ldims == rldims, (ldims, rldims)
+    for a, b in zip(levels, rlevels):
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    return len(levels)

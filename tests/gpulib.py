@@ -174,6 +174,35 @@ class Lib:
         _libc.free(dst)
         return 0, out
 
+    def decomp_3d_multires(self, stream, output_float=False):
+        """-> (rc, full volume, dims, [coarse volumes, coarsest first], [their dims])"""
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        f = self.lib.sperr_b200_decomp_3d_multires
+        f.restype = C.c_int
+        f.argtypes = [vp, sz, C.c_int, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), C.POINTER(vp),
+                      C.POINTER(sz), vp, vp]
+        dx, dy, dz, nl = sz(0), sz(0), sz(0), sz(0)
+        dst = vp(None)
+        ld = np.zeros(24, dtype=np.uint64)
+        lv = (vp * 8)()
+        rc = f(_ptr(stream), stream.size, int(output_float), C.byref(dx), C.byref(dy), C.byref(dz),
+               C.byref(dst), C.byref(nl), _ptr(ld), C.cast(lv, vp))
+        if rc != 0:
+            return rc, None, None, None, None
+        dt = np.float32 if output_float else np.float64
+        isz = np.dtype(dt).itemsize
+        n = dx.value * dy.value * dz.value
+        full = np.frombuffer(C.string_at(dst.value, n * isz), dtype=dt).copy()
+        _libc.free(dst)
+        levels, dims = [], []
+        for h in range(nl.value):
+            d = tuple(int(x) for x in ld[3 * h:3 * h + 3])
+            m = d[0] * d[1] * d[2]
+            levels.append(np.frombuffer(C.string_at(lv[h], m * isz), dtype=dt).copy())
+            dims.append(d)
+            _libc.free(lv[h])
+        return 0, full, (dx.value, dy.value, dz.value), levels, dims
+
     # ---- 2D slices ----
     def stage_speck2d_encode(self, mags, signs, dims, budget_bits=0):
         mags = np.ascontiguousarray(mags, dtype=np.uint64)

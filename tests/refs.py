@@ -233,6 +233,29 @@ class Coder:
         libc_free(dst)
         return 0, out
 
+    def decomp_3d_multires(self, stream):
+        """reference only (oracle/ref_shim.cpp over sperr::SPERR3D_OMP_D): -> (rc, full, dims,
+        [coarse volumes, coarsest first], [their dims]), all fp64"""
+        assert self.is_ref
+        stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        f = self.lib.ref_decomp_3d_multires; f.restype = C.c_int
+        f.argtypes = [vp, sz, C.POINTER(sz), vp, vp, C.POINTER(vp), vp]
+        nl = sz(0); ld = np.zeros(24, dtype=np.uint64); lv = (vp * 8)(); full = vp(None)
+        d3 = np.zeros(3, dtype=np.uint64)
+        rc = f(_ptr(stream), stream.size, C.byref(nl), _ptr(ld), C.cast(lv, vp), C.byref(full), _ptr(d3))
+        if rc != 0:
+            return rc, None, None, None, None
+        dims = tuple(int(x) for x in d3)
+        vol = np.frombuffer(C.string_at(full.value, dims[0] * dims[1] * dims[2] * 8), dtype=np.float64).copy()
+        libc_free(full)
+        levels, ldims = [], []
+        for h in range(nl.value):
+            d = tuple(int(x) for x in ld[3 * h:3 * h + 3])
+            levels.append(np.frombuffer(C.string_at(lv[h], d[0] * d[1] * d[2] * 8), dtype=np.float64).copy())
+            ldims.append(d)
+            libc_free(lv[h])
+        return 0, vol, dims, levels, ldims
+
     def comp_2d(self, img, dims, mode, quality, header=False):
         img = np.ascontiguousarray(img)
         f = self._capi("comp_2d"); f.restype = C.c_int

@@ -103,3 +103,27 @@ def test_sperr2d_files_match_oracle(sperr2d, oracle, tmp_path):
     assert rc == 0, out
     _, dexp = oracle.decomp_2d(exp[10:], (90, 90), True)
     assert np.array_equal(np.fromfile(df, dtype=np.uint32), dexp.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_sperr3d_lowres_files(sperr3d, oracle, tmp_path):
+    """--decomp_lowres_d: one file per coarsened level, named like the reference's, holding what the
+    reference class returns (oracle/ref_shim.cpp)"""
+    ref = refs.ref()
+    if ref is None or not hasattr(ref.lib, "ref_decomp_3d_multires"):
+        pytest.skip("reference library with the multi-resolution shim not built")
+    src = os.path.join(ROOT, "tests", "golden", "vorticity.128_128_41")
+    bs, low = str(tmp_path / "s.sperr"), str(tmp_path / "low")
+    rc, out = run(sperr3d, "-c", "--ftype", "32", "--dims", "128", "128", "41", "--chunks", "64", "64", "41",
+                  "--pwe", "1e-5", "--bitstream", bs, src)
+    assert rc == 0, out
+    rc, out = run(sperr3d, "-d", "--decomp_lowres_d", low, bs)
+    assert rc == 0, out
+    rc2, full, d, levels, ldims = ref.decomp_3d_multires(np.fromfile(bs, dtype=np.uint8))
+    assert rc2 == 0 and len(levels) == 3
+    for lv, ld in zip(levels, ldims):
+        f = "%s.%dx%dx%d" % (low, ld[0], ld[1], ld[2])
+        assert np.array_equal(np.fromfile(f, dtype=np.uint64), lv.view(np.uint64)), f
+    rc, out = run(sperr3d, "-c", "--ftype", "32", "--dims", "128", "128", "41", "--chunks", "60", "64", "41",
+                  "--pwe", "1e-5", "--decomp_lowres_f", low, src)
+    assert rc != 0 and "cannot support multi-resolution decoding" in out

@@ -3,8 +3,6 @@
 // on the class mirrors of include/sperr_b200.hpp, i.e. on the C ABI of libsperr_b200.so. Host code
 // only: argument parsing (CLI11 is not available here, so a small parser of its own), file I/O and
 // the quality statistics of --print_stats (calc_stats / calc_mean_var, src/sperr_helper.cpp:429-640).
-// Not offered: --decomp_lowres_f / --decomp_lowres_d (multi-resolution decoding is outside the hot
-// path; the options are recognised and refused).
 //
 //   sperr3d -c --ftype 32 --dims 128 128 128 --pwe 1e-3 --bitstream out.sperr in.float
 //   sperr3d -d --decomp_f out.float out.sperr
@@ -71,6 +69,57 @@ int output_buffer(const sp::vecd_type& buf, const std::string& name_f64, const s
   return 0;
 }
 
+// utilities/sperr3d.cpp:15-67: one file per coarsened level, named <name>.<X>x<Y>x<Z>
+int output_hierarchy(const std::vector<sp::vecd_type>& hierarchy, const std::vector<std::array<size_t, 3>>& res,
+                     const std::string& lowres_f64, const std::string& lowres_f32)
+{
+  auto fname = [&](const std::string& base, size_t i) {
+    return base + "." + std::to_string(res[i][0]) + "x" + std::to_string(res[i][1]) + "x" + std::to_string(res[i][2]);
+  };
+  for (size_t i = 0; i < hierarchy.size(); i++) {
+    if (!lowres_f64.empty() && !write_bytes(fname(lowres_f64, i), hierarchy[i].data(), hierarchy[i].size() * 8)) {
+      std::cout << "Writing decompressed hierarchy failed: " << fname(lowres_f64, i) << std::endl;
+      return 1;
+    }
+    if (!lowres_f32.empty()) {
+      std::vector<float> f(hierarchy[i].size());
+      std::copy(hierarchy[i].cbegin(), hierarchy[i].cend(), f.begin());
+      if (!write_bytes(fname(lowres_f32, i), f.data(), f.size() * 4)) {
+        std::cout << "Writing decompressed hierarchy failed: " << fname(lowres_f32, i) << std::endl;
+        return 1;
+      }
+    }
+  }
+  return 0;
+}
+
+// sperr::coarsened_resolutions(vdims, cdims), src/sperr_helper.cpp:70-123 (3D)
+std::vector<std::array<size_t, 3>> coarsened_resolutions(std::array<size_t, 3> v, std::array<size_t, 3> c)
+{
+  std::vector<std::array<size_t, 3>> out;
+  for (int i = 0; i < 3; i++)
+    if (c[i] == 0 || v[i] % c[i] != 0)
+      return out;
+  if (c[2] <= 1 || c[1] < 2)
+    return out;
+  auto nxf = [](size_t len) { size_t n = 0; while (len >= 9) { n++; len -= len / 2; } return std::min<size_t>(n, 6); };
+  const size_t xy = nxf(std::min(c[0], c[1])), z = nxf(c[2]);
+  if (!(xy == z || (xy >= 5 && z >= 5)))
+    return out;
+  const size_t L = std::min(xy, z);
+  for (size_t lev = L; lev > 0; lev--) {
+    std::array<size_t, 3> r;
+    for (int i = 0; i < 3; i++) {
+      size_t low = c[i];
+      for (size_t k = 0; k < lev; k++)
+        low -= low / 2;
+      r[i] = low * (v[i] / c[i]);
+    }
+    out.push_back(r);
+  }
+  return out;
+}
+
 // src/sperr_helper.cpp:429-513: {rmse, linfty, psnr, min, max}, sums taken per stride of 8192
 template <typename T>
 std::array<T, 5> calc_stats(const T* a, const T* b, size_t n)
@@ -132,6 +181,8 @@ void usage()
       "  --bitstream FILE         Output compressed bitstream.\n"
       "  --decomp_f FILE          Output decompressed volume in f32 precision.\n"
       "  --decomp_d FILE          Output decompressed volume in f64 precision.\n"
+      "  --decomp_lowres_f FILE   Output lower resolutions of the decompressed volume in f32 precision.\n"
+      "  --decomp_lowres_d FILE   Output lower resolutions of the decompressed volume in f64 precision.\n"
       "  --print_stats            Print statistics measuring the compression quality.\n"
       "Compression settings:\n"
       "  --chunks X Y Z           Preferred chunk size. Default: 256 256 256\n"
@@ -205,11 +256,18 @@ int main(int argc, char* argv[])
     std::cout << "Compression quality (--psnr, --pwe) must be positive!" << std::endl;
     return 1;
   }
-  if (!lowres_f32.empty() || !lowres_f64.empty()) {
-    std::cout << "Multi-resolution decoding (--decomp_lowres_*) is not available in this build." << std::endl;
+  const bool multi_res = !lowres_f32.empty() || !lowres_f64.empty();
+  if (cflag && multi_res && coarsened_resolutions(dims, {std::min(chunks[0], dims[0]), std::min(chunks[1], dims[1]),
+                                                          std::min(chunks[2], dims[2])}).empty()) {
+    std::printf(
+        " Warning: the combo of volume dimension (%lu, %lu, %lu) and chunk dimension"
+        " (%lu, %lu, %lu)\n cannot support multi-resolution decoding. "
+        " Try to use chunk dimensions that\n are similar in length and"
+        " can divide the volume dimension.\n",
+        dims[0], dims[1], dims[2], chunks[0], chunks[1], chunks[2]);
     return 1;
   }
-  if (dflag && decomp_f32.empty() && decomp_f64.empty()) {
+  if (dflag && decomp_f32.empty() && decomp_f64.empty() && !multi_res) {
     std::cout << "SPERR needs an output destination when decoding!" << std::endl;
     return 1;
   }
@@ -239,14 +297,17 @@ int main(int argc, char* argv[])
       std::cout << "Writing compressed bitstream failed: " << bitstream << std::endl;
       return 1;
     }
-    if (print_stats || !decomp_f64.empty() || !decomp_f32.empty()) {
+    if (print_stats || !decomp_f64.empty() || !decomp_f32.empty() || multi_res) {
       sp::SPERR3D_OMP_D decoder;
       decoder.use_bitstream(stream.data(), stream.size());
-      if (decoder.decompress(stream.data()) != sp::RTNType::Good) {
+      if (decoder.decompress(stream.data(), multi_res) != sp::RTNType::Good) {
         std::cout << "Decompression failed!" << std::endl;
         return 1;
       }
       const auto outputd = decoder.release_decoded_data();
+      if (output_hierarchy(decoder.view_hierarchy(), coarsened_resolutions(decoder.get_dims(), decoder.get_chunk_dims()),
+                           lowres_f64, lowres_f32))
+        return 1;
       if (output_buffer(outputd, decomp_f64, decomp_f32))
         return 1;
       if (print_stats) {
@@ -275,11 +336,14 @@ int main(int argc, char* argv[])
   else {
     sp::SPERR3D_OMP_D decoder;
     decoder.use_bitstream(input.data(), input.size());
-    if (decoder.decompress(input.data()) != sp::RTNType::Good) {
+    if (decoder.decompress(input.data(), multi_res) != sp::RTNType::Good) {
       std::cout << "Decompression failed!" << std::endl;
       return 1;
     }
     const auto outputd = decoder.release_decoded_data();
+    if (output_hierarchy(decoder.view_hierarchy(), coarsened_resolutions(decoder.get_dims(), decoder.get_chunk_dims()),
+                         lowres_f64, lowres_f32))
+      return 1;
     if (output_buffer(outputd, decomp_f64, decomp_f32))
       return 1;
   }
