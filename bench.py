@@ -250,6 +250,7 @@ def workload_config(n):
     return {"workload": "synthetic smooth 1024x1024x%d fp32, PWE tol 1e-3, 256^3 chunks (%d chunks), "
                         "step = compress + decompress" % (1024 * n, 64 * n),
             "l2": "inputs (4 GiB per GPU) larger than L2", "chunk": [CHUNK] * 3, "mode": "PWE",
+            "container": "value: kept in HBM on rank 0 between compress and decompress; e2e: host buffers",
             "tolerance": TOL}
 
 
@@ -293,7 +294,10 @@ def run_ours(args):
     state = {}
 
     def comp_dev():
-        s = sharded.compress_3d_sharded(L.lib, box, gdims, (CHUNK,) * 3, 3, TOL)
+        # device-resident step: the reference-layout container is assembled in rank 0's HBM
+        # (sharded.DeviceContainer); only chunk lengths and chunk headers visit the host. The e2e
+        # figure below is the one that includes every host <-> device copy.
+        s = sharded.compress_3d_sharded(L.lib, box, gdims, (CHUNK,) * 3, 3, TOL, device_container=True)
         state["stream"] = s
         return s
 

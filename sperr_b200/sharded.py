@@ -102,10 +102,27 @@ def _pinned_u8(n, key):
     return t
 
 
-def compress_3d_sharded(cdll, box, vol, chunk, mode, quality, group=None):
+class DeviceContainer:
+    """A reference-layout container that stays where it was produced: `data` is a uint8 tensor on
+    rank 0's device holding header + chunk streams, `header` the same header bytes on the host
+    (they are all a reader needs to find the chunks). `numpy()` brings the whole thing to the host."""
+
+    def __init__(self, data, header):
+        self.data, self.header = data, header
+
+    @property
+    def size(self):
+        return int(self.data.numel())
+
+    def numpy(self):
+        return self.data.cpu().numpy()
+
+
+def compress_3d_sharded(cdll, box, vol, chunk, mode, quality, group=None, device_container=False):
     """box: this rank's part of the volume as a contiguous float32 / float64 torch tensor (z, y, x)
     that lives where the library computes (CUDA device for libsperr_b200.so). Returns the container
-    (uint8 numpy array, backed by a reused staging buffer) on rank 0 and None elsewhere."""
+    on rank 0 and None elsewhere: a uint8 numpy array backed by a reused pinned staging buffer, or --
+    device_container=True -- a DeviceContainer whose bytes never leave rank 0's device."""
     rank, world = _world(group)
     sh = Shard(cdll, vol, chunk, rank, world)
     assert box.is_contiguous() and tuple(box.shape) == sh.box_extent[::-1], (box.shape, sh.box_extent)
@@ -146,6 +163,18 @@ def compress_3d_sharded(cdll, box, vol, chunk, mode, quality, group=None):
     all32 = np.concatenate(lens_by_rank).astype(np.uint32)
     hlen = int(sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), None, sh.nchunks, None, 0))
     total = hlen + sum(bytes_by_rank)
+    if device_container:
+        hdr = np.zeros(hlen, dtype=np.uint8)
+        got = sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), all32.ctypes.data_as(vp),
+                                                  sh.nchunks, hdr.ctypes.data_as(vp), hdr.size)
+        assert got == hlen
+        data = torch.empty(total, dtype=torch.uint8, device=dev)
+        data[:hlen].copy_(torch.from_numpy(hdr))
+        pos = hlen
+        for r in range(world):
+            data[pos:pos + bytes_by_rank[r]].copy_(parts[r][:bytes_by_rank[r]])
+            pos += bytes_by_rank[r]
+        return DeviceContainer(data, hdr)
     stage = _pinned_u8(total, "container")
     out = stage.numpy()[:total]
     got = sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), all32.ctypes.data_as(vp),
@@ -178,8 +207,61 @@ def parse_container(cdll, stream):
     return tuple(vol), tuple(chunk), bool(isf.value), hlen.value, lens
 
 
+def parse_header_only(cdll, header, total_len):
+    """parse_container for a container whose header bytes are on the host and whose total length is
+    known (the chunk streams may live elsewhere)."""
+    cdll = _bind(cdll)
+    header = np.ascontiguousarray(header, dtype=np.uint8)
+    vol, chunk = sz3(), sz3()
+    isf, hlen, nch = C.c_int(0), sz(0), sz(0)
+    rc = cdll.sperr_b200_parse_container(header.ctypes.data_as(vp), header.size, vol, chunk, C.byref(isf),
+                                         C.byref(hlen), None, 0, C.byref(nch))
+    if rc != 0 or hlen.value != header.size:
+        raise ValueError("not a SPERR 3D container header")
+    lens = np.zeros(nch.value, dtype=np.uint32)
+    rc = cdll.sperr_b200_parse_container(header.ctypes.data_as(vp), header.size, vol, chunk, C.byref(isf),
+                                         C.byref(hlen), lens.ctypes.data_as(vp), lens.size, C.byref(nch))
+    if rc != 0 or hlen.value + int(lens.astype(np.int64).sum()) != total_len:
+        raise ValueError("truncated SPERR 3D container")
+    return tuple(vol), tuple(chunk), bool(isf.value), hlen.value, lens
+
+
+def _chunk_headers_to_host(d_streams, lens, nb):
+    """Host image of this rank's chunk streams that holds only the bytes the host-side parser reads
+    (SPECK_FLT::use_bitstream, /root/reference/src/SPECK_FLT.cpp:27-109): per chunk the 17-byte
+    conditioner header + 9-byte SPECK header, and the 9-byte header of the outlier stream where one
+    follows. Everything else reads as zero (calloc'd pages that are never touched)."""
+    dev = d_streams.device
+    lens64 = lens.astype(np.int64)
+    offs = np.concatenate([[0], np.cumsum(lens64)])[:-1]
+    h = np.zeros(max(nb, 1), dtype=np.uint8)
+    if lens64.size == 0:
+        return h[:nb]
+    idx = (offs[:, None] + np.arange(26)[None, :]).reshape(-1)
+    idx = np.minimum(idx, max(nb - 1, 0))
+    first = d_streams[torch.from_numpy(idx).to(dev)].cpu().numpy().reshape(-1, 26)
+    pos2 = []
+    for c in range(lens64.size):
+        n = int(min(26, lens64[c]))
+        h[offs[c]:offs[c] + n] = first[c, :n]
+        if lens64[c] < 26 or (first[c, 0] & 1):
+            continue
+        tb = int(np.frombuffer(first[c, 18:26].tobytes(), dtype=np.uint64)[0])
+        speck_len = min(9 + (tb + 7) // 8, int(lens64[c]) - 17)
+        p = int(offs[c]) + 17 + speck_len
+        if p + 9 <= int(offs[c] + lens64[c]):
+            pos2.append(p)
+    if pos2:
+        idx2 = (np.asarray(pos2, dtype=np.int64)[:, None] + np.arange(9)[None, :]).reshape(-1)
+        second = d_streams[torch.from_numpy(idx2).to(dev)].cpu().numpy().reshape(-1, 9)
+        for k, p in enumerate(pos2):
+            h[p:p + 9] = second[k]
+    return h[:nb]
+
+
 def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
-    """stream: the container (uint8 numpy array) on rank 0, ignored elsewhere. Every rank returns
+    """stream: the container (uint8 numpy array, or the DeviceContainer compress_3d_sharded returned)
+    on rank 0, ignored elsewhere. Every rank returns
     (box, shard): its part of the decoded volume as a (z, y, x) tensor on `device`, and the Shard that
     says where the box sits."""
     rank, world = _world(group)
@@ -187,8 +269,12 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
     dev = torch.device(device)
     src0 = dist.get_global_rank(group, 0) if group is not None else 0
     meta = [None]
+    on_device = isinstance(stream, DeviceContainer)
     if rank == 0:
-        vol, chunk, isf, hlen, lens = parse_container(cdll, stream)
+        if on_device:
+            vol, chunk, isf, hlen, lens = parse_header_only(cdll, stream.header, stream.size)
+        else:
+            vol, chunk, isf, hlen, lens = parse_container(cdll, stream)
         meta = [(vol, chunk, lens)]
     dist.broadcast_object_list(meta, src=src0, group=group)
     vol, chunk, lens = meta[0]
@@ -199,7 +285,7 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
     parts = None
     if rank == 0:
         # one upload of the container, then equal-sized device slices for the scatter
-        d_all = torch.from_numpy(np.ascontiguousarray(stream)).to(dev)
+        d_all = stream.data if on_device else torch.from_numpy(np.ascontiguousarray(stream)).to(dev)
         parts, pos = [], hlen
         for r in range(world):
             t = torch.empty(longest, dtype=torch.uint8, device=dev)
@@ -208,13 +294,20 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
             pos += bytes_by_rank[r]
     dist.scatter(mine, parts, src=src0, group=group)
     nb = bytes_by_rank[rank]
-    # chunk headers are parsed on the host: bring this rank's streams over once (pinned staging)
-    stage = _pinned_u8(nb, "streams")
-    stage[:nb].copy_(mine[:nb])
-    if dev.type == "cuda":
-        torch.cuda.current_stream(dev).synchronize()
-    h = stage.numpy()[:nb]
     mylens = np.ascontiguousarray(lens[sh.begin:sh.end], dtype=np.uint32)
+    meta_flags = [bool(on_device)]
+    dist.broadcast_object_list(meta_flags, src=src0, group=group)
+    if meta_flags[0]:
+        # the chunk headers (conditioner 17 B, SPECK header 9 B, outlier header 9 B) are all the host
+        # parses: fetch only those bytes, the streams themselves stay on the device
+        h = _chunk_headers_to_host(mine, mylens, nb)
+    else:
+        # bring this rank's streams over once (pinned staging)
+        stage = _pinned_u8(nb, "streams")
+        stage[:nb].copy_(mine[:nb])
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()
+        h = stage.numpy()[:nb]
     e = sh.box_extent
     box = torch.empty((e[2], e[1], e[0]), dtype=torch.float32 if output_float else torch.float64,
                       device=dev)

@@ -36,5 +36,10 @@ def test_sharded_nccl_world1(oracle):
             rc, dec, dims = oracle.decomp_3d(exp, True)
             assert sh.box_extent == vol
             assert np.array_equal(out.cpu().numpy().reshape(-1).view(np.uint32), dec.view(np.uint32))
+            # container kept in HBM: same bytes, same decode, only the chunk headers visit the host
+            dc = sharded.compress_3d_sharded(L.lib, box, vol, chunk, mode, q, device_container=True)
+            assert dc.data.is_cuda and np.array_equal(dc.numpy(), exp)
+            out2, _ = sharded.decompress_3d_sharded(L.lib, dc, dev, True)
+            assert torch.equal(out.view(torch.int32), out2.view(torch.int32))
     finally:
         dist.destroy_process_group()

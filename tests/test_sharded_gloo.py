@@ -51,6 +51,14 @@ def _worker(rank, world, port, case, q):
         assert rc == 0 and dims == tuple(vol)
         want = dec.reshape(vol[2], vol[1], vol[0])[sh2.slices()]
         assert np.array_equal(out.numpy().view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
+        # the same with the container kept where it was produced: only the chunk headers visit the host
+        dc = sharded.compress_3d_sharded(cdll, box, vol, chunk, mode, quality, device_container=True)
+        if rank == 0:
+            assert isinstance(dc, sharded.DeviceContainer) and np.array_equal(dc.numpy(), exp), "device container differs"
+        else:
+            assert dc is None
+        out3, sh3 = sharded.decompress_3d_sharded(cdll, dc, torch.device("cpu"), True)
+        assert np.array_equal(out3.numpy().view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
         q.put((rank, "ok"))
     except Exception as e:  # noqa: BLE001
         q.put((rank, "FAIL: %r" % (e,)))
