@@ -37,6 +37,7 @@ SYN_SMALL = [
     ((64, 64, 64), (64, 64, 64), 1, 3.0),
     ((32, 32, 64), (32, 32, 64), 3, 1e-2),
     ((128, 16, 16), (128, 16, 16), 3, 1e-3),
+    ((96, 80, 72), (96, 80, 72), 3, 1e-3),      # tiles interior in x: 128-bit loads of the float volume
 ]
 SYN_GPU = SYN_SMALL + [
     ((256, 256, 128), (256, 256, 128), 3, 1e-3),
