@@ -20,7 +20,7 @@ using namespace sperr_b200;
 
 namespace {
 
-std::mutex g_mutex;  // one job at a time per process: the work buffers are shared
+std::mutex& g_mutex = shared_api_mutex();  // one job at a time per process: the work buffers are shared
 Compressor* g_comp = nullptr;
 // grow-only device staging of the host-pointer entry points (input volume, container, output volume)
 rt::DBuf g_in, g_stream, g_vol, g_cstream;
@@ -167,7 +167,7 @@ int comp_3d_device(const void* d_src, int is_float, size_t dimx, size_t dimy, si
     if (c.lx > 65535 || c.ly > 65535 || c.lz > 65535 || c.nelem() >= (1ull << 31))
       return -1;  // Set3D coordinates are 16-bit in the reference as well
   if (!g_comp)
-    g_comp = new Compressor();
+    g_comp = &shared_compressor();
   SrcVol sv{d_src, is_float, dimx, dimy};
   rt::DBuf& d_out = g_cstream;
   d_out.reserve(size_t(1) << 20);
@@ -267,7 +267,7 @@ void decomp_3d_device(const uint8_t* h_stream, const uint8_t* d_stream, const Co
                       int output_float, void* d_dst, cudaStream_t st)
 {
   if (!g_decomp)
-    g_decomp = new Decompressor();
+    g_decomp = &shared_decompressor();
   SrcVol dv{d_dst, output_float, ci.vol[0], ci.vol[1]};
   g_decomp->decompress(h_stream, d_stream, ci.chunks, ci.cs, dv, st);
 }
@@ -290,7 +290,7 @@ int comp_2d_device(const void* d_src, int is_float, size_t dimx, size_t dimy, si
 {
   const auto chunks = slice_chunks(dimx, dimy, nslices);
   if (!g_comp)
-    g_comp = new Compressor();
+    g_comp = &shared_compressor();
   g_comp->max_batch = 0;
   g_comp->before_batch = nullptr;
   SrcVol sv{d_src, is_float, dimx, dimy};
@@ -350,7 +350,7 @@ void decomp_2d_device(const uint8_t* h_streams, const size_t* lens, size_t nslic
   g_stream.reserve(off + 16);
   HostPipe::get().h2d(g_stream.p, h_streams, off, st);
   if (!g_decomp)
-    g_decomp = new Decompressor();
+    g_decomp = &shared_decompressor();
   g_decomp->max_batch = 0;
   g_decomp->after_batch = nullptr;
   SrcVol dv{d_dst, output_float, dimx, dimy};
@@ -379,7 +379,7 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
     PhaseTimer pt;
     g_in.reserve(bytes);
     if (!g_comp)
-      g_comp = new Compressor();
+      g_comp = &shared_compressor();
     g_comp->max_batch = 0;
     g_comp->before_batch = nullptr;
 #ifndef SPERR_EMUL
@@ -525,7 +525,7 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
     PhaseTimer pt;
     HostPipe::get().prefault_begin(o, total * esz);
     if (!g_decomp)
-      g_decomp = new Decompressor();
+      g_decomp = &shared_decompressor();
     g_decomp->max_batch = 0;
     g_decomp->after_batch = nullptr;
     bool batched = false;
@@ -818,7 +818,7 @@ int sperr_b200_decomp_3d_multires(const void* src, size_t src_len, int output_fl
     HostPipe::get().h2d(g_stream.p, src, src_len, st);
     g_vol.reserve(total * esz);
     if (!g_decomp)
-      g_decomp = new Decompressor();
+      g_decomp = &shared_decompressor();
     g_decomp->max_batch = 0;
     g_decomp->after_batch = nullptr;
     g_decomp->multires = mr.d_level.empty() ? nullptr : &mr;

@@ -17,7 +17,7 @@ using namespace sperr_b200;
 
 namespace {
 
-std::mutex g_rmutex;
+std::mutex& g_rmutex = shared_api_mutex();
 Compressor* g_rcomp = nullptr;
 Decompressor* g_rdecomp = nullptr;
 rt::DBuf g_rout, g_rstream;
@@ -119,11 +119,15 @@ int sperr_b200_comp_3d_range_dev(const void* d_box, int is_float, const size_t v
     if (!range_chunks(vol, chunk, chunk_begin, chunk_end, box_origin, box_extent, chunks))
       return -1;
     if (!g_rcomp)
-      g_rcomp = new Compressor();
+      g_rcomp = &shared_compressor();
     cudaStream_t st = 0;
     SrcVol sv{d_box, is_float, box_extent[0], box_extent[1]};
     g_rout.reserve(size_t(1) << 20);
     std::vector<size_t> l;
+    g_rcomp->max_batch = 0;   // shared with the host-pointer API: no leftovers of its overlap hooks
+    g_rcomp->before_batch = nullptr;
+    g_rcomp->group_chunks = 0;
+    g_rcomp->before_group = nullptr;
     g_rcomp->compress(sv, chunks, mode, quality, false, g_rout, l, st);
     size_t total = 0;
     for (size_t i = 0; i < l.size(); i++) {
@@ -238,7 +242,7 @@ int sperr_b200_decomp_3d_range_dev(const void* h_streams, const void* d_streams,
     if (off != streams_len)
       return -1;
     if (!g_rdecomp)
-      g_rdecomp = new Decompressor();
+      g_rdecomp = &shared_decompressor();
     cudaStream_t st = 0;
     const uint8_t* ds = static_cast<const uint8_t*>(d_streams);
     if (!ds) {
@@ -247,6 +251,11 @@ int sperr_b200_decomp_3d_range_dev(const void* h_streams, const void* d_streams,
       ds = g_rstream.as<uint8_t>();
     }
     SrcVol dv{d_box_out, output_float, box_extent[0], box_extent[1]};
+    g_rdecomp->max_batch = 0;
+    g_rdecomp->after_batch = nullptr;
+    g_rdecomp->group_chunks = 0;
+    g_rdecomp->after_group = nullptr;
+    g_rdecomp->multires = nullptr;
     g_rdecomp->decompress(static_cast<const uint8_t*>(h_streams), ds, chunks, cs, dv, st);
     rt::sync(st);
     return 0;

@@ -26,6 +26,24 @@ struct Piece {
 
 }  // namespace
 
+// One pipeline pair and one lock per process: the host-pointer API, the device-pointer API and the
+// chunk-range API all reuse the same grow-only work buffers (tens of GB for a 1024^3 call).
+Compressor& shared_compressor()
+{
+  static Compressor* p = new Compressor();
+  return *p;
+}
+Decompressor& shared_decompressor()
+{
+  static Decompressor* p = new Decompressor();
+  return *p;
+}
+std::mutex& shared_api_mutex()
+{
+  static std::mutex* m = new std::mutex();
+  return *m;
+}
+
 // One block column per piece; bytes are copied with a grid-stride loop.
 __global__ void k_copy_pieces(const Piece* pieces, unsigned char* dst)
 {
@@ -43,6 +61,7 @@ size_t pick_batch_chunks(const std::vector<Chunk>& chunks, size_t first, bool pw
 #ifndef SPERR_EMUL
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
     free_b = size_t(64) << 30;
+  free_b += rt::DBuf::held();   // our own grow-only buffers are reused, not allocated again
 #endif
   (void)total_b;
   (void)pwe;

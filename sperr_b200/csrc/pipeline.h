@@ -4,6 +4,7 @@
 #pragma once
 
 #include <functional>
+#include <mutex>
 
 #include "batch.h"
 #include "outlier.h"
@@ -99,6 +100,10 @@ class Decompressor {
   bool whole_call_ = false;  // the current batch holds every chunk of the call
   rt::DBuf ids_, lis_off1_, tols_, obits_, ckey_[2], cval_[2], ccount_, coff_, csort_;
 };
+
+Compressor& shared_compressor();
+Decompressor& shared_decompressor();
+std::mutex& shared_api_mutex();
 
 // Largest number of chunks processed at once (bounded by the list-key layout and by memory).
 size_t pick_batch_chunks(const std::vector<Chunk>& chunks, size_t first, bool pwe);

@@ -15,6 +15,7 @@ size_t pick_dec_batch(const std::vector<Chunk>& chunks, size_t first)
 #ifndef SPERR_EMUL
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
     free_b = size_t(64) << 30;
+  free_b += rt::DBuf::held();   // our own grow-only buffers are reused, not allocated again
 #endif
   (void)total_b;
   const double budget = double(free_b) * 0.7;

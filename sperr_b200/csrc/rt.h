@@ -216,6 +216,14 @@ struct DBuf {
     release();
     p = dmalloc(n);
     bytes = n;
+    held() += n;
+  }
+  // device bytes all DBufs of this process hold right now (grow-only work buffers are reused by the
+  // next call, so batch sizing counts them as available)
+  static std::atomic<size_t>& held()
+  {
+    static std::atomic<size_t> h{0};
+    return h;
   }
   // grow-only
   void reserve(size_t n)
@@ -226,6 +234,8 @@ struct DBuf {
   void release()
   {
     dfree(p);
+    if (p)
+      held() -= bytes;
     p = nullptr;
     bytes = 0;
   }
