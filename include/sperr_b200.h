@@ -147,8 +147,9 @@ int sperr_b200_parse_container(const void* src, size_t len, size_t vol[3], size_
 
 /* Decodes the chunks of the range from their streams (back to back, lens[i] each) into the caller's
  * DEVICE box (float when output_float != 0, else double). h_streams: the streams in HOST memory
- * (chunk headers are parsed on the host); d_streams: the same bytes in DEVICE memory, or NULL to
- * have them uploaded. */
+ * (chunk headers are parsed on the host), or NULL when only the device copy exists (the library then
+ * fetches the 26 + 9 header bytes of every chunk itself); d_streams: the same bytes in DEVICE memory,
+ * or NULL to have them uploaded. At least one of the two must be given. */
 int sperr_b200_decomp_3d_range_dev(const void* h_streams, const void* d_streams, size_t streams_len,
                                    const uint32_t* lens,
                                    const size_t vol[3], const size_t chunk[3],

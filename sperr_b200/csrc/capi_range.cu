@@ -245,6 +245,8 @@ int sperr_b200_decomp_3d_range_dev(const void* h_streams, const void* d_streams,
       g_rdecomp = &shared_decompressor();
     cudaStream_t st = 0;
     const uint8_t* ds = static_cast<const uint8_t*>(d_streams);
+    if (!ds && !h_streams)
+      return -1;
     if (!ds) {
       g_rstream.reserve(streams_len + 16);
       rt::h2d(g_rstream.p, h_streams, streams_len, st);

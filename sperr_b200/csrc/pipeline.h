@@ -99,6 +99,7 @@ class Decompressor {
   size_t batch_first_ = 0;   // index of the current batch's first chunk in the caller's list
   bool whole_call_ = false;  // the current batch holds every chunk of the call
   rt::DBuf ids_, lis_off1_, tols_, obits_, ckey_[2], cval_[2], ccount_, coff_, csort_;
+  rt::DBuf hdr_off_, hdr_cnt_, hdr_out_;   // chunk headers fetched from the device (no host copy given)
 };
 
 Compressor& shared_compressor();

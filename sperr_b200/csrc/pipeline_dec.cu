@@ -33,6 +33,15 @@ size_t pick_dec_batch(const std::vector<Chunk>& chunks, size_t first)
 
 }  // namespace
 
+// out[i * stride .. + n[i]) = src[off[i] .. + n[i]): the few header bytes of every chunk stream
+__global__ void k_gather_bytes(const uint8_t* src, const unsigned long long* off, const unsigned* n, int stride,
+                               uint8_t* out)
+{
+  const unsigned i = blockIdx.x;
+  for (unsigned b = threadIdx.x; b < n[i]; b += blockDim.x)
+    out[(size_t)i * stride + b] = src[off[i] + b];
+}
+
 void Decompressor::decompress(const uint8_t* h_stream, const uint8_t* d_stream,
                               const std::vector<Chunk>& chunks, const std::vector<ChunkStream>& cs,
                               const SrcVol& dst, cudaStream_t st, bool is_2d)
@@ -72,8 +81,54 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
   };
   std::vector<Parsed> ps(nc);
   bool any_wide = false, any_out = false, any_owide = false;
+  // Without a host copy of the streams the bytes the parser reads are fetched from the device: the
+  // first 26 bytes of every chunk (conditioner + SPECK header), then the 9-byte header of the
+  // outlier stream where one may follow.
+  std::vector<uint8_t> hdr1, hdr2;
+  if (!h_stream) {
+    hdr1.assign(size_t(nc) * 26, 0);
+    hdr2.assign(size_t(nc) * 9, 0);
+    std::vector<unsigned long long> off(nc);
+    std::vector<unsigned> cnt(nc);
+    hdr_off_.reserve(size_t(nc) * 8);
+    hdr_cnt_.reserve(size_t(nc) * 4);
+    hdr_out_.reserve(size_t(nc) * 26);
+    auto fetch = [&](int stride, uint8_t* dst) {
+      rt::h2d(hdr_off_.p, off.data(), size_t(nc) * 8, st);
+      rt::h2d(hdr_cnt_.p, cnt.data(), size_t(nc) * 4, st);
+      LAUNCH(k_gather_bytes, dim3(unsigned(nc)), dim3(32), 0, st, d_stream, hdr_off_.as<unsigned long long>(),
+             hdr_cnt_.as<unsigned>(), stride, hdr_out_.as<uint8_t>());
+      rt::d2h(dst, hdr_out_.p, size_t(nc) * stride, st);
+      rt::sync(st);
+    };
+    for (int c = 0; c < nc; c++) {
+      off[c] = cs[c].off;
+      cnt[c] = unsigned(std::min<size_t>(26, cs[c].len));
+    }
+    fetch(26, hdr1.data());
+    bool any2 = false;
+    for (int c = 0; c < nc; c++) {
+      const uint8_t* p = &hdr1[size_t(c) * 26];
+      cnt[c] = 0;
+      off[c] = cs[c].off;
+      if (cs[c].len < 26 || (p[0] & 0x01))
+        continue;
+      unsigned long long tb;
+      std::memcpy(&tb, p + 18, 8);
+      if (tb > (1ull << 48))
+        continue;
+      const size_t pos = 17 + std::min(9 + size_t((tb + 7) / 8), cs[c].len - 17);
+      if (pos < cs[c].len && cs[c].len - pos >= 9) {
+        off[c] = cs[c].off + pos;
+        cnt[c] = 9;
+        any2 = true;
+      }
+    }
+    if (any2)
+      fetch(9, hdr2.data());
+  }
   for (int c = 0; c < nc; c++) {
-    const uint8_t* p = h_stream + cs[c].off;
+    const uint8_t* p = h_stream ? h_stream + cs[c].off : &hdr1[size_t(c) * 26];
     const size_t len = cs[c].len;
     Parsed& P = ps[c];
     if (len < 17)
@@ -104,7 +159,7 @@ void Decompressor::run_batch(const uint8_t* h_stream, const uint8_t* d_stream,
     if (pos < len) {
       remaining = len - pos;
       if (remaining >= 9) {
-        const uint8_t* op = p + pos;
+        const uint8_t* op = h_stream ? p + pos : &hdr2[size_t(c) * 9];
         unsigned long long nb;
         std::memcpy(&nb, op + 1, 8);
         const size_t ofull = nb > (1ull << 48) ? 0 : 9 + size_t((nb + 7) / 8);

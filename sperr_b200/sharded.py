@@ -134,6 +134,29 @@ def compress_3d_sharded(cdll, box, vol, chunk, mode, quality, group=None, device
                                               sh.origin, sh.extent, sh.begin, sh.end, mode, quality,
                                               C.byref(d_streams), C.byref(n), lens.ctypes.data_as(vp))
     dev = box.device
+    if world == 1:
+        # a world of one rank needs no exchange: header + this rank's streams are the container
+        if rc != 0:
+            raise RuntimeError("sperr_b200_comp_3d_range_dev failed (rc=%d)" % rc)
+        hlen = int(sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), None, sh.nchunks, None, 0))
+        total = hlen + n.value
+        hdr = np.zeros(hlen, dtype=np.uint8)
+        got = sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), lens.ctypes.data_as(vp),
+                                                  sh.nchunks, hdr.ctypes.data_as(vp), hdr.size)
+        assert got == hlen
+        if device_container:
+            data = torch.empty(total, dtype=torch.uint8, device=dev)
+            data[:hlen].copy_(torch.from_numpy(hdr))
+            if n.value:
+                assert sh.cdll.sperr_b200_memcpy_dev(vp(data.data_ptr() + hlen), d_streams, n.value, 0) == 0
+            return DeviceContainer(data, hdr)
+        stage = _pinned_u8(total, "container")
+        out = stage.numpy()[:total]
+        out[:hlen] = hdr
+        if n.value:
+            kind = 2 if dev.type == "cuda" else 0   # device -> host (the emulated library "device" is the host)
+            assert sh.cdll.sperr_b200_memcpy_dev(vp(stage.data_ptr() + hlen), d_streams, n.value, kind) == 0
+        return out
     ok = torch.tensor([abs(rc)], device=dev, dtype=torch.int32)
     dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=group)
     if int(ok.item()) != 0:
@@ -226,37 +249,30 @@ def parse_header_only(cdll, header, total_len):
     return tuple(vol), tuple(chunk), bool(isf.value), hlen.value, lens
 
 
-def _chunk_headers_to_host(d_streams, lens, nb):
-    """Host image of this rank's chunk streams that holds only the bytes the host-side parser reads
-    (SPECK_FLT::use_bitstream, /root/reference/src/SPECK_FLT.cpp:27-109): per chunk the 17-byte
-    conditioner header + 9-byte SPECK header, and the 9-byte header of the outlier stream where one
-    follows. Everything else reads as zero (calloc'd pages that are never touched)."""
-    dev = d_streams.device
-    lens64 = lens.astype(np.int64)
-    offs = np.concatenate([[0], np.cumsum(lens64)])[:-1]
-    h = np.zeros(max(nb, 1), dtype=np.uint8)
-    if lens64.size == 0:
-        return h[:nb]
-    idx = (offs[:, None] + np.arange(26)[None, :]).reshape(-1)
-    idx = np.minimum(idx, max(nb - 1, 0))
-    first = d_streams[torch.from_numpy(idx).to(dev)].cpu().numpy().reshape(-1, 26)
-    pos2 = []
-    for c in range(lens64.size):
-        n = int(min(26, lens64[c]))
-        h[offs[c]:offs[c] + n] = first[c, :n]
-        if lens64[c] < 26 or (first[c, 0] & 1):
-            continue
-        tb = int(np.frombuffer(first[c, 18:26].tobytes(), dtype=np.uint64)[0])
-        speck_len = min(9 + (tb + 7) // 8, int(lens64[c]) - 17)
-        p = int(offs[c]) + 17 + speck_len
-        if p + 9 <= int(offs[c] + lens64[c]):
-            pos2.append(p)
-    if pos2:
-        idx2 = (np.asarray(pos2, dtype=np.int64)[:, None] + np.arange(9)[None, :]).reshape(-1)
-        second = d_streams[torch.from_numpy(idx2).to(dev)].cpu().numpy().reshape(-1, 9)
-        for k, p in enumerate(pos2):
-            h[p:p + 9] = second[k]
-    return h[:nb]
+def _decompress_world1(cdll, stream, dev, output_float, on_device):
+    """decompress_3d_sharded for a world of one rank: no exchange at all."""
+    if on_device:
+        vol, chunk, isf, hlen, lens = parse_header_only(cdll, stream.header, stream.size)
+        d_all = stream.data
+    else:
+        vol, chunk, isf, hlen, lens = parse_container(cdll, stream)
+        d_all = torch.from_numpy(np.ascontiguousarray(stream)).to(dev)
+    sh = Shard(cdll, vol, chunk, 0, 1)
+    nb = int(lens.astype(np.int64).sum())
+    mine = d_all[hlen:hlen + nb]
+    mylens = np.ascontiguousarray(lens, dtype=np.uint32)
+    # device container: no host copy of the streams, the library fetches the chunk headers itself
+    h = None if on_device else np.ascontiguousarray(stream)[hlen:hlen + nb]
+    e = sh.box_extent
+    box = torch.empty((e[2], e[1], e[0]), dtype=torch.float32 if output_float else torch.float64, device=dev)
+    rc = cdll.sperr_b200_decomp_3d_range_dev(h.ctypes.data_as(vp) if h is not None else vp(None),
+                                             vp(mine.data_ptr()), nb,
+                                             mylens.ctypes.data_as(vp), sh.vol, sh.chunk, sh.origin,
+                                             sh.extent, sh.begin, sh.end, int(output_float),
+                                             vp(box.data_ptr()))
+    if rc != 0:
+        raise RuntimeError("sperr_b200_decomp_3d_range_dev failed (rc=%d)" % rc)
+    return box, sh
 
 
 def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
@@ -268,8 +284,10 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
     cdll = _bind(cdll)
     dev = torch.device(device)
     src0 = dist.get_global_rank(group, 0) if group is not None else 0
-    meta = [None]
     on_device = isinstance(stream, DeviceContainer)
+    if world == 1:
+        return _decompress_world1(cdll, stream, dev, output_float, on_device)
+    meta = [None]
     if rank == 0:
         if on_device:
             vol, chunk, isf, hlen, lens = parse_header_only(cdll, stream.header, stream.size)
@@ -298,9 +316,9 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
     meta_flags = [bool(on_device)]
     dist.broadcast_object_list(meta_flags, src=src0, group=group)
     if meta_flags[0]:
-        # the chunk headers (conditioner 17 B, SPECK header 9 B, outlier header 9 B) are all the host
-        # parses: fetch only those bytes, the streams themselves stay on the device
-        h = _chunk_headers_to_host(mine, mylens, nb)
+        # the streams stay on the device: the library fetches the chunk headers (conditioner 17 B,
+        # SPECK header 9 B, outlier header 9 B) it parses on the host itself
+        h = None
     else:
         # bring this rank's streams over once (pinned staging)
         stage = _pinned_u8(nb, "streams")
@@ -311,7 +329,8 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
     e = sh.box_extent
     box = torch.empty((e[2], e[1], e[0]), dtype=torch.float32 if output_float else torch.float64,
                       device=dev)
-    rc = cdll.sperr_b200_decomp_3d_range_dev(h.ctypes.data_as(vp), vp(mine.data_ptr()), nb,
+    rc = cdll.sperr_b200_decomp_3d_range_dev(h.ctypes.data_as(vp) if h is not None else vp(None),
+                                             vp(mine.data_ptr()), nb,
                                              mylens.ctypes.data_as(vp), sh.vol, sh.chunk, sh.origin,
                                              sh.extent, sh.begin, sh.end, int(output_float),
                                              vp(box.data_ptr()))

@@ -82,6 +82,19 @@ def test_sharded_roundtrip_gloo_world2(case):
     assert all(r[1] == "ok" for r in res), res
 
 
+def test_sharded_world1_gloo():
+    """a world of one rank takes the exchange-free path (what bench.py --gpus 1 runs)"""
+    gpulib.build_emul()
+    refs.oracle()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=_worker, args=(0, 1, random.randint(20000, 40000), CASES[0], q))
+    p.start()
+    res = q.get(timeout=300)
+    p.join(timeout=60)
+    assert res[1] == "ok", res
+
+
 def test_chunk_ranges_cover_everything():
     from sperr_b200 import sharded
     for n in (1, 2, 7, 8, 64, 65):
