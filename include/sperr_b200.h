@@ -157,6 +157,16 @@ int sperr_b200_decomp_3d_range_dev(const void* h_streams, const void* d_streams,
                                    size_t chunk_begin, size_t chunk_end, int output_float,
                                    void* d_box_out);
 
+/* Arithmetic flavour of the CDF 9/7 lifting steps, process-wide, for all later calls. 0 (default):
+ * every multiply and add rounded separately -- streams and decoded values equal to the reference
+ * built with -ffp-contract=off (what the north star calls the reference's exact operation order
+ * with -fmad=false). 1: the steps contracted the way the reference's stock x86 build contracts them
+ * (g++ -O3 -mfma with GCC's default -ffp-contract=fast: x +- C*s as one fma), so that streams and
+ * decoded values equal THAT library's (SURVEY.md section 0 finding 1: fixed-rate streams and the
+ * last bit of decoded values differ between the two builds). Also settable with the environment
+ * variable SPERR_B200_FMA=1 before the first call. */
+void sperr_b200_set_fma_flavour(int on);
+
 /* Stage profiler: when enabled every stage of the pipelines is bracketed by CUDA events on the
  * launching stream. prof_dump writes a JSON object {"stage": {"ms": total, "n": ranges}, ...} into
  * buf (NUL-terminated, truncated to cap) and returns the full length. Enabling clears the totals. */

@@ -195,9 +195,74 @@ static cdf_consts cdf_get(void)
   return c;
 }
 
+/* Arithmetic flavour of the lifting steps. 0 = STRICT: every multiply and add rounded separately
+ * (the reference built with -ffp-contract=off; what the CUDA kernels reproduce with -fmad=false).
+ * 1 = FMA: the contraction pattern g++ 13 -O3 -mfma -ffp-contract=fast gives the reference's stock
+ * x86 build (read from its disassembly): forward steps 1-3 fma(C, sum, x),
+ * step 4 EPSILON * fma(DELTA, sum, e); inverse step 2 fma(e, INV_EPSILON, -(DELTA * sum)) with the
+ * product rounded first, inverse steps 3-5 fma(-C, sum, x). */
+static int g_fma_flavour = 0;
+void so_set_fma_flavour(int on) { g_fma_flavour = on != 0; }
+
+static void analysis_fma(const cdf_consts* c, double* sig, size_t len)
+{
+  const size_t el = len - len / 2, ol = len / 2;
+  double *even = sig, *odd = sig + el;
+  for (size_t i = 0; i + 1 < ol; i++)
+    odd[i] = fma(c->ALPHA, even[i] + even[i + 1], odd[i]);
+  odd[ol - 1] = fma(c->ALPHA, even[ol - 1] + even[el - 1], odd[ol - 1]);
+
+  even[0] = fma(2.0 * c->BETA, odd[0], even[0]);
+  for (size_t i = 1; i + 1 < el; i++)
+    even[i] = fma(c->BETA, odd[i - 1] + odd[i], even[i]);
+  even[el - 1] = fma(c->BETA, odd[el - 2] + odd[ol - 1], even[el - 1]);
+
+  for (size_t i = 0; i + 1 < ol; i++)
+    odd[i] = fma(c->GAMMA, even[i] + even[i + 1], odd[i]);
+  odd[ol - 1] = fma(c->GAMMA, even[ol - 1] + even[el - 1], odd[ol - 1]);
+
+  even[0] = c->EPSILON * fma(2.0 * c->DELTA, odd[0], even[0]);
+  for (size_t i = 1; i + 1 < el; i++)
+    even[i] = c->EPSILON * fma(c->DELTA, odd[i - 1] + odd[i], even[i]);
+  even[el - 1] = c->EPSILON * fma(c->DELTA, odd[el - 2] + odd[ol - 1], even[el - 1]);
+
+  for (size_t i = 0; i < ol; i++)
+    odd[i] *= -c->INV_EPSILON;
+}
+
+static void synthesis_fma(const cdf_consts* c, double* sig, size_t len)
+{
+  const size_t el = len - len / 2, ol = len / 2;
+  double *even = sig, *odd = sig + el;
+  for (size_t i = 0; i < ol; i++)
+    odd[i] *= (-c->EPSILON);
+
+  even[0] = fma(even[0], c->INV_EPSILON, -((2.0 * c->DELTA) * odd[0]));
+  for (size_t i = 1; i + 1 < el; i++)
+    even[i] = fma(even[i], c->INV_EPSILON, -(c->DELTA * (odd[i - 1] + odd[i])));
+  even[el - 1] = fma(even[el - 1], c->INV_EPSILON, -(c->DELTA * (odd[el - 2] + odd[ol - 1])));
+
+  for (size_t i = 0; i + 1 < ol; i++)
+    odd[i] = fma(-c->GAMMA, even[i] + even[i + 1], odd[i]);
+  odd[ol - 1] = fma(-c->GAMMA, even[ol - 1] + even[el - 1], odd[ol - 1]);
+
+  even[0] = fma(-(2.0 * c->BETA), odd[0], even[0]);
+  for (size_t i = 1; i + 1 < el; i++)
+    even[i] = fma(-c->BETA, odd[i - 1] + odd[i], even[i]);
+  even[el - 1] = fma(-c->BETA, odd[el - 2] + odd[ol - 1], even[el - 1]);
+
+  for (size_t i = 0; i + 1 < ol; i++)
+    odd[i] = fma(-c->ALPHA, even[i] + even[i + 1], odd[i]);
+  odd[ol - 1] = fma(-c->ALPHA, even[ol - 1] + even[el - 1], odd[ol - 1]);
+}
+
 /* src/CDF97.cpp:598-631; `sig` holds evens then odds. */
 static void analysis(const cdf_consts* c, double* sig, size_t len)
 {
+  if (g_fma_flavour) {
+    analysis_fma(c, sig, len);
+    return;
+  }
   const size_t el = len - len / 2, ol = len / 2;
   double *even = sig, *odd = sig + el;
   for (size_t i = 0; i + 1 < ol; i++)
@@ -225,6 +290,10 @@ static void analysis(const cdf_consts* c, double* sig, size_t len)
 /* src/CDF97.cpp:633-666 */
 static void synthesis(const cdf_consts* c, double* sig, size_t len)
 {
+  if (g_fma_flavour) {
+    synthesis_fma(c, sig, len);
+    return;
+  }
   const size_t el = len - len / 2, ol = len / 2;
   double *even = sig, *odd = sig + el;
   for (size_t i = 0; i < ol; i++)

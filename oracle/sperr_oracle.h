@@ -85,6 +85,9 @@ int so_comp_2d(const void* src, int is_float, size_t dimx, size_t dimy, int mode
 int so_decomp_2d(const void* src, size_t src_len, int output_float, size_t dimx, size_t dimy,
                  void** dst);
 
+/* 0 (default): STRICT arithmetic; 1: the lifting steps contracted like the reference's stock x86 build */
+void so_set_fma_flavour(int on);
+
 int so_trunc_3d(const void* src, size_t src_len, unsigned pct, void** dst, size_t* dst_len);
 
 #ifdef __cplusplus

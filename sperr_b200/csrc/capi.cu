@@ -931,6 +931,13 @@ int sperr_trunc_3d(const void* src, size_t src_len, unsigned pct, void** dst, si
   return 0;
 }
 
+// Arithmetic flavour of the wavelet lifting steps for all later calls (kernels.h: lift_add).
+void sperr_b200_set_fma_flavour(int on)
+{
+  std::lock_guard<std::mutex> lock(g_mutex);
+  fma_flavour() = on ? 1 : 0;
+}
+
 void sperr_b200_prof_enable(int on)
 {
   rt::prof().on = on != 0;

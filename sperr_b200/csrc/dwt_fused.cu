@@ -48,13 +48,14 @@ __device__ __forceinline__ int mirror(int i, int L)
 struct FwdState {
   double E, O, O1, E1, O2;
 };
+template <bool FMA>
 __device__ __forceinline__ void fwd_step(const CdfC& k, FwdState& s, double e, double o, double& e2,
                                          double& o3)
 {
-  const double o1n = __dadd_rn(s.O, __dmul_rn(k.ALPHA, __dadd_rn(s.E, e)));
-  const double e1n = __dadd_rn(s.E, __dmul_rn(k.BETA, __dadd_rn(s.O1, o1n)));
-  const double o2n = __dadd_rn(s.O1, __dmul_rn(k.GAMMA, __dadd_rn(s.E1, e1n)));
-  e2 = __dmul_rn(k.EPSILON, __dadd_rn(s.E1, __dmul_rn(k.DELTA, __dadd_rn(s.O2, o2n))));
+  const double o1n = lift_add<FMA>(s.O, k.ALPHA, __dadd_rn(s.E, e));
+  const double e1n = lift_add<FMA>(s.E, k.BETA, __dadd_rn(s.O1, o1n));
+  const double o2n = lift_add<FMA>(s.O1, k.GAMMA, __dadd_rn(s.E1, e1n));
+  e2 = lift_scale_fwd<FMA>(k, s.E1, __dadd_rn(s.O2, o2n));
   o3 = __dmul_rn(o2n, -k.INV_EPSILON);
   s.E = e; s.O = o; s.O1 = o1n; s.E1 = e1n; s.O2 = o2n;
 }
@@ -62,15 +63,16 @@ __device__ __forceinline__ void fwd_step(const CdfC& k, FwdState& s, double e, d
 struct InvState {
   double OP, E1, O1, E2;
 };
+template <bool FMA>
 __device__ __forceinline__ void inv_step(const CdfC& k, InvState& s, double e, double o, double& x0,
                                          double& x1)
 {
   const double opn = __dmul_rn(o, -k.EPSILON);
-  const double e1n = __dsub_rn(__dmul_rn(e, k.INV_EPSILON), __dmul_rn(k.DELTA, __dadd_rn(s.OP, opn)));
-  const double o1n = __dsub_rn(s.OP, __dmul_rn(k.GAMMA, __dadd_rn(s.E1, e1n)));
-  const double e2n = __dsub_rn(s.E1, __dmul_rn(k.BETA, __dadd_rn(s.O1, o1n)));
+  const double e1n = lift_scale_inv<FMA>(k, e, __dadd_rn(s.OP, opn));
+  const double o1n = lift_sub<FMA>(s.OP, k.GAMMA, __dadd_rn(s.E1, e1n));
+  const double e2n = lift_sub<FMA>(s.E1, k.BETA, __dadd_rn(s.O1, o1n));
   x0 = s.E2;
-  x1 = __dsub_rn(s.O1, __dmul_rn(k.ALPHA, __dadd_rn(s.E2, e2n)));
+  x1 = lift_sub<FMA>(s.O1, k.ALPHA, __dadd_rn(s.E2, e2n));
   s.OP = opn; s.E1 = e1n; s.O1 = o1n; s.E2 = e2n;
 }
 
@@ -80,7 +82,7 @@ __device__ __forceinline__ void inv_step(const CdfC& k, InvState& s, double e, d
 // The four lifting stages are skewed by one iteration each (stage s of iteration j works on what
 // stage s-1 produced in iteration j-1), so the stages of one iteration are independent instruction
 // chains: same operations on the same operands as fwd_step / inv_step, more ILP per thread.
-template <bool INVERSE>
+template <bool INVERSE, bool FMA>
 __device__ __forceinline__ void lift_line(const CdfC& k, double* p, int stride)
 {
   if (!INVERSE) {
@@ -92,11 +94,11 @@ __device__ __forceinline__ void lift_line(const CdfC& k, double* p, int stride)
     for (int j = 0; j < kFNP + 3; j++) {
       const double e = j < kFNP ? p[(2 * j) * stride] : 0.0;
       const double o = j < kFNP ? p[(2 * j + 1) * stride] : 0.0;
-      const double n_o1 = __dadd_rn(oA, __dmul_rn(k.ALPHA, __dadd_rn(eA, e)));
-      const double n_e1 = __dadd_rn(eB, __dmul_rn(k.BETA, __dadd_rn(p2, p1)));
-      const double n_o2 = __dadd_rn(p3, __dmul_rn(k.GAMMA, __dadd_rn(q2, q1)));
+      const double n_o1 = lift_add<FMA>(oA, k.ALPHA, __dadd_rn(eA, e));
+      const double n_e1 = lift_add<FMA>(eB, k.BETA, __dadd_rn(p2, p1));
+      const double n_o2 = lift_add<FMA>(p3, k.GAMMA, __dadd_rn(q2, q1));
       if (j >= 7) {   // pair j - 5
-        p[(2 * j - 10) * stride] = __dmul_rn(k.EPSILON, __dadd_rn(q3, __dmul_rn(k.DELTA, __dadd_rn(r2, r1))));
+        p[(2 * j - 10) * stride] = lift_scale_fwd<FMA>(k, q3, __dadd_rn(r2, r1));
         p[(2 * j - 9) * stride] = __dmul_rn(r1, -k.INV_EPSILON);
       }
       eB = eA; eA = e; oA = o;
@@ -115,12 +117,12 @@ __device__ __forceinline__ void lift_line(const CdfC& k, double* p, int stride)
       const double e = j < kFNP ? p[(2 * j) * stride] : 0.0;
       const double o = j < kFNP ? p[(2 * j + 1) * stride] : 0.0;
       const double opn = __dmul_rn(o, -k.EPSILON);
-      const double e1n = __dsub_rn(__dmul_rn(e, k.INV_EPSILON), __dmul_rn(k.DELTA, __dadd_rn(OP1, opn)));
-      const double o1n = __dsub_rn(OP2, __dmul_rn(k.GAMMA, __dadd_rn(E1b, E1a)));
-      const double e2n = __dsub_rn(E1c, __dmul_rn(k.BETA, __dadd_rn(O1b, O1a)));
+      const double e1n = lift_scale_inv<FMA>(k, e, __dadd_rn(OP1, opn));
+      const double o1n = lift_sub<FMA>(OP2, k.GAMMA, __dadd_rn(E1b, E1a));
+      const double e2n = lift_sub<FMA>(E1c, k.BETA, __dadd_rn(O1b, O1a));
       if (j >= 7) {   // pair j - 5
         p[(2 * j - 10) * stride] = E2b;
-        p[(2 * j - 9) * stride] = __dsub_rn(O1c, __dmul_rn(k.ALPHA, __dadd_rn(E2b, E2a)));
+        p[(2 * j - 9) * stride] = lift_sub<FMA>(O1c, k.ALPHA, __dadd_rn(E2b, E2a));
       }
       OP2 = OP1; OP1 = opn;
       E1c = E1b; E1b = E1a; E1a = e1n;
@@ -156,7 +158,7 @@ __device__ __forceinline__ unsigned long long abs_bits(double v)
 }
 
 // SRC 0: float volume, 1: double volume (both minus the chunk mean), 2: compact fp64 box in scratch
-template <int SRC>
+template <int SRC, bool FMA>
 __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
 {
   DYN_SMEM(double, tile);   // [kPlanes][kFI][kFP]
@@ -255,11 +257,11 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
     __syncthreads();
     // ---- rows (x): kPlanes * 40 lines ----
     if (tid < kPlanes * kFI)
-      lift_line<false>(k, tile + (size_t)(tid / kFI) * kFI * kFP + (tid % kFI) * kFP, 1);
+      lift_line<false, FMA>(k, tile + (size_t)(tid / kFI) * kFI * kFP + (tid % kFI) * kFP, 1);
     __syncthreads();
     // ---- columns (y), only the x positions that are valid after the row pass ----
     if (tid < kPlanes * kFT)
-      lift_line<false>(k, tile + (size_t)(tid / kFT) * kFI * kFP + kFH + tid % kFT, kFP);
+      lift_line<false, FMA>(k, tile + (size_t)(tid / kFT) * kFI * kFP + kFH + tid % kFT, kFP);
     __syncthreads();
     // ---- z: streaming state in registers, 4 (x, y) columns per thread, kNPB pairs in order ----
 #pragma unroll
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
       for (int c = 0; c < 4; c++) {
         const int ry = warp + 8 * c;
         double e2, o3;
-        fwd_step(k, st[c], te[ry * kFP], to[ry * kFP], e2, o3);
+        fwd_step<FMA>(k, st[c], te[ry * kFP], to[ry * kFP], e2, o3);
         if (emit && live[c]) {
           if (apos[c] >= 0) {   // approx band of this level (plane kk of the low band)
             abox[(size_t)kk * aplane + apos[c]] = e2;
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
 // OUT 0: fp64 box in scratch (levels > 0) or, at level 0, raw fp64 values into the volume `vol`,
 //     1: destination volume (+ outlier corrector, + mean, float or double),
 //     2: compare with the source volume and record the outliers
-template <int OUT>
+template <int OUT, bool FMA>
 __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
 {
   DYN_SMEM(double, tile);   // [kPlanes][kFI][kFP]
@@ -391,7 +393,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
       for (int s = 0; s < kPer; s++) {
         if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
           double x0, x1;
-          inv_step(k, st[s], ev[s], ov[s], x0, x1);
+          inv_step<FMA>(k, st[s], ev[s], ov[s], x0, x1);
           t0[sidx[s]] = x0;
           t0[kFI * kFP + sidx[s]] = x1;
         }
@@ -401,10 +403,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     // planes 2 (j0 - 2) .. of the rebuilt box sit in the tile; pair q is wanted iff k0 <= j0+q-2 < k1
     // ---- columns (y) over all x of the tile, then rows (x) over the valid y ----
     if (tid < kPlanes * kFI)
-      lift_line<true>(k, tile + (size_t)(tid / kFI) * kFI * kFP + tid % kFI, kFP);
+      lift_line<true, FMA>(k, tile + (size_t)(tid / kFI) * kFI * kFP + tid % kFI, kFP);
     __syncthreads();
     if (tid < kPlanes * kFT)
-      lift_line<true>(k, tile + (size_t)(tid / kFT) * kFI * kFP + (kFH + tid % kFT) * kFP, 1);
+      lift_line<true, FMA>(k, tile + (size_t)(tid / kFT) * kFI * kFP + (kFH + tid % kFT) * kFP, 1);
     __syncthreads();
     // ---- epilogue: kPlanes x 32 x 32 values; a thread owns (lane, warp + 8 c) of every plane ----
 #pragma unroll
@@ -564,12 +566,18 @@ static void fused_attrs()
   if (done)
     return;
   const int sm = int(kFusedSmem);
-  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   done = true;
 #endif
 }
@@ -598,12 +606,19 @@ void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const
     a.last = l + 1 == L;
     dim3 grid;
     fused_grid(a, nids, grid);
-    if (l > 0)
-      LAUNCH(k_fwd3d<2>, grid, dim3(kFThreads), kFusedSmem, st, a);
-    else if (src.is_float)
-      LAUNCH(k_fwd3d<0>, grid, dim3(kFThreads), kFusedSmem, st, a);
-    else
-      LAUNCH(k_fwd3d<1>, grid, dim3(kFThreads), kFusedSmem, st, a);
+    const int which = l > 0 ? 2 : (src.is_float ? 0 : 1);
+#define SPERR_FWD(S, F) LAUNCH((k_fwd3d<S, F>), grid, dim3(kFThreads), kFusedSmem, st, a)
+    if (a.k.fma) {
+      if (which == 2) SPERR_FWD(2, true);
+      else if (which == 0) SPERR_FWD(0, true);
+      else SPERR_FWD(1, true);
+    }
+    else {
+      if (which == 2) SPERR_FWD(2, false);
+      else if (which == 0) SPERR_FWD(0, false);
+      else SPERR_FWD(1, false);
+    }
+#undef SPERR_FWD
   }
 }
 
@@ -636,12 +651,19 @@ void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chu
     a.out_off = l > 0 ? off[l] : -1;
     dim3 grid;
     fused_grid(a, nids, grid);
-    if (l > 0 || mode == 0)
-      LAUNCH(k_inv3d<0>, grid, dim3(kFThreads), kFusedSmem, st, a);
-    else if (mode == 1)
-      LAUNCH(k_inv3d<1>, grid, dim3(kFThreads), kFusedSmem, st, a);
-    else
-      LAUNCH(k_inv3d<2>, grid, dim3(kFThreads), kFusedSmem, st, a);
+    const int which = (l > 0 || mode == 0) ? 0 : (mode == 1 ? 1 : 2);
+#define SPERR_INV(O, F) LAUNCH((k_inv3d<O, F>), grid, dim3(kFThreads), kFusedSmem, st, a)
+    if (a.k.fma) {
+      if (which == 0) SPERR_INV(0, true);
+      else if (which == 1) SPERR_INV(1, true);
+      else SPERR_INV(2, true);
+    }
+    else {
+      if (which == 0) SPERR_INV(0, false);
+      else if (which == 1) SPERR_INV(1, false);
+      else SPERR_INV(2, false);
+    }
+#undef SPERR_INV
   }
 }
 

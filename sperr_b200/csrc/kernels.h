@@ -17,7 +17,44 @@ struct SrcVol {
 
 struct CdfC {
   double ALPHA, BETA, GAMMA, DELTA, EPSILON, INV_EPSILON;
+  int fma;   // arithmetic flavour of the lifting steps (see lift_add below)
 };
+
+// Arithmetic flavour of the lifting steps. STRICT (default): every multiply and add rounded
+// separately, the reference built with -ffp-contract=off. FMA: the contraction pattern of the
+// reference's stock x86 build (g++ -O3 -mfma, -ffp-contract=fast; SURVEY.md appendix A.3, pinned
+// against that build in tests/test_fma_flavour.py): x + C*s and x - C*s become one fma, the scaled
+// steps keep their separate multiply. The flavour is a template parameter of the hot kernels, so
+// the STRICT code is unchanged by the existence of the other one.
+int& fma_flavour();   // process-wide switch read by cdf_constants(): 0 STRICT, 1 FMA
+template <bool FMA>
+__device__ __forceinline__ double lift_add(double x, double C, double s)   // x + C * s
+{
+  if (FMA)
+    return __fma_rn(C, s, x);
+  return __dadd_rn(x, __dmul_rn(C, s));
+}
+template <bool FMA>
+__device__ __forceinline__ double lift_sub(double x, double C, double s)   // x - C * s
+{
+  if (FMA)
+    return __fma_rn(-C, s, x);
+  return __dsub_rn(x, __dmul_rn(C, s));
+}
+template <bool FMA>
+__device__ __forceinline__ double lift_scale_fwd(const CdfC& k, double e, double s)   // EPSILON * (e + DELTA * s)
+{
+  if (FMA)
+    return __dmul_rn(k.EPSILON, __fma_rn(k.DELTA, s, e));
+  return __dmul_rn(k.EPSILON, __dadd_rn(e, __dmul_rn(k.DELTA, s)));
+}
+template <bool FMA>
+__device__ __forceinline__ double lift_scale_inv(const CdfC& k, double e, double s)   // e * INV_EPSILON - DELTA * s
+{
+  if (FMA)
+    return __fma_rn(e, k.INV_EPSILON, -__dmul_rn(k.DELTA, s));
+  return __dsub_rn(__dmul_rn(e, k.INV_EPSILON), __dmul_rn(k.DELTA, s));
+}
 
 // Unordered append list of PWE outliers found by a batch: key = chunk << 32 | position in chunk.
 struct OutlierSink {

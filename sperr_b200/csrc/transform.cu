@@ -213,29 +213,29 @@ __global__ void k_gather_sub(SrcVol src, const ChunkDev* chunks)
 // `get/put` index the line; `tid/nthr` enumerate the cooperating threads; `sync` separates steps.
 // ---------------------------------------------------------------------------------------------
 
-template <typename Line, typename Sync>
+template <bool FMA, typename Line, typename Sync>
 __device__ __forceinline__ void lift_forward(const CdfC& k, Line L, int len, int tid, int nthr,
                                              Sync sync)
 {
   const int el = len - len / 2, ol = len / 2;
   for (int i = tid; i < ol; i += nthr) {
     const int i1 = i + 1 < el ? i + 1 : el - 1;
-    L.o(i) = __dadd_rn(L.o(i), __dmul_rn(k.ALPHA, __dadd_rn(L.e(i), L.e(i1))));
+    L.o(i) = lift_add<FMA>(L.o(i), k.ALPHA, __dadd_rn(L.e(i), L.e(i1)));
   }
   sync();
   for (int i = tid; i < el; i += nthr) {
     const int a = i > 0 ? i - 1 : 0, b = i < ol ? i : ol - 1;
-    L.e(i) = __dadd_rn(L.e(i), __dmul_rn(k.BETA, __dadd_rn(L.o(a), L.o(b))));
+    L.e(i) = lift_add<FMA>(L.e(i), k.BETA, __dadd_rn(L.o(a), L.o(b)));
   }
   sync();
   for (int i = tid; i < ol; i += nthr) {
     const int i1 = i + 1 < el ? i + 1 : el - 1;
-    L.o(i) = __dadd_rn(L.o(i), __dmul_rn(k.GAMMA, __dadd_rn(L.e(i), L.e(i1))));
+    L.o(i) = lift_add<FMA>(L.o(i), k.GAMMA, __dadd_rn(L.e(i), L.e(i1)));
   }
   sync();
   for (int i = tid; i < el; i += nthr) {
     const int a = i > 0 ? i - 1 : 0, b = i < ol ? i : ol - 1;
-    L.e(i) = __dmul_rn(k.EPSILON, __dadd_rn(L.e(i), __dmul_rn(k.DELTA, __dadd_rn(L.o(a), L.o(b)))));
+    L.e(i) = lift_scale_fwd<FMA>(k, L.e(i), __dadd_rn(L.o(a), L.o(b)));
   }
   sync();
   for (int i = tid; i < ol; i += nthr)
@@ -243,7 +243,7 @@ __device__ __forceinline__ void lift_forward(const CdfC& k, Line L, int len, int
   sync();
 }
 
-template <typename Line, typename Sync>
+template <bool FMA, typename Line, typename Sync>
 __device__ __forceinline__ void lift_inverse(const CdfC& k, Line L, int len, int tid, int nthr,
                                              Sync sync)
 {
@@ -253,22 +253,22 @@ __device__ __forceinline__ void lift_inverse(const CdfC& k, Line L, int len, int
   sync();
   for (int i = tid; i < el; i += nthr) {
     const int a = i > 0 ? i - 1 : 0, b = i < ol ? i : ol - 1;
-    L.e(i) = __dsub_rn(__dmul_rn(L.e(i), k.INV_EPSILON), __dmul_rn(k.DELTA, __dadd_rn(L.o(a), L.o(b))));
+    L.e(i) = lift_scale_inv<FMA>(k, L.e(i), __dadd_rn(L.o(a), L.o(b)));
   }
   sync();
   for (int i = tid; i < ol; i += nthr) {
     const int i1 = i + 1 < el ? i + 1 : el - 1;
-    L.o(i) = __dsub_rn(L.o(i), __dmul_rn(k.GAMMA, __dadd_rn(L.e(i), L.e(i1))));
+    L.o(i) = lift_sub<FMA>(L.o(i), k.GAMMA, __dadd_rn(L.e(i), L.e(i1)));
   }
   sync();
   for (int i = tid; i < el; i += nthr) {
     const int a = i > 0 ? i - 1 : 0, b = i < ol ? i : ol - 1;
-    L.e(i) = __dsub_rn(L.e(i), __dmul_rn(k.BETA, __dadd_rn(L.o(a), L.o(b))));
+    L.e(i) = lift_sub<FMA>(L.e(i), k.BETA, __dadd_rn(L.o(a), L.o(b)));
   }
   sync();
   for (int i = tid; i < ol; i += nthr) {
     const int i1 = i + 1 < el ? i + 1 : el - 1;
-    L.o(i) = __dsub_rn(L.o(i), __dmul_rn(k.ALPHA, __dadd_rn(L.e(i), L.e(i1))));
+    L.o(i) = lift_sub<FMA>(L.o(i), k.ALPHA, __dadd_rn(L.e(i), L.e(i1)));
   }
   sync();
 }
@@ -317,12 +317,18 @@ __global__ void k_dwt_x(const ChunkDev* chunks, const int* ids, CdfC k, int lx, 
     SmemLine L{s, el};
     auto sync = [] { __syncwarp(); };
     if (!INVERSE) {
-      lift_forward(k, L, lx, lane, 32, sync);
+      if (k.fma)
+        lift_forward<true>(k, L, lx, lane, 32, sync);
+      else
+        lift_forward<false>(k, L, lx, lane, 32, sync);
       for (int i = lane; i < lx; i += 32)
         g[i] = s[i];
     }
     else {
-      lift_inverse(k, L, lx, lane, 32, sync);
+      if (k.fma)
+        lift_inverse<true>(k, L, lx, lane, 32, sync);
+      else
+        lift_inverse<false>(k, L, lx, lane, 32, sync);
       for (int i = lane; i < lx; i += 32)
         g[i] = s[(i & 1) ? el + (i >> 1) : (i >> 1)];
     }
@@ -360,10 +366,18 @@ __global__ void k_dwt_col(const ChunkDev* chunks, const int* ids, CdfC k, int ax
   SmemCol L{smem, el, tw, cx};
   auto sync = [] { __syncthreads(); };
   // out-of-range columns still walk the barriers; they touch only their own (unused) column
-  if (!INVERSE)
-    lift_forward(k, L, in ? len : 0, r0, th, sync);
-  else
-    lift_inverse(k, L, in ? len : 0, r0, th, sync);
+  if (!INVERSE) {
+    if (k.fma)
+      lift_forward<true>(k, L, in ? len : 0, r0, th, sync);
+    else
+      lift_forward<false>(k, L, in ? len : 0, r0, th, sync);
+  }
+  else {
+    if (k.fma)
+      lift_inverse<true>(k, L, in ? len : 0, r0, th, sync);
+    else
+      lift_inverse<false>(k, L, in ? len : 0, r0, th, sync);
+  }
   if (in) {
     if (!INVERSE)
       for (int i = r0; i < len; i += th)
@@ -526,6 +540,12 @@ __global__ void k_scatter_out(SrcVol dst, const ChunkDev* chunks)
 // host launchers
 // ---------------------------------------------------------------------------------------------
 
+int& fma_flavour()
+{
+  static int f = std::getenv("SPERR_B200_FMA") ? std::atoi(std::getenv("SPERR_B200_FMA")) : 0;
+  return f;
+}
+
 CdfC cdf_constants()
 {
   // Same expressions as include/CDF97.h:136-147, evaluated in plain IEEE double arithmetic
@@ -556,6 +576,7 @@ CdfC cdf_constants()
   c.EPSILON = sq * t0;
   volatile double eps = c.EPSILON;
   c.INV_EPSILON = 1.0 / eps;
+  c.fma = fma_flavour() ? 1 : 0;
   return c;
 }
 

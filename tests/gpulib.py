@@ -31,6 +31,12 @@ class Lib:
         self.path = path
         self.lib = C.CDLL(path)
 
+    def set_fma_flavour(self, on):
+        f = self.lib.sperr_b200_set_fma_flavour
+        f.restype = None
+        f.argtypes = [C.c_int]
+        f(int(on))
+
     # ---- stage hooks ----
     def stage_condition(self, vol, dims):
         vol = np.ascontiguousarray(vol)
