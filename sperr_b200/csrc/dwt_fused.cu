@@ -182,6 +182,11 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
     s_max = 0;
   const CdfC k = a.k;
   const double mean = ch.mean;
+  // The ChunkDev lives in global memory: anything read through `ch` after a global store has to be
+  // fetched again (the store might alias it), which puts a dependent load in front of every store
+  // of the z phase. Local copies of the few fields used inside the loop avoid that.
+  double* const coef = ch.coef;
+  const unsigned cz0 = ch.z0;
 
   // what this thread loads of every plane: tile elements tid, tid + 256, ...
   constexpr int kPer = (kFI * kFI + kFThreads - 1) / kFThreads;   // 7
@@ -218,7 +223,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
     apos[c] = ((x | y) & 1) ? -1ll
                             : (a.apx_off >= 0 ? (long long)(y >> 1) * ax + (x >> 1) : (long long)dpos[c]);
   }
-  double* const abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : ch.coef;
+  double* const abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : coef;
+  ASSUME_GLOBAL(coef);
+  ASSUME_GLOBAL(abox);
+  ASSUME_GLOBAL(sbox);
   const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
   unsigned long long vmax = 0;
 
@@ -226,13 +234,13 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
     // ---- load planes 2 j0 .. 2 j0 + kPlanes - 1 (mirrored) ----
     for (int p = 0; p < kPlanes; p++) {
       const int gz = mirror(2 * j0 + p, lz);
-      const unsigned long long zoff = (SRC == 2 ? (unsigned long long)gz : (unsigned long long)(ch.z0 + gz)) * plane;
+      const unsigned long long zoff = (SRC == 2 ? (unsigned long long)gz : (unsigned long long)(cz0 + gz)) * plane;
       double* const tp = tile + (size_t)p * kFI * kFP;
 #ifndef SPERR_EMUL
       if (SRC != 2 && j0 + kNPB <= k1 + 1) {
         // the planes of the next step: pull them into L2 now, their loads then see L2 latency
         const int gz2 = mirror(2 * (j0 + kNPB) + p, lz);
-        const unsigned long long zoff2 = (unsigned long long)(ch.z0 + gz2) * plane;
+        const unsigned long long zoff2 = (unsigned long long)(cz0 + gz2) * plane;
 #pragma unroll
         for (int s = 0; s < kPer - 1; s++) {
           const void* ptr = SRC == 0 ? (const void*)(vf + zoff2 + goff[s]) : (const void*)(vd + zoff2 + goff[s]);
@@ -284,12 +292,12 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
             }
           }
           else {
-            ch.coef[(size_t)kk * cnxy + dpos[c]] = e2;
+            coef[(size_t)kk * cnxy + dpos[c]] = e2;
             const unsigned long long b = abs_bits(e2);
             vmax = b > vmax ? b : vmax;
           }
           if (kk < lz / 2) {   // odd z output (plane az + kk)
-            ch.coef[(size_t)(az + kk) * cnxy + dpos[c]] = o3;
+            coef[(size_t)(az + kk) * cnxy + dpos[c]] = o3;
             const unsigned long long b = abs_bits(o3);
             vmax = b > vmax ? b : vmax;
           }
@@ -333,6 +341,9 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     return;
   const CdfC k = a.k;
   const size_t cnx = ch.nx, cnxy = (size_t)ch.nx * ch.ny;
+  // local copies of what the loop reads through `ch` (see k_fwd3d)
+  const double* const coef = ch.coef;
+  const unsigned cz0 = ch.z0;
 
   // the (x, y) columns this thread runs the z lifting for: tile elements tid, tid + 256, ...
   constexpr int kPer = (kFI * kFI + kFThreads - 1) / kFThreads;   // 7
@@ -355,7 +366,11 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
       eoff[s] = a.apx_off >= 0 ? unsigned((gy >> 1) * ax + (gx >> 1)) : unsigned((size_t)(gy >> 1) * cnx + (gx >> 1));
     }
   }
-  const double* abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : ch.coef;
+  const double* abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : coef;
+  double* const obox = a.out_off >= 0 ? ch.scratch + a.out_off : nullptr;   // OUT 0, levels > 0
+  ASSUME_GLOBAL(coef);
+  ASSUME_GLOBAL(abox);
+  ASSUME_GLOBAL(obox);
   const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
 
   // epilogue ownership: (x, y) = (X0 + lane, Y0 + warp + 8 c), c = 0 .. 3, of every plane
@@ -371,21 +386,59 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     if (X0 + ep_lane < lx && Y0 + ep_warp + 8 * c < ly)
       ep_live |= 1u << c;
 
+  // mode 1 with correctors: lane 4 p + c of every warp fetches the 32 corrector flags of the row
+  // the warp owns in plane p of the step (row Y0 + warp + 8 c) at the top of the step; the epilogue
+  // gets them by shuffle. The load is in flight during the lifting passes instead of standing,
+  // one dependent global load per value, between the epilogue's stores.
+  const uint32_t* const obits = (OUT == 1 && a.cor.key) ? ch.obits : nullptr;
+  const int fl_p = ep_lane >> 2, fl_c = ep_lane & 3;
+  const bool fl_row = ep_lane < 4 * kPlanes && Y0 + ep_warp + 8 * fl_c < ly;
+  const unsigned long long fl_i0 = (unsigned long long)(Y0 + ep_warp + 8 * fl_c) * cnx + X0;
+
   for (int j0 = k0 - 2; j0 <= k1 + 1; j0 += kNPB) {
+    unsigned flags = 0;
+    if (OUT == 1 && obits) {
+      const int kk = j0 + (fl_p >> 1) - 2;
+      const int z = 2 * kk + (fl_p & 1);
+      if (fl_row && kk >= k0 && kk < k1 && z < lz) {
+        const unsigned long long i0 = (unsigned long long)z * cnxy + fl_i0;
+        const unsigned sh = unsigned(i0 & 31);
+        unsigned long long w = __ldg(obits + (i0 >> 5));
+        if (sh)   // the row straddles two words (every chunk's flag array ends with a spare word)
+          w |= (unsigned long long)__ldg(obits + (i0 >> 5) + 1) << 32;
+        flags = unsigned(w >> sh);
+      }
+    }
+#ifndef SPERR_EMUL
+    if (OUT == 2) {
+      // the source values the epilogue compares with: the same lane pulls the row's line into L2
+      const int kk = j0 + (fl_p >> 1) - 2;
+      const int z = 2 * kk + (fl_p & 1);
+      if (fl_row && kk >= k0 && kk < k1 && z < lz) {
+        const unsigned long long e = (unsigned long long)(cz0 + z) * ep_vplane + ep_g0 - ep_lane + fl_c * ep_gs;
+        const char* const ptr = reinterpret_cast<const char*>(a.vol.ptr) + e * (a.vol.is_float ? 4 : 8);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+        if (!a.vol.is_float)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 128));
+      }
+    }
+#endif
     // ---- z: pair j = (low-band plane mirror(2j) / 2, high-band plane az + mirror(2j + 1) / 2) ----
 #pragma unroll
     for (int q = 0; q < kNPB; q++) {
       const int j = j0 + q;
       const int ze = mirror(2 * j, lz) >> 1, zo = az + (mirror(2 * j + 1, lz) >> 1);
-      const double* const pe = ch.coef + (size_t)ze * cnxy;
-      const double* const po = ch.coef + (size_t)zo * cnxy;
+      const double* const pe = coef + (size_t)ze * cnxy;
+      const double* const po = coef + (size_t)zo * cnxy;
       const double* const pa = abox + (size_t)ze * aplane;
       double* const t0 = tile + (size_t)(2 * q) * kFI * kFP;
       double ev[kPer], ov[kPer];
 #pragma unroll
       for (int s = 0; s < kPer; s++) {
         if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
-          ev[s] = (((apx >> s) & 1u) ? pa : pe)[eoff[s]];
+          const double* const pz = ((apx >> s) & 1u) ? pa : pe;
+          ASSUME_GLOBAL(pz);
+          ev[s] = pz[eoff[s]];
           ov[s] = po[coff[s]];
         }
       }
@@ -417,14 +470,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
         continue;
       const double* const tp = tile + (size_t)p * kFI * kFP + (kFH + ep_warp) * kFP + kFH + ep_lane;
       if (OUT == 0 && a.out_off >= 0) {
-        double* const ob = ch.scratch + a.out_off + (size_t)z * ly * lx;
+        double* const ob = obox + (size_t)z * ly * lx;
 #pragma unroll
         for (int c = 0; c < 4; c++)
           if ((ep_live >> c) & 1u)
             ob[(size_t)(Y0 + ep_warp + 8 * c) * lx + X0 + ep_lane] = tp[8 * c * kFP];
         continue;
       }
-      const unsigned long long gz = (unsigned long long)(ch.z0 + z) * ep_vplane;
+      const unsigned long long gz = (unsigned long long)(cz0 + z) * ep_vplane;
       if (OUT == 0) {
         double* const vd = reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr)) + gz;
 #pragma unroll
@@ -436,13 +489,14 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
         const unsigned long long iz = (unsigned long long)z * cnxy;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
+          // flags of row c of plane p (all lanes take part in the shuffle)
+          const unsigned rowflags = obits ? __shfl_sync(0xffffffffu, flags, 4 * p + c) : 0u;
           if (!((ep_live >> c) & 1u))
             continue;
           double w = tp[8 * c * kFP];
-          if (a.cor.key) {   // src/SPECK_FLT.cpp:576-585: correctors are added before the mean
+          if ((rowflags >> ep_lane) & 1u) {   // src/SPECK_FLT.cpp:576-585: correctors are added before the mean
             const unsigned long long i = iz + ep_c0 + c * ep_cs;
-            if ((ch.obits[i >> 5] >> (i & 31)) & 1u)
-              w = __dadd_rn(w, corrector_lookup(a.cor, a.ids[blockIdx.y], i));
+            w = __dadd_rn(w, corrector_lookup(a.cor, a.ids[blockIdx.y], i));
           }
           w = __dadd_rn(w, ep_mean);
           if (a.vol.is_float)

@@ -22,6 +22,7 @@ typedef int cudaStream_t;
   emu::launch(grid, block, smem, [=]() { kern(__VA_ARGS__); })
 #define DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem())
 #define HD
+#define ASSUME_GLOBAL(p) ((void)0)
 #else
 #include <cuda_runtime.h>
 #define LAUNCH(kern, grid, block, smem, stream, ...)        \
@@ -34,7 +35,19 @@ typedef int cudaStream_t;
   extern __shared__ __align__(16) unsigned char name##_raw_smem[];  \
   type* name = reinterpret_cast<type*>(name##_raw_smem)
 #define HD __host__ __device__
+// A pointer fetched from a descriptor in memory is a generic pointer to the compiler: it emits LD /
+// ST, which may alias shared memory and therefore pin every shared-memory access behind them in
+// program order. This tells it the pointer is a global one (LDG / STG).
+#define ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
 #endif
+
+// The same hint as an expression: gptr(ch.coef)[i]
+template <class T>
+__device__ __forceinline__ T* gptr(T* p)
+{
+  ASSUME_GLOBAL(p);
+  return p;
+}
 
 namespace rt {
 

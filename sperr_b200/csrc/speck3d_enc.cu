@@ -23,15 +23,15 @@ __device__ __forceinline__ int node_p(const ShapeDev& s, const ChunkDev& ch, int
 {
   const LevelDesc& lv = s.h->lv[L];
   if (L == s.h->leaf_level)
-    return ch.pleaf[node_lin(lv, ix, iy, iz)];
-  return ch.pyr_p[lv.p_off + node_lin(lv, ix, iy, iz)];
+    return gptr(ch.pleaf)[node_lin(lv, ix, iy, iz)];
+  return gptr(ch.pyr_p)[lv.p_off + node_lin(lv, ix, iy, iz)];
 }
 
 __device__ __forceinline__ unsigned node_d(const ShapeDev& s, const ChunkDev& ch, int L, unsigned ix,
                                            unsigned iy, unsigned iz)
 {
   const LevelDesc& lv = s.h->lv[L];
-  return ch.pyr_d[lv.p_off + node_lin(lv, ix, iy, iz)];
+  return gptr(ch.pyr_d)[lv.p_off + node_lin(lv, ix, iy, iz)];
 }
 
 // Is the node below one of the initial sets of its own chain? (only matters for wavelet-packet
@@ -78,8 +78,8 @@ __global__ void k_pyr_level(const ChunkDev* chunks, const ShapeDev* shapes, cons
   NodeGeom g;
   node_geom(s, make_node(L, ix, iy, iz), g);
   if (g.lenx * g.leny * g.lenz == 1) {  // a pixel that persists at this level
-    ch.pyr_p[lv.p_off + idx] = int8_t(node_p(s, ch, g.Lc, g.x0, g.y0, g.z0));
-    ch.pyr_d[lv.p_off + idx] = 0;
+    gptr(ch.pyr_p)[lv.p_off + idx] = int8_t(node_p(s, ch, g.Lc, g.x0, g.y0, g.z0));
+    gptr(ch.pyr_d)[lv.p_off + idx] = 0;
     return;
   }
   int pc[8];
@@ -110,8 +110,8 @@ __global__ void k_pyr_level(const ChunkDev* chunks, const ShapeDev* shapes, cons
       }
     }
   }
-  ch.pyr_p[lv.p_off + idx] = int8_t(pmax);
-  ch.pyr_d[lv.p_off + idx] = D;
+  gptr(ch.pyr_p)[lv.p_off + idx] = int8_t(pmax);
+  gptr(ch.pyr_d)[lv.p_off + idx] = D;
   // pixels born when this set splits enter the LIP at plane pmax
   if (pmax >= 0 && (!check_real || node_is_real(s, L, ix, iy, iz))) {
     int k = 0;
@@ -119,7 +119,7 @@ __global__ void k_pyr_level(const ChunkDev* chunks, const ShapeDev* shapes, cons
       for (unsigned cy = 0; cy < g.nyc; cy++)
         for (unsigned cx = 0; cx < g.nxc; cx++, k++)
           if (pix[k])
-            ch.cmap[node_raster(s, g.Lc, g.x0 + cx, g.y0 + cy, g.z0 + cz)] = int8_t(pmax);
+            gptr(ch.cmap)[node_raster(s, g.Lc, g.x0 + cx, g.y0 + cy, g.z0 + cz)] = int8_t(pmax);
   }
 }
 
@@ -164,7 +164,7 @@ struct Tree3D {
             r.d = 0;
             r.lis_desc = 0;
             const unsigned long long ri = node_raster(s, g.Lc, jx, jy, jz);
-            r.sign = (ch.signs[ri >> 5] >> (ri & 31)) & 1u;
+            r.sign = (gptr(ch.signs)[ri >> 5] >> (ri & 31)) & 1u;
           }
           else {
             r.kind = (lx <= 2 && ly <= 2 && lz <= 2) ? 1 : 2;
@@ -184,7 +184,7 @@ struct Tree3D {
     for (int l = 0; l < s.h->nlevels; l++)
       if (s.h->lv[l].chain == 0 && s.h->lv[l].j == 0)
         top = l;
-    const int pm = top >= 0 ? int(ch.pyr_p[s.h->lv[top].p_off]) : int(ch.pleaf[0]);
+    const int pm = top >= 0 ? int(gptr(ch.pyr_p)[s.h->lv[top].p_off]) : int(gptr(ch.pleaf)[0]);
     return pm + 1;
   }
 
@@ -246,13 +246,13 @@ __global__ void k_pyr_pow2(const ChunkDev* chunks, Pow2Info g, int j)
     const unsigned jz = sz ? iz * 2 + ((unsigned(k) >> (sx + sy)) & 1u) : iz;
     if (leaf) {
       cpos[k] = ((size_t)jz * g.ny + jy) * g.nx + jx;
-      pc[k] = ch.pleaf[cpos[k]];
+      pc[k] = gptr(ch.pleaf)[cpos[k]];
       dc[k] = 1u;
     }
     else {
       cpos[k] = g.p_off[cj] + pow2_lin(g, cj, jx, jy, jz);
-      pc[k] = ch.pyr_p[cpos[k]];
-      dc[k] = ch.pyr_d[cpos[k]];
+      pc[k] = gptr(ch.pyr_p)[cpos[k]];
+      dc[k] = gptr(ch.pyr_d)[cpos[k]];
     }
     pmax = pc[k] > pmax ? pc[k] : pmax;
   }
@@ -268,11 +268,11 @@ __global__ void k_pyr_pow2(const ChunkDev* chunks, Pow2Info g, int j)
       }
     }
   }
-  ch.pyr_p[g.p_off[j] + idx] = int8_t(pmax);
-  ch.pyr_d[g.p_off[j] + idx] = D;
+  gptr(ch.pyr_p)[g.p_off[j] + idx] = int8_t(pmax);
+  gptr(ch.pyr_d)[g.p_off[j] + idx] = D;
   if (leaf && pmax >= 0)   // pixels born when this set splits enter the LIP at plane pmax
     for (int k = 0; k < nch; k++)
-      ch.cmap[cpos[k]] = int8_t(pmax);
+      gptr(ch.cmap)[cpos[k]] = int8_t(pmax);
 }
 
 struct Tree3DPow2 {
@@ -299,15 +299,15 @@ struct Tree3DPow2 {
       const unsigned jz = sz ? iz * 2 + ((unsigned(r) >> sy) & 1u) : iz;
       const size_t ri = ((size_t)jz * g.ny + jy) * g.nx + (sx ? ix * 2 : ix);
       if (sx) {   // ri is even: both values in one aligned 16-bit word, both sign bits in one word
-        const unsigned v = *reinterpret_cast<const unsigned short*>(ch.pleaf + ri);
+        const unsigned v = *reinterpret_cast<const unsigned short*>(gptr(ch.pleaf) + ri);
         p[k] = int(int8_t(v & 0xff));
         p[k + 1] = int(int8_t(v >> 8));
-        sg |= ((ch.signs[ri >> 5] >> (ri & 31)) & 3u) << k;
+        sg |= ((gptr(ch.signs)[ri >> 5] >> (ri & 31)) & 3u) << k;
         k += 2;
       }
       else {
-        p[k] = ch.pleaf[ri];
-        sg |= ((ch.signs[ri >> 5] >> (ri & 31)) & 1u) << k;
+        p[k] = gptr(ch.pleaf)[ri];
+        sg |= ((gptr(ch.signs)[ri >> 5] >> (ri & 31)) & 1u) << k;
         k += 1;
       }
     }
@@ -320,13 +320,13 @@ struct Tree3DPow2 {
     const Pow2Info& g = t.g;
     const int j = node_level(nd);
     if (j == g.J) {
-      p = ch.pleaf[((size_t)node_iz(nd) * g.ny + node_iy(nd)) * g.nx + node_ix(nd)];
+      p = gptr(ch.pleaf)[((size_t)node_iz(nd) * g.ny + node_iy(nd)) * g.nx + node_ix(nd)];
       d = 0;
       return;
     }
     const size_t at = g.p_off[j] + pow2_lin(g, j, node_ix(nd), node_iy(nd), node_iz(nd));
-    p = ch.pyr_p[at];
-    d = ch.pyr_d[at];
+    p = gptr(ch.pyr_p)[at];
+    d = gptr(ch.pyr_d)[at];
   }
 
   static __device__ __forceinline__ int children(const Data& t, const ChunkDev& ch, unsigned,
@@ -348,15 +348,15 @@ struct Tree3DPow2 {
       r.kind = kind;
       if (kind == 0) {
         const size_t ri = ((size_t)jz * g.ny + jy) * g.nx + jx;
-        r.p = ch.pleaf[ri];
+        r.p = gptr(ch.pleaf)[ri];
         r.d = 0;
         r.lis_desc = 0;
-        r.sign = (ch.signs[ri >> 5] >> (ri & 31)) & 1u;
+        r.sign = (gptr(ch.signs)[ri >> 5] >> (ri & 31)) & 1u;
       }
       else {
         const size_t at = g.p_off[cj] + pow2_lin(g, cj, jx, jy, jz);
-        r.p = ch.pyr_p[at];
-        r.d = ch.pyr_d[at];
+        r.p = gptr(ch.pyr_p)[at];
+        r.d = gptr(ch.pyr_d)[at];
         r.lis_desc = lis_desc;
         r.sign = 0;
       }
@@ -366,7 +366,7 @@ struct Tree3DPow2 {
 
   static __device__ __forceinline__ int planes(const Data& t, const ChunkDev& ch, unsigned)
   {
-    return int(ch.pyr_p[t.g.p_off[0]]) + 1;
+    return int(gptr(ch.pyr_p)[t.g.p_off[0]]) + 1;
   }
 
   static __device__ __forceinline__ int num_roots(const Data& t, const ChunkDev& ch, unsigned)
@@ -436,8 +436,8 @@ __global__ void k_pyr_iset(const ChunkDev* chunks, const ShapeDev* shapes, const
           D += di;
       }
     }
-    ch.pyr_p[h->pyr_nodes + l] = int8_t(pmax);
-    ch.pyr_d[h->pyr_nodes + l] = D;
+    gptr(ch.pyr_p)[h->pyr_nodes + l] = int8_t(pmax);
+    gptr(ch.pyr_d)[h->pyr_nodes + l] = D;
     pi = pmax;
     di = D;
   }
@@ -452,8 +452,8 @@ struct Tree2D {
   {
     if (is_inode(nd)) {
       const ShapeHeader* h = t.shapes[ch.shape].h;
-      p = ch.pyr_p[h->pyr_nodes + node_ix(nd)];
-      d = ch.pyr_d[h->pyr_nodes + node_ix(nd)];
+      p = gptr(ch.pyr_p)[h->pyr_nodes + node_ix(nd)];
+      d = gptr(ch.pyr_d)[h->pyr_nodes + node_ix(nd)];
       return;
     }
     Tree3D::pd(t, ch, c, nd, p, d);
@@ -488,8 +488,8 @@ struct Tree2D {
         return 3 | 0x100;
       ChildRec& r = out[3];
       r.id = make_node(kINodeLevel, unsigned(l - 1), 0, 0);
-      r.p = ch.pyr_p[h->pyr_nodes + l - 1];
-      r.d = ch.pyr_d[h->pyr_nodes + l - 1];
+      r.p = gptr(ch.pyr_p)[h->pyr_nodes + l - 1];
+      r.d = gptr(ch.pyr_d)[h->pyr_nodes + l - 1];
       r.kind = 2;
       r.lis_desc = unsigned(h->nlis);   // behind list 0
       r.sign = 0;
@@ -511,7 +511,7 @@ struct Tree2D {
           r.d = 0;
           r.lis_desc = 0;
           const unsigned long long ri = node_raster(s, g.Lc, jx, jy, 0);
-          r.sign = (ch.signs[ri >> 5] >> (ri & 31)) & 1u;
+          r.sign = (gptr(ch.signs)[ri >> 5] >> (ri & 31)) & 1u;
         }
         else
           fill_set(s, ch, g.Lc, jx, jy, r);

@@ -50,7 +50,7 @@ __device__ __forceinline__ unsigned long long fetch64(const DecChunk& d, unsigne
     return 0ull;
   const unsigned long long w = p >> 5;
   const unsigned sh = unsigned(p & 31);
-  const unsigned long long lo = d.bits[w], mid = d.bits[w + 1], hi = d.bits[w + 2];
+  const unsigned long long lo = gptr(d.bits)[w], mid = gptr(d.bits)[w + 1], hi = gptr(d.bits)[w + 2];
   unsigned long long v = (lo | (mid << 32)) >> sh;
   if (sh)
     v |= hi << (64 - sh);
@@ -67,7 +67,7 @@ struct BitReader {
   uint32_t cur;
   __device__ __forceinline__ void init(const DecChunk& d, unsigned long long p)
   {
-    w = d.bits;
+    w = gptr(d.bits);
     avail = d.avail;
     pos = p;
     cur_idx = ~0ull;
@@ -138,8 +138,8 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
   if (K == 0)
     return;
   for (unsigned long long i = tid; i < (K + 31) / 32 + 1; i += kDecThreads) {
-    d.sigarr[i] = 0;
-    d.signarr[i] = 0;
+    gptr(d.sigarr)[i] = 0;
+    gptr(d.signarr)[i] = 0;
   }
   __syncthreads();
 
@@ -208,9 +208,9 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
       if (s == 0) {
         if (ord < K) {
           if (b) {
-            atomicOr(&d.sigarr[ord >> 5], 1u << (ord & 31));
+            atomicOr(&gptr(d.sigarr)[ord >> 5], 1u << (ord & 31));
             if ((w64 >> (i + 1)) & 1ull)
-              atomicOr(&d.signarr[ord >> 5], 1u << (ord & 31));
+              atomicOr(&gptr(d.signarr)[ord >> 5], 1u << (ord & 31));
           }
           if (ord == K - 1)
             S.endpos = p + i + 1 + b;
@@ -235,7 +235,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
   const unsigned long long w0 = per_warp * warp, w1 = min((words + 3) & ~3ull, w0 + per_warp);
   unsigned long long cnt = 0;
   for (unsigned long long j = w0 + 4ull * lane; j < w1; j += 128) {
-    const uint4 m4 = *reinterpret_cast<const uint4*>(d.lip + j);
+    const uint4 m4 = *reinterpret_cast<const uint4*>(gptr(d.lip) + j);
     cnt += __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w);
   }
   for (int o = 16; o; o >>= 1)
@@ -255,7 +255,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
     const unsigned long long j = j0 + 4ull * lane;
     uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
     if (j < w1)
-      m4 = *reinterpret_cast<const uint4*>(d.lip + j);
+      m4 = *reinterpret_cast<const uint4*>(gptr(d.lip) + j);
     unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
     const unsigned c4 = unsigned(__popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w));
     unsigned inc = c4;
@@ -279,12 +279,12 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
       const unsigned long long wi = k >> 5;
       const unsigned sh = unsigned(k & 31);
       k += c;
-      unsigned sg = __funnelshift_r(d.sigarr[wi], d.sigarr[wi + 1], sh);
+      unsigned sg = __funnelshift_r(gptr(d.sigarr)[wi], gptr(d.sigarr)[wi + 1], sh);
       if (c < 32)
         sg &= (1u << c) - 1u;
       if (sg == 0)
         continue;
-      const unsigned sn = __funnelshift_r(d.signarr[wi], d.signarr[wi + 1], sh);
+      const unsigned sn = __funnelshift_r(gptr(d.signarr)[wi], gptr(d.signarr)[wi + 1], sh);
       unsigned keep = m;
       int t = 0;
       while (m) {
@@ -292,7 +292,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
         m &= m - 1;
         if ((sg >> t) & 1u) {
           keep &= ~(1u << bit);
-          d.pl[(j + q) * 32 + bit] = uint8_t(n_plane | (((sn >> t) & 1u) ? 0 : 0x80));
+          gptr(d.pl)[(j + q) * 32 + bit] = uint8_t(n_plane | (((sn >> t) & 1u) ? 0 : 0x80));
         }
         t++;
       }
@@ -301,7 +301,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
       nsig += __popc(sg);
     }
     if (changed)
-      *reinterpret_cast<uint4*>(d.lip + j) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
+      *reinterpret_cast<uint4*>(gptr(d.lip) + j) = make_uint4(mw[0], mw[1], mw[2], mw[3]);
   }
   for (int o = 16; o; o >>= 1)
     nsig += __shfl_xor_sync(0xffffffffu, nsig, o);
@@ -378,12 +378,12 @@ __device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c
       const unsigned long long i = ch.idx;
       if (sig) {
         const unsigned sgn = br.get();
-        d.pl[i] = uint8_t(n_plane | (sgn ? 0 : 0x80));
+        gptr(d.pl)[i] = uint8_t(n_plane | (sgn ? 0 : 0x80));
         knew++;
         f.sigc++;
       }
       else {
-        d.lip[i >> 5] |= 1u << (i & 31);
+        gptr(d.lip)[i >> 5] |= 1u << (i & 31);
         klip++;
       }
     }
@@ -404,13 +404,13 @@ __device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c
     else if (T::kHasI && ch.lis < 0)
       d.iset = ch.id;   // the set I stays outside the lists: it is tested after all of them
     else {
-      const unsigned slot = d.lis_cnt[ch.lis];
-      if (d.lis_off[ch.lis] + slot >= d.lis_off[ch.lis + 1]) {
+      const unsigned slot = gptr(d.lis_cnt)[ch.lis];
+      if (gptr(d.lis_off)[ch.lis] + slot >= gptr(d.lis_off)[ch.lis + 1]) {
         d.err |= 1u;
         return;
       }
-      d.lis[d.lis_off[ch.lis] + slot] = ch.id;
-      d.lis_cnt[ch.lis] = slot + 1;
+      gptr(d.lis)[gptr(d.lis_off)[ch.lis] + slot] = ch.id;
+      gptr(d.lis_cnt)[ch.lis] = slot + 1;
     }
   }
 }
@@ -423,10 +423,10 @@ __device__ void dec_lis_walk(DecChunk& d, const typename T::Data& tree, unsigned
   br.init(d, S.pos);
   unsigned long long klip = S.klip, knew = S.knew;
   for (int lev = d.nlis - 1; lev >= 0; lev--) {
-    const unsigned cnt = d.lis_cnt[lev];
+    const unsigned cnt = gptr(d.lis_cnt)[lev];
     if (cnt == 0)
       continue;
-    node_t* list = d.lis + d.lis_off[lev];
+    node_t* list = gptr(d.lis) + gptr(d.lis_off)[lev];
     unsigned w = 0;
     for (unsigned i = 0; i < cnt; i++) {
       const node_t nd = list[i];
@@ -438,7 +438,7 @@ __device__ void dec_lis_walk(DecChunk& d, const typename T::Data& tree, unsigned
       if (d.err)
         return;
     }
-    d.lis_cnt[lev] = w;
+    gptr(d.lis_cnt)[lev] = w;
   }
   if (T::kHasI && d.iset) {   // SPECK2D_INT::m_sorting_pass, third step (src/SPECK2D_INT.cpp:54-57)
     if (br.get()) {
@@ -474,15 +474,15 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
     S.knew = 0;
     S.endpos = 0;
     for (int l = 0; l < d.nlis; l++)
-      d.lis_cnt[l] = 0;
+      gptr(d.lis_cnt)[l] = 0;
     d.iset = T::kHasI ? T::iset(tree, d, c) : 0;
     const int nr = T::num_roots(tree, d, c);
     for (int r = 0; r < nr; r++) {
       node_t nd;
       int lis;
       T::root(tree, d, c, r, nd, lis);
-      d.lis[d.lis_off[lis] + d.lis_cnt[lis]] = nd;
-      d.lis_cnt[lis]++;
+      gptr(d.lis)[gptr(d.lis_off)[lis] + gptr(d.lis_cnt)[lis]] = nd;
+      gptr(d.lis_cnt)[lis]++;
     }
   }
   __syncthreads();

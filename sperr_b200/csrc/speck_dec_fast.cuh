@@ -260,7 +260,7 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
   const int nbits = kinds == 0 ? kFW + 64 : (kinds == 1 ? kFW + 256 : kFBits);
   for (int i = tid; i < nbits / 32 + 3; i += kDecThreads) {
     const unsigned long long w = w0 + i;
-    F.bits[i] = w < d.stage_words ? d.bits[w] : 0u;
+    F.bits[i] = w < d.stage_words ? gptr(d.bits)[w] : 0u;
   }
   if (tid == 0)
     F.boff = unsigned(base & 31);
@@ -365,11 +365,11 @@ static __device__ void f_expand_pixels(const DecChunk& d, const FastSmem& F, uns
     const unsigned long long i = base + cy * nx + cz * nxy;
     const unsigned s = (sigm >> (r * per_row)) & rm, g = (sgnm >> (r * per_row)) & rm;
     if (s & 1u)
-      d.pl[i] = uint8_t(n_plane | ((g & 1u) ? 0 : 0x80));
+      gptr(d.pl)[i] = uint8_t(n_plane | ((g & 1u) ? 0 : 0x80));
     if (s & 2u)
-      d.pl[i + 1] = uint8_t(n_plane | ((g & 2u) ? 0 : 0x80));
+      gptr(d.pl)[i + 1] = uint8_t(n_plane | ((g & 2u) ? 0 : 0x80));
     if (rm & ~s)   // x0 is even when a row has two pixels: both bits are in the same word
-      atomicOr(&d.lip[i >> 5], (rm & ~s) << (i & 31));
+      atomicOr(&gptr(d.lip)[i >> 5], (rm & ~s) << (i & 31));
   }
 }
 
@@ -430,7 +430,7 @@ static __device__ void f_expand_level(DecChunk& d, FastSmem& F, int j, const uns
           a++;
         }
         else
-          d.lis[b++] = kid[k];
+          gptr(d.lis)[b++] = kid[k];
       }
     }
     __syncthreads();
@@ -516,7 +516,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
   const unsigned m = F.cnt[lis];
   if (m == 0)
     return;
-  node_t* const list = d.lis + F.off[lis];
+  node_t* const list = gptr(d.lis) + F.off[lis];
   unsigned long long* const qn = kind == 0 ? F.qa_node : (kind == 1 ? F.qb_node : F.qc_node);
   uint16_t* const qp = kind == 0 ? F.qa_pos : (kind == 1 ? F.qb_pos : F.qc_pos);
   const unsigned qcap = kind == 2 ? unsigned(kFTok) : unsigned(kFQ);
@@ -807,7 +807,7 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
         F.err |= 1u;
         break;
       }
-      d.lis[F.off[cl] + slot] = pack(cj, jx, jy, jz);
+      gptr(d.lis)[F.off[cl] + slot] = pack(cj, jx, jy, jz);
       F.cnt[cl] = slot + 1;
     }
   }
@@ -883,7 +883,7 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
       const unsigned nst = min(unsigned(kFRoots), cnt - first);
       __syncthreads();
       for (unsigned t = tid; t < nst; t += kDecThreads)
-        F.rs_node[t] = iphase ? ((unsigned long long)(0x100 | F.iset) << 32) : d.lis[F.off[lis] + first + t];
+        F.rs_node[t] = iphase ? ((unsigned long long)(0x100 | F.iset) << 32) : gptr(d.lis)[F.off[lis] + first + t];
       for (unsigned t = tid; t < unsigned(kFRoots / 32); t += kDecThreads)
         F.rs_gone[t] = 0;
       if (tid == 0) {
@@ -902,7 +902,7 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
       }
       __syncthreads();
       if (!iphase)
-        f_compact_roots(F, d.lis + F.off[lis]);
+        f_compact_roots(F, gptr(d.lis) + F.off[lis]);
       __syncthreads();
       const long long f_te = F_CLOCK();
       if (tid == 0)
@@ -930,10 +930,19 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
   DYN_SMEM(FastSmem, Fp);
   FastSmem& F = *Fp;
   const unsigned c = blockIdx.x;
-  DecChunk& d = chunks[c];
-  if (d.skip || d.planes == 0 || !d.pow2)
+  if (chunks[c].skip || chunks[c].planes == 0 || !chunks[c].pow2)
     return;
   const int tid = threadIdx.x;
+  // The job descriptor is worked on in shared memory and written back at the end. Read through
+  // the global struct, every pointer in it (bits, pl, lip, lis, ...) has to be fetched again after
+  // each global store, which may alias it: one more dependent load in front of nearly every access
+  // of a kernel that is bound by exactly such chains. Shared memory cannot alias the global arrays.
+  __shared__ DecChunk sd;
+  static_assert(sizeof(DecChunk) % 8 == 0, "DecChunk is copied in 8-byte words");
+  for (unsigned i = tid; i < sizeof(DecChunk) / 8; i += blockDim.x)
+    reinterpret_cast<unsigned long long*>(&sd)[i] = reinterpret_cast<const unsigned long long*>(&chunks[c])[i];
+  __syncthreads();
+  DecChunk& d = sd;
   if (tid == 0) {
     S.pos = 0;
     S.klip = 0;
@@ -950,7 +959,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     for (int k = 0; k < 8; k++)
       F.prof[k] = 0;
     for (int l = 0; l <= d.nlis; l++)
-      F.off[l] = d.lis_off[l];
+      F.off[l] = gptr(d.lis_off)[l];
     for (int l = 0; l < d.nlis; l++)
       F.cnt[l] = 0;
   }
@@ -960,7 +969,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     for (int r = 0; r < d.nroots; r++) {
       const unsigned long long nd = d.roots[r];
       const int lis = f_lis(F, int(nd >> 32));
-      d.lis[F.off[lis] + F.cnt[lis]] = nd;
+      gptr(d.lis)[F.off[lis] + F.cnt[lis]] = nd;
       F.cnt[lis]++;
     }
   }
@@ -986,6 +995,9 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     for (int k = 0; k < 8; k++)
       d.prof[k] = F.prof[k];
   }
+  __syncthreads();
+  for (unsigned i = tid; i < sizeof(DecChunk) / 8; i += blockDim.x)
+    reinterpret_cast<unsigned long long*>(&chunks[c])[i] = reinterpret_cast<const unsigned long long*>(&sd)[i];
 }
 
 }  // namespace sperr_b200

@@ -74,8 +74,8 @@ constexpr int kLrBlock = 1024;
 
 __device__ __forceinline__ unsigned long long load_mag(const ChunkDev& ch, unsigned long long i)
 {
-  return ch.wide ? reinterpret_cast<const unsigned long long*>(ch.mag)[i]
-                 : (unsigned long long)reinterpret_cast<const unsigned*>(ch.mag)[i];
+  return ch.wide ? reinterpret_cast<const unsigned long long*>(gptr(ch.mag))[i]
+                 : (unsigned long long)reinterpret_cast<const unsigned*>(gptr(ch.mag))[i];
 }
 
 // A CUDA block takes kLrUnits consecutive 1024-coefficient units: their loads are in flight together
@@ -88,7 +88,7 @@ __device__ __forceinline__ int lr_load(const ChunkDev& ch, unsigned long long i)
 {
   if (i >= ch.n)
     return -1;
-  return (int(ch.pleaf[i]) & 0xff) | (int(ch.cmap[i]) << 8);
+  return (int(gptr(ch.pleaf)[i]) & 0xff) | (int(gptr(ch.cmap)[i]) << 8);
 }
 __device__ __forceinline__ int lr_p(int v) { return int(int8_t(v & 0xff)); }
 __device__ __forceinline__ int lr_cm(int v) { return v >> 8; }
@@ -292,7 +292,7 @@ static __global__ void __launch_bounds__(kLrBlock, 2) k_lipref_emit(const ChunkD
     }
     __syncthreads();
     const unsigned long long mag = (valid && p >= 0 && wmax >= 0) ? load_mag(ch, i) : 0;
-    const unsigned sgn = (valid && wmax >= 0) ? (ch.signs[i >> 5] >> (i & 31)) & 1u : 0;
+    const unsigned sgn = (valid && wmax >= 0) ? (gptr(ch.signs)[i >> 5] >> (i & 31)) & 1u : 0;
     for (int n = wmax - 1; n >= first; n--) {   // warp-uniform bounds (no iteration when wmax < 0)
       const bool inlip = cm > n && p <= n;
       const bool newsig = inlip && p == n;
@@ -305,8 +305,8 @@ static __global__ void __launch_bounds__(kLrBlock, 2) k_lipref_emit(const ChunkD
         if (inlip) {
           const unsigned long long pos = s_blip[n] + before + __popc(b0 & lt) + __popc(b1 & lt);
           if (newsig) {
-            put_bit(ch.spk, pos, 1);
-            put_bit(ch.spk, pos + 1, sgn);
+            put_bit(gptr(ch.spk), pos, 1);
+            put_bit(gptr(ch.spk), pos + 1, sgn);
           }
         }
       }
@@ -314,7 +314,7 @@ static __global__ void __launch_bounds__(kLrBlock, 2) k_lipref_emit(const ChunkD
         const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? unsigned(s_ref[n][lane]) : 0u);
         if (ref) {
           const unsigned long long pos = s_bref[n] + before + __popc(b2 & lt);
-          put_bit(ch.spk, pos, unsigned(mag >> n) & 1u);
+          put_bit(gptr(ch.spk), pos, unsigned(mag >> n) & 1u);
         }
       }
     }
@@ -435,7 +435,7 @@ __global__ void k_root_emit(EncCtx ctx, typename T::Data tree, unsigned long lon
     unsigned d;
     T::pd(tree, ch, c, nd, p, d);
     if (p == ch.cur_n) {
-      put_bit(ch.spk, pos, 1);
+      put_bit(gptr(ch.spk), pos, 1);
       app.front(0, c, nd, pos + 1);
     }
     else if (ch.next_needed)  // insignificant: stays in its list, same position
@@ -465,7 +465,7 @@ __global__ void k_expand(EncCtx ctx, typename T::Data tree, int src)
     const int nch = nchf & 0xff;
     const bool all_tested = (nchf & 0x100) != 0;   // 2D: last split of the set I
     BitRun run;
-    run.start(ch.spk, cur);
+    run.start(gptr(ch.spk), cur);
     int sigc = 0;
     for (int k = 0; k < nch; k++) {
       const bool need = sigc != 0 || k != nch - 1 || all_tested;

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kRecBlock, 2) k_rec_count(const DecChunk* jobs
 #pragma unroll
   for (int u = 0; u < kRecUnits; u++) {
     const unsigned long long i = (unsigned long long)(blk0 + u) * kRecBlock + threadIdx.x;
-    pu[u] = i < d.n ? rec_plane(d.pl[i]) : -1;
+    pu[u] = i < d.n ? rec_plane(gptr(d.pl)[i]) : -1;
   }
 #pragma unroll
   for (int u = 0; u < kRecUnits; u++)
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs
       for (int u = 0; u < kRecUnits; u++) {
         const unsigned long long i = (unsigned long long)(blk0 + u) * kRecBlock + threadIdx.x;
         if (i < ch.n)
-          ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, 0.0), 1.0);
+          gptr(ch.coef)[i] = __dmul_rn(__dmul_rn(ch.q, 0.0), 1.0);
       }
     return;
   }
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs
 #pragma unroll
   for (int u = 0; u < kRecUnits; u++) {
     const unsigned long long i = (unsigned long long)(blk0 + u) * kRecBlock + threadIdx.x;
-    vu[u] = i < d.n ? d.pl[i] : 0xFFu;
+    vu[u] = i < d.n ? gptr(d.pl)[i] : 0xFFu;
   }
   if (int(threadIdx.x) < d.planes && threadIdx.x < kMaxPlanes) {
     s_nref[threadIdx.x] = d.ref_cnt[threadIdx.x];
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs
     const bool neg = p >= 0 && (v & 0x80u);
     if (!((mask >> u) & 1u)) {   // uniform over the block: all zero, or significant at plane 0 only
       if (mode == 0 && in)
-        ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, p >= 0 ? 1.0 : 0.0), neg ? -1.0 : 1.0);
+        gptr(ch.coef)[i] = __dmul_rn(__dmul_rn(ch.q, p >= 0 ? 1.0 : 0.0), neg ? -1.0 : 1.0);
       continue;
     }
     if (threadIdx.x == 0)
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs
             (unsigned long long)counts[((size_t)c * maxp + n) * nblk + blk] + before + __popc(b & lt);
         if (rank < nref) {
           const unsigned long long bp = s_base[n] + rank;
-          const unsigned bit = (d.bits[bp >> 5] >> (bp & 31)) & 1u;
+          const unsigned bit = (gptr(d.bits)[bp >> 5] >> (bp & 31)) & 1u;
           if (n >= 1) {
             const unsigned long long half = 1ull << (n - 1);
             mag = bit ? mag + half : mag - half;
@@ -236,14 +236,14 @@ __global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs
     }
     if (mode == 0) {
       if (in)
-        ch.coef[i] = __dmul_rn(__dmul_rn(ch.q, __ull2double_rn(mag)), neg ? -1.0 : 1.0);
+        gptr(ch.coef)[i] = __dmul_rn(__dmul_rn(ch.q, __ull2double_rn(mag)), neg ? -1.0 : 1.0);
     }
     else {
       // outlier correctors: a sorted list for the consumers plus one flag bit per value
       const bool has = in && p >= 0 && mag != 0;
       const unsigned b = __ballot_sync(0xffffffffu, has);
       if (lane == 0 && in)
-        ch.obits[i >> 5] = b;
+        gptr(ch.obits)[i >> 5] = b;
       if (has) {
         double e = mag == 1 ? 1.1 : __dsub_rn(__ull2double_rn(mag), 0.25);
         e = __dmul_rn(e, __dmul_rn(tols[c], neg ? -1.0 : 1.0));
@@ -266,7 +266,7 @@ __global__ void k_apply_correctors(const ChunkDev* chunks, const unsigned long l
   if (ch.fused)
     return;
   const unsigned long long pos = k & 0xffffffffull;
-  ch.coef[pos] = __dadd_rn(ch.coef[pos], val[i]);
+  gptr(ch.coef)[pos] = __dadd_rn(gptr(ch.coef)[pos], val[i]);
 }
 
 void launch_apply_correctors(const ChunkDev* d_chunks, const unsigned long long* d_key,

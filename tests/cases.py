@@ -38,6 +38,8 @@ SYN_SMALL = [
     ((32, 32, 64), (32, 32, 64), 3, 1e-2),
     ((128, 16, 16), (128, 16, 16), 3, 1e-3),
     ((96, 80, 72), (96, 80, 72), 3, 1e-3),      # tiles interior in x: 128-bit loads of the float volume
+    ((50, 44, 40), (50, 44, 40), 3, 1e-3),      # rows of a tile straddle two words of the corrector flags
+    ((100, 88, 40), (50, 44, 40), 3, 2e-3),     # the same with four chunks
 ]
 SYN_GPU = SYN_SMALL + [
     ((256, 256, 128), (256, 256, 128), 3, 1e-3),
