@@ -502,6 +502,7 @@ __global__ void k_pix_first(const unsigned long long* keys, unsigned npix_total,
 
 struct Tree1D {
   static constexpr bool kHasLeaf8 = false;
+  static constexpr bool kIsOutlierTree = true;   // profile ranges of this encoder are named enc1d.*
   struct Data {
     const ONode* nodes;
     const OutMeta* meta;

@@ -344,6 +344,10 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   b_.push(st);
 
   auto quantize_and_encode = [&](Speck3DEncoder& enc, std::vector<EncResult>& res) {
+    // counters read back by this thread and by the outlier thread below go through pinned bounce
+    // buffers, so that neither thread's read-back holds up the other's launches (rt.h)
+    rt::ReadbackScope readback_main;
+    (void)readback_main;
     launch_qdecide(b_.dev(), nc, st);
     b_.pull(st);
     bool any_wide = false;
@@ -410,6 +414,8 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     std::exception_ptr side_err;
     std::thread helper([&] {
       try {
+        rt::ReadbackScope readback_side;
+        (void)readback_side;
         RT_CHECK(cudaSetDevice(dev));
         outlier_chain(side_);
         rt::sync(side_);

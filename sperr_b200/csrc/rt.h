@@ -85,11 +85,6 @@ inline void h2d(void* d, const void* s, size_t n, cudaStream_t st)
   if (n)
     RT_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, st));
 }
-inline void d2h(void* d, const void* s, size_t n, cudaStream_t st)
-{
-  if (n)
-    RT_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st));
-}
 inline void d2d(void* d, const void* s, size_t n, cudaStream_t st)
 {
   if (n)
@@ -100,7 +95,6 @@ inline void dset(void* d, int v, size_t n, cudaStream_t st)
   if (n)
     RT_CHECK(cudaMemsetAsync(d, v, n, st));
 }
-inline void sync(cudaStream_t st) { RT_CHECK(cudaStreamSynchronize(st)); }
 inline void* hmalloc_pinned(size_t n)
 {
   void* p = nullptr;
@@ -121,6 +115,76 @@ inline bool is_pinned_host(const void* p)
   }
   return a.type == cudaMemoryTypeHost;
 }
+
+// Small read-backs (counters, chunk descriptors) into ordinary host memory. A cudaMemcpyAsync into
+// pageable memory only returns when the copy has been done, i.e. after everything queued on the
+// stream before it, and the other host threads of the process cannot launch meanwhile: the outlier
+// thread of the compressor, reading a counter behind a 13 ms kernel, stalled the SPECK encoder's
+// thread for as long. Such copies land in a pinned bounce buffer of the stream instead (really
+// asynchronous) and are handed to their destinations by the rt::sync of that stream. A stream is
+// used by one host thread at a time, every d2h is followed by the sync of its stream on the same
+// thread; copies into pinned memory and large ones are issued directly, as before. Opt-in per host
+// thread (ReadbackScope): the compressor's two threads use it, everything else copies as before.
+constexpr size_t kReadbackMax = size_t(1) << 20;
+inline bool& readback_on()
+{
+  static thread_local bool on = false;
+  return on;
+}
+struct ReadbackScope {
+  bool prev;
+  ReadbackScope() : prev(readback_on()) { readback_on() = true; }
+  ~ReadbackScope() { readback_on() = prev; }
+};
+struct Readback {
+  struct Item {
+    void* dst;
+    size_t off, n;
+  };
+  char* pin = nullptr;
+  size_t cap = 0, used = 0;
+  std::vector<Item> items;
+};
+inline Readback& readback_of(cudaStream_t st)
+{
+  static std::mutex mu;
+  static std::map<cudaStream_t, Readback>* m = new std::map<cudaStream_t, Readback>();   // lives as long as the process
+  std::lock_guard<std::mutex> l(mu);
+  return (*m)[st];
+}
+inline void d2h(void* d, const void* s, size_t n, cudaStream_t st)
+{
+  if (!n)
+    return;
+  if (readback_on() && n <= kReadbackMax && !is_pinned_host(d)) {
+    Readback& r = readback_of(st);
+    const size_t need = (n + 15) & ~size_t(15);
+    if (r.used + need > r.cap && r.items.empty()) {   // nothing in flight: the buffer may be replaced
+      hfree_pinned(r.pin);
+      r.pin = nullptr;
+      r.cap = 0;
+      r.pin = static_cast<char*>(hmalloc_pinned(4 * kReadbackMax));
+      r.cap = 4 * kReadbackMax;
+      r.used = 0;
+    }
+    if (r.used + need <= r.cap) {
+      RT_CHECK(cudaMemcpyAsync(r.pin + r.used, s, n, cudaMemcpyDeviceToHost, st));
+      r.items.push_back(Readback::Item{d, r.used, n});
+      r.used += need;
+      return;
+    }
+  }
+  RT_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, st));
+}
+inline void sync(cudaStream_t st)
+{
+  RT_CHECK(cudaStreamSynchronize(st));
+  Readback& r = readback_of(st);
+  for (const Readback::Item& it : r.items)
+    std::memcpy(it.dst, r.pin + it.off, it.n);
+  r.items.clear();
+  r.used = 0;
+}
 inline bool is_device_ptr(const void* p)
 {
   cudaPointerAttributes a;
@@ -138,6 +202,7 @@ inline void d2h(void* d, const void* s, size_t n, cudaStream_t) { std::memcpy(d,
 inline void d2d(void* d, const void* s, size_t n, cudaStream_t) { std::memmove(d, s, n); }
 inline void dset(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); }
 inline void sync(cudaStream_t) {}
+struct ReadbackScope {};
 inline void* hmalloc_pinned(size_t n) { return std::malloc(n ? n : 1); }
 inline void hfree_pinned(void* p) { std::free(p); }
 inline bool is_device_ptr(const void*) { return false; }

@@ -130,6 +130,7 @@ __global__ void k_pyr_level(const ChunkDev* chunks, const ShapeDev* shapes, cons
 
 struct Tree3D {
   static constexpr bool kHasLeaf8 = false;
+  static constexpr bool kIsOutlierTree = false;
   struct Data {
     const ShapeDev* shapes;
   };
@@ -277,6 +278,7 @@ __global__ void k_pyr_pow2(const ChunkDev* chunks, Pow2Info g, int j)
 
 struct Tree3DPow2 {
   static constexpr bool kHasLeaf8 = true;
+  static constexpr bool kIsOutlierTree = false;
   struct Data {
     const ShapeDev* shapes;
     Pow2Info g;
@@ -445,6 +447,7 @@ __global__ void k_pyr_iset(const ChunkDev* chunks, const ShapeDev* shapes, const
 
 struct Tree2D {
   static constexpr bool kHasLeaf8 = false;
+  static constexpr bool kIsOutlierTree = false;
   typedef Tree3D::Data Data;
 
   static __device__ __forceinline__ void pd(const Data& t, const ChunkDev& ch, unsigned c, node_t nd,

@@ -648,6 +648,7 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   ctx.maxp = 1;
   ctx.sizes = ctx.bases = nullptr;
 
+  rt::ProfScope* ps_seed = new rt::ProfScope(T::kIsOutlierTree ? "enc1d.seed" : "enc.seed", st);
   LAUNCH(k_enc_seed<T>, dim3(1), dim3(1024), 0, st, ctx, tree);
 
   // planes are only known on the device: fetch them to size the staging buffers and tables
@@ -656,6 +657,8 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   unsigned long long total_roots = 0;
   rt::d2h(&total_roots, ctx.total_roots, 8, st);
   rt::sync(st);
+  delete ps_seed;
+  rt::ProfScope* ps_zero = new rt::ProfScope(T::kIsOutlierTree ? "enc1d.stage_zero" : "enc.stage_zero", st);
   int maxp = 1;
   for (auto& c : hc)
     maxp = std::max(maxp, c.planes);
@@ -687,8 +690,9 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   ctx.sizes = w.sizes.as<unsigned long long>();
   ctx.bases = ctx.sizes + (size_t)nchunks * 2 * maxp;
   unsigned* d_counts = w.counts.as<unsigned>();
+  delete ps_zero;
   if (nblk) {
-    rt::ProfScope ps("enc.lipref_count", st);
+    rt::ProfScope ps(T::kIsOutlierTree ? "enc1d.lipref_count" : "enc.lipref_count", st);
     LAUNCH(k_lipref_count, dim3((nblk + kLrUnits - 1) / kLrUnits, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, maxp, nblk);
     LAUNCH(k_lipref_scan, dim3(2 * maxp, nchunks), dim3(1024), 0, st, d_chunks, d_counts, ctx.sizes,
            maxp, nblk);
@@ -698,7 +702,7 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   void* d_scan_tmp = w.scan_tmp.p;
   const unsigned cgrid = unsigned((nchunks + 127) / 128);
   for (int step = 0; step < maxp; step++) {
-    rt::ProfScope ps("enc.plane_loop", st);
+    rt::ProfScope ps(T::kIsOutlierTree ? "enc1d.plane_loop" : "enc.plane_loop", st);
     LAUNCH(k_plane_pre, dim3(cgrid), dim3(128), 0, st, ctx, step);
     const unsigned rgrid = unsigned(std::min<unsigned long long>((total_roots + 255) / 256, 148 * 16));
     if (total_roots)
@@ -724,7 +728,7 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   }
 
   // LIP / refinement emission
-  rt::ProfScope ps_emit("enc.lipref_emit", st);
+  rt::ProfScope ps_emit(T::kIsOutlierTree ? "enc1d.lipref_emit" : "enc.lipref_emit", st);
   if (nblk)
     LAUNCH(k_lipref_emit, dim3((nblk + kLrUnits - 1) / kLrUnits, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, ctx.bases,
            maxp, nblk);
