@@ -330,11 +330,14 @@ def run_ours(args):
         # launched on, over these very steps (two event records per range, no synchronisation
         # before the loop ends); per-stage times below are averages over the timed steps
         prof_on(1)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
         e0.record()
-        for _ in range(args.steps):
+        for i in range(args.steps):
             stream = step_dev()
+            marks[i].record()   # per-step times (reported as step_ms_each; one record, no wait)
         e1.record()
         barrier()
+        step_each = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
         launches_per_step = (launch_count() - l0) // args.steps
         buf = C.create_string_buffer(1 << 16)
         prof_dump(buf, len(buf))
@@ -348,19 +351,24 @@ def run_ours(args):
     ms = float(t.item())
 
     # compress-only and decompress-only rates (device-resident)
-    def timed(fn, reps):
+    each = {}
+
+    def timed(fn, reps, tag):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        mk = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
         a.record()
-        for _ in range(reps):
+        for i in range(reps):
             fn()
+            mk[i].record()
         b.record()
         barrier()
+        each[tag] = [round(x.elapsed_time(y), 2) for x, y in zip([a] + mk[:-1], mk)]
         tt = torch.tensor([a.elapsed_time(b) / reps], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
-    ms_c = timed(comp_dev, args.steps)
-    ms_d = timed(lambda: decomp_dev(stream), args.steps)
+    ms_c = timed(comp_dev, args.steps, "compress")
+    ms_d = timed(lambda: decomp_dev(stream), args.steps, "decompress")
     got = state["out"].reshape(-1)
     maxerr = float((got.double() - vol.double()).abs().max().item())
     # decoded values are rounded to fp32 after the bound was enforced in fp64: allow one fp32 ulp
@@ -428,6 +436,9 @@ def run_ours(args):
             "compress_gbs": world * nbytes / (ms_c * 1e-3) / GB,
             "decompress_gbs": world * nbytes / (ms_d * 1e-3) / GB, "max_abs_err": maxerr,
             "e2e": e2e, "gpu_launches": launches_per_step,
+            # rank 0's individual calls (ms): a host-side stall in one call shows here
+            "step_ms_each": [round(x, 2) for x in step_each], "compress_ms_each": each["compress"],
+            "decompress_ms_each": each["decompress"],
         }
         out.update(rooflines(stages, nvals, int(stream.size)))
         if world == 1 and args.cpu_baseline:
