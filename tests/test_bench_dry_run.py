@@ -1,0 +1,67 @@
+"""bench.py's host logic (timed loops, stage ranges, JSON line) executed in this GPU-less container.
+
+The device layer is faked for the run: torch's CUDA calls become no-ops / host timers, the process
+group is gloo, and the compute behind the C ABI is the CPU SIMT emulation of the CUDA kernels
+(tests/emul -- test infrastructure only; the product never loads it). What is checked is that
+`python bench.py` walks through every statement of its own arm and prints one JSON line with the
+keys the driver reads; numbers are meaningless here.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import gpulib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+DRIVER = r"""
+import sys, time, types
+sys.path.insert(0, %(root)r)
+sys.path.insert(0, %(tests)r)
+import torch
+import torch.distributed as dist
+
+class Ev:
+    def __init__(self, enable_timing=True):
+        self.t = None
+    def record(self):
+        self.t = time.perf_counter()
+    def elapsed_time(self, other):
+        return (other.t - self.t) * 1e3
+
+cpu = torch.device("cpu")
+real_device = torch.device
+torch.cuda.Event = Ev
+torch.cuda.set_device = lambda *a, **k: None
+torch.cuda.synchronize = lambda *a, **k: None
+torch.device = lambda *a, **k: cpu
+real_init = dist.init_process_group
+dist.init_process_group = lambda backend, rank, world_size, device_id=None: real_init("gloo", rank=rank, world_size=world_size)
+
+import sperr_b200
+from sperr_b200 import api
+real_load = api.load
+sperr_b200.load = lambda path=None: real_load(%(emul)r)
+
+import bench
+sys.argv = ["bench.py", "--size", "32", "--steps", "2", "--warmup", "1", "--e2e", "0", "--cpu-baseline", "0"]
+bench.main()
+"""
+
+
+def test_bench_own_arm_dry_run():
+    gpulib.build_emul()
+    code = DRIVER % {"root": ROOT, "tests": os.path.join(ROOT, "tests"), "emul": gpulib.EMUL_SO}
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617", RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches",
+              "stages_ms", "compress_gbs", "decompress_gbs", "step_ms_each", "compress_ms_each",
+              "decompress_ms_each"):
+        assert k in d, k
+    assert d["steps"] == 2 and len(d["step_ms_each"]) == 2 and len(d["decompress_ms_each"]) == 2
+    assert d["max_abs_err"] <= 1e-3 + 1.2e-7
