@@ -65,3 +65,24 @@ def test_bench_own_arm_dry_run():
         assert k in d, k
     assert d["steps"] == 2 and len(d["step_ms_each"]) == 2 and len(d["decompress_ms_each"]) == 2
     assert d["max_abs_err"] <= 1e-3 + 1.2e-7
+
+
+def test_bench_two_ranks_dry_run():
+    """the torchrun shape of the same arm: two ranks, chunk streams gathered to rank 0 (gloo here)"""
+    gpulib.build_emul()
+    code = DRIVER % {"root": ROOT, "tests": os.path.join(ROOT, "tests"), "emul": gpulib.EMUL_SO}
+    code = code.replace('"--size", "32"', '"--gpus", "2", "--size", "32"')
+    code = code.replace("bench.main()", "bench.CHUNK = 16   # 32 x 32 x 64 values: 16 chunks, 8 per rank\nbench.main()")
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29627", RANK=str(rank), WORLD_SIZE="2",
+                   LOCAL_RANK=str(rank))
+        procs.append(subprocess.Popen([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                      text=True, env=env))
+    outs = [p.communicate(timeout=900) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-3000:]
+    lines = [ln for ln in outs[0][0].splitlines() if ln.startswith("{")]
+    assert lines and not [ln for ln in outs[1][0].splitlines() if ln.startswith("{")]   # rank 0 alone prints
+    d = json.loads(lines[-1])
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and len(d["step_ms_each"]) == 2
