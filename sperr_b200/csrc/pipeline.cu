@@ -346,6 +346,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   auto quantize_and_encode = [&](Speck3DEncoder& enc, std::vector<EncResult>& res) {
     // counters read back by this thread and by the outlier thread below go through pinned bounce
     // buffers, so that neither thread's read-back holds up the other's launches (rt.h)
+    rt::readback_abandon();   // nothing of an earlier, failed call may be delivered now
     rt::ReadbackScope readback_main;
     (void)readback_main;
     launch_qdecide(b_.dev(), nc, st);

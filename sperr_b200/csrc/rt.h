@@ -145,12 +145,32 @@ struct Readback {
   size_t cap = 0, used = 0;
   std::vector<Item> items;
 };
+struct ReadbackTable {
+  std::mutex mu;
+  std::map<cudaStream_t, Readback> m;
+};
+inline ReadbackTable& readback_table()
+{
+  static ReadbackTable* t = new ReadbackTable();   // lives as long as the process
+  return *t;
+}
 inline Readback& readback_of(cudaStream_t st)
 {
-  static std::mutex mu;
-  static std::map<cudaStream_t, Readback>* m = new std::map<cudaStream_t, Readback>();   // lives as long as the process
-  std::lock_guard<std::mutex> l(mu);
-  return (*m)[st];
+  ReadbackTable& t = readback_table();
+  std::lock_guard<std::mutex> l(t.mu);
+  return t.m[st];
+}
+// Forgets copies whose rt::sync never came (a call that ended in an exception between the two):
+// their destinations are gone. Only for a point where no read-back of the process is in flight,
+// i.e. the start of an API call (callers are serialised) before it starts helper threads.
+inline void readback_abandon()
+{
+  ReadbackTable& t = readback_table();
+  std::lock_guard<std::mutex> l(t.mu);
+  for (auto& kv : t.m) {
+    kv.second.items.clear();
+    kv.second.used = 0;
+  }
 }
 inline void d2h(void* d, const void* s, size_t n, cudaStream_t st)
 {
@@ -203,6 +223,7 @@ inline void d2d(void* d, const void* s, size_t n, cudaStream_t) { std::memmove(d
 inline void dset(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); }
 inline void sync(cudaStream_t) {}
 struct ReadbackScope {};
+inline void readback_abandon() {}
 inline void* hmalloc_pinned(size_t n) { return std::malloc(n ? n : 1); }
 inline void hfree_pinned(void* p) { std::free(p); }
 inline bool is_device_ptr(const void*) { return false; }
