@@ -226,7 +226,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
   double* const abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : coef;
   ASSUME_GLOBAL(coef);
   ASSUME_GLOBAL(abox);
-  ASSUME_GLOBAL(sbox);
+  if (SRC == 2)   // (the hint is only given for pointers that are dereferenced: never for a null one)
+    ASSUME_GLOBAL(sbox);
   const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
   unsigned long long vmax = 0;
 
@@ -370,7 +371,6 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
   double* const obox = a.out_off >= 0 ? ch.scratch + a.out_off : nullptr;   // OUT 0, levels > 0
   ASSUME_GLOBAL(coef);
   ASSUME_GLOBAL(abox);
-  ASSUME_GLOBAL(obox);
   const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
 
   // epilogue ownership: (x, y) = (X0 + lane, Y0 + warp + 8 c), c = 0 .. 3, of every plane
@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
       const double* const tp = tile + (size_t)p * kFI * kFP + (kFH + ep_warp) * kFP + kFH + ep_lane;
       if (OUT == 0 && a.out_off >= 0) {
         double* const ob = obox + (size_t)z * ly * lx;
+        ASSUME_GLOBAL(ob);
 #pragma unroll
         for (int c = 0; c < 4; c++)
           if ((ep_live >> c) & 1u)
