@@ -2,6 +2,11 @@
 # A/B measurement of library variants in ONE GPU call: variants/<name>.so are copied over the
 # product library one after the other, each timed by the same bench line; the last one stays in
 # place for a parity run.   usage: scripts/gpu_variants.sh A C B
+# Variants are built here, without a GPU:  python -m sperr_b200.build --variant recprefix -DSPERR_REC_PREFIX=1
+# (-> variants/recprefix.so; cp sperr_b200/libsperr_b200.so variants/base.so for the baseline) and
+# checked for bit-exactness under the emulator first:
+#   SPERR_EMUL_DEFS=-DSPERR_REC_PREFIX=1 SPERR_EMUL_TAG=recprefix tests/emul/build.sh
+# Restore the product library afterwards (python -m sperr_b200.build --force) and delete variants/.
 mkdir -p gpurun_out
 for v in "$@"; do
   cp variants/$v.so sperr_b200/libsperr_b200.so

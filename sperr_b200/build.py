@@ -1,6 +1,9 @@
 """Builds sperr_b200/libsperr_b200.so (the product library) in-tree with nvcc for sm_100a.
 
     python -m sperr_b200.build [--force]
+    python -m sperr_b200.build --variant NAME -DFLAG=1 ...   # experiments: variants/NAME.so, built
+                                                             # from objects of its own with the
+                                                             # extra defines (scripts/gpu_variants.sh)
 
 Every .cu under csrc/ is compiled with ``-gencode arch=compute_100a,code=sm_100a -fmad=false``
 (-fmad=false is part of the parity contract: the fp64 lifting / quantiser arithmetic must round
@@ -45,36 +48,43 @@ def _headers_mtime():
     return max(m, os.path.getmtime(os.path.abspath(__file__)))
 
 
-def _compile(nvcc, src, obj):
-    cmd = [nvcc] + NVCC_FLAGS + ["-x", "cu", "-c", src, "-o", obj]
+def _compile(nvcc, src, obj, extra=()):
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-x", "cu", "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout[-4000:], r.stderr[-4000:]))
     return r.stderr
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, variant=None, extra=()):
     nvcc = _nvcc()
-    os.makedirs(OBJ, exist_ok=True)
+    obj_dir, out = OBJ, OUT
+    if variant:
+        obj_dir = os.path.join(HERE, "build", "variant_" + variant)
+        out = os.path.join(os.path.dirname(HERE), "variants", variant + ".so")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     hm = _headers_mtime()
     jobs, objs = [], []
     for s in _sources():
-        o = os.path.join(OBJ, os.path.basename(s) + ".o")
+        o = os.path.join(obj_dir, os.path.basename(s) + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hm):
             jobs.append((s, o))
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
-            for log in ex.map(lambda j: _compile(nvcc, j[0], j[1]), jobs):
+            for log in ex.map(lambda j: _compile(nvcc, j[0], j[1], extra), jobs):
                 if verbose and log:
                     sys.stderr.write(log)
-    if jobs or not os.path.exists(OUT):
-        cmd = [nvcc, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    if jobs or not os.path.exists(out):
+        cmd = [nvcc, "-shared", "-o", out] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stderr[-4000:])
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    name = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose=True, variant=name, extra=defs))

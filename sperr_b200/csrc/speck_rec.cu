@@ -24,6 +24,15 @@ __device__ __forceinline__ int rec_plane(unsigned v) { return v == 0xFFu ? -1 : 
 // sub-bands of a smooth field) cost no barrier at all.
 constexpr int kRecUnits = 8;
 
+// Experiment (off by default, see scripts/build_variants.sh): k_rec_apply is bound by its
+// instruction count (~500 per thread and unit on the full path). With SPERR_REC_PREFIX the
+// per-plane ranks of every warp's first coefficient (unit base + counts of the warps before) are
+// computed once per unit, one warp per plane, instead of by every warp in every plane iteration:
+// one barrier more per unit, a REDUX, a select and a global load less per plane iteration.
+#ifndef SPERR_REC_PREFIX
+#define SPERR_REC_PREFIX 0
+#endif
+
 // counts[(c * maxp + n) * nblk + blk] = coefficients of unit blk significant before plane n
 // (the caller zeroes the array: empty units write nothing)
 __global__ void __launch_bounds__(kRecBlock, 2) k_rec_count(const DecChunk* jobs, unsigned* counts, int maxp,
@@ -205,6 +214,20 @@ __global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs
         s_cnt[n][warp] = unsigned(__popc(b));
     }
     __syncthreads();
+#if SPERR_REC_PREFIX
+    for (int n = warp; n < bmax; n += 32) {   // warp-uniform
+      const unsigned v = s_cnt[n][lane];
+      unsigned inc = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+          inc += t;
+      }
+      const unsigned base = __shfl_sync(0xffffffffu, lane == 0 ? counts[((size_t)c * maxp + n) * nblk + blk] : 0u, 0);
+      s_cnt[n][lane] = base + inc - v;
+    }
+    __syncthreads();
+#endif
     unsigned long long mag = 0;
     if (p >= 0) {
       const unsigned long long thr = 1ull << p;
@@ -218,10 +241,18 @@ __global__ void __launch_bounds__(kRecBlock, 2) k_rec_apply(const DecChunk* jobs
       const unsigned b = __ballot_sync(0xffffffffu, mine);
       if (b == 0)
         continue;
+#if SPERR_REC_PREFIX
+      const unsigned long long first = s_cnt[n][warp];
+#else
       const unsigned before = __reduce_add_sync(0xffffffffu, lane < warp ? s_cnt[n][lane] : 0u);
+#endif
       if (mine) {
+#if SPERR_REC_PREFIX
+        const unsigned long long rank = first + __popc(b & lt);
+#else
         const unsigned long long rank =
             (unsigned long long)counts[((size_t)c * maxp + n) * nblk + blk] + before + __popc(b & lt);
+#endif
         if (rank < nref) {
           const unsigned long long bp = s_base[n] + rank;
           const unsigned bit = (gptr(d.bits)[bp >> 5] >> (bp & 31)) & 1u;
