@@ -1,6 +1,7 @@
 #include "pipeline.h"
 
 #include <cmath>
+#include <condition_variable>
 #include <exception>
 #include <limits>
 #include <thread>
@@ -412,12 +413,49 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     RT_CHECK(cudaStreamWaitEvent(side_, side_ev_, 0));
     int dev = 0;
     RT_CHECK(cudaGetDevice(&dev));
+    // Experiment (SPERR_B200_STAGGER=1, off by default): both chains start with their
+    // bandwidth-bound kernels (pyramid + LIP / refinement counts here, de-quantisation + inverse
+    // transform there: enc.lipref_count takes 14.9 ms beside k_inv3d<2> against 3.3 ms alone) and
+    // end with latency-bound loops that leave the GPU idle. Staggered, the outlier chain starts when
+    // the encoder enters its bit-plane loop, so that its heavy kernels fill that loop's idle GPU.
+    struct Gate {
+      std::mutex m;
+      std::condition_variable cv;
+      bool open = false;
+      void release()
+      {
+        {
+          std::lock_guard<std::mutex> l(m);
+          open = true;
+        }
+        cv.notify_all();
+      }
+      void wait()
+      {
+        std::unique_lock<std::mutex> l(m);
+        cv.wait(l, [this] { return open; });
+      }
+    } gate;
+    const bool stagger = std::getenv("SPERR_B200_STAGGER") != nullptr;
+    if (stagger) {
+      if (!stagger_ev_)
+        RT_CHECK(cudaEventCreateWithFlags(&stagger_ev_, cudaEventDisableTiming));
+      enc.set_before_plane_loop([&](cudaStream_t s) {
+        RT_CHECK(cudaEventRecord(stagger_ev_, s));
+        gate.release();
+      });
+    }
+    else
+      gate.release();
     std::exception_ptr side_err;
     std::thread helper([&] {
       try {
         rt::ReadbackScope readback_side;
         (void)readback_side;
         RT_CHECK(cudaSetDevice(dev));
+        gate.wait();
+        if (stagger)
+          RT_CHECK(cudaStreamWaitEvent(side_, stagger_ev_, 0));
         outlier_chain(side_);
         rt::sync(side_);
       }
@@ -429,9 +467,13 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
       speck_chain();
     }
     catch (...) {
+      enc.set_before_plane_loop(nullptr);
+      gate.release();   // the encoder may have failed before it reached its plane loop
       helper.join();
       throw;
     }
+    enc.set_before_plane_loop(nullptr);
+    gate.release();   // (no-op unless the encoder had nothing to code)
     helper.join();
     if (side_err)
       std::rethrow_exception(side_err);

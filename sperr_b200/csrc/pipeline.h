@@ -50,6 +50,7 @@ class Compressor {
 #ifndef SPERR_EMUL
   cudaStream_t side_ = nullptr;   // PWE: the outlier path runs beside the SPECK3D encoder
   cudaEvent_t side_ev_ = nullptr;
+  cudaEvent_t stagger_ev_ = nullptr;   // SPERR_B200_STAGGER: the encoder has reached its bit-plane loop
 #endif
 };
 

@@ -1,6 +1,8 @@
 // Integer SPECK coders: batch-level context and host drivers.
 #pragma once
 
+#include <functional>
+
 #include "kernels.h"
 
 namespace sperr_b200 {
@@ -50,6 +52,10 @@ struct EncResult {
 struct EncWork {
   rt::DBuf keys[2], nodes[2], fnode[2], fpos[2], rseg, rpos, scan_tmp, sort_tmp, small, stage,
       counts, sizes;
+  // called once per run, right after the last bandwidth-bound launch before the bit-plane loop
+  // (pyramid and LIP / refinement counts are queued; what follows is latency-bound): the point at
+  // which work of another stream no longer competes with this encoder for the memory system
+  std::function<void(cudaStream_t)> before_plane_loop;
 };
 
 class Speck3DEncoder {
@@ -59,6 +65,7 @@ class Speck3DEncoder {
   void encode(ChunkDev* d_chunks, const std::vector<ChunkDev>& h_chunks,
               const ShapeDev* d_shapes, const std::vector<ShapeTables>& shapes,
               std::vector<EncResult>& results, cudaStream_t st);
+  void set_before_plane_loop(std::function<void(cudaStream_t)> f) { work_.before_plane_loop = std::move(f); }
 
  private:
   rt::DBuf ids_;

@@ -698,6 +698,9 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
            maxp, nblk);
   }
 
+  if (w.before_plane_loop)
+    w.before_plane_loop(st);
+
   // bit-plane loop (LIS part)
   void* d_scan_tmp = w.scan_tmp.p;
   const unsigned cgrid = unsigned((nchunks + 127) / 128);
