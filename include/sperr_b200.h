@@ -120,6 +120,12 @@ size_t sperr_b200_num_chunks(const size_t vol[3], const size_t chunk[3]);
 int sperr_b200_chunk_box(const size_t vol[3], const size_t chunk[3], size_t begin, size_t end,
                          size_t origin[3], size_t extent[3]);
 
+/* Partition of the chunks over `world` ranks: rank r owns [begins[r], begins[r + 1]) (begins has
+ * world + 1 entries). Every range is exactly a box of chunks, so a rank's bounding box holds no
+ * chunk of another rank (even split of chunks, else of whole chunk rows, else of whole z-slabs).
+ * Returns 0, or -1 when there are fewer chunks than ranks or no such split exists. */
+int sperr_b200_shard_ranges(const size_t vol[3], const size_t chunk[3], size_t world, size_t* begins);
+
 /* Compresses the chunks of the range. *d_streams receives a library-owned DEVICE buffer (valid
  * until the next call into the library) holding their streams back to back, lens[i] the length of
  * chunk chunk_begin + i. Returns 0 ok; 2 bad parameter; -1 other error. */

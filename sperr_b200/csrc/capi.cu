@@ -240,10 +240,12 @@ bool parse_container(const uint8_t* p, size_t len, ContainerInfo& ci)
   for (int i = 0; i < 3; i++)
     if (ci.vol[i] == 0 || ci.cd[i] == 0)
       return false;
-  ci.chunks = chunk_volume(ci.vol, ci.cd);
-  const size_t nchunks = ci.chunks.size();
-  if (len < pos + 4 * nchunks)
+  // untrusted dimensions: the chunk count must fit the bytes that are there before any vector of
+  // that size is built
+  size_t nseg[3], nchunks = 0;
+  if (!chunk_grid(ci.vol, ci.cd, nseg, &nchunks) || nchunks > (len - pos) / 4)
     return false;
+  ci.chunks = chunk_volume(ci.vol, ci.cd);
   ci.cs.resize(nchunks);
   size_t off = pos + 4 * nchunks;
   for (size_t i = 0; i < nchunks; i++) {
@@ -888,11 +890,18 @@ int sperr_trunc_3d(const void* src, size_t src_len, unsigned pct, void** dst, si
   for (int i = 0; i < 3; i++)
     if (vol[i] == 0 || cd[i] == 0)
       return -1;
-  const size_t nchunks = chunk_volume(vol, cd).size();
-  const size_t hlen = pos + 4 * nchunks;
-  if (src_len < hlen)
+  size_t nseg[3], nchunks = 0;
+  if (!chunk_grid(vol, cd, nseg, &nchunks) || nchunks > (src_len - pos) / 4)
     return -1;
-  std::vector<size_t> off(nchunks), len(nchunks);
+  const size_t hlen = pos + 4 * nchunks;
+  std::vector<size_t> off, len;
+  try {
+    off.resize(nchunks);
+    len.resize(nchunks);
+  }
+  catch (const std::exception&) {
+    return -1;
+  }
   size_t at = hlen, far = 0, total = hlen;
   const size_t min_bytes = 64;   // m_progressive_min_chunk_bytes
   for (size_t i = 0; i < nchunks; i++) {

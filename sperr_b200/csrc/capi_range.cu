@@ -74,7 +74,8 @@ size_t sperr_b200_num_chunks(const size_t vol[3], const size_t chunk[3])
       return 0;
     cd[i] = std::min(std::max<size_t>(1, chunk[i]), vol[i]);
   }
-  return chunk_volume(vol, cd).size();
+  size_t nseg[3], n = 0;
+  return chunk_grid(vol, cd, nseg, &n) ? n : 0;
 }
 
 int sperr_b200_chunk_box(const size_t vol[3], const size_t chunk[3], size_t begin, size_t end,
@@ -86,7 +87,13 @@ int sperr_b200_chunk_box(const size_t vol[3], const size_t chunk[3], size_t begi
       return -1;
     cd[i] = std::min(std::max<size_t>(1, chunk[i]), vol[i]);
   }
-  const auto all = chunk_volume(vol, cd);
+  std::vector<Chunk> all;
+  try {
+    all = chunk_volume(vol, cd);
+  }
+  catch (const std::exception&) {
+    return -1;
+  }
   if (begin >= end || end > all.size())
     return -1;
   size_t lo[3] = {~size_t(0), ~size_t(0), ~size_t(0)}, hi[3] = {0, 0, 0};
@@ -103,6 +110,11 @@ int sperr_b200_chunk_box(const size_t vol[3], const size_t chunk[3], size_t begi
     extent[k] = hi[k] - lo[k];
   }
   return 0;
+}
+
+int sperr_b200_shard_ranges(const size_t vol[3], const size_t chunk[3], size_t world, size_t* begins)
+{
+  return shard_ranges(vol, chunk, world, begins) ? 0 : -1;
 }
 
 int sperr_b200_comp_3d_range_dev(const void* d_box, int is_float, const size_t vol[3],
@@ -192,7 +204,9 @@ int sperr_b200_parse_container(const void* src, size_t len, size_t vol[3], size_
   for (int i = 0; i < 3; i++)
     if (vol[i] == 0 || chunk[i] == 0)
       return -1;
-  const size_t n = chunk_volume(vol, chunk).size();
+  size_t nseg[3], n = 0;
+  if (!chunk_grid(vol, chunk, nseg, &n) || n > (~size_t(0) - pos) / 4)
+    return -1;
   *nchunks = n;
   *header_len = pos + 4 * n;
   if (len < pos + 4 * n)

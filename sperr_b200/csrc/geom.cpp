@@ -46,16 +46,84 @@ std::array<size_t, 2> calc_approx_detail_len(size_t len, size_t lev)
   return {low, high};
 }
 
-std::vector<Chunk> chunk_volume(const size_t vol[3], const size_t chunk[3])
+bool chunk_grid(const size_t vol[3], const size_t chunk[3], size_t nseg[3], size_t* count)
 {
-  size_t nseg[3];
+  size_t total = 1;
   for (int a = 0; a < 3; a++) {
+    if (vol[a] == 0 || chunk[a] == 0)
+      return false;
     nseg[a] = vol[a] / chunk[a];
     if (vol[a] % chunk[a] > chunk[a] / 2)
       nseg[a]++;
     if (nseg[a] == 0)
       nseg[a] = 1;
+    if (total > (~size_t(0)) / nseg[a])
+      return false;   // the product does not fit a size_t
+    total *= nseg[a];
   }
+  *count = total;
+  return true;
+}
+
+bool shard_ranges(const size_t vol[3], const size_t chunk[3], size_t world, size_t* begins)
+{
+  size_t cd[3], g[3], total = 0;
+  for (int a = 0; a < 3; a++)
+    cd[a] = std::min(std::max<size_t>(1, chunk[a]), vol[a]);
+  if (world == 0 || !chunk_grid(vol, cd, g, &total) || total < world)
+    return false;
+  // a contiguous index range [b, e) of the x-fastest chunk grid is a box iff its bounding box
+  // (in chunk units) holds exactly e - b chunks
+  auto is_box = [&](size_t b, size_t e) {
+    size_t lo[3] = {~size_t(0), ~size_t(0), ~size_t(0)}, hi[3] = {0, 0, 0};
+    // the extremes of a contiguous range are reached at its ends and at row / slab crossings
+    const size_t row = g[0], slab = g[0] * g[1];
+    auto visit = [&](size_t i) {
+      const size_t c[3] = {i % row, (i / row) % g[1], i / slab};
+      for (int k = 0; k < 3; k++) {
+        lo[k] = std::min(lo[k], c[k]);
+        hi[k] = std::max(hi[k], c[k]);
+      }
+    };
+    visit(b);
+    visit(e - 1);
+    if (b / row != (e - 1) / row) {   // crosses a row boundary: all x are touched
+      lo[0] = 0;
+      hi[0] = row - 1;
+    }
+    if (b / slab != (e - 1) / slab) {   // crosses a slab boundary: all y are touched
+      lo[1] = 0;
+      hi[1] = g[1] - 1;
+    }
+    return (hi[0] - lo[0] + 1) * (hi[1] - lo[1] + 1) * (hi[2] - lo[2] + 1) == e - b;
+  };
+  const size_t units[3] = {1, g[0], g[0] * g[1]};   // chunks, whole rows, whole slabs
+  for (int u = 0; u < 3; u++) {
+    if (u > 0 && units[u] == units[u - 1])
+      continue;
+    const size_t n = total / units[u];
+    if (n < world)
+      break;
+    const size_t base = n / world, rem = n % world;
+    bool ok = true;
+    size_t pos = 0;
+    for (size_t r = 0; r < world && ok; r++) {
+      begins[r] = pos * units[u];
+      pos += base + (r < rem ? 1 : 0);
+      ok = is_box(begins[r], pos * units[u]);
+    }
+    begins[world] = total;
+    if (ok)
+      return true;
+  }
+  return false;
+}
+
+std::vector<Chunk> chunk_volume(const size_t vol[3], const size_t chunk[3])
+{
+  size_t nseg[3], total = 0;
+  if (!chunk_grid(vol, chunk, nseg, &total) || total > (size_t(1) << 40))
+    throw std::length_error("chunk_volume: unreasonable chunk grid");
   auto seg = [&](int a, size_t i, uint32_t& beg, uint32_t& len) {
     const size_t b = i * chunk[a];
     const size_t e = (i + 1 == nseg[a]) ? vol[a] : (i + 1) * chunk[a];

@@ -25,6 +25,14 @@ struct Chunk {
   size_t nelem() const { return size_t(lx) * ly * lz; }
 };
 std::vector<Chunk> chunk_volume(const size_t vol[3], const size_t chunk[3]);
+// Segments per axis and their product (false when an extent is zero or the product overflows):
+// what callers that hold UNTRUSTED header dimensions check before chunk_volume builds its vector.
+bool chunk_grid(const size_t vol[3], const size_t chunk[3], size_t nseg[3], size_t* count);
+// Partition of chunk_volume's order over `world` ranks such that every rank's contiguous range
+// [begins[r], begins[r + 1]) is exactly a box of chunks (so the bounding box a rank holds contains
+// no chunk of another rank). Tries an even split of chunks, then of whole rows, then of whole
+// z-slabs; false when none of them gives boxes or there are fewer chunks than ranks.
+bool shard_ranges(const size_t vol[3], const size_t chunk[3], size_t world, size_t* begins);
 
 // Number of strides the conditioner's mean uses (Conditioner::m_adjust_strides,
 // /root/reference/src/Conditioner.cpp:137-163).

@@ -31,6 +31,8 @@ def _bind(cdll):
     cdll.sperr_b200_num_chunks.argtypes = [sz3, sz3]
     cdll.sperr_b200_chunk_box.restype = C.c_int
     cdll.sperr_b200_chunk_box.argtypes = [sz3, sz3, sz, sz, sz3, sz3]
+    cdll.sperr_b200_shard_ranges.restype = C.c_int
+    cdll.sperr_b200_shard_ranges.argtypes = [sz3, sz3, sz, C.POINTER(sz)]
     cdll.sperr_b200_comp_3d_range_dev.restype = C.c_int
     cdll.sperr_b200_comp_3d_range_dev.argtypes = [vp, C.c_int, sz3, sz3, sz3, sz3, sz, sz, C.c_int,
                                                   C.c_double, C.POINTER(vp), C.POINTER(sz), vp]
@@ -63,12 +65,19 @@ class Shard:
         self.nchunks = int(self.cdll.sperr_b200_num_chunks(self.vol, self.chunk))
         if self.nchunks < world:
             raise ValueError("fewer chunks (%d) than ranks (%d)" % (self.nchunks, world))
-        self.begin, self.end = chunk_range(self.nchunks, rank, world)
+        # every rank's range must be exactly a box of chunks (its bounding box is what it holds and
+        # what it decodes into): the library splits chunks, whole rows or whole z-slabs evenly
+        begins = (sz * (world + 1))()
+        if self.cdll.sperr_b200_shard_ranges(self.vol, self.chunk, world, begins) != 0:
+            raise ValueError("the %d chunks of volume %s do not split into %d boxes of whole chunks"
+                             % (self.nchunks, tuple(vol), world))
+        self.ranges = [(int(begins[r]), int(begins[r + 1])) for r in range(world)]
+        self.begin, self.end = self.ranges[rank]
         self.origin, self.extent = sz3(), sz3()
         rc = self.cdll.sperr_b200_chunk_box(self.vol, self.chunk, self.begin, self.end, self.origin,
                                             self.extent)
-        assert rc == 0
-        self.ranges = [chunk_range(self.nchunks, r, world) for r in range(world)]
+        if rc != 0:
+            raise ValueError("bad chunk range")
 
     @property
     def box_origin(self):
@@ -118,98 +127,119 @@ class DeviceContainer:
         return self.data.cpu().numpy()
 
 
+class _DevPtr:
+    """A library-owned device buffer as something torch.as_tensor can wrap without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _wrap(ptr, n, dev):
+    """uint8 tensor VIEW of n bytes at ptr (device memory for a CUDA device, host memory for the
+    emulated library)."""
+    if n == 0:
+        return torch.empty(0, dtype=torch.uint8, device=dev)
+    if dev.type == "cuda":
+        return torch.as_tensor(_DevPtr(ptr, n), device=dev)
+    return torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,)))
+
+
+def _pre_call(dev):
+    """The library computes on the legacy default stream: work the caller queued on another torch
+    stream (a producer of `box`, a consumer of an earlier result) must be done before it starts."""
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
+
+
+def _all_ok(rc, dev, group, what):
+    """Every rank learns whether any rank failed BEFORE the next collective (a rank that raised on
+    its own would leave the others waiting in it)."""
+    ok = torch.tensor([abs(int(rc))], device=dev, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=group)
+    if int(ok.item()) != 0:
+        raise RuntimeError("%s failed on some rank (rc=%d here)" % (what, rc))
+
+
 def compress_3d_sharded(cdll, box, vol, chunk, mode, quality, group=None, device_container=False):
     """box: this rank's part of the volume as a contiguous float32 / float64 torch tensor (z, y, x)
     that lives where the library computes (CUDA device for libsperr_b200.so). Returns the container
     on rank 0 and None elsewhere: a uint8 numpy array backed by a reused pinned staging buffer, or --
     device_container=True -- a DeviceContainer whose bytes never leave rank 0's device."""
     rank, world = _world(group)
-    sh = Shard(cdll, vol, chunk, rank, world)
-    assert box.is_contiguous() and tuple(box.shape) == sh.box_extent[::-1], (box.shape, sh.box_extent)
+    dev = box.device
+    sh = Shard(cdll, vol, chunk, rank, world)   # raises on every rank alike (same arguments)
     is_float = box.dtype == torch.float32
     n_mine = sh.end - sh.begin
     lens = np.zeros(n_mine, dtype=np.uint32)
     d_streams, n = vp(None), sz(0)
-    rc = sh.cdll.sperr_b200_comp_3d_range_dev(vp(box.data_ptr()), int(is_float), sh.vol, sh.chunk,
-                                              sh.origin, sh.extent, sh.begin, sh.end, mode, quality,
-                                              C.byref(d_streams), C.byref(n), lens.ctypes.data_as(vp))
-    dev = box.device
-    if world == 1:
-        # a world of one rank needs no exchange: header + this rank's streams are the container
-        if rc != 0:
-            raise RuntimeError("sperr_b200_comp_3d_range_dev failed (rc=%d)" % rc)
-        hlen = int(sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), None, sh.nchunks, None, 0))
-        total = hlen + n.value
-        hdr = np.zeros(hlen, dtype=np.uint8)
-        got = sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), lens.ctypes.data_as(vp),
-                                                  sh.nchunks, hdr.ctypes.data_as(vp), hdr.size)
-        assert got == hlen
-        if device_container:
-            data = torch.empty(total, dtype=torch.uint8, device=dev)
-            data[:hlen].copy_(torch.from_numpy(hdr))
-            if n.value:
-                assert sh.cdll.sperr_b200_memcpy_dev(vp(data.data_ptr() + hlen), d_streams, n.value, 0) == 0
-            return DeviceContainer(data, hdr)
-        stage = _pinned_u8(total, "container")
-        out = stage.numpy()[:total]
-        out[:hlen] = hdr
-        if n.value:
-            kind = 2 if dev.type == "cuda" else 0   # device -> host (the emulated library "device" is the host)
-            assert sh.cdll.sperr_b200_memcpy_dev(vp(stage.data_ptr() + hlen), d_streams, n.value, kind) == 0
-        return out
-    ok = torch.tensor([abs(rc)], device=dev, dtype=torch.int32)
-    dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=group)
-    if int(ok.item()) != 0:
-        raise RuntimeError("sperr_b200_comp_3d_range_dev failed on some rank (rc=%d here)" % rc)
+    if box.is_contiguous() and tuple(box.shape) == sh.box_extent[::-1] and box.dtype in (torch.float32, torch.float64):
+        _pre_call(dev)
+        rc = sh.cdll.sperr_b200_comp_3d_range_dev(vp(box.data_ptr()), int(is_float), sh.vol, sh.chunk,
+                                                  sh.origin, sh.extent, sh.begin, sh.end, mode, quality,
+                                                  C.byref(d_streams), C.byref(n), lens.ctypes.data_as(vp))
+    else:
+        rc = -100   # local precondition: reported through the same all-reduce as a library failure
+    if world > 1:
+        _all_ok(rc, dev, group, "sperr_b200_comp_3d_range_dev")
+    elif rc == -100:
+        raise ValueError("box must be a contiguous %s tensor" % (sh.box_extent[::-1],))
+    elif rc != 0:
+        raise RuntimeError("sperr_b200_comp_3d_range_dev failed (rc=%d)" % rc)
+    mine = _wrap(d_streams.value, n.value, dev)   # view of the library's buffer, valid until the next call
 
-    # 1. all-gather the per-chunk byte counts (ranges may differ by one chunk: pad)
-    per = max(e - b for b, e in sh.ranges)
-    mylens = torch.zeros(per, dtype=torch.int64, device=dev)
-    mylens[:n_mine] = torch.from_numpy(lens.astype(np.int64)).to(dev)
-    all_lens = [torch.zeros(per, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(all_lens, mylens, group=group)
-    lens_by_rank = [t.cpu().numpy()[:e - b] for t, (b, e) in zip(all_lens, sh.ranges)]
+    # 1. all-gather the per-chunk byte counts (the header needs all of them; ranges may differ in size: pad)
+    if world > 1:
+        per = max(e - b for b, e in sh.ranges)
+        mylens = torch.zeros(per, dtype=torch.int64, device=dev)
+        mylens[:n_mine] = torch.from_numpy(lens.astype(np.int64)).to(dev)
+        all_lens = torch.empty(world * per, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(all_lens, mylens, group=group)
+        al = all_lens.cpu().numpy().reshape(world, per)
+        lens_by_rank = [al[r, :e - b] for r, (b, e) in enumerate(sh.ranges)]
+    else:
+        lens_by_rank = [lens.astype(np.int64)]
     bytes_by_rank = [int(l.sum()) for l in lens_by_rank]
-
-    # 2. gather the chunk streams on rank 0, device to device (variable length: pad to the longest)
-    longest = max(max(bytes_by_rank), 1)
-    payload = torch.empty(longest, dtype=torch.uint8, device=dev)
-    if n.value:
-        rc = sh.cdll.sperr_b200_memcpy_dev(vp(payload.data_ptr()), d_streams, n.value, 0)
-        assert rc == 0
-    parts = [torch.empty(longest, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
-    dist.gather(payload, parts, dst=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    if rank != 0:
-        return None
-
-    # 3. reference-layout container: header with every chunk length, then the streams in chunk order
     all32 = np.concatenate(lens_by_rank).astype(np.uint32)
     hlen = int(sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), None, sh.nchunks, None, 0))
     total = hlen + sum(bytes_by_rank)
-    if device_container:
+
+    # 2. the chunk streams travel device to device, exact sizes, straight to their place in the
+    #    reference-layout container on rank 0 (one grouped send / receive)
+    data = None
+    if rank == 0:
+        data = torch.empty(total, dtype=torch.uint8, device=dev)
         hdr = np.zeros(hlen, dtype=np.uint8)
         got = sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), all32.ctypes.data_as(vp),
                                                   sh.nchunks, hdr.ctypes.data_as(vp), hdr.size)
         assert got == hlen
-        data = torch.empty(total, dtype=torch.uint8, device=dev)
         data[:hlen].copy_(torch.from_numpy(hdr))
-        pos = hlen
-        for r in range(world):
-            data[pos:pos + bytes_by_rank[r]].copy_(parts[r][:bytes_by_rank[r]])
-            pos += bytes_by_rank[r]
+        data[hlen:hlen + bytes_by_rank[0]].copy_(mine)
+    if world > 1:
+        root = dist.get_global_rank(group, 0) if group is not None else 0
+        ops = []
+        if rank == 0:
+            pos = hlen + bytes_by_rank[0]
+            for r in range(1, world):
+                if bytes_by_rank[r]:
+                    peer = dist.get_global_rank(group, r) if group is not None else r
+                    ops.append(dist.P2POp(dist.irecv, data[pos:pos + bytes_by_rank[r]], peer, group))
+                pos += bytes_by_rank[r]
+        elif n.value:
+            ops.append(dist.P2POp(dist.isend, mine, root, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()   # `mine` is the library's buffer: done with it
+    if rank != 0:
+        return None
+    if device_container:
         return DeviceContainer(data, hdr)
     stage = _pinned_u8(total, "container")
-    out = stage.numpy()[:total]
-    got = sh.cdll.sperr_b200_container_header(sh.vol, sh.chunk, int(is_float), all32.ctypes.data_as(vp),
-                                              sh.nchunks, out.ctypes.data_as(vp), out.size)
-    assert got == hlen
-    pos = hlen
-    for r in range(world):
-        stage[pos:pos + bytes_by_rank[r]].copy_(parts[r][:bytes_by_rank[r]])
-        pos += bytes_by_rank[r]
+    stage[:total].copy_(data)
     if dev.type == "cuda":
         torch.cuda.current_stream(dev).synchronize()
-    return out
+    return stage.numpy()[:total]
 
 
 def parse_container(cdll, stream):
@@ -265,6 +295,7 @@ def _decompress_world1(cdll, stream, dev, output_float, on_device):
     h = None if on_device else np.ascontiguousarray(stream)[hlen:hlen + nb]
     e = sh.box_extent
     box = torch.empty((e[2], e[1], e[0]), dtype=torch.float32 if output_float else torch.float64, device=dev)
+    _pre_call(dev)
     rc = cdll.sperr_b200_decomp_3d_range_dev(h.ctypes.data_as(vp) if h is not None else vp(None),
                                              vp(mine.data_ptr()), nb,
                                              mylens.ctypes.data_as(vp), sh.vol, sh.chunk, sh.origin,
@@ -287,35 +318,49 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
     on_device = isinstance(stream, DeviceContainer)
     if world == 1:
         return _decompress_world1(cdll, stream, dev, output_float, on_device)
-    meta = [None]
+    # container geometry as two small tensor broadcasts (no pickling): 8 fixed words, then the lengths
+    head = torch.zeros(9, dtype=torch.int64, device=dev)
+    bad = 0
     if rank == 0:
-        if on_device:
-            vol, chunk, isf, hlen, lens = parse_header_only(cdll, stream.header, stream.size)
-        else:
-            vol, chunk, isf, hlen, lens = parse_container(cdll, stream)
-        meta = [(vol, chunk, lens)]
-    dist.broadcast_object_list(meta, src=src0, group=group)
-    vol, chunk, lens = meta[0]
+        try:
+            if on_device:
+                vol, chunk, isf, hlen, lens = parse_header_only(cdll, stream.header, stream.size)
+            else:
+                vol, chunk, isf, hlen, lens = parse_container(cdll, stream)
+            head = torch.tensor(list(vol) + list(chunk) + [hlen, lens.size, int(on_device)], dtype=torch.int64,
+                                device=dev)
+        except ValueError:
+            bad = 1
+    _all_ok(bad, dev, group, "parsing the container")
+    dist.broadcast(head, src=src0, group=group)
+    hv = [int(x) for x in head.cpu().numpy()]
+    vol, chunk, hlen, nch, streams_on_device = tuple(hv[0:3]), tuple(hv[3:6]), hv[6], hv[7], bool(hv[8])
+    lens_t = torch.from_numpy(lens.astype(np.int64)).to(dev) if rank == 0 else torch.empty(nch, dtype=torch.int64, device=dev)
+    dist.broadcast(lens_t, src=src0, group=group)
+    lens = lens_t.cpu().numpy().astype(np.uint32)
     sh = Shard(cdll, vol, chunk, rank, world)
     bytes_by_rank = [int(lens[b:e].astype(np.int64).sum()) for b, e in sh.ranges]
-    longest = max(max(bytes_by_rank), 1)
-    mine = torch.empty(longest, dtype=torch.uint8, device=dev)
-    parts = None
-    if rank == 0:
-        # one upload of the container, then equal-sized device slices for the scatter
-        d_all = stream.data if on_device else torch.from_numpy(np.ascontiguousarray(stream)).to(dev)
-        parts, pos = [], hlen
-        for r in range(world):
-            t = torch.empty(longest, dtype=torch.uint8, device=dev)
-            t[:bytes_by_rank[r]].copy_(d_all[pos:pos + bytes_by_rank[r]])
-            parts.append(t)
-            pos += bytes_by_rank[r]
-    dist.scatter(mine, parts, src=src0, group=group)
     nb = bytes_by_rank[rank]
+    # every rank receives exactly its byte range of the container (one grouped send / receive)
+    ops = []
+    if rank == 0:
+        d_all = stream.data if on_device else torch.from_numpy(np.ascontiguousarray(stream)).to(dev)
+        mine = d_all[hlen:hlen + nb]
+        pos = hlen + nb
+        for r in range(1, world):
+            if bytes_by_rank[r]:
+                peer = dist.get_global_rank(group, r) if group is not None else r
+                ops.append(dist.P2POp(dist.isend, d_all[pos:pos + bytes_by_rank[r]], peer, group))
+            pos += bytes_by_rank[r]
+    else:
+        mine = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)[:nb]
+        if nb:
+            ops.append(dist.P2POp(dist.irecv, mine, src0, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
     mylens = np.ascontiguousarray(lens[sh.begin:sh.end], dtype=np.uint32)
-    meta_flags = [bool(on_device)]
-    dist.broadcast_object_list(meta_flags, src=src0, group=group)
-    if meta_flags[0]:
+    if streams_on_device:
         # the streams stay on the device: the library fetches the chunk headers (conditioner 17 B,
         # SPECK header 9 B, outlier header 9 B) it parses on the host itself
         h = None
@@ -323,9 +368,8 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
         # bring this rank's streams over once (pinned staging)
         stage = _pinned_u8(nb, "streams")
         stage[:nb].copy_(mine[:nb])
-        if dev.type == "cuda":
-            torch.cuda.current_stream(dev).synchronize()
         h = stage.numpy()[:nb]
+    _pre_call(dev)
     e = sh.box_extent
     box = torch.empty((e[2], e[1], e[0]), dtype=torch.float32 if output_float else torch.float64,
                       device=dev)
@@ -334,8 +378,5 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
                                              mylens.ctypes.data_as(vp), sh.vol, sh.chunk, sh.origin,
                                              sh.extent, sh.begin, sh.end, int(output_float),
                                              vp(box.data_ptr()))
-    ok = torch.tensor([abs(rc)], device=dev, dtype=torch.int32)
-    dist.all_reduce(ok, op=dist.ReduceOp.MAX, group=group)
-    if int(ok.item()) != 0:
-        raise RuntimeError("sperr_b200_decomp_3d_range_dev failed (rc=%d here)" % rc)
+    _all_ok(rc, dev, group, "sperr_b200_decomp_3d_range_dev")
     return box, sh

@@ -72,7 +72,7 @@ def test_bench_two_ranks_dry_run():
     gpulib.build_emul()
     code = DRIVER % {"root": ROOT, "tests": os.path.join(ROOT, "tests"), "emul": gpulib.EMUL_SO}
     code = code.replace('"--size", "32"', '"--gpus", "2", "--size", "32"')
-    code = code.replace("bench.main()", "bench.CHUNK = 16   # 32 x 32 x 64 values: 16 chunks, 8 per rank\nbench.main()")
+    code = code.replace("bench.main()", "bench.CHUNK = 16   # 32^3 values: 8 chunks, 4 per rank\nbench.main()")
     procs = []
     for rank in range(2):
         env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29627", RANK=str(rank), WORLD_SIZE="2",
@@ -85,4 +85,7 @@ def test_bench_two_ranks_dry_run():
     lines = [ln for ln in outs[0][0].splitlines() if ln.startswith("{")]
     assert lines and not [ln for ln in outs[1][0].splitlines() if ln.startswith("{")]   # rank 0 alone prints
     d = json.loads(lines[-1])
-    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and len(d["step_ms_each"]) == 2
+    assert d["n_gpus"] == 2 and d["scaling"] == "strong" and len(d["step_ms_each"]) == 2
+    assert "32x32x32" in d["config"]["workload"]           # the SAME volume at every N
+    assert d["parity"]["n_gpus"] == 2 and len(d["parity"]["container_sha256_16"]) == 16
+    assert d["extra"]["weak"]["scaling"] == "weak" and "32x32x64" in d["extra"]["weak"]["config"]["workload"]

@@ -66,6 +66,36 @@ def _worker(rank, world, port, case, q):
         dist.destroy_process_group()
 
 
+def test_sharded_world3_on_2x2x2_grid_gloo():
+    """8 chunks over 3 ranks: an even split of the chunk order (3, 3, 2) is not a set of boxes, so
+    the partition falls back to whole rows (2, 1, 1 rows): every rank's box holds only its own
+    chunks and the assembled container / decoded boxes are still the oracle's."""
+    gpulib.load("emul")
+    refs.oracle()
+    from sperr_b200 import sharded
+    cdll = C.CDLL(gpulib.EMUL_SO)
+    seen = []
+    for r in range(3):
+        sh = sharded.Shard(cdll, (32, 32, 32), (16, 16, 16), r, 3)
+        e = sh.box_extent
+        assert e[0] * e[1] * e[2] == (sh.end - sh.begin) * 16 ** 3, "box holds foreign chunks"
+        seen.extend(range(sh.begin, sh.end))
+    assert seen == list(range(8))
+    with pytest.raises(ValueError):
+        sharded.Shard(cdll, (16, 48, 32), (16, 16, 16), 0, 4)   # 1 x 3 x 2 grid, 4 ranks: no box split
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = random.randint(20000, 40000)
+    case = ((32, 32, 32), (16, 16, 16), 3, 1e-3)
+    procs = [ctx.Process(target=_worker, args=(r, 3, port, case, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(map(str, c[0])) + "-m%d" % c[2])
 def test_sharded_roundtrip_gloo_world2(case):
     gpulib.load("emul")   # builds tests/emul/libsperr_emul.so when needed
