@@ -12,7 +12,9 @@
 #include <array>
 #include <cstdint>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
+#include <string>
 #include <utility>
 #include <vector>
 
@@ -163,6 +165,157 @@ class SPERR3D_OMP_D {
   size_t m_len = 0;
   vecd_type m_vol;
   std::vector<vecd_type> m_hierarchy;
+};
+
+// ---------------------------------------------------------------------------------------------
+// sperr::SPERR3D_Header / sperr::SPERR3D_Stream_Tools
+//   /root/reference/include/SPERR3D_Stream_Tools.h:11-46, src/SPERR3D_Stream_Tools.cpp:11-226
+// Host-only container tools: header parsing and progressive access (keep pct % of every chunk,
+// at least 64 bytes, header flagged is_portion). Same method names and results; the geometry and
+// the truncation itself go through the C ABI (sperr_b200_parse_container, sperr_trunc_3d).
+// ---------------------------------------------------------------------------------------------
+struct SPERR3D_Header {
+  uint8_t major_version = 0;
+  bool is_portion = false;
+  bool is_3D = false;
+  bool is_float = false;
+  bool multi_chunk = false;
+  dims_type vol_dims = {0, 0, 0};
+  dims_type chunk_dims = {0, 0, 0};
+  size_t header_len = 0;
+  size_t stream_len = 0;
+  std::vector<size_t> chunk_offsets;   // {offset, length} pairs, one per chunk
+};
+
+class SPERR3D_Stream_Tools {
+ public:
+  // Total header length from the first 20 bytes of a container (0: not a valid geometry).
+  size_t get_header_len(std::array<uint8_t, 20> magic) const
+  {
+    dims_type v, c;
+    const bool multi = m_geometry(magic.data(), v, c);
+    size_t vol[3] = {v[0], v[1], v[2]}, chunk[3] = {c[0], c[1], c[2]};
+    const size_t n = sperr_b200_num_chunks(vol, chunk);
+    return n == 0 ? 0 : (multi ? 20 : 14) + 4 * n;
+  }
+
+  // `p` must hold at least get_header_len() bytes.
+  SPERR3D_Header get_stream_header(const void* p) const
+  {
+    SPERR3D_Header h;
+    const uint8_t* u = static_cast<const uint8_t*>(p);
+    h.major_version = u[0];
+    h.is_portion = (u[1] & 0x80) != 0;
+    h.is_3D = (u[1] & 0x40) != 0;
+    h.is_float = (u[1] & 0x20) != 0;
+    h.multi_chunk = m_geometry(u, h.vol_dims, h.chunk_dims);
+    size_t vol[3] = {h.vol_dims[0], h.vol_dims[1], h.vol_dims[2]};
+    size_t chunk[3] = {h.chunk_dims[0], h.chunk_dims[1], h.chunk_dims[2]};
+    const size_t n = sperr_b200_num_chunks(vol, chunk);
+    const size_t pos = h.multi_chunk ? 20 : 14;
+    h.header_len = pos + 4 * n;
+    h.stream_len = h.header_len;
+    h.chunk_offsets.resize(2 * n);
+    for (size_t i = 0; i < n; i++) {
+      uint32_t l;
+      std::memcpy(&l, u + pos + 4 * i, 4);
+      h.chunk_offsets[2 * i] = h.stream_len;
+      h.chunk_offsets[2 * i + 1] = l;
+      h.stream_len += l;
+    }
+    return h;
+  }
+
+  // Reads only the header and the leading pct % of every chunk of a container file. Empty on any
+  // I/O error (src/SPERR3D_Stream_Tools.cpp:107-129).
+  vec8_type progressive_read(const std::string& filename, unsigned pct) const
+  {
+    std::FILE* f = std::fopen(filename.c_str(), "rb");
+    if (!f)
+      return {};
+    vec8_type out;
+    std::array<uint8_t, 20> magic{};
+    size_t hlen = 0;
+    if (std::fread(magic.data(), 1, 20, f) == 20 && (hlen = get_header_len(magic)) >= 14) {
+      vec8_type header(hlen);
+      std::rewind(f);
+      if (std::fread(header.data(), 1, hlen, f) == hlen) {
+        const SPERR3D_Header h = get_stream_header(header.data());
+        const auto keep = m_kept_lengths(h, pct);
+        out = m_new_header(header, h, keep, pct);
+        bool ok = true;
+        for (size_t i = 0; i < keep.size() && ok; i++) {
+          const size_t at = out.size();
+          out.resize(at + keep[i]);
+          ok = std::fseek(f, long(h.chunk_offsets[2 * i]), SEEK_SET) == 0 &&
+               std::fread(out.data() + at, 1, keep[i], f) == keep[i];
+        }
+        if (!ok)
+          out.clear();
+      }
+    }
+    std::fclose(f);
+    return out;
+  }
+
+  // The same on a container in memory; stream_len only needs to cover what is kept. Empty on
+  // error (src/SPERR3D_Stream_Tools.cpp:131-226).
+  vec8_type progressive_truncate(const void* stream, size_t stream_len, unsigned pct) const
+  {
+    void* out = nullptr;
+    size_t n = 0;
+    if (stream == nullptr || sperr_trunc_3d(stream, stream_len, pct, &out, &n) != 0)
+      return {};
+    vec8_type v(static_cast<uint8_t*>(out), static_cast<uint8_t*>(out) + n);
+    std::free(out);
+    return v;
+  }
+
+ private:
+  static constexpr size_t m_progressive_min_chunk_bytes = 64;
+
+  static bool m_geometry(const uint8_t* u, dims_type& vol, dims_type& chunk)
+  {
+    const bool multi = (u[1] & 0x10) != 0;
+    uint32_t v3[3];
+    std::memcpy(v3, u + 2, 12);
+    vol = {v3[0], v3[1], v3[2]};
+    chunk = vol;
+    if (multi) {
+      uint16_t c3[3];
+      std::memcpy(c3, u + 14, 6);
+      chunk = {c3[0], c3[1], c3[2]};
+    }
+    return multi;
+  }
+  static std::vector<size_t> m_kept_lengths(const SPERR3D_Header& h, unsigned pct)
+  {
+    std::vector<size_t> keep(h.chunk_offsets.size() / 2);
+    for (size_t i = 0; i < keep.size(); i++) {
+      size_t l = h.chunk_offsets[2 * i + 1];
+      if (pct != 0 && pct < 100 && l > m_progressive_min_chunk_bytes) {
+        const size_t want = size_t(double(pct) / 100.0 * double(l));
+        l = want < m_progressive_min_chunk_bytes ? m_progressive_min_chunk_bytes : want;
+      }
+      keep[i] = l;
+    }
+    return keep;
+  }
+  static vec8_type m_new_header(const vec8_type& old, const SPERR3D_Header& h, const std::vector<size_t>& keep,
+                                unsigned pct)
+  {
+    vec8_type out(old.begin(), old.begin() + long(h.header_len));
+    if (pct == 0 || pct >= 100)
+      return out;   // the complete container, header untouched
+    out[0] = 0;       // SPERR_VERSION_MAJOR
+    out[1] |= 0x80;   // is_portion
+    const size_t pos = h.multi_chunk ? 20 : 14;
+    for (size_t i = 0; i < keep.size(); i++) {
+      const uint32_t l = uint32_t(keep[i]);
+      std::memcpy(out.data() + pos + 4 * i, &l, 4);
+    }
+    return out;
+  }
 };
 
 }  // namespace sperr_b200

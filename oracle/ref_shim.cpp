@@ -283,3 +283,35 @@ extern "C" int ref_decomp_3d_multires(const void* src, size_t len, size_t* nleve
   }
   return 0;
 }
+
+// ---- SPERR3D_Stream_Tools through the reference's own class (src/SPERR3D_Stream_Tools.cpp) ----
+#include "SPERR3D_Stream_Tools.h"
+
+extern "C" size_t ref_tools_header_len(const uint8_t* magic20)
+{
+  std::array<uint8_t, 20> a{};
+  std::memcpy(a.data(), magic20, 20);
+  return sperr::SPERR3D_Stream_Tools().get_header_len(a);
+}
+
+// fields[0..11] = major, is_portion, is_3D, is_float, multi_chunk, vol xyz, chunk xyz, header_len;
+// fields[12] = stream_len; offsets receives up to cap {offset, length} entries; returns their count
+extern "C" size_t ref_tools_stream_header(const void* p, size_t* fields, size_t* offsets, size_t cap)
+{
+  const auto h = sperr::SPERR3D_Stream_Tools().get_stream_header(p);
+  const size_t f[13] = {h.major_version, h.is_portion, h.is_3D, h.is_float, h.multi_chunk,
+                        h.vol_dims[0], h.vol_dims[1], h.vol_dims[2], h.chunk_dims[0], h.chunk_dims[1],
+                        h.chunk_dims[2], h.header_len, h.stream_len};
+  std::memcpy(fields, f, sizeof(f));
+  for (size_t i = 0; i < h.chunk_offsets.size() && i < cap; i++)
+    offsets[i] = h.chunk_offsets[i];
+  return h.chunk_offsets.size();
+}
+
+extern "C" size_t ref_tools_progressive_read(const char* filename, unsigned pct, uint8_t* out, size_t cap)
+{
+  const auto v = sperr::SPERR3D_Stream_Tools().progressive_read(filename, pct);
+  if (v.size() <= cap)
+    std::memcpy(out, v.data(), v.size());
+  return v.size();
+}

@@ -823,6 +823,131 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
   S.pos = F.win_base + q;
 }
 
+// The walker of a 1D outlier array (SPECK1D_INT_DEC, /root/reference/src/SPECK1D_INT_DEC.cpp:12-125):
+// same contract as f_walk<1>, written for the shape of that stream -- with a PWE bound most
+// correctors are 1 or 2 quanta, so nearly the whole stream is ONE depth-first descent from the two
+// halves of the array in the last plane, a strictly sequential chain of some 10^5 bits that no
+// amount of speculation shortens. What can be cut is the cost per bit. In a binary tree the stack is
+// implicit: the parent of node ix at depth j is ix >> 1, the child being coded is ix & 1, and a
+// frame one returns to has seen a significant child (one only descends into significant sets). So
+// the state is (j, ix, k, sg) in registers plus the depth j0 of the staged root; no frame is ever
+// parked in shared memory, and the stream is read 32 bits at a time into a register.
+static __device__ void f_walk1d(DecChunk& d, DecShared& S, FastSmem& F)
+{
+  const unsigned boff = F.boff;
+  unsigned cw = 0, cbase = ~0u;   // 32 stream bits starting at window position cbase
+  auto load = [&](unsigned qq) {
+    const unsigned a = qq + boff;
+    cw = __funnelshift_r(F.bits[a >> 5], F.bits[(a >> 5) + 1], a & 31);
+    cbase = qq;
+  };
+  unsigned q = F.wk_q;
+  unsigned ntok = 0;
+  int depth = F.wk_depth;   // < 0: between roots
+  unsigned i = F.wk_i;
+  const unsigned cnt = F.wk_cnt;
+  const unsigned i_end = F.rs_first + F.rs_cnt;
+  const int jC = F.J - 3;
+  int j = 0, k = 0, sg = 0, j0 = 0;
+  unsigned ix = 0;
+  if (depth >= 0) {   // resume the expansion a previous round left
+    j = int(F.wk_node[0] >> 32);
+    ix = unsigned(F.wk_node[0]);
+    j0 = int(F.wk_node[1]);
+    k = F.wk_k[0];
+    sg = F.wk_sig[0];
+  }
+  node_t* const lis = gptr(d.lis);
+  for (;;) {
+    if (depth < 0) {
+      if (i == cnt)
+        break;
+      if (q + 1 >= unsigned(kFW) || i >= i_end)
+        break;
+      const unsigned room = min(min(32u, i_end - i), unsigned(kFW) - 1u - q);
+      load(q);
+      unsigned u = cw;
+      if (room < 32)
+        u &= (1u << room) - 1u;
+      const unsigned run = u ? unsigned(__ffs(u) - 1) : room;
+      i += run;
+      q += run;
+      if (run == room)
+        continue;
+      const unsigned r = i - F.rs_first;
+      F.rs_gone[r >> 5] |= 1u << (r & 31);
+      const node_t nd = F.rs_node[r];
+      i++;
+      q++;
+      depth = 0;
+      j = j0 = int(nd >> 32);
+      ix = unsigned(nd);
+      k = 0;
+      sg = 0;
+      continue;
+    }
+    if (k == 2) {   // both halves done: back to the parent, whose first or second half this was
+      if (j == j0) {
+        depth = -1;
+        continue;
+      }
+      k = int(ix & 1u) + 1;
+      ix >>= 1;
+      j--;
+      sg = 1;
+      continue;
+    }
+    if (q + 1 >= unsigned(kFW) || ntok >= unsigned(kFTok))
+      break;
+    unsigned s = 1u;
+    if (sg != 0 || k == 0) {   // the second half is inferred when the first was insignificant
+      if (q - cbase >= 32u)
+        load(q);
+      s = (cw >> (q - cbase)) & 1u;
+      q++;
+    }
+    const unsigned cix = ix * 2u + unsigned(k);
+    const int cj = j + 1;
+    k++;
+    if (s) {
+      sg = 1;
+      if (cj == jC) {   // a size-C set: queue it and skip its bits
+        F.qc_node[ntok] = ((unsigned long long)cj << 32) | cix;
+        F.qc_pos[ntok] = uint16_t(q);
+        ntok++;
+        q += F.bodyC[q];
+      }
+      else {
+        j = cj;
+        ix = cix;
+        k = 0;
+        sg = 0;
+      }
+    }
+    else {
+      const unsigned slot = F.cnt[cj];
+      const unsigned long long at = F.off[cj] + slot;
+      if (at >= F.off[cj + 1]) {
+        F.err |= 1u;
+        break;
+      }
+      lis[at] = ((unsigned long long)cj << 32) | cix;
+      F.cnt[cj] = slot + 1;
+    }
+  }
+  if (depth >= 0) {
+    F.wk_node[0] = ((unsigned long long)j << 32) | ix;
+    F.wk_node[1] = (unsigned long long)j0;
+    F.wk_k[0] = (unsigned char)k;
+    F.wk_sig[0] = (unsigned char)sg;
+  }
+  F.wk_depth = depth;
+  F.wk_i = i;
+  F.wk_q = q;
+  F.nqc = ntok;
+  S.pos = F.win_base + q;
+}
+
 // Survivors of the staged roots [rs_first, wk_i) keep their order: list[wk_w ...] (whole CTA).
 static __device__ void f_compact_roots(FastSmem& F, node_t* list)
 {
@@ -894,7 +1019,7 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
       const long long f_tw = F_CLOCK();
       if (tid == 0) {
         if (d.kind == 1)
-          f_walk<1>(d, S, F);
+          f_walk1d(d, S, F);
         else if (d.kind == 2)
           f_walk<2>(d, S, F);
         else

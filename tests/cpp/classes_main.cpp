@@ -46,6 +46,36 @@ int main(int argc, char** argv)
     std::puts("hostonly ok");
     return 0;
   }
+  if (argc == 5 && std::string(argv[1]) == "tools") {
+    // classes_main tools <container file> pct <out prefix>: SPERR3D_Stream_Tools mirror; writes
+    // <prefix>.hdr (text: the header fields and {offset, length} pairs), <prefix>.read
+    // (progressive_read) and <prefix>.trunc (progressive_truncate of the whole file)
+    const std::string path = argv[2], prefix = argv[4];
+    const unsigned pct = unsigned(std::atoi(argv[3]));
+    std::ifstream in(path, std::ios::binary);
+    std::vector<uint8_t> all((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    if (all.size() < 20) return fail("container too short");
+    SPERR3D_Stream_Tools tools;
+    std::array<uint8_t, 20> magic{};
+    std::memcpy(magic.data(), all.data(), 20);
+    const size_t hlen = tools.get_header_len(magic);
+    const SPERR3D_Header h = tools.get_stream_header(all.data());
+    if (h.header_len != hlen) return fail("header length");
+    std::FILE* f = std::fopen((prefix + ".hdr").c_str(), "w");
+    std::fprintf(f, "%u %d %d %d %d %zu %zu %zu %zu %zu %zu %zu %zu\n", unsigned(h.major_version), int(h.is_portion),
+                 int(h.is_3D), int(h.is_float), int(h.multi_chunk), h.vol_dims[0], h.vol_dims[1], h.vol_dims[2],
+                 h.chunk_dims[0], h.chunk_dims[1], h.chunk_dims[2], h.header_len, h.stream_len);
+    for (size_t v : h.chunk_offsets)
+      std::fprintf(f, "%zu ", v);
+    std::fprintf(f, "\n");
+    std::fclose(f);
+    const auto r = tools.progressive_read(path, pct);
+    std::ofstream((prefix + ".read").c_str(), std::ios::binary).write(reinterpret_cast<const char*>(r.data()), long(r.size()));
+    const auto t = tools.progressive_truncate(all.data(), all.size(), pct);
+    std::ofstream((prefix + ".trunc").c_str(), std::ios::binary).write(reinterpret_cast<const char*>(t.data()), long(t.size()));
+    if (!tools.progressive_read(path + ".does_not_exist", pct).empty()) return fail("missing file");
+    return 0;
+  }
   if (argc != 13 || std::string(argv[1]) != "run")
     return fail("usage");
   const size_t nx = std::atol(argv[3]), ny = std::atol(argv[4]), nz = std::atol(argv[5]);
