@@ -20,6 +20,8 @@
 typedef int cudaStream_t;
 #define LAUNCH(kern, grid, block, smem, stream, ...) \
   emu::launch(grid, block, smem, [=]() { kern(__VA_ARGS__); })
+#define LAUNCH_CLUSTER(kern, grid, block, smem, stream, csize, ...) \
+  emu::launch_cluster(grid, block, smem, csize, [=]() { kern(__VA_ARGS__); })
 #define DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem())
 #define HD
 #define ASSUME_GLOBAL(p) ((void)0)
@@ -30,6 +32,24 @@ typedef int cudaStream_t;
     kern<<<grid, block, smem, stream>>>(__VA_ARGS__);       \
     rt::check(cudaGetLastError(), #kern, __FILE__, __LINE__); \
     rt::launch_counter()++;                                 \
+  } while (0)
+// thread-block clusters of `csize` consecutive CTAs (1D grids)
+#define LAUNCH_CLUSTER(kern, grid_, block_, smem_, stream_, csize, ...)                      \
+  do {                                                                                       \
+    cudaLaunchConfig_t cfg_ = {};                                                            \
+    cfg_.gridDim = grid_;                                                                    \
+    cfg_.blockDim = block_;                                                                  \
+    cfg_.dynamicSmemBytes = smem_;                                                           \
+    cfg_.stream = stream_;                                                                   \
+    cudaLaunchAttribute at_[1];                                                              \
+    at_[0].id = cudaLaunchAttributeClusterDimension;                                         \
+    at_[0].val.clusterDim.x = csize;                                                         \
+    at_[0].val.clusterDim.y = 1;                                                             \
+    at_[0].val.clusterDim.z = 1;                                                             \
+    cfg_.attrs = at_;                                                                        \
+    cfg_.numAttrs = 1;                                                                       \
+    rt::check(cudaLaunchKernelEx(&cfg_, kern, __VA_ARGS__), #kern, __FILE__, __LINE__);      \
+    rt::launch_counter()++;                                                                  \
   } while (0)
 #define DYN_SMEM(type, name)                                        \
   extern __shared__ __align__(16) unsigned char name##_raw_smem[];  \
@@ -48,6 +68,25 @@ __device__ __forceinline__ T* gptr(T* p)
   ASSUME_GLOBAL(p);
   return p;
 }
+
+// ---- thread-block clusters: rank of the CTA and the cluster-wide barrier (release / acquire, so
+// what a CTA wrote to global memory before it is visible to the others after it) ----
+#ifdef SPERR_EMUL
+inline unsigned cluster_rank() { return emu::cluster_rank(); }
+inline void cluster_sync() { emu::sync_cluster(); }
+#elif defined(__CUDACC__)
+__device__ __forceinline__ unsigned cluster_rank()
+{
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync()
+{
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+#endif
 
 namespace rt {
 

@@ -291,6 +291,40 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
       d.roots[r] = j.roots[r];
     max_words = std::max(max_words, sw[c]);
   }
+  // Clusters: the chain phases of a power-of-two 3D / 2D stream are shared by R CTAs (R consecutive
+  // windows of the stream at a time); as many as keep about one CTA per SM busy. 1D outlier streams
+  // are one long walk: one CTA each, launched beside the clusters on a second stream.
+  int n_cl = 0;
+  for (int c = 0; c < nj; c++)
+    if (!jobs[c].skip && jobs[c].pow2 && jobs[c].kind != 1)
+      n_cl++;
+  int R = 1;
+  while (R < kFMaxR && n_cl > 0 && n_cl * R * 2 <= 136)
+    R *= 2;
+  if (const char* e = std::getenv("SPERR_B200_DEC_CLUSTER"))
+    R = std::max(1, std::min(kFMaxR, std::atoi(e)));
+  if (R & (R - 1))
+    R = 1;
+  bool any_cl = false, any_single = false;
+  if (R > 1) {
+    w.boxes.reserve(sizeof(ClusterBox) * size_t(n_cl) + 16);
+    w.scr.reserve(size_t(n_cl) * R * 2 * kFScr * sizeof(node_t) + 16);
+  }
+  for (int c = 0, k = 0; c < nj; c++) {
+    DecChunk& d = w.h[c];
+    d.R = 1;
+    if (jobs[c].skip || !jobs[c].pow2)
+      continue;
+    if (R > 1 && jobs[c].kind != 1) {
+      d.R = R;
+      d.box = w.boxes.as<ClusterBox>() + k;
+      d.scr = w.scr.as<node_t>() + size_t(k) * R * 2 * kFScr;
+      k++;
+      any_cl = true;
+    }
+    else
+      any_single = true;
+  }
   w.dchunks.reserve(sizeof(DecChunk) * nj);
   rt::h2d(w.dchunks.p, w.h.data(), sizeof(DecChunk) * nj, st);
   const size_t aux_bytes = size_t(nj) * 24;
@@ -319,13 +353,39 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
     if (any_fast) {
 #ifndef SPERR_EMUL
       static bool attr_done = false;
+      static cudaStream_t side = nullptr;
+      static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
       if (!attr_done) {
-        RT_CHECK(cudaFuncSetAttribute(k_speck_decode_fast, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RT_CHECK(cudaFuncSetAttribute(k_speck_decode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(sizeof(FastSmem))));
+        RT_CHECK(cudaFuncSetAttribute(k_speck_decode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(sizeof(FastSmem))));
+        RT_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        RT_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        RT_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         attr_done = true;
       }
+      const bool fork = any_cl && any_single;
+      if (fork) {   // the single-CTA streams run beside the clusters
+        RT_CHECK(cudaEventRecord(ev_fork, st));
+        RT_CHECK(cudaStreamWaitEvent(side, ev_fork, 0));
+      }
+      if (any_cl)
+        LAUNCH_CLUSTER(k_speck_decode_fast<true>, dim3(unsigned(nj) * unsigned(R)), dim3(kDecThreads),
+                       sizeof(FastSmem), st, unsigned(R), dch, R);
+      if (any_single)
+        LAUNCH(k_speck_decode_fast<false>, dim3(nj), dim3(kDecThreads), sizeof(FastSmem), fork ? side : st, dch, 1);
+      if (fork) {
+        RT_CHECK(cudaEventRecord(ev_join, side));
+        RT_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
+      }
+#else
+      if (any_cl)
+        LAUNCH_CLUSTER(k_speck_decode_fast<true>, dim3(unsigned(nj) * unsigned(R)), dim3(kDecThreads),
+                       sizeof(FastSmem), st, unsigned(R), dch, R);
+      if (any_single)
+        LAUNCH(k_speck_decode_fast<false>, dim3(nj), dim3(kDecThreads), sizeof(FastSmem), st, dch, 1);
 #endif
-      LAUNCH(k_speck_decode_fast, dim3(nj), dim3(kDecThreads), sizeof(FastSmem), st, dch);
     }
   }
   rt::d2h(w.h.data(), w.dchunks.p, sizeof(DecChunk) * nj, st);

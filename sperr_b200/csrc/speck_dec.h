@@ -50,6 +50,10 @@ struct DecChunk {
   // coefficients (raster order) own one bit each (fewer than all of them only where a truncated
   // stream ends inside the section)
   unsigned long long ref_base[kMaxPlanes], ref_cnt[kMaxPlanes];
+  // thread-block cluster of R CTAs per stream (speck_dec_fast.cuh): mailbox and append scratch
+  int R;
+  struct ClusterBox* box;
+  node_t* scr;
   // clock64() totals of the fast decoder's phases (thread 0): 0 LIP pass, 1 window staging + body
   // tables, 2 token chains, 3 token expansion, 4 tree walker, 6 windows built
   unsigned long long prof[8];
@@ -76,7 +80,7 @@ struct DecJob {
 };
 
 struct DecWork {
-  rt::DBuf dchunks, masks, pl, lis, lis_cnt, stage, aux, counts;
+  rt::DBuf dchunks, masks, pl, lis, lis_cnt, stage, aux, counts, boxes, scr;
   std::vector<DecChunk> h;   // copy of the device state after the last run
   size_t max_n = 0;        // largest decoded job
   size_t fill_n = 0;       // largest chunk of the batch (set by the caller; zero-fill of mode 0)

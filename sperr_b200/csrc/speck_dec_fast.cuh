@@ -40,6 +40,24 @@ constexpr int kFQ = 2048;             // size-B / size-A tokens in flight (a sli
 constexpr int kFSlice = kFQ / 8;
 constexpr int kFMaxDepth = 32;
 constexpr int kFRoots = 2048;         // roots of the walker's current list staged per round
+// thread-block clusters: R CTAs decode R consecutive windows of one stream at the same time
+constexpr int kFMaxR = 8;
+constexpr int kFEntry = 1120;         // a chain enters a window at an offset below this (>= kFNext - kFW)
+constexpr int kFScr = kFW + kFLA;     // sets one window can append to one list (each costs a bit)
+
+// Mailbox of one stream's cluster in global memory. Every field is written by one CTA before a
+// cluster barrier and read by the others after it.
+struct ClusterBox {
+  // decoder state, published by the leader (rank 0) after the parts it runs alone
+  unsigned long long pos, klip, klsp, knew;
+  unsigned cnt[kMaxLis];
+  int iset, go, plane;
+  unsigned err;
+  // per rank, per round of a chain phase
+  unsigned marks[kFMaxR], surv[kFMaxR], app[kFMaxR][2], errs[kFMaxR];
+  unsigned long long dklip[kFMaxR], dknew[kFMaxR], newpos[kFMaxR];
+  uint16_t exits[kFMaxR][kFEntry];   // window position a chain entering at offset e leaves the window at
+};
 
 struct FastSmem {
   uint32_t bits[kFBits / 32 + 4];     // window of the stream, word aligned; bit q is at q + boff
@@ -50,7 +68,11 @@ struct FastSmem {
   // bit ([bit][body if 1]): length in the low bits, the significance bit on top
   uint8_t stepA[kFBodyA + 8];     // len | sig << 7
   uint16_t stepB[kFBodyB + 8];    // len | sig << 15
-  uint16_t nxt[2][kFNext + 8];
+  // chain tables: [0], [1] ping-pong of the pointer doubling, [2] = 16 tokens ahead, [3] = 256 ahead
+  uint16_t nxt[4][kFNext + 8];
+  uint16_t anc256[40], anc16[33 * 16];
+  unsigned n256, n16;
+  int flag[3];
   uint32_t mark[kFW / 32];
   uint16_t T1[256], T2[2][256];       // pixel-set tables: sig(4) | sign(4) << 4 | bits << 8
   // token queues of one round: sets known to be significant, by size class (C: depth J-3, B: J-2,
@@ -88,9 +110,27 @@ struct FastSmem {
   uint32_t rs_gone[kFRoots / 32];        // staged roots that turned significant in this round
   unsigned rs_first, rs_cnt;
   int go;
+  int plane;
   unsigned err;
+  // cluster
+  int R, rank;
+  unsigned entry;            // offset at which the chain enters this CTA's window
+  unsigned app_cnt[2];       // sets appended to the scratch of the two child lists in this round
+  unsigned Tr, i0r, sumT, rstar, wsurv_r, sum_surv;
   unsigned long long prof[8];
 };
+
+// mailbox accesses bypass L1 (another SM wrote the data)
+template <class T>
+__device__ __forceinline__ T mb_ld(const T* p)
+{
+  return __ldcg(gptr(p));
+}
+template <class T>
+__device__ __forceinline__ void mb_st(T* p, T v)
+{
+  __stcg(gptr(p), v);
+}
 
 #ifdef SPERR_EMUL
 #define F_CLOCK() 0ll
@@ -376,7 +416,9 @@ static __device__ void f_expand_pixels(const DecChunk& d, const FastSmem& F, uns
 // One level of expansion: `np` parent tokens (pn, pp) at depth j; significant children go to the
 // child queue (cn, cp, *ncq), the others to the list of depth j + 1. CHILD_TAB: body table of the
 // children (bodyB for size-C parents, bodyA for size-B parents).
-template <class Tab>
+// CL: appends go to this CTA's scratch of the child list (slot 0: depth J - 2, 1: depth J - 1); the
+// cluster copies them to the lists in rank order at the end of the round.
+template <class Tab, bool CL>
 static __device__ void f_expand_level(DecChunk& d, FastSmem& F, int j, const unsigned long long* pn,
                                       const uint16_t* pp, unsigned np, const Tab* child_body,
                                       unsigned long long* cn, uint16_t* cp, unsigned* ncq)
@@ -418,11 +460,15 @@ static __device__ void f_expand_level(DecChunk& d, FastSmem& F, int j, const uns
     const unsigned exs = unsigned(ex) & 0x1fffffu, exi = unsigned(ex >> 21) & 0x1fffffu;
     const unsigned tots = unsigned(tot) & 0x1fffffu, toti = unsigned(tot >> 21) & 0x1fffffu;
     const unsigned qbase = *ncq;
-    const unsigned long long lbase = F.off[cl] + F.cnt[cl];
-    const bool ok = lbase + toti <= F.off[cl + 1] && qbase + tots <= unsigned(kFQ);
+    const int slot = j + 3 - F.J;   // CL only: children at depth J - 2 -> 0, J - 1 -> 1
+    const unsigned long long lbase =
+        CL ? ((unsigned long long)(F.rank * 2 + slot) * kFScr + F.app_cnt[slot]) : F.off[cl] + F.cnt[cl];
+    const bool ok = (CL ? F.app_cnt[slot] + toti <= unsigned(kFScr) : lbase + toti <= F.off[cl + 1]) &&
+                    qbase + tots <= unsigned(kFQ);
     if (ok) {
       unsigned a = qbase + exs;
       unsigned long long b = lbase + exi;
+      node_t* const dst = CL ? gptr(d.scr) : gptr(d.lis);
       for (int k = 0; k < nk; k++) {
         if ((sigmask >> k) & 1u) {
           cn[a] = kid[k];
@@ -430,7 +476,7 @@ static __device__ void f_expand_level(DecChunk& d, FastSmem& F, int j, const uns
           a++;
         }
         else
-          gptr(d.lis)[b++] = kid[k];
+          dst[b++] = kid[k];
       }
     }
     __syncthreads();
@@ -438,7 +484,10 @@ static __device__ void f_expand_level(DecChunk& d, FastSmem& F, int j, const uns
       if (!ok)
         F.err |= 1u;
       *ncq = qbase + tots;
-      F.cnt[cl] += toti;
+      if (CL)
+        F.app_cnt[slot] += toti;
+      else
+        F.cnt[cl] += toti;
     }
     __syncthreads();
   }
@@ -461,6 +510,7 @@ static __device__ void f_expand_A(DecChunk& d, DecShared& S, FastSmem& F, const 
 
 // Expands the tokens of a round. kind: size class of the tokens in the entry queue
 // (2: qc, 1: qb, 0: qa).
+template <bool CL>
 static __device__ void f_expand_round(DecChunk& d, DecShared& S, FastSmem& F, int kind, int n_plane)
 {
   const int J = F.J;
@@ -475,8 +525,8 @@ static __device__ void f_expand_round(DecChunk& d, DecShared& S, FastSmem& F, in
       if (threadIdx.x == 0)
         F.nqa = 0;
       __syncthreads();
-      f_expand_level(d, F, J - 2, F.qb_node + b0, F.qb_pos + b0, min(unsigned(kFSlice), nb - b0),
-                     F.bodyA, F.qa_node, F.qa_pos, &F.nqa);
+      f_expand_level<uint8_t, CL>(d, F, J - 2, F.qb_node + b0, F.qb_pos + b0, min(unsigned(kFSlice), nb - b0),
+                                  F.bodyA, F.qa_node, F.qa_pos, &F.nqa);
       if (F.err)
         return;
       f_expand_A(d, S, F, F.qa_node, F.qa_pos, F.nqa, n_plane);
@@ -488,8 +538,8 @@ static __device__ void f_expand_round(DecChunk& d, DecShared& S, FastSmem& F, in
     if (threadIdx.x == 0)
       F.nqb = 0;
     __syncthreads();
-    f_expand_level(d, F, J - 3, F.qc_node + c0, F.qc_pos + c0, min(unsigned(kFSlice), nc - c0),
-                   F.bodyB, F.qb_node, F.qb_pos, &F.nqb);
+    f_expand_level<uint8_t, CL>(d, F, J - 3, F.qc_node + c0, F.qc_pos + c0, min(unsigned(kFSlice), nc - c0),
+                                F.bodyB, F.qb_node, F.qb_pos, &F.nqb);
     if (F.err)
       return;
     const unsigned nb = F.nqb;
@@ -497,8 +547,8 @@ static __device__ void f_expand_round(DecChunk& d, DecShared& S, FastSmem& F, in
       if (threadIdx.x == 0)
         F.nqa = 0;
       __syncthreads();
-      f_expand_level(d, F, J - 2, F.qb_node + b0, F.qb_pos + b0, min(unsigned(kFSlice), nb - b0),
-                     F.bodyA, F.qa_node, F.qa_pos, &F.nqa);
+      f_expand_level<uint8_t, CL>(d, F, J - 2, F.qb_node + b0, F.qb_pos + b0, min(unsigned(kFSlice), nb - b0),
+                                  F.bodyA, F.qa_node, F.qa_pos, &F.nqa);
       if (F.err)
         return;
       f_expand_A(d, S, F, F.qa_node, F.qa_pos, F.nqa, n_plane);
@@ -507,71 +557,182 @@ static __device__ void f_expand_round(DecChunk& d, DecShared& S, FastSmem& F, in
 }
 
 // ---- phase A: the lists of the three smallest set sizes, by token chains -------------------------
+//
+// One round resolves R consecutive windows of the stream, one per CTA of the cluster (R = 1: one
+// window). Everything that does not depend on where the token chain enters a window is computed by
+// all CTAs at once: the body tables, the token length of every position, and -- by pointer
+// doubling -- where a chain entering at any offset leaves the window. Then the entry offsets are
+// handed down the ranks (one table look-up each), every CTA marks the token starts of its window
+// from its true entry (hierarchically: 256-token and 16-token jump tables kept from the doubling),
+// and the windows' tokens are mapped to the roots of the list, expanded, and their results appended
+// in rank order, which is stream order.
 
+__device__ __forceinline__ unsigned f_token_len(const FastSmem& F, int kind, unsigned q)
+{
+  if (kind == 0)
+    return F.stepA[q] & 127u;
+  if (kind == 1)
+    return F.stepB[q] & 0x7fffu;
+  return f_bit(F, q) ? 1u + F.bodyC[q + 1] : 1u;
+}
+
+template <bool CL>
 static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, int kind, int n_plane)
 {
   const int tid = threadIdx.x;
+  const int R = CL ? F.R : 1, rank = CL ? F.rank : 0;
   const int j = F.J - 1 - kind;
   const int lis = f_lis(F, j);
   const unsigned m = F.cnt[lis];
   if (m == 0)
     return;
+  ClusterBox* const box = d.box;
   node_t* const list = gptr(d.lis) + F.off[lis];
   unsigned long long* const qn = kind == 0 ? F.qa_node : (kind == 1 ? F.qb_node : F.qc_node);
   uint16_t* const qp = kind == 0 ? F.qa_pos : (kind == 1 ? F.qb_pos : F.qc_pos);
   const unsigned qcap = kind == 2 ? unsigned(kFTok) : unsigned(kFQ);
+  const int n_entry = CL ? kFEntry : 1;
   unsigned i0 = 0, wsurv = 0;
   while (i0 < m) {
-    f_build_window(d, F, S.pos, kind, true);
+    const unsigned long long round_base = S.pos;
+    f_build_window(d, F, round_base + (unsigned long long)rank * kFW, kind, true);
     const long long f_tc = F_CLOCK();
     // token length of every window position; positions beyond the window absorb
-    for (int q = tid; q < kFNext; q += kDecThreads) {
-      unsigned nx = q;
-      if (q < kFW) {
-        unsigned len;
-        if (kind == 0)
-          len = F.stepA[q] & 127u;
-        else if (kind == 1)
-          len = F.stepB[q] & 0x7fffu;
-        else
-          len = f_bit(F, q) ? 1u + F.bodyC[q + 1] : 1u;
-        nx = q + len;
-      }
-      F.nxt[0][q] = uint16_t(nx);
-    }
+    for (int q = tid; q < kFNext; q += kDecThreads)
+      F.nxt[0][q] = uint16_t(q < kFW ? q + f_token_len(F, kind, q) : q);
     for (int i = tid; i < kFW / 32; i += kDecThreads)
-      F.mark[i] = i == 0 ? 1u : 0u;
+      F.mark[i] = 0u;
+    if (tid == 0) {
+      F.flag[0] = 0;
+      F.app_cnt[0] = F.app_cnt[1] = 0;
+    }
     __syncthreads();
-    // pointer doubling: after round r the marks cover the first 2^(r+1) tokens of the chain
-    int cur = 0;
+    // pointer doubling: table r + 1 = 2^(r+1) tokens ahead; until every entry offset has left
+    int src = 0, have4 = 0, have8 = 0;
     for (int r = 0; r < 14; r++) {
-      const uint16_t* cn = F.nxt[cur];
-      uint16_t* nn = F.nxt[cur ^ 1];
-      unsigned t = (F.mark[tid >> 2] >> ((tid & 3) * 8)) & 0xffu;   // my 8 positions
-      while (t) {
-        const int b = __ffs(t) - 1;
-        t &= t - 1;
-        const unsigned tgt = cn[tid * 8 + b];
-        if (tgt < unsigned(kFW))
-          atomicOr(&F.mark[tgt >> 5], 1u << (tgt & 31));
-      }
+      const int dst = r == 3 ? 2 : (r == 7 ? 3 : (src == 0 ? 1 : 0));
+      const uint16_t* cn = F.nxt[src];
+      uint16_t* nn = F.nxt[dst];
+      if (tid == 0)
+        F.flag[(r + 1) % 3] = 0;   // (round r + 1 resets the flag of round r + 2: nobody reads it any more)
 #pragma unroll
       for (int it = 0; it < (kFNext + kDecThreads - 1) / kDecThreads; it++) {
         const int q = tid + it * kDecThreads;
-        if (q < kFNext)
-          nn[q] = q < kFW ? cn[cn[q]] : uint16_t(q);
+        if (q < kFNext) {
+          const uint16_t v = q < kFW ? cn[cn[q]] : uint16_t(q);
+          nn[q] = v;
+          if (q < n_entry && v < kFW)
+            F.flag[r % 3] = 1;
+        }
       }
       __syncthreads();
-      cur ^= 1;
-      if (F.nxt[cur][0] >= kFW)   // 2^(r+1) steps leave the window: every token start is marked
+      src = dst;
+      have4 |= r == 3;
+      have8 |= r == 7;
+      if (!F.flag[r % 3])
         break;
     }
-    const unsigned exitpos = F.nxt[cur][0];
+    const uint16_t* const fin = F.nxt[src];
+    // where does the chain enter my window?
+    unsigned entry = 0;
+    if (CL) {
+      for (int e = tid; e < kFEntry; e += kDecThreads)
+        mb_st(&box->exits[rank][e], fin[e]);
+      cluster_sync();
+      uint16_t* const xtab = reinterpret_cast<uint16_t*>(F.qa_node);   // idle until the expansion
+      for (int e = tid; e < rank * kFEntry; e += kDecThreads)
+        xtab[e] = mb_ld(&box->exits[0][0] + e);
+      __syncthreads();
+      if (tid == 0) {
+        unsigned e = 0;
+        for (int s2 = 0; s2 < rank; s2++)
+          e = unsigned(xtab[s2 * kFEntry + e]) - unsigned(kFW);
+        F.entry = e;
+      }
+      __syncthreads();
+      entry = F.entry;
+    }
+    const unsigned exitpos = fin[entry];
+    // token starts of my window: anchors every 256 tokens, then every 16, then single steps
+    if (tid == 0) {
+      unsigned n = 0;
+      if (have8) {
+        unsigned p2 = entry;
+        while (p2 < unsigned(kFW) && n < 33u) {
+          F.anc256[n++] = uint16_t(p2);
+          p2 = F.nxt[3][p2];
+        }
+      }
+      else
+        F.anc256[n++] = uint16_t(entry);
+      F.n256 = n;
+    }
+    __syncthreads();
+    if (have4) {
+      if (tid < int(F.n256)) {
+        unsigned p2 = F.anc256[tid];
+        for (int u = 0; u < 16; u++) {
+          F.anc16[tid * 16 + u] = uint16_t(p2 < unsigned(kFW) ? p2 : 0xFFFFu);
+          if (p2 < unsigned(kFW))
+            p2 = F.nxt[2][p2];
+        }
+      }
+      if (tid == 0)
+        F.n16 = F.n256 * 16;
+    }
+    else if (tid == 0) {
+      F.anc16[0] = F.anc256[0];
+      F.n16 = 1;
+    }
+    __syncthreads();
+    if (tid < int(F.n16)) {
+      unsigned p2 = F.anc16[tid];
+      for (int u = 0; u < 16 && p2 < unsigned(kFW); u++) {
+        atomicOr(&F.mark[p2 >> 5], 1u << (p2 & 31));
+        p2 += f_token_len(F, kind, p2);
+      }
+    }
+    __syncthreads();
     // rank of my marks = index of the root they belong to
     const unsigned mb = (F.mark[tid >> 2] >> ((tid & 3) * 8)) & 0xffu;
     unsigned long long ex = f_block_scan(F, (unsigned long long)__popc(mb));
     const unsigned total_marks = unsigned(F.scan_total);
-    const unsigned T = min(total_marks, m - i0);
+    // which roots are mine: tokens of the windows before mine come first
+    unsigned T, i0r, sumT, rstar = 0;
+    if (CL) {
+      if (tid == 0)
+        mb_st(&box->marks[rank], total_marks);
+      cluster_sync();
+      if (tid == 0) {
+        unsigned at = i0, sum = 0, mine_i0 = 0, mine_T = 0, last = 0;
+        for (int s2 = 0; s2 < R; s2++) {
+          const unsigned mk = mb_ld(&box->marks[s2]);
+          const unsigned t2 = min(mk, m - at);
+          if (s2 == rank) {
+            mine_i0 = at;
+            mine_T = t2;
+          }
+          if (t2 > 0)
+            last = unsigned(s2);
+          at += t2;
+          sum += t2;
+        }
+        F.i0r = mine_i0;
+        F.Tr = mine_T;
+        F.sumT = sum;
+        F.rstar = last;
+      }
+      __syncthreads();
+      T = F.Tr;
+      i0r = F.i0r;
+      sumT = F.sumT;
+      rstar = F.rstar;
+    }
+    else {
+      T = min(total_marks, m - i0);
+      i0r = i0;
+      sumT = T;
+    }
     // my tokens: survivors keep their place in the list, significant ones are queued
     node_t surv[8], sigs[8];
     uint16_t sigq[8];
@@ -583,7 +744,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         t &= t - 1;
         const unsigned q = tid * 8 + b;
         if (r < T) {
-          const node_t nd = list[i0 + r];
+          const node_t nd = CL ? __ldcg(&list[i0r + r]) : list[i0r + r];
           if (f_bit(F, q)) {
             sigs[ng] = nd;
             sigq[ng++] = uint16_t(q + 1);
@@ -600,14 +761,35 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
     ex = f_block_scan(F, (unsigned long long)ns | ((unsigned long long)ng << 32));
     const unsigned tot_surv = unsigned(F.scan_total & 0xffffffffull);
     const unsigned tot_sig = unsigned(F.scan_total >> 32);
-    for (int s = 0; s < ns; s++)
-      list[wsurv + unsigned(ex & 0xffffffffull) + s] = surv[s];
+    unsigned wsurv_r = wsurv, sum_surv = tot_surv;
+    if (CL) {
+      if (tid == 0)
+        mb_st(&box->surv[rank], tot_surv);
+      cluster_sync();   // ... in every window of the round
+      if (tid == 0) {
+        unsigned before = 0, sum = 0;
+        for (int s2 = 0; s2 < R; s2++) {
+          const unsigned v = mb_ld(&box->surv[s2]);
+          if (s2 < rank)
+            before += v;
+          sum += v;
+        }
+        F.wsurv_r = wsurv + before;
+        F.sum_surv = sum;
+      }
+      __syncthreads();
+      wsurv_r = F.wsurv_r;
+      sum_surv = F.sum_surv;
+    }
+    for (int s2 = 0; s2 < ns; s2++)
+      list[wsurv_r + unsigned(ex & 0xffffffffull) + s2] = surv[s2];
     const long long f_te = F_CLOCK();
     if (tid == 0)
       F.prof[2] += (unsigned long long)(f_te - f_tc);
+    const unsigned long long klip0 = S.klip, knew0 = S.knew;
     // the significant roots enter the queue of their size class, qcap at a time
     const unsigned myq = unsigned(ex >> 32);
-    for (unsigned g0 = 0; g0 < tot_sig; g0 += qcap) {
+    for (unsigned g0 = 0; g0 < tot_sig && !F.err; g0 += qcap) {
       for (int g = 0; g < ng; g++) {
         const unsigned slot = myq + g;
         if (slot >= g0 && slot < g0 + qcap) {
@@ -622,17 +804,75 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         else F.nqc = cntq;
       }
       __syncthreads();
-      f_expand_round(d, S, F, kind, n_plane);
+      f_expand_round<CL>(d, S, F, kind, n_plane);
       __syncthreads();
+    }
+    if (tid == 0)
+      F.prof[3] += (unsigned long long)(F_CLOCK() - f_te);
+    if (!CL) {
       if (F.err)
         return;
+      if (tid == 0)
+        S.pos += T == total_marks ? exitpos : F.cutpos;
     }
-    if (tid == 0) {
-      F.prof[3] += (unsigned long long)(F_CLOCK() - f_te);
-      S.pos += T == total_marks ? exitpos : F.cutpos;
+    else {
+      // end of the round: scratch appends to the lists in rank order, counters and position agreed
+      if (tid == 0) {
+        mb_st(&box->app[rank][0], F.app_cnt[0]);
+        mb_st(&box->app[rank][1], F.app_cnt[1]);
+        mb_st(&box->dklip[rank], S.klip - klip0);
+        mb_st(&box->dknew[rank], S.knew - knew0);
+        mb_st(&box->errs[rank], F.err);
+        if (unsigned(rank) == rstar)
+          mb_st(&box->newpos[rank], round_base + (unsigned long long)rank * kFW +
+                                        (T == total_marks ? exitpos : F.cutpos));
+      }
+      cluster_sync();
+      for (int a = 0; a < 2; a++) {
+        unsigned before = 0, sum = 0;
+        for (int s2 = 0; s2 < R; s2++) {
+          const unsigned v = mb_ld(&box->app[s2][a]);
+          if (s2 < rank)
+            before += v;
+          sum += v;
+        }
+        if (sum == 0)
+          continue;   // the same on every thread of every rank
+        const int cl = f_lis(F, F.J - 2 + a);
+        const unsigned long long at = F.off[cl] + F.cnt[cl];
+        const bool fits = at + sum <= F.off[cl + 1];
+        const unsigned mine = F.app_cnt[a];
+        if (fits) {
+          const node_t* const from = gptr(d.scr) + (unsigned long long)(rank * 2 + a) * kFScr;
+          for (unsigned t = tid; t < mine; t += kDecThreads)
+            gptr(d.lis)[at + before + t] = from[t];
+        }
+        __syncthreads();   // every thread has read F.cnt[cl]
+        if (tid == 0) {
+          if (!fits)
+            F.err |= 1u;
+          F.cnt[cl] += sum;
+        }
+      }
+      if (tid == 0) {
+        unsigned long long dl = 0, dn = 0;
+        unsigned e = 0;
+        for (int s2 = 0; s2 < R; s2++) {
+          dl += mb_ld(&box->dklip[s2]);
+          dn += mb_ld(&box->dknew[s2]);
+          e |= mb_ld(&box->errs[s2]);
+        }
+        S.klip = klip0 + dl;
+        S.knew = knew0 + dn;
+        S.pos = mb_ld(&box->newpos[rstar]);
+        F.err |= e;
+      }
+      __syncthreads();
+      if (F.err)
+        return;   // the same on every rank
     }
-    i0 += T;
-    wsurv += tot_surv;
+    i0 += sumT;
+    wsurv += sum_surv;
     __syncthreads();
   }
   if (tid == 0)
@@ -835,7 +1075,7 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
 static __device__ void f_walk1d(DecChunk& d, DecShared& S, FastSmem& F)
 {
   const unsigned boff = F.boff;
-  unsigned cw = 0, cbase = ~0u;   // 32 stream bits starting at window position cbase
+  unsigned cw = 0, cbase = 1u << 30;   // 32 stream bits starting at window position cbase (none yet)
   auto load = [&](unsigned qq) {
     const unsigned a = qq + boff;
     cw = __funnelshift_r(F.bits[a >> 5], F.bits[(a >> 5) + 1], a & 31);
@@ -968,15 +1208,22 @@ static __device__ void f_compact_roots(FastSmem& F, node_t* list)
     F.wk_w = w0 + total;
 }
 
-// The LIS part of one bit-plane.
-static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int n_plane)
+// The LIS part of one bit-plane: the lists of the three smallest set sizes (every CTA of the
+// cluster) ...
+template <bool CL>
+static __device__ void dec_lis_chains(DecChunk& d, DecShared& S, FastSmem& F, int n_plane)
 {
-  const int tid = threadIdx.x;
   for (int kind = 0; kind < 3; kind++) {
-    f_list_by_chain(d, S, F, kind, n_plane);
+    f_list_by_chain<CL>(d, S, F, kind, n_plane);
     if (F.err)
       return;
   }
+}
+
+// ... and the lists of the larger sets (one CTA)
+static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int n_plane)
+{
+  const int tid = threadIdx.x;
   bool have_window = false;
   // lj == 0 (2D only): the set I, tested after all lists (src/SPECK2D_INT.cpp:54-57), as a
   // one-entry pseudo list
@@ -1008,7 +1255,7 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
       const unsigned nst = min(unsigned(kFRoots), cnt - first);
       __syncthreads();
       for (unsigned t = tid; t < nst; t += kDecThreads)
-        F.rs_node[t] = iphase ? ((unsigned long long)(0x100 | F.iset) << 32) : gptr(d.lis)[F.off[lis] + first + t];
+        F.rs_node[t] = iphase ? ((unsigned long long)(0x100 | F.iset) << 32) : __ldcg(gptr(d.lis) + F.off[lis] + first + t);
       for (unsigned t = tid; t < unsigned(kFRoots / 32); t += kDecThreads)
         F.rs_gone[t] = 0;
       if (tid == 0) {
@@ -1032,7 +1279,7 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
       const long long f_te = F_CLOCK();
       if (tid == 0)
         F.prof[4] += (unsigned long long)(f_te - f_tw);
-      f_expand_round(d, S, F, 2, n_plane);
+      f_expand_round<false>(d, S, F, 2, n_plane);
       __syncthreads();
       if (tid == 0)
         F.prof[3] += (unsigned long long)(F_CLOCK() - f_te);
@@ -1049,14 +1296,55 @@ static __device__ void dec_lis_fast(DecChunk& d, DecShared& S, FastSmem& F, int 
 
 // ---- the kernel -----------------------------------------------------------------------------------
 
-static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChunk* chunks)
+// Cluster mode: the leader (rank 0) runs the LIP pass, the walker and the end-of-plane bookkeeping
+// alone and publishes the decoder state; the other CTAs pick it up for the chain phases.
+static __device__ void f_state_sync(DecChunk& d, DecShared& S, FastSmem& F)
+{
+  const int tid = threadIdx.x;
+  ClusterBox* const box = d.box;
+  if (F.rank == 0) {
+    if (tid == 0) {
+      mb_st(&box->pos, S.pos);
+      mb_st(&box->klip, S.klip);
+      mb_st(&box->klsp, S.klsp);
+      mb_st(&box->knew, S.knew);
+      mb_st(&box->iset, F.iset);
+      mb_st(&box->go, F.go);
+      mb_st(&box->plane, F.plane);
+      mb_st(&box->err, F.err);
+    }
+    for (int l = tid; l < d.nlis; l += kDecThreads)
+      mb_st(&box->cnt[l], F.cnt[l]);
+  }
+  cluster_sync();
+  if (F.rank != 0) {
+    if (tid == 0) {
+      S.pos = mb_ld(&box->pos);
+      S.klip = mb_ld(&box->klip);
+      S.klsp = mb_ld(&box->klsp);
+      S.knew = mb_ld(&box->knew);
+      F.iset = mb_ld(&box->iset);
+      F.go = mb_ld(&box->go);
+      F.plane = mb_ld(&box->plane);
+      F.err = mb_ld(&box->err);
+    }
+    for (int l = tid; l < d.nlis; l += kDecThreads)
+      F.cnt[l] = mb_ld(&box->cnt[l]);
+  }
+  cluster_sync();   // read before the leader publishes again
+}
+
+// CL: launched as clusters of chunks[.].R CTAs per job (every job of the launch has the same R).
+template <bool CL>
+static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChunk* chunks, int R)
 {
   __shared__ DecShared S;
   DYN_SMEM(FastSmem, Fp);
   FastSmem& F = *Fp;
-  const unsigned c = blockIdx.x;
-  if (chunks[c].skip || chunks[c].planes == 0 || !chunks[c].pow2)
-    return;
+  const unsigned c = CL ? blockIdx.x / unsigned(R) : blockIdx.x;
+  const int rank = CL ? int(cluster_rank()) : 0;
+  if (chunks[c].skip || chunks[c].planes == 0 || !chunks[c].pow2 || chunks[c].R != R)
+    return;   // the same for every CTA of a cluster
   const int tid = threadIdx.x;
   // The job descriptor is worked on in shared memory and written back at the end. Read through
   // the global struct, every pointer in it (bits, pl, lip, lis, ...) has to be fetched again after
@@ -1080,6 +1368,10 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     F.is2d = d.kind == 2;
     F.iset = d.kind == 2 ? int(d.iset) : 0;
     F.err = 0;
+    F.R = R;
+    F.rank = rank;
+    F.go = 1;
+    F.plane = d.planes - 1;
     F.nqa = F.nqb = F.nqc = 0;
     for (int k = 0; k < 8; k++)
       F.prof[k] = 0;
@@ -1090,7 +1382,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
   }
   f_build_luts(F);
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0 && rank == 0) {
     for (int r = 0; r < d.nroots; r++) {
       const unsigned long long nd = d.roots[r];
       const int lis = f_lis(F, int(nd >> 32));
@@ -1099,22 +1391,38 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     }
   }
   __syncthreads();
-  int n = d.planes - 1;
-  for (int bp = 0; bp < d.planes; bp++, n--) {
-    {
-      F_TIC();
-      dec_lip_pass(d, S, n);
-      __syncthreads();
-      F_TOC(F, 0);
-    }
-    dec_lis_fast(d, S, F, n);
-    __syncthreads();
-    if (tid == 0)
-      F.go = (!F.err && dec_plane_end(d, S, n)) ? 1 : 0;
+  // (the LIP is empty in the first plane: nothing to do before its LIS part)
+  for (;;) {
+    if (CL)
+      f_state_sync(d, S, F);
     __syncthreads();
     if (!F.go)
       break;
+    const int n = F.plane;
+    dec_lis_chains<CL>(d, S, F, n);
+    __syncthreads();
+    if (rank == 0) {
+      if (!F.err)
+        dec_lis_walk(d, S, F, n);
+      __syncthreads();
+      if (tid == 0) {
+        const bool more = !F.err && dec_plane_end(d, S, n);
+        F.go = (more && n > 0) ? 1 : 0;
+        F.plane = n - 1;
+      }
+      __syncthreads();
+      if (F.go) {
+        F_TIC();
+        dec_lip_pass(d, S, n - 1);
+        __syncthreads();
+        F_TOC(F, 0);
+      }
+    }
+    else if (!CL)
+      break;   // not reached: a lone CTA is its own leader
   }
+  if (rank != 0)
+    return;
   if (tid == 0) {
     d.err = F.err;
     for (int k = 0; k < 8; k++)

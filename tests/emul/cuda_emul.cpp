@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- runtime of the CPU SIMT emulator (see cuda_emul.h).
 #include "cuda_emul.h"
 
+#include <pthread.h>
 #include <sys/mman.h>
 
 #include <atomic>
@@ -33,7 +34,7 @@ emu_switch:
 
 namespace emu {
 
-enum State { RUNNABLE, WAIT_BLOCK, DONE };
+enum State { RUNNABLE, WAIT_BLOCK, WAIT_CLUSTER, DONE };
 
 struct Fiber {
   void* sp = nullptr;
@@ -61,6 +62,9 @@ struct Worker {
   dim3 bdim, gdim;
   std::vector<char> smem;
   const std::function<void()>* body = nullptr;
+  // thread-block clusters: rank inside the cluster and the barrier its workers share
+  unsigned crank = 0, csize = 1;
+  pthread_barrier_t* cbar = nullptr;
 };
 
 static thread_local Worker* W = nullptr;
@@ -79,6 +83,14 @@ static void yield_to_sched()
 {
   Fiber* f = W->current;
   emu_switch(&f->sp, W->sched_sp);
+}
+
+unsigned cluster_rank() { return W ? W->crank : 0; }
+unsigned cluster_size() { return W ? W->csize : 1; }
+void sync_cluster()
+{
+  W->current->st = WAIT_CLUSTER;
+  yield_to_sched();
 }
 
 void sync_block()
@@ -176,15 +188,27 @@ static void run_block(Worker& wk, unsigned nthreads)
       for (unsigned l = 0; l < 32; l++) {
         State s = wk.fibers[w * 32 + l].st;
         done += (s == DONE);
-        waiting += (s == WAIT_BLOCK);
+        waiting += (s == WAIT_BLOCK || s == WAIT_CLUSTER);
       }
     }
     if (done == nthreads)
       break;
     // every live thread is at the barrier: release
     (void)waiting;
+    bool at_cluster = false;
     for (unsigned t = 0; t < nthreads; t++)
-      if (wk.fibers[t].st == WAIT_BLOCK)
+      at_cluster |= wk.fibers[t].st == WAIT_CLUSTER;
+    if (at_cluster) {
+      for (unsigned t = 0; t < nthreads; t++)
+        if (wk.fibers[t].st == WAIT_BLOCK) {
+          std::fprintf(stderr, "emu: block %u mixes __syncthreads and cluster barriers\n", wk.bid.x);
+          std::abort();
+        }
+      if (wk.cbar)
+        pthread_barrier_wait(wk.cbar);   // the other blocks of the cluster arrive the same way
+    }
+    for (unsigned t = 0; t < nthreads; t++)
+      if (wk.fibers[t].st == WAIT_BLOCK || wk.fibers[t].st == WAIT_CLUSTER)
         wk.fibers[t].st = RUNNABLE;
   }
 }
@@ -237,6 +261,63 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
       th.emplace_back(work, i);
     for (auto& t : th)
       t.join();
+  }
+}
+
+// Clusters of `csize` consecutive blocks (1D grids): the blocks of a cluster run at the same time on
+// csize OS threads that share a barrier. Every block of a cluster must reach every cluster barrier.
+void launch_cluster(dim3 grid, dim3 block, size_t smem, unsigned csize, const std::function<void()>& body)
+{
+  const unsigned nthreads = block.x * block.y * block.z;
+  if (csize <= 1) {
+    launch(grid, block, smem, body);
+    return;
+  }
+  if (grid.y != 1 || grid.z != 1 || grid.x % csize != 0 || nthreads % 32 != 0 || nthreads > 1024) {
+    std::fprintf(stderr, "emu: bad cluster launch\n");
+    std::abort();
+  }
+  const unsigned nclusters = grid.x / csize;
+  const unsigned ngroups = std::max(1u, std::min(nclusters, 8u / csize));
+  std::vector<Worker*> ws(size_t(ngroups) * csize);
+  for (auto& w : ws)
+    w = new Worker();
+  std::vector<pthread_barrier_t> bars(ngroups);
+  for (auto& b : bars)
+    pthread_barrier_init(&b, nullptr, csize);
+  auto work = [&](unsigned g, unsigned r) {
+    Worker& wk = *ws[size_t(g) * csize + r];
+    W = &wk;
+    wk.fibers.resize(nthreads);
+    wk.warps.resize(nthreads / 32);
+    wk.smem.resize(smem + 64);
+    wk.bdim = block;
+    wk.gdim = grid;
+    wk.body = &body;
+    wk.crank = r;
+    wk.csize = csize;
+    wk.cbar = &bars[g];
+    for (unsigned c = g; c < nclusters; c += ngroups) {
+      wk.bid.x = c * csize + r;
+      wk.bid.y = wk.bid.z = 0;
+      run_block(wk, nthreads);
+      pthread_barrier_wait(wk.cbar);   // the next cluster starts when every block of this one is done
+    }
+    W = nullptr;
+  };
+  std::vector<std::thread> th;
+  for (unsigned g = 0; g < ngroups; g++)
+    for (unsigned r = 0; r < csize; r++)
+      th.emplace_back(work, g, r);
+  for (auto& t : th)
+    t.join();
+  for (auto& b : bars)
+    pthread_barrier_destroy(&b);
+  for (auto w : ws) {
+    for (auto& f : w->fibers)
+      if (f.stack)
+        munmap(f.stack, kStack);
+    delete w;
   }
 }
 

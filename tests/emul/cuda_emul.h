@@ -68,6 +68,11 @@ void warp_exchange(uint64_t mine, uint64_t* out);
 unsigned lane();
 void* dyn_smem();
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+// thread-block clusters of csize consecutive blocks
+void launch_cluster(dim3 grid, dim3 block, size_t smem, unsigned csize, const std::function<void()>& body);
+unsigned cluster_rank();
+unsigned cluster_size();
+void sync_cluster();
 }  // namespace emu
 
 #define threadIdx (emu::tid())
@@ -234,6 +239,16 @@ template <typename T>
 inline T __ldg(const T* p)
 {
   return *p;
+}
+template <typename T>
+inline T __ldcg(const T* p)
+{
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+}
+template <typename T>
+inline void __stcg(T* p, T v)
+{
+  __atomic_store_n(p, v, __ATOMIC_RELAXED);
 }
 
 // atomics (blocks may run on different OS threads)
