@@ -31,7 +31,7 @@ struct EncCtx {
   // significant sets waiting to be expanded (ping-pong)
   node_t* fnode[2];
   unsigned long long* fpos[2];  // (absolute bit position << 10) | chunk
-  unsigned long long* fcount;   // two counters
+  unsigned long long* fcount;   // three rotating counters (k_lis_plane)
   unsigned long long front_cap;
 
   unsigned* err;

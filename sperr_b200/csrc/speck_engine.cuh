@@ -392,161 +392,245 @@ static __global__ void k_plane_begin(EncCtx ctx)
   ch.next_needed = 1;
 }
 
-struct Appender {
-  EncCtx ctx;
-  __device__ __forceinline__ void cand(unsigned c, unsigned long long key, node_t nd) const
-  {
-    const unsigned long long slot = atomicAdd(ctx.cand_count, 1ull);
-    if (slot >= ctx.cand_cap) {
-      atomicOr(ctx.err, 1u);
-      return;
-    }
-    ctx.ckey[slot] = key;
-    ctx.cnode[slot] = nd;
-    atomicAdd(&ctx.chunks[c].ncand, 1u);
-  }
-  __device__ __forceinline__ void front(int dst, unsigned c, node_t nd, unsigned long long pos) const
-  {
-    const unsigned long long slot = atomicAdd(&ctx.fcount[dst], 1ull);
-    if (slot >= ctx.front_cap) {
-      atomicOr(ctx.err, 2u);
-      return;
-    }
-    ctx.fnode[dst][slot] = nd;
-    ctx.fpos[dst][slot] = (pos << 10) | c;
-  }
-};
-
-template <class T>
-__global__ void k_root_emit(EncCtx ctx, typename T::Data tree, unsigned long long nroots)
+// ---- work-list appends: one atomic per warp ---------------------------------------------------
+// Every lane of the warp calls with the number of slots it needs; returns the lane's first slot.
+__device__ __forceinline__ unsigned long long warp_reserve(unsigned long long* counter, unsigned n)
 {
-  const Appender app{ctx};
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nroots;
-       i += stride) {
-    const unsigned long long key = ctx.rkey[i];
-    const unsigned c = key_chunk(key);
-    const ChunkDev& ch = ctx.chunks[c];
-    if (!ch.plane_live)
-      continue;
-    const unsigned long long pos = ch.lis_base + (ctx.rpos[i] - ctx.rpos[ctx.rstart[c]]);
-    const node_t nd = ctx.rnode[i];
-    int p;
-    unsigned d;
-    T::pd(tree, ch, c, nd, p, d);
-    if (p == ch.cur_n) {
-      put_bit(gptr(ch.spk), pos, 1);
-      app.front(0, c, nd, pos + 1);
-    }
-    else if (ch.next_needed)  // insignificant: stays in its list, same position
-      app.cand(c, key, nd);
+  const int lane = threadIdx.x & 31;
+  unsigned inc = n;
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o)
+      inc += t;
   }
+  const unsigned total = __shfl_sync(0xffffffffu, inc, 31);
+  unsigned long long base = 0;
+  if (lane == 31 && total)
+    base = atomicAdd(counter, (unsigned long long)total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  return base + inc - n;
 }
 
-// One thread per significant set: m_code_S (src/SPECK3D_INT.cpp:140-212, src/SPECK1D_INT_ENC.cpp:
-// 121-160) with every child placed by its D instead of by recursion order.
-template <class T>
-__global__ void k_expand(EncCtx ctx, typename T::Data tree, int src)
+// ---- grid-wide barrier of the persistent plane kernel (all CTAs are co-resident: cooperative
+// launch). bar[0]: arrivals, bar[1]: generation. ----
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks)
 {
-  const Appender app{ctx};
-  const int dst = src ^ 1;
-  const unsigned long long count = ctx.fcount[src];
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
-       i += stride) {
-    const node_t nd = ctx.fnode[src][i];
-    const unsigned long long pc = ctx.fpos[src][i];
-    const unsigned c = unsigned(pc & 1023u);
-    unsigned long long cur = pc >> 10;
-    const ChunkDev& ch = ctx.chunks[c];
-    const int n = ch.cur_n;
-    ChildRec kid[8];
-    const int nchf = T::children(tree, ch, c, nd, kid);
-    const int nch = nchf & 0xff;
-    const bool all_tested = (nchf & 0x100) != 0;   // 2D: last split of the set I
-    BitRun run;
-    run.start(gptr(ch.spk), cur);
-    int sigc = 0;
-    for (int k = 0; k < nch; k++) {
-      const bool need = sigc != 0 || k != nch - 1 || all_tested;
-      const bool sig = !need || kid[k].p == n;
-      if (need)
-        run.push(sig);
-      if (kid[k].kind == 0) {
-        if (sig) {
-          run.push(kid[k].sign);
-          sigc++;
-        }
-      }
-      else if (sig) {
-        sigc++;
-        if (kid[k].kind == 1) {  // all grandchildren are pixels: finish them here
-          int gp[8];
-          unsigned gsign = 0;
-          int ng;
-          if constexpr (T::kHasLeaf8)
-            ng = T::leaf8(tree, ch, kid[k].id, gp, gsign);
-          else {
-            ChildRec g[8];
-            ng = T::children(tree, ch, c, kid[k].id, g) & 0xff;
-            for (int j = 0; j < ng; j++) {
-              gp[j] = g[j].p;
-              gsign |= g[j].sign << j;
-            }
-          }
-          int gs = 0;
-          for (int j = 0; j < ng; j++) {
-            const bool gneed = gs != 0 || j != ng - 1;
-            const bool gsig = !gneed || gp[j] == n;
-            if (gneed)
-              run.push(gsig);
-            if (gsig) {
-              run.push((gsign >> j) & 1u);
-              gs++;
-            }
-          }
-        }
-        else {
-          app.front(dst, c, kid[k].id, run.cur());
-          run.skip(kid[k].d);
-        }
-      }
-      else if (ch.next_needed)
-        app.cand(c, make_key(c, kid[k].lis_desc, (run.cur() - 1) + 64), kid[k].id);
-    }
-    run.flush();
-  }
-}
-
-static __global__ void k_front_reset(EncCtx ctx, int which)
-{
-  if (threadIdx.x == 0 && blockIdx.x == 0)
-    ctx.fcount[which] = 0;
-}
-
-// Single block: list segment of every chunk for the next plane.
-static __global__ void k_plane_end(EncCtx ctx)
-{
-  __shared__ unsigned long long s_start[kMaxBatchChunks + 1];
-  for (int c = threadIdx.x; c < ctx.nchunks; c += blockDim.x)
-    s_start[c] = ctx.chunks[c].ncand;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long acc = 0;
-    for (int c = 0; c < ctx.nchunks; c++) {
-      const unsigned long long v = s_start[c];
-      s_start[c] = acc;
-      acc += v;
+  if (threadIdx.x == 0 && nblocks > 1) {
+    __threadfence();
+    const unsigned gen = __ldcg(&bar[1]);
+    if (atomicAdd(&bar[0], 1u) == nblocks - 1) {
+      atomicExch(&bar[0], 0u);
+      __threadfence();
+      atomicAdd(&bar[1], 1u);
     }
-    s_start[ctx.nchunks] = acc;
-    *ctx.total_roots = acc;
+    else {
+      while (__ldcg(&bar[1]) == gen) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// The LIS part of one plane in ONE launch: the roots' significance bits, then the expansion of the
+// significant sets level by level until the frontier is empty -- the number of rounds is whatever
+// the data needs, decided on the device. m_code_S (src/SPECK3D_INT.cpp:140-212,
+// src/SPECK1D_INT_ENC.cpp:121-160) with every child placed by its D instead of by recursion order.
+// Frontier buffers alternate (round & 1); their counters rotate over three slots so that the one a
+// round appends to was cleared a full round earlier.
+template <class T>
+__global__ void __launch_bounds__(256) k_lis_plane(EncCtx ctx, typename T::Data tree, unsigned* bar)
+{
+  const unsigned nblocks = gridDim.x;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  const unsigned long long tid0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long nroots = *ctx.total_roots;
+  // --- roots ---
+  for (unsigned long long b0 = 0; b0 < nroots; b0 += stride) {   // warp-uniform trip count
+    const unsigned long long i = b0 + tid0;
+    bool sig = false, keep = false;
+    unsigned long long key = 0, pos = 0;
+    node_t nd = 0;
+    unsigned c = 0;
+    if (i < nroots) {
+      key = ctx.rkey[i];
+      c = key_chunk(key);
+      const ChunkDev& ch = ctx.chunks[c];
+      if (ch.plane_live) {
+        pos = ch.lis_base + (ctx.rpos[i] - ctx.rpos[ctx.rstart[c]]);
+        nd = ctx.rnode[i];
+        int p;
+        unsigned d;
+        T::pd(tree, ch, c, nd, p, d);
+        if (p == ch.cur_n) {
+          put_bit(gptr(ch.spk), pos, 1);
+          sig = true;
+        }
+        else
+          keep = ch.next_needed != 0;   // insignificant: stays in its list, same position
+      }
+    }
+    const unsigned long long fs = warp_reserve(&ctx.fcount[0], sig ? 1u : 0u);
+    const unsigned long long cs = warp_reserve(ctx.cand_count, keep ? 1u : 0u);
+    if (sig) {
+      if (fs < ctx.front_cap) {
+        ctx.fnode[0][fs] = nd;
+        ctx.fpos[0][fs] = ((pos + 1) << 10) | c;
+      }
+      else
+        atomicOr(ctx.err, 2u);
+    }
+    if (keep) {
+      if (cs < ctx.cand_cap) {
+        ctx.ckey[cs] = key;
+        ctx.cnode[cs] = nd;
+      }
+      else
+        atomicOr(ctx.err, 1u);
+    }
+  }
+  grid_barrier(bar, nblocks);
+  // --- expansion rounds ---
+  for (int round = 0;; round++) {
+    const int src = round & 1, dst = src ^ 1;
+    unsigned long long* const cnt_src = &ctx.fcount[round % 3];
+    unsigned long long* const cnt_dst = &ctx.fcount[(round + 1) % 3];
+    const unsigned long long count = min(__ldcg(cnt_src), ctx.front_cap);
+    if (count == 0)
+      break;   // the same on every thread of the grid
+    if (tid0 == 0)
+      ctx.fcount[(round + 2) % 3] = 0;   // read a round ago, appended to a round from now
+    for (unsigned long long b0 = 0; b0 < count; b0 += stride) {
+      const unsigned long long i = b0 + tid0;
+      const bool valid = i < count;
+      node_t nd = 0;
+      unsigned c = 0;
+      unsigned long long cur = 0;
+      ChildRec kid[8];
+      int nch = 0, n = 0;
+      bool all_tested = false, next_needed = false;
+      unsigned ncand = 0, nfront = 0;
+      if (valid) {
+        nd = ctx.fnode[src][i];
+        const unsigned long long pc = ctx.fpos[src][i];
+        c = unsigned(pc & 1023u);
+        cur = pc >> 10;
+        const ChunkDev& ch = ctx.chunks[c];
+        n = ch.cur_n;
+        next_needed = ch.next_needed != 0;
+        const int nchf = T::children(tree, ch, c, nd, kid);
+        nch = nchf & 0xff;
+        all_tested = (nchf & 0x100) != 0;   // 2D: last split of the set I
+        int sc = 0;
+        for (int k = 0; k < nch; k++) {   // what will this set append?
+          const bool need = sc != 0 || k != nch - 1 || all_tested;
+          const bool sig = !need || kid[k].p == n;
+          sc += sig;
+          if (kid[k].kind != 0) {
+            if (sig)
+              nfront += kid[k].kind == 2;
+            else
+              ncand += next_needed;
+          }
+        }
+      }
+      unsigned long long fs = warp_reserve(cnt_dst, nfront);
+      unsigned long long cs = warp_reserve(ctx.cand_count, ncand);
+      if (!valid)
+        continue;
+      if (fs + nfront > ctx.front_cap) {
+        atomicOr(ctx.err, 2u);
+        continue;
+      }
+      if (cs + ncand > ctx.cand_cap) {
+        atomicOr(ctx.err, 1u);
+        continue;
+      }
+      const ChunkDev& ch = ctx.chunks[c];
+      BitRun run;
+      run.start(gptr(ch.spk), cur);
+      int sigc = 0;
+      for (int k = 0; k < nch; k++) {
+        const bool need = sigc != 0 || k != nch - 1 || all_tested;
+        const bool sig = !need || kid[k].p == n;
+        if (need)
+          run.push(sig);
+        if (kid[k].kind == 0) {
+          if (sig) {
+            run.push(kid[k].sign);
+            sigc++;
+          }
+        }
+        else if (sig) {
+          sigc++;
+          if (kid[k].kind == 1) {  // all grandchildren are pixels: finish them here
+            int gp[8];
+            unsigned gsign = 0;
+            int ng;
+            if constexpr (T::kHasLeaf8)
+              ng = T::leaf8(tree, ch, kid[k].id, gp, gsign);
+            else {
+              ChildRec g[8];
+              ng = T::children(tree, ch, c, kid[k].id, g) & 0xff;
+              for (int j = 0; j < ng; j++) {
+                gp[j] = g[j].p;
+                gsign |= g[j].sign << j;
+              }
+            }
+            int gs = 0;
+            for (int j = 0; j < ng; j++) {
+              const bool gneed = gs != 0 || j != ng - 1;
+              const bool gsig = !gneed || gp[j] == n;
+              if (gneed)
+                run.push(gsig);
+              if (gsig) {
+                run.push((gsign >> j) & 1u);
+                gs++;
+              }
+            }
+          }
+          else {
+            ctx.fnode[dst][fs] = kid[k].id;
+            ctx.fpos[dst][fs] = (run.cur() << 10) | c;
+            fs++;
+            run.skip(kid[k].d);
+          }
+        }
+        else if (next_needed) {
+          ctx.ckey[cs] = make_key(c, kid[k].lis_desc, (run.cur() - 1) + 64);
+          ctx.cnode[cs] = kid[k].id;
+          cs++;
+        }
+      }
+      run.flush();
+    }
+    grid_barrier(bar, nblocks);
+  }
+}
+
+// After the live sets have been sorted into list order: first root of every chunk, counters cleared.
+static __global__ void k_plane_end(EncCtx ctx, unsigned long long total)
+{
+  for (int c = threadIdx.x; c <= ctx.nchunks; c += blockDim.x) {
+    // first key whose chunk is >= c
+    unsigned long long lo = 0, hi = total;
+    while (lo < hi) {
+      const unsigned long long mid = (lo + hi) >> 1;
+      if (key_chunk(ctx.rkey[mid]) < unsigned(c))
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    ctx.rstart[c] = c == ctx.nchunks ? total : lo;
+  }
+  if (threadIdx.x == 0) {
+    *ctx.total_roots = total;
     *ctx.cand_count = 0;
     ctx.fcount[0] = 0;
     ctx.fcount[1] = 0;
+    ctx.fcount[2] = 0;
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c <= ctx.nchunks; c += blockDim.x)
-    ctx.rstart[c] = s_start[c];
 }
 
 // Seeds the per-chunk coder state once `planes` is known and lays the initial sets into the
@@ -600,6 +684,32 @@ __global__ void k_enc_seed(EncCtx ctx, typename T::Data tree)
 // host driver of the bit-plane loop
 // ---------------------------------------------------------------------------------------------
 
+// One cooperative launch (every CTA resident, so the grid barrier cannot deadlock): as many CTAs of
+// 256 threads as the device holds at once, at most 8 per SM.
+template <class T>
+void launch_lis_plane(const EncCtx& ctx, const typename T::Data& tree, unsigned* d_bar, cudaStream_t st)
+{
+#ifdef SPERR_EMUL
+  LAUNCH(k_lis_plane<T>, dim3(1), dim3(256), 0, st, ctx, tree, d_bar);
+#else
+  static int grid = 0;
+  if (!grid) {
+    int dev = 0, sms = 0, per = 0;
+    RT_CHECK(cudaGetDevice(&dev));
+    RT_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lis_plane<T>, 256, 0));
+    grid = sms * std::max(1, std::min(per, 8));
+  }
+  EncCtx c = ctx;
+  typename T::Data t = tree;
+  void* args[] = {&c, &t, &d_bar};
+  rt::check(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_lis_plane<T>), dim3(unsigned(grid)),
+                                        dim3(256), args, 0, st),
+            "k_lis_plane", __FILE__, __LINE__);
+  rt::launch_counter()++;
+#endif
+}
+
 // `cap_nodes`: upper bound on the number of sets alive / expanded at once over the whole batch.
 // `bits_bound(c, planes)`: upper bound of the payload size of chunk c. `max_depth`: number of
 // expansion rounds that empties any frontier.
@@ -634,8 +744,9 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   unsigned long long* small = w.small.as<unsigned long long>();
   ctx.total_roots = small + 0;
   ctx.cand_count = small + 1;
-  ctx.fcount = small + 2;  // two counters
+  ctx.fcount = small + 5;  // three rotating counters
   ctx.err = reinterpret_cast<unsigned*>(small + 4);
+  unsigned* const d_bar = reinterpret_cast<unsigned*>(small + 2);   // grid barrier of k_lis_plane
   ctx.rstart = small + 8;
   ctx.rkey = w.keys[0].as<unsigned long long>();
   ctx.rnode = w.nodes[0].as<node_t>();
@@ -712,23 +823,19 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
       LAUNCH(k_root_seglen<T>, dim3(rgrid), dim3(256), 0, st, ctx, tree, total_roots);
     exclusive_scan_u32(ctx.rseg, ctx.rpos, total_roots, d_scan_tmp, st);
     LAUNCH(k_plane_begin, dim3(cgrid), dim3(128), 0, st, ctx);
-    if (total_roots) {
-      LAUNCH(k_root_emit<T>, dim3(rgrid), dim3(256), 0, st, ctx, tree, total_roots);
-      for (int d = 0; d < max_depth; d++) {
-        LAUNCH(k_expand<T>, dim3(148 * 8), dim3(256), 0, st, ctx, tree, d & 1);
-        LAUNCH(k_front_reset, dim3(1), dim3(32), 0, st, ctx, d & 1);
-      }
-    }
-    LAUNCH(k_plane_end, dim3(1), dim3(1024), 0, st, ctx);
-    rt::d2h(&total_roots, ctx.total_roots, 8, st);
+    if (total_roots)
+      launch_lis_plane<T>(ctx, tree, d_bar, st);
+    rt::d2h(&total_roots, ctx.cand_count, 8, st);
     rt::sync(st);
-    if (total_roots == 0)
-      continue;  // later planes have no LIS part; k_plane_begin still places LIP / refinement
     if (total_roots > ctx.cand_cap)
       throw std::runtime_error("SPECK list overflow");
-    sort_pairs_u64(ctx.ckey, ctx.rkey, ctx.cnode, ctx.rnode, total_roots, kKeyBits, w.sort_tmp.p,
-                   sort_bytes, st);
+    // later planes may have no LIS part; k_plane_begin still places LIP / refinement
+    if (total_roots)
+      sort_pairs_u64(ctx.ckey, ctx.rkey, ctx.cnode, ctx.rnode, total_roots, kKeyBits, w.sort_tmp.p,
+                     sort_bytes, st);
+    LAUNCH(k_plane_end, dim3(1), dim3(1024), 0, st, ctx, total_roots);
   }
+  (void)max_depth;
 
   // LIP / refinement emission
   rt::ProfScope ps_emit(T::kIsOutlierTree ? "enc1d.lipref_emit" : "enc.lipref_emit", st);
