@@ -168,7 +168,7 @@ int comp_3d_device(const void* d_src, int is_float, size_t dimx, size_t dimy, si
       return -1;  // Set3D coordinates are 16-bit in the reference as well
   if (!g_comp)
     g_comp = &shared_compressor();
-  SrcVol sv{d_src, is_float, dimx, dimy};
+  SrcVol sv{d_src, is_float, dimx, dimy, dimz};
   rt::DBuf& d_out = g_cstream;
   d_out.reserve(size_t(1) << 20);
   std::vector<size_t> lens;

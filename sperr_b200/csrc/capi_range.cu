@@ -133,7 +133,7 @@ int sperr_b200_comp_3d_range_dev(const void* d_box, int is_float, const size_t v
     if (!g_rcomp)
       g_rcomp = &shared_compressor();
     cudaStream_t st = 0;
-    SrcVol sv{d_box, is_float, box_extent[0], box_extent[1]};
+    SrcVol sv{d_box, is_float, box_extent[0], box_extent[1], box_extent[2]};
     g_rout.reserve(size_t(1) << 20);
     std::vector<size_t> l;
     g_rcomp->max_batch = 0;   // shared with the host-pointer API: no leftovers of its overlap hooks

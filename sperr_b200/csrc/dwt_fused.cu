@@ -24,6 +24,9 @@
 // Levels ping-pong through compact per-level boxes (ChunkDev::scratch) so that no CTA reads what
 // another one is overwriting; detail sub-bands are written once to their final place in `coef`.
 #include "kernels.h"
+#ifndef SPERR_EMUL
+#include <cuda.h>
+#endif
 
 namespace sperr_b200 {
 
@@ -317,6 +320,222 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
   if (tid == 0 && s_max)
     atomicMax(const_cast<unsigned long long*>(&ch.max_bits), s_max);
 }
+
+#ifndef SPERR_EMUL
+// ---------------------------------------------------------------------------------------------
+// Level 0 of the forward transform with the source planes staged by TMA.
+//
+// The tile kernel above is bound by the latency of its own phases: load -> barrier -> rows ->
+// barrier -> columns -> barrier -> z, with the loads of a step issued only when the previous step is
+// done. Here the (40 x 40) float boxes of a step are fetched by the TMA unit
+// (cp.async.bulk.tensor, completion on an mbarrier) into one of two staging buffers while the CTA
+// lifts the step before: the tensor map describes the whole source volume, so a box that leaves it
+// is zero-filled by the hardware and a box that leaves the CHUNK brings values of the neighbour;
+// both are replaced when the staged floats are converted into the fp64 tile, because whole-sample
+// mirroring x[-k] = x[k] only ever needs samples that sit in the same box (z: the mirrored plane is
+// fetched instead). Two sample pairs (4 planes) per step keep two CTAs on an SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTNPB = 2;
+constexpr int kTPlanes = 2 * kTNPB;
+constexpr int kTStage = kFI * kFI;                                   // floats of one staged plane
+constexpr size_t kTmaTileBytes = (size_t)kTPlanes * kFI * kFP * sizeof(double);
+constexpr size_t kTmaStageBytes = (size_t)kTPlanes * kTStage * sizeof(float);
+constexpr size_t kTmaSmem = kTmaTileBytes + 2 * kTmaStageBytes + 128;   // + alignment slack
+
+__device__ __forceinline__ unsigned smem_u32(const void* p)
+{
+  return unsigned(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// one (kFI x kFI x 1) box of the float volume: x fastest
+__device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* tm, int x, int y, int z,
+                                               unsigned long long* bar)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <bool FMA>
+__global__ void __launch_bounds__(kFThreads, 2) k_fwd3d_tma(FusedArgs a, const __grid_constant__ CUtensorMap tmap)
+{
+  extern __shared__ unsigned char tma_raw_smem[];
+  unsigned char* const sbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tma_raw_smem) + 127) & ~uintptr_t(127));
+  float* const stage = reinterpret_cast<float*>(sbase);                             // [2][kTPlanes][kFI * kFI]
+  double* const tile = reinterpret_cast<double*>(sbase + 2 * kTmaStageBytes);       // [kTPlanes][kFI][kFP]
+  __shared__ unsigned long long s_max;
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  const ChunkDev& ch = a.chunks[a.ids[blockIdx.y]];
+  if (ch.is_const)
+    return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int bb = blockIdx.x;
+  const int X0 = (bb % a.tiles_x) * kFT;
+  bb /= a.tiles_x;
+  const int Y0 = (bb % a.tiles_y) * kFT;
+  const int seg = bb / a.tiles_y;
+  const int lx = a.lx, ly = a.ly, lz = a.lz;
+  const int ax = lx - lx / 2, ay = ly - ly / 2, az = lz - lz / 2;
+  const int pps = (az + a.zsegs - 1) / a.zsegs;
+  const int k0 = seg * pps, k1 = min(az, k0 + pps);
+  if (k0 >= k1)
+    return;
+  const CdfC k = a.k;
+  const double mean = ch.mean;
+  double* const coef = ch.coef;
+  const int gx0 = int(ch.x0) + X0 - kFH, gy0 = int(ch.y0) + Y0 - kFH, gz0 = int(ch.z0);
+  if (tid == 0) {
+    s_max = 0;
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // step t covers pairs j0 = k0 - 2 + kTNPB t; its planes go to staging buffer t & 1
+  const int nsteps = (k1 + 1 - (k0 - 2)) / kTNPB + 1;
+  auto issue = [&](int t) {   // thread 0
+    const int j0 = k0 - 2 + kTNPB * t;
+    unsigned long long* const bar = &s_bar[t & 1];
+    mbar_expect_tx(bar, unsigned(kTmaStageBytes));
+    float* const dst = stage + (size_t)(t & 1) * kTPlanes * kTStage;
+#pragma unroll
+    for (int p = 0; p < kTPlanes; p++)
+      tma_load_plane(dst + p * kTStage, &tmap, gx0, gy0, gz0 + mirror(2 * j0 + p, lz), bar);
+  };
+  if (tid == 0) {
+    issue(0);
+    if (nsteps > 1)
+      issue(1);
+  }
+
+  // what this thread converts of every plane: tile elements tid, tid + 256, ...; the source of an
+  // element outside the chunk is its mirror image inside the same box
+  constexpr int kPer = (kFI * kFI + kFThreads - 1) / kFThreads;   // 7
+  unsigned short sidx[kPer], ssrc[kPer];
+  for (int s = 0; s < kPer; s++) {
+    const int idx = min(tid + s * kFThreads, kFI * kFI - 1);
+    const int ty = idx / kFI, tx = idx % kFI;
+    sidx[s] = (unsigned short)(ty * kFP + tx);
+    const int mx = mirror(X0 - kFH + tx, lx) - (X0 - kFH), my = mirror(Y0 - kFH + ty, ly) - (Y0 - kFH);
+    ssrc[s] = (unsigned short)(min(max(my, 0), kFI - 1) * kFI + min(max(mx, 0), kFI - 1));
+  }
+
+  // the 4 (x, y) columns whose z lifting this thread runs, and where their outputs go
+  const size_t cnx = ch.nx, cnxy = (size_t)ch.nx * ch.ny;
+  const int x = X0 + lane;
+  const int xo = (x >> 1) + ((x & 1) ? ax : 0);
+  FwdState st[4];
+  size_t dpos[4];
+  long long apos[4];
+  bool live[4];
+  for (int c = 0; c < 4; c++) {
+    st[c] = FwdState{0.0, 0.0, 0.0, 0.0, 0.0};
+    const int y = Y0 + warp + 8 * c;
+    live[c] = x < lx && y < ly;
+    dpos[c] = (size_t)((y >> 1) + ((y & 1) ? ay : 0)) * cnx + xo;
+    apos[c] = ((x | y) & 1) ? -1ll
+                            : (a.apx_off >= 0 ? (long long)(y >> 1) * ax + (x >> 1) : (long long)dpos[c]);
+  }
+  double* const abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : coef;
+  ASSUME_GLOBAL(coef);
+  ASSUME_GLOBAL(abox);
+  const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
+  unsigned long long vmax = 0;
+
+  for (int t = 0; t < nsteps; t++) {
+    const int j0 = k0 - 2 + kTNPB * t;
+    // ---- the step's planes have landed: convert (float - mean, mirrored) into the fp64 tile ----
+    mbar_wait(&s_bar[t & 1], unsigned(t >> 1) & 1u);
+    const float* const sp = stage + (size_t)(t & 1) * kTPlanes * kTStage;
+#pragma unroll
+    for (int p = 0; p < kTPlanes; p++) {
+      double* const tp = tile + (size_t)p * kFI * kFP;
+#pragma unroll
+      for (int s = 0; s < kPer; s++)
+        if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI)
+          tp[sidx[s]] = __dsub_rn(double(sp[p * kTStage + ssrc[s]]), mean);
+    }
+    // every thread's reads of the staging buffer are ordered before the TMA writes that refill it
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0 && t + 2 < nsteps)
+      issue(t + 2);
+    // ---- rows (x) ----
+    if (tid < kTPlanes * kFI)
+      lift_line<false, FMA>(k, tile + (size_t)(tid / kFI) * kFI * kFP + (tid % kFI) * kFP, 1);
+    __syncthreads();
+    // ---- columns (y), only the x positions that are valid after the row pass ----
+    if (tid < kTPlanes * kFT)
+      lift_line<false, FMA>(k, tile + (size_t)(tid / kFT) * kFI * kFP + kFH + tid % kFT, kFP);
+    __syncthreads();
+    // ---- z: streaming state in registers, 4 (x, y) columns per thread ----
+#pragma unroll
+    for (int q = 0; q < kTNPB; q++) {
+      const int kk = j0 + q - 2;   // output pair index
+      const bool emit = kk >= k0 && kk < k1;
+      const double* const te = tile + (size_t)(2 * q) * kFI * kFP + kFH * kFP + kFH + lane;
+      const double* const to = te + kFI * kFP;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int ry = warp + 8 * c;
+        double e2, o3;
+        fwd_step<FMA>(k, st[c], te[ry * kFP], to[ry * kFP], e2, o3);
+        if (emit && live[c]) {
+          if (apos[c] >= 0) {
+            abox[(size_t)kk * aplane + apos[c]] = e2;
+            if (a.last) {
+              const unsigned long long b = abs_bits(e2);
+              vmax = b > vmax ? b : vmax;
+            }
+          }
+          else {
+            coef[(size_t)kk * cnxy + dpos[c]] = e2;
+            const unsigned long long b = abs_bits(e2);
+            vmax = b > vmax ? b : vmax;
+          }
+          if (kk < lz / 2) {
+            coef[(size_t)(az + kk) * cnxy + dpos[c]] = o3;
+            const unsigned long long b = abs_bits(o3);
+            vmax = b > vmax ? b : vmax;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long t2 = __shfl_xor_sync(0xffffffffu, vmax, o);
+    vmax = t2 > vmax ? t2 : vmax;
+  }
+  if (lane == 0 && vmax)
+    atomicMax(&s_max, vmax);
+  __syncthreads();
+  if (tid == 0 && s_max)
+    atomicMax(const_cast<unsigned long long*>(&ch.max_bits), s_max);
+}
+#endif   // !SPERR_EMUL
 
 // OUT 0: fp64 box in scratch (levels > 0) or, at level 0, raw fp64 values into the volume `vol`,
 //     1: destination volume (+ outlier corrector, + mean, float or double),
@@ -614,6 +833,46 @@ static void fused_grid(FusedArgs& a, int nids, dim3& grid)
 
 CdfC cdf_constants();
 
+#ifndef SPERR_EMUL
+// Tensor map of the whole float source volume (x fastest), boxes of kFI x kFI x 1 samples.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_volume_tmap(const SrcVol& src, CUtensorMap& tm)
+{
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      cudaGetLastError();
+  }
+  if (!fn)
+    return false;
+  const cuuint64_t gdim[3] = {src.vx, src.vy, src.vz};
+  const cuuint64_t gstr[2] = {src.vx * 4ull, src.vx * src.vy * 4ull};
+  const cuuint32_t box[3] = {kFI, kFI, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(src.ptr), gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// TMA needs a 16-byte aligned base and row pitch; mirroring inside the box needs the box to reach
+// 4 samples past an edge it straddles (any level-0 box of at least 9 samples does).
+static bool fwd_tma_usable(const SrcVol& src, const FusedArgs& a)
+{
+  if (std::getenv("SPERR_B200_NO_TMA"))
+    return false;
+  return src.is_float && src.vz > 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 15) == 0 && src.vx % 4 == 0 &&
+         a.lx >= 2 * kFH + 1 && a.ly >= 2 * kFH + 1 && a.lz >= 2 * kFH + 1;
+}
+#endif
+
 static void fused_attrs()
 {
 #ifndef SPERR_EMUL
@@ -633,6 +892,8 @@ static void fused_attrs()
   RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_inv3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmaSmem)));
+  RT_CHECK(cudaFuncSetAttribute(k_fwd3d_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmaSmem)));
   done = true;
 #endif
 }
@@ -646,8 +907,7 @@ void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const
   const int L = can_use_dyadic(nx, ny, nz);
   long long off[8];
   fused_scratch_elems(nx, ny, nz, off);
-  FusedArgs a;
-  std::memset(&a, 0, sizeof(a));
+  FusedArgs a{};
   a.chunks = d_chunks;
   a.ids = d_ids;
   a.vol = src;
@@ -662,6 +922,18 @@ void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const
     dim3 grid;
     fused_grid(a, nids, grid);
     const int which = l > 0 ? 2 : (src.is_float ? 0 : 1);
+#ifndef SPERR_EMUL
+    if (which == 0 && fwd_tma_usable(src, a)) {
+      CUtensorMap tm;
+      if (make_volume_tmap(src, tm)) {
+        if (a.k.fma)
+          LAUNCH((k_fwd3d_tma<true>), grid, dim3(kFThreads), kTmaSmem, st, a, tm);
+        else
+          LAUNCH((k_fwd3d_tma<false>), grid, dim3(kFThreads), kTmaSmem, st, a, tm);
+        continue;
+      }
+    }
+#endif
 #define SPERR_FWD(S, F) LAUNCH((k_fwd3d<S, F>), grid, dim3(kFThreads), kFusedSmem, st, a)
     if (a.k.fma) {
       if (which == 2) SPERR_FWD(2, true);
@@ -689,8 +961,7 @@ void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chu
   const int L = can_use_dyadic(nx, ny, nz);
   long long off[8];
   fused_scratch_elems(nx, ny, nz, off);
-  FusedArgs a;
-  std::memset(&a, 0, sizeof(a));
+  FusedArgs a{};
   a.chunks = d_chunks;
   a.ids = d_ids;
   a.vol = vol;

@@ -13,6 +13,7 @@ struct SrcVol {
   const void* ptr;
   int is_float;
   unsigned long long vx, vy;   // row length and number of rows per plane
+  unsigned long long vz = 0;   // number of planes (0: unknown; only the TMA path of the forward transform needs it)
 };
 
 struct CdfC {

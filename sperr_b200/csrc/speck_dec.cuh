@@ -131,6 +131,12 @@ __device__ __forceinline__ unsigned long long warp_incl_scan(unsigned long long 
 
 // ---- LIP part ---------------------------------------------------------------------------------
 
+__device__ __forceinline__ uint4 lip_load(const DecChunk& d, unsigned long long j)
+{
+  const uint4* const p = reinterpret_cast<const uint4*>(gptr(d.lip) + j);
+  return d.R > 1 ? __ldcg(p) : *p;
+}
+
 static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,7 +241,8 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
   const unsigned long long w0 = per_warp * warp, w1 = min((words + 3) & ~3ull, w0 + per_warp);
   unsigned long long cnt = 0;
   for (unsigned long long j = w0 + 4ull * lane; j < w1; j += 128) {
-    const uint4 m4 = *reinterpret_cast<const uint4*>(gptr(d.lip) + j);
+    // (.cg in cluster mode: other SMs set these bits, with atomics that live in L2)
+    const uint4 m4 = lip_load(d, j);
     cnt += __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w);
   }
   for (int o = 16; o; o >>= 1)
@@ -255,7 +262,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
     const unsigned long long j = j0 + 4ull * lane;
     uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
     if (j < w1)
-      m4 = *reinterpret_cast<const uint4*>(gptr(d.lip) + j);
+      m4 = lip_load(d, j);
     unsigned mw[4] = {m4.x, m4.y, m4.z, m4.w};
     const unsigned c4 = unsigned(__popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w));
     unsigned inc = c4;

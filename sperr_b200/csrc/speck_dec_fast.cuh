@@ -145,6 +145,15 @@ __device__ __forceinline__ void mb_st(T* p, T v)
       (F).prof[k] += (unsigned long long)(F_CLOCK() - f_t0);   \
   } while (0)
 
+// List entries may have been written by another CTA of the cluster: read them from L2 (every cluster
+// barrier is preceded by a __threadfence, so they are there). A lone CTA must NOT do that: its own
+// plain stores are only guaranteed to be visible to the CTA's ordinary loads (measured on B200: an
+// ld.global.cg right after a __syncthreads can miss a store of the same CTA).
+__device__ __forceinline__ node_t f_list_load(const FastSmem& F, const node_t* p)
+{
+  return F.R > 1 ? __ldcg(p) : *p;
+}
+
 // ---- geometry of power-of-two trees -----------------------------------------------------------
 // A set at depth j is the box (ix, iy, iz) of the grid with 2^min(j, D_a) cells along axis a; it is
 // stored as (j << 32 | linear index), its list index is sum_a min(j, D_a).
@@ -744,7 +753,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         t &= t - 1;
         const unsigned q = tid * 8 + b;
         if (r < T) {
-          const node_t nd = CL ? __ldcg(&list[i0r + r]) : list[i0r + r];
+          const node_t nd = f_list_load(F, &list[i0r + r]);
           if (f_bit(F, q)) {
             sigs[ng] = nd;
             sigq[ng++] = uint16_t(q + 1);
@@ -1255,7 +1264,8 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
       const unsigned nst = min(unsigned(kFRoots), cnt - first);
       __syncthreads();
       for (unsigned t = tid; t < nst; t += kDecThreads)
-        F.rs_node[t] = iphase ? ((unsigned long long)(0x100 | F.iset) << 32) : __ldcg(gptr(d.lis) + F.off[lis] + first + t);
+        F.rs_node[t] = iphase ? ((unsigned long long)(0x100 | F.iset) << 32)
+                              : f_list_load(F, gptr(d.lis) + F.off[lis] + first + t);
       for (unsigned t = tid; t < unsigned(kFRoots / 32); t += kDecThreads)
         F.rs_gone[t] = 0;
       if (tid == 0) {
@@ -1266,7 +1276,11 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
       const long long f_tw = F_CLOCK();
       if (tid == 0) {
         if (d.kind == 1)
+#ifdef SPERR_OLD_WALK1D
+          f_walk<1>(d, S, F);
+#else
           f_walk1d(d, S, F);
+#endif
         else if (d.kind == 2)
           f_walk<2>(d, S, F);
         else

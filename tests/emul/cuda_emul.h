@@ -243,7 +243,10 @@ inline T __ldg(const T* p)
 template <typename T>
 inline T __ldcg(const T* p)
 {
-  return __atomic_load_n(p, __ATOMIC_RELAXED);
+  if constexpr (sizeof(T) <= 8)
+    return __atomic_load_n(p, __ATOMIC_RELAXED);
+  else
+    return *p;
 }
 template <typename T>
 inline void __stcg(T* p, T v)
