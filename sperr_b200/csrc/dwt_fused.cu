@@ -151,9 +151,31 @@ struct FusedArgs {
   CdfC k;
 };
 
-constexpr int kNPB = 3;                 // sample pairs (2 planes each) a CTA transforms per step
+constexpr int kNPB = 2;                 // sample pairs (2 planes each) a CTA transforms per step
 constexpr int kPlanes = 2 * kNPB;
 constexpr size_t kFusedSmem = (size_t)kPlanes * kFI * kFP * sizeof(double);
+// inverse transform: the low / high band inputs of the NEXT step are fetched with cp.async while
+// the CTA lifts the current one; every thread stages exactly the values it consumes itself
+constexpr int kInvPer = (kFI * kFI + kFThreads - 1) / kFThreads;   // 7 tile elements per thread and plane
+constexpr size_t kInvStage = (size_t)kNPB * 2 * kInvPer * kFThreads;   // doubles
+constexpr size_t kInvSmem = kFusedSmem + kInvStage * sizeof(double);
+
+// 8-byte asynchronous copy global -> shared (LDGSTS); a plain copy under the CPU emulator
+__device__ __forceinline__ void async_copy8(double* dst, const double* src)
+{
+#ifdef SPERR_EMUL
+  *dst = *src;
+#else
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src)
+               : "memory");
+#endif
+}
+__device__ __forceinline__ void async_commit_wait_all()
+{
+#ifndef SPERR_EMUL
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
 
 __device__ __forceinline__ unsigned long long abs_bits(double v)
 {
@@ -356,17 +378,23 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
+  // bounded: a transfer that never completes (a bad tensor map) must fail the launch, not hang it
+  for (unsigned spins = 0;; spins++) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done)
+      return;
+    if (spins > (1u << 24))
+      __trap();
+  }
 }
 // one (kFI x kFI x 1) box of the float volume: x fastest
 __device__ __forceinline__ void tma_load_plane(void* dst, const CUtensorMap* tm, int x, int y, int z,
@@ -614,6 +642,29 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
   const bool fl_row = ep_lane < 4 * kPlanes && Y0 + ep_warp + 8 * fl_c < ly;
   const unsigned long long fl_i0 = (unsigned long long)(Y0 + ep_warp + 8 * fl_c) * cnx + X0;
 
+  // stage the z-phase inputs of a step: pair q -> (low band sample, high band sample) of my elements
+  double* const stg = tile + (size_t)kPlanes * kFI * kFP;   // [kNPB][2][kPer][kFThreads]
+  auto stage_step = [&](int j0) {
+#pragma unroll
+    for (int q = 0; q < kNPB; q++) {
+      const int j = j0 + q;
+      const int ze = mirror(2 * j, lz) >> 1, zo = az + (mirror(2 * j + 1, lz) >> 1);
+      const double* const pe = coef + (size_t)ze * cnxy;
+      const double* const po = coef + (size_t)zo * cnxy;
+      const double* const pa = abox + (size_t)ze * aplane;
+#pragma unroll
+      for (int s = 0; s < kPer; s++) {
+        if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
+          const double* const pz = ((apx >> s) & 1u) ? pa : pe;
+          ASSUME_GLOBAL(pz);
+          async_copy8(stg + ((size_t)(q * 2 + 0) * kPer + s) * kFThreads + tid, pz + eoff[s]);
+          async_copy8(stg + ((size_t)(q * 2 + 1) * kPer + s) * kFThreads + tid, po + coff[s]);
+        }
+      }
+    }
+  };
+  stage_step(k0 - 2);
+
   for (int j0 = k0 - 2; j0 <= k1 + 1; j0 += kNPB) {
     unsigned flags = 0;
     if (OUT == 1 && obits) {
@@ -643,35 +694,26 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     }
 #endif
     // ---- z: pair j = (low-band plane mirror(2j) / 2, high-band plane az + mirror(2j + 1) / 2) ----
+    async_commit_wait_all();   // my own copies of this step have landed (nobody else reads them)
 #pragma unroll
     for (int q = 0; q < kNPB; q++) {
-      const int j = j0 + q;
-      const int ze = mirror(2 * j, lz) >> 1, zo = az + (mirror(2 * j + 1, lz) >> 1);
-      const double* const pe = coef + (size_t)ze * cnxy;
-      const double* const po = coef + (size_t)zo * cnxy;
-      const double* const pa = abox + (size_t)ze * aplane;
       double* const t0 = tile + (size_t)(2 * q) * kFI * kFP;
-      double ev[kPer], ov[kPer];
 #pragma unroll
       for (int s = 0; s < kPer; s++) {
         if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
-          const double* const pz = ((apx >> s) & 1u) ? pa : pe;
-          ASSUME_GLOBAL(pz);
-          ev[s] = pz[eoff[s]];
-          ov[s] = po[coff[s]];
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < kPer; s++) {
-        if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
+          const double ev = stg[((size_t)(q * 2 + 0) * kPer + s) * kFThreads + tid];
+          const double ov = stg[((size_t)(q * 2 + 1) * kPer + s) * kFThreads + tid];
           double x0, x1;
-          inv_step<FMA>(k, st[s], ev[s], ov[s], x0, x1);
+          inv_step<FMA>(k, st[s], ev, ov, x0, x1);
           t0[sidx[s]] = x0;
           t0[kFI * kFP + sidx[s]] = x1;
         }
       }
     }
     __syncthreads();
+    // the staging slots have been read: fetch the next step's inputs while this one is lifted
+    if (j0 + kNPB <= k1 + 1)
+      stage_step(j0 + kNPB);
     // planes 2 (j0 - 2) .. of the rebuilt box sit in the tile; pair q is wanted iff k0 <= j0+q-2 < k1
     // ---- columns (y) over all x of the tile, then rows (x) over the valid y ----
     if (tid < kPlanes * kFI)
@@ -883,15 +925,16 @@ static void fused_attrs()
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  const int smi = int(kInvSmem);
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmaSmem)));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmaSmem)));
   done = true;
@@ -978,7 +1021,7 @@ void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chu
     dim3 grid;
     fused_grid(a, nids, grid);
     const int which = (l > 0 || mode == 0) ? 0 : (mode == 1 ? 1 : 2);
-#define SPERR_INV(O, F) LAUNCH((k_inv3d<O, F>), grid, dim3(kFThreads), kFusedSmem, st, a)
+#define SPERR_INV(O, F) LAUNCH((k_inv3d<O, F>), grid, dim3(kFThreads), kInvSmem, st, a)
     if (a.k.fma) {
       if (which == 0) SPERR_INV(0, true);
       else if (which == 1) SPERR_INV(1, true);

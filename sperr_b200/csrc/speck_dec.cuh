@@ -136,13 +136,27 @@ __device__ __forceinline__ uint4 lip_load(const DecChunk& d, unsigned long long 
   const uint4* const p = reinterpret_cast<const uint4*>(gptr(d.lip) + j);
   return d.R > 1 ? __ldcg(p) : *p;
 }
+__device__ __forceinline__ uint32_t lip_res_load(const DecChunk& d, const uint32_t* p)
+{
+  return d.R > 1 ? __ldcg(p) : *p;
+}
 
-static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
+// Cluster mode: what the CTAs of a stream's cluster tell each other during the LIP pass (global
+// memory; written before a cluster barrier, read after it).
+struct LipBox {
+  unsigned long long cnt[8], sig[8], endpos;
+};
+
+// R, rank, lb: the stream's cluster (R = 1: one CTA does it all). The stream side -- a scan over
+// the bit string -- is the leader's; the mask side is split over the 32 R warps of the cluster.
+static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int R = 1, int rank = 0,
+                                    LipBox* lb = nullptr)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long K = S.klip;
   if (K == 0)
-    return;
+    return;   // the same on every CTA of the cluster
+  if (rank == 0) {
   for (unsigned long long i = tid; i < (K + 31) / 32 + 1; i += kDecThreads) {
     gptr(d.sigarr)[i] = 0;
     gptr(d.signarr)[i] = 0;
@@ -233,12 +247,20 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
     base_pos += 32ull * kDecThreads;
     __syncthreads();
   }
+  }   // rank == 0
+  if (R > 1) {
+    if (rank == 0 && tid == 0)
+      __stcg(gptr(&lb->endpos), S.endpos);
+    cluster_sync();   // the token arrays are complete (and visible: the barrier fences)
+  }
 
   // mask side: the k-th LIP pixel in raster order owns token k. A lane takes four mask words at a
   // time (one 128-bit load; the mask arrays are 16-byte aligned and zero padded).
   const unsigned long long words = (d.n + 31) / 32;
-  const unsigned long long per_warp = ((words + kDecWarps - 1) / kDecWarps + 127) / 128 * 128;
-  const unsigned long long w0 = per_warp * warp, w1 = min((words + 3) & ~3ull, w0 + per_warp);
+  const unsigned long long nwarps = (unsigned long long)kDecWarps * R;
+  const unsigned long long per_warp = ((words + nwarps - 1) / nwarps + 127) / 128 * 128;
+  const unsigned long long w0 = per_warp * ((unsigned long long)rank * kDecWarps + warp),
+                           w1 = min((words + 3) & ~3ull, w0 + per_warp);
   unsigned long long cnt = 0;
   for (unsigned long long j = w0 + 4ull * lane; j < w1; j += 128) {
     // (.cg in cluster mode: other SMs set these bits, with atomics that live in L2)
@@ -254,9 +276,18 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
     const unsigned long long v = S.wtot[lane];
     const unsigned long long inc = warp_incl_scan(v, lane);
     S.wtot[lane] = inc - v;
+    if (lane == 31)
+      S.wtot2[0] = inc;   // LIP pixels in this CTA's part of the mask
   }
   __syncthreads();
   unsigned long long run = S.wtot[warp];
+  if (R > 1) {   // ... after those of the lower ranks
+    if (tid == 0)
+      __stcg(gptr(&lb->cnt[rank]), S.wtot2[0]);
+    cluster_sync();
+    for (int r2 = 0; r2 < rank; r2++)
+      run += __ldcg(gptr(&lb->cnt[r2]));
+  }
   unsigned long long nsig = 0;
   for (unsigned long long j0 = w0; j0 < w1; j0 += 128) {
     const unsigned long long j = j0 + 4ull * lane;
@@ -286,12 +317,12 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
       const unsigned long long wi = k >> 5;
       const unsigned sh = unsigned(k & 31);
       k += c;
-      unsigned sg = __funnelshift_r(gptr(d.sigarr)[wi], gptr(d.sigarr)[wi + 1], sh);
+      unsigned sg = __funnelshift_r(lip_res_load(d, gptr(d.sigarr) + wi), lip_res_load(d, gptr(d.sigarr) + wi + 1), sh);
       if (c < 32)
         sg &= (1u << c) - 1u;
       if (sg == 0)
         continue;
-      const unsigned sn = __funnelshift_r(gptr(d.signarr)[wi], gptr(d.signarr)[wi + 1], sh);
+      const unsigned sn = __funnelshift_r(lip_res_load(d, gptr(d.signarr) + wi), lip_res_load(d, gptr(d.signarr) + wi + 1), sh);
       unsigned keep = m;
       int t = 0;
       while (m) {
@@ -316,6 +347,25 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane)
   if (lane == 0)
     S.wtot[warp] = nsig;
   __syncthreads();
+  if (R > 1) {
+    if (tid == 0) {
+      unsigned long long t = 0;
+      for (int i = 0; i < kDecWarps; i++)
+        t += S.wtot[i];
+      __stcg(gptr(&lb->sig[rank]), t);
+    }
+    cluster_sync();
+    if (tid == 0) {
+      unsigned long long t = 0;
+      for (int r2 = 0; r2 < R; r2++)
+        t += __ldcg(gptr(&lb->sig[r2]));
+      S.klip -= t;
+      S.knew += t;
+      S.pos = __ldcg(gptr(&lb->endpos));
+    }
+    __syncthreads();
+    return;
+  }
   if (tid == 0) {
     unsigned long long t = 0;
     for (int i = 0; i < kDecWarps; i++)

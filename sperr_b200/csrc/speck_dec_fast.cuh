@@ -57,6 +57,7 @@ struct ClusterBox {
   unsigned marks[kFMaxR], surv[kFMaxR], app[kFMaxR][2], errs[kFMaxR];
   unsigned long long dklip[kFMaxR], dknew[kFMaxR], newpos[kFMaxR];
   uint16_t exits[kFMaxR][kFEntry];   // window position a chain entering at offset e leaves the window at
+  LipBox lip;
 };
 
 struct FastSmem {
@@ -1405,7 +1406,6 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     }
   }
   __syncthreads();
-  // (the LIP is empty in the first plane: nothing to do before its LIS part)
   for (;;) {
     if (CL)
       f_state_sync(d, S, F);
@@ -1413,6 +1413,12 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     if (!F.go)
       break;
     const int n = F.plane;
+    {   // LIP part: the leader tokenises the bit string, every CTA matches its share of the mask
+      F_TIC();
+      dec_lip_pass(d, S, n, CL ? R : 1, rank, CL ? &d.box->lip : nullptr);
+      __syncthreads();
+      F_TOC(F, 0);
+    }
     dec_lis_chains<CL>(d, S, F, n);
     __syncthreads();
     if (rank == 0) {
@@ -1425,15 +1431,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
         F.plane = n - 1;
       }
       __syncthreads();
-      if (F.go) {
-        F_TIC();
-        dec_lip_pass(d, S, n - 1);
-        __syncthreads();
-        F_TOC(F, 0);
-      }
     }
-    else if (!CL)
-      break;   // not reached: a lone CTA is its own leader
   }
   if (rank != 0)
     return;

@@ -418,15 +418,23 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks)
   __syncthreads();
   if (threadIdx.x == 0 && nblocks > 1) {
     __threadfence();
-    const unsigned gen = __ldcg(&bar[1]);
+    volatile unsigned* const vbar = bar;   // volatile: re-read from L2 on every turn of the spin
+    const unsigned gen = vbar[1];
     if (atomicAdd(&bar[0], 1u) == nblocks - 1) {
       atomicExch(&bar[0], 0u);
       __threadfence();
       atomicAdd(&bar[1], 1u);
     }
     else {
-      while (__ldcg(&bar[1]) == gen) {
+      unsigned spins = 0;
+      while (vbar[1] == gen) {
+#if !defined(SPERR_EMUL)
+        __nanosleep(64);
+        if (++spins > (1u << 26))   // seconds: a CTA is missing, fail the launch instead of hanging
+          __trap();
+#endif
       }
+      (void)spins;
     }
     __threadfence();
   }
