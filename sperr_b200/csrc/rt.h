@@ -83,6 +83,7 @@ __device__ __forceinline__ unsigned cluster_rank()
 }
 __device__ __forceinline__ void cluster_sync()
 {
+  __syncwarp();   // the .aligned barrier wants the whole warp
   __threadfence();
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }

@@ -398,6 +398,13 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
                      "%.2f  Mcycles\n",
                      c, w.h[c].n, w.h[c].prof[0] * 1e-6, w.h[c].prof[1] * 1e-6, w.h[c].prof[6],
                      w.h[c].prof[2] * 1e-6, w.h[c].prof[3] * 1e-6, w.h[c].prof[4] * 1e-6);
+  if (std::getenv("SPERR_B200_DECTRACE"))
+    for (int c = 0; c < nj && c < 2; c++)
+      if (w.h[c].pow2 && !w.h[c].skip)
+        for (int n = w.h[c].planes - 1; n >= 0 && n < kMaxPlanes; n--)
+          std::fprintf(stderr, "dectrace job %d plane %d: lip %llu %llx | chains %llu %llx | walk %llu %llx\n", c, n,
+                       w.h[c].dbg[n][0][0], w.h[c].dbg[n][0][1], w.h[c].dbg[n][1][0], w.h[c].dbg[n][1][1],
+                       w.h[c].dbg[n][2][0], w.h[c].dbg[n][2][1]);
   for (int c = 0; c < nj; c++)
     if (w.h[c].err)
       throw std::runtime_error("SPECK decoder: list capacity exceeded (corrupt stream?)");

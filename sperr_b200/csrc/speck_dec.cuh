@@ -27,6 +27,17 @@
 
 namespace sperr_b200 {
 
+// CTA barrier of the decoders. Much of their control flow is `if (tid == 0) { long serial part }`
+// followed by a barrier; measured on B200 (compute-sanitizer synccheck: "divergent thread(s) in
+// warp" at such a barrier, and decoder state that only made sense if thread 0 was one barrier
+// behind its warp) the warp is not always reconverged when it gets there. __syncwarp() makes the
+// reconvergence explicit.
+__device__ __forceinline__ void block_sync()
+{
+  __syncwarp();
+  __syncthreads();
+}
+
 constexpr int kDecThreads = 1024;
 constexpr int kDecWarps = kDecThreads / 32;
 
@@ -161,7 +172,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
     gptr(d.sigarr)[i] = 0;
     gptr(d.signarr)[i] = 0;
   }
-  __syncthreads();
+  block_sync();
 
   // stream side: tokenise until K pixels have been seen
   unsigned long long base_pos = S.pos, ord_base = 0;
@@ -186,7 +197,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
       S.fA[warp] = fA;
       S.fB[warp] = fB;
     }
-    __syncthreads();
+    block_sync();
     if (warp == 0) {
       unsigned gA = S.fA[lane], gB = S.fB[lane];
       for (int o = 1; o < 32; o <<= 1) {
@@ -206,7 +217,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
         S.tile_fB = gB;
       }
     }
-    __syncthreads();
+    block_sync();
     // exclusive prefix of this thread = (warps before) then (lanes before)
     unsigned eA = __shfl_up_sync(0xffffffffu, fA, 1), eB = __shfl_up_sync(0xffffffffu, fB, 1);
     if (lane == 0) {
@@ -245,7 +256,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
     ord_base += tile >> 1;
     state_in = tile & 1u;
     base_pos += 32ull * kDecThreads;
-    __syncthreads();
+    block_sync();
   }
   }   // rank == 0
   if (R > 1) {
@@ -271,7 +282,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
     cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0)
     S.wtot[warp] = cnt;
-  __syncthreads();
+  block_sync();
   if (warp == 0) {
     const unsigned long long v = S.wtot[lane];
     const unsigned long long inc = warp_incl_scan(v, lane);
@@ -279,7 +290,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
     if (lane == 31)
       S.wtot2[0] = inc;   // LIP pixels in this CTA's part of the mask
   }
-  __syncthreads();
+  block_sync();
   unsigned long long run = S.wtot[warp];
   if (R > 1) {   // ... after those of the lower ranks
     if (tid == 0)
@@ -343,10 +354,10 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
   }
   for (int o = 16; o; o >>= 1)
     nsig += __shfl_xor_sync(0xffffffffu, nsig, o);
-  __syncthreads();
+  block_sync();
   if (lane == 0)
     S.wtot[warp] = nsig;
-  __syncthreads();
+  block_sync();
   if (R > 1) {
     if (tid == 0) {
       unsigned long long t = 0;
@@ -363,7 +374,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
       S.knew += t;
       S.pos = __ldcg(gptr(&lb->endpos));
     }
-    __syncthreads();
+    block_sync();
     return;
   }
   if (tid == 0) {
@@ -374,7 +385,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
     S.knew += t;
     S.pos = S.endpos;
   }
-  __syncthreads();
+  block_sync();
 }
 
 // ---- end of a plane: where its refinement bits are (src/SPECK_INT.cpp:165-228, 359-469) ---------
@@ -542,16 +553,16 @@ __global__ void __launch_bounds__(kDecThreads) k_speck_decode(DecChunk* chunks, 
       gptr(d.lis_cnt)[lis]++;
     }
   }
-  __syncthreads();
+  block_sync();
   int n = d.planes - 1;
   for (int bp = 0; bp < d.planes; bp++, n--) {
     dec_lip_pass(d, S, n);
-    __syncthreads();   // every thread has read the LIP population before the walker changes it
+    block_sync();   // every thread has read the LIP population before the walker changes it
     if (tid == 0) {
       dec_lis_walk<T>(d, tree, c, S, stack, n);
       s_go = (!d.err && dec_plane_end(d, S, n)) ? 1 : 0;
     }
-    __syncthreads();
+    block_sync();
     if (!s_go)
       return;
   }

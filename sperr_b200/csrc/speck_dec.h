@@ -57,6 +57,9 @@ struct DecChunk {
   // clock64() totals of the fast decoder's phases (thread 0): 0 LIP pass, 1 window staging + body
   // tables, 2 token chains, 3 token expansion, 4 tree walker, 6 windows built
   unsigned long long prof[8];
+  // debugging aid (SPERR_B200_DECPROF): per plane (position, LIP population, new significant, sets in the
+  // lists) after the LIP part, the chain phases and the walker
+  unsigned long long dbg[kMaxPlanes][3][2];
 };
 
 // One integer stream to decode.

@@ -215,10 +215,10 @@ __device__ __forceinline__ unsigned long long f_block_scan(FastSmem& F, unsigned
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long inc = warp_incl_scan(v, lane);
-  __syncthreads();   // previous users of wsum / scan_total are done
+  block_sync();   // previous users of wsum / scan_total are done
   if (lane == 31)
     F.wsum[warp] = inc;
-  __syncthreads();
+  block_sync();
   if (warp == 0) {
     const unsigned long long w = F.wsum[lane];
     const unsigned long long winc = warp_incl_scan(w, lane);
@@ -226,7 +226,7 @@ __device__ __forceinline__ unsigned long long f_block_scan(FastSmem& F, unsigned
     if (lane == 31)
       F.scan_total = winc;
   }
-  __syncthreads();
+  block_sync();
   return F.wsum[warp] + inc - v;
 }
 
@@ -296,7 +296,7 @@ static __device__ void f_build_window(const DecChunk& d, FastSmem& F, unsigned l
 {
   F_TIC();
   f_build_window_impl(d, F, base, kinds, after_one);
-  __syncthreads();
+  block_sync();
   F_TOC(F, 1);
   if (threadIdx.x == 0)
     F.prof[6]++;
@@ -305,7 +305,7 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
                                            int kinds, bool after_one)
 {
   const int tid = threadIdx.x;
-  __syncthreads();   // every reader of the previous window is done
+  block_sync();   // every reader of the previous window is done
   const unsigned long long w0 = base >> 5;
   const int nbits = kinds == 0 ? kFW + 64 : (kinds == 1 ? kFW + 256 : kFBits);
   for (int i = tid; i < nbits / 32 + 3; i += kDecThreads) {
@@ -314,7 +314,7 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
   }
   if (tid == 0)
     F.boff = unsigned(base & 31);
-  __syncthreads();
+  block_sync();
   const int J = F.J;
   const int nchA = f_nch(F, J - 1);
   const int nA = kinds == 0 ? kFW + 8 : (kinds == 1 ? kFW + 144 : kFBodyA);
@@ -328,12 +328,12 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
       F.bodyA[q] = uint8_t(f_pixels(F, q, nchA, sm, gm));
     }
   }
-  __syncthreads();
+  block_sync();
   for (int q = tid; q < nA - 1; q += kDecThreads)
     F.stepA[q] = f_bit(F, q) ? uint8_t((1u + F.bodyA[q + 1]) | 0x80u) : uint8_t(1);
   if (kinds == 0)
     return;
-  __syncthreads();
+  block_sync();
   const int nchB = f_nch(F, J - 2);
   const int nB = kinds == 1 ? kFW + 8 : kFBodyB;
 #pragma unroll
@@ -351,17 +351,17 @@ static __device__ void f_build_window_impl(const DecChunk& d, FastSmem& F, unsig
     F.bodyB[q] = uint8_t(pos - q);
   }
   if (kinds == 1 && after_one) {
-    __syncthreads();
+    block_sync();
     for (int q = tid; q < nB - 1; q += kDecThreads)
       F.stepB[q] = f_bit(F, q) ? uint16_t((1u + F.bodyB[q + 1]) | 0x8000u) : uint16_t(1);
     return;
   }
   if (kinds == 1)
     return;
-  __syncthreads();
+  block_sync();
   for (int q = tid; q < nB - 1; q += kDecThreads)
     F.stepB[q] = f_bit(F, q) ? uint16_t((1u + F.bodyB[q + 1]) | 0x8000u) : uint16_t(1);
-  __syncthreads();
+  block_sync();
   const int nchC = f_nch(F, J - 3);
 #pragma unroll
   for (int it = 0; it < (kFW + 8 + kDecThreads - 1) / kDecThreads; it++) {
@@ -489,7 +489,7 @@ static __device__ void f_expand_level(DecChunk& d, FastSmem& F, int j, const uns
           dst[b++] = kid[k];
       }
     }
-    __syncthreads();
+    block_sync();
     if (tid == 0) {
       if (!ok)
         F.err |= 1u;
@@ -499,7 +499,7 @@ static __device__ void f_expand_level(DecChunk& d, FastSmem& F, int j, const uns
       else
         F.cnt[cl] += toti;
     }
-    __syncthreads();
+    block_sync();
   }
 }
 
@@ -515,7 +515,7 @@ static __device__ void f_expand_A(DecChunk& d, DecShared& S, FastSmem& F, const 
     S.klip += F.scan_total & 0xffffffffull;
     S.knew += F.scan_total >> 32;
   }
-  __syncthreads();
+  block_sync();
 }
 
 // Expands the tokens of a round. kind: size class of the tokens in the entry queue
@@ -534,7 +534,7 @@ static __device__ void f_expand_round(DecChunk& d, DecShared& S, FastSmem& F, in
     for (unsigned b0 = 0; b0 < nb; b0 += kFSlice) {
       if (threadIdx.x == 0)
         F.nqa = 0;
-      __syncthreads();
+      block_sync();
       f_expand_level<uint8_t, CL>(d, F, J - 2, F.qb_node + b0, F.qb_pos + b0, min(unsigned(kFSlice), nb - b0),
                                   F.bodyA, F.qa_node, F.qa_pos, &F.nqa);
       if (F.err)
@@ -547,7 +547,7 @@ static __device__ void f_expand_round(DecChunk& d, DecShared& S, FastSmem& F, in
   for (unsigned c0 = 0; c0 < nc; c0 += kFSlice) {
     if (threadIdx.x == 0)
       F.nqb = 0;
-    __syncthreads();
+    block_sync();
     f_expand_level<uint8_t, CL>(d, F, J - 3, F.qc_node + c0, F.qc_pos + c0, min(unsigned(kFSlice), nc - c0),
                                 F.bodyB, F.qb_node, F.qb_pos, &F.nqb);
     if (F.err)
@@ -556,7 +556,7 @@ static __device__ void f_expand_round(DecChunk& d, DecShared& S, FastSmem& F, in
     for (unsigned b0 = 0; b0 < nb; b0 += kFSlice) {
       if (threadIdx.x == 0)
         F.nqa = 0;
-      __syncthreads();
+      block_sync();
       f_expand_level<uint8_t, CL>(d, F, J - 2, F.qb_node + b0, F.qb_pos + b0, min(unsigned(kFSlice), nb - b0),
                                   F.bodyA, F.qa_node, F.qa_pos, &F.nqa);
       if (F.err)
@@ -616,7 +616,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
       F.flag[0] = 0;
       F.app_cnt[0] = F.app_cnt[1] = 0;
     }
-    __syncthreads();
+    block_sync();
     // pointer doubling: table r + 1 = 2^(r+1) tokens ahead; until every entry offset has left
     int src = 0, have4 = 0, have8 = 0;
     for (int r = 0; r < 14; r++) {
@@ -635,7 +635,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
             F.flag[r % 3] = 1;
         }
       }
-      __syncthreads();
+      block_sync();
       src = dst;
       have4 |= r == 3;
       have8 |= r == 7;
@@ -652,14 +652,14 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
       uint16_t* const xtab = reinterpret_cast<uint16_t*>(F.qa_node);   // idle until the expansion
       for (int e = tid; e < rank * kFEntry; e += kDecThreads)
         xtab[e] = mb_ld(&box->exits[0][0] + e);
-      __syncthreads();
+      block_sync();
       if (tid == 0) {
         unsigned e = 0;
         for (int s2 = 0; s2 < rank; s2++)
           e = unsigned(xtab[s2 * kFEntry + e]) - unsigned(kFW);
         F.entry = e;
       }
-      __syncthreads();
+      block_sync();
       entry = F.entry;
     }
     const unsigned exitpos = fin[entry];
@@ -677,7 +677,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         F.anc256[n++] = uint16_t(entry);
       F.n256 = n;
     }
-    __syncthreads();
+    block_sync();
     if (have4) {
       if (tid < int(F.n256)) {
         unsigned p2 = F.anc256[tid];
@@ -694,7 +694,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
       F.anc16[0] = F.anc256[0];
       F.n16 = 1;
     }
-    __syncthreads();
+    block_sync();
     if (tid < int(F.n16)) {
       unsigned p2 = F.anc16[tid];
       for (int u = 0; u < 16 && p2 < unsigned(kFW); u++) {
@@ -702,7 +702,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         p2 += f_token_len(F, kind, p2);
       }
     }
-    __syncthreads();
+    block_sync();
     // rank of my marks = index of the root they belong to
     const unsigned mb = (F.mark[tid >> 2] >> ((tid & 3) * 8)) & 0xffu;
     unsigned long long ex = f_block_scan(F, (unsigned long long)__popc(mb));
@@ -732,7 +732,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         F.sumT = sum;
         F.rstar = last;
       }
-      __syncthreads();
+      block_sync();
       T = F.Tr;
       i0r = F.i0r;
       sumT = F.sumT;
@@ -787,7 +787,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         F.wsurv_r = wsurv + before;
         F.sum_surv = sum;
       }
-      __syncthreads();
+      block_sync();
       wsurv_r = F.wsurv_r;
       sum_surv = F.sum_surv;
     }
@@ -813,9 +813,9 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         else if (kind == 1) F.nqb = cntq;
         else F.nqc = cntq;
       }
-      __syncthreads();
+      block_sync();
       f_expand_round<CL>(d, S, F, kind, n_plane);
-      __syncthreads();
+      block_sync();
     }
     if (tid == 0)
       F.prof[3] += (unsigned long long)(F_CLOCK() - f_te);
@@ -857,7 +857,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
           for (unsigned t = tid; t < mine; t += kDecThreads)
             gptr(d.lis)[at + before + t] = from[t];
         }
-        __syncthreads();   // every thread has read F.cnt[cl]
+        block_sync();   // every thread has read F.cnt[cl]
         if (tid == 0) {
           if (!fits)
             F.err |= 1u;
@@ -877,17 +877,17 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         S.pos = mb_ld(&box->newpos[rstar]);
         F.err |= e;
       }
-      __syncthreads();
+      block_sync();
       if (F.err)
         return;   // the same on every rank
     }
     i0 += sumT;
     wsurv += sum_surv;
-    __syncthreads();
+    block_sync();
   }
   if (tid == 0)
     F.cnt[lis] = wsurv;
-  __syncthreads();
+  block_sync();
 }
 
 // ---- phase B: larger sets, one thread walks the top of the tree ----------------------------------
@@ -1213,7 +1213,7 @@ static __device__ void f_compact_roots(FastSmem& F, node_t* list)
       list[w0 + total + unsigned(ex)] = F.rs_node[t];
     total += unsigned(F.scan_total);
   }
-  __syncthreads();
+  block_sync();
   if (tid == 0)
     F.wk_w = w0 + total;
 }
@@ -1250,7 +1250,7 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
       F.wk_cnt = cnt;
       F.wk_depth = -1;
     }
-    __syncthreads();
+    block_sync();
     for (;;) {
       if (!have_window || F.wk_q + 1 >= unsigned(kFW)) {
         f_build_window(d, F, S.pos, 2, false);
@@ -1263,7 +1263,7 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
       // stage the next roots of the list (the walker never reads the list itself)
       const unsigned first = F.wk_i;
       const unsigned nst = min(unsigned(kFRoots), cnt - first);
-      __syncthreads();
+      block_sync();
       for (unsigned t = tid; t < nst; t += kDecThreads)
         F.rs_node[t] = iphase ? ((unsigned long long)(0x100 | F.iset) << 32)
                               : f_list_load(F, gptr(d.lis) + F.off[lis] + first + t);
@@ -1273,7 +1273,7 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
         F.rs_first = first;
         F.rs_cnt = nst;
       }
-      __syncthreads();
+      block_sync();
       const long long f_tw = F_CLOCK();
       if (tid == 0) {
         if (d.kind == 1)
@@ -1287,15 +1287,15 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
         else
           f_walk<0>(d, S, F);
       }
-      __syncthreads();
+      block_sync();
       if (!iphase)
         f_compact_roots(F, gptr(d.lis) + F.off[lis]);
-      __syncthreads();
+      block_sync();
       const long long f_te = F_CLOCK();
       if (tid == 0)
         F.prof[4] += (unsigned long long)(f_te - f_tw);
       f_expand_round<false>(d, S, F, 2, n_plane);
-      __syncthreads();
+      block_sync();
       if (tid == 0)
         F.prof[3] += (unsigned long long)(F_CLOCK() - f_te);
       if (F.err)
@@ -1305,7 +1305,7 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
     }
     if (tid == 0 && !iphase)
       F.cnt[lis] = F.wk_w;   // survivors; the sets created in this plane went to deeper lists
-    __syncthreads();
+    block_sync();
   }
 }
 
@@ -1369,7 +1369,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
   static_assert(sizeof(DecChunk) % 8 == 0, "DecChunk is copied in 8-byte words");
   for (unsigned i = tid; i < sizeof(DecChunk) / 8; i += blockDim.x)
     reinterpret_cast<unsigned long long*>(&sd)[i] = reinterpret_cast<const unsigned long long*>(&chunks[c])[i];
-  __syncthreads();
+  block_sync();
   DecChunk& d = sd;
   if (tid == 0) {
     S.pos = 0;
@@ -1396,7 +1396,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
       F.cnt[l] = 0;
   }
   f_build_luts(F);
-  __syncthreads();
+  block_sync();
   if (tid == 0 && rank == 0) {
     for (int r = 0; r < d.nroots; r++) {
       const unsigned long long nd = d.roots[r];
@@ -1405,32 +1405,44 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
       F.cnt[lis]++;
     }
   }
-  __syncthreads();
+  block_sync();
   for (;;) {
     if (CL)
       f_state_sync(d, S, F);
-    __syncthreads();
+    block_sync();
     if (!F.go)
       break;
     const int n = F.plane;
     {   // LIP part: the leader tokenises the bit string, every CTA matches its share of the mask
       F_TIC();
       dec_lip_pass(d, S, n, CL ? R : 1, rank, CL ? &d.box->lip : nullptr);
-      __syncthreads();
+      block_sync();
       F_TOC(F, 0);
     }
+    auto trace = [&](int stage) {   // debugging aid, leader only
+      if (tid == 0 && rank == 0 && n < kMaxPlanes) {
+        unsigned long long sets = 0;
+        for (int l = 0; l < d.nlis; l++)
+          sets += F.cnt[l];
+        d.dbg[n][stage][0] = S.pos;
+        d.dbg[n][stage][1] = (S.klip << 40) ^ (S.knew << 20) ^ sets;
+      }
+    };
+    trace(0);
     dec_lis_chains<CL>(d, S, F, n);
-    __syncthreads();
+    block_sync();
+    trace(1);
     if (rank == 0) {
       if (!F.err)
         dec_lis_walk(d, S, F, n);
-      __syncthreads();
+      block_sync();
+      trace(2);
       if (tid == 0) {
         const bool more = !F.err && dec_plane_end(d, S, n);
         F.go = (more && n > 0) ? 1 : 0;
         F.plane = n - 1;
       }
-      __syncthreads();
+      block_sync();
     }
   }
   if (rank != 0)
@@ -1440,7 +1452,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     for (int k = 0; k < 8; k++)
       d.prof[k] = F.prof[k];
   }
-  __syncthreads();
+  block_sync();
   for (unsigned i = tid; i < sizeof(DecChunk) / 8; i += blockDim.x)
     reinterpret_cast<unsigned long long*>(&chunks[c])[i] = reinterpret_cast<const unsigned long long*>(&sd)[i];
 }
