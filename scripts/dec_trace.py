@@ -5,7 +5,8 @@ os.environ["SPERR_B200_DECTRACE"] = "1"
 os.environ.setdefault("SPERR_B200_DEC_CLUSTER", "1")
 import numpy as np
 import gpulib, refs
-lib = gpulib.load(sys.argv[1] if len(sys.argv) > 1 else "cuda")
+a = sys.argv[1] if len(sys.argv) > 1 else "cuda"
+lib = gpulib.load(a) if a in ("cuda", "emul") else gpulib.Lib(a)
 oracle = refs.oracle()
 dims = (64, 64, 64)
 v = refs.synthetic_field(dims, seed=5)

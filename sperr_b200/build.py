@@ -49,7 +49,7 @@ def _headers_mtime():
 
 
 def _compile(nvcc, src, obj, extra=()):
-    cmd = [nvcc] + NVCC_FLAGS + list(extra) + ["-x", "cu", "-c", src, "-o", obj]
+    cmd = [nvcc] + NVCC_FLAGS + list(extra) + os.environ.get("SPERR_B200_EXTRA_NVCC", "").split() + ["-x", "cu", "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout[-4000:], r.stderr[-4000:]))

@@ -405,6 +405,21 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
           std::fprintf(stderr, "dectrace job %d plane %d: lip %llu %llx | chains %llu %llx | walk %llu %llx\n", c, n,
                        w.h[c].dbg[n][0][0], w.h[c].dbg[n][0][1], w.h[c].dbg[n][1][0], w.h[c].dbg[n][1][1],
                        w.h[c].dbg[n][2][0], w.h[c].dbg[n][2][1]);
+  if (std::getenv("SPERR_B200_DECTRACE"))
+    for (int c = 0; c < nj && c < 2; c++)
+      if (w.h[c].pow2 && !w.h[c].skip) {
+        for (int pi = 0; pi < 2; pi++)
+          for (int sgi = 0; sgi < 3; sgi++) {
+            std::fprintf(stderr, "dectrace job %d plane#%d stage %d lists:", c, pi, sgi);
+            for (int l = 0; l < w.h[c].nlis && l < 32; l++)
+              std::fprintf(stderr, " %u", w.h[c].dbgl[pi][sgi][l]);
+            std::fprintf(stderr, "\n");
+          }
+        for (unsigned k = 0; k < w.h[c].dbgw_n && k < 16; k++)
+          std::fprintf(stderr, "dectrace job %d walk: plane %u depth %u roots %u visited %u survivors %u lis %u q %u staged %u\n",
+                       c, w.h[c].dbgw[k][0], w.h[c].dbgw[k][1], w.h[c].dbgw[k][2], w.h[c].dbgw[k][3],
+                       w.h[c].dbgw[k][4], w.h[c].dbgw[k][5], w.h[c].dbgw[k][6], w.h[c].dbgw[k][7]);
+      }
   for (int c = 0; c < nj; c++)
     if (w.h[c].err)
       throw std::runtime_error("SPECK decoder: list capacity exceeded (corrupt stream?)");

@@ -60,6 +60,9 @@ struct DecChunk {
   // debugging aid (SPERR_B200_DECPROF): per plane (position, LIP population, new significant, sets in the
   // lists) after the LIP part, the chain phases and the walker
   unsigned long long dbg[kMaxPlanes][3][2];
+  unsigned dbgl[2][3][32];   // the first two planes: sets per list at the three stages
+  unsigned dbgw[16][8];      // the first walker list visits: plane, depth, roots, visited, survivors, ...
+  unsigned dbgw_n, dbg_pad;
 };
 
 // One integer stream to decode.

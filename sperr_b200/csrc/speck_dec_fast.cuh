@@ -211,7 +211,8 @@ __device__ __forceinline__ unsigned f_peek(const FastSmem& F, unsigned q)
 }
 
 // packed three-field block scan (21 bits per field); returns the exclusive prefix, total in F
-__device__ __forceinline__ unsigned long long f_block_scan(FastSmem& F, unsigned long long v)
+// (a real call, for the reason given at f_compact_roots)
+__noinline__ static __device__ unsigned long long f_block_scan(FastSmem& F, unsigned long long v)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long inc = warp_incl_scan(v, lane);
@@ -1199,11 +1200,20 @@ static __device__ void f_walk1d(DecChunk& d, DecShared& S, FastSmem& F)
 }
 
 // Survivors of the staged roots [rs_first, wk_i) keep their order: list[wk_w ...] (whole CTA).
-static __device__ void f_compact_roots(FastSmem& F, node_t* list)
+// __noinline__: measured on B200 with nvcc 12.9 -- inlined into the walker loop at ptxas -O3, the
+// first compaction of a decode came back with zero survivors (the same source is correct at
+// -Xptxas -O1, in the CPU emulation, and as a real call; volatile loads of the inputs change
+// nothing). The call costs nothing next to the three barriers inside.
+__noinline__ static __device__ void f_compact_roots(FastSmem& F, node_t* list)
 {
   const int tid = threadIdx.x;
+#ifdef SPERR_DEC_VOLATILE
+  const unsigned n = *(volatile unsigned*)&F.wk_i - *(volatile unsigned*)&F.rs_first;
+  const unsigned w0 = *(volatile unsigned*)&F.wk_w;
+#else
   const unsigned n = F.wk_i - F.rs_first;   // roots visited in this round
   const unsigned w0 = F.wk_w;
+#endif
   unsigned total = 0;
   for (unsigned b0 = 0; b0 < n; b0 += kDecThreads) {
     const unsigned t = b0 + tid;
@@ -1231,6 +1241,9 @@ static __device__ void dec_lis_chains(DecChunk& d, DecShared& S, FastSmem& F, in
 }
 
 // ... and the lists of the larger sets (one CTA)
+#ifdef SPERR_DEC_FORCEINLINE
+__forceinline__
+#endif
 static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int n_plane)
 {
   const int tid = threadIdx.x;
@@ -1303,6 +1316,11 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
       if (F.wk_depth < 0 && F.wk_i == cnt)
         break;
     }
+    if (tid == 0 && d.dbgw_n < 16) {
+      unsigned* const r = d.dbgw[d.dbgw_n++];
+      r[0] = unsigned(n_plane); r[1] = unsigned(lj); r[2] = cnt; r[3] = F.wk_i; r[4] = F.wk_w;
+      r[5] = unsigned(lis); r[6] = F.wk_q; r[7] = F.rs_cnt;
+    }
     if (tid == 0 && !iphase)
       F.cnt[lis] = F.wk_w;   // survivors; the sets created in this plane went to deeper lists
     block_sync();
@@ -1361,6 +1379,13 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
   if (chunks[c].skip || chunks[c].planes == 0 || !chunks[c].pow2 || chunks[c].R != R)
     return;   // the same for every CTA of a cluster
   const int tid = threadIdx.x;
+#ifdef SPERR_DEC_ZERO_SMEM
+  for (unsigned i = tid; i < sizeof(FastSmem) / 4; i += blockDim.x)
+    reinterpret_cast<unsigned*>(&F)[i] = 0;
+  for (unsigned i = tid; i < sizeof(DecShared) / 4; i += blockDim.x)
+    reinterpret_cast<unsigned*>(&S)[i] = 0;
+  block_sync();
+#endif
   // The job descriptor is worked on in shared memory and written back at the end. Read through
   // the global struct, every pointer in it (bits, pl, lip, lis, ...) has to be fetched again after
   // each global store, which may alias it: one more dependent load in front of nearly every access
@@ -1426,6 +1451,10 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
           sets += F.cnt[l];
         d.dbg[n][stage][0] = S.pos;
         d.dbg[n][stage][1] = (S.klip << 40) ^ (S.knew << 20) ^ sets;
+        const int pi = d.planes - 1 - n;
+        if (pi < 2)
+          for (int l = 0; l < d.nlis && l < 32; l++)
+            d.dbgl[pi][stage][l] = F.cnt[l];
       }
     };
     trace(0);

@@ -26,6 +26,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static thread_local
 #define __align__(n) alignas(n)
