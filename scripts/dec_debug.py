@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import gpulib, refs, cases
 so = sys.argv[1] if len(sys.argv) > 1 else gpulib.CUDA_SO
-lib = gpulib.Lib(so)
+lib = gpulib.load(so) if so in ("cuda", "emul") else gpulib.Lib(so)
 oracle = refs.oracle()
 todo = [((64, 32, 16), (64, 32, 16), 3, 1e-4), ((64, 64, 64), (64, 64, 64), 1, 3.0), ((32, 32, 32), (16, 16, 16), 3, 1e-3),
         ((128, 128, 128), (128, 128, 128), 3, 1e-3)]

@@ -20,13 +20,33 @@ using namespace sperr_b200;
 
 namespace {
 
-std::mutex& g_mutex = shared_api_mutex();  // one job at a time per process: the work buffers are shared
-Compressor* g_comp = nullptr;
-// grow-only device staging of the host-pointer entry points (input volume, container, output volume)
-rt::DBuf g_in, g_stream, g_vol, g_cstream;
+class SerialWorker;
+// Per-device state of the entry points (the device is the one the calling host thread has selected):
+// pipelines, grow-only device staging of the host-pointer API (input volume, container, output
+// volume), the copy stream and its helper thread. One job at a time per device (shared_api_mutex).
+struct DevState {
+  Compressor* comp = nullptr;
+  Decompressor* decomp = nullptr;
+  rt::DBuf in, stream, vol, cstream;
 #ifndef SPERR_EMUL
-cudaStream_t g_copy_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
 #endif
+  SerialWorker* d2h_worker = nullptr;
+};
+DevState& dev_state()
+{
+  static DevState s[rt::kMaxDevices];
+  return s[rt::cur_dev()];
+}
+#define g_mutex (shared_api_mutex())
+#define g_comp (dev_state().comp)
+#define g_decomp (dev_state().decomp)
+#define g_in (dev_state().in)
+#define g_stream (dev_state().stream)
+#define g_vol (dev_state().vol)
+#define g_cstream (dev_state().cstream)
+#define g_copy_stream (dev_state().copy_stream)
+#define g_d2h_worker (dev_state().d2h_worker)
 
 bool device_ok()
 {
@@ -110,7 +130,6 @@ class SerialWorker {
   bool stop_ = false;
   std::exception_ptr err_;
 };
-SerialWorker* g_d2h_worker = nullptr;
 
 // wall-clock phases of the host-pointer entry points, printed when SPERR_B200_TIMING is set
 struct PhaseTimer {
@@ -263,7 +282,6 @@ bool parse_container(const uint8_t* p, size_t len, ContainerInfo& ci)
   return true;
 }
 
-Decompressor* g_decomp = nullptr;
 
 void decomp_3d_device(const uint8_t* h_stream, const uint8_t* d_stream, const ContainerInfo& ci,
                       int output_float, void* d_dst, cudaStream_t st)

@@ -17,10 +17,21 @@ using namespace sperr_b200;
 
 namespace {
 
-std::mutex& g_rmutex = shared_api_mutex();
-Compressor* g_rcomp = nullptr;
-Decompressor* g_rdecomp = nullptr;
-rt::DBuf g_rout, g_rstream;
+struct RangeState {   // per device, like the pipelines it uses
+  Compressor* comp = nullptr;
+  Decompressor* decomp = nullptr;
+  rt::DBuf out, stream;
+};
+RangeState& range_state()
+{
+  static RangeState s[rt::kMaxDevices];
+  return s[rt::cur_dev()];
+}
+#define g_rmutex (shared_api_mutex())
+#define g_rcomp (range_state().comp)
+#define g_rdecomp (range_state().decomp)
+#define g_rout (range_state().out)
+#define g_rstream (range_state().stream)
 
 template <typename F>
 int guarded(F&& f)

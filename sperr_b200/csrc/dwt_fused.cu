@@ -918,8 +918,8 @@ static bool fwd_tma_usable(const SrcVol& src, const FusedArgs& a)
 static void fused_attrs()
 {
 #ifndef SPERR_EMUL
-  static bool done = false;
-  if (done)
+  static rt::OncePerDevice once;
+  if (!once.first())
     return;
   const int sm = int(kFusedSmem);
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -937,7 +937,6 @@ static void fused_attrs()
   RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmaSmem)));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmaSmem)));
-  done = true;
 #endif
 }
 

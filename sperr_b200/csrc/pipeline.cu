@@ -27,22 +27,34 @@ struct Piece {
 
 }  // namespace
 
-// One pipeline pair and one lock per process: the host-pointer API, the device-pointer API and the
-// chunk-range API all reuse the same grow-only work buffers (tens of GB for a 1024^3 call).
+// One pipeline pair and one lock per DEVICE: the host-pointer API, the device-pointer API and the
+// chunk-range API all reuse the same grow-only work buffers (tens of GB for a 1024^3 call) of the
+// device the calling thread has selected.
 Compressor& shared_compressor()
 {
-  static Compressor* p = new Compressor();
-  return *p;
+  static Compressor* p[rt::kMaxDevices] = {};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> l(mu);
+  Compressor*& c = p[rt::cur_dev()];
+  if (!c)
+    c = new Compressor();
+  return *c;
 }
 Decompressor& shared_decompressor()
 {
-  static Decompressor* p = new Decompressor();
-  return *p;
+  static Decompressor* p[rt::kMaxDevices] = {};
+  static std::mutex mu;
+  std::lock_guard<std::mutex> l(mu);
+  Decompressor*& c = p[rt::cur_dev()];
+  if (!c)
+    c = new Decompressor();
+  return *c;
 }
+// One job at a time per DEVICE: the work buffers of a device are shared by all entry points.
 std::mutex& shared_api_mutex()
 {
-  static std::mutex* m = new std::mutex();
-  return *m;
+  static std::mutex* m = new std::mutex[rt::kMaxDevices];
+  return m[rt::cur_dev()];
 }
 
 // One block column per piece; bytes are copied with a grid-stride loop.

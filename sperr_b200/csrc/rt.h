@@ -83,13 +83,44 @@ __device__ __forceinline__ unsigned cluster_rank()
 }
 __device__ __forceinline__ void cluster_sync()
 {
-  __syncwarp();   // the .aligned barrier wants the whole warp
+  // NOT the .aligned form: that one requires every thread of a warp to execute the same barrier
+  // instruction together, which the decoders' control flow (long single-thread parts between
+  // barriers) does not guarantee after optimisation -- measured on B200: with .aligned the cluster
+  // decode of a 128^3 chunk hangs, without it it is bit-exact.
   __threadfence();
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
 #endif
 
 namespace rt {
+
+// The CUDA device of the calling host thread (0 under the emulator). Everything the library keeps
+// between calls -- work buffers, helper streams, per-kernel attributes -- is kept per device, so
+// that host threads driving different GPUs never share state.
+constexpr int kMaxDevices = 16;
+inline int cur_dev()
+{
+#ifndef SPERR_EMUL
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess)
+    d = 0;
+  return d < kMaxDevices ? d : 0;
+#else
+  return 0;
+#endif
+}
+// true exactly once per device: guards one-time per-device set-up (cudaFuncSetAttribute, ...)
+struct OncePerDevice {
+  bool done[kMaxDevices] = {};
+  bool first()
+  {
+    const int d = cur_dev();
+    if (done[d])
+      return false;
+    done[d] = true;
+    return true;
+  }
+};
 
 // number of kernels of this library launched so far (bench.py reports the count per step)
 inline std::atomic<unsigned long long>& launch_counter()

@@ -352,10 +352,12 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
       LAUNCH(k_speck_decode<DecTree1D>, dim3(nj), dim3(kDecThreads), 0, st, dch, DecTree1D::Data{0});
     if (any_fast) {
 #ifndef SPERR_EMUL
-      static bool attr_done = false;
-      static cudaStream_t side = nullptr;
-      static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-      if (!attr_done) {
+      static rt::OncePerDevice once;
+      static cudaStream_t sides[rt::kMaxDevices] = {};
+      static cudaEvent_t evs_fork[rt::kMaxDevices] = {}, evs_join[rt::kMaxDevices] = {};
+      cudaStream_t& side = sides[rt::cur_dev()];
+      cudaEvent_t &ev_fork = evs_fork[rt::cur_dev()], &ev_join = evs_join[rt::cur_dev()];
+      if (once.first()) {
         RT_CHECK(cudaFuncSetAttribute(k_speck_decode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(sizeof(FastSmem))));
         RT_CHECK(cudaFuncSetAttribute(k_speck_decode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -363,7 +365,6 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
         RT_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
         RT_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         RT_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-        attr_done = true;
       }
       const bool fork = any_cl && any_single;
       if (fork) {   // the single-CTA streams run beside the clusters

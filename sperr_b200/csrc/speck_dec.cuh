@@ -31,11 +31,16 @@ namespace sperr_b200 {
 // followed by a barrier; measured on B200 (compute-sanitizer synccheck: "divergent thread(s) in
 // warp" at such a barrier, and decoder state that only made sense if thread 0 was one barrier
 // behind its warp) the warp is not always reconverged when it gets there. __syncwarp() makes the
-// reconvergence explicit.
+// reconvergence explicit ... and is not enough; what is, is a barrier that does not need it:
 __device__ __forceinline__ void block_sync()
 {
-  __syncwarp();
+#if defined(SPERR_EMUL)
   __syncthreads();
+#else
+  // barrier.sync WITHOUT .aligned (what __syncthreads() compiles to is the aligned form): threads of
+  // a warp may arrive separately
+  asm volatile("barrier.sync 0;" ::: "memory");
+#endif
 }
 
 constexpr int kDecThreads = 1024;

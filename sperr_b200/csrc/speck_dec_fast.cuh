@@ -211,8 +211,7 @@ __device__ __forceinline__ unsigned f_peek(const FastSmem& F, unsigned q)
 }
 
 // packed three-field block scan (21 bits per field); returns the exclusive prefix, total in F
-// (a real call, for the reason given at f_compact_roots)
-__noinline__ static __device__ unsigned long long f_block_scan(FastSmem& F, unsigned long long v)
+__device__ __forceinline__ unsigned long long f_block_scan(FastSmem& F, unsigned long long v)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long inc = warp_incl_scan(v, lane);
@@ -1200,11 +1199,7 @@ static __device__ void f_walk1d(DecChunk& d, DecShared& S, FastSmem& F)
 }
 
 // Survivors of the staged roots [rs_first, wk_i) keep their order: list[wk_w ...] (whole CTA).
-// __noinline__: measured on B200 with nvcc 12.9 -- inlined into the walker loop at ptxas -O3, the
-// first compaction of a decode came back with zero survivors (the same source is correct at
-// -Xptxas -O1, in the CPU emulation, and as a real call; volatile loads of the inputs change
-// nothing). The call costs nothing next to the three barriers inside.
-__noinline__ static __device__ void f_compact_roots(FastSmem& F, node_t* list)
+static __device__ void f_compact_roots(FastSmem& F, node_t* list)
 {
   const int tid = threadIdx.x;
 #ifdef SPERR_DEC_VOLATILE
@@ -1440,7 +1435,14 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     const int n = F.plane;
     {   // LIP part: the leader tokenises the bit string, every CTA matches its share of the mask
       F_TIC();
+#ifdef SPERR_CL_LIP_LEADER
+      if (rank == 0)
+        dec_lip_pass(d, S, n);
+      if (CL)
+        f_state_sync(d, S, F);
+#else
       dec_lip_pass(d, S, n, CL ? R : 1, rank, CL ? &d.box->lip : nullptr);
+#endif
       block_sync();
       F_TOC(F, 0);
     }

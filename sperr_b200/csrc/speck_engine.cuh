@@ -700,7 +700,8 @@ void launch_lis_plane(const EncCtx& ctx, const typename T::Data& tree, unsigned*
 #ifdef SPERR_EMUL
   LAUNCH(k_lis_plane<T>, dim3(1), dim3(256), 0, st, ctx, tree, d_bar);
 #else
-  static int grid = 0;
+  static int grids[rt::kMaxDevices] = {};
+  int& grid = grids[rt::cur_dev()];
   if (!grid) {
     int dev = 0, sms = 0, per = 0;
     RT_CHECK(cudaGetDevice(&dev));

@@ -613,14 +613,13 @@ static int pick_tw(int len)
 static void ensure_smem_attr()
 {
 #ifndef SPERR_EMUL
-  static bool done = false;
-  if (!done) {
+  static rt::OncePerDevice once;
+  if (once.first()) {
     const int big = 220 * 1024;
     RT_CHECK(cudaFuncSetAttribute(k_dwt_col<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     RT_CHECK(cudaFuncSetAttribute(k_dwt_col<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     RT_CHECK(cudaFuncSetAttribute(k_dwt_x<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     RT_CHECK(cudaFuncSetAttribute(k_dwt_x<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    done = true;
   }
 #endif
 }
