@@ -392,6 +392,15 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
     return 2;
   if (mode < 1 || mode > 3)
     return 2;
+  {   // several GPUs (SPERR_B200_DEVICES): the chunks of this call are spread over them
+    const std::vector<int> devs = multi_devices();
+    if (!devs.empty() && dimx && dimy && dimz) {
+      const size_t vol[3] = {dimx, dimy, dimz}, ck[3] = {chunk_x, chunk_y, chunk_z};
+      const int rc = comp_3d_multi(src, is_float, vol, ck, mode, quality, devs, dst, dst_len);
+      if (rc != -2)
+        return rc;
+    }
+  }
   std::lock_guard<std::mutex> lock(g_mutex);
   return guarded([&] {
     cudaStream_t st = 0;
@@ -525,6 +534,14 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
   (void)nthreads;
   if (*dst != nullptr)
     return 1;
+  {
+    const std::vector<int> devs = multi_devices();
+    if (!devs.empty() && src && src_len >= 14) {
+      const int rc = decomp_3d_multi(src, src_len, output_float, devs, dimx, dimy, dimz, dst);
+      if (rc != -2)
+        return rc;
+    }
+  }
   std::lock_guard<std::mutex> lock(g_mutex);
   return guarded([&] {
     cudaStream_t st = 0;

@@ -151,14 +151,21 @@ struct FusedArgs {
   CdfC k;
 };
 
-constexpr int kNPB = 2;                 // sample pairs (2 planes each) a CTA transforms per step
+// SPERR_INV_ASYNC=1: the inverse transform stages the z-phase inputs of the next step with cp.async
+// (needs two pairs per step to keep two CTAs on an SM). Measured on B200 (1024^3): 13.97 ms against
+// 12.69 ms for the direct-load kernel with three pairs per step -- the smaller step costs more
+// barriers per sample than the overlap saves -- so it is off.
+#ifndef SPERR_INV_ASYNC
+#define SPERR_INV_ASYNC 0
+#endif
+constexpr int kNPB = SPERR_INV_ASYNC ? 2 : 3;   // sample pairs (2 planes each) a CTA transforms per step
 constexpr int kPlanes = 2 * kNPB;
 constexpr size_t kFusedSmem = (size_t)kPlanes * kFI * kFP * sizeof(double);
 // inverse transform: the low / high band inputs of the NEXT step are fetched with cp.async while
 // the CTA lifts the current one; every thread stages exactly the values it consumes itself
 constexpr int kInvPer = (kFI * kFI + kFThreads - 1) / kFThreads;   // 7 tile elements per thread and plane
 constexpr size_t kInvStage = (size_t)kNPB * 2 * kInvPer * kFThreads;   // doubles
-constexpr size_t kInvSmem = kFusedSmem + kInvStage * sizeof(double);
+constexpr size_t kInvSmem = kFusedSmem + (SPERR_INV_ASYNC ? kInvStage * sizeof(double) : 0);
 
 // 8-byte asynchronous copy global -> shared (LDGSTS); a plain copy under the CPU emulator
 __device__ __forceinline__ void async_copy8(double* dst, const double* src)
@@ -663,7 +670,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
       }
     }
   };
-  stage_step(k0 - 2);
+  if (SPERR_INV_ASYNC)
+    stage_step(k0 - 2);
 
   for (int j0 = k0 - 2; j0 <= k1 + 1; j0 += kNPB) {
     unsigned flags = 0;
@@ -694,17 +702,40 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     }
 #endif
     // ---- z: pair j = (low-band plane mirror(2j) / 2, high-band plane az + mirror(2j + 1) / 2) ----
-    async_commit_wait_all();   // my own copies of this step have landed (nobody else reads them)
+    if (SPERR_INV_ASYNC)
+      async_commit_wait_all();   // my own copies of this step have landed (nobody else reads them)
 #pragma unroll
     for (int q = 0; q < kNPB; q++) {
       double* const t0 = tile + (size_t)(2 * q) * kFI * kFP;
+      double ev[kPer], ov[kPer];
+      if (SPERR_INV_ASYNC) {
+#pragma unroll
+        for (int s = 0; s < kPer; s++)
+          if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
+            ev[s] = stg[((size_t)(q * 2 + 0) * kPer + s) * kFThreads + tid];
+            ov[s] = stg[((size_t)(q * 2 + 1) * kPer + s) * kFThreads + tid];
+          }
+      }
+      else {   // straight from global memory: pair j = (low-band plane mirror(2j) / 2, high-band plane az + mirror(2j + 1) / 2)
+        const int j = j0 + q;
+        const int ze = mirror(2 * j, lz) >> 1, zo = az + (mirror(2 * j + 1, lz) >> 1);
+        const double* const pe = coef + (size_t)ze * cnxy;
+        const double* const po = coef + (size_t)zo * cnxy;
+        const double* const pa = abox + (size_t)ze * aplane;
+#pragma unroll
+        for (int s = 0; s < kPer; s++)
+          if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
+            const double* const pz = ((apx >> s) & 1u) ? pa : pe;
+            ASSUME_GLOBAL(pz);
+            ev[s] = pz[eoff[s]];
+            ov[s] = po[coff[s]];
+          }
+      }
 #pragma unroll
       for (int s = 0; s < kPer; s++) {
         if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
-          const double ev = stg[((size_t)(q * 2 + 0) * kPer + s) * kFThreads + tid];
-          const double ov = stg[((size_t)(q * 2 + 1) * kPer + s) * kFThreads + tid];
           double x0, x1;
-          inv_step<FMA>(k, st[s], ev, ov, x0, x1);
+          inv_step<FMA>(k, st[s], ev[s], ov[s], x0, x1);
           t0[sidx[s]] = x0;
           t0[kFI * kFP + sidx[s]] = x1;
         }
@@ -712,7 +743,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     }
     __syncthreads();
     // the staging slots have been read: fetch the next step's inputs while this one is lifted
-    if (j0 + kNPB <= k1 + 1)
+    if (SPERR_INV_ASYNC && j0 + kNPB <= k1 + 1)
       stage_step(j0 + kNPB);
     // planes 2 (j0 - 2) .. of the rebuilt box sit in the tile; pair q is wanted iff k0 <= j0+q-2 < k1
     // ---- columns (y) over all x of the tile, then rows (x) over the valid y ----
@@ -910,7 +941,10 @@ static bool fwd_tma_usable(const SrcVol& src, const FusedArgs& a)
 {
   if (std::getenv("SPERR_B200_NO_TMA"))
     return false;
-  return src.is_float && src.vz > 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 15) == 0 && src.vx % 4 == 0 &&
+  // (row pitch a multiple of 128 bytes: with a 400-byte pitch -- a 100 x 88 x 40 volume -- the copy
+  // instruction itself faulted on B200, "illegal instruction" at the UTMALDG, although the tensor
+  // map had been accepted; such volumes take the tile kernel)
+  return src.is_float && src.vz > 0 && (reinterpret_cast<uintptr_t>(src.ptr) & 127) == 0 && src.vx % 32 == 0 &&
          a.lx >= 2 * kFH + 1 && a.ly >= 2 * kFH + 1 && a.lz >= 2 * kFH + 1;
 }
 #endif

@@ -107,6 +107,15 @@ Compressor& shared_compressor();
 Decompressor& shared_decompressor();
 std::mutex& shared_api_mutex();
 
+// Several GPUs behind one call of the host-pointer API (capi_multi.cu). multi_devices(): the devices
+// SPERR_B200_DEVICES names (empty: one device, the calling thread's). The two functions return -2
+// when the call cannot be split over them (the caller then takes the one-device path).
+std::vector<int> multi_devices();
+int comp_3d_multi(const void* src, int is_float, const size_t vol[3], const size_t chunk[3], int mode,
+                  double quality, const std::vector<int>& devs, void** dst, size_t* dst_len);
+int decomp_3d_multi(const void* src, size_t src_len, int output_float, const std::vector<int>& devs,
+                    size_t* dimx, size_t* dimy, size_t* dimz, void** dst);
+
 // Largest number of chunks processed at once (bounded by the list-key layout and by memory).
 size_t pick_batch_chunks(const std::vector<Chunk>& chunks, size_t first, bool pwe);
 

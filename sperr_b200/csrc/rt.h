@@ -69,6 +69,21 @@ __device__ __forceinline__ T* gptr(T* p)
   return p;
 }
 
+// ---- CTA barrier that does not require the threads of a warp to arrive together. What
+// __syncthreads() compiles to is barrier.sync.aligned: every thread of a warp has to execute the same
+// barrier instruction at the same time. Kernels whose warps run long single-thread sections between
+// barriers (thread 0 walking a tree, thread 0 spinning on a grid barrier) do not always have their
+// warps reconverged at the barrier after optimisation; on B200 that showed as decoder state that was
+// one barrier out of step (compute-sanitizer synccheck: "divergent thread(s) in warp"). ----
+#ifdef SPERR_EMUL
+inline void cta_sync() { __syncthreads(); }
+#elif defined(__CUDACC__)
+__device__ __forceinline__ void cta_sync()
+{
+  asm volatile("barrier.sync 0;" ::: "memory");
+}
+#endif
+
 // ---- thread-block clusters: rank of the CTA and the cluster-wide barrier (release / acquire, so
 // what a CTA wrote to global memory before it is visible to the others after it) ----
 #ifdef SPERR_EMUL

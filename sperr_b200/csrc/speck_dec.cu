@@ -298,8 +298,15 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
   for (int c = 0; c < nj; c++)
     if (!jobs[c].skip && jobs[c].pow2 && jobs[c].kind != 1)
       n_cl++;
+  int n_single = 0;
+  for (int c = 0; c < nj; c++)
+    if (!jobs[c].skip && jobs[c].pow2 && jobs[c].kind == 1)
+      n_single++;
+  // every CTA needs an SM of its own (212 KB of shared memory): as large a cluster as still leaves
+  // all streams of the batch resident at once (measured: 64 + 64 streams, R = 2 -> the 1D streams
+  // queue behind the clusters and the stage takes 67 ms instead of 43)
   int R = 1;
-  while (R < kFMaxR && n_cl > 0 && n_cl * R * 2 <= 136)
+  while (R < kFMaxR && n_cl > 0 && n_cl * R * 2 + n_single <= 148)
     R *= 2;
   if (const char* e = std::getenv("SPERR_B200_DEC_CLUSTER"))
     R = std::max(1, std::min(kFMaxR, std::atoi(e)));

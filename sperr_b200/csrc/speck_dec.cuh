@@ -27,19 +27,28 @@
 
 namespace sperr_b200 {
 
-// CTA barrier of the decoders. Much of their control flow is `if (tid == 0) { long serial part }`
-// followed by a barrier; measured on B200 (compute-sanitizer synccheck: "divergent thread(s) in
-// warp" at such a barrier, and decoder state that only made sense if thread 0 was one barrier
-// behind its warp) the warp is not always reconverged when it gets there. __syncwarp() makes the
-// reconvergence explicit ... and is not enough; what is, is a barrier that does not need it:
+// The serial parts of the decoders ("one thread walks ...") are run by ALL 32 lanes of warp 0,
+// redundantly: the lanes hold the same values, take the same branches and store the same data to the
+// same addresses, so the result is that of one thread -- but the warp never diverges. With
+// `if (tid == 0) { long serial part }` the warp of thread 0 was not always reconverged at the barrier
+// that follows (B200, nvcc 12.9 -O3; compute-sanitizer synccheck: "divergent thread(s) in warp"), and
+// a barrier reached that way releases early: decoder state one barrier out of step. Nothing inside a
+// serial part may therefore be an atomic or depend on the lane. (The CPU emulator runs lanes one
+// after the other, not in lockstep: there it is thread 0 alone.)
+#ifdef SPERR_EMUL
+#define DEC_SERIAL(tid) ((tid) == 0)
+#else
+#define DEC_SERIAL(tid) (((tid) >> 5) == 0)
+#endif
+
+// CTA barrier of the decoders. SPERR_DEC_UNALIGNED_BARRIER: barrier.sync without .aligned (threads of
+// a warp may arrive separately; about 30 % slower on this kernel), kept as a switch.
 __device__ __forceinline__ void block_sync()
 {
-#if defined(SPERR_EMUL)
-  __syncthreads();
+#ifdef SPERR_DEC_UNALIGNED_BARRIER
+  cta_sync();
 #else
-  // barrier.sync WITHOUT .aligned (what __syncthreads() compiles to is the aligned form): threads of
-  // a warp may arrive separately
-  asm volatile("barrier.sync 0;" ::: "memory");
+  __syncthreads();
 #endif
 }
 
@@ -364,14 +373,14 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
     S.wtot[warp] = nsig;
   block_sync();
   if (R > 1) {
-    if (tid == 0) {
+    if (DEC_SERIAL(tid)) {
       unsigned long long t = 0;
       for (int i = 0; i < kDecWarps; i++)
         t += S.wtot[i];
       __stcg(gptr(&lb->sig[rank]), t);
     }
     cluster_sync();
-    if (tid == 0) {
+    if (DEC_SERIAL(tid)) {
       unsigned long long t = 0;
       for (int r2 = 0; r2 < R; r2++)
         t += __ldcg(gptr(&lb->sig[r2]));
@@ -382,7 +391,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
     block_sync();
     return;
   }
-  if (tid == 0) {
+  if (DEC_SERIAL(tid)) {
     unsigned long long t = 0;
     for (int i = 0; i < kDecWarps; i++)
       t += S.wtot[i];

@@ -113,6 +113,7 @@ struct FastSmem {
   int go;
   int plane;
   unsigned err;
+  unsigned napp;             // 1D walker: sets logged for appending in this round (the log lives in nxt[])
   // cluster
   int R, rank;
   unsigned entry;            // offset at which the chain enters this CTA's window
@@ -653,7 +654,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
       for (int e = tid; e < rank * kFEntry; e += kDecThreads)
         xtab[e] = mb_ld(&box->exits[0][0] + e);
       block_sync();
-      if (tid == 0) {
+      if (DEC_SERIAL(tid)) {
         unsigned e = 0;
         for (int s2 = 0; s2 < rank; s2++)
           e = unsigned(xtab[s2 * kFEntry + e]) - unsigned(kFW);
@@ -664,7 +665,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
     }
     const unsigned exitpos = fin[entry];
     // token starts of my window: anchors every 256 tokens, then every 16, then single steps
-    if (tid == 0) {
+    if (DEC_SERIAL(tid)) {
       unsigned n = 0;
       if (have8) {
         unsigned p2 = entry;
@@ -713,7 +714,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
       if (tid == 0)
         mb_st(&box->marks[rank], total_marks);
       cluster_sync();
-      if (tid == 0) {
+      if (DEC_SERIAL(tid)) {
         unsigned at = i0, sum = 0, mine_i0 = 0, mine_T = 0, last = 0;
         for (int s2 = 0; s2 < R; s2++) {
           const unsigned mk = mb_ld(&box->marks[s2]);
@@ -776,7 +777,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
       if (tid == 0)
         mb_st(&box->surv[rank], tot_surv);
       cluster_sync();   // ... in every window of the round
-      if (tid == 0) {
+      if (DEC_SERIAL(tid)) {
         unsigned before = 0, sum = 0;
         for (int s2 = 0; s2 < R; s2++) {
           const unsigned v = mb_ld(&box->surv[s2]);
@@ -864,7 +865,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
           F.cnt[cl] += sum;
         }
       }
-      if (tid == 0) {
+      if (DEC_SERIAL(tid)) {
         unsigned long long dl = 0, dn = 0;
         unsigned e = 0;
         for (int s2 = 0; s2 < R; s2++) {
@@ -1107,7 +1108,13 @@ static __device__ void f_walk1d(DecChunk& d, DecShared& S, FastSmem& F)
     k = F.wk_k[0];
     sg = F.wk_sig[0];
   }
-  node_t* const lis = gptr(d.lis);
+  // sets that stay insignificant are appended to the list of their depth -- not here: a counter
+  // look-up, a bounds check and two stores per set are most of what a step of this loop would
+  // cost. They are logged (depth, index) in shared memory, at most one per stream bit of the round,
+  // and the whole CTA files them afterwards (f_flush_appends); nobody reads those lists before the
+  // next plane.
+  uint32_t* const alog = reinterpret_cast<uint32_t*>(&F.nxt[0][0]);
+  unsigned napp = 0;
   for (;;) {
     if (depth < 0) {
       if (i == cnt)
@@ -1174,17 +1181,10 @@ static __device__ void f_walk1d(DecChunk& d, DecShared& S, FastSmem& F)
         sg = 0;
       }
     }
-    else {
-      const unsigned slot = F.cnt[cj];
-      const unsigned long long at = F.off[cj] + slot;
-      if (at >= F.off[cj + 1]) {
-        F.err |= 1u;
-        break;
-      }
-      lis[at] = ((unsigned long long)cj << 32) | cix;
-      F.cnt[cj] = slot + 1;
-    }
+    else
+      alog[napp++] = (unsigned(cj) << 27) | cix;   // one store; f_flush_appends puts it into its list
   }
+  F.napp = napp;
   if (depth >= 0) {
     F.wk_node[0] = ((unsigned long long)j << 32) | ix;
     F.wk_node[1] = (unsigned long long)j0;
@@ -1199,6 +1199,56 @@ static __device__ void f_walk1d(DecChunk& d, DecShared& S, FastSmem& F)
 }
 
 // Survivors of the staged roots [rs_first, wk_i) keep their order: list[wk_w ...] (whole CTA).
+// Files the sets the 1D walker logged in this round: entry e = (depth << 27 | index), in log order,
+// goes to list `depth` behind the entries of the same depth logged before it (a stable counting
+// sort, 1024 entries at a time: ranks inside a warp by match / popc, across warps by a small table).
+static __device__ void f_flush_appends(DecChunk& d, FastSmem& F)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned n = F.napp;
+  if (n == 0)
+    return;
+  const uint32_t* const alog = reinterpret_cast<const uint32_t*>(&F.nxt[0][0]);
+  uint16_t* const wc = reinterpret_cast<uint16_t*>(&F.nxt[2][0]);   // [32 depths][32 warps]: sets of the batch
+  uint32_t* const wt = F.mark;                                      // [32 depths]: batch totals
+  for (unsigned b0 = 0; b0 < n; b0 += kDecThreads) {
+    const unsigned e = b0 + tid;
+    const bool have = e < n;
+    const uint32_t v = have ? alog[e] : 0u;
+    const unsigned lev = have ? (v >> 27) : 31u;   // idle lanes share a bucket nobody files (depths are < 31)
+    const unsigned peers = __match_any_sync(0xffffffffu, lev);
+    const unsigned before = unsigned(__popc(peers & ((1u << lane) - 1u)));
+    for (int i = tid; i < 32 * 32; i += kDecThreads)
+      wc[i] = 0;
+    block_sync();
+    if (have && before == 0)
+      wc[lev * 32 + warp] = uint16_t(__popc(peers));
+    block_sync();
+    {   // warp l scans depth l over the 32 warps: exclusive prefix back into the table, total to wt
+      const unsigned c = wc[warp * 32 + lane];
+      unsigned inc = c;
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+          inc += t;
+      }
+      wc[warp * 32 + lane] = uint16_t(inc - c);
+      if (lane == 31) {
+        wt[warp] = inc;
+        if (inc && F.off[warp] + F.cnt[warp] + inc > F.off[warp + 1])
+          F.err |= 1u;
+      }
+    }
+    block_sync();
+    if (have && !F.err)
+      gptr(d.lis)[F.off[lev] + F.cnt[lev] + wc[lev * 32 + warp] + before] = ((unsigned long long)lev << 32) | (v & 0x7ffffffu);
+    block_sync();
+    if (tid < 31)
+      F.cnt[tid] += wt[tid];
+    block_sync();
+  }
+}
+
 static __device__ void f_compact_roots(FastSmem& F, node_t* list)
 {
   const int tid = threadIdx.x;
@@ -1283,7 +1333,7 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
       }
       block_sync();
       const long long f_tw = F_CLOCK();
-      if (tid == 0) {
+      if (DEC_SERIAL(tid)) {
         if (d.kind == 1)
 #ifdef SPERR_OLD_WALK1D
           f_walk<1>(d, S, F);
@@ -1296,6 +1346,8 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
           f_walk<0>(d, S, F);
       }
       block_sync();
+      if (d.kind == 1)
+        f_flush_appends(d, F);
       if (!iphase)
         f_compact_roots(F, gptr(d.lis) + F.off[lis]);
       block_sync();
@@ -1311,7 +1363,7 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
       if (F.wk_depth < 0 && F.wk_i == cnt)
         break;
     }
-    if (tid == 0 && d.dbgw_n < 16) {
+    if (DEC_SERIAL(tid) && d.dbgw_n < 16) {
       unsigned* const r = d.dbgw[d.dbgw_n++];
       r[0] = unsigned(n_plane); r[1] = unsigned(lj); r[2] = cnt; r[3] = F.wk_i; r[4] = F.wk_w;
       r[5] = unsigned(lis); r[6] = F.wk_q; r[7] = F.rs_cnt;
@@ -1391,7 +1443,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     reinterpret_cast<unsigned long long*>(&sd)[i] = reinterpret_cast<const unsigned long long*>(&chunks[c])[i];
   block_sync();
   DecChunk& d = sd;
-  if (tid == 0) {
+  if (DEC_SERIAL(tid)) {
     S.pos = 0;
     S.klip = 0;
     S.klsp = 0;
@@ -1417,7 +1469,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
   }
   f_build_luts(F);
   block_sync();
-  if (tid == 0 && rank == 0) {
+  if (DEC_SERIAL(tid) && rank == 0) {
     for (int r = 0; r < d.nroots; r++) {
       const unsigned long long nd = d.roots[r];
       const int lis = f_lis(F, int(nd >> 32));
@@ -1447,7 +1499,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
       F_TOC(F, 0);
     }
     auto trace = [&](int stage) {   // debugging aid, leader only
-      if (tid == 0 && rank == 0 && n < kMaxPlanes) {
+      if (DEC_SERIAL(tid) && rank == 0 && n < kMaxPlanes) {
         unsigned long long sets = 0;
         for (int l = 0; l < d.nlis; l++)
           sets += F.cnt[l];
@@ -1468,7 +1520,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
         dec_lis_walk(d, S, F, n);
       block_sync();
       trace(2);
-      if (tid == 0) {
+      if (DEC_SERIAL(tid)) {
         const bool more = !F.err && dec_plane_end(d, S, n);
         F.go = (more && n > 0) ? 1 : 0;
         F.plane = n - 1;

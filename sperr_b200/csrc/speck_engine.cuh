@@ -415,7 +415,7 @@ __device__ __forceinline__ unsigned long long warp_reserve(unsigned long long* c
 // launch). bar[0]: arrivals, bar[1]: generation. ----
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks)
 {
-  __syncthreads();
+  cta_sync();
   if (threadIdx.x == 0 && nblocks > 1) {
     __threadfence();
     volatile unsigned* const vbar = bar;   // volatile: re-read from L2 on every turn of the spin
@@ -438,7 +438,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks)
     }
     __threadfence();
   }
-  __syncthreads();
+  cta_sync();   // thread 0 arrives from its spin loop: not the aligned form
 }
 
 // The LIS part of one plane in ONE launch: the roots' significance bits, then the expansion of the
@@ -707,7 +707,12 @@ void launch_lis_plane(const EncCtx& ctx, const typename T::Data& tree, unsigned*
     RT_CHECK(cudaGetDevice(&dev));
     RT_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     RT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_lis_plane<T>, 256, 0));
-    grid = sms * std::max(1, std::min(per, 8));
+    // The compressor runs two of these loops side by side (SPECK3D of the coefficients, SPECK1D of the
+    // outliers), and a cooperative grid only starts when ALL its CTAs fit: sized to the whole GPU
+    // each, the two chains take turns (measured: c.outlier_encode 6 -> 25 ms). The big tree takes
+    // all but one CTA slot per SM, the outlier tree one.
+    const int slots = std::max(1, std::min(per, 8));
+    grid = T::kIsOutlierTree ? sms : sms * std::max(1, slots - 1);
   }
   EncCtx c = ctx;
   typename T::Data t = tree;

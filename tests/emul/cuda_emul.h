@@ -156,6 +156,16 @@ inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32)
   (void)width;
   return emu_unpack<T>(o[l ^ m]);
 }
+inline unsigned __match_any_sync(unsigned, unsigned v)
+{
+  uint64_t o[32];
+  emu::warp_exchange(v, o);
+  unsigned r = 0;
+  for (int i = 0; i < 32; i++)
+    if (unsigned(o[i]) == v)
+      r |= 1u << i;
+  return r;
+}
 inline unsigned __reduce_or_sync(unsigned, unsigned v)
 {
   uint64_t o[32];
