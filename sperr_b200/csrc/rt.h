@@ -104,6 +104,7 @@ __device__ __forceinline__ void cluster_sync()
   // decode of a 128^3 chunk hangs, without it it is bit-exact.
   __threadfence();
   asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+  __syncwarp();   // ... and leave converged: the CTA barriers that follow are the aligned kind
 }
 #endif
 

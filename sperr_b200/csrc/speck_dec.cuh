@@ -35,10 +35,16 @@ namespace sperr_b200 {
 // a barrier reached that way releases early: decoder state one barrier out of step. Nothing inside a
 // serial part may therefore be an atomic or depend on the lane. (The CPU emulator runs lanes one
 // after the other, not in lockstep: there it is thread 0 alone.)
+// Lockstep is what makes a read-modify-write inside a serial part (S.klip -= t) happen once: the
+// lanes are brought together when they enter (DEC_SERIAL_CONVERGE, the first statement of every
+// serial part) -- per-lane branches before it, or a barrier that does not converge the warp, may have
+// left them apart.
 #ifdef SPERR_EMUL
 #define DEC_SERIAL(tid) ((tid) == 0)
+#define DEC_SERIAL_CONVERGE() ((void)0)
 #else
 #define DEC_SERIAL(tid) (((tid) >> 5) == 0)
+#define DEC_SERIAL_CONVERGE() __syncwarp()
 #endif
 
 // CTA barrier of the decoders. SPERR_DEC_UNALIGNED_BARRIER: barrier.sync without .aligned (threads of
@@ -374,6 +380,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
   block_sync();
   if (R > 1) {
     if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
       unsigned long long t = 0;
       for (int i = 0; i < kDecWarps; i++)
         t += S.wtot[i];
@@ -381,6 +388,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
     }
     cluster_sync();
     if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
       unsigned long long t = 0;
       for (int r2 = 0; r2 < R; r2++)
         t += __ldcg(gptr(&lb->sig[r2]));
@@ -392,6 +400,7 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
     return;
   }
   if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
     unsigned long long t = 0;
     for (int i = 0; i < kDecWarps; i++)
       t += S.wtot[i];

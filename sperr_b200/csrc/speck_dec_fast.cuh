@@ -655,6 +655,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         xtab[e] = mb_ld(&box->exits[0][0] + e);
       block_sync();
       if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
         unsigned e = 0;
         for (int s2 = 0; s2 < rank; s2++)
           e = unsigned(xtab[s2 * kFEntry + e]) - unsigned(kFW);
@@ -666,6 +667,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
     const unsigned exitpos = fin[entry];
     // token starts of my window: anchors every 256 tokens, then every 16, then single steps
     if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
       unsigned n = 0;
       if (have8) {
         unsigned p2 = entry;
@@ -715,6 +717,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         mb_st(&box->marks[rank], total_marks);
       cluster_sync();
       if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
         unsigned at = i0, sum = 0, mine_i0 = 0, mine_T = 0, last = 0;
         for (int s2 = 0; s2 < R; s2++) {
           const unsigned mk = mb_ld(&box->marks[s2]);
@@ -778,6 +781,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         mb_st(&box->surv[rank], tot_surv);
       cluster_sync();   // ... in every window of the round
       if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
         unsigned before = 0, sum = 0;
         for (int s2 = 0; s2 < R; s2++) {
           const unsigned v = mb_ld(&box->surv[s2]);
@@ -866,6 +870,7 @@ static __device__ void f_list_by_chain(DecChunk& d, DecShared& S, FastSmem& F, i
         }
       }
       if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
         unsigned long long dl = 0, dn = 0;
         unsigned e = 0;
         for (int s2 = 0; s2 < R; s2++) {
@@ -1334,6 +1339,7 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
       block_sync();
       const long long f_tw = F_CLOCK();
       if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
         if (d.kind == 1)
 #ifdef SPERR_OLD_WALK1D
           f_walk<1>(d, S, F);
@@ -1364,6 +1370,7 @@ static __device__ void dec_lis_walk(DecChunk& d, DecShared& S, FastSmem& F, int 
         break;
     }
     if (DEC_SERIAL(tid) && d.dbgw_n < 16) {
+      DEC_SERIAL_CONVERGE();
       unsigned* const r = d.dbgw[d.dbgw_n++];
       r[0] = unsigned(n_plane); r[1] = unsigned(lj); r[2] = cnt; r[3] = F.wk_i; r[4] = F.wk_w;
       r[5] = unsigned(lis); r[6] = F.wk_q; r[7] = F.rs_cnt;
@@ -1444,6 +1451,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
   block_sync();
   DecChunk& d = sd;
   if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
     S.pos = 0;
     S.klip = 0;
     S.klsp = 0;
@@ -1470,6 +1478,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
   f_build_luts(F);
   block_sync();
   if (DEC_SERIAL(tid) && rank == 0) {
+      DEC_SERIAL_CONVERGE();
     for (int r = 0; r < d.nroots; r++) {
       const unsigned long long nd = d.roots[r];
       const int lis = f_lis(F, int(nd >> 32));
@@ -1500,6 +1509,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
     }
     auto trace = [&](int stage) {   // debugging aid, leader only
       if (DEC_SERIAL(tid) && rank == 0 && n < kMaxPlanes) {
+      DEC_SERIAL_CONVERGE();
         unsigned long long sets = 0;
         for (int l = 0; l < d.nlis; l++)
           sets += F.cnt[l];
@@ -1521,6 +1531,7 @@ static __global__ void __launch_bounds__(kDecThreads) k_speck_decode_fast(DecChu
       block_sync();
       trace(2);
       if (DEC_SERIAL(tid)) {
+      DEC_SERIAL_CONVERGE();
         const bool more = !F.err && dec_plane_end(d, S, n);
         F.go = (more && n > 0) ? 1 : 0;
         F.plane = n - 1;
