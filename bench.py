@@ -397,8 +397,10 @@ def measure(args, L, dev, rank, world, scaling, full):
         state["stream"] = s
         return s
 
+    out_box = torch.empty((ext[2], ext[1], ext[0]), dtype=torch.float32, device=dev)   # reused by every step
+
     def decomp_dev(stream, d_stream=None):
-        b, _ = sharded.decompress_3d_sharded(L.lib, stream, dev, True)
+        b, _ = sharded.decompress_3d_sharded(L.lib, stream, dev, True, out=out_box)
         state["out"] = b
 
     def step_dev():

@@ -279,7 +279,19 @@ def parse_header_only(cdll, header, total_len):
     return tuple(vol), tuple(chunk), bool(isf.value), hlen.value, lens
 
 
-def _decompress_world1(cdll, stream, dev, output_float, on_device):
+def _out_box(out, e, output_float, dev):
+    """the tensor a rank decodes into: a fresh one, or the caller's (reused across calls: a 4 GiB
+    allocation inside a timed loop may cost a cudaMalloc, which synchronises the device)"""
+    dt = torch.float32 if output_float else torch.float64
+    shape = (e[2], e[1], e[0])
+    if out is None:
+        return torch.empty(shape, dtype=dt, device=dev)
+    if tuple(out.shape) != shape or out.dtype != dt or not out.is_contiguous() or out.device != dev:
+        raise ValueError("out must be a contiguous %s tensor of shape %s on %s" % (dt, shape, dev))
+    return out
+
+
+def _decompress_world1(cdll, stream, dev, output_float, on_device, out=None):
     """decompress_3d_sharded for a world of one rank: no exchange at all."""
     if on_device:
         vol, chunk, isf, hlen, lens = parse_header_only(cdll, stream.header, stream.size)
@@ -294,7 +306,7 @@ def _decompress_world1(cdll, stream, dev, output_float, on_device):
     # device container: no host copy of the streams, the library fetches the chunk headers itself
     h = None if on_device else np.ascontiguousarray(stream)[hlen:hlen + nb]
     e = sh.box_extent
-    box = torch.empty((e[2], e[1], e[0]), dtype=torch.float32 if output_float else torch.float64, device=dev)
+    box = _out_box(out, e, output_float, dev)
     _pre_call(dev)
     rc = cdll.sperr_b200_decomp_3d_range_dev(h.ctypes.data_as(vp) if h is not None else vp(None),
                                              vp(mine.data_ptr()), nb,
@@ -306,18 +318,18 @@ def _decompress_world1(cdll, stream, dev, output_float, on_device):
     return box, sh
 
 
-def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
+def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None, out=None):
     """stream: the container (uint8 numpy array, or the DeviceContainer compress_3d_sharded returned)
     on rank 0, ignored elsewhere. Every rank returns
     (box, shard): its part of the decoded volume as a (z, y, x) tensor on `device`, and the Shard that
-    says where the box sits."""
+    says where the box sits. `out`: optional preallocated tensor of the box's shape to decode into."""
     rank, world = _world(group)
     cdll = _bind(cdll)
     dev = torch.device(device)
     src0 = dist.get_global_rank(group, 0) if group is not None else 0
     on_device = isinstance(stream, DeviceContainer)
     if world == 1:
-        return _decompress_world1(cdll, stream, dev, output_float, on_device)
+        return _decompress_world1(cdll, stream, dev, output_float, on_device, out)
     # container geometry as two small tensor broadcasts (no pickling): 8 fixed words, then the lengths
     head = torch.zeros(9, dtype=torch.int64, device=dev)
     bad = 0
@@ -371,8 +383,7 @@ def decompress_3d_sharded(cdll, stream, device, output_float=True, group=None):
         h = stage.numpy()[:nb]
     _pre_call(dev)
     e = sh.box_extent
-    box = torch.empty((e[2], e[1], e[0]), dtype=torch.float32 if output_float else torch.float64,
-                      device=dev)
+    box = _out_box(out, e, output_float, dev)
     rc = cdll.sperr_b200_decomp_3d_range_dev(h.ctypes.data_as(vp) if h is not None else vp(None),
                                              vp(mine.data_ptr()), nb,
                                              mylens.ctypes.data_as(vp), sh.vol, sh.chunk, sh.origin,
