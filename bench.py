@@ -92,10 +92,10 @@ class Clocks:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, idle=False):
         self.index = index
         self.samples = []
-        self.stop = False
+        self.stop = idle   # idle: no sampling at all (--diag noclocks)
         self.t = threading.Thread(target=self.run, daemon=True)
 
     def _nvml(self):
@@ -351,6 +351,9 @@ def run_ours(args):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     L = sperr_b200.load()
     out = measure(args, L, dev, rank, world, args.scaling, full=True)
+    if out is None and args.diag:
+        dist.destroy_process_group()
+        return
     if world > 1 and args.scaling == "strong" and args.weak_extra:
         w = measure(args, L, dev, rank, world, "weak", full=False)
         if rank == 0:
@@ -421,13 +424,14 @@ def measure(args, L, dev, rank, world, scaling, full):
     gc.disable()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launch_count = L.fn("sperr_b200_launch_count", C.c_ulonglong, [])
-    with Clocks(local_index(dev)) as clk:
+    diag = set(x for x in args.diag.split(",") if x)
+    with Clocks(local_index(dev), idle="noclocks" in diag) as clk:
         barrier()
         l0 = launch_count()
         # stage ranges: CUDA events the library records on the stream each kernel (family) is
         # launched on, over these very steps (two event records per range, no synchronisation
         # before the loop ends); per-stage times below are averages over the timed steps
-        prof_on(1)
+        prof_on(0 if "noprof" in diag else 1)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         e0.record()
         for i in range(steps):
@@ -443,6 +447,11 @@ def measure(args, L, dev, rank, world, scaling, full):
         stages = json.loads(buf.value.decode())
         for v in stages.values():
             v["ms"] /= steps
+    if diag:   # diagnosis run: the per-step times are all that is wanted
+        if rank == 0:
+            print(json.dumps({"diag": sorted(diag), "step_ms_each": [round(x, 2) for x in step_each]}))
+        gc.enable()
+        return None
     ms = e0.elapsed_time(e1) / steps
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -651,6 +660,7 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=("strong", "weak"))
     ap.add_argument("--weak-extra", type=int, default=1, help="N > 1: also report the weak-scaled run as extra.weak")
     ap.add_argument("--check", type=int, default=1, help="rank 0 checks the container bytes after the timed loops")
+    ap.add_argument("--diag", default="", help="diagnosis of host-side stalls: comma list of noclocks, noprof")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

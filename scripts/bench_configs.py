@@ -135,7 +135,9 @@ def main():
             del vol, out
         elif w == "4":   # 4096x4096x1024 f32, PSNR target, decompression only
             full = (4096, 4096, 1024)
-            dims = (4096, 4096, 1024 // a.share) if a.share > 1 else full
+            # a box of whole 256^3 chunks: the z axis has only 4 chunk slabs, so 8 shares split z by 4 and y by 2
+            zs = min(a.share, 4)
+            dims = (4096, 4096 // (a.share // zs), 1024 // zs) if a.share > 1 else full
             vol = field(dims, torch.float32, dev)
             n = vol.numel()
             rc, stream = L.compress_3d_dev(vol.data_ptr(), True, dims, (CK,) * 3, 2, 80.0)

@@ -31,3 +31,12 @@ for name in ("dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum"
         i = hh.index(name)
         for r in rr[2:]:
             print(f"  raw {name:75s} {r[i]:>14s} {rr[1][i]}")
+# stall breakdown: warps stalled per issue, by reason (sums to "Warp Cycles Per Issued Instruction")
+for i, name in enumerate(hh):
+    if name.startswith("smsp__average_warps_issue_stalled_") and name.endswith("_per_issue_active.ratio"):
+        for r in rr[2:]:
+            try:
+                if float(r[i].replace(",", "")) >= 0.05:
+                    print(f"  stall {name[34:-23]:30s} {r[i]:>10s} warps per issue")
+            except ValueError:
+                pass

@@ -77,6 +77,8 @@ class Library:
         vol = np.ascontiguousarray(vol)
         if vol.dtype not in (np.float32, np.float64):
             raise TypeError("float32 or float64 input expected")
+        if vol.size != int(dims[0]) * int(dims[1]) * int(dims[2]):
+            raise ValueError("volume holds %d values, dims say %d" % (vol.size, int(dims[0]) * int(dims[1]) * int(dims[2])))
         dst, n = vp(None), sz(0)
         rc = self.lib.sperr_comp_3d(vol.ctypes.data_as(vp), int(vol.dtype == np.float32), *dims,
                                     *chunks, mode, quality, nthreads, C.byref(dst), C.byref(n))
@@ -123,6 +125,8 @@ class Library:
         img = np.ascontiguousarray(img)
         if img.dtype not in (np.float32, np.float64):
             raise TypeError("float32 or float64 input expected")
+        if img.size != int(dims[0]) * int(dims[1]):
+            raise ValueError("slice holds %d values, dims say %d" % (img.size, int(dims[0]) * int(dims[1])))
         dst, n = vp(None), sz(0)
         rc = self.lib.sperr_comp_2d(img.ctypes.data_as(vp), int(img.dtype == np.float32), dims[0],
                                     dims[1], mode, quality, int(header), C.byref(dst), C.byref(n))
@@ -133,6 +137,8 @@ class Library:
     def decompress_2d(self, stream, dims, output_float=True):
         """stream: a slice stream WITHOUT the 10-byte header. Returns (rc, flat array or None)."""
         stream = np.ascontiguousarray(stream, dtype=np.uint8)
+        if int(dims[0]) * int(dims[1]) == 0:
+            raise ValueError("empty slice")
         dst = vp(None)
         rc = self.lib.sperr_decomp_2d(stream.ctypes.data_as(vp), stream.size, int(output_float),
                                       dims[0], dims[1], C.byref(dst))
@@ -150,6 +156,11 @@ class Library:
             f, ptr = self.lib.sperr_b200_comp_2d_batch_dev, vp(src)
         else:
             src = np.ascontiguousarray(src)
+            if src.dtype != (np.float32 if is_float else np.float64):
+                raise TypeError("src dtype does not match is_float")
+            if src.size != int(nslices) * int(dims[0]) * int(dims[1]):
+                raise ValueError("src holds %d values, nslices * dims say %d"
+                                 % (src.size, int(nslices) * int(dims[0]) * int(dims[1])))
             f, ptr = self.lib.sperr_b200_comp_2d_batch, src.ctypes.data_as(vp)
         rc = f(ptr, int(is_float), dims[0], dims[1], nslices, mode, quality, int(header),
                C.byref(dst), lens.ctypes.data_as(vp))
@@ -162,6 +173,8 @@ class Library:
         Returns (rc, flat array) or, with d_out_ptr (device buffer), (rc, None)."""
         streams = np.ascontiguousarray(streams, dtype=np.uint8)
         lens = np.ascontiguousarray(lens, dtype=np.uint64)
+        if int(lens.sum()) > streams.size:
+            raise ValueError("lens add up to %d bytes, the buffer holds %d" % (int(lens.sum()), streams.size))
         if d_out_ptr is not None:
             rc = self.lib.sperr_b200_decomp_2d_batch_dev(streams.ctypes.data_as(vp),
                                                          lens.ctypes.data_as(vp), lens.size,

@@ -988,8 +988,11 @@ void sperr_b200_prof_enable(int on)
 {
   rt::prof().on = on != 0;
   if (on) {
+    rt::prof_collect();   // ranges left over from an earlier session hand their events back
     rt::prof().acc.clear();
-    rt::prof().open.clear();
+#ifndef SPERR_EMUL
+    rt::prof_reserve(4096);   // outside any timed region: the ranges of a timed loop only take from the pool
+#endif
   }
 }
 

@@ -24,6 +24,7 @@
 // Levels ping-pong through compact per-level boxes (ChunkDev::scratch) so that no CTA reads what
 // another one is overwriting; detail sub-bands are written once to their final place in `coef`.
 #include "kernels.h"
+#include <type_traits>
 #ifndef SPERR_EMUL
 #include <cuda.h>
 #endif
@@ -151,38 +152,14 @@ struct FusedArgs {
   CdfC k;
 };
 
-// SPERR_INV_ASYNC=1: the inverse transform stages the z-phase inputs of the next step with cp.async
-// (needs two pairs per step to keep two CTAs on an SM). Measured on B200 (1024^3): 13.97 ms against
-// 12.69 ms for the direct-load kernel with three pairs per step -- the smaller step costs more
-// barriers per sample than the overlap saves -- so it is off.
-#ifndef SPERR_INV_ASYNC
-#define SPERR_INV_ASYNC 0
-#endif
-constexpr int kNPB = SPERR_INV_ASYNC ? 2 : 3;   // sample pairs (2 planes each) a CTA transforms per step
+constexpr int kNPB = 3;   // sample pairs (2 planes each) a CTA transforms per step
 constexpr int kPlanes = 2 * kNPB;
 constexpr size_t kFusedSmem = (size_t)kPlanes * kFI * kFP * sizeof(double);
-// inverse transform: the low / high band inputs of the NEXT step are fetched with cp.async while
-// the CTA lifts the current one; every thread stages exactly the values it consumes itself
-constexpr int kInvPer = (kFI * kFI + kFThreads - 1) / kFThreads;   // 7 tile elements per thread and plane
-constexpr size_t kInvStage = (size_t)kNPB * 2 * kInvPer * kFThreads;   // doubles
-constexpr size_t kInvSmem = kFusedSmem + (SPERR_INV_ASYNC ? kInvStage * sizeof(double) : 0);
-
-// 8-byte asynchronous copy global -> shared (LDGSTS); a plain copy under the CPU emulator
-__device__ __forceinline__ void async_copy8(double* dst, const double* src)
-{
-#ifdef SPERR_EMUL
-  *dst = *src;
-#else
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(unsigned(__cvta_generic_to_shared(dst))), "l"(src)
-               : "memory");
-#endif
-}
-__device__ __forceinline__ void async_commit_wait_all()
-{
-#ifndef SPERR_EMUL
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-#endif
-}
+// (A cp.async variant of the inverse transform -- every thread staging the z-phase inputs of the next
+// step while the CTA lifts the current one -- was measured on B200 and dropped: 13.97 ms against
+// 12.69 ms; it needed two pairs per step to keep two CTAs on an SM, and the smaller step costs more
+// barriers per sample than the overlap saves.)
+constexpr size_t kInvSmem = kFusedSmem;
 
 __device__ __forceinline__ unsigned long long abs_bits(double v)
 {
@@ -575,11 +552,34 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d_tma(FusedArgs a, const _
 // OUT 0: fp64 box in scratch (levels > 0) or, at level 0, raw fp64 values into the volume `vol`,
 //     1: destination volume (+ outlier corrector, + mean, float or double),
 //     2: compare with the source volume and record the outliers
-template <int OUT, bool FMA>
-__global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
+//
+// Thread roles (kIThreads = 416 = 13 warps; round 2: the first version spent its time issuing
+// instructions, ~3900 per thread and step with the z states spilled to local memory -- see DESIGN.md):
+//   z phase   thread t < 400 owns the 2 x 2 quad (rows 2i, 2i+1; columns 2j, 2j+1), i = t / 20,
+//             j = t % 20, of the 40 x 40 tile: one column of every (x, y) parity class, so which
+//             sub-band a load comes from is known at compile time and the four lifting states
+//             (16 doubles) stay in registers;
+//   y, x      one thread per line, as in the forward kernel;
+//   epilogue  warp w < 12 owns 16 rows of ONE plane of the step (plane w / 2, rows 16 (w % 2) ..),
+//             lane = x: addresses are a base per step plus compile-time multiples of the row pitch.
+// (out of line: a binary search that a handful of values per chunk take; inlined sixteen times it
+// was half of the kernel's code)
+__device__ __noinline__ double corrector_value(const CorrectorList l, unsigned chunk, unsigned pos)
+{
+  return corrector_lookup(l, chunk, pos);
+}
+
+constexpr int kIThreads = 416;
+constexpr int kIQuads = kFNP * kFNP;   // 400
+static_assert(kIQuads <= kIThreads && kPlanes * kFI <= kIThreads && 2 * kPlanes <= kIThreads / 32, "roles");
+constexpr int kIRows = 16;             // rows of a plane an epilogue warp owns
+
+template <int OUT, bool FMA, bool F32>
+__global__ void __launch_bounds__(kIThreads, 2) k_inv3d(FusedArgs a)
 {
   DYN_SMEM(double, tile);   // [kPlanes][kFI][kFP]
-  const ChunkDev& ch = a.chunks[a.ids[blockIdx.y]];
+  const unsigned cid = a.ids[blockIdx.y];
+  const ChunkDev& ch = a.chunks[cid];
   if (ch.is_const)
     return;
   const int tid = threadIdx.x;
@@ -599,152 +599,103 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
   // local copies of what the loop reads through `ch` (see k_fwd3d)
   const double* const coef = ch.coef;
   const unsigned cz0 = ch.z0;
-
-  // the (x, y) columns this thread runs the z lifting for: tile elements tid, tid + 256, ...
-  constexpr int kPer = (kFI * kFI + kFThreads - 1) / kFThreads;   // 7
-  unsigned coff[kPer];     // offset inside a z plane of coef (chunks hold < 2^31 values)
-  unsigned eoff[kPer];     // where the even-z sample comes from: offset inside a plane of the approx
-  unsigned apx = 0;        // box (bit s of apx set) or of coef
-  InvState st[kPer];
-  unsigned short sidx[kPer];
-  for (int s = 0; s < kPer; s++) {
-    st[s] = InvState{0.0, 0.0, 0.0, 0.0};
-    const int idx = tid + s * kFThreads;
-    const int ty = idx / kFI, tx = idx % kFI;
-    sidx[s] = (unsigned short)(ty * kFP + tx);
-    const int gx = mirror(X0 - kFH + tx, lx), gy = mirror(Y0 - kFH + ty, ly);
-    const int xo = (gx >> 1) + ((gx & 1) ? ax : 0), yo = (gy >> 1) + ((gy & 1) ? ay : 0);
-    coff[s] = unsigned((size_t)yo * cnx + xo);
-    eoff[s] = coff[s];
-    if (!((gx | gy) & 1)) {
-      apx |= 1u << s;
-      eoff[s] = a.apx_off >= 0 ? unsigned((gy >> 1) * ax + (gx >> 1)) : unsigned((size_t)(gy >> 1) * cnx + (gx >> 1));
-    }
-  }
-  const double* abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : coef;
-  double* const obox = a.out_off >= 0 ? ch.scratch + a.out_off : nullptr;   // OUT 0, levels > 0
+  const double* const abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : coef;
   ASSUME_GLOBAL(coef);
   ASSUME_GLOBAL(abox);
-  const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
+  const unsigned cnxy32 = unsigned(cnxy), aplane32 = a.apx_off >= 0 ? unsigned(ax * ay) : cnxy32;
 
-  // epilogue ownership: (x, y) = (X0 + lane, Y0 + warp + 8 c), c = 0 .. 3, of every plane
-  const int ep_lane = tid & 31, ep_warp = tid >> 5;
-  const unsigned long long ep_vplane = a.vol.vx * a.vol.vy;
+  // ---- z phase: my quad. Slot s = 2 py + px is the column (2i + py, 2j + px) of the tile; the tile
+  // starts at an even sample and mirroring keeps parity, so slot s is always of parity class
+  // (px, py): slot 0 reads its even-z samples from the approximation box, the others from coef.
+  const bool zthread = tid < kIQuads;
+  const int qi = zthread ? tid / kFNP : 0, qj = zthread ? tid % kFNP : 0;
+  unsigned coff[4];       // offset inside a z plane of coef (chunks hold < 2^31 values)
+  unsigned eoff0 = 0;     // slot 0: offset inside a z plane of the approximation box
+  InvState st[4];
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    st[s] = InvState{0.0, 0.0, 0.0, 0.0};
+    const int gx = mirror(X0 - kFH + 2 * qj + (s & 1), lx), gy = mirror(Y0 - kFH + 2 * qi + (s >> 1), ly);
+    const int xo = (gx >> 1) + ((gx & 1) ? ax : 0), yo = (gy >> 1) + ((gy & 1) ? ay : 0);
+    coff[s] = unsigned((size_t)yo * cnx + xo);
+    if (s == 0)   // (a position clamped by mirror() can have the wrong parity: its value is never used,
+                  // the load only has to stay inside the box)
+      eoff0 = ((gx | gy) & 1) ? 0u
+                              : (a.apx_off >= 0 ? unsigned((gy >> 1) * ax + (gx >> 1))
+                                                : unsigned((size_t)(gy >> 1) * cnx + (gx >> 1)));
+  }
+  double* const zt = tile + (2 * qi) * kFP + 2 * qj;   // my quad in plane 0 of the tile
+
+  // ---- epilogue: my plane of the step and my rows in it ----
+  const int lane = tid & 31, warp = tid >> 5;
+  const int ep_p = warp >> 1, ep_r0 = (warp & 1) * kIRows;
+  const bool ep_warp = warp < 2 * kPlanes;
+  const bool ep_x = X0 + lane < lx;
+  const int ep_rows = ep_warp ? max(0, min(kIRows, ly - Y0 - ep_r0)) : 0;   // rows of mine inside the box
+  const double* const ep_t = tile + (size_t)ep_p * kFI * kFP + (kFH + ep_r0) * kFP + kFH + lane;
+  const unsigned long long vplane = a.vol.vx * a.vol.vy;
   const double ep_mean = ch.mean;
-  // offsets inside a z plane of the volume / of the chunk: c-th owned value at ep_g0 + c * ep_gs
-  const unsigned long long ep_g0 = (unsigned long long)(ch.y0 + Y0 + ep_warp) * a.vol.vx + (ch.x0 + X0 + ep_lane);
-  const unsigned long long ep_gs = 8ull * a.vol.vx;
-  const unsigned ep_c0 = unsigned((size_t)(Y0 + ep_warp) * cnx + X0 + ep_lane), ep_cs = unsigned(8 * cnx);
-  unsigned ep_live = 0;
-  for (int c = 0; c < 4; c++)
-    if (X0 + ep_lane < lx && Y0 + ep_warp + 8 * c < ly)
-      ep_live |= 1u << c;
-
-  // mode 1 with correctors: lane 4 p + c of every warp fetches the 32 corrector flags of the row
-  // the warp owns in plane p of the step (row Y0 + warp + 8 c) at the top of the step; the epilogue
-  // gets them by shuffle. The load is in flight during the lifting passes instead of standing,
-  // one dependent global load per value, between the epilogue's stores.
+  // offset of (lane, first row of mine) inside a z plane of the volume / of the chunk
+  const unsigned long long ep_g0 = (unsigned long long)(ch.y0 + Y0 + ep_r0) * a.vol.vx + (ch.x0 + X0 + lane);
+  const unsigned ep_c0 = unsigned((size_t)(Y0 + ep_r0) * cnx + X0 + lane);
+  double* const obox = (OUT == 0 && a.out_off >= 0) ? ch.scratch + a.out_off : nullptr;
+  // mode 1 with correctors: lane r < 16 fetches the 32 corrector flags of row r of the warp's plane
+  // at the top of the step (in flight during the lifting passes); the epilogue gets them by shuffle
   const uint32_t* const obits = (OUT == 1 && a.cor.key) ? ch.obits : nullptr;
-  const int fl_p = ep_lane >> 2, fl_c = ep_lane & 3;
-  const bool fl_row = ep_lane < 4 * kPlanes && Y0 + ep_warp + 8 * fl_c < ly;
-  const unsigned long long fl_i0 = (unsigned long long)(Y0 + ep_warp + 8 * fl_c) * cnx + X0;
-
-  // stage the z-phase inputs of a step: pair q -> (low band sample, high band sample) of my elements
-  double* const stg = tile + (size_t)kPlanes * kFI * kFP;   // [kNPB][2][kPer][kFThreads]
-  auto stage_step = [&](int j0) {
-#pragma unroll
-    for (int q = 0; q < kNPB; q++) {
-      const int j = j0 + q;
-      const int ze = mirror(2 * j, lz) >> 1, zo = az + (mirror(2 * j + 1, lz) >> 1);
-      const double* const pe = coef + (size_t)ze * cnxy;
-      const double* const po = coef + (size_t)zo * cnxy;
-      const double* const pa = abox + (size_t)ze * aplane;
-#pragma unroll
-      for (int s = 0; s < kPer; s++) {
-        if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
-          const double* const pz = ((apx >> s) & 1u) ? pa : pe;
-          ASSUME_GLOBAL(pz);
-          async_copy8(stg + ((size_t)(q * 2 + 0) * kPer + s) * kFThreads + tid, pz + eoff[s]);
-          async_copy8(stg + ((size_t)(q * 2 + 1) * kPer + s) * kFThreads + tid, po + coff[s]);
-        }
-      }
-    }
-  };
-  if (SPERR_INV_ASYNC)
-    stage_step(k0 - 2);
+  const unsigned fl_i0 = unsigned((size_t)(Y0 + ep_r0 + (lane & (kIRows - 1))) * cnx + X0);
 
   for (int j0 = k0 - 2; j0 <= k1 + 1; j0 += kNPB) {
+    // plane of mine in this step: pair kk = j0 + p / 2 - 2, sample z = 2 kk + p % 2
+    const int ep_kk = j0 + (ep_p >> 1) - 2;
+    const int ep_z = 2 * ep_kk + (ep_p & 1);
+    const bool ep_on = ep_warp && ep_kk >= k0 && ep_kk < k1 && ep_z < lz;   // warp-uniform
     unsigned flags = 0;
-    if (OUT == 1 && obits) {
-      const int kk = j0 + (fl_p >> 1) - 2;
-      const int z = 2 * kk + (fl_p & 1);
-      if (fl_row && kk >= k0 && kk < k1 && z < lz) {
-        const unsigned long long i0 = (unsigned long long)z * cnxy + fl_i0;
-        const unsigned sh = unsigned(i0 & 31);
-        unsigned long long w = __ldg(obits + (i0 >> 5));
-        if (sh)   // the row straddles two words (every chunk's flag array ends with a spare word)
-          w |= (unsigned long long)__ldg(obits + (i0 >> 5) + 1) << 32;
-        flags = unsigned(w >> sh);
-      }
+    if (OUT == 1 && obits && ep_on && lane < ep_rows) {
+      const unsigned i0 = unsigned(ep_z) * cnxy32 + fl_i0;
+      const unsigned sh = i0 & 31u;
+      unsigned long long w = __ldg(obits + (i0 >> 5));
+      if (sh)   // the row straddles two words (every chunk's flag array ends with a spare word)
+        w |= (unsigned long long)__ldg(obits + (i0 >> 5) + 1) << 32;
+      flags = unsigned(w >> sh);
     }
 #ifndef SPERR_EMUL
-    if (OUT == 2) {
-      // the source values the epilogue compares with: the same lane pulls the row's line into L2
-      const int kk = j0 + (fl_p >> 1) - 2;
-      const int z = 2 * kk + (fl_p & 1);
-      if (fl_row && kk >= k0 && kk < k1 && z < lz) {
-        const unsigned long long e = (unsigned long long)(cz0 + z) * ep_vplane + ep_g0 - ep_lane + fl_c * ep_gs;
-        const char* const ptr = reinterpret_cast<const char*>(a.vol.ptr) + e * (a.vol.is_float ? 4 : 8);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-        if (!a.vol.is_float)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 128));
-      }
+    if (OUT == 2 && ep_on && lane < ep_rows) {
+      // the source values the epilogue compares with: lane r pulls row r's line into L2
+      const unsigned long long e = (unsigned long long)(cz0 + ep_z) * vplane + ep_g0 - lane + (unsigned long long)lane * a.vol.vx;
+      const char* const ptr = reinterpret_cast<const char*>(a.vol.ptr) + e * (F32 ? 4 : 8);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+      if (!F32)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + 128));
     }
 #endif
     // ---- z: pair j = (low-band plane mirror(2j) / 2, high-band plane az + mirror(2j + 1) / 2) ----
-    if (SPERR_INV_ASYNC)
-      async_commit_wait_all();   // my own copies of this step have landed (nobody else reads them)
+    if (zthread) {
 #pragma unroll
-    for (int q = 0; q < kNPB; q++) {
-      double* const t0 = tile + (size_t)(2 * q) * kFI * kFP;
-      double ev[kPer], ov[kPer];
-      if (SPERR_INV_ASYNC) {
-#pragma unroll
-        for (int s = 0; s < kPer; s++)
-          if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
-            ev[s] = stg[((size_t)(q * 2 + 0) * kPer + s) * kFThreads + tid];
-            ov[s] = stg[((size_t)(q * 2 + 1) * kPer + s) * kFThreads + tid];
-          }
-      }
-      else {   // straight from global memory: pair j = (low-band plane mirror(2j) / 2, high-band plane az + mirror(2j + 1) / 2)
+      for (int q = 0; q < kNPB; q++) {
         const int j = j0 + q;
-        const int ze = mirror(2 * j, lz) >> 1, zo = az + (mirror(2 * j + 1, lz) >> 1);
-        const double* const pe = coef + (size_t)ze * cnxy;
-        const double* const po = coef + (size_t)zo * cnxy;
-        const double* const pa = abox + (size_t)ze * aplane;
+        // plane offsets as 32-bit element indices (a chunk holds < 2^31 values): one add and one
+        // widening multiply-add per load instead of 64-bit arithmetic per thread
+        const unsigned ze = unsigned(mirror(2 * j, lz) >> 1), zo = unsigned(az + (mirror(2 * j + 1, lz) >> 1));
+        const unsigned ie = ze * cnxy32, io = zo * cnxy32, ia = ze * aplane32;
+        double ev[4], ov[4];
+        ev[0] = abox[ia + eoff0];
 #pragma unroll
-        for (int s = 0; s < kPer; s++)
-          if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
-            const double* const pz = ((apx >> s) & 1u) ? pa : pe;
-            ASSUME_GLOBAL(pz);
-            ev[s] = pz[eoff[s]];
-            ov[s] = po[coff[s]];
-          }
-      }
+        for (int s = 1; s < 4; s++)
+          ev[s] = coef[ie + coff[s]];
 #pragma unroll
-      for (int s = 0; s < kPer; s++) {
-        if (s < kPer - 1 || tid + s * kFThreads < kFI * kFI) {
+        for (int s = 0; s < 4; s++)
+          ov[s] = coef[io + coff[s]];
+        double* const t0 = zt + (size_t)(2 * q) * kFI * kFP;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
           double x0, x1;
           inv_step<FMA>(k, st[s], ev[s], ov[s], x0, x1);
-          t0[sidx[s]] = x0;
-          t0[kFI * kFP + sidx[s]] = x1;
+          t0[(s >> 1) * kFP + (s & 1)] = x0;
+          t0[kFI * kFP + (s >> 1) * kFP + (s & 1)] = x1;
         }
       }
     }
     __syncthreads();
-    // the staging slots have been read: fetch the next step's inputs while this one is lifted
-    if (SPERR_INV_ASYNC && j0 + kNPB <= k1 + 1)
-      stage_step(j0 + kNPB);
     // planes 2 (j0 - 2) .. of the rebuilt box sit in the tile; pair q is wanted iff k0 <= j0+q-2 < k1
     // ---- columns (y) over all x of the tile, then rows (x) over the valid y ----
     if (tid < kPlanes * kFI)
@@ -753,68 +704,83 @@ __global__ void __launch_bounds__(kFThreads, 2) k_inv3d(FusedArgs a)
     if (tid < kPlanes * kFT)
       lift_line<true, FMA>(k, tile + (size_t)(tid / kFT) * kFI * kFP + (kFH + tid % kFT) * kFP, 1);
     __syncthreads();
-    // ---- epilogue: kPlanes x 32 x 32 values; a thread owns (lane, warp + 8 c) of every plane ----
-#pragma unroll
-    for (int p = 0; p < kPlanes; p++) {
-      const int kk = j0 + (p >> 1) - 2;
-      const int z = 2 * kk + (p & 1);
-      if (kk < k0 || kk >= k1 || z >= lz)   // uniform over the CTA
-        continue;
-      const double* const tp = tile + (size_t)p * kFI * kFP + (kFH + ep_warp) * kFP + kFH + ep_lane;
-      if (OUT == 0 && a.out_off >= 0) {
-        double* const ob = obox + (size_t)z * ly * lx;
+    // ---- epilogue: 16 rows x 32 values of one plane per warp. The common case (my rows and my x
+    // inside the box, no corrector in my rows) is a straight run of load / convert / store with
+    // compile-time offsets; everything else takes the general loops. ----
+    if (ep_on) {
+      const bool whole = ep_rows == kIRows && X0 + kFT <= lx;   // warp-uniform
+      if (OUT == 0 && obox) {
+        double* const ob = obox + ((size_t)ep_z * ly + Y0 + ep_r0) * lx + X0 + lane;
         ASSUME_GLOBAL(ob);
+        if (whole) {
 #pragma unroll
-        for (int c = 0; c < 4; c++)
-          if ((ep_live >> c) & 1u)
-            ob[(size_t)(Y0 + ep_warp + 8 * c) * lx + X0 + ep_lane] = tp[8 * c * kFP];
-        continue;
+          for (int r = 0; r < kIRows; r++)
+            ob[r * lx] = ep_t[r * kFP];
+        }
+        else if (ep_x) {
+          for (int r = 0; r < ep_rows; r++)
+            ob[r * lx] = ep_t[r * kFP];
+        }
       }
-      const unsigned long long gz = (unsigned long long)(cz0 + z) * ep_vplane;
-      if (OUT == 0) {
-        double* const vd = reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr)) + gz;
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-          if ((ep_live >> c) & 1u)
-            vd[ep_g0 + c * ep_gs] = tp[8 * c * kFP];
+      else if (OUT == 0) {
+        double* const vd = reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr)) + (unsigned long long)(cz0 + ep_z) * vplane + ep_g0;
+        if (ep_x)
+          for (int r = 0; r < ep_rows; r++)
+            vd[(unsigned long long)r * a.vol.vx] = ep_t[r * kFP];
       }
       else if (OUT == 1) {
-        const unsigned long long iz = (unsigned long long)z * cnxy;
+        typedef typename std::conditional<F32, float, double>::type TOut;
+        TOut* const vo = reinterpret_cast<TOut*>(const_cast<void*>(a.vol.ptr)) + (unsigned long long)(cz0 + ep_z) * vplane + ep_g0;
+        const unsigned long long vx = a.vol.vx;
+        const bool marked = obits && __any_sync(0xffffffffu, flags != 0);
+        if (whole && !marked) {
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          // flags of row c of plane p (all lanes take part in the shuffle)
-          const unsigned rowflags = obits ? __shfl_sync(0xffffffffu, flags, 4 * p + c) : 0u;
-          if (!((ep_live >> c) & 1u))
-            continue;
-          double w = tp[8 * c * kFP];
-          if ((rowflags >> ep_lane) & 1u) {   // src/SPECK_FLT.cpp:576-585: correctors are added before the mean
-            const unsigned long long i = iz + ep_c0 + c * ep_cs;
-            w = __dadd_rn(w, corrector_lookup(a.cor, a.ids[blockIdx.y], i));
+          for (int r = 0; r < kIRows; r++) {
+            const double w = __dadd_rn(ep_t[r * kFP], ep_mean);
+            vo[r * vx] = F32 ? TOut(__double2float_rn(w)) : TOut(w);
           }
-          w = __dadd_rn(w, ep_mean);
-          if (a.vol.is_float)
-            reinterpret_cast<float*>(const_cast<void*>(a.vol.ptr))[gz + ep_g0 + c * ep_gs] = __double2float_rn(w);
-          else
-            reinterpret_cast<double*>(const_cast<void*>(a.vol.ptr))[gz + ep_g0 + c * ep_gs] = w;
+        }
+        else {
+          const unsigned iz = unsigned(ep_z) * cnxy32 + ep_c0;
+          for (int r = 0; r < kIRows; r++) {   // (all lanes take part in the shuffle)
+            const unsigned rowflags = __shfl_sync(0xffffffffu, flags, r);
+            if (r < ep_rows && ep_x) {
+              double w = ep_t[r * kFP];
+              if ((rowflags >> lane) & 1u)   // src/SPECK_FLT.cpp:576-585: correctors are added before the mean
+                w = __dadd_rn(w, corrector_value(a.cor, cid, iz + unsigned(r) * unsigned(cnx)));
+              w = __dadd_rn(w, ep_mean);
+              vo[r * vx] = F32 ? TOut(__double2float_rn(w)) : TOut(w);
+            }
+          }
         }
       }
       else {
-        // the four source values first (independent loads in flight), then the comparisons
-        double orig[4];
+        typedef typename std::conditional<F32, float, double>::type TIn;
+        const TIn* const vi = reinterpret_cast<const TIn*>(a.vol.ptr) + (unsigned long long)(cz0 + ep_z) * vplane + ep_g0;
+        const unsigned long long vx = a.vol.vx;
+        const unsigned iz = unsigned(ep_z) * cnxy32 + ep_c0;
+        if (whole) {
+          // the source values first (independent loads in flight), then the comparisons
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          orig[c] = 0.0;
-          if ((ep_live >> c) & 1u)
-            orig[c] = a.vol.is_float ? double(__ldg(reinterpret_cast<const float*>(a.vol.ptr) + gz + ep_g0 + c * ep_gs))
-                                     : __ldg(reinterpret_cast<const double*>(a.vol.ptr) + gz + ep_g0 + c * ep_gs);
+          for (int h = 0; h < kIRows; h += 8) {
+            double orig[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+              orig[r] = double(__ldg(vi + (h + r) * vx));
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+              const double diff = __dsub_rn(__dsub_rn(orig[r], ep_mean), ep_t[(h + r) * kFP]);
+              if (fabs(diff) > a.tol)
+                outlier_append(a.sink, cid, iz + unsigned(h + r) * unsigned(cnx), diff);
+            }
+          }
         }
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          if (!((ep_live >> c) & 1u))
-            continue;
-          const double diff = __dsub_rn(__dsub_rn(orig[c], ep_mean), tp[8 * c * kFP]);
-          if (fabs(diff) > a.tol)
-            outlier_append(a.sink, a.ids[blockIdx.y], (unsigned long long)z * cnxy + ep_c0 + c * ep_cs, diff);
+        else if (ep_x) {
+          for (int r = 0; r < ep_rows; r++) {
+            const double diff = __dsub_rn(__dsub_rn(double(__ldg(vi + r * vx)), ep_mean), ep_t[r * kFP]);
+            if (fabs(diff) > a.tol)
+              outlier_append(a.sink, cid, iz + unsigned(r) * unsigned(cnx), diff);
+          }
         }
       }
     }
@@ -960,15 +926,19 @@ static void fused_attrs()
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   const int smi = int(kInvSmem);
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+#define SPERR_INV_ATTR(O) \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi)); \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  SPERR_INV_ATTR(1)
+  SPERR_INV_ATTR(2)
+#undef SPERR_INV_ATTR
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmaSmem)));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTmaSmem)));
 #endif
@@ -1054,17 +1024,39 @@ void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chu
     dim3 grid;
     fused_grid(a, nids, grid);
     const int which = (l > 0 || mode == 0) ? 0 : (mode == 1 ? 1 : 2);
-#define SPERR_INV(O, F) LAUNCH((k_inv3d<O, F>), grid, dim3(kFThreads), kInvSmem, st, a)
+    if (which == 2) {
+      // The outlier scan runs beside the SPECK3D encoder, whose kernels have priority (pipeline.cu):
+      // short-lived CTAs (about 32 sample pairs each instead of the whole z extent, 4 of them
+      // recomputed) hand their slots over quickly.
+      static const int seg_pairs = std::getenv("SPERR_B200_SCAN_SEG_PAIRS") ? std::atoi(std::getenv("SPERR_B200_SCAN_SEG_PAIRS")) : 32;
+      const int az = a.lz - a.lz / 2;
+      if (seg_pairs > 0) {
+        int zs = a.zsegs;
+        while (az / (zs * 2) >= seg_pairs)
+          zs *= 2;
+        a.zsegs = zs;
+        grid = dim3(unsigned(a.tiles_x * a.tiles_y * zs), unsigned(nids));
+      }
+    }
+#define SPERR_INV(O, F, T) LAUNCH((k_inv3d<O, F, T>), grid, dim3(kIThreads), kInvSmem, st, a)
+#define SPERR_INV_T(O, F)        \
+  do {                           \
+    if (vol.is_float)            \
+      SPERR_INV(O, F, true);     \
+    else                         \
+      SPERR_INV(O, F, false);    \
+  } while (0)
     if (a.k.fma) {
-      if (which == 0) SPERR_INV(0, true);
-      else if (which == 1) SPERR_INV(1, true);
-      else SPERR_INV(2, true);
+      if (which == 0) SPERR_INV(0, true, false);
+      else if (which == 1) SPERR_INV_T(1, true);
+      else SPERR_INV_T(2, true);
     }
     else {
-      if (which == 0) SPERR_INV(0, false);
-      else if (which == 1) SPERR_INV(1, false);
-      else SPERR_INV(2, false);
+      if (which == 0) SPERR_INV(0, false, false);
+      else if (which == 1) SPERR_INV_T(1, false);
+      else SPERR_INV_T(2, false);
     }
+#undef SPERR_INV_T
 #undef SPERR_INV
   }
 }

@@ -405,9 +405,10 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
       rt::ProfScope ps("c.outlier_encode", s);
       out_.encode(tl, quality, out_res_, s);
     };
+    cudaStream_t enc_st = st;
     auto speck_chain = [&] {
-      rt::ProfScope ps("c.speck3d", st);
-      enc.encode(b_.dev(), b_.h, b_.dev_shapes(), b_.shapes, res, st);
+      rt::ProfScope ps("c.speck3d", enc_st);
+      enc.encode(b_.dev(), b_.h, b_.dev_shapes(), b_.shapes, res, enc_st);
     };
     if (mode != kModePWE) {
       speck_chain();
@@ -423,6 +424,21 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     }
     RT_CHECK(cudaEventRecord(side_ev_, st));
     RT_CHECK(cudaStreamWaitEvent(side_, side_ev_, 0));
+    // Both chains share the GPU. The encoder is the longer one and mostly small, latency-bound
+    // launches; the outlier chain starts with two bandwidth kernels that fill every SM (measured:
+    // enc.lipref_count 15 ms beside k_inv3d<2>, 3.3 ms alone). With the encoder on a stream of the
+    // highest priority the block scheduler hands freed CTA slots to its kernels first (the inverse
+    // transform of the outlier chain runs in short z segments for that reason, dwt_fused.cu).
+    if (!std::getenv("SPERR_B200_NO_PRIO")) {
+      if (!hi_) {
+        int least = 0, greatest = 0;
+        RT_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        RT_CHECK(cudaStreamCreateWithPriority(&hi_, cudaStreamNonBlocking, greatest));
+        RT_CHECK(cudaEventCreateWithFlags(&hi_ev_, cudaEventDisableTiming));
+      }
+      RT_CHECK(cudaStreamWaitEvent(hi_, side_ev_, 0));
+      enc_st = hi_;
+    }
     int dev = 0;
     RT_CHECK(cudaGetDevice(&dev));
     // Experiment (SPERR_B200_STAGGER=1, off by default): both chains start with their
@@ -487,6 +503,10 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     enc.set_before_plane_loop(nullptr);
     gate.release();   // (no-op unless the encoder had nothing to code)
     helper.join();
+    if (enc_st != st) {   // (the encoder has synchronised its stream; this orders later work on st after it)
+      RT_CHECK(cudaEventRecord(hi_ev_, enc_st));
+      RT_CHECK(cudaStreamWaitEvent(st, hi_ev_, 0));
+    }
     if (side_err)
       std::rethrow_exception(side_err);
 #endif

@@ -50,6 +50,10 @@ class Compressor {
 #ifndef SPERR_EMUL
   cudaStream_t side_ = nullptr;   // PWE: the outlier path runs beside the SPECK3D encoder
   cudaEvent_t side_ev_ = nullptr;
+  // PWE: the SPECK3D encoder (the critical path) runs on a stream of the highest priority, so that
+  // CTA slots the outlier path's bandwidth kernels free go to the encoder's kernels first
+  cudaStream_t hi_ = nullptr;
+  cudaEvent_t hi_ev_ = nullptr;
   cudaEvent_t stagger_ev_ = nullptr;   // SPERR_B200_STAGGER: the encoder has reached its bit-plane loop
 #endif
 };

@@ -321,6 +321,7 @@ struct ProfEntry {
   const char* name;
 #ifndef SPERR_EMUL
   cudaEvent_t e0, e1;
+  int dev;
 #endif
 };
 struct ProfState {
@@ -328,24 +329,106 @@ struct ProfState {
   std::mutex mu;   // ranges may be recorded by the pipelines' helper threads
   std::vector<ProfEntry> open;                       // recorded, not yet resolved
   std::map<std::string, std::pair<double, long>> acc;  // name -> (ms, ranges)
+#ifndef SPERR_EMUL
+  // Events are REUSED. Creating two per range inside a timed loop (the first version) stalled the
+  // host now and then for 15 - 110 ms -- measured on B200: steps of 119 ms became 130 - 230 ms one
+  // time in three with the profiler on, never with it off -- presumably when the driver has to grow
+  // its event storage under a busy GPU. The pool is filled when the profiler is switched on and
+  // finished ranges hand their events back as soon as a later range finds them complete.
+  std::map<int, std::vector<cudaEvent_t>> pool;      // per device
+#endif
 };
 inline ProfState& prof()
 {
   static ProfState s;
   return s;
 }
+#ifndef SPERR_EMUL
+// diagnosis: SPERR_B200_PROF_NOTIMING=1 records events without time stamps (all ranges read 0 ms)
+inline unsigned prof_event_flags()
+{
+  static const bool notiming = std::getenv("SPERR_B200_PROF_NOTIMING") != nullptr;
+  return notiming ? cudaEventDisableTiming : cudaEventDefault;
+}
+inline cudaEvent_t prof_event_locked(int dev)
+{
+  auto& v = prof().pool[dev];
+  if (!v.empty()) {
+    cudaEvent_t e = v.back();
+    v.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreateWithFlags(&e, prof_event_flags());
+  return e;
+}
+// resolves the ranges at the front of the list that have completed (never waits)
+inline void prof_resolve_done_locked(bool wait)
+{
+  auto& open = prof().open;
+  size_t done = 0;
+  for (; done < open.size(); done++) {
+    ProfEntry& e = open[done];
+    if (wait)
+      cudaEventSynchronize(e.e1);
+    else if (cudaEventQuery(e.e1) != cudaSuccess) {
+      cudaGetLastError();
+      break;
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e.e0, e.e1) != cudaSuccess) {
+      cudaGetLastError();
+      if (!wait)
+        break;
+    }
+    auto& a = prof().acc[e.name];
+    a.first += ms;
+    a.second += 1;
+    auto& v = prof().pool[e.dev];
+    v.push_back(e.e0);
+    v.push_back(e.e1);
+  }
+  open.erase(open.begin(), open.begin() + done);
+}
+// fills the current device's pool (called when the profiler is switched on, outside any timed region)
+inline void prof_reserve(size_t events)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> l(prof().mu);
+  auto& v = prof().pool[dev];
+  while (v.size() < events) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, prof_event_flags()) != cudaSuccess) {
+      cudaGetLastError();
+      break;
+    }
+    v.push_back(e);
+  }
+}
+#endif
 struct ProfScope {
 #ifndef SPERR_EMUL
   cudaStream_t st;
   ProfEntry e;
   bool live;
-  ProfScope(const char* name, cudaStream_t s) : st(s), live(prof().on)
+  // diagnosis: SPERR_B200_PROF_ONLY=<prefix> records only the ranges whose name starts with it
+  static bool wanted(const char* name)
+  {
+    static const char* only = std::getenv("SPERR_B200_PROF_ONLY");
+    return !only || std::strncmp(name, only, std::strlen(only)) == 0;
+  }
+  ProfScope(const char* name, cudaStream_t s) : st(s), live(prof().on && wanted(name))
   {
     if (!live)
       return;
     e.name = name;
-    cudaEventCreate(&e.e0);
-    cudaEventCreate(&e.e1);
+    cudaGetDevice(&e.dev);
+    {
+      std::lock_guard<std::mutex> l(prof().mu);
+      e.e0 = prof_event_locked(e.dev);
+      e.e1 = prof_event_locked(e.dev);
+    }
     cudaEventRecord(e.e0, st);
   }
   ~ProfScope()
@@ -355,6 +438,8 @@ struct ProfScope {
     cudaEventRecord(e.e1, st);
     std::lock_guard<std::mutex> l(prof().mu);
     prof().open.push_back(e);
+    if (prof().open.size() >= 256)
+      prof_resolve_done_locked(false);
   }
 #else
   ProfScope(const char*, cudaStream_t) {}
@@ -364,16 +449,8 @@ struct ProfScope {
 inline void prof_collect()
 {
 #ifndef SPERR_EMUL
-  for (auto& e : prof().open) {
-    cudaEventSynchronize(e.e1);
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e.e0, e.e1);
-    auto& a = prof().acc[e.name];
-    a.first += ms;
-    a.second += 1;
-    cudaEventDestroy(e.e0);
-    cudaEventDestroy(e.e1);
-  }
+  std::lock_guard<std::mutex> l(prof().mu);
+  prof_resolve_done_locked(true);
 #endif
   prof().open.clear();
 }
