@@ -95,6 +95,7 @@ class Clocks:
     def __init__(self, index, idle=False):
         self.index = index
         self.samples = []
+        self.first = 0
         self.stop = idle   # idle: no sampling at all (--diag noclocks)
         self.t = threading.Thread(target=self.run, daemon=True)
 
@@ -140,16 +141,21 @@ class Clocks:
         self.t.start()
         return self
 
+    def mark(self):
+        """drops the samples taken so far (the sampler is started before the warm-up)"""
+        self.first = len(self.samples)
+
     def __exit__(self, *a):
         self.stop = True
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = [int(s[0]) for s in self.samples if len(s) >= 6 and s[0].isdigit()]
-        mx = [int(s[1]) for s in self.samples if len(s) >= 6 and s[1].isdigit()]
+        samples = self.samples[self.first:]
+        sm = [int(s[0]) for s in samples if len(s) >= 6 and s[0].isdigit()]
+        mx = [int(s[1]) for s in samples if len(s) >= 6 and s[1].isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in samples:
             if len(s) >= 6:
                 for i, n in enumerate(names):
                     if s[2 + i].lower().startswith("active"):
@@ -406,16 +412,38 @@ def measure(args, L, dev, rank, world, scaling, full):
         b, _ = sharded.decompress_3d_sharded(L.lib, stream, dev, True, out=out_box)
         state["out"] = b
 
+    host_split = []   # host wall time of the two calls of every step (ms): shows which call a stall sits in
+
     def step_dev():
+        t0 = time.perf_counter()
         stream = comp_dev()
+        t1 = time.perf_counter()
         decomp_dev(stream)
+        host_split.append((round((t1 - t0) * 1e3, 1), round((time.perf_counter() - t1) * 1e3, 1)))
         return stream
 
     prof_on = L.fn("sperr_b200_prof_enable", None, [C.c_int])
     prof_dump = L.fn("sperr_b200_prof_dump", C.c_size_t, [C.c_char_p, C.c_size_t])
 
+    # Everything that is set up once goes BEFORE the warm-up, so that the warm-up steps absorb it: the
+    # clock sampler (NVML initialisation enumerates every GPU of the box), the first NCCL collectives
+    # (communicator and its lazily connected transports), the profiler's event pool. Started at the
+    # top of the timed loop instead (round 1 and the first half of round 2) they stalled the host
+    # side of the first timed steps by 20 - 100 ms each, one run in two: measured with
+    # step_host_ms_each below, stage ranges unaffected, later steps clean.
+    diag = set(x for x in args.diag.split(",") if x)
+    clk = Clocks(local_index(dev), idle="noclocks" in diag)
+    clk.__enter__()
+    barrier()
+    barrier()
+    prof_on(0 if "noprof" in diag else 1)
+    t_warm = time.perf_counter()
     for _ in range(args.warmup):
         stream = step_dev()
+    extra = 0
+    while time.perf_counter() - t_warm < args.settle and extra < 16:   # (extra warm-up steps, reported)
+        stream = step_dev()
+        extra += 1
     barrier()
     # the host side of a step is hundreds of launches and tens of read-backs: keep the
     # interpreter's cyclic collector from running in the middle of one
@@ -424,8 +452,8 @@ def measure(args, L, dev, rank, world, scaling, full):
     gc.disable()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launch_count = L.fn("sperr_b200_launch_count", C.c_ulonglong, [])
-    diag = set(x for x in args.diag.split(",") if x)
-    with Clocks(local_index(dev), idle="noclocks" in diag) as clk:
+    clk.mark()   # only samples taken from here on count
+    if True:
         barrier()
         l0 = launch_count()
         # stage ranges: CUDA events the library records on the stream each kernel (family) is
@@ -447,9 +475,11 @@ def measure(args, L, dev, rank, world, scaling, full):
         stages = json.loads(buf.value.decode())
         for v in stages.values():
             v["ms"] /= steps
+    clk.__exit__()
     if diag:   # diagnosis run: the per-step times are all that is wanted
         if rank == 0:
-            print(json.dumps({"diag": sorted(diag), "step_ms_each": [round(x, 2) for x in step_each]}))
+            print(json.dumps({"diag": sorted(diag), "step_ms_each": [round(x, 2) for x in step_each],
+                              "host_ms_each": host_split[-steps:]}))
         gc.enable()
         return None
     ms = e0.elapsed_time(e1) / steps
@@ -492,11 +522,15 @@ def measure(args, L, dev, rank, world, scaling, full):
             "dtype": "f64", "data": "synthetic", "config": workload_config(world, scaling, n),
             "stream_bytes": int(stream.size), "bpp": stream.size * 8.0 / nvals,
             "clocks": clk.summary(), "stages_ms": {k: round(v["ms"], 3) for k, v in stages.items()},
+            # longest host wall time between the two records of a stage's ranges (ms): a host-side stall shows here
+            "stages_host_max_ms": {k: round(v.get("host_max_ms", 0.0), 1) for k, v in stages.items()},
             "compress_gbs": total_bytes / (ms_c * 1e-3) / GB,
             "decompress_gbs": total_bytes / (ms_d * 1e-3) / GB, "max_abs_err": maxerr,
             "gpu_launches": launches_per_step,
             # rank 0's individual calls (ms): a host-side stall in one call shows here
-            "step_ms_each": [round(x, 2) for x in step_each], "compress_ms_each": each["compress"],
+            "warmup_extra_steps": extra,
+            "step_ms_each": [round(x, 2) for x in step_each], "step_host_ms_each": host_split[-steps:],
+            "compress_ms_each": each["compress"],
             "decompress_ms_each": each["decompress"],
         }
         # rank 0's stage times over rank 0's share of the values
@@ -660,6 +694,8 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=("strong", "weak"))
     ap.add_argument("--weak-extra", type=int, default=1, help="N > 1: also report the weak-scaled run as extra.weak")
     ap.add_argument("--check", type=int, default=1, help="rank 0 checks the container bytes after the timed loops")
+    ap.add_argument("--settle", type=float, default=1.5,
+                    help="warm up for at least this many seconds (extra untimed steps beyond --warmup)")
     ap.add_argument("--diag", default="", help="diagnosis of host-side stalls: comma list of noclocks, noprof")
     args = ap.parse_args()
     if args.impl == "reference":

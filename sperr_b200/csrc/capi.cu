@@ -990,6 +990,7 @@ void sperr_b200_prof_enable(int on)
   if (on) {
     rt::prof_collect();   // ranges left over from an earlier session hand their events back
     rt::prof().acc.clear();
+    rt::prof().host.clear();
 #ifndef SPERR_EMUL
     rt::prof_reserve(4096);   // outside any timed region: the ranges of a timed loop only take from the pool
 #endif
@@ -1003,8 +1004,11 @@ size_t sperr_b200_prof_dump(char* buf, size_t cap)
   bool first = true;
   for (auto& kv : rt::prof().acc) {
     char tmp[256];
-    std::snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"n\": %ld}", first ? "" : ", ",
-                  kv.first.c_str(), kv.second.first, kv.second.second);
+    const auto hit = rt::prof().host.find(kv.first);
+    const double hsum = hit == rt::prof().host.end() ? 0.0 : hit->second.first;
+    const double hmax = hit == rt::prof().host.end() ? 0.0 : hit->second.second;
+    std::snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"ms\": %.6f, \"n\": %ld, \"host_ms\": %.3f, \"host_max_ms\": %.3f}",
+                  first ? "" : ", ", kv.first.c_str(), kv.second.first, kv.second.second, hsum, hmax);
     s += tmp;
     first = false;
   }

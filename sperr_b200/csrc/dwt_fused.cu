@@ -569,6 +569,12 @@ __device__ __noinline__ double corrector_value(const CorrectorList l, unsigned c
   return corrector_lookup(l, chunk, pos);
 }
 
+// SPERR_INV_PREFETCH=1: L2 prefetch of the next step's z-phase inputs. Measured on B200 (1024^3):
+// d.idwt 9.34 ms with it, 9.23 ms without -- two CTAs per SM already overlap one CTA's loads with
+// the other's lifting -- so it is off.
+#ifndef SPERR_INV_PREFETCH
+#define SPERR_INV_PREFETCH 0
+#endif
 constexpr int kIThreads = 416;
 constexpr int kIQuads = kFNP * kFNP;   // 400
 static_assert(kIQuads <= kIThreads && kPlanes * kFI <= kIThreads && 2 * kPlanes <= kIThreads / 32, "roles");
@@ -625,6 +631,9 @@ __global__ void __launch_bounds__(kIThreads, 2) k_inv3d(FusedArgs a)
                                                 : unsigned((size_t)(gy >> 1) * cnx + (gx >> 1)));
   }
   double* const zt = tile + (2 * qi) * kFP + 2 * qj;   // my quad in plane 0 of the tile
+#if SPERR_INV_PREFETCH
+  const bool pf_thread = zthread && ((qj & 3) == 0 || qj == kFNP - 1);
+#endif
 
   // ---- epilogue: my plane of the step and my rows in it ----
   const int lane = tid & 31, warp = tid >> 5;
@@ -669,6 +678,26 @@ __global__ void __launch_bounds__(kIThreads, 2) k_inv3d(FusedArgs a)
     }
 #endif
     // ---- z: pair j = (low-band plane mirror(2j) / 2, high-band plane az + mirror(2j + 1) / 2) ----
+#if SPERR_INV_PREFETCH && !defined(SPERR_EMUL)
+    // the inputs of the NEXT step: every fourth quad of a quad row pulls the lines of its eight loads
+    // into L2 now (a quad row reads 20 consecutive doubles per sub-band: the lines of quads 0, 4, ..
+    // 16 and of the last one cover them), so that the loads of the next step see L2 latency
+    if (pf_thread && j0 + kNPB <= k1 + 1) {
+#pragma unroll
+      for (int q = 0; q < kNPB; q++) {
+        const int j = j0 + kNPB + q;
+        const unsigned ze = unsigned(mirror(2 * j, lz) >> 1), zo = unsigned(az + (mirror(2 * j + 1, lz) >> 1));
+        const unsigned ie = ze * cnxy32, io = zo * cnxy32, ia = ze * aplane32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(abox + (ia + eoff0)));
+#pragma unroll
+        for (int s = 1; s < 4; s++)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(coef + (ie + coff[s])));
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(coef + (io + coff[s])));
+      }
+    }
+#endif
     if (zthread) {
 #pragma unroll
       for (int q = 0; q < kNPB; q++) {
@@ -1028,7 +1057,7 @@ void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chu
       // The outlier scan runs beside the SPECK3D encoder, whose kernels have priority (pipeline.cu):
       // short-lived CTAs (about 32 sample pairs each instead of the whole z extent, 4 of them
       // recomputed) hand their slots over quickly.
-      static const int seg_pairs = std::getenv("SPERR_B200_SCAN_SEG_PAIRS") ? std::atoi(std::getenv("SPERR_B200_SCAN_SEG_PAIRS")) : 32;
+      static const int seg_pairs = std::getenv("SPERR_B200_SCAN_SEG_PAIRS") ? std::atoi(std::getenv("SPERR_B200_SCAN_SEG_PAIRS")) : 0;   // off: measured, no gain
       const int az = a.lz - a.lz / 2;
       if (seg_pairs > 0) {
         int zs = a.zsegs;

@@ -429,7 +429,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     // enc.lipref_count 15 ms beside k_inv3d<2>, 3.3 ms alone). With the encoder on a stream of the
     // highest priority the block scheduler hands freed CTA slots to its kernels first (the inverse
     // transform of the outlier chain runs in short z segments for that reason, dwt_fused.cu).
-    if (!std::getenv("SPERR_B200_NO_PRIO")) {
+    if (std::getenv("SPERR_B200_PRIO")) {   // measured: no gain, off by default
       if (!hi_) {
         int least = 0, greatest = 0;
         RT_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));

@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -329,6 +331,9 @@ struct ProfState {
   std::mutex mu;   // ranges may be recorded by the pipelines' helper threads
   std::vector<ProfEntry> open;                       // recorded, not yet resolved
   std::map<std::string, std::pair<double, long>> acc;  // name -> (ms, ranges)
+  // host wall time between the two records of a range: (sum, longest) in ms -- a host-side stall
+  // (a blocked API call, a descheduled thread) shows here and not in the device times
+  std::map<std::string, std::pair<double, double>> host;
 #ifndef SPERR_EMUL
   // Events are REUSED. Creating two per range inside a timed loop (the first version) stalled the
   // host now and then for 15 - 110 ms -- measured on B200: steps of 119 ms became 130 - 230 ms one
@@ -412,6 +417,7 @@ struct ProfScope {
   cudaStream_t st;
   ProfEntry e;
   bool live;
+  std::chrono::steady_clock::time_point t0;
   // diagnosis: SPERR_B200_PROF_ONLY=<prefix> records only the ranges whose name starts with it
   static bool wanted(const char* name)
   {
@@ -430,13 +436,18 @@ struct ProfScope {
       e.e1 = prof_event_locked(e.dev);
     }
     cudaEventRecord(e.e0, st);
+    t0 = std::chrono::steady_clock::now();
   }
   ~ProfScope()
   {
     if (!live)
       return;
     cudaEventRecord(e.e1, st);
+    const double hms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::lock_guard<std::mutex> l(prof().mu);
+    auto& h = prof().host[e.name];
+    h.first += hms;
+    h.second = std::max(h.second, hms);
     prof().open.push_back(e);
     if (prof().open.size() >= 256)
       prof_resolve_done_locked(false);

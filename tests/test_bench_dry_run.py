@@ -45,7 +45,7 @@ real_load = api.load
 sperr_b200.load = lambda path=None: real_load(%(emul)r)
 
 import bench
-sys.argv = ["bench.py", "--size", "32", "--steps", "2", "--warmup", "1", "--e2e", "0", "--cpu-baseline", "0"]
+sys.argv = ["bench.py", "--size", "32", "--steps", "2", "--warmup", "1", "--e2e", "0", "--cpu-baseline", "0", "--settle", "0"]
 bench.main()
 """
 
