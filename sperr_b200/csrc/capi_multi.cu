@@ -88,7 +88,7 @@ struct Barrier {   // std::barrier is C++20
 
 // Per-device staging of this file: the device copy of the box and a ring of pinned slots.
 constexpr int kRing = 4;
-constexpr size_t kSlot = size_t(16) << 20;
+constexpr size_t kSlot = size_t(32) << 20;
 struct MultiState {
   rt::DBuf box;
   void* slot[kRing] = {nullptr, nullptr, nullptr, nullptr};
@@ -141,22 +141,68 @@ struct BoxMap {
 
 bool pinned(const void* p) { return rt::is_pinned_host(p); }
 
+// Host copies between the caller's (pageable) box and a pinned slot, spread over a few threads: one
+// thread moves 5 - 10 GB/s, a PCIe 5 x16 link takes 55. `nthreads` is what the box's cores allow per
+// device (all devices stage at the same time).
+struct Seg {
+  char* dst;
+  const char* src;
+  size_t n;
+};
+void par_copy(const std::vector<Seg>& segs, int nthreads)
+{
+  size_t total = 0;
+  for (const Seg& g : segs)
+    total += g.n;
+  if (nthreads <= 1 || total < (size_t(4) << 20)) {
+    for (const Seg& g : segs)
+      std::memcpy(g.dst, g.src, g.n);
+    return;
+  }
+  auto share = [&](int k) {   // bytes [lo, hi) of the concatenated segments
+    const size_t lo = total * size_t(k) / size_t(nthreads), hi = total * size_t(k + 1) / size_t(nthreads);
+    size_t pos = 0;
+    for (const Seg& g : segs) {
+      const size_t a = std::max(lo, pos), b = std::min(hi, pos + g.n);
+      if (a < b)
+        std::memcpy(g.dst + (a - pos), g.src + (a - pos), b - a);
+      pos += g.n;
+      if (pos >= hi)
+        break;
+    }
+  };
+  std::vector<std::thread> th;
+  for (int k = 1; k < nthreads; k++)
+    th.emplace_back(share, k);
+  share(0);
+  for (auto& t : th)
+    t.join();
+}
+int copy_threads(int ndev)
+{
+  const int hw = int(std::thread::hardware_concurrency());
+  return std::max(1, std::min(6, (hw > 2 ? hw - 2 : 1) / std::max(1, ndev)));
+}
+
 // host box -> device (linear box layout)
-void box_h2d(MultiState& m, void* d_box, const BoxMap& b)
+void box_h2d(MultiState& m, void* d_box, const BoxMap& b, int nthreads)
 {
   size_t done = 0;
+  std::vector<Seg> segs;
   for (size_t i = 0; done < b.bytes; i++) {
     const int s = int(i % kRing);
     const size_t len = std::min(kSlot, b.bytes - done);
     if (i >= size_t(kRing))
       RT_CHECK(cudaEventSynchronize(m.ev[s]));
+    segs.clear();
     for (size_t o = 0; o < len;) {
       size_t left;
       const char* src = b.at(done + o, left);
       const size_t c = std::min(left, len - o);
-      std::memcpy(static_cast<char*>(m.slot[s]) + o, src, c);
+      segs.push_back(Seg{static_cast<char*>(m.slot[s]) + o, src, c});
       o += c;
     }
+    par_copy(segs, nthreads);
     RT_CHECK(cudaMemcpyAsync(static_cast<char*>(d_box) + done, m.slot[s], len, cudaMemcpyHostToDevice, m.st));
     RT_CHECK(cudaEventRecord(m.ev[s], m.st));
     done += len;
@@ -165,20 +211,23 @@ void box_h2d(MultiState& m, void* d_box, const BoxMap& b)
 }
 
 // device (linear box layout) -> host box
-void box_d2h(MultiState& m, const void* d_box, const BoxMap& b)
+void box_d2h(MultiState& m, const void* d_box, const BoxMap& b, int nthreads)
 {
   const size_t n = (b.bytes + kSlot - 1) / kSlot;
+  std::vector<Seg> segs;
   auto drain = [&](size_t i) {
     const int s = int(i % kRing);
     const size_t off = i * kSlot, len = std::min(kSlot, b.bytes - off);
     RT_CHECK(cudaEventSynchronize(m.ev[s]));
+    segs.clear();
     for (size_t o = 0; o < len;) {
       size_t left;
       char* dst = b.at(off + o, left);
       const size_t c = std::min(left, len - o);
-      std::memcpy(dst, static_cast<const char*>(m.slot[s]) + o, c);
+      segs.push_back(Seg{dst, static_cast<const char*>(m.slot[s]) + o, c});
       o += c;
     }
+    par_copy(segs, nthreads);   // (the threads also fault the pages of the fresh result buffer in)
   };
   for (size_t i = 0; i < n; i++) {
     if (i >= size_t(kRing))
@@ -240,7 +289,7 @@ int comp_3d_multi(const void* src, int is_float, const size_t vol[3], const size
         throw std::runtime_error("chunk box");
       const BoxMap bm(src, vol, org, ext, esz);
       m.box.reserve(bm.bytes);
-      box_h2d(m, m.box.p, bm);
+      box_h2d(m, m.box.p, bm, copy_threads(nd));
       size_t n = 0;
       rcs[d] = sperr_b200_comp_3d_range_dev(m.box.p, is_float, vol, cd, org, ext, begins[d], begins[d + 1], mode,
                                             quality, &d_streams, &n, lens.data() + begins[d]);
@@ -355,7 +404,7 @@ int decomp_3d_multi(const void* src, size_t src_len, int output_float, const std
       if (rc != 0)
         failed = 1;
       else
-        box_d2h(m, m.box.p, bm);
+        box_d2h(m, m.box.p, bm, copy_threads(nd));
     }
     catch (const std::exception& e) {
       if (std::getenv("SPERR_B200_VERBOSE"))

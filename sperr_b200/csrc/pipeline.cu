@@ -464,14 +464,26 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
         cv.wait(l, [this] { return open; });
       }
     } gate;
-    const bool stagger = std::getenv("SPERR_B200_STAGGER") != nullptr;
+    // Where the outlier chain is let go (SPERR_B200_GATE): "none" (default) at once; "setup" when the
+    // encoder has queued the zeroing of its staging arrays and tables; "loop" (the SPERR_B200_STAGGER
+    // experiment) when it enters its bit-plane loop. Measured on B200 (1024^3): compress 53.5 / 53.2 /
+    // 53.2 ms, c.speck3d 40.1 / 40.8 / 40.7 ms -- the gate only moves the contention (none:
+    // enc.stage_zero 6.9, pyramid 5.9, plane loop 16.4 ms; setup: 0.3, 3.0, 23.9; loop: 0.3, 3.0,
+    // 26.6): both chains need the whole GPU for about as long as they run, and the sum is what it is.
+    const char* const gate_env = std::getenv("SPERR_B200_GATE");
+    const std::string gate_at = std::getenv("SPERR_B200_STAGGER") ? "loop" : (gate_env ? gate_env : "none");
+    const bool stagger = gate_at == "loop" || gate_at == "setup";
     if (stagger) {
       if (!stagger_ev_)
         RT_CHECK(cudaEventCreateWithFlags(&stagger_ev_, cudaEventDisableTiming));
-      enc.set_before_plane_loop([&](cudaStream_t s) {
+      auto open_gate = [&](cudaStream_t s) {
         RT_CHECK(cudaEventRecord(stagger_ev_, s));
         gate.release();
-      });
+      };
+      if (gate_at == "loop")
+        enc.set_before_plane_loop(open_gate);
+      else
+        enc.set_after_setup(open_gate);
     }
     else
       gate.release();
@@ -496,11 +508,13 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     }
     catch (...) {
       enc.set_before_plane_loop(nullptr);
+      enc.set_after_setup(nullptr);
       gate.release();   // the encoder may have failed before it reached its plane loop
       helper.join();
       throw;
     }
     enc.set_before_plane_loop(nullptr);
+    enc.set_after_setup(nullptr);
     gate.release();   // (no-op unless the encoder had nothing to code)
     helper.join();
     if (enc_st != st) {   // (the encoder has synchronised its stream; this orders later work on st after it)

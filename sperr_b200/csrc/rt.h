@@ -236,7 +236,9 @@ struct Readback {
 };
 struct ReadbackTable {
   std::mutex mu;
-  std::map<cudaStream_t, Readback> m;
+  // keyed by (device, stream): the legacy stream is handle 0 on EVERY device, and the threads that
+  // drive different devices (capi_multi.cu) use it at the same time
+  std::map<std::pair<int, cudaStream_t>, Readback> m;
 };
 inline ReadbackTable& readback_table()
 {
@@ -246,8 +248,9 @@ inline ReadbackTable& readback_table()
 inline Readback& readback_of(cudaStream_t st)
 {
   ReadbackTable& t = readback_table();
+  const int dev = cur_dev();
   std::lock_guard<std::mutex> l(t.mu);
-  return t.m[st];
+  return t.m[std::make_pair(dev, st)];
 }
 // Forgets copies whose rt::sync never came (a call that ended in an exception between the two):
 // their destinations are gone. Only for a point where no read-back of the process is in flight,
@@ -255,8 +258,11 @@ inline Readback& readback_of(cudaStream_t st)
 inline void readback_abandon()
 {
   ReadbackTable& t = readback_table();
+  const int dev = cur_dev();
   std::lock_guard<std::mutex> l(t.mu);
   for (auto& kv : t.m) {
+    if (kv.first.first != dev)
+      continue;   // another device's thread may have copies in flight (calls are serialised per device)
     kv.second.items.clear();
     kv.second.used = 0;
   }

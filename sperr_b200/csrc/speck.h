@@ -1,6 +1,8 @@
 // Integer SPECK coders: batch-level context and host drivers.
 #pragma once
 
+#include <vector>
+#include <utility>
 #include <functional>
 
 #include "kernels.h"
@@ -56,6 +58,16 @@ struct EncWork {
   // (pyramid and LIP / refinement counts are queued; what follows is latency-bound): the point at
   // which work of another stream no longer competes with this encoder for the memory system
   std::function<void(cudaStream_t)> before_plane_loop;
+  // called once per run when the zeroing of the staging arrays and count tables has been queued (a
+  // string of small memory operations: each of them waits for a CTA slot if another stream is
+  // flooding the GPU meanwhile)
+  std::function<void(cudaStream_t)> after_setup;
+  // `stage` (the zeroed bit arrays the coder ORs its output into) is sized for the worst case, 69 MB
+  // per 256^3 chunk; a run writes a few MB of it. It is zeroed as a whole only when it is new (or a
+  // run ended in an exception); otherwise a run clears just what the run before wrote
+  // (stage_dirty: word offset, words).
+  bool stage_clean = false;
+  std::vector<std::pair<size_t, size_t>> stage_dirty;
 };
 
 class Speck3DEncoder {
@@ -66,6 +78,7 @@ class Speck3DEncoder {
               const ShapeDev* d_shapes, const std::vector<ShapeTables>& shapes,
               std::vector<EncResult>& results, cudaStream_t st);
   void set_before_plane_loop(std::function<void(cudaStream_t)> f) { work_.before_plane_loop = std::move(f); }
+  void set_after_setup(std::function<void(cudaStream_t)> f) { work_.after_setup = std::move(f); }
 
  private:
   rt::DBuf ids_;

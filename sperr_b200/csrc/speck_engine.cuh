@@ -818,14 +818,32 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   ctx.maxp = maxp;
 
   // staging bit arrays
+  std::vector<unsigned long long> stage_words_off;
   {
     std::vector<unsigned long long> words_off(nchunks + 1, 0);
     for (int c = 0; c < nchunks; c++) {
       const unsigned long long bits = hc[c].planes > 0 ? bits_bound(c, hc[c]) : 0;
       words_off[c + 1] = words_off[c] + (bits + 31) / 32 + 2;
     }
-    w.stage.reserve(words_off[nchunks] * 4);
-    rt::dset(w.stage.p, 0, words_off[nchunks] * 4, st);
+    const size_t stage_bytes = words_off[nchunks] * 4;
+    if (stage_bytes > w.stage.bytes)
+      w.stage_clean = false;   // reserve() will hand out new, uninitialised memory
+    w.stage.reserve(stage_bytes);
+    if (!w.stage_clean)
+      rt::dset(w.stage.p, 0, w.stage.bytes, st);
+    else
+      for (const auto& r : w.stage_dirty)
+        rt::dset(w.stage.as<uint32_t>() + r.first, 0, r.second * 4, st);
+    if (std::getenv("SPERR_B200_STAGE_DEBUG")) {
+      size_t dirty = 0;
+      for (const auto& r : w.stage_dirty)
+        dirty += r.second * 4;
+      std::fprintf(stderr, "stage: need %zu bytes, buffer %zu, %s, dirty ranges %zu (%zu bytes)\n", stage_bytes, w.stage.bytes,
+                   w.stage_clean ? "clean" : "zeroed as a whole", w.stage_dirty.size(), dirty);
+    }
+    w.stage_clean = false;   // until this run has recorded what it wrote (an exception leaves it false)
+    w.stage_dirty.clear();
+    stage_words_off = words_off;
     for (int c = 0; c < nchunks; c++) {
       hc[c].spk = w.stage.as<uint32_t>() + words_off[c];
       hc[c].spk_cap_bits = (words_off[c + 1] - words_off[c]) * 32;
@@ -844,6 +862,8 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   ctx.bases = ctx.sizes + (size_t)nchunks * 2 * maxp;
   unsigned* d_counts = w.counts.as<unsigned>();
   delete ps_zero;
+  if (w.after_setup)
+    w.after_setup(st);
   if (nblk) {
     rt::ProfScope ps(T::kIsOutlierTree ? "enc1d.lipref_count" : "enc.lipref_count", st);
     LAUNCH(k_lipref_count, dim3((nblk + kLrUnits - 1) / kLrUnits, nchunks), dim3(kLrBlock), 0, st, d_chunks, d_counts, maxp, nblk);
@@ -891,6 +911,14 @@ void run_encoder(EncWork& w, ChunkDev* d_chunks, int nchunks, size_t max_n,
   rt::sync(st);
   if (err)
     throw std::runtime_error("SPECK encoder work-list overflow");
+  // what this run wrote into the staging array: bits [0, total_bits) of every chunk's slot
+  for (int c = 0; c < nchunks; c++) {
+    const size_t slot = size_t(stage_words_off[c + 1] - stage_words_off[c]);
+    const size_t used = hc[c].planes > 0 ? std::min<size_t>(slot, size_t((hc[c].total_bits + 31) / 32 + 2)) : 0;
+    if (used)
+      w.stage_dirty.emplace_back(size_t(stage_words_off[c]), used);
+  }
+  w.stage_clean = true;
   for (int c = 0; c < nchunks; c++) {
     results[c].planes = hc[c].planes;
     results[c].total_bits = hc[c].total_bits;
