@@ -212,6 +212,11 @@ static __global__ void k_stage_bits(const DecChunk* chunks, const unsigned char*
 
 // Decodes the sorting passes of every job (3D coefficient streams and 1D outlier streams run side
 // by side: one CTA each); w.h / w.dchunks hold the decoder state afterwards.
+static size_t lipsum_words(size_t mask_words_of_chunk)
+{
+  return ((mask_words_of_chunk / 128 + 1 + 31) / 32 + 3) & ~size_t(3);   // keeps the pieces 16-byte aligned
+}
+
 void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d_shapes,
                   cudaStream_t st)
 {
@@ -227,7 +232,7 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
     const DecJob& j = jobs[c];
     mw[c] = j.skip ? 0 : ((size_t(j.n + 31) / 32 + 8) & ~size_t(3));   // 16-byte aligned pieces, zero padded
     sw[c] = j.skip ? 0 : (size_t(j.payload_bytes) / 4 + 4);
-    mask_words += 3 * mw[c];
+    mask_words += 3 * mw[c] + lipsum_words(mw[c]);
     pl_bytes += j.skip ? 0 : ((size_t(j.n) + 63) & ~size_t(63));
     lis_entries += j.skip ? 0 : j.lis_total;
     cnt_entries += j.skip ? 0 : size_t(j.nlis + 1);
@@ -270,7 +275,8 @@ void speck_decode(DecWork& w, const std::vector<DecJob>& jobs, const ShapeDev* d
     d.lip = m;
     d.sigarr = m + mw[c];
     d.signarr = m + 2 * mw[c];
-    om += 3 * mw[c];
+    d.lipsum = m + 3 * mw[c];
+    om += 3 * mw[c] + lipsum_words(mw[c]);
     d.pl = w.pl.as<uint8_t>() + op;
     op += (size_t(j.n) + 63) & ~size_t(63);
     d.lis = w.lis.as<node_t>() + ol;

@@ -171,6 +171,48 @@ __device__ __forceinline__ uint32_t lip_res_load(const DecChunk& d, const uint32
 {
   return d.R > 1 ? __ldcg(p) : *p;
 }
+// SPERR_LIP_SUMMARY=1: the LIP pass skips the 128-word groups of the mask no pixel was ever put in
+// (DecChunk::lipsum). The sweeps are bound by the latency of their loads, one per group and warp.
+#ifndef SPERR_LIP_SUMMARY
+#define SPERR_LIP_SUMMARY 1
+#endif
+// word `w` of the LIP mask has received a pixel
+__device__ __forceinline__ void lip_mark_group(const DecChunk& d, unsigned long long w)
+{
+#if SPERR_LIP_SUMMARY
+  const unsigned long long g = w >> 7;
+  uint32_t* const p = gptr(d.lipsum) + (g >> 5);
+  const uint32_t bit = 1u << (g & 31);
+  if (!(__ldcg(p) & bit))   // (L2: the bit is set with an atomic, by any CTA of the cluster)
+    atomicOr(p, bit);
+#endif
+}
+// The summary bits of the groups a warp sweeps, 32 per lane (lane l: groups g0 + 32 l ...), fetched
+// once per LIP pass; group number `it` of the warp's range is live iff its bit is set.
+__device__ __forceinline__ uint32_t lip_summary_of(const DecChunk& d, unsigned long long g0, int lane)
+{
+#if SPERR_LIP_SUMMARY
+  const unsigned long long g = g0 + 32ull * lane;
+  const uint32_t* const p = gptr(d.lipsum) + (g >> 5);
+  const unsigned long long last = (((d.n + 31) / 32) >> 7) >> 5;   // last word that holds a group
+  const uint32_t lo = (g >> 5) <= last ? __ldcg(p) : 0u, hi = (g >> 5) + 1 <= last ? __ldcg(p + 1) : 0u;
+  return __funnelshift_r(lo, hi, unsigned(g & 31));
+#else
+  return 0xffffffffu;
+#endif
+}
+__device__ __forceinline__ bool lip_group_live(const DecChunk& d, uint32_t mine, unsigned long long g0,
+                                               unsigned long long it)
+{
+#if SPERR_LIP_SUMMARY
+  if (it < 1024)
+    return (__shfl_sync(0xffffffffu, mine, int(it >> 5)) >> (it & 31)) & 1u;
+  const unsigned long long g = g0 + it;   // (ranges of more than 2^22 pixels per warp)
+  return (__ldcg(gptr(d.lipsum) + (g >> 5)) >> (g & 31)) & 1u;
+#else
+  return true;
+#endif
+}
 
 // Cluster mode: what the CTAs of a stream's cluster tell each other during the LIP pass (global
 // memory; written before a cluster barrier, read after it).
@@ -293,7 +335,13 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
   const unsigned long long w0 = per_warp * ((unsigned long long)rank * kDecWarps + warp),
                            w1 = min((words + 3) & ~3ull, w0 + per_warp);
   unsigned long long cnt = 0;
-  for (unsigned long long j = w0 + 4ull * lane; j < w1; j += 128) {
+  const uint32_t summary = lip_summary_of(d, w0 >> 7, lane);   // (w0 is a multiple of 128)
+  for (unsigned long long j0 = w0; j0 < w1; j0 += 128) {
+    if (!lip_group_live(d, summary, w0 >> 7, (j0 - w0) >> 7))   // warp-uniform
+      continue;
+    const unsigned long long j = j0 + 4ull * lane;
+    if (j >= w1)
+      continue;
     // (.cg in cluster mode: other SMs set these bits, with atomics that live in L2)
     const uint4 m4 = lip_load(d, j);
     cnt += __popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w);
@@ -321,6 +369,8 @@ static __device__ void dec_lip_pass(DecChunk& d, DecShared& S, int n_plane, int 
   }
   unsigned long long nsig = 0;
   for (unsigned long long j0 = w0; j0 < w1; j0 += 128) {
+    if (!lip_group_live(d, summary, w0 >> 7, (j0 - w0) >> 7))   // an empty group: no tokens, `run` unchanged
+      continue;
     const unsigned long long j = j0 + 4ull * lane;
     uint4 m4 = make_uint4(0u, 0u, 0u, 0u);
     if (j < w1)
@@ -475,6 +525,7 @@ __device__ void dec_expand(DecChunk& d, const typename T::Data& tree, unsigned c
       }
       else {
         gptr(d.lip)[i >> 5] |= 1u << (i & 31);
+        lip_mark_group(d, i >> 5);
         klip++;
       }
     }

@@ -34,6 +34,9 @@ struct DecChunk {
   uint32_t* lip;                 // LIP mask, all zero on entry
   uint32_t* sigarr;              // scratch of the LIP pass (ceil(n / 32) + 2 words each)
   uint32_t* signarr;
+  // one bit per group of 128 words (4096 pixels) of the LIP mask: set when a pixel of the group is
+  // put on the list, never cleared -- the two sweeps of a LIP pass skip the groups whose bit is clear
+  uint32_t* lipsum;
   node_t* lis;                   // list storage
   const unsigned long long* lis_off;   // nlis + 1 offsets into `lis`
   unsigned* lis_cnt;             // nlis counters

@@ -419,8 +419,10 @@ static __device__ void f_expand_pixels(const DecChunk& d, const FastSmem& F, uns
       gptr(d.pl)[i] = uint8_t(n_plane | ((g & 1u) ? 0 : 0x80));
     if (s & 2u)
       gptr(d.pl)[i + 1] = uint8_t(n_plane | ((g & 2u) ? 0 : 0x80));
-    if (rm & ~s)   // x0 is even when a row has two pixels: both bits are in the same word
+    if (rm & ~s) {   // x0 is even when a row has two pixels: both bits are in the same word
       atomicOr(&gptr(d.lip)[i >> 5], (rm & ~s) << (i & 31));
+      lip_mark_group(d, i >> 5);
+    }
   }
 }
 
@@ -1088,6 +1090,9 @@ static __device__ void f_walk(DecChunk& d, DecShared& S, FastSmem& F)
 // frame one returns to has seen a significant child (one only descends into significant sets). So
 // the state is (j, ix, k, sg) in registers plus the depth j0 of the staged root; no frame is ever
 // parked in shared memory, and the stream is read 32 bits at a time into a register.
+#ifndef SPERR_WALK1D_FAST
+#define SPERR_WALK1D_FAST 1
+#endif
 static __device__ void f_walk1d(DecChunk& d, DecShared& S, FastSmem& F)
 {
   const unsigned boff = F.boff;
@@ -1161,6 +1166,54 @@ static __device__ void f_walk1d(DecChunk& d, DecShared& S, FastSmem& F)
     }
     if (q + 1 >= unsigned(kFW) || ntok >= unsigned(kFTok))
       break;
+#if SPERR_WALK1D_FAST
+    // A freshly entered set with exactly ONE significant size-C set below it -- the usual case in the
+    // lower levels of a sparse outlier array -- is finished in one step. On the way down every level
+    // costs one bit d (1: the first half is significant, take it; 0: it is not, the second half is
+    // significant by inference); after the body of the size-C set, every level that went into its
+    // first half tests its second half, one bit each. If those bits are all 0 the h direction bits
+    // give the path, every level leaves exactly one insignificant sibling behind (the log is sorted
+    // by depth afterwards, stably: entries of different depths may be logged in any order), and the
+    // walker is back at this set with both halves done. Otherwise nothing is committed and the set
+    // is taken bit by bit as before.
+    if (k == 0 && sg == 0) {
+      const int h = jC - j;
+      if (h >= 2 && q + unsigned(h) < unsigned(kFW)) {
+        load(q);
+        const unsigned D = cw & ((1u << h) - 1u);   // h <= 24 - 3
+        const unsigned qb = q + unsigned(h);        // body of the size-C set at the end of the path
+        const unsigned q2 = qb + F.bodyC[qb];
+        const unsigned nleft = unsigned(__popc(D));
+        if (q2 + nleft < unsigned(kFW)) {
+          unsigned rest = 0;
+          if (nleft) {
+            const unsigned a = q2 + boff;
+            rest = __funnelshift_r(F.bits[a >> 5], F.bits[(a >> 5) + 1], a & 31) & ((1u << nleft) - 1u);
+          }
+          if (rest == 0) {
+            const unsigned path = (ix << h) | (__brev(~D) >> (32 - h));   // index of the size-C set
+            F.qc_node[ntok] = ((unsigned long long)jC << 32) | path;
+            F.qc_pos[ntok] = uint16_t(qb);
+            ntok++;
+            for (int i = 1; i <= h; i++)
+              alog[napp++] = (unsigned(j + i) << 27) | ((path >> (h - i)) ^ 1u);
+            q = q2 + nleft;
+            k = 2;
+            sg = 1;
+#if defined(SPERR_EMUL) && defined(SPERR_WALK_COUNT)
+            if (threadIdx.x == 0) {
+              static unsigned long long fast_levels = 0, fast_hits = 0;
+              fast_levels += h;
+              ++fast_hits; if ((fast_hits & (fast_hits - 1)) == 0)
+                std::fprintf(stderr, "walk1d fast path: %llu hits, %llu levels\n", fast_hits, fast_levels);
+            }
+#endif
+            continue;
+          }
+        }
+      }
+    }
+#endif
     unsigned s = 1u;
     if (sg != 0 || k == 0) {   // the second half is inferred when the first was insignificant
       if (q - cbase >= 32u)

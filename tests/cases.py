@@ -40,23 +40,38 @@ SYN_SMALL = [
     ((96, 80, 72), (96, 80, 72), 3, 1e-3),      # tiles interior in x: 128-bit loads of the float volume
     ((50, 44, 40), (50, 44, 40), 3, 1e-3),      # rows of a tile straddle two words of the corrector flags
     ((100, 88, 40), (50, 44, 40), 3, 2e-3),     # the same with four chunks
+    # + N(0, sigma) noise (5th field): many outliers, the 1D stream's walker and its one-step
+    # single-path descents (speck_dec_fast.cuh, f_walk1d) get real work
+    ((64, 64, 64), (64, 64, 64), 3, 1e-3, 3e-4),
+    ((64, 64, 64), (32, 32, 32), 3, 1e-3, 1e-3),
 ]
 SYN_GPU = SYN_SMALL + [
     ((256, 256, 128), (256, 256, 128), 3, 1e-3),
     ((512, 64, 64), (512, 64, 64), 2, 90.0),
     ((300, 200, 100), (128, 128, 100), 3, 1e-3),
     ((128, 128, 128), (128, 128, 128), 1, 0.5),
+    ((128, 128, 128), (128, 128, 128), 3, 1e-3, 2e-4),
+    ((256, 256, 256), (256, 256, 256), 3, 1e-3, 1e-3),   # the noisy bench chunk: 2.6 bpp
 ]
 
 
 def syn_id(c):
-    return "syn%s-%s-m%d-%g" % ("x".join(map(str, c[0])), "x".join(map(str, c[1])), c[2], c[3])
+    return "syn%s-%s-m%d-%g%s" % ("x".join(map(str, c[0])), "x".join(map(str, c[1])), c[2], c[3],
+                                  "-noise%g" % c[4] if len(c) > 4 else "")
+
+
+def syn_field(case):
+    v = refs.synthetic_field(case[0], seed=5)
+    if len(case) > 4:
+        rng = np.random.default_rng(7)
+        v = (v + case[4] * rng.standard_normal(v.shape)).astype(v.dtype)
+    return v
 
 
 def check_syn_roundtrip(lib, oracle, case):
     """compress with the library -> bytes equal the oracle's; decompress -> bits equal the oracle's"""
-    dims, chunks, mode, q = case
-    v = refs.synthetic_field(dims, seed=5)
+    dims, chunks, mode, q = case[:4]
+    v = syn_field(case)
     rc, got = lib.comp_3d(v, dims, chunks, mode, q)
     rc2, exp = oracle.comp_3d(v, dims, chunks, mode, q)
     assert rc == rc2 == 0
