@@ -401,6 +401,12 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
         return rc;
     }
   }
+  if (dimx && dimy && dimz) {   // a volume that does not fit in HBM beside the work buffers: slab groups
+    const size_t vol[3] = {dimx, dimy, dimz}, ck[3] = {chunk_x, chunk_y, chunk_z};
+    const int rc = comp_3d_streamed(src, is_float, vol, ck, mode, quality, dst, dst_len);
+    if (rc != -2)
+      return rc;
+  }
   std::lock_guard<std::mutex> lock(g_mutex);
   return guarded([&] {
     cudaStream_t st = 0;
@@ -543,6 +549,11 @@ int sperr_decomp_3d(const void* src, size_t src_len, int output_float, size_t nt
       if (rc != -2)
         return rc;
     }
+  }
+  if (src && src_len >= 14) {   // a volume that does not fit in HBM beside the work buffers: slab groups
+    const int rc = decomp_3d_streamed(src, src_len, output_float, dimx, dimy, dimz, dst);
+    if (rc != -2)
+      return rc;
   }
   std::lock_guard<std::mutex> lock(g_mutex);
   return guarded([&] {

@@ -117,6 +117,12 @@ std::mutex& shared_api_mutex();
 std::vector<int> multi_devices();
 int comp_3d_multi(const void* src, int is_float, const size_t vol[3], const size_t chunk[3], int mode,
                   double quality, const std::vector<int>& devs, void** dst, size_t* dst_len);
+// Volumes too large to sit in HBM beside the work buffers: one group of chunk slabs at a time
+// (capi_stream.cu). -2: not needed / not possible, take the resident path.
+int comp_3d_streamed(const void* src, int is_float, const size_t vol[3], const size_t chunk[3], int mode,
+                     double quality, void** dst, size_t* dst_len);
+int decomp_3d_streamed(const void* src, size_t src_len, int output_float, size_t* dimx, size_t* dimy,
+                       size_t* dimz, void** dst);
 int decomp_3d_multi(const void* src, size_t src_len, int output_float, const std::vector<int>& devs,
                     size_t* dimx, size_t* dimy, size_t* dimz, void** dst);
 
