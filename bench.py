@@ -461,11 +461,13 @@ def measure(args, L, dev, rank, world, scaling, full):
         # before the loop ends); per-stage times below are averages over the timed steps
         prof_on(0 if "noprof" in diag else 1)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        hc0 = host_counters()
         e0.record()
         for i in range(steps):
             stream = step_dev()
             marks[i].record()   # per-step times (reported as step_ms_each; one record, no wait)
         e1.record()
+        hc1 = host_counters()
         barrier()
         step_each = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
         launches_per_step = (launch_count() - l0) // steps
@@ -529,6 +531,7 @@ def measure(args, L, dev, rank, world, scaling, full):
             "gpu_launches": launches_per_step,
             # rank 0's individual calls (ms): a host-side stall in one call shows here
             "warmup_extra_steps": extra,
+            "host_counters_delta": {k: hc1[k] - hc0.get(k, 0) for k in hc1},
             "step_ms_each": [round(x, 2) for x in step_each], "step_host_ms_each": host_split[-steps:],
             "compress_ms_each": each["compress"],
             "decompress_ms_each": each["decompress"],
@@ -604,6 +607,29 @@ def measure(args, L, dev, rank, world, scaling, full):
         if world == 1 and args.cpu_baseline:
             res["cpu_baseline"] = cpu_baseline_sample()
     return res
+
+
+def host_counters():
+    """what the OS did to this process: involuntary context switches of the main thread and cgroup CPU
+    throttling (when the files exist); deltas over the timed region go into the bench line so that a
+    host-side stall (step_host_ms_each) can be told from a preempted or throttled process"""
+    out = {}
+    try:
+        for line in open("/proc/self/status"):
+            if line.startswith("nonvoluntary_ctxt_switches"):
+                out["preempted"] = int(line.split()[1])
+    except Exception:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.stat", "/sys/fs/cgroup/cpu/cpu.stat", "/sys/fs/cgroup/cpu,cpuacct/cpu.stat"):
+        try:
+            for line in open(path):
+                k, v = line.split()
+                if k in ("nr_throttled", "throttled_usec", "throttled_time"):
+                    out[k] = int(v)
+            break
+        except Exception:
+            continue
+    return out
 
 
 def local_index(dev):

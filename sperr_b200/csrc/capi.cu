@@ -493,6 +493,85 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
         };
       }
     }
+    // Pageable source (what an unchanged C caller passes) and several z-slabs of chunks: a helper
+    // thread takes the slab groups through the pinned ring (HostPipe::h2d) one after the other, the
+    // coder starts on a group as soon as it has arrived. Measured before this existed: upload 88 ms,
+    // THEN coder 58 ms, whatever the group size (the overlap above needs a pinned source).
+    struct Uploader {
+      std::thread th;
+      std::mutex mu;
+      std::condition_variable cv;
+      size_t done = 0;
+      std::exception_ptr err;
+      ~Uploader()
+      {
+        if (th.joinable())
+          th.join();
+      }
+    } up;
+    if (evs.empty() && !rt::is_pinned_host(src) && dimx && dimy && dimz && !std::getenv("SPERR_B200_NO_PAGEABLE_OVERLAP")) {
+      const size_t vol[3] = {dimx, dimy, dimz};
+      size_t cd[3] = {chunk_x, chunk_y, chunk_z};
+      for (int i = 0; i < 3; i++)
+        cd[i] = std::min(std::max<size_t>(1, cd[i]), vol[i]);
+      const auto chunks = chunk_volume(vol, cd);
+      size_t per_slab = 0;
+      while (per_slab < chunks.size() && chunks[per_slab].z0 == chunks[0].z0)
+        per_slab++;
+      const size_t nslabs = chunks.size() / std::max<size_t>(per_slab, 1);
+      const size_t min_group = std::getenv("SPERR_B200_OVERLAP_MIN_CHUNKS")
+                                   ? size_t(std::atoi(std::getenv("SPERR_B200_OVERLAP_MIN_CHUNKS")))
+                                   : 16;
+      if (nslabs >= 2 && per_slab * nslabs == chunks.size() && bytes >= (size_t(256) << 20) &&
+          chunks.size() >= 2 * min_group) {
+        const size_t groups = std::min<size_t>(nslabs, std::min<size_t>(4, chunks.size() / min_group));
+        const size_t slabs_per = (nslabs + groups - 1) / groups;
+        const size_t mb = slabs_per * per_slab;
+        g_comp->max_batch = mb;
+        if (!g_copy_stream)
+          RT_CHECK(cudaStreamCreateWithFlags(&g_copy_stream, cudaStreamNonBlocking));
+        int dev = 0;
+        RT_CHECK(cudaGetDevice(&dev));
+        const size_t plane = dimx * dimy * esz;
+        std::vector<std::pair<size_t, size_t>> parts;   // byte range of every group
+        for (size_t s0 = 0; s0 < nslabs; s0 += slabs_per) {
+          const size_t s1 = std::min(nslabs, s0 + slabs_per);
+          const size_t z0 = chunks[s0 * per_slab].z0;
+          const size_t z1 = s1 == nslabs ? dimz : chunks[s1 * per_slab].z0;
+          parts.emplace_back(z0 * plane, (z1 - z0) * plane);
+        }
+        void* const d_in = g_in.p;
+        cudaStream_t cs = g_copy_stream;
+        up.th = std::thread([&up, parts, d_in, src, dev, cs] {
+          try {
+            RT_CHECK(cudaSetDevice(dev));
+            for (size_t g = 0; g < parts.size(); g++) {
+              HostPipe::get().h2d(static_cast<char*>(d_in) + parts[g].first,
+                                  static_cast<const char*>(src) + parts[g].first, parts[g].second, cs);
+              {
+                std::lock_guard<std::mutex> l(up.mu);
+                up.done = g + 1;
+              }
+              up.cv.notify_all();
+            }
+          }
+          catch (...) {
+            {
+              std::lock_guard<std::mutex> l(up.mu);
+              up.err = std::current_exception();
+            }
+            up.cv.notify_all();
+          }
+        });
+        g_comp->before_batch = [&up, mb](size_t first, size_t count) {
+          const size_t need = (first + count - 1) / mb + 1;
+          std::unique_lock<std::mutex> l(up.mu);
+          up.cv.wait(l, [&] { return up.done >= need || up.err; });
+          if (up.err)
+            std::rethrow_exception(up.err);
+        };
+      }
+    }
     struct EvGuard {
       std::vector<cudaEvent_t>& v;
       ~EvGuard()
@@ -507,7 +586,7 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
         }
       }
     } ev_guard{evs};
-    if (evs.empty())
+    if (evs.empty() && !up.th.joinable())
 #endif
       HostPipe::get().h2d(g_in.p, src, bytes, st);
     pt.mark("h2d");

@@ -93,6 +93,14 @@ def test_host_api_batched_overlap_path_512(lib):
     assert rc == 0 and d2 == dims
     assert np.array_equal(out_host.view(np.uint32), d_out.cpu().numpy().view(np.uint32))
     assert np.max(np.abs(out_host.astype(np.float64) - v.astype(np.float64))) <= 1e-3 + 1.2e-7
+    # the same from PAGEABLE memory: a helper thread takes the slab groups through the pinned ring
+    # while the coder works on the groups that have arrived
+    rc, s_page = L.compress_3d(v, dims, (256, 256, 256), 3, 1e-3, copy=False)
+    assert rc == 0 and np.array_equal(s_page, s_dev)
+    os.environ["SPERR_B200_NO_PAGEABLE_OVERLAP"] = "1"
+    rc, s_page2 = L.compress_3d(v, dims, (256, 256, 256), 3, 1e-3, copy=False)
+    del os.environ["SPERR_B200_NO_PAGEABLE_OVERLAP"]
+    assert rc == 0 and np.array_equal(s_page2, s_dev)
     del os.environ["SPERR_B200_OVERLAP_MIN_CHUNKS"]
 
 
