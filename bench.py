@@ -89,6 +89,14 @@ def field_torch(dims, origin, device):
 # ---------------------------------------------------------------------------------------------
 
 class Clocks:
+    """SM clock and throttle reasons DURING the timed region, read through NVML by the benchmark's own
+    thread right after each timed step (`sample()`), never by a thread of its own: a sampler thread
+    calling NVML five to ten times a second beside the thread that drives the GPU was what stalled
+    single steps by 20 - 170 ms in rounds 1 and 2 (two runs of ten steps each way on one box: with the
+    thread `[108.4, .., 196.0, ..]` and `[108.7, 274.7, ..]`, without it every step within 108.4 -
+    112.5 ms; `profiles/r2_call_r2ai.log`). Between two steps the GPU has been idle for microseconds:
+    the clocks read there are the clocks under load. The time the samples take is inside the timed
+    region and reported (`sample_ms`)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -96,12 +104,19 @@ class Clocks:
         self.index = index
         self.samples = []
         self.first = 0
-        self.stop = idle   # idle: no sampling at all (--diag noclocks)
-        self.t = threading.Thread(target=self.run, daemon=True)
+        self.idle = idle   # no sampling at all (--diag noclocks)
+        self.sample_s = 0.0
+        self.nv, self.h, self.max_mhz = None, None, None
+        if not idle:
+            self.nv, self.h = self._nvml()
+            if self.nv is not None:
+                try:
+                    self.max_mhz = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                except Exception:
+                    self.max_mhz = None
 
     def _nvml(self):
-        """NVML handle of the GPU (same counters nvidia-smi prints, without spawning a process and
-        enumerating every device five times a second while the timed region runs)."""
+        """NVML handle of the GPU (same counters nvidia-smi prints, without spawning a process)."""
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -115,39 +130,41 @@ class Clocks:
         except Exception:
             return None, None
 
-    def run(self):
-        nv, h = self._nvml()
-        while not self.stop:
-            try:
-                if nv is not None:
-                    sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                    mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    act = lambda bit: "Active" if (r & bit) else "Not Active"
-                    self.samples.append([str(sm), str(mx), act(nv.nvmlClocksThrottleReasonHwSlowdown),
-                                         act(nv.nvmlClocksThrottleReasonHwThermalSlowdown),
-                                         act(nv.nvmlClocksThrottleReasonSwThermalSlowdown),
-                                         act(nv.nvmlClocksThrottleReasonSwPowerCap)])
-                else:
-                    o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                        "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                       timeout=5).stdout.strip().split(",")
-                    self.samples.append([s.strip() for s in o])
-            except Exception:
-                pass
-            time.sleep(0.1 if nv is not None else 0.2)
+    def sample(self):
+        """one sample, taken by the calling thread"""
+        if self.idle:
+            return
+        t0 = time.perf_counter()
+        try:
+            nv, h = self.nv, self.h
+            if nv is not None:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                act = lambda bit: "Active" if (r & bit) else "Not Active"
+                self.samples.append([str(sm), str(self.max_mhz if self.max_mhz is not None else sm),
+                                     act(nv.nvmlClocksThrottleReasonHwSlowdown),
+                                     act(nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                                     act(nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                                     act(nv.nvmlClocksThrottleReasonSwPowerCap)])
+            else:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                   timeout=5).stdout.strip().split(",")
+                self.samples.append([x.strip() for x in o])
+        except Exception:
+            pass
+        self.sample_s += time.perf_counter() - t0
 
     def __enter__(self):
-        self.t.start()
         return self
 
-    def mark(self):
-        """drops the samples taken so far (the sampler is started before the warm-up)"""
-        self.first = len(self.samples)
-
     def __exit__(self, *a):
-        self.stop = True
-        self.t.join(timeout=6)
+        return False
+
+    def mark(self):
+        """drops the samples taken so far (warm-up)"""
+        self.first = len(self.samples)
+        self.sample_s = 0.0
 
     def summary(self):
         samples = self.samples[self.first:]
@@ -161,7 +178,8 @@ class Clocks:
                     if s[2 + i].lower().startswith("active"):
                         reasons.add(n)
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sample_ms": round(self.sample_s * 1e3, 2),
+                "how": "NVML, by the timing thread after every timed step"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -425,12 +443,10 @@ def measure(args, L, dev, rank, world, scaling, full):
     prof_on = L.fn("sperr_b200_prof_enable", None, [C.c_int])
     prof_dump = L.fn("sperr_b200_prof_dump", C.c_size_t, [C.c_char_p, C.c_size_t])
 
-    # Everything that is set up once goes BEFORE the warm-up, so that the warm-up steps absorb it: the
-    # clock sampler (NVML initialisation enumerates every GPU of the box), the first NCCL collectives
-    # (communicator and its lazily connected transports), the profiler's event pool. Started at the
-    # top of the timed loop instead (round 1 and the first half of round 2) they stalled the host
-    # side of the first timed steps by 20 - 100 ms each, one run in two: measured with
-    # step_host_ms_each below, stage ranges unaffected, later steps clean.
+    # Everything that is set up once goes BEFORE the warm-up, so that the warm-up steps absorb it: NVML
+    # initialisation (enumerates every GPU of the box), the first NCCL collectives (communicator and
+    # its lazily connected transports), the profiler's event pool. And nothing but the timing thread
+    # talks to the driver during the timed region: see class Clocks for what a sampler thread cost.
     diag = set(x for x in args.diag.split(",") if x)
     clk = Clocks(local_index(dev), idle="noclocks" in diag)
     clk.__enter__()
@@ -440,6 +456,7 @@ def measure(args, L, dev, rank, world, scaling, full):
     t_warm = time.perf_counter()
     for _ in range(args.warmup):
         stream = step_dev()
+        clk.sample()   # (the first NVML calls of the process are the slow ones: not in the timed region)
     extra = 0
     while time.perf_counter() - t_warm < args.settle and extra < 16:   # (extra warm-up steps, reported)
         stream = step_dev()
@@ -466,6 +483,7 @@ def measure(args, L, dev, rank, world, scaling, full):
         for i in range(steps):
             stream = step_dev()
             marks[i].record()   # per-step times (reported as step_ms_each; one record, no wait)
+            clk.sample()        # clocks under load: inside the timed region, by this thread
         e1.record()
         hc1 = host_counters()
         barrier()

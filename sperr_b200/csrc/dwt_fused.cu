@@ -394,7 +394,9 @@ template <bool FMA>
 __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d_tma(FusedArgs a, const __grid_constant__ CUtensorMap tmap)
 {
   extern __shared__ unsigned char tma_raw_smem[];
-  unsigned char* const sbase = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tma_raw_smem) + 127) & ~uintptr_t(127));
+  // 128-byte aligned start, as an OFFSET into the shared array: a pointer rebuilt from an integer
+  // (round 2's first version) made every access to the staging buffers and the tile a generic LD / ST
+  unsigned char* const sbase = tma_raw_smem + ((128u - (smem_u32(tma_raw_smem) & 127u)) & 127u);
   float* const stage = reinterpret_cast<float*>(sbase);                             // [2][kTPlanes][kFI * kFI]
   double* const tile = reinterpret_cast<double*>(sbase + 2 * kTmaStageBytes);       // [kTPlanes][kFI][kFP]
   __shared__ unsigned long long s_max;
@@ -459,21 +461,28 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d_tma(FusedArgs a, const _
   const int x = X0 + lane;
   const int xo = (x >> 1) + ((x & 1) ? ax : 0);
   FwdState st[4];
-  size_t dpos[4];
-  long long apos[4];
-  bool live[4];
+  unsigned dpos[4];    // offset of the column inside a z plane of coef (a chunk holds < 2^31 values)
+  unsigned apos[4];    // approx columns (x, y even): offset inside a z plane of the approx box
+  unsigned live = 0, isapx = 0;   // bit c: column c is inside the box / is an approx column
   for (int c = 0; c < 4; c++) {
     st[c] = FwdState{0.0, 0.0, 0.0, 0.0, 0.0};
     const int y = Y0 + warp + 8 * c;
-    live[c] = x < lx && y < ly;
-    dpos[c] = (size_t)((y >> 1) + ((y & 1) ? ay : 0)) * cnx + xo;
-    apos[c] = ((x | y) & 1) ? -1ll
-                            : (a.apx_off >= 0 ? (long long)(y >> 1) * ax + (x >> 1) : (long long)dpos[c]);
+    if (x < lx && y < ly)
+      live |= 1u << c;
+    dpos[c] = unsigned((size_t)((y >> 1) + ((y & 1) ? ay : 0)) * cnx + xo);
+    apos[c] = dpos[c];
+    if (!((x | y) & 1)) {
+      isapx |= 1u << c;
+      if (a.apx_off >= 0)
+        apos[c] = unsigned((y >> 1) * ax + (x >> 1));
+    }
   }
   double* const abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : coef;
   ASSUME_GLOBAL(coef);
   ASSUME_GLOBAL(abox);
-  const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
+  const unsigned cnxy32 = unsigned(cnxy), aplane32 = a.apx_off >= 0 ? unsigned(ax * ay) : cnxy32;
+  const bool last_level = a.last != 0;
+  const int nhigh = lz / 2;   // pairs that have a high-band sample
   unsigned long long vmax = 0;
 
   for (int t = 0; t < nsteps; t++) {
@@ -514,21 +523,20 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d_tma(FusedArgs a, const _
         const int ry = warp + 8 * c;
         double e2, o3;
         fwd_step<FMA>(k, st[c], te[ry * kFP], to[ry * kFP], e2, o3);
-        if (emit && live[c]) {
-          if (apos[c] >= 0) {
-            abox[(size_t)kk * aplane + apos[c]] = e2;
-            if (a.last) {
-              const unsigned long long b = abs_bits(e2);
-              vmax = b > vmax ? b : vmax;
-            }
-          }
-          else {
-            coef[(size_t)kk * cnxy + dpos[c]] = e2;
+        if (emit && ((live >> c) & 1u)) {
+          // (the approximation band of a level that is not the last one is transformed again: its
+          // values do not count towards the largest coefficient)
+          const bool apx = (isapx >> c) & 1u;
+          if (apx)
+            abox[unsigned(kk) * aplane32 + apos[c]] = e2;
+          else
+            coef[unsigned(kk) * cnxy32 + dpos[c]] = e2;
+          if (!apx || last_level) {
             const unsigned long long b = abs_bits(e2);
             vmax = b > vmax ? b : vmax;
           }
-          if (kk < lz / 2) {
-            coef[(size_t)(az + kk) * cnxy + dpos[c]] = o3;
+          if (kk < nhigh) {
+            coef[unsigned(az + kk) * cnxy32 + dpos[c]] = o3;
             const unsigned long long b = abs_bits(o3);
             vmax = b > vmax ? b : vmax;
           }
