@@ -219,7 +219,13 @@ int comp_3d_device(const void* d_src, int is_float, size_t dimx, size_t dimy, si
     std::memcpy(o + pos, &l32, 4);
     pos += 4;
   }
-  HostPipe::get().d2h(o + pos, d_out.p, total - hlen, st);
+  try {
+    HostPipe::get().d2h(o + pos, d_out.p, total - hlen, st);
+  }
+  catch (...) {
+    std::free(o);   // (guarded() turns the exception into -1: the buffer must not outlive it)
+    throw;
+  }
   *dst = o;
   *dst_len = total;
   return 0;
@@ -576,6 +582,8 @@ int sperr_comp_3d(const void* src, int is_float, size_t dimx, size_t dimy, size_
       std::vector<cudaEvent_t>& v;
       ~EvGuard()
       {
+        if (!v.empty() && g_copy_stream)   // (also on the exception path: uploads from the caller's buffer
+          cudaStreamSynchronize(g_copy_stream);   // must not be in flight when the call returns)
         for (auto e : v)
           cudaEventDestroy(e);
         if (g_comp) {
@@ -969,16 +977,22 @@ int sperr_b200_decomp_3d_multires(const void* src, size_t src_len, int output_fl
     if (!o)
       return fail();
     outs.push_back(o);
-    HostPipe::get().d2h(o, g_vol.p, total * esz, st);
-    for (size_t h = 0; h < mr.d_level.size(); h++) {
-      const size_t nb = mr.dims[h][0] * mr.dims[h][1] * mr.dims[h][2] * esz;
-      void* p = std::malloc(std::max<size_t>(nb, 1));
-      if (!p)
-        return fail();
-      outs.push_back(p);
-      HostPipe::get().d2h(p, mr.d_level[h], nb, st);
+    try {
+      HostPipe::get().d2h(o, g_vol.p, total * esz, st);
+      for (size_t h = 0; h < mr.d_level.size(); h++) {
+        const size_t nb = mr.dims[h][0] * mr.dims[h][1] * mr.dims[h][2] * esz;
+        void* p = std::malloc(std::max<size_t>(nb, 1));
+        if (!p)
+          return fail();
+        outs.push_back(p);
+        HostPipe::get().d2h(p, mr.d_level[h], nb, st);
+      }
+      HostPipe::get().wait_idle();
     }
-    HostPipe::get().wait_idle();
+    catch (...) {
+      fail();   // a failed copy must not leak the buffers handed out so far
+      throw;
+    }
     *dst = o;
     *dimx = ci.vol[0]; *dimy = ci.vol[1]; *dimz = ci.vol[2];
     *nlevels = mr.d_level.size();
