@@ -102,8 +102,10 @@ __device__ __forceinline__ double corrector_lookup(const CorrectorList& l, unsig
 
 // ---- dwt_fused.cu: one HBM round trip per level, dyadic chunks only ----
 size_t fused_scratch_elems(uint32_t nx, uint32_t ny, uint32_t nz, long long off[8]);
+// quant_q > 0: the kernels also quantise every final coefficient with that step (magnitude, msb
+// position, sign bit: what k_quantize would write; the caller zeroes the sign words first)
 void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const int* d_ids, int nids,
-                              uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st);
+                              uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st, double quant_q = 0.0);
 void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chunks, const int* d_ids,
                               int nids, uint32_t nx, uint32_t ny, uint32_t nz, double tol,
                               const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st);

@@ -237,6 +237,16 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   ids_.reserve(flat.size() * 4 + 4);
   rt::h2d(ids_.p, flat.data(), flat.size() * 4, st);
   rt::sync(st);
+  // PWE mode, every chunk on the fused path: the quantisation step (1.5 x tolerance,
+  // src/SPECK_FLT.cpp:439) does not depend on the coefficients, so the forward transform quantises
+  // what it writes (dwt_fused.cu, quant_store) and k_quantize's pass over the coefficients is not
+  // needed -- unless a magnitude does not fit 32 bits, which k_qdecide finds from the maximum as
+  // before; then k_quantize runs after all.
+  const double fused_q = (mode == kModePWE && !any_unfused && !std::getenv("SPERR_B200_NO_FUSED_QUANT"))
+                             ? quality * 1.5
+                             : 0.0;
+  if (fused_q > 0.0)
+    rt::dset(b_.signs.p, 0, b_.sign_words * 4, st);
   // dyadic shapes: fused kernels (dwt_fused.cu) that read the volume themselves and track the
   // coefficient maximum; everything else: gather, per-axis passes in place, separate maximum
   auto group_fused = [&](size_t s) { return b_.h[groups[s][0]].fused != 0; };
@@ -251,7 +261,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
       if (!fused_groups)
         launch_dwt(inverse, b_.dev(), ids, n, h.nx, h.ny, h.nz, is_2d, st);
       else if (!inverse)
-        launch_dwt_fused_forward(src, b_.dev(), ids, n, h.nx, h.ny, h.nz, st);
+        launch_dwt_fused_forward(src, b_.dev(), ids, n, h.nx, h.ny, h.nz, st, fused_q);
       else   // PWE: rebuild the values, compare with the source, record the outliers
         launch_dwt_fused_inverse(src, 2, b_.dev(), ids, n, h.nx, h.ny, h.nz, quality, sink,
                                  CorrectorList{nullptr, nullptr, nullptr}, st);
@@ -278,7 +288,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
           continue;
         const ShapeHeader& h = b_.shapes[si].h;
         launch_dwt_fused_forward(src, b_.dev(), ids_.as<int>() + goff[si] + (lo - groups[si].begin()),
-                                 int(hi - lo), h.nx, h.ny, h.nz, st);
+                                 int(hi - lo), h.nx, h.ny, h.nz, st, fused_q);
       }
     }
   }
@@ -374,7 +384,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
       b_.make_wide(st);
       b_.push(st);
     }
-    {
+    if (!(fused_q > 0.0 && mode == kModePWE && !any_wide)) {
       rt::ProfScope ps("c.quantize", st);
       launch_quantize(b_.dev(), nc, b_.max_n, st);
     }
