@@ -642,7 +642,11 @@ constexpr int kIQuads = kFNP * kFNP;   // 400
 static_assert(kIQuads <= kIThreads && kPlanes * kFI <= kIThreads && 2 * kPlanes <= kIThreads / 32, "roles");
 constexpr int kIRows = 16;             // rows of a plane an epilogue warp owns
 
-template <int OUT, bool FMA, bool F32>
+// DEQ (compress side, PWE mode): the coefficients are not read from `coef` but rebuilt from the
+// quantised magnitudes and sign bits on the fly -- what k_inv_quantize (transform.cu) would have
+// written there: (q * m) * (+-1), src/SPECK_FLT.cpp:359-399 -- so that pass and its 16 B per value of
+// HBM traffic are not needed. 32-bit magnitudes only (the caller checks).
+template <int OUT, bool FMA, bool F32, bool DEQ>
 __global__ void __launch_bounds__(kIThreads, 2) k_inv3d(FusedArgs a)
 {
   DYN_SMEM(double, tile);   // [kPlanes][kFI][kFP]
@@ -671,6 +675,21 @@ __global__ void __launch_bounds__(kIThreads, 2) k_inv3d(FusedArgs a)
   ASSUME_GLOBAL(coef);
   ASSUME_GLOBAL(abox);
   const unsigned cnxy32 = unsigned(cnxy), aplane32 = a.apx_off >= 0 ? unsigned(ax * ay) : cnxy32;
+  const unsigned* const qmag = reinterpret_cast<const unsigned*>(ch.mag);
+  const uint32_t* const qsigns = ch.signs;
+  const double qstep = ch.q;
+  if (DEQ) {
+    ASSUME_GLOBAL(qmag);
+    ASSUME_GLOBAL(qsigns);
+  }
+  auto coef_at = [&](unsigned idx) -> double {
+    if (!DEQ)
+      return coef[idx];
+    const double m = __uint2double_rn(qmag[idx]);
+    const bool pos = (qsigns[idx >> 5] >> (idx & 31u)) & 1u;
+    return __dmul_rn(__dmul_rn(qstep, m), pos ? 1.0 : -1.0);
+  };
+  const bool apx_in_coef = a.apx_off < 0;   // the coarsest level: its approximation band is in coef too
 
   // ---- z phase: my quad. Slot s = 2 py + px is the column (2i + py, 2j + px) of the tile; the tile
   // starts at an even sample and mirroring keeps parity, so slot s is always of parity class
@@ -769,13 +788,13 @@ __global__ void __launch_bounds__(kIThreads, 2) k_inv3d(FusedArgs a)
         const unsigned ze = unsigned(mirror(2 * j, lz) >> 1), zo = unsigned(az + (mirror(2 * j + 1, lz) >> 1));
         const unsigned ie = ze * cnxy32, io = zo * cnxy32, ia = ze * aplane32;
         double ev[4], ov[4];
-        ev[0] = abox[ia + eoff0];
+        ev[0] = (DEQ && apx_in_coef) ? coef_at(ia + eoff0) : abox[ia + eoff0];
 #pragma unroll
         for (int s = 1; s < 4; s++)
-          ev[s] = coef[ie + coff[s]];
+          ev[s] = coef_at(ie + coff[s]);
 #pragma unroll
         for (int s = 0; s < 4; s++)
-          ov[s] = coef[io + coff[s]];
+          ov[s] = coef_at(io + coff[s]);
         double* const t0 = zt + (size_t)(2 * q) * kFI * kFP;
 #pragma unroll
         for (int s = 0; s < 4; s++) {
@@ -1017,15 +1036,18 @@ static void fused_attrs()
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   const int smi = int(kInvSmem);
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-#define SPERR_INV_ATTR(O) \
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi)); \
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  SPERR_INV_ATTR(1)
-  SPERR_INV_ATTR(2)
+#define SPERR_INV_ATTR(O, D) \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, false, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi)); \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, true, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, false, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, true, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  SPERR_INV_ATTR(1, false)
+  SPERR_INV_ATTR(2, false)
+  SPERR_INV_ATTR(2, true)
 #undef SPERR_INV_ATTR
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -1094,7 +1116,7 @@ void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const
 // `sink` (unordered).
 void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chunks, const int* d_ids,
                               int nids, uint32_t nx, uint32_t ny, uint32_t nz, double tol,
-                              const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st)
+                              const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st, bool deq)
 {
   fused_attrs();
   const int L = can_use_dyadic(nx, ny, nz);
@@ -1131,23 +1153,23 @@ void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chu
         grid = dim3(unsigned(a.tiles_x * a.tiles_y * zs), unsigned(nids));
       }
     }
-#define SPERR_INV(O, F, T) LAUNCH((k_inv3d<O, F, T>), grid, dim3(kIThreads), kInvSmem, st, a)
-#define SPERR_INV_T(O, F)        \
-  do {                           \
-    if (vol.is_float)            \
-      SPERR_INV(O, F, true);     \
-    else                         \
-      SPERR_INV(O, F, false);    \
+#define SPERR_INV(O, F, T, D) LAUNCH((k_inv3d<O, F, T, D>), grid, dim3(kIThreads), kInvSmem, st, a)
+#define SPERR_INV_T(O, F, D)        \
+  do {                              \
+    if (vol.is_float)               \
+      SPERR_INV(O, F, true, D);     \
+    else                            \
+      SPERR_INV(O, F, false, D);    \
   } while (0)
     if (a.k.fma) {
-      if (which == 0) SPERR_INV(0, true, false);
-      else if (which == 1) SPERR_INV_T(1, true);
-      else SPERR_INV_T(2, true);
+      if (which == 0) { if (deq) SPERR_INV(0, true, false, true); else SPERR_INV(0, true, false, false); }
+      else if (which == 1) SPERR_INV_T(1, true, false);
+      else { if (deq) SPERR_INV_T(2, true, true); else SPERR_INV_T(2, true, false); }
     }
     else {
-      if (which == 0) SPERR_INV(0, false, false);
-      else if (which == 1) SPERR_INV_T(1, false);
-      else SPERR_INV_T(2, false);
+      if (which == 0) { if (deq) SPERR_INV(0, false, false, true); else SPERR_INV(0, false, false, false); }
+      else if (which == 1) SPERR_INV_T(1, false, false);
+      else { if (deq) SPERR_INV_T(2, false, true); else SPERR_INV_T(2, false, false); }
     }
 #undef SPERR_INV_T
 #undef SPERR_INV

@@ -108,7 +108,8 @@ void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const
                               uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st, double quant_q = 0.0);
 void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chunks, const int* d_ids,
                               int nids, uint32_t nx, uint32_t ny, uint32_t nz, double tol,
-                              const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st);
+                              const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st,
+                              bool deq = false);   // deq: coefficients rebuilt from mag / signs / q on the fly
 void launch_level_gather(const ChunkDev* d_chunks, int nchunks, uint32_t nx, uint32_t ny, uint32_t nz,
                          int h, void* dst, int is_float, size_t vx, size_t vy, cudaStream_t st);
 CdfC cdf_constants();

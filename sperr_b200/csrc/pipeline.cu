@@ -250,6 +250,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   // dyadic shapes: fused kernels (dwt_fused.cu) that read the volume themselves and track the
   // coefficient maximum; everything else: gather, per-axis passes in place, separate maximum
   auto group_fused = [&](size_t s) { return b_.h[groups[s][0]].fused != 0; };
+  bool inverse_deq = false;   // PWE: the inverse transform de-quantises on the fly (set before the outlier chain)
   auto transform = [&](bool inverse, bool fused_groups, const OutlierSink& sink, cudaStream_t st) {
     rt::ProfScope ps(inverse ? "c.idwt" : "c.dwt", st);
     for (size_t s = 0; s < groups.size(); s++) {
@@ -264,7 +265,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
         launch_dwt_fused_forward(src, b_.dev(), ids, n, h.nx, h.ny, h.nz, st, fused_q);
       else   // PWE: rebuild the values, compare with the source, record the outliers
         launch_dwt_fused_inverse(src, 2, b_.dev(), ids, n, h.nx, h.ny, h.nz, quality, sink,
-                                 CorrectorList{nullptr, nullptr, nullptr}, st);
+                                 CorrectorList{nullptr, nullptr, nullptr}, st, inverse_deq);
     }
   };
   if (by_groups) {
@@ -391,8 +392,12 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     // PWE: the outlier path (de-quantise, inverse transform, compare with the source, SPECK1D-code
     // the differences) only needs the quantised integers, like the SPECK3D encoder, and both are
     // chains of small launches with host round trips: run them side by side on two streams.
+    // Every chunk on the fused path and 32-bit magnitudes: the inverse transform rebuilds the
+    // coefficients from magnitude, sign and step where it loads them (k_inv3d<.., DEQ>), and
+    // k_inv_quantize's round trip over HBM (4 + 8 B per value) is not needed.
+    inverse_deq = mode == kModePWE && !any_unfused && !any_wide && !b_.wide && !std::getenv("SPERR_B200_NO_FUSED_DEQ");
     auto outlier_chain = [&](cudaStream_t s) {
-      {
+      if (!inverse_deq) {
         rt::ProfScope ps("c.inv_quantize", s);
         launch_inv_quantize(b_.dev(), nc, b_.max_n, s);
       }
