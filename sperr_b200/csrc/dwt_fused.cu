@@ -146,7 +146,8 @@ struct FusedArgs {
   long long out_off;    // inverse, mode 0: the rebuilt box goes compact to scratch + out_off, or -1: coef
   int tiles_x, tiles_y, zsegs;
   int last;             // forward: this is the coarsest level (its approx band is final)
-  int quant;            // forward: also write magnitude / msb / sign of every final value (see quant_store)
+  int quant;            // forward: 1: also write magnitude / msb / sign of every final value (see quant_store);
+                        // 2: write ONLY those (the fp64 coefficients are not stored: nobody reads them)
   double q;             // ... with this quantisation step
   double tol;           // inverse mode 2
   OutlierSink sink;     // inverse mode 2: where outliers are recorded
@@ -210,6 +211,7 @@ __device__ __forceinline__ void quant_store(unsigned* mag, int8_t* pleaf, uint32
 // what a forward kernel needs for it (after `ch` and `a`)
 #define FWD_QUANT_SETUP                                                                          \
   const bool quant = a.quant != 0;                                                               \
+  const bool wcoef = a.quant != 2;                                                               \
   const double qinv = quant ? __ddiv_rn(1.0, a.q) : 0.0;                                         \
   unsigned* const qmag = reinterpret_cast<unsigned*>(ch.mag);                                    \
   int8_t* const qleaf = ch.pleaf;                                                                \
@@ -227,14 +229,18 @@ __device__ __forceinline__ void quant_store(unsigned* mag, int8_t* pleaf, uint32
     const unsigned io = unsigned(az + kk) * cnxy32 + dpos[c];                                    \
     if (emit && lv) {                                                                            \
       /* (the approximation band of a level that is not the last one is transformed again: its   \
-         values do not count towards the largest coefficient) */                                 \
-      (apx ? abox : coef)[ie] = e2;                                                              \
-      if (!apx || last_level) {                                                                  \
+         values do not count towards the largest coefficient; a final value is not stored as a   \
+         double when nobody will read it: quant == 2) */                                         \
+      const bool final_e = !apx || last_level;                                                   \
+      if (!final_e || wcoef)                                                                     \
+        (apx ? abox : coef)[ie] = e2;                                                            \
+      if (final_e) {                                                                             \
         const unsigned long long b = abs_bits(e2);                                               \
         vmax = b > vmax ? b : vmax;                                                              \
       }                                                                                          \
       if (kk < nhigh) {                                                                          \
-        coef[io] = o3;                                                                           \
+        if (wcoef)                                                                               \
+          coef[io] = o3;                                                                         \
         const unsigned long long b = abs_bits(o3);                                               \
         vmax = b > vmax ? b : vmax;                                                              \
       }                                                                                          \
@@ -1060,7 +1066,8 @@ static void fused_attrs()
 // Forward transform of dyadic chunks straight from the source volume: coef receives the final
 // coefficients, ChunkDev::max_bits the largest magnitude.
 void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const int* d_ids, int nids,
-                              uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st, double quant_q)
+                              uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st, double quant_q,
+                              bool keep_coef)
 {
   fused_attrs();
   const int L = can_use_dyadic(nx, ny, nz);
@@ -1071,7 +1078,7 @@ void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const
   a.ids = d_ids;
   a.vol = src;
   a.k = cdf_constants();
-  a.quant = quant_q > 0.0 ? 1 : 0;   // (the caller has zeroed the sign words)
+  a.quant = quant_q > 0.0 ? (keep_coef ? 1 : 2) : 0;   // (the caller has zeroed the sign words)
   a.q = quant_q;
   for (int l = 0; l < L; l++) {
     a.lx = int(calc_approx_detail_len(nx, l)[0]);

@@ -242,9 +242,13 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   // what it writes (dwt_fused.cu, quant_store) and k_quantize's pass over the coefficients is not
   // needed -- unless a magnitude does not fit 32 bits, which k_qdecide finds from the maximum as
   // before; then k_quantize runs after all.
-  const double fused_q = (mode == kModePWE && !any_unfused && !std::getenv("SPERR_B200_NO_FUSED_QUANT"))
-                             ? quality * 1.5
-                             : 0.0;
+  double fused_q = (mode == kModePWE && !any_unfused && !std::getenv("SPERR_B200_NO_FUSED_QUANT"))
+                       ? quality * 1.5
+                       : 0.0;
+  // ... and when the outlier scan will de-quantise on the fly as well (k_inv3d<.., DEQ>, below) nobody
+  // reads the fp64 coefficients: they are not stored (the one exception, magnitudes that need 64 bits,
+  // transforms again).
+  bool keep_coef = !(fused_q > 0.0 && !std::getenv("SPERR_B200_NO_FUSED_DEQ") && !std::getenv("SPERR_B200_KEEP_COEF"));
   if (fused_q > 0.0)
     rt::dset(b_.signs.p, 0, b_.sign_words * 4, st);
   // dyadic shapes: fused kernels (dwt_fused.cu) that read the volume themselves and track the
@@ -262,7 +266,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
       if (!fused_groups)
         launch_dwt(inverse, b_.dev(), ids, n, h.nx, h.ny, h.nz, is_2d, st);
       else if (!inverse)
-        launch_dwt_fused_forward(src, b_.dev(), ids, n, h.nx, h.ny, h.nz, st, fused_q);
+        launch_dwt_fused_forward(src, b_.dev(), ids, n, h.nx, h.ny, h.nz, st, fused_q, keep_coef);
       else   // PWE: rebuild the values, compare with the source, record the outliers
         launch_dwt_fused_inverse(src, 2, b_.dev(), ids, n, h.nx, h.ny, h.nz, quality, sink,
                                  CorrectorList{nullptr, nullptr, nullptr}, st, inverse_deq);
@@ -289,7 +293,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
           continue;
         const ShapeHeader& h = b_.shapes[si].h;
         launch_dwt_fused_forward(src, b_.dev(), ids_.as<int>() + goff[si] + (lo - groups[si].begin()),
-                                 int(hi - lo), h.nx, h.ny, h.nz, st, fused_q);
+                                 int(hi - lo), h.nx, h.ny, h.nz, st, fused_q, keep_coef);
       }
     }
   }
@@ -381,6 +385,18 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
         throw std::runtime_error("FE_INVALID while quantising");
       any_wide |= (!d.is_const && d.wide);
     }
+    if (any_wide && fused_q > 0.0) {
+      // a magnitude does not fit 32 bits: what the forward transform quantised is of no use
+      if (std::getenv("SPERR_B200_VERBOSE"))
+        std::fprintf(stderr, "sperr_b200: 64-bit magnitudes, quantising after the transform%s\n",
+                     keep_coef ? "" : " (transforming again: the coefficients were not stored)");
+      if (!keep_coef) {   // ... and the coefficients were not stored: transform again, this time for real
+        fused_q = 0.0;
+        keep_coef = true;
+        transform(false, true, OutlierSink{}, st);
+      }
+      fused_q = 0.0;
+    }
     if (any_wide && !b_.wide) {
       b_.make_wide(st);
       b_.push(st);
@@ -395,7 +411,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
     // Every chunk on the fused path and 32-bit magnitudes: the inverse transform rebuilds the
     // coefficients from magnitude, sign and step where it loads them (k_inv3d<.., DEQ>), and
     // k_inv_quantize's round trip over HBM (4 + 8 B per value) is not needed.
-    inverse_deq = mode == kModePWE && !any_unfused && !any_wide && !b_.wide && !std::getenv("SPERR_B200_NO_FUSED_DEQ");
+    inverse_deq = mode == kModePWE && !any_unfused && !any_wide && !std::getenv("SPERR_B200_NO_FUSED_DEQ");
     auto outlier_chain = [&](cudaStream_t s) {
       if (!inverse_deq) {
         rt::ProfScope ps("c.inv_quantize", s);

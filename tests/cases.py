@@ -42,6 +42,10 @@ SYN_SMALL = [
     ((100, 88, 40), (50, 44, 40), 3, 2e-3),     # the same with four chunks
     # + N(0, sigma) noise (5th field): many outliers, the 1D stream's walker and its one-step
     # single-path descents (speck_dec_fast.cuh, f_walk1d) get real work
+    # PWE with magnitudes that need 64 bits: what the forward transform quantised on the fly is
+    # discarded, the chunks are transformed again and quantised by k_quantize (pipeline.cu)
+    ((32, 32, 32), (32, 32, 32), 3, 1e-10),
+    ((64, 32, 32), (32, 32, 32), 3, 2e-10),
     ((64, 64, 64), (64, 64, 64), 3, 1e-3, 3e-4),
     ((64, 64, 64), (32, 32, 32), 3, 1e-3, 1e-3),
 ]
