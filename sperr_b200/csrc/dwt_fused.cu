@@ -146,9 +146,6 @@ struct FusedArgs {
   long long out_off;    // inverse, mode 0: the rebuilt box goes compact to scratch + out_off, or -1: coef
   int tiles_x, tiles_y, zsegs;
   int last;             // forward: this is the coarsest level (its approx band is final)
-  int quant;            // forward: 1: also write magnitude / msb / sign of every final value (see quant_store);
-                        // 2: write ONLY those (the fp64 coefficients are not stored: nobody reads them)
-  double q;             // ... with this quantisation step
   double tol;           // inverse mode 2
   OutlierSink sink;     // inverse mode 2: where outliers are recorded
   CorrectorList cor;    // inverse mode 1: outlier correctors to add before the mean (may be empty)
@@ -168,89 +165,6 @@ __device__ __forceinline__ unsigned long long abs_bits(double v)
 {
   return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
 }
-
-// ---- quantisation inside the forward transform (FusedArgs::quant) ------------------------------
-// With a step q that does not depend on the coefficients (PWE mode: 1.5 x tolerance) the values a
-// level writes for good -- its detail bands, and the approximation band of the last level -- can be
-// quantised where they are produced: magnitude, msb position and sign bit of k_quantize
-// (transform.cu; src/SPECK_FLT.cpp:318-357) without reading the coefficients back. Same arithmetic:
-// llrint(v * (1 / q)). A warp's lanes of equal parity hold 16 consecutive coefficients, so a warp
-// contributes two 16-bit runs of sign bits per output row (the sign words are shared between tiles:
-// atomicOr into the zeroed array). All 32 lanes call it; `on`: this lane's value is stored.
-__device__ __forceinline__ unsigned even_bits(unsigned x)   // bits 0, 2, 4 .. 30 -> bits 0 .. 15
-{
-  x &= 0x55555555u;
-  x = (x | (x >> 1)) & 0x33333333u;
-  x = (x | (x >> 2)) & 0x0f0f0f0fu;
-  x = (x | (x >> 4)) & 0x00ff00ffu;
-  x = (x | (x >> 8)) & 0x0000ffffu;
-  return x;
-}
-__device__ __forceinline__ void quant_store(unsigned* mag, int8_t* pleaf, uint32_t* signs, unsigned idx, double v,
-                                            double qinv, bool on, int lane)
-{
-  const long long ll = on ? __double2ll_rn(__dmul_rn(v, qinv)) : -1ll;
-  const unsigned long long m = (unsigned long long)(ll < 0 ? -ll : ll);
-  const unsigned sb = __ballot_sync(0xffffffffu, on && ll >= 0);
-  if (on) {
-    mag[idx] = unsigned(m);
-    pleaf[idx] = int8_t(63 - __clzll((long long)m));
-  }
-  const unsigned i0 = __shfl_sync(0xffffffffu, idx, 0), i1 = __shfl_sync(0xffffffffu, idx, 1);
-  if (lane < 2) {
-    const unsigned bits = even_bits(lane == 0 ? sb : sb >> 1);
-    if (bits) {
-      const unsigned i = lane == 0 ? i0 : i1;
-      const unsigned long long w = (unsigned long long)bits << (i & 31u);
-      atomicOr(&signs[i >> 5], unsigned(w));
-      if (w >> 32)
-        atomicOr(&signs[(i >> 5) + 1], unsigned(w >> 32));
-    }
-  }
-}
-// what a forward kernel needs for it (after `ch` and `a`)
-#define FWD_QUANT_SETUP                                                                          \
-  const bool quant = a.quant != 0;                                                               \
-  const bool wcoef = a.quant != 2;                                                               \
-  const double qinv = quant ? __ddiv_rn(1.0, a.q) : 0.0;                                         \
-  unsigned* const qmag = reinterpret_cast<unsigned*>(ch.mag);                                    \
-  int8_t* const qleaf = ch.pleaf;                                                                \
-  uint32_t* const qsigns = ch.signs;                                                             \
-  if (quant) {                                                                                   \
-    ASSUME_GLOBAL(qmag);                                                                         \
-    ASSUME_GLOBAL(qleaf);                                                                        \
-    ASSUME_GLOBAL(qsigns);                                                                       \
-  }
-// one column's outputs of a step: e2 = pair kk of the low band, o3 = pair kk of the high band
-#define FWD_EMIT                                                                                 \
-  {                                                                                              \
-    const bool lv = (live >> c) & 1u, apx = (isapx >> c) & 1u;                                   \
-    const unsigned ie = unsigned(kk) * (apx ? aplane32 : cnxy32) + (apx ? apos[c] : dpos[c]);    \
-    const unsigned io = unsigned(az + kk) * cnxy32 + dpos[c];                                    \
-    if (emit && lv) {                                                                            \
-      /* (the approximation band of a level that is not the last one is transformed again: its   \
-         values do not count towards the largest coefficient; a final value is not stored as a   \
-         double when nobody will read it: quant == 2) */                                         \
-      const bool final_e = !apx || last_level;                                                   \
-      if (!final_e || wcoef)                                                                     \
-        (apx ? abox : coef)[ie] = e2;                                                            \
-      if (final_e) {                                                                             \
-        const unsigned long long b = abs_bits(e2);                                               \
-        vmax = b > vmax ? b : vmax;                                                              \
-      }                                                                                          \
-      if (kk < nhigh) {                                                                          \
-        if (wcoef)                                                                               \
-          coef[io] = o3;                                                                         \
-        const unsigned long long b = abs_bits(o3);                                               \
-        vmax = b > vmax ? b : vmax;                                                              \
-      }                                                                                          \
-    }                                                                                            \
-    if (quant && emit) { /* warp-uniform */                                                      \
-      quant_store(qmag, qleaf, qsigns, ie, e2, qinv, lv && (!apx || last_level), lane);          \
-      if (kk < nhigh)                                                                            \
-        quant_store(qmag, qleaf, qsigns, io, o3, qinv, lv, lane);                                \
-    }                                                                                            \
-  }
 
 // SRC 0: float volume, 1: double volume (both minus the chunk mean), 2: compact fp64 box in scratch
 template <int SRC, bool FMA>
@@ -307,31 +221,23 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
   const int x = X0 + lane;
   const int xo = (x >> 1) + ((x & 1) ? ax : 0);
   FwdState st[4];
-  unsigned dpos[4];    // offset of the column inside a z plane of coef (a chunk holds < 2^31 values)
-  unsigned apos[4];    // approx columns (x, y even): offset inside a z plane of the approx box
-  unsigned live = 0, isapx = 0;   // bit c: column c is inside the box / is an approx column
+  size_t dpos[4];      // offset of the column inside a z plane of coef (de-interleaved position)
+  long long apos[4];   // approx columns (x, y even): offset inside a z plane of the approx box; else -1
+  bool live[4];
   for (int c = 0; c < 4; c++) {
     st[c] = FwdState{0.0, 0.0, 0.0, 0.0, 0.0};
     const int y = Y0 + warp + 8 * c;
-    if (x < lx && y < ly)
-      live |= 1u << c;
-    dpos[c] = unsigned((size_t)((y >> 1) + ((y & 1) ? ay : 0)) * cnx + xo);
-    apos[c] = dpos[c];
-    if (!((x | y) & 1)) {
-      isapx |= 1u << c;
-      if (a.apx_off >= 0)
-        apos[c] = unsigned((y >> 1) * ax + (x >> 1));
-    }
+    live[c] = x < lx && y < ly;
+    dpos[c] = (size_t)((y >> 1) + ((y & 1) ? ay : 0)) * cnx + xo;
+    apos[c] = ((x | y) & 1) ? -1ll
+                            : (a.apx_off >= 0 ? (long long)(y >> 1) * ax + (x >> 1) : (long long)dpos[c]);
   }
   double* const abox = a.apx_off >= 0 ? ch.scratch + a.apx_off : coef;
   ASSUME_GLOBAL(coef);
   ASSUME_GLOBAL(abox);
   if (SRC == 2)   // (the hint is only given for pointers that are dereferenced: never for a null one)
     ASSUME_GLOBAL(sbox);
-  const unsigned cnxy32 = unsigned(cnxy), aplane32 = a.apx_off >= 0 ? unsigned(ax * ay) : cnxy32;
-  const bool last_level = a.last != 0;
-  const int nhigh = lz / 2;   // pairs that have a high-band sample
-  FWD_QUANT_SETUP
+  const size_t aplane = a.apx_off >= 0 ? (size_t)ax * ay : cnxy;
   unsigned long long vmax = 0;
 
   for (int j0 = k0 - 2; j0 <= k1 + 1; j0 += kNPB) {
@@ -387,7 +293,25 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d(FusedArgs a)
         const int ry = warp + 8 * c;
         double e2, o3;
         fwd_step<FMA>(k, st[c], te[ry * kFP], to[ry * kFP], e2, o3);
-        FWD_EMIT
+        if (emit && live[c]) {
+          if (apos[c] >= 0) {   // approx band of this level (plane kk of the low band)
+            abox[(size_t)kk * aplane + apos[c]] = e2;
+            if (a.last) {
+              const unsigned long long b = abs_bits(e2);
+              vmax = b > vmax ? b : vmax;
+            }
+          }
+          else {
+            coef[(size_t)kk * cnxy + dpos[c]] = e2;
+            const unsigned long long b = abs_bits(e2);
+            vmax = b > vmax ? b : vmax;
+          }
+          if (kk < lz / 2) {   // odd z output (plane az + kk)
+            coef[(size_t)(az + kk) * cnxy + dpos[c]] = o3;
+            const unsigned long long b = abs_bits(o3);
+            vmax = b > vmax ? b : vmax;
+          }
+        }
       }
     }
     __syncthreads();
@@ -559,7 +483,6 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d_tma(FusedArgs a, const _
   const unsigned cnxy32 = unsigned(cnxy), aplane32 = a.apx_off >= 0 ? unsigned(ax * ay) : cnxy32;
   const bool last_level = a.last != 0;
   const int nhigh = lz / 2;   // pairs that have a high-band sample
-  FWD_QUANT_SETUP
   unsigned long long vmax = 0;
 
   for (int t = 0; t < nsteps; t++) {
@@ -600,7 +523,24 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fwd3d_tma(FusedArgs a, const _
         const int ry = warp + 8 * c;
         double e2, o3;
         fwd_step<FMA>(k, st[c], te[ry * kFP], to[ry * kFP], e2, o3);
-        FWD_EMIT
+        if (emit && ((live >> c) & 1u)) {
+          // (the approximation band of a level that is not the last one is transformed again: its
+          // values do not count towards the largest coefficient)
+          const bool apx = (isapx >> c) & 1u;
+          if (apx)
+            abox[unsigned(kk) * aplane32 + apos[c]] = e2;
+          else
+            coef[unsigned(kk) * cnxy32 + dpos[c]] = e2;
+          if (!apx || last_level) {
+            const unsigned long long b = abs_bits(e2);
+            vmax = b > vmax ? b : vmax;
+          }
+          if (kk < nhigh) {
+            coef[unsigned(az + kk) * cnxy32 + dpos[c]] = o3;
+            const unsigned long long b = abs_bits(o3);
+            vmax = b > vmax ? b : vmax;
+          }
+        }
       }
     }
     __syncthreads();
@@ -648,11 +588,7 @@ constexpr int kIQuads = kFNP * kFNP;   // 400
 static_assert(kIQuads <= kIThreads && kPlanes * kFI <= kIThreads && 2 * kPlanes <= kIThreads / 32, "roles");
 constexpr int kIRows = 16;             // rows of a plane an epilogue warp owns
 
-// DEQ (compress side, PWE mode): the coefficients are not read from `coef` but rebuilt from the
-// quantised magnitudes and sign bits on the fly -- what k_inv_quantize (transform.cu) would have
-// written there: (q * m) * (+-1), src/SPECK_FLT.cpp:359-399 -- so that pass and its 16 B per value of
-// HBM traffic are not needed. 32-bit magnitudes only (the caller checks).
-template <int OUT, bool FMA, bool F32, bool DEQ>
+template <int OUT, bool FMA, bool F32>
 __global__ void __launch_bounds__(kIThreads, 2) k_inv3d(FusedArgs a)
 {
   DYN_SMEM(double, tile);   // [kPlanes][kFI][kFP]
@@ -681,21 +617,6 @@ __global__ void __launch_bounds__(kIThreads, 2) k_inv3d(FusedArgs a)
   ASSUME_GLOBAL(coef);
   ASSUME_GLOBAL(abox);
   const unsigned cnxy32 = unsigned(cnxy), aplane32 = a.apx_off >= 0 ? unsigned(ax * ay) : cnxy32;
-  const unsigned* const qmag = reinterpret_cast<const unsigned*>(ch.mag);
-  const uint32_t* const qsigns = ch.signs;
-  const double qstep = ch.q;
-  if (DEQ) {
-    ASSUME_GLOBAL(qmag);
-    ASSUME_GLOBAL(qsigns);
-  }
-  auto coef_at = [&](unsigned idx) -> double {
-    if (!DEQ)
-      return coef[idx];
-    const double m = __uint2double_rn(qmag[idx]);
-    const bool pos = (qsigns[idx >> 5] >> (idx & 31u)) & 1u;
-    return __dmul_rn(__dmul_rn(qstep, m), pos ? 1.0 : -1.0);
-  };
-  const bool apx_in_coef = a.apx_off < 0;   // the coarsest level: its approximation band is in coef too
 
   // ---- z phase: my quad. Slot s = 2 py + px is the column (2i + py, 2j + px) of the tile; the tile
   // starts at an even sample and mirroring keeps parity, so slot s is always of parity class
@@ -794,13 +715,13 @@ __global__ void __launch_bounds__(kIThreads, 2) k_inv3d(FusedArgs a)
         const unsigned ze = unsigned(mirror(2 * j, lz) >> 1), zo = unsigned(az + (mirror(2 * j + 1, lz) >> 1));
         const unsigned ie = ze * cnxy32, io = zo * cnxy32, ia = ze * aplane32;
         double ev[4], ov[4];
-        ev[0] = (DEQ && apx_in_coef) ? coef_at(ia + eoff0) : abox[ia + eoff0];
+        ev[0] = abox[ia + eoff0];
 #pragma unroll
         for (int s = 1; s < 4; s++)
-          ev[s] = coef_at(ie + coff[s]);
+          ev[s] = coef[ie + coff[s]];
 #pragma unroll
         for (int s = 0; s < 4; s++)
-          ov[s] = coef_at(io + coff[s]);
+          ov[s] = coef[io + coff[s]];
         double* const t0 = zt + (size_t)(2 * q) * kFI * kFP;
 #pragma unroll
         for (int s = 0; s < 4; s++) {
@@ -1042,18 +963,15 @@ static void fused_attrs()
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   const int smi = int(kInvSmem);
-#define SPERR_INV_ATTR(O, D) \
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, false, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi)); \
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, true, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, false, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, true, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
-  SPERR_INV_ATTR(1, false)
-  SPERR_INV_ATTR(2, false)
-  SPERR_INV_ATTR(2, true)
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<0, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+#define SPERR_INV_ATTR(O) \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi)); \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));  \
+  RT_CHECK(cudaFuncSetAttribute(k_inv3d<O, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smi));
+  SPERR_INV_ATTR(1)
+  SPERR_INV_ATTR(2)
 #undef SPERR_INV_ATTR
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
   RT_CHECK(cudaFuncSetAttribute(k_fwd3d<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
@@ -1066,8 +984,7 @@ static void fused_attrs()
 // Forward transform of dyadic chunks straight from the source volume: coef receives the final
 // coefficients, ChunkDev::max_bits the largest magnitude.
 void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const int* d_ids, int nids,
-                              uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st, double quant_q,
-                              bool keep_coef)
+                              uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st)
 {
   fused_attrs();
   const int L = can_use_dyadic(nx, ny, nz);
@@ -1078,8 +995,6 @@ void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const
   a.ids = d_ids;
   a.vol = src;
   a.k = cdf_constants();
-  a.quant = quant_q > 0.0 ? (keep_coef ? 1 : 2) : 0;   // (the caller has zeroed the sign words)
-  a.q = quant_q;
   for (int l = 0; l < L; l++) {
     a.lx = int(calc_approx_detail_len(nx, l)[0]);
     a.ly = int(calc_approx_detail_len(ny, l)[0]);
@@ -1123,7 +1038,7 @@ void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const
 // `sink` (unordered).
 void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chunks, const int* d_ids,
                               int nids, uint32_t nx, uint32_t ny, uint32_t nz, double tol,
-                              const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st, bool deq)
+                              const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st)
 {
   fused_attrs();
   const int L = can_use_dyadic(nx, ny, nz);
@@ -1160,23 +1075,23 @@ void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chu
         grid = dim3(unsigned(a.tiles_x * a.tiles_y * zs), unsigned(nids));
       }
     }
-#define SPERR_INV(O, F, T, D) LAUNCH((k_inv3d<O, F, T, D>), grid, dim3(kIThreads), kInvSmem, st, a)
-#define SPERR_INV_T(O, F, D)        \
-  do {                              \
-    if (vol.is_float)               \
-      SPERR_INV(O, F, true, D);     \
-    else                            \
-      SPERR_INV(O, F, false, D);    \
+#define SPERR_INV(O, F, T) LAUNCH((k_inv3d<O, F, T>), grid, dim3(kIThreads), kInvSmem, st, a)
+#define SPERR_INV_T(O, F)        \
+  do {                           \
+    if (vol.is_float)            \
+      SPERR_INV(O, F, true);     \
+    else                         \
+      SPERR_INV(O, F, false);    \
   } while (0)
     if (a.k.fma) {
-      if (which == 0) { if (deq) SPERR_INV(0, true, false, true); else SPERR_INV(0, true, false, false); }
-      else if (which == 1) SPERR_INV_T(1, true, false);
-      else { if (deq) SPERR_INV_T(2, true, true); else SPERR_INV_T(2, true, false); }
+      if (which == 0) SPERR_INV(0, true, false);
+      else if (which == 1) SPERR_INV_T(1, true);
+      else SPERR_INV_T(2, true);
     }
     else {
-      if (which == 0) { if (deq) SPERR_INV(0, false, false, true); else SPERR_INV(0, false, false, false); }
-      else if (which == 1) SPERR_INV_T(1, false, false);
-      else { if (deq) SPERR_INV_T(2, false, true); else SPERR_INV_T(2, false, false); }
+      if (which == 0) SPERR_INV(0, false, false);
+      else if (which == 1) SPERR_INV_T(1, false);
+      else SPERR_INV_T(2, false);
     }
 #undef SPERR_INV_T
 #undef SPERR_INV

@@ -102,15 +102,11 @@ __device__ __forceinline__ double corrector_lookup(const CorrectorList& l, unsig
 
 // ---- dwt_fused.cu: one HBM round trip per level, dyadic chunks only ----
 size_t fused_scratch_elems(uint32_t nx, uint32_t ny, uint32_t nz, long long off[8]);
-// quant_q > 0: the kernels also quantise every final coefficient with that step (magnitude, msb
-// position, sign bit: what k_quantize would write; the caller zeroes the sign words first)
 void launch_dwt_fused_forward(const SrcVol& src, const ChunkDev* d_chunks, const int* d_ids, int nids,
-                              uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st, double quant_q = 0.0,
-                              bool keep_coef = true);   // false (with quant_q): the fp64 coefficients are not stored
+                              uint32_t nx, uint32_t ny, uint32_t nz, cudaStream_t st);
 void launch_dwt_fused_inverse(const SrcVol& vol, int mode, const ChunkDev* d_chunks, const int* d_ids,
                               int nids, uint32_t nx, uint32_t ny, uint32_t nz, double tol,
-                              const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st,
-                              bool deq = false);   // deq: coefficients rebuilt from mag / signs / q on the fly
+                              const OutlierSink& sink, const CorrectorList& cor, cudaStream_t st);
 void launch_level_gather(const ChunkDev* d_chunks, int nchunks, uint32_t nx, uint32_t ny, uint32_t nz,
                          int h, void* dst, int is_float, size_t vx, size_t vy, cudaStream_t st);
 CdfC cdf_constants();

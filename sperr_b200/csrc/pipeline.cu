@@ -237,24 +237,9 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
   ids_.reserve(flat.size() * 4 + 4);
   rt::h2d(ids_.p, flat.data(), flat.size() * 4, st);
   rt::sync(st);
-  // PWE mode, every chunk on the fused path: the quantisation step (1.5 x tolerance,
-  // src/SPECK_FLT.cpp:439) does not depend on the coefficients, so the forward transform quantises
-  // what it writes (dwt_fused.cu, quant_store) and k_quantize's pass over the coefficients is not
-  // needed -- unless a magnitude does not fit 32 bits, which k_qdecide finds from the maximum as
-  // before; then k_quantize runs after all.
-  double fused_q = (mode == kModePWE && !any_unfused && !std::getenv("SPERR_B200_NO_FUSED_QUANT"))
-                       ? quality * 1.5
-                       : 0.0;
-  // ... and when the outlier scan will de-quantise on the fly as well (k_inv3d<.., DEQ>, below) nobody
-  // reads the fp64 coefficients: they are not stored (the one exception, magnitudes that need 64 bits,
-  // transforms again).
-  bool keep_coef = !(fused_q > 0.0 && !std::getenv("SPERR_B200_NO_FUSED_DEQ") && !std::getenv("SPERR_B200_KEEP_COEF"));
-  if (fused_q > 0.0)
-    rt::dset(b_.signs.p, 0, b_.sign_words * 4, st);
   // dyadic shapes: fused kernels (dwt_fused.cu) that read the volume themselves and track the
   // coefficient maximum; everything else: gather, per-axis passes in place, separate maximum
   auto group_fused = [&](size_t s) { return b_.h[groups[s][0]].fused != 0; };
-  bool inverse_deq = false;   // PWE: the inverse transform de-quantises on the fly (set before the outlier chain)
   auto transform = [&](bool inverse, bool fused_groups, const OutlierSink& sink, cudaStream_t st) {
     rt::ProfScope ps(inverse ? "c.idwt" : "c.dwt", st);
     for (size_t s = 0; s < groups.size(); s++) {
@@ -266,10 +251,10 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
       if (!fused_groups)
         launch_dwt(inverse, b_.dev(), ids, n, h.nx, h.ny, h.nz, is_2d, st);
       else if (!inverse)
-        launch_dwt_fused_forward(src, b_.dev(), ids, n, h.nx, h.ny, h.nz, st, fused_q, keep_coef);
+        launch_dwt_fused_forward(src, b_.dev(), ids, n, h.nx, h.ny, h.nz, st);
       else   // PWE: rebuild the values, compare with the source, record the outliers
         launch_dwt_fused_inverse(src, 2, b_.dev(), ids, n, h.nx, h.ny, h.nz, quality, sink,
-                                 CorrectorList{nullptr, nullptr, nullptr}, st, inverse_deq);
+                                 CorrectorList{nullptr, nullptr, nullptr}, st);
     }
   };
   if (by_groups) {
@@ -293,7 +278,7 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
           continue;
         const ShapeHeader& h = b_.shapes[si].h;
         launch_dwt_fused_forward(src, b_.dev(), ids_.as<int>() + goff[si] + (lo - groups[si].begin()),
-                                 int(hi - lo), h.nx, h.ny, h.nz, st, fused_q, keep_coef);
+                                 int(hi - lo), h.nx, h.ny, h.nz, st);
       }
     }
   }
@@ -385,35 +370,19 @@ void Compressor::run_batch(const SrcVol& src, const std::vector<Chunk>& chunks, 
         throw std::runtime_error("FE_INVALID while quantising");
       any_wide |= (!d.is_const && d.wide);
     }
-    if (any_wide && fused_q > 0.0) {
-      // a magnitude does not fit 32 bits: what the forward transform quantised is of no use
-      if (std::getenv("SPERR_B200_VERBOSE"))
-        std::fprintf(stderr, "sperr_b200: 64-bit magnitudes, quantising after the transform%s\n",
-                     keep_coef ? "" : " (transforming again: the coefficients were not stored)");
-      if (!keep_coef) {   // ... and the coefficients were not stored: transform again, this time for real
-        fused_q = 0.0;
-        keep_coef = true;
-        transform(false, true, OutlierSink{}, st);
-      }
-      fused_q = 0.0;
-    }
     if (any_wide && !b_.wide) {
       b_.make_wide(st);
       b_.push(st);
     }
-    if (!(fused_q > 0.0 && mode == kModePWE && !any_wide)) {
+    {
       rt::ProfScope ps("c.quantize", st);
       launch_quantize(b_.dev(), nc, b_.max_n, st);
     }
     // PWE: the outlier path (de-quantise, inverse transform, compare with the source, SPECK1D-code
     // the differences) only needs the quantised integers, like the SPECK3D encoder, and both are
     // chains of small launches with host round trips: run them side by side on two streams.
-    // Every chunk on the fused path and 32-bit magnitudes: the inverse transform rebuilds the
-    // coefficients from magnitude, sign and step where it loads them (k_inv3d<.., DEQ>), and
-    // k_inv_quantize's round trip over HBM (4 + 8 B per value) is not needed.
-    inverse_deq = mode == kModePWE && !any_unfused && !any_wide && !std::getenv("SPERR_B200_NO_FUSED_DEQ");
     auto outlier_chain = [&](cudaStream_t s) {
-      if (!inverse_deq) {
+      {
         rt::ProfScope ps("c.inv_quantize", s);
         launch_inv_quantize(b_.dev(), nc, b_.max_n, s);
       }
