@@ -89,3 +89,23 @@ def test_bench_two_ranks_dry_run():
     assert "32x32x32" in d["config"]["workload"]           # the SAME volume at every N
     assert d["parity"]["n_gpus"] == 2 and len(d["parity"]["container_sha256_16"]) == 16
     assert d["extra"]["weak"]["scaling"] == "weak" and "32x32x64" in d["extra"]["weak"]["config"]["workload"]
+
+
+def test_bench_helpers_without_gpu():
+    """the pieces of bench.py that talk to the OS: host counters (deltas go into the bench line) and
+    the clock sampler switched off (--diag noclocks): no thread, no NVML, an empty summary"""
+    import importlib
+    import sys as _sys
+    argv = _sys.argv
+    _sys.argv = ["bench.py"]
+    try:
+        bench = importlib.import_module("bench")
+    finally:
+        _sys.argv = argv
+    hc = bench.host_counters()
+    assert isinstance(hc, dict) and all(isinstance(v, int) for v in hc.values())
+    clk = bench.Clocks(0, idle=True)
+    clk.sample()
+    clk.mark()
+    s = clk.summary()
+    assert s["samples"] == 0 and s["sm_mhz"] is None and s["reasons"] == []
