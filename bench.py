@@ -738,10 +738,20 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=("strong", "weak"))
     ap.add_argument("--weak-extra", type=int, default=1, help="N > 1: also report the weak-scaled run as extra.weak")
     ap.add_argument("--check", type=int, default=1, help="rank 0 checks the container bytes after the timed loops")
+    ap.add_argument("--config", default="",
+                    help="comma list of 3, 4, 5, 2n: measure those BASELINE configurations instead (one GPU, one line each)")
     ap.add_argument("--settle", type=float, default=1.5,
                     help="warm up for at least this many seconds (extra untimed steps beyond --warmup)")
     ap.add_argument("--diag", default="", help="diagnosis of host-side stalls: comma list of noclocks, noprof")
     args = ap.parse_args()
+    if args.config:
+        # the other BASELINE configurations (3: 2048^3 f64 2 bpp, 4: 4096 x 4096 x 1024 f32 PSNR
+        # decompression, 5: 4096 slices of 2048^2, 2n: config 2 with a noise floor), each on the box one
+        # of eight GPUs holds, one JSON line per configuration: scripts/bench_configs.py
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_configs
+        bench_configs.main([c for c in args.config.split(",") if c] + ["--cpu", str(args.cpu_baseline)])
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -97,13 +97,13 @@ def cpu_sample(vol, dims_full, is_float, mode, q):
                              "sample": "%dx%dx%d leading box of the same field, all host threads" % sd}}, sd, stream
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=["3", "4", "5", "2n"])
     ap.add_argument("--share", type=int, default=8, help="measure the box one of SHARE GPUs gets (1: the whole volume)")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cpu", type=int, default=1)
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     L = sperr_b200.load()
     dev = torch.device("cuda", 0)
 
