@@ -37,3 +37,10 @@ def test_cluster_decode_emulated(lib, oracle, R, monkeypatch):
         rc, s = oracle.comp_3d(v, dims, dims, mode, q)
         assert rc == 0
         cases.check_decomp3d(lib, oracle, s, True)
+    # with a noise floor: a dense LIP for the cluster's split mask sweep, and an outlier tree with
+    # both single-path subtrees (taken in one step by the 1D walker) and crowded ones (bit by bit)
+    import numpy as np
+    vn = (v + 3e-4 * np.random.default_rng(11).standard_normal(v.shape)).astype(np.float32)
+    rc, s = oracle.comp_3d(vn, dims, dims, 3, 1e-3)
+    assert rc == 0
+    cases.check_decomp3d(lib, oracle, s, True)
